@@ -1,0 +1,306 @@
+"""wav2vec2-style acoustic encoder on the aptai_b200 kernels.
+
+`Wav2Vec2Backbone` is the drop-in for the `transformers.Wav2Vec2Model` instance the reference wraps
+(models/aptai.py:33-40, models/w2v2_pr.py:28-33): same constructor source (`from_pretrained(id, config=...,
+cache_dir=...)`), same `state_dict` keys/shapes (incl. the weight-norm parametrisation
+`encoder.pos_conv_embed.conv.parametrizations.weight.original0/1`), same call
+`forward(input_values, attention_mask=lengths[:, None], output_hidden_states=True, return_dict=True)`.
+The torch submodules below are parameter containers only — they are never called; the arithmetic runs in the
+sm_100a kernels through `aptai_b200.ops`:
+
+  conv0+norm+GELU (HBM-bound SIMT)  ->  conv1..6 implicit GEMM, LN/GELU epilogue (tcgen05)
+  -> LayerNorm -> projection GEMM (bias, padded frames zeroed) -> grouped pos-conv GEMM (+GELU +residual)
+  -> N x [LN -> QKV GEMM -> masked flash attention -> out-proj GEMM(+residual) -> LN -> FFN GEMM(+GELU)
+          -> FFN GEMM(+residual)]  (pre-LN 'stable' or post-LN wiring)  -> final LN
+
+Precision policy: bf16 GEMM/attention operands, fp32 accumulation, fp32 residual stream,
+LayerNorm statistics and softmax in fp32.
+Inference only in this round: the kernels have no backward, so `forward` runs under no_grad and refuses
+`self.training` with stochastic regularisers enabled.
+"""
+from __future__ import annotations
+
+import os
+from types import SimpleNamespace
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .config import W2V2Config
+
+BF16, F32, I32 = torch.bfloat16, torch.float32, torch.int32
+
+
+# ----------------------------------------------------------------------------------------- parameter containers
+class _ConvLayer(nn.Module):
+    def __init__(self, cin, cout, k, s, bias, with_ln):
+        super().__init__()
+        self.conv = nn.Conv1d(cin, cout, k, stride=s, bias=bias)
+        if with_ln:
+            self.layer_norm = nn.LayerNorm(cout)      # GroupNorm(512,512) has the same parameter names/shapes
+
+
+class _FeatureExtractor(nn.Module):
+    def __init__(self, cfg: W2V2Config):
+        super().__init__()
+        layers = []
+        cin = 1
+        for i, (c, k, s) in enumerate(zip(cfg.conv_dim, cfg.conv_kernel, cfg.conv_stride)):
+            layers.append(_ConvLayer(cin, c, k, s, cfg.conv_bias, cfg.feat_extract_norm == "layer" or i == 0))
+            cin = c
+        self.conv_layers = nn.ModuleList(layers)
+
+
+class _FeatureProjection(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.layer_norm = nn.LayerNorm(cfg.conv_dim[-1], eps=cfg.layer_norm_eps)
+        self.projection = nn.Linear(cfg.conv_dim[-1], cfg.hidden_size)
+
+
+class _PosConv(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        conv = nn.Conv1d(cfg.hidden_size, cfg.hidden_size, cfg.num_conv_pos_embeddings,
+                         padding=cfg.num_conv_pos_embeddings // 2, groups=cfg.num_conv_pos_embedding_groups)
+        self.conv = nn.utils.parametrizations.weight_norm(conv, name="weight", dim=2)
+
+
+class _Attention(nn.Module):
+    def __init__(self, H):
+        super().__init__()
+        self.k_proj = nn.Linear(H, H)
+        self.v_proj = nn.Linear(H, H)
+        self.q_proj = nn.Linear(H, H)
+        self.out_proj = nn.Linear(H, H)
+
+
+class _FeedForward(nn.Module):
+    def __init__(self, H, F):
+        super().__init__()
+        self.intermediate_dense = nn.Linear(H, F)
+        self.output_dense = nn.Linear(F, H)
+
+
+class _EncoderLayer(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.attention = _Attention(cfg.hidden_size)
+        self.layer_norm = nn.LayerNorm(cfg.hidden_size, eps=cfg.layer_norm_eps)
+        self.feed_forward = _FeedForward(cfg.hidden_size, cfg.intermediate_size)
+        self.final_layer_norm = nn.LayerNorm(cfg.hidden_size, eps=cfg.layer_norm_eps)
+
+
+class _Encoder(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.pos_conv_embed = _PosConv(cfg)
+        self.layer_norm = nn.LayerNorm(cfg.hidden_size, eps=cfg.layer_norm_eps)
+        self.layers = nn.ModuleList([_EncoderLayer(cfg) for _ in range(cfg.num_hidden_layers)])
+
+
+# ----------------------------------------------------------------------------------------- kernel-side weights
+class _Plan:
+    """Kernel-ready copies of the parameters (bf16 GEMM operands, fused QKV, tap-major conv weights, folded
+    weight-norm).  Rebuilt whenever a parameter changes (load_state_dict, optimizer step, .to())."""
+
+    def __init__(self, m: "Wav2Vec2Backbone"):
+        cfg = m.cfg
+        dev = m.masked_spec_embed.device
+        f = lambda t: t.detach().to(device=dev, dtype=F32).contiguous()
+        b = lambda t: t.detach().to(device=dev, dtype=BF16).contiguous()
+        cl = m.feature_extractor.conv_layers
+        self.conv0_w = f(cl[0].conv.weight.reshape(cfg.conv_dim[0], cfg.conv_kernel[0]))
+        self.conv_b = [f(l.conv.bias) if l.conv.bias is not None else None for l in cl]
+        self.conv_ln_w = [f(l.layer_norm.weight) if hasattr(l, "layer_norm") else None for l in cl]
+        self.conv_ln_b = [f(l.layer_norm.bias) if hasattr(l, "layer_norm") else None for l in cl]
+        # conv i >= 1: [out][in][k] -> [out][k][in]  (K index = tap*C_in + c)
+        self.conv_w = [None] + [b(l.conv.weight.permute(0, 2, 1).reshape(l.conv.weight.shape[0], -1)) for l in cl[1:]]
+        fp = m.feature_projection
+        self.fp_ln_w, self.fp_ln_b = f(fp.layer_norm.weight), f(fp.layer_norm.bias)
+        self.fp_w, self.fp_b = b(fp.projection.weight), f(fp.projection.bias)
+        pc = m.encoder.pos_conv_embed.conv
+        g = f(pc.parametrizations.weight.original0)
+        v = f(pc.parametrizations.weight.original1)
+        self.pos_w = ops.posconv_fold(g, v, cpad=64)
+        self.pos_b = f(pc.bias)
+        self.enc_ln_w, self.enc_ln_b = f(m.encoder.layer_norm.weight), f(m.encoder.layer_norm.bias)
+        scale = float(cfg.head_dim) ** -0.5     # folded into q (0.125 for head_dim 64: exact in bf16)
+        self.layers = []
+        for l in m.encoder.layers:
+            a = l.attention
+            qkv_w = torch.cat([a.q_proj.weight.detach().float() * scale, a.k_proj.weight.detach().float(),
+                               a.v_proj.weight.detach().float()], dim=0)
+            qkv_b = torch.cat([a.q_proj.bias.detach().float() * scale, a.k_proj.bias.detach().float(),
+                               a.v_proj.bias.detach().float()], dim=0)
+            self.layers.append(SimpleNamespace(
+                qkv_w=b(qkv_w), qkv_b=f(qkv_b), o_w=b(a.out_proj.weight), o_b=f(a.out_proj.bias),
+                ln1_w=f(l.layer_norm.weight), ln1_b=f(l.layer_norm.bias),
+                ff1_w=b(l.feed_forward.intermediate_dense.weight), ff1_b=f(l.feed_forward.intermediate_dense.bias),
+                ff2_w=b(l.feed_forward.output_dense.weight), ff2_b=f(l.feed_forward.output_dense.bias),
+                ln2_w=f(l.final_layer_norm.weight), ln2_b=f(l.final_layer_norm.bias)))
+
+
+class Wav2Vec2Backbone(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.config = config                       # whatever the caller passed (HF config object or ours)
+        self.cfg = W2V2Config.from_any(config)
+        self.cfg.validate_for_kernels()
+        cfg = self.cfg
+        self.masked_spec_embed = nn.Parameter(torch.empty(cfg.hidden_size).uniform_())
+        self.feature_extractor = _FeatureExtractor(cfg)
+        self.feature_projection = _FeatureProjection(cfg)
+        self.encoder = _Encoder(cfg)
+        self._plan: Optional[_Plan] = None
+        self._plan_key = None
+        self._feature_encoder_frozen = False
+
+    # ---- reference-facing helpers --------------------------------------------------------------------------
+    @classmethod
+    def from_pretrained(cls, model_id, config=None, cache_dir=None, **_):
+        """Local `save_pretrained` directory (model.safetensors / pytorch_model.bin).  There is no network in
+        this environment, so hub ids are refused with a clear error instead of a silent random init."""
+        if config is None:
+            raise ValueError("Wav2Vec2Backbone.from_pretrained needs config=")
+        m = cls(config)
+        path = str(model_id)
+        if os.path.isdir(path):
+            st = os.path.join(path, "model.safetensors")
+            pt = os.path.join(path, "pytorch_model.bin")
+            if os.path.exists(st):
+                from safetensors.torch import load_file
+                sd = load_file(st)
+            elif os.path.exists(pt):
+                sd = torch.load(pt, map_location="cpu")
+            else:
+                raise FileNotFoundError(f"no model.safetensors / pytorch_model.bin under {path}")
+            sd = {k[len("wav2vec2."):] if k.startswith("wav2vec2.") else k: v for k, v in sd.items()}
+            missing, unexpected = m.load_state_dict(sd, strict=False)
+            missing = [k for k in missing if k != "masked_spec_embed"]
+            if missing:
+                raise RuntimeError(f"checkpoint {path} is missing {missing[:5]}...")
+        else:
+            raise FileNotFoundError(
+                f"'{model_id}' is not a local directory; hub downloads are unavailable (no network). "
+                "Pass a directory written by save_pretrained().")
+        return m
+
+    def gradient_checkpointing_enable(self, *a, **k):    # models/aptai.py:38 — no autograd graph to checkpoint here
+        return None
+
+    def freeze_feature_encoder(self):                    # models/aptai.py:39-40
+        for p in self.feature_extractor.parameters():
+            p.requires_grad = False
+        self._feature_encoder_frozen = True
+
+    def _get_feat_extract_output_lengths(self, input_lengths):
+        """HF:1005-1024 on tensors or ints."""
+        n = input_lengths
+        for k, s in zip(self.cfg.conv_kernel, self.cfg.conv_stride):
+            n = torch.div(n - k, s, rounding_mode="floor") + 1 if torch.is_tensor(n) else (n - k) // s + 1
+        return n
+
+    # ---- plan ------------------------------------------------------------------------------------------------
+    def plan(self) -> _Plan:
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._plan is None or key != self._plan_key:
+            with torch.no_grad():
+                self._plan = _Plan(self)
+            self._plan_key = key
+        return self._plan
+
+    # ---- the hot path ----------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def encode(self, wav: torch.Tensor, frame_lens: torch.Tensor, *, collect_hidden: bool = False,
+               want_features: bool = False):
+        """wav fp32 [B,L] (CUDA), frame_lens int32 [B] (CUDA, valid frames per utterance).
+        Returns (last_hidden fp32 [B,T,H], hidden tuple | None, features bf16 [B,T,512] | None)."""
+        cfg, P = self.cfg, self.plan()
+        B, L = wav.shape
+        norm = 1 if cfg.feat_extract_norm == "layer" else 2
+        y = ops.conv0(wav, P.conv0_w, P.conv_b[0], P.conv_ln_w[0], P.conv_ln_b[0], norm)
+        for i in range(1, len(cfg.conv_kernel)):
+            y = _conv_layer(y, P, i, cfg)
+        T = y.shape[1]
+        M = B * T
+        H = cfg.hidden_size
+        feats = y
+        _, xn = ops.layernorm(y.view(M, -1), P.fp_ln_w, P.fp_ln_b, cfg.layer_norm_eps)
+        h, _ = ops.linear(xn, P.fp_w, P.fp_b, want_f32=True, want_bf16=False, seg_rows=T, seg_valid_rows=frame_lens)
+        taps = cfg.num_conv_pos_embeddings
+        hp = ops.cast_pad(h.view(B, T, H), taps // 2)
+        ops.posconv(hp, P.pos_w, P.pos_b, h, T, H, cfg.num_conv_pos_embedding_groups, taps, h)
+        hidden = [] if collect_hidden else None
+        eps = cfg.layer_norm_eps
+        heads = cfg.num_attention_heads
+        if not cfg.do_stable_layer_norm:
+            h, x = ops.layernorm(h, P.enc_ln_w, P.enc_ln_b, eps, want_f32=True, want_bf16=True)
+            for lw in P.layers:
+                if collect_hidden:
+                    hidden.append(h.view(B, T, H).clone())
+                _, qkv = ops.linear(x, lw.qkv_w, lw.qkv_b)
+                ctx = ops.attention(qkv, frame_lens, B, T, heads)
+                t32, _ = ops.linear(ctx, lw.o_w, lw.o_b, residual=h, want_f32=True, want_bf16=False)
+                h, x = ops.layernorm(t32, lw.ln1_w, lw.ln1_b, eps, want_f32=True, want_bf16=True)
+                _, u = ops.linear(x, lw.ff1_w, lw.ff1_b, act=1)
+                t32, _ = ops.linear(u, lw.ff2_w, lw.ff2_b, residual=h, want_f32=True, want_bf16=False)
+                h, x = ops.layernorm(t32, lw.ln2_w, lw.ln2_b, eps, want_f32=True, want_bf16=True)
+            last = h
+        else:
+            for lw in P.layers:
+                if collect_hidden:
+                    hidden.append(h.view(B, T, H).clone())
+                _, x = ops.layernorm(h, lw.ln1_w, lw.ln1_b, eps)
+                _, qkv = ops.linear(x, lw.qkv_w, lw.qkv_b)
+                ctx = ops.attention(qkv, frame_lens, B, T, heads)
+                ops.linear(ctx, lw.o_w, lw.o_b, residual=h, out_f32=h, want_bf16=False)
+                _, x = ops.layernorm(h, lw.ln2_w, lw.ln2_b, eps)
+                _, u = ops.linear(x, lw.ff1_w, lw.ff1_b, act=1)
+                ops.linear(u, lw.ff2_w, lw.ff2_b, residual=h, out_f32=h, want_bf16=False)
+            last, _ = ops.layernorm(h, P.enc_ln_w, P.enc_ln_b, eps, want_f32=True, want_bf16=False)
+        last = last.view(B, T, H)
+        if collect_hidden:
+            hidden.append(last)
+        return last, (tuple(hidden) if collect_hidden else None), (feats if want_features else None)
+
+    def forward(self, input_values, attention_mask=None, output_hidden_states=False, return_dict=True, **_):
+        """HF-compatible call.  `attention_mask` is what the reference passes: `lengths[:, None]`, a (B,1) tensor
+        of sample counts (models/aptai.py:77; the cumsum trick of HF:1031), or a (B,L) 0/1 mask, or None."""
+        if self.training and (self.cfg.apply_spec_augment or self.cfg.layerdrop > 0):
+            raise NotImplementedError("aptai_b200: the training-mode stochastic path (SpecAugment/LayerDrop/dropout)"
+                                      " and backward kernels are not built yet; call .eval()")
+        if not input_values.is_cuda:
+            raise RuntimeError("aptai_b200: input_values must be on a CUDA (sm_100) device; there is no CPU path")
+        wav = input_values.to(F32).contiguous()
+        B, L = wav.shape
+        if attention_mask is None:
+            lens = torch.full((B,), L, dtype=torch.int64, device=wav.device)
+        else:
+            am = attention_mask.reshape(B, -1)
+            lens = am.sum(-1) if am.shape[1] == L and L > 1 else am[:, -1]
+            lens = lens.to(device=wav.device, dtype=torch.int64)
+        flen = self._get_feat_extract_output_lengths(lens).to(I32).contiguous()
+        last, hidden, feats = self.encode(wav, flen, collect_hidden=output_hidden_states, want_features=True)
+        out = SimpleNamespace(last_hidden_state=last, extract_features=feats, hidden_states=hidden, attentions=None)
+        if not return_dict:
+            return tuple(v for v in (last, feats, hidden) if v is not None)
+        return _Output(out)
+
+
+class _Output(SimpleNamespace):
+    """BaseModelOutput-like: attribute access plus `outputs[0]` (models/w2v2_pr.py:53)."""
+
+    def __init__(self, ns):
+        super().__init__(**vars(ns))
+
+    def __getitem__(self, i):
+        return tuple(v for v in (self.last_hidden_state, self.extract_features, self.hidden_states) if v is not None)[i]
+
+
+def _conv_layer(y, P, i, cfg):
+    # y comes from ops.conv0 / ops.conv_igemm, whose buffers carry slack rows for the strided TMA view
+    return ops.conv_igemm(y, P.conv_w[i], P.conv_b[i], cfg.conv_kernel[i], cfg.conv_stride[i],
+                          ln_gamma=P.conv_ln_w[i], ln_beta=P.conv_ln_b[i], act=1)

@@ -1,0 +1,406 @@
+// HBM-bound row kernels of the encoder and the APTAI heads: LayerNorm, bf16 cast+halo pad, weight-norm fold,
+// the two small output heads + argmax, the 51-tap low-pass FIR, and the masked MSE / CE losses.
+#include "common.h"
+#include "ptx.cuh"
+
+#include <math.h>
+
+namespace aptai {
+
+// ---------------------------------------------------------------------------------------------- LayerNorm
+// One warp per row; the row lives in registers (NV float4 per lane), exact two-pass statistics in fp32.
+template <int NV, bool IN_BF16>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const void* __restrict__ xin, long long rows, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, float* __restrict__ out_f32,
+                 __nv_bfloat16* __restrict__ out_bf16) {
+  constexpr int COLS = NV * 128;
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float4 v[NV];
+  if (IN_BF16) {
+    const uint2* p = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(xin) + row * COLS);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const uint2 u = __ldg(p + i * 32 + lane);
+      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+      const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+      v[i] = make_float4(a.x, a.y, b.x, b.y);
+    }
+  } else {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(xin) + row * COLS);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = __ldg(p + i * 32 + lane);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.0f / COLS);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q * (1.0f / COLS) + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int col = (i * 32 + lane) * 4;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + col));
+    const float4 e = __ldg(reinterpret_cast<const float4*>(beta + col));
+    float4 y;
+    y.x = fmaf((v[i].x - mean) * rstd, g.x, e.x);
+    y.y = fmaf((v[i].y - mean) * rstd, g.y, e.y);
+    y.z = fmaf((v[i].z - mean) * rstd, g.z, e.z);
+    y.w = fmaf((v[i].w - mean) * rstd, g.w, e.w);
+    if (out_f32) reinterpret_cast<float4*>(out_f32 + row * COLS)[i * 32 + lane] = y;
+    if (out_bf16)
+      reinterpret_cast<uint2*>(out_bf16 + row * COLS)[i * 32 + lane] =
+          make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+  }
+}
+
+template <int NV>
+static void launch_ln(const void* x, int x_is_bf16, long long rows, const float* gamma, const float* beta, float eps,
+                      float* of, void* ob, cudaStream_t st) {
+  const int wpb = 8;
+  const unsigned grid = static_cast<unsigned>((rows + wpb - 1) / wpb);
+  if (x_is_bf16)
+    layernorm_kernel<NV, true><<<grid, wpb * 32, 0, st>>>(x, rows, gamma, beta, eps, of,
+                                                           reinterpret_cast<__nv_bfloat16*>(ob));
+  else
+    layernorm_kernel<NV, false><<<grid, wpb * 32, 0, st>>>(x, rows, gamma, beta, eps, of,
+                                                            reinterpret_cast<__nv_bfloat16*>(ob));
+}
+
+// ---------------------------------------------------------------------------------------------- cast + halo pad
+__global__ void cast_pad_kernel(const float* __restrict__ x, int rows, int cols4, int halo,
+                                __nv_bfloat16* __restrict__ out) {
+  // grid.y = segment; each thread moves 4 elements; halo rows are written as zeros
+  const int seg = blockIdx.y;
+  const long long prow = rows + 2 * halo;
+  const long long total = prow * cols4;
+  uint2* o = reinterpret_cast<uint2*>(out) + seg * total;
+  const float4* in = reinterpret_cast<const float4*>(x) + static_cast<long long>(seg) * rows * cols4;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cols4 - halo;
+    uint2 u = make_uint2(0u, 0u);
+    if (r >= 0 && r < rows) {
+      const float4 v = __ldg(in + r * cols4 + (i % cols4));
+      u = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    }
+    o[i] = u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- weight-norm fold
+__global__ void posconv_norm_kernel(const float* __restrict__ v, int n_oc, int taps, float* __restrict__ norm) {
+  // one block per tap: ||v[:, :, j]||_2 over all (o, c), fp64 accumulation, deterministic tree
+  const int j = blockIdx.x;
+  double s = 0;
+  for (int i = threadIdx.x; i < n_oc; i += blockDim.x) {
+    const double a = v[static_cast<long long>(i) * taps + j];
+    s += a * a;
+  }
+  __shared__ double red[256];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) norm[j] = static_cast<float>(sqrt(red[0]));
+}
+
+__global__ void posconv_fold_kernel(const float* __restrict__ g, const float* __restrict__ v,
+                                    const float* __restrict__ norm, int H, int cin, int taps, int cpad,
+                                    __nv_bfloat16* __restrict__ w) {
+  // w[o][j][c] = g[j] * v[o][c][j] / norm[j]   (c >= cin -> 0)
+  const long long total = static_cast<long long>(H) * taps * cpad;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % cpad);
+    const int j = static_cast<int>((i / cpad) % taps);
+    const long long o = i / (static_cast<long long>(cpad) * taps);
+    float val = 0.f;
+    if (c < cin) val = g[j] * v[(o * cin + c) * taps + j] / norm[j];
+    w[i] = __float2bfloat16(val);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- heads
+// Both heads in one pass over h: 32 rows per block, outputs in 64 slots (head A: slots 0..15, head B: 16..63).
+constexpr int HD_ROWS = 32;
+constexpr int HD_KC = 32;
+constexpr int HD_SLOTS = 64;
+constexpr int HD_A = 16;
+
+__device__ __forceinline__ float head_act(float x, int act) {
+  if (act == 1) return tanhf(x);
+  if (act == 2) return x > 0.f ? x : 0.01f * x;
+  return x;
+}
+
+__global__ void __launch_bounds__(256)
+heads_kernel(const float* __restrict__ h, long long rows, int H, const float* __restrict__ wa,
+             const float* __restrict__ ba, int na, int act_a, float* __restrict__ out_a,
+             const float* __restrict__ wb, const float* __restrict__ bb, int nb, int act_b,
+             float* __restrict__ out_b, long long* __restrict__ argmax_b) {
+  __shared__ float hA[HD_ROWS][HD_KC + 1];
+  __shared__ float hB[HD_ROWS][HD_KC + 1];
+  __shared__ float ws[HD_SLOTS][HD_KC + 1];
+  __shared__ float res[HD_ROWS][HD_SLOTS + 1];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15;        // 4 output slots each
+  const int ty = tid >> 4;        // 2 rows each
+  const long long row0 = static_cast<long long>(blockIdx.x) * HD_ROWS;
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  const bool is_a = tx < HD_A / 4;
+  for (int k0 = 0; k0 < H; k0 += HD_KC) {
+    for (int i = tid; i < HD_ROWS * HD_KC; i += 256) {
+      const int r = i / HD_KC, k = i % HD_KC;
+      const long long row = row0 + r;
+      const float x = row < rows ? __ldg(h + row * H + k0 + k) : 0.f;
+      hA[r][k] = head_act(x, act_a);
+      hB[r][k] = head_act(x, act_b);
+    }
+    for (int i = tid; i < HD_SLOTS * HD_KC; i += 256) {
+      const int s = i / HD_KC, k = i % HD_KC;
+      float wv = 0.f;
+      if (s < HD_A) {
+        if (s < na) wv = __ldg(wa + static_cast<long long>(s) * H + k0 + k);
+      } else if (s - HD_A < nb) {
+        wv = __ldg(wb + static_cast<long long>(s - HD_A) * H + k0 + k);
+      }
+      ws[s][k] = wv;
+    }
+    __syncthreads();
+    const float (*hs)[HD_KC + 1] = is_a ? hA : hB;
+#pragma unroll 8
+    for (int k = 0; k < HD_KC; ++k) {
+      const float x0 = hs[ty * 2][k], x1 = hs[ty * 2 + 1][k];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float wv = ws[tx * 4 + j][k];
+        acc[0][j] = fmaf(x0, wv, acc[0][j]);
+        acc[1][j] = fmaf(x1, wv, acc[1][j]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int s = tx * 4 + j;
+    float bv = 0.f;
+    if (s < HD_A) {
+      if (s < na) bv = ba[s];
+    } else if (s - HD_A < nb) {
+      bv = bb[s - HD_A];
+    }
+    res[ty * 2][s] = acc[0][j] + bv;
+    res[ty * 2 + 1][s] = acc[1][j] + bv;
+  }
+  __syncthreads();
+  for (int i = tid; i < HD_ROWS * HD_SLOTS; i += 256) {
+    const int r = i / HD_SLOTS, s = i % HD_SLOTS;
+    const long long row = row0 + r;
+    if (row >= rows) continue;
+    if (s < HD_A) {
+      if (s < na) out_a[row * na + s] = res[r][s];
+    } else if (s - HD_A < nb) {
+      out_b[row * nb + (s - HD_A)] = res[r][s];
+    }
+  }
+  if (argmax_b && nb > 0 && tid < HD_ROWS) {
+    const long long row = row0 + tid;
+    if (row < rows) {
+      int best = 0;
+      float bv = res[tid][HD_A];
+      for (int s = 1; s < nb; ++s) {
+        const float v = res[tid][HD_A + s];
+        if (v > bv) {   // strict: first maximum wins, as torch.argmax
+          bv = v;
+          best = s;
+        }
+      }
+      argmax_b[row] = best;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- low-pass FIR
+__global__ void lowpass_kernel(const float* __restrict__ x, int T, int C, const double* __restrict__ taps, int ntaps,
+                               float* __restrict__ y, long long total) {
+  extern __shared__ double tp[];
+  for (int i = threadIdx.x; i < ntaps; i += blockDim.x) tp[i] = taps[i];
+  __syncthreads();
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = static_cast<int>(i % C);
+  const int t = static_cast<int>((i / C) % T);
+  const long long b = i / (static_cast<long long>(C) * T);
+  const float* xb = x + b * T * C + c;
+  // torch Conv1d(padding='same') is a cross-correlation: y[t] = sum_j w[j] * x[t + j - (N-1)/2], zeros outside
+  const int half = (ntaps - 1) / 2;
+  double acc = 0.0;
+  for (int j = 0; j < ntaps; ++j) {
+    const int tt = t + j - half;
+    if (tt >= 0 && tt < T) acc += tp[j] * static_cast<double>(xb[static_cast<long long>(tt) * C]);
+  }
+  y[i] = static_cast<float>(acc);
+}
+
+// ---------------------------------------------------------------------------------------------- masked MSE + CE
+// accum: [0] sum sq err, [1] count tv, [2] sum ce, [3] count ce   (doubles)
+__global__ void mse_ce_kernel(const float* __restrict__ tv_pred, const float* __restrict__ tv_tgt,
+                              const float* __restrict__ logits, const long long* __restrict__ phn_tgt,
+                              long long rows, int ntv, int V, double* __restrict__ accum) {
+  double se = 0, ce = 0;
+  long long ntvv = 0, nce = 0;
+  for (long long r = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; r < rows;
+       r += static_cast<long long>(gridDim.x) * blockDim.x) {
+    for (int j = 0; j < ntv; ++j) {
+      const float tg = tv_tgt[r * ntv + j];
+      if (tg != -100.0f) {
+        const float d = tv_pred[r * ntv + j] - tg;
+        se += static_cast<double>(d * d);
+        ++ntvv;
+      }
+    }
+    const long long tg = phn_tgt[r];
+    if (tg != 0) {   // padding mask and ignore_index=0 coincide (models/aptai.py:73,95-100)
+      const float* lg = logits + r * V;
+      float m = lg[0];
+      for (int c = 1; c < V; ++c) m = fmaxf(m, lg[c]);
+      float s = 0.f;
+      for (int c = 0; c < V; ++c) s += expf(lg[c] - m);
+      ce += static_cast<double>(logf(s) + m - lg[tg]);
+      ++nce;
+    }
+  }
+  double v4[4] = {se, static_cast<double>(ntvv), ce, static_cast<double>(nce)};
+  __shared__ double red[4];
+  if (threadIdx.x < 4) red[threadIdx.x] = 0;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    double v = v4[k];
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&red[k], v);
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) atomicAdd(&accum[threadIdx.x], red[threadIdx.x]);
+}
+
+__global__ void mse_ce_finalize_kernel(const double* __restrict__ accum, float* __restrict__ out3) {
+  const double mse = accum[0] / accum[1];   // 0/0 -> NaN exactly like F.mse_loss on an empty selection
+  const double ce = accum[2] / accum[3];
+  out3[1] = static_cast<float>(mse);
+  out3[2] = static_cast<float>(ce);
+  out3[0] = 0.5f * static_cast<float>(mse) + 0.5f * static_cast<float>(ce);
+}
+
+}  // namespace aptai
+
+using namespace aptai;
+
+extern "C" int aptai_layernorm(const void* x, int x_is_bf16, int64_t rows, int cols, const float* gamma,
+                               const float* beta, float eps, float* out_f32, void* out_bf16, void* stream) {
+  if (int rc = check_arch()) return rc;
+  APTAI_REQUIRE(x && gamma && beta && (out_f32 || out_bf16), "layernorm: null pointer");
+  APTAI_REQUIRE(rows >= 1, "layernorm: rows=%lld", (long long)rows);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (cols) {
+    case 128: launch_ln<1>(x, x_is_bf16, rows, gamma, beta, eps, out_f32, out_bf16, st); break;
+    case 256: launch_ln<2>(x, x_is_bf16, rows, gamma, beta, eps, out_f32, out_bf16, st); break;
+    case 384: launch_ln<3>(x, x_is_bf16, rows, gamma, beta, eps, out_f32, out_bf16, st); break;
+    case 512: launch_ln<4>(x, x_is_bf16, rows, gamma, beta, eps, out_f32, out_bf16, st); break;
+    case 768: launch_ln<6>(x, x_is_bf16, rows, gamma, beta, eps, out_f32, out_bf16, st); break;
+    case 1024: launch_ln<8>(x, x_is_bf16, rows, gamma, beta, eps, out_f32, out_bf16, st); break;
+    case 1280: launch_ln<10>(x, x_is_bf16, rows, gamma, beta, eps, out_f32, out_bf16, st); break;
+    default:
+      set_error("layernorm: unsupported width %d (128, 256, 384, 512, 768, 1024, 1280)", cols);
+      return APTAI_ERR_ARG;
+  }
+  return after_launch("layernorm");
+}
+
+extern "C" int aptai_cast_pad_bf16(const float* x, int segs, int rows, int cols, int halo, void* out_bf16,
+                                   void* stream) {
+  if (int rc = check_arch()) return rc;
+  APTAI_REQUIRE(x && out_bf16, "cast_pad: null pointer");
+  APTAI_REQUIRE(segs >= 1 && rows >= 1 && cols % 4 == 0 && halo >= 0, "cast_pad: bad shape");
+  const long long total = static_cast<long long>(rows + 2 * halo) * (cols / 4);
+  int gx = static_cast<int>((total + 255) / 256);
+  if (gx > 4096) gx = 4096;
+  cast_pad_kernel<<<dim3(gx, segs), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, rows, cols / 4, halo, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  return after_launch("cast_pad_bf16");
+}
+
+extern "C" int aptai_posconv_fold(const float* g, const float* v, int H, int cin, int taps, int cpad, void* w_bf16,
+                                  float* norm_ws, void* stream) {
+  if (int rc = check_arch()) return rc;
+  APTAI_REQUIRE(g && v && w_bf16 && norm_ws, "posconv_fold: null pointer");
+  APTAI_REQUIRE(cpad >= cin && H >= 1 && taps >= 1, "posconv_fold: bad shape");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  posconv_norm_kernel<<<taps, 256, 0, st>>>(v, H * cin, taps, norm_ws);
+  if (int rc = after_launch("posconv_norm")) return rc;
+  const long long total = static_cast<long long>(H) * taps * cpad;
+  int gx = static_cast<int>((total + 255) / 256);
+  if (gx > 8192) gx = 8192;
+  posconv_fold_kernel<<<gx, 256, 0, st>>>(g, v, norm_ws, H, cin, taps, cpad, reinterpret_cast<__nv_bfloat16*>(w_bf16));
+  return after_launch("posconv_fold");
+}
+
+extern "C" int aptai_heads(const float* h, int64_t rows, int H, const float* wa, const float* ba, int na, int act_a,
+                           float* out_a, const float* wb, const float* bb, int nb, int act_b, float* out_b,
+                           int64_t* argmax_b, void* stream) {
+  if (int rc = check_arch()) return rc;
+  APTAI_REQUIRE(h && rows >= 1 && H % HD_KC == 0, "heads: bad input (H must be a multiple of %d)", HD_KC);
+  APTAI_REQUIRE(na >= 0 && na <= HD_A && nb >= 0 && nb <= HD_SLOTS - HD_A, "heads: na <= %d and nb <= %d", HD_A,
+                HD_SLOTS - HD_A);
+  APTAI_REQUIRE(na == 0 || (wa && ba && out_a), "heads: head A pointers");
+  APTAI_REQUIRE(nb == 0 || (wb && bb && out_b), "heads: head B pointers");
+  const unsigned grid = static_cast<unsigned>((rows + HD_ROWS - 1) / HD_ROWS);
+  heads_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      h, rows, H, wa, ba, na, act_a, out_a, wb, bb, nb, act_b, out_b, reinterpret_cast<long long*>(argmax_b));
+  return after_launch("heads");
+}
+
+extern "C" int aptai_lowpass_fir(const float* x, int B, int T, int C, const double* taps, int ntaps, float* y,
+                                 void* stream) {
+  if (int rc = check_arch()) return rc;
+  APTAI_REQUIRE(x && y && taps, "lowpass: null pointer");
+  APTAI_REQUIRE(B >= 1 && T >= 1 && C >= 1 && ntaps >= 1 && (ntaps & 1), "lowpass: bad shape (ntaps must be odd)");
+  const long long total = static_cast<long long>(B) * T * C;
+  lowpass_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, ntaps * sizeof(double),
+                   reinterpret_cast<cudaStream_t>(stream)>>>(x, T, C, taps, ntaps, y, total);
+  return after_launch("lowpass_fir");
+}
+
+extern "C" int aptai_masked_mse_ce(const float* tv_pred, const float* tv_tgt, const float* logits,
+                                   const int64_t* phn_tgt, int64_t rows, int ntv, int V, float* accum_ws,
+                                   float* out3, void* stream) {
+  if (int rc = check_arch()) return rc;
+  APTAI_REQUIRE(tv_pred && tv_tgt && logits && phn_tgt && accum_ws && out3, "mse_ce: null pointer");
+  APTAI_REQUIRE((reinterpret_cast<uintptr_t>(accum_ws) & 7) == 0, "mse_ce: accum_ws must be 8-byte aligned (4 doubles)");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  double* acc = reinterpret_cast<double*>(accum_ws);
+  cudaError_t e = cudaMemsetAsync(acc, 0, 4 * sizeof(double), st);
+  if (e != cudaSuccess) {
+    set_error("mse_ce: memset: %s", cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
+  int grid = static_cast<int>((rows + 127) / 128);
+  if (grid > 1024) grid = 1024;
+  mse_ce_kernel<<<grid, 128, 0, st>>>(tv_pred, tv_tgt, logits, reinterpret_cast<const long long*>(phn_tgt), rows,
+                                       ntv, V, acc);
+  if (int rc = after_launch("mse_ce")) return rc;
+  mse_ce_finalize_kernel<<<1, 1, 0, st>>>(acc, out3);
+  return after_launch("mse_ce_finalize");
+}

@@ -1,0 +1,409 @@
+// tcgen05 / TMEM / TMA bf16 GEMM family for sm_100a.
+//
+// One persistent, warp-specialised kernel (TMA producer warp, single-thread MMA issuer, 8 epilogue warps) serves
+//   * nn.Linear projections of the wav2vec2 encoder            (HF:429-434, 524-547, 566-573)
+//   * the strided conv layers 1..6 as implicit GEMM            (HF:254-323)  [A rows = overlapping frame windows]
+//   * the grouped positional conv (k=128, 16 groups)           (HF:329-368)  [A rows = shifted frame windows]
+// by describing the A operand with a 4-D tensor map (channel, row parity, row/P, segment) so that the k-block
+// `kb` of output row r reads physical row r*P + tap, tap = kb / kb_per_tap.
+//
+// Tile: 128 x BN x 64 per pipeline stage, accumulators in TMEM (double buffered when 2*BN <= 512 columns),
+// epilogue straight from TMEM: bias / LayerNorm(512) / erf-GELU / fp32 residual / padded-row zeroing / fp32+bf16 stores.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace aptai {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 384;   // warp 0: TMA, warp 1: MMA, warp 2: TMEM alloc, warp 3: idle, warps 4..11: epilogue
+constexpr int EPI_WARP0 = 4;
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+
+struct GemmParams {
+  int num_kb, kb_per_tap, P, a_col_per_nblk;
+  int rows_per_seg, m_tiles_per_seg, n_tiles, num_tiles;
+  const float* bias;
+  const float* gamma;
+  const float* beta;
+  const float* residual;
+  float* out_f32;
+  __nv_bfloat16* out_bf16;
+  long long ldo, out_seg_stride;
+  const int* seg_valid_rows;
+  int mask_seg_rows;
+  int act;
+  float ln_eps;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int UN = BN > 256 ? 256 : BN;                 // N of one tcgen05.mma
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BN >= 512 ? 2 : (BN >= 256 ? 4 : 6);
+  static constexpr int ACC_STRIDE = BN < 64 ? 64 : BN;
+  static constexpr int ACC_STAGES = (2 * ACC_STRIDE <= 512) ? 2 : 1;
+  static constexpr int TMEM_COLS = ACC_STAGES * ACC_STRIDE <= 128 ? 128 : (ACC_STAGES * ACC_STRIDE <= 256 ? 256 : 512);
+  static constexpr int CHUNK = (BN % 64 == 0) ? 32 : 8;          // columns per tcgen05.ld in the epilogue
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int LN_BYTES = 2 * 2 * BLOCK_M * sizeof(float2);
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES + LN_BYTES;
+};
+
+template <int CH>
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[CH]);
+template <>
+__device__ __forceinline__ void tmem_ld_chunk<32>(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld32(taddr, r); }
+template <>
+__device__ __forceinline__ void tmem_ld_chunk<8>(uint32_t taddr, uint32_t (&r)[8]) { tmem_ld8(taddr, r); }
+
+template <int BN, bool LN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const GemmParams p) {
+  using C = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tfull_bar = empty_bar + C::STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float2* ln_part = reinterpret_cast<float2*>(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (one thread)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int n_blk = tile % p.n_tiles;
+        const int mt = tile / p.n_tiles;
+        const int seg = mt / p.m_tiles_per_seg;
+        const int r0 = (mt - seg * p.m_tiles_per_seg) * BLOCK_M;
+        const int a_col0 = n_blk * p.a_col_per_nblk;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          const int tap = kb / p.kb_per_tap;
+          const int kc = kb - tap * p.kb_per_tap;
+          const int tq = tap / p.P;
+          tma_load_4d(&tmA, &full_bar[stage], sa, kc * BLOCK_K + a_col0, tap - tq * p.P, r0 + tq, seg);
+#pragma unroll
+          for (int nh = 0; nh < BN / C::UN; ++nh)
+            tma_load_2d(&tmB, &full_bar[stage], sb + nh * C::UN * BLOCK_K * 2, kb * BLOCK_K, n_blk * BN + nh * C::UN);
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      constexpr uint32_t IDESC = umma_idesc_bf16(BLOCK_M, C::UN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * C::ACC_STRIDE;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t b_base = a_base + C::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t adesc = umma_desc_sw128(a_base + k * UMMA_K * 2);
+#pragma unroll
+            for (int nh = 0; nh < BN / C::UN; ++nh) {
+              const uint64_t bdesc = umma_desc_sw128(b_base + nh * C::UN * BLOCK_K * 2 + k * UMMA_K * 2);
+              umma_bf16(d_tmem + nh * C::UN, adesc, bdesc, IDESC, (kb | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs have read it
+          if (++stage == C::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);       // accumulator complete -> epilogue
+        if (C::ACC_STAGES == 2) {
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+        } else {
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ------------------------------------------------------------------ epilogue: TMEM -> registers -> global
+    constexpr int CH = C::CHUNK;
+    const int q = warp & 3;                  // TMEM lane quadrant this warp may read
+    const int half = (warp - EPI_WARP0) >> 2;
+    constexpr int HALF_N = BN / 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int ln_buf = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int n_blk = tile % p.n_tiles;
+      const int mt = tile / p.n_tiles;
+      const int seg = mt / p.m_tiles_per_seg;
+      const int row_in_tile = q * 32 + lane;
+      const int r = (mt - seg * p.m_tiles_per_seg) * BLOCK_M + row_in_tile;
+      const bool valid_row = r < p.rows_per_seg;
+      const long long out_row = static_cast<long long>(seg) * p.out_seg_stride + r;
+      bool zero_row = false;
+      if (p.seg_valid_rows != nullptr && valid_row) {
+        const long long ms = out_row / p.mask_seg_rows;
+        zero_row = (out_row - ms * p.mask_seg_rows) >= __ldg(p.seg_valid_rows + ms);
+      }
+      const long long out_off = out_row * p.ldo;
+      const int n_tile0 = n_blk * BN;
+
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * C::ACC_STRIDE;
+
+      float mean = 0.f, rstd = 1.f;
+      if (LN) {
+        // pass 1: shifted single-pass statistics of (acc + bias) over this warp's half row, then Chan-combine
+        float pivot = 0.f, s1 = 0.f, s2 = 0.f;
+        for (int c = half * HALF_N; c < (half + 1) * HALF_N; c += CH) {
+          uint32_t regs[CH];
+          tmem_ld_chunk<CH>(t_row + c, regs);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < CH; ++i) {
+            float v = __uint_as_float(regs[i]);
+            if (p.bias) v += __ldg(p.bias + n_tile0 + c + i);
+            if (c == half * HALF_N && i == 0) pivot = v;
+            const float d = v - pivot;
+            s1 += d;
+            s2 = fmaf(d, d, s2);
+          }
+        }
+        const float inv_n = 1.0f / HALF_N;
+        const float mean_h = pivot + s1 * inv_n;
+        const float m2_h = fmaxf(s2 - s1 * s1 * inv_n, 0.f);
+        float2* buf = ln_part + ln_buf * 2 * BLOCK_M;
+        buf[half * BLOCK_M + row_in_tile] = make_float2(mean_h, m2_h);
+        named_bar_sync(1, EPI_THREADS);
+        const float2 o = buf[(half ^ 1) * BLOCK_M + row_in_tile];
+        ln_buf ^= 1;
+        const float dm = mean_h - o.x;
+        mean = 0.5f * (mean_h + o.x);
+        const float var = (m2_h + o.y + dm * dm * (0.5f * HALF_N)) * (1.0f / BN);
+        rstd = rsqrtf(var + p.ln_eps);
+      }
+
+      for (int c = half * HALF_N; c < (half + 1) * HALF_N; c += CH) {
+        uint32_t regs[CH];
+        tmem_ld_chunk<CH>(t_row + c, regs);
+        tmem_ld_wait();
+        float v[CH];
+        const int n0 = n_tile0 + c;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(regs[i]);
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < CH; i += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
+            v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+          }
+        }
+        if (LN) {
+#pragma unroll
+          for (int i = 0; i < CH; i += 4) {
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + n0 + i));
+            const float4 e4 = __ldg(reinterpret_cast<const float4*>(p.beta + n0 + i));
+            v[i] = fmaf((v[i] - mean) * rstd, g4.x, e4.x);
+            v[i + 1] = fmaf((v[i + 1] - mean) * rstd, g4.y, e4.y);
+            v[i + 2] = fmaf((v[i + 2] - mean) * rstd, g4.z, e4.z);
+            v[i + 3] = fmaf((v[i + 3] - mean) * rstd, g4.w, e4.w);
+          }
+        }
+        if (p.act == 1) {
+#pragma unroll
+          for (int i = 0; i < CH; ++i) v[i] = gelu_erf(v[i]);
+        }
+        if (valid_row) {
+          if (p.residual) {
+            const float4* rp = reinterpret_cast<const float4*>(p.residual + out_off + n0);
+#pragma unroll
+            for (int i = 0; i < CH; i += 4) {
+              const float4 r4 = __ldg(rp + i / 4);
+              v[i] += r4.x; v[i + 1] += r4.y; v[i + 2] += r4.z; v[i + 3] += r4.w;
+            }
+          }
+          if (zero_row) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) v[i] = 0.f;
+          }
+          if (p.out_f32) {
+            float4* op = reinterpret_cast<float4*>(p.out_f32 + out_off + n0);
+#pragma unroll
+            for (int i = 0; i < CH; i += 4) op[i / 4] = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+          }
+          if (p.out_bf16) {
+            uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + out_off + n0);
+#pragma unroll
+            for (int i = 0; i < CH; i += 8)
+              op[i / 8] = make_uint4(pack_bf16(v[i], v[i + 1]), pack_bf16(v[i + 2], v[i + 3]),
+                                     pack_bf16(v[i + 4], v[i + 5]), pack_bf16(v[i + 6], v[i + 7]));
+          }
+        }
+      }
+      // all tcgen05.ld of this warp have completed (wait::ld above) -> hand the accumulator back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (C::ACC_STAGES == 2) {
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      } else {
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int BN, bool LN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  using C = GemmCfg<BN>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, LN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("gemm: cudaFuncSetAttribute(%d bytes): %s", C::SMEM_BYTES, cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    attr_set = true;
+  }
+  int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  kern<<<grid, GEMM_THREADS, C::SMEM_BYTES, st>>>(ta, tb, p);
+  return after_launch("gemm_bf16_tcgen05");
+}
+
+}  // namespace aptai
+
+using namespace aptai;
+
+extern "C" int aptai_gemm_bf16(const aptai_gemm_args* g, void* stream) {
+  if (int rc = check_arch()) return rc;
+  APTAI_REQUIRE(g != nullptr, "gemm: null args");
+  APTAI_REQUIRE(g->a && g->w, "gemm: null operand");
+  APTAI_REQUIRE(g->out_f32 || g->out_bf16, "gemm: no output pointer");
+  APTAI_REQUIRE(g->P >= 1 && g->taps >= 1 && g->kb_per_tap >= 1, "gemm: bad tap geometry");
+  APTAI_REQUIRE(g->segs >= 1 && g->rows_per_seg >= 1 && g->a_rows >= 1, "gemm: bad row geometry");
+  APTAI_REQUIRE(g->a_row_stride % 8 == 0 && g->a_seg_stride % 8 == 0, "gemm: A strides must be multiples of 8");
+  APTAI_REQUIRE((reinterpret_cast<uintptr_t>(g->a) & 15) == 0 && (reinterpret_cast<uintptr_t>(g->w) & 15) == 0,
+                "gemm: operands must be 16-byte aligned");
+  APTAI_REQUIRE(g->ldo % 8 == 0, "gemm: ldo must be a multiple of 8");
+  APTAI_REQUIRE(g->seg_valid_rows == nullptr || g->mask_seg_rows >= 1, "gemm: mask_seg_rows must be >= 1");
+  int bn = g->block_n;
+  if (g->ln) {
+    APTAI_REQUIRE(g->N == 512 && (bn == 0 || bn == 512), "gemm: fused LayerNorm needs N == 512");
+    APTAI_REQUIRE(g->gamma && g->beta, "gemm: fused LayerNorm needs gamma/beta");
+    bn = 512;
+  } else if (bn == 0) {
+    bn = (g->N % 256 == 0) ? 256 : (g->N % 128 == 0) ? 128 : (g->N % 64 == 0) ? 64 : (g->N % 48 == 0) ? 48 : 0;
+  }
+  APTAI_REQUIRE(bn == 48 || bn == 64 || bn == 128 || bn == 256 || bn == 512, "gemm: unsupported block_n for N=%d",
+                g->N);
+  APTAI_REQUIRE(g->N % bn == 0, "gemm: N=%d not a multiple of block_n=%d", g->N, bn);
+  APTAI_REQUIRE(bn != 512 || g->ln, "gemm: block_n 512 is the fused-LayerNorm tile");
+  const long long K = static_cast<long long>(g->taps) * g->kb_per_tap * BLOCK_K;
+
+  CUtensorMap ta, tb;
+  {
+    const uint64_t r2 = (static_cast<uint64_t>(g->a_rows) + g->P - 1) / g->P;
+    uint64_t dims[4] = {static_cast<uint64_t>(g->a_cols), static_cast<uint64_t>(g->P), r2,
+                        static_cast<uint64_t>(g->segs)};
+    uint64_t seg_stride = g->a_seg_stride > 0 ? static_cast<uint64_t>(g->a_seg_stride)
+                                              : static_cast<uint64_t>(g->a_row_stride) * g->a_rows;
+    uint64_t strides[3] = {static_cast<uint64_t>(g->a_row_stride) * 2,
+                           static_cast<uint64_t>(g->a_row_stride) * 2 * g->P, seg_stride * 2};
+    uint32_t box[4] = {BLOCK_K, 1, BLOCK_M, 1};
+    if (int rc = encode_tmap_bf16(&ta, g->a, 4, dims, strides, box, 1)) return rc;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(g->N)};
+    uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
+    uint32_t box[2] = {BLOCK_K, static_cast<uint32_t>(bn > 256 ? 256 : bn)};
+    if (int rc = encode_tmap_bf16(&tb, g->w, 2, dims, strides, box, 1)) return rc;
+  }
+  GemmParams p;
+  p.num_kb = g->taps * g->kb_per_tap;
+  p.kb_per_tap = g->kb_per_tap;
+  p.P = g->P;
+  p.a_col_per_nblk = g->a_col_per_nblk;
+  p.rows_per_seg = g->rows_per_seg;
+  p.m_tiles_per_seg = (g->rows_per_seg + BLOCK_M - 1) / BLOCK_M;
+  p.n_tiles = g->N / bn;
+  p.num_tiles = g->segs * p.m_tiles_per_seg * p.n_tiles;
+  p.bias = g->bias;
+  p.gamma = g->gamma;
+  p.beta = g->beta;
+  p.residual = g->residual;
+  p.out_f32 = g->out_f32;
+  p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(g->out_bf16);
+  p.ldo = g->ldo;
+  p.out_seg_stride = g->out_seg_stride;
+  p.seg_valid_rows = g->seg_valid_rows;
+  p.mask_seg_rows = g->mask_seg_rows;
+  p.act = g->act;
+  p.ln_eps = g->ln_eps;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (g->ln) return launch_gemm<512, true>(ta, tb, p, st);
+  switch (bn) {
+    case 256: return launch_gemm<256, false>(ta, tb, p, st);
+    case 128: return launch_gemm<128, false>(ta, tb, p, st);
+    case 64: return launch_gemm<64, false>(ta, tb, p, st);
+    case 48: return launch_gemm<48, false>(ta, tb, p, st);
+  }
+  set_error("gemm: unreachable block_n %d", bn);
+  return APTAI_ERR_ARG;
+}

@@ -1,0 +1,92 @@
+"""ctypes binding of `libaptai_b200.so` (the C ABI declared in include/aptai_b200.h).
+
+There is deliberately no fallback of any kind: if the shared library is missing, or a compute entry point is
+called on a device that is not sm_100, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libaptai_b200.so"
+
+c_void_p, c_int, c_i64, c_float, c_size_t = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
+
+
+class GemmArgs(C.Structure):
+    """struct aptai_gemm_args (include/aptai_b200.h)."""
+    _fields_ = [
+        ("a", c_void_p), ("a_row_stride", c_i64), ("a_seg_stride", c_i64),
+        ("a_rows", C.c_int32), ("a_cols", C.c_int32), ("P", C.c_int32), ("taps", C.c_int32),
+        ("kb_per_tap", C.c_int32), ("a_col_per_nblk", C.c_int32),
+        ("w", c_void_p), ("N", C.c_int32), ("block_n", C.c_int32), ("segs", C.c_int32), ("rows_per_seg", C.c_int32),
+        ("bias", c_void_p), ("gamma", c_void_p), ("beta", c_void_p), ("residual", c_void_p),
+        ("out_f32", c_void_p), ("out_bf16", c_void_p), ("ldo", c_i64), ("out_seg_stride", c_i64),
+        ("seg_valid_rows", c_void_p), ("mask_seg_rows", C.c_int32), ("act", C.c_int32), ("ln", C.c_int32), ("ln_eps", c_float),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/aptai_b200.h declares
+PROTOTYPES = {
+    "aptai_version": (c_int, []),
+    "aptai_last_error_string": (C.c_char_p, []),
+    "aptai_launch_count": (c_i64, []),
+    "aptai_gemm_bf16": (c_int, [C.POINTER(GemmArgs), c_void_p]),
+    "aptai_conv0_norm_gelu": (c_int, [c_void_p, c_int, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float,
+                                      c_void_p, c_int, c_void_p, c_void_p]),
+    "aptai_layernorm": (c_int, [c_void_p, c_int, c_i64, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
+                                c_void_p]),
+    "aptai_cast_pad_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "aptai_posconv_fold": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "aptai_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "aptai_heads": (c_int, [c_void_p, c_i64, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                            c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "aptai_lowpass_fir": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "aptai_masked_mse_ce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p,
+                                    c_void_p]),
+    "aptai_ctc_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "aptai_logsoftmax_ctc": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "aptai_logsoftmax_ctc_ex": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_int,
+                                        c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_size_t, c_void_p]),
+    "aptai_viterbi_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "aptai_ctc_viterbi_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                      c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "aptai_ctc_greedy": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
+                                 c_void_p]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (building is the job of `aptai_b200.build` / `__graft_entry__.build()`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            f"{LIB_PATH} not found: the CUDA extension is not built. Run `python -m aptai_b200.build` "
+            "(aptai_b200 has no CPU or PyTorch fallback).")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)   # AttributeError if a declared symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().aptai_last_error_string().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"aptai_b200.{what} failed (status {rc}): {last_error()}")
+
+
+def launch_count() -> int:
+    return int(load().aptai_launch_count())

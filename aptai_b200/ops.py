@@ -1,0 +1,286 @@
+"""Torch-facing wrappers of the C-ABI kernels: argument checks, output allocation (PyTorch's caching allocator
+owns every buffer), launch on torch's current CUDA stream.  No arithmetic happens here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import lib as _lib
+from .lib import GemmArgs, check
+
+BF16, F32, I32, I64, F64 = torch.bfloat16, torch.float32, torch.int32, torch.int64, torch.float64
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise RuntimeError(f"aptai_b200: {name} must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise TypeError(f"aptai_b200: {name} must be {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"aptai_b200: {name} must be contiguous")
+    return t
+
+
+def alloc_rows_bf16(B: int, T: int, C: int, device, slack_rows: int = 2) -> torch.Tensor:
+    """bf16 [B,T,C] view of a flat buffer with `slack_rows` zeroed rows behind it: the strided (conv) TMA view of
+    the next layer may address one row past the last utterance, and must not leave the allocation."""
+    flat = torch.empty((B * T + slack_rows) * C, dtype=BF16, device=device)
+    flat[B * T * C:].zero_()
+    return flat[: B * T * C].view(B, T, C)
+
+
+def gemm_raw(args: GemmArgs) -> None:
+    check(_lib.load().aptai_gemm_bf16(C.byref(args), _stream()), "gemm_bf16")
+
+
+def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: int = 0,
+           residual: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None,
+           out_bf16: Optional[torch.Tensor] = None, want_f32: bool = False, want_bf16: bool = True,
+           seg_rows: Optional[int] = None, seg_valid_rows: Optional[torch.Tensor] = None,
+           block_n: int = 0):
+    """out = epilogue(a @ w.T): a bf16 [M,K], w bf16 [N,K] (nn.Linear layout), bias fp32 [N].
+
+    seg_rows / seg_valid_rows: rows are grouped in segments of seg_rows; rows >= seg_valid_rows[s] are written as 0.
+    """
+    _req(a, BF16, "a"); _req(w, BF16, "w")
+    M, K = a.shape
+    N, K2 = w.shape
+    if K != K2 or K % 64:
+        raise ValueError(f"linear: K mismatch or not a multiple of 64 ({K}, {K2})")
+    if want_f32 and out_f32 is None:
+        out_f32 = torch.empty((M, N), dtype=F32, device=a.device)
+    if want_bf16 and out_bf16 is None:
+        out_bf16 = torch.empty((M, N), dtype=BF16, device=a.device)
+    g = GemmArgs()
+    g.a = a.data_ptr(); g.a_row_stride = K; g.a_cols = K; g.P = 1; g.taps = 1; g.kb_per_tap = K // 64
+    g.a_col_per_nblk = 0
+    g.segs = 1; g.rows_per_seg = M; g.a_rows = M; g.a_seg_stride = 0; g.out_seg_stride = 0
+    if seg_valid_rows is not None:
+        assert seg_rows is not None and M % seg_rows == 0
+        _req(seg_valid_rows, I32, "seg_valid_rows")
+        g.seg_valid_rows = seg_valid_rows.data_ptr(); g.mask_seg_rows = seg_rows
+    else:
+        g.seg_valid_rows = None; g.mask_seg_rows = 0
+    g.w = w.data_ptr(); g.N = N; g.block_n = block_n
+    g.bias = _ptr(_req(bias, F32, "bias")) if bias is not None else None
+    g.gamma = None; g.beta = None
+    g.residual = _ptr(_req(residual, F32, "residual")) if residual is not None else None
+    g.out_f32 = _ptr(out_f32); g.out_bf16 = _ptr(out_bf16); g.ldo = N
+    g.act = act; g.ln = 0; g.ln_eps = 0.0
+    gemm_raw(g)
+    return out_f32, out_bf16
+
+
+def conv_igemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], k: int, stride: int, *,
+               ln_gamma: Optional[torch.Tensor] = None, ln_beta: Optional[torch.Tensor] = None,
+               eps: float = 1e-5, act: int = 1, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Strided conv1d as implicit GEMM.  x bf16 [B,T_in,C] channels-last, w bf16 [N, k*C] (tap-major K), out bf16
+    [B,T_out,N]; epilogue = (+bias) -> (LayerNorm over N, if gamma) -> GELU."""
+    _req(x, BF16, "x"); _req(w, BF16, "w")
+    B, T_in, Cc = x.shape
+    N = w.shape[0]
+    assert w.shape[1] == k * Cc and Cc % 64 == 0
+    T_out = (T_in - k) // stride + 1
+    if out is None:
+        out = alloc_rows_bf16(B, T_out, N, x.device)
+    g = GemmArgs()
+    g.a = x.data_ptr(); g.a_row_stride = Cc; g.a_seg_stride = T_in * Cc; g.a_rows = T_in; g.a_cols = Cc
+    g.P = stride; g.taps = k; g.kb_per_tap = Cc // 64; g.a_col_per_nblk = 0
+    g.w = w.data_ptr(); g.N = N; g.block_n = 0; g.segs = B; g.rows_per_seg = T_out
+    g.bias = _ptr(bias)
+    g.gamma = _ptr(ln_gamma); g.beta = _ptr(ln_beta); g.residual = None
+    g.out_f32 = None; g.out_bf16 = out.data_ptr(); g.ldo = N; g.out_seg_stride = T_out
+    g.seg_valid_rows = None; g.mask_seg_rows = 0; g.act = act; g.ln = 1 if ln_gamma is not None else 0; g.ln_eps = eps
+    gemm_raw(g)
+    return out
+
+
+def posconv(x_pad: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, residual: torch.Tensor, T: int, H: int,
+            groups: int, taps: int, out_f32: torch.Tensor) -> torch.Tensor:
+    """Grouped positional conv + bias + GELU + residual.  x_pad bf16 [B, T+2*halo, H] (halo = taps//2, zeroed),
+    w bf16 [H, taps*64] (per output channel: tap-major, 64-padded group input channels)."""
+    _req(x_pad, BF16, "x_pad"); _req(w, BF16, "w")
+    B, Tp, H2 = x_pad.shape
+    assert H2 == H and Tp == T + taps
+    gw = H // groups
+    g = GemmArgs()
+    g.a = x_pad.data_ptr(); g.a_row_stride = H; g.a_seg_stride = Tp * H; g.a_rows = Tp; g.a_cols = H
+    g.P = 1; g.taps = taps; g.kb_per_tap = 1; g.a_col_per_nblk = gw
+    g.w = w.data_ptr(); g.N = H; g.block_n = gw; g.segs = B; g.rows_per_seg = T
+    g.bias = bias.data_ptr(); g.gamma = None; g.beta = None; g.residual = residual.data_ptr()
+    g.out_f32 = out_f32.data_ptr(); g.out_bf16 = None; g.ldo = H; g.out_seg_stride = T
+    g.seg_valid_rows = None; g.mask_seg_rows = 0; g.act = 1; g.ln = 0; g.ln_eps = 0.0
+    gemm_raw(g)
+    return out_f32
+
+
+def conv0(wav: torch.Tensor, w: torch.Tensor, bias, gamma, beta, norm: int, eps: float = 1e-5) -> torch.Tensor:
+    _req(wav, F32, "wav"); _req(w, F32, "w")
+    B, L = wav.shape
+    T0 = (L - 10) // 5 + 1
+    out = alloc_rows_bf16(B, T0, 512, wav.device)
+    ws = torch.empty((max(256, B * (65 * 2 + 1024) + 16),), dtype=F32, device=wav.device) if norm else None
+    check(_lib.load().aptai_conv0_norm_gelu(wav.data_ptr(), B, L, w.data_ptr(), _ptr(bias), _ptr(gamma), _ptr(beta),
+                                            norm, eps, out.data_ptr(), T0, _ptr(ws), _stream()), "conv0_norm_gelu")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5, *, want_f32=False,
+              want_bf16=True, out_f32=None, out_bf16=None):
+    assert x.dtype in (F32, BF16) and x.is_cuda and x.is_contiguous()
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    if want_f32 and out_f32 is None:
+        out_f32 = torch.empty(x.shape, dtype=F32, device=x.device)
+    if want_bf16 and out_bf16 is None:
+        out_bf16 = torch.empty(x.shape, dtype=BF16, device=x.device)
+    check(_lib.load().aptai_layernorm(x.data_ptr(), int(x.dtype == BF16), rows, cols, gamma.data_ptr(),
+                                      beta.data_ptr(), eps, _ptr(out_f32), _ptr(out_bf16), _stream()), "layernorm")
+    return out_f32, out_bf16
+
+
+def cast_pad(x: torch.Tensor, halo: int) -> torch.Tensor:
+    _req(x, F32, "x")
+    B, T, H = x.shape
+    out = torch.empty((B, T + 2 * halo, H), dtype=BF16, device=x.device)
+    check(_lib.load().aptai_cast_pad_bf16(x.data_ptr(), B, T, H, halo, out.data_ptr(), _stream()), "cast_pad_bf16")
+    return out
+
+
+def posconv_fold(g: torch.Tensor, v: torch.Tensor, cpad: int = 64) -> torch.Tensor:
+    """weight_norm(dim=2) fold: g [1,1,taps], v [H, cin, taps] -> bf16 [H, taps*cpad]."""
+    _req(g, F32, "g"); _req(v, F32, "v")
+    H, cin, taps = v.shape
+    w = torch.empty((H, taps * cpad), dtype=BF16, device=v.device)
+    ws = torch.empty((taps,), dtype=F32, device=v.device)
+    check(_lib.load().aptai_posconv_fold(g.data_ptr(), v.data_ptr(), H, cin, taps, cpad, w.data_ptr(), ws.data_ptr(),
+                                         _stream()), "posconv_fold")
+    return w
+
+
+def attention(qkv: torch.Tensor, key_len: Optional[torch.Tensor], B: int, T: int, heads: int,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(qkv, BF16, "qkv")
+    H = heads * 64
+    assert qkv.numel() == B * T * 3 * H
+    if out is None:
+        out = torch.empty((B * T, H), dtype=BF16, device=qkv.device)
+    if key_len is not None:
+        _req(key_len, I32, "key_len")
+    check(_lib.load().aptai_attention_fwd(qkv.data_ptr(), out.data_ptr(), _ptr(key_len), B, T, heads, _stream()),
+          "attention_fwd")
+    return out
+
+
+ACT_NONE, ACT_TANH, ACT_LEAKY = 0, 1, 2
+
+
+def heads(h: torch.Tensor, wa, ba, act_a: int, wb, bb, act_b: int, want_argmax: bool = True):
+    """h fp32 [rows,H] -> (out_a [rows,na] | None, out_b [rows,nb] | None, argmax_b int64 [rows] | None)."""
+    _req(h, F32, "h")
+    rows, H = h.shape
+    na = 0 if wa is None else wa.shape[0]
+    nb = 0 if wb is None else wb.shape[0]
+    oa = torch.empty((rows, na), dtype=F32, device=h.device) if na else None
+    ob = torch.empty((rows, nb), dtype=F32, device=h.device) if nb else None
+    am = torch.empty((rows,), dtype=I64, device=h.device) if (nb and want_argmax) else None
+    check(_lib.load().aptai_heads(h.data_ptr(), rows, H, _ptr(wa), _ptr(ba), na, act_a, _ptr(oa), _ptr(wb), _ptr(bb),
+                                  nb, act_b, _ptr(ob), _ptr(am), _stream()), "heads")
+    return oa, ob, am
+
+
+def lowpass(x: torch.Tensor, taps: torch.Tensor) -> torch.Tensor:
+    _req(x, F32, "x"); _req(taps, F64, "taps")
+    B, T, Cc = x.shape
+    y = torch.empty_like(x)
+    check(_lib.load().aptai_lowpass_fir(x.data_ptr(), B, T, Cc, taps.data_ptr(), taps.numel(), y.data_ptr(),
+                                        _stream()), "lowpass_fir")
+    return y
+
+
+def masked_mse_ce(tv_pred, tv_tgt, logits, phn_tgt) -> torch.Tensor:
+    _req(tv_pred, F32, "tv_pred"); _req(tv_tgt, F32, "tv_tgt"); _req(logits, F32, "logits"); _req(phn_tgt, I64, "phn")
+    rows = phn_tgt.numel()
+    ntv = tv_pred.shape[-1]
+    V = logits.shape[-1]
+    ws = torch.empty((4,), dtype=F64, device=logits.device)
+    out = torch.empty((3,), dtype=F32, device=logits.device)
+    check(_lib.load().aptai_masked_mse_ce(tv_pred.data_ptr(), tv_tgt.data_ptr(), logits.data_ptr(), phn_tgt.data_ptr(),
+                                          rows, ntv, V, ws.data_ptr(), out.data_ptr(), _stream()), "masked_mse_ce")
+    return out
+
+
+def logsoftmax_ctc(logits: torch.Tensor, targets: torch.Tensor, input_len: torch.Tensor, target_len: torch.Tensor, *,
+                   blank: int = 0, zero_infinity: bool = True, scale: Optional[torch.Tensor] = None,
+                   want_log_probs: bool = True, want_grad: bool = False, prepend_blank: bool = False,
+                   blank_value: float = 0.0, vocab_len: Optional[torch.Tensor] = None):
+    """Returns dict(nll [B], loss_sum [1], log_probs [T,B,Veff] | None, grad [B,T,V] | None)."""
+    _req(logits, F32, "logits"); _req(targets, I32, "targets")
+    _req(input_len, I32, "input_len"); _req(target_len, I32, "target_len")
+    B, T, V = logits.shape
+    Smax = targets.shape[1]
+    Veff = V + int(prepend_blank)
+    dev = logits.device
+    L = _lib.load()
+    nbytes = L.aptai_ctc_workspace_bytes(B, T, Smax)
+    if nbytes == 0:
+        raise ValueError(f"logsoftmax_ctc: Smax={Smax} unsupported (limit 127 labels)")
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    nll = torch.empty((B,), dtype=F32, device=dev)
+    loss_sum = torch.empty((1,), dtype=F32, device=dev)
+    lp = torch.empty((T, B, Veff), dtype=F32, device=dev) if want_log_probs else None
+    grad = torch.empty((B, T, V), dtype=F32, device=dev) if want_grad else None
+    if scale is not None:
+        _req(scale, F32, "scale")
+    if vocab_len is not None:
+        _req(vocab_len, I32, "vocab_len")
+    check(L.aptai_logsoftmax_ctc_ex(logits.data_ptr(), B, T, V, int(prepend_blank), float(blank_value),
+                                    _ptr(vocab_len), targets.data_ptr(), Smax, input_len.data_ptr(),
+                                    target_len.data_ptr(), blank, int(zero_infinity), _ptr(lp), nll.data_ptr(),
+                                    _ptr(scale), loss_sum.data_ptr(), _ptr(grad), ws.data_ptr(), nbytes, _stream()),
+          "logsoftmax_ctc")
+    return {"nll": nll, "loss_sum": loss_sum, "log_probs": lp, "grad": grad}
+
+
+def ctc_viterbi(log_probs: torch.Tensor, targets: torch.Tensor, input_len: torch.Tensor, target_len: torch.Tensor,
+                blank: int = 0):
+    """log_probs fp32 [B,T,C]; returns (paths int32 [B,T], scores fp32 [B,T], status int32 [B])."""
+    _req(log_probs, F32, "log_probs"); _req(targets, I32, "targets")
+    _req(input_len, I32, "input_len"); _req(target_len, I32, "target_len")
+    B, T, Cc = log_probs.shape
+    Smax = targets.shape[1]
+    dev = log_probs.device
+    L = _lib.load()
+    nbytes = L.aptai_viterbi_workspace_bytes(B, T, Smax)
+    ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    paths = torch.empty((B, T), dtype=I32, device=dev)
+    scores = torch.empty((B, T), dtype=F32, device=dev)
+    status = torch.empty((B,), dtype=I32, device=dev)
+    check(L.aptai_ctc_viterbi_f32(log_probs.data_ptr(), targets.data_ptr(), input_len.data_ptr(), target_len.data_ptr(),
+                                  B, T, Cc, Smax, blank, paths.data_ptr(), scores.data_ptr(), status.data_ptr(),
+                                  ws.data_ptr(), nbytes, _stream()), "ctc_viterbi")
+    return paths, scores, status
+
+
+def ctc_greedy(logits: torch.Tensor, input_len: Optional[torch.Tensor], blank: int = 0, maxtok: Optional[int] = None):
+    _req(logits, F32, "logits")
+    B, T, V = logits.shape
+    maxtok = maxtok or T
+    dev = logits.device
+    tokens = torch.zeros((B, maxtok), dtype=I32, device=dev)
+    frames = torch.zeros((B, maxtok), dtype=I32, device=dev)
+    ntok = torch.empty((B,), dtype=I32, device=dev)
+    check(_lib.load().aptai_ctc_greedy(logits.data_ptr(), B, T, V, _ptr(input_len), blank, tokens.data_ptr(),
+                                       frames.data_ptr(), ntok.data_ptr(), maxtok, _stream()), "ctc_greedy")
+    return tokens, frames, ntok

@@ -1,0 +1,166 @@
+/* aptai_b200 — C ABI of the B200-native APTAI hot path.
+ *
+ * The reference (tobwei/APTAI) has no FFI of its own: its hot path is the Python nn.Module API of
+ * models/aptai.py, models/w2v2_pr.py, models/force_aptai.py, models/modules.py, which in turn calls
+ * transformers.Wav2Vec2Model and torch ops.  Each entry point below replaces one library call
+ * the reference makes on that path; the call site it replaces is cited next to it ("HF:n" = transformers 5.5.0
+ * models/wav2vec2/modeling_wav2vec2.py line n).  The Python facade in aptai_b200/ binds these with ctypes.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is DEVICE memory unless the name ends in _host
+ *  - the caller (PyTorch) owns all buffers; nothing here allocates device memory
+ *  - all launches are asynchronous on `stream` (a cudaStream_t passed as void*)
+ *  - return 0 on success, negative aptai_status on argument errors, positive cudaError_t on launch errors;
+ *    aptai_last_error_string() returns a thread-local message
+ *  - there is no CPU fallback: on a device that is not sm_100 every compute call returns APTAI_ERR_ARCH
+ */
+#ifndef APTAI_B200_H
+#define APTAI_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum aptai_status {
+  APTAI_OK = 0,
+  APTAI_ERR_ARG = -1,       /* bad shape / null pointer / misalignment */
+  APTAI_ERR_ARCH = -2,      /* device is not sm_100 */
+  APTAI_ERR_WORKSPACE = -3, /* workspace too small */
+  APTAI_ERR_DRIVER = -4     /* cuTensorMapEncodeTiled unavailable / failed */
+};
+
+int aptai_version(void);
+const char* aptai_last_error_string(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+int64_t aptai_launch_count(void);
+
+/* ------------------------------------------------------------------ tcgen05 GEMM family ---------------------
+ * One kernel family serves nn.Linear (HF:429-434, 524-547, 566-573), the strided conv layers 1..6 as implicit
+ * GEMM (HF:254-323) and the grouped positional conv (HF:329-368).
+ *
+ *   out[s, r, n] = epilogue( sum_{tap, c} A[s, (r*P + tap), colbase(n) + c] * W[n, tap*kb_per_tap*64 + c] )
+ *
+ * A is bf16, logically [segs][a_rows][a_cols] with row stride a_row_stride and segment stride a_seg_stride
+ * (elements).  W is bf16 [N][K] row-major (K contiguous), K = taps*kb_per_tap*64.
+ * Plain GEMM: segs=1, P=1, taps=1.  Conv k/stride 2: P=2, taps=k, kb_per_tap=C_in/64.
+ * Grouped pos-conv: taps=128, kb_per_tap=1, block_n = group width, a_col_per_nblk = group width.
+ * epilogue: (+bias[n]) -> (LayerNorm over the N=512 row, ln=1) -> (GELU, act=1) -> (+residual) ->
+ *           (padded rows written as 0, see seg_valid_rows) -> fp32 and/or bf16 store at row s*out_seg_stride + r.
+ */
+typedef struct aptai_gemm_args {
+  const void* a;          /* bf16 */
+  int64_t a_row_stride;   /* elements */
+  int64_t a_seg_stride;   /* elements */
+  int32_t a_rows;         /* physical rows per segment the TMA may touch */
+  int32_t a_cols;         /* channels per physical row */
+  int32_t P;              /* row step per output row (conv stride) */
+  int32_t taps;
+  int32_t kb_per_tap;     /* 64-element K blocks per tap */
+  int32_t a_col_per_nblk; /* channel offset per n tile (grouped conv), else 0 */
+  const void* w;          /* bf16 [N][K] */
+  int32_t N;
+  int32_t block_n;        /* 0 = choose; otherwise one of 48, 64, 128, 256 (512 when ln=1) */
+  int32_t segs;
+  int32_t rows_per_seg;   /* output rows per segment */
+  const float* bias;      /* [N] or NULL */
+  const float* gamma;     /* [N], ln=1 only */
+  const float* beta;      /* [N], ln=1 only */
+  const float* residual;  /* fp32, same row mapping and ldo as the outputs, or NULL */
+  float* out_f32;         /* or NULL */
+  void* out_bf16;         /* or NULL */
+  int64_t ldo;            /* output row pitch in elements */
+  int64_t out_seg_stride; /* output rows between segments */
+  const int32_t* seg_valid_rows; /* [out_rows / mask_seg_rows] or NULL: valid rows per masking segment */
+  int32_t mask_seg_rows;  /* output row o = s*out_seg_stride + r is zeroed when o % mask_seg_rows >= seg_valid_rows[o / mask_seg_rows] */
+  int32_t act;            /* 0 none, 1 erf-GELU */
+  int32_t ln;             /* 0/1: LayerNorm over the full row (requires N == 512) */
+  float ln_eps;
+} aptai_gemm_args;
+
+int aptai_gemm_bf16(const aptai_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------ feature encoder front end ---------------
+ * conv layer 0 (1 -> 512 channels, kernel 10, stride 5) + norm + GELU, channels-last bf16 output [B][T0][512].
+ * norm=1: LayerNorm over channels per frame (HF:281-299).  norm=2: GroupNorm(512 groups) over time per
+ * channel, statistics over all T0 frames of the padded row (HF:308-323).  norm=0: none (HF:260-272).
+ * w is fp32 [512][10]; bias may be NULL.  stats_ws: 2*B*512 floats (norm=2 only).
+ */
+int aptai_conv0_norm_gelu(const float* wav, int B, int64_t L, const float* w, const float* bias,
+                          const float* gamma, const float* beta, int norm, float eps, void* out_bf16, int T0,
+                          float* stats_ws, void* stream);
+
+/* LayerNorm over the last dim (HF:431, 600-602, 639, 645, 692, 792): fp32 or bf16 in, fp32 and/or bf16 out. */
+int aptai_layernorm(const void* x, int x_is_bf16, int64_t rows, int cols, const float* gamma, const float* beta,
+                    float eps, float* out_f32, void* out_bf16, void* stream);
+
+/* fp32 [segs][rows][cols] -> bf16 [segs][halo+rows+halo][cols] with zeroed halo rows (HF:371-379 'same' pad). */
+int aptai_cast_pad_bf16(const float* x, int segs, int rows, int cols, int halo, void* out_bf16, void* stream);
+
+/* weight-norm fold of the positional conv (torch parametrizations.weight_norm, dim=2; HF:336-358):
+ * w[o][c][j] = g[j] * v[o][c][j] / ||v[:, :, j]||, written bf16 as [H][taps][cpad] (cpad >= cin, zero padded). */
+int aptai_posconv_fold(const float* g, const float* v, int H, int cin, int taps, int cpad, void* w_bf16,
+                       float* norm_ws, void* stream);
+
+/* ------------------------------------------------------------------ attention (HF:500-549, SDPA) ------------
+ * qkv: bf16 [B*T][3*H] (q | k | v, q pre-scaled by head_dim^-0.5), ctx: bf16 [B*T][H], head_dim 64.
+ * Keys t >= key_len[b] are masked; every query row is computed (padded queries attend to valid keys, HF:438-463).
+ */
+int aptai_attention_fwd(const void* qkv, void* ctx, const int32_t* key_len, int B, int T, int heads, void* stream);
+
+/* ------------------------------------------------------------------ heads and post-processing ---------------
+ * APTAI heads (models/aptai.py:43-55,83-86,105-106): tv = tanh(h) W_tv^T + b_tv (9), logits = leaky_relu(h)
+ * W_phn^T + b_phn (V), pred = argmax (first maximum).  act_a/act_b: 0 identity, 1 tanh, 2 leaky_relu(0.01).
+ * Either head may be absent (n = 0).  h is fp32 [rows][H].
+ */
+int aptai_heads(const float* h, int64_t rows, int H, const float* wa, const float* ba, int na, int act_a,
+                float* out_a, const float* wb, const float* bb, int nb, int act_b, float* out_b,
+                int64_t* argmax_b, void* stream);
+
+/* LowPassFilterLayer (models/modules.py:46-61): per channel 51-tap FIR, zero 'same' padding along T, fp64
+ * accumulation of the fp64 taps, fp32 in/out [B][T][C]. */
+int aptai_lowpass_fir(const float* x, int B, int T, int C, const double* taps, int ntaps, float* y, void* stream);
+
+/* masked MSE + cross entropy of APTAI.forward (models/aptai.py:89-102).  out3 = {loss, mse, ce}. */
+int aptai_masked_mse_ce(const float* tv_pred, const float* tv_tgt, const float* logits, const int64_t* phn_tgt,
+                        int64_t rows, int ntv, int V, float* accum_ws, float* out3, void* stream);
+
+/* ------------------------------------------------------------------ CTC / alignment -------------------------
+ * log_softmax over V then CTC loss and gradient w.r.t. the logits (models/w2v2_pr.py:59-81, F.ctc_loss with
+ * zero_infinity; models/modules.py:93-116 via per-utterance lengths).  logits fp32 [B][T][V] (ld = V).
+ * targets int32 [B][Smax]; entries at s >= target_len[b] are ignored.  log_probs_tbv (optional) fp32 [T][B][V].
+ * nll[b] = -log p(target|input) (0 where infeasible and zero_infinity).  grad (optional) fp32 [B][T][V] is
+ * d(sum_b scale[b]*nll[b])/d logits, scale may be NULL (= 1).  Workspace: aptai_ctc_workspace_bytes().
+ */
+size_t aptai_ctc_workspace_bytes(int B, int T, int Smax);
+int aptai_logsoftmax_ctc(const float* logits, int B, int T, int V, const int32_t* targets, int Smax,
+                         const int32_t* input_len, const int32_t* target_len, int blank, int zero_infinity,
+                         float* log_probs_tbv, float* nll, const float* scale, float* grad, void* ws,
+                         size_t ws_bytes, void* stream);
+
+/* Extended form used by ForwardSumLoss (models/modules.py:93-116): prepend_blank=1 makes class 0 a virtual column
+ * of constant value blank_value (F.pad(..., value=blank_logprob)), class c>=1 is logits column c-1; vocab_len[b]
+ * (optional) restricts the log-softmax of utterance b to its first vocab_len[b] classes; loss_sum (optional)
+ * receives sum_b scale[b]*nll[b].  grad is always w.r.t. the physical logits columns. */
+int aptai_logsoftmax_ctc_ex(const float* logits, int B, int T, int V, int prepend_blank, float blank_value,
+                            const int32_t* vocab_len, const int32_t* targets, int Smax, const int32_t* input_len,
+                            const int32_t* target_len, int blank, int zero_infinity, float* log_probs_tbv,
+                            float* nll, const float* scale, float* loss_sum, float* grad, void* ws,
+                            size_t ws_bytes, void* stream);
+
+/* CTC Viterbi forced alignment, bit-exact with torchaudio.functional.forced_align.
+ * log_probs fp32 [B][T][C]; paths int32 [B][T] (frames t >= input_len[b] get -1); scores fp32 [B][T]. */
+size_t aptai_viterbi_workspace_bytes(int B, int T, int Smax);
+int aptai_ctc_viterbi_f32(const float* log_probs, const int32_t* targets, const int32_t* input_len,
+                          const int32_t* target_len, int B, int T, int C, int Smax, int blank, int32_t* paths,
+                          float* scores, int32_t* status, void* ws, size_t ws_bytes, void* stream);
+
+/* greedy CTC collapse on device (argmax -> merge repeats -> drop blank); models/w2v2_pr.py:143-159 next-row. */
+int aptai_ctc_greedy(const float* logits, int B, int T, int V, const int32_t* input_len, int blank,
+                     int32_t* tokens, int32_t* token_frames, int32_t* ntokens, int maxtok, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* APTAI_B200_H */

@@ -1,0 +1,55 @@
+"""End-to-end parity of the CUDA encoder (aptai_b200.backbone) against the CPU oracle on identical weights."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from aptai_b200.backbone import Wav2Vec2Backbone
+from aptai_b200.config import W2V2Config
+from oracle import w2v2 as ow
+from oracle.weights import backbone_state_dict, waveforms
+
+
+def _cfg(variant, **kw):
+    base = dict(hidden_size=256, num_hidden_layers=2, num_attention_heads=4, intermediate_size=512,
+                num_conv_pos_embedding_groups=4)
+    base.update(kw)
+    if variant == "layer":
+        return W2V2Config.large(**base)
+    return W2V2Config.base(**base)
+
+
+def _run(cfg, lens, L, cuda):
+    sd = backbone_state_dict(cfg, seed=0)
+    wav = waveforms(len(lens), L, lens, seed=1234)
+    ref = ow.forward(sd, cfg, wav, lens)
+    m = Wav2Vec2Backbone(cfg)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(cuda).eval()
+    out = m(wav.to(cuda), attention_mask=torch.tensor(lens, device=cuda)[:, None], output_hidden_states=True)
+    return ref, out
+
+
+@pytest.mark.parametrize("variant", ["layer", "group"])
+def test_tiny_encoder_matches_oracle(cuda, variant):
+    cfg = _cfg(variant)
+    lens = [16000, 12000, 9000]
+    ref, out = _run(cfg, lens, 16000, cuda)
+    assert len(out.hidden_states) == cfg.num_hidden_layers + 1
+    for i, (r, o) in enumerate(zip(ref, out.hidden_states)):
+        err = (o.cpu() - r).abs().max().item()
+        assert err < 6e-2, f"{variant}: hidden[{i}] max abs err {err}"
+    # padded frames are zeroed before the encoder but still computed afterwards (HF:679-682): compare all frames
+    err = (out.last_hidden_state.cpu() - ref[-1]).abs()
+    assert err.mean().item() < 6e-3
+
+
+@pytest.mark.parametrize("variant,H,heads,F", [("layer", 1024, 16, 4096), ("group", 768, 12, 3072)])
+def test_full_width_two_layers(cuda, variant, H, heads, F):
+    """Real hidden sizes (pos-conv group widths 64 and 48, N tiles of 256) with two layers to keep the CPU oracle fast."""
+    cfg = _cfg(variant, hidden_size=H, num_attention_heads=heads, intermediate_size=F, num_hidden_layers=2,
+               num_conv_pos_embedding_groups=16)
+    lens = [32000, 20000]
+    ref, out = _run(cfg, lens, 32000, cuda)
+    err = (out.last_hidden_state.cpu() - ref[-1]).abs()
+    assert err.max().item() < 6e-2 and err.mean().item() < 6e-3, (err.max().item(), err.mean().item())

@@ -1,0 +1,102 @@
+"""Parity of the tcgen05 GEMM family (plain Linear, implicit-GEMM conv, grouped pos-conv, fused LN epilogue)
+against fp32 torch references on bf16-rounded operands.  Calls go through the C ABI (aptai_b200.ops -> ctypes)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from aptai_b200 import ops
+
+
+def _rand(shape, dev, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dev)
+
+
+def _close_bf16(out, ref, what, atol=2e-2, rtol=2e-2):
+    out, ref = out.float(), ref.float()
+    err = (out - ref).abs()
+    tol = atol + rtol * ref.abs()
+    bad = (err > tol).sum().item()
+    assert bad == 0, f"{what}: {bad} mismatches, max err {err.max().item():.4g}"
+
+
+@pytest.mark.parametrize("M,K,N", [(128, 64, 256), (300, 512, 1024), (1000, 1024, 3072), (777, 768, 2304),
+                                   (129, 256, 128), (64, 128, 64), (5000, 4096, 1024)])
+def test_linear_bias(cuda, M, K, N):
+    a = _rand((M, K), cuda, 1.0, 1).bfloat16()
+    w = _rand((N, K), cuda, 0.05, 2).bfloat16()
+    b = _rand((N,), cuda, 0.5, 3)
+    o32, o16 = ops.linear(a, w, b, want_f32=True, want_bf16=True)
+    ref = a.float() @ w.float().t() + b
+    torch.testing.assert_close(o32, ref, atol=2e-3, rtol=2e-3)
+    _close_bf16(o16, ref, "bf16 out")
+
+
+def test_linear_gelu_residual_mask(cuda):
+    B, T, K, N = 3, 210, 512, 768
+    M = B * T
+    a = _rand((M, K), cuda, 1.0, 4).bfloat16()
+    w = _rand((N, K), cuda, 0.05, 5).bfloat16()
+    b = _rand((N,), cuda, 0.5, 6)
+    res = _rand((M, N), cuda, 1.0, 7)
+    _, o16 = ops.linear(a, w, b, act=1)
+    ref = F.gelu(a.float() @ w.float().t() + b)
+    _close_bf16(o16, ref, "gelu")
+    o32, _ = ops.linear(a, w, b, residual=res, want_f32=True, want_bf16=False)
+    torch.testing.assert_close(o32, a.float() @ w.float().t() + b + res, atol=2e-3, rtol=2e-3)
+    # in-place residual (out aliases residual) + padded-row zeroing
+    lens = torch.tensor([210, 100, 1], dtype=torch.int32, device=cuda)
+    h = res.clone()
+    ops.linear(a, w, b, residual=h, out_f32=h, want_bf16=False, seg_rows=T, seg_valid_rows=lens)
+    ref = (a.float() @ w.float().t() + b + res).view(B, T, N)
+    for i, n in enumerate(lens.tolist()):
+        ref[i, n:] = 0
+    torch.testing.assert_close(h.view(B, T, N), ref, atol=2e-3, rtol=2e-3)
+
+
+@pytest.mark.parametrize("k,T_in,B,ln", [(3, 801, 2, True), (3, 640, 3, False), (2, 399, 2, True), (2, 130, 1, False),
+                                         (3, 2563, 2, True)])
+def test_conv_igemm(cuda, k, T_in, B, ln):
+    C = 512
+    x = ops.alloc_rows_bf16(B, T_in, C, cuda)
+    x.copy_(_rand((B, T_in, C), cuda, 1.0, 8).bfloat16())
+    w = _rand((C, C, k), cuda, (2.0 / (C * k)) ** 0.5, 9)                  # torch layout [out][in][k]
+    bias = _rand((C,), cuda, 0.1, 10)
+    gam = 1 + _rand((C,), cuda, 0.1, 11)
+    bet = _rand((C,), cuda, 0.1, 12)
+    wk = w.permute(0, 2, 1).reshape(C, k * C).bfloat16().contiguous()
+    y = ops.conv_igemm(x, wk, bias, k, 2, ln_gamma=gam if ln else None, ln_beta=bet if ln else None, act=1)
+    ref = F.conv1d(x.float().transpose(1, 2), w.bfloat16().float(), bias, stride=2)
+    if ln:
+        ref = F.layer_norm(ref.transpose(1, 2), (C,), gam, bet, 1e-5).transpose(1, 2)
+    ref = F.gelu(ref).transpose(1, 2)
+    assert y.shape == ref.shape
+    _close_bf16(y, ref, "conv_igemm")
+
+
+@pytest.mark.parametrize("H,groups,T,B", [(1024, 16, 199, 2), (768, 16, 130, 2), (256, 4, 77, 3)])
+def test_posconv(cuda, H, groups, T, B):
+    taps = 128
+    gw = H // groups
+    x = _rand((B, T, H), cuda, 1.0, 13)
+    v = _rand((H, gw, taps), cuda, 2 * (1.0 / (taps * H)) ** 0.5, 14)
+    g = torch.linalg.vector_norm(v, dim=(0, 1), keepdim=True) * (1 + _rand((1, 1, taps), cuda, 0.05, 15))
+    bias = _rand((H,), cuda, 0.1, 16)
+    wf = ops.posconv_fold(g.contiguous(), v.contiguous(), 64)
+    w_ref = g * v / torch.linalg.vector_norm(v, dim=(0, 1), keepdim=True)
+    # fold check (bf16 rounding of the exact quotient)
+    wf_ref = torch.zeros((H, taps, 64), device=cuda)
+    wf_ref[:, :, :gw] = w_ref.permute(0, 2, 1)
+    torch.testing.assert_close(wf.float().view(H, taps, 64), wf_ref.bfloat16().float(), atol=1e-3, rtol=1e-2)
+    xp = ops.cast_pad(x, taps // 2)
+    assert xp.shape == (B, T + taps, H)
+    assert torch.equal(xp[:, taps // 2: taps // 2 + T], x.bfloat16())
+    assert float(xp[:, : taps // 2].abs().max()) == 0 and float(xp[:, taps // 2 + T:].abs().max()) == 0
+    h = x.clone().view(B * T, H)
+    ops.posconv(xp, wf, bias, h, T, H, groups, taps, h)
+    pos = F.conv1d(x.bfloat16().float().transpose(1, 2), w_ref.bfloat16().float(), bias, padding=taps // 2,
+                   groups=groups)[:, :, :-1]
+    ref = x + F.gelu(pos).transpose(1, 2)
+    torch.testing.assert_close(h.view(B, T, H), ref, atol=5e-3, rtol=5e-3)

@@ -1,0 +1,199 @@
+"""Parity of the HBM-bound kernels, attention and the alignment kernels, through the C ABI."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from aptai_b200 import ops
+from oracle import ctc as octc
+from oracle import heads as oheads
+
+
+def _rand(shape, dev, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dev)
+
+
+@pytest.mark.parametrize("norm,bias", [(1, True), (2, False), (2, True), (0, False)])
+def test_conv0(cuda, norm, bias):
+    B, L = 3, 16000
+    lens = [16000, 12345, 4000]
+    wav = _rand((B, L), cuda, 0.1, 1)
+    for b, n in enumerate(lens):
+        wav[b, n:] = 0
+    w = _rand((512, 1, 10), cuda, (2.0 / 10) ** 0.5, 2)
+    bs = _rand((512,), cuda, 0.2, 3) if bias else None
+    gam = 1 + _rand((512,), cuda, 0.1, 4)
+    bet = _rand((512,), cuda, 0.1, 5)
+    y = ops.conv0(wav, w.view(512, 10).contiguous(), bs, gam, bet, norm)
+    ref = F.conv1d(wav[:, None], w, bs, stride=5)
+    if norm == 1:
+        ref = F.layer_norm(ref.transpose(1, 2), (512,), gam, bet, 1e-5).transpose(1, 2)
+    elif norm == 2:
+        ref = F.group_norm(ref, 512, gam, bet, 1e-5)
+    ref = F.gelu(ref).transpose(1, 2)
+    assert y.shape == ref.shape
+    err = (y.float() - ref).abs()
+    tol = 1e-2 + 1e-2 * ref.abs()
+    assert (err > tol).sum().item() == 0, f"max err {err.max().item()}"
+    # beyond bf16 rounding the fp32 math must agree closely: compare in fp32 before rounding via mean error
+    assert err.mean().item() < 2e-3
+
+
+@pytest.mark.parametrize("cols", [512, 768, 1024, 256])
+@pytest.mark.parametrize("in_bf16", [False, True])
+def test_layernorm(cuda, cols, in_bf16):
+    rows = 1000
+    x = _rand((rows, cols), cuda, 2.0, 6) + 0.5
+    if in_bf16:
+        x = x.bfloat16()
+    g = 1 + _rand((cols,), cuda, 0.1, 7)
+    b = _rand((cols,), cuda, 0.1, 8)
+    o32, o16 = ops.layernorm(x, g, b, 1e-5, want_f32=True, want_bf16=True)
+    ref = F.layer_norm(x.float(), (cols,), g, b, 1e-5)
+    torch.testing.assert_close(o32, ref, atol=2e-5, rtol=2e-5)
+    torch.testing.assert_close(o16.float(), ref.bfloat16().float(), atol=2e-2, rtol=1e-2)
+
+
+@pytest.mark.parametrize("B,T,heads,lens", [(2, 199, 16, [199, 150]), (3, 64, 12, [64, 1, 33]), (1, 999, 4, [999]),
+                                            (2, 130, 2, [70, 130])])
+def test_attention(cuda, B, T, heads, lens):
+    H = heads * 64
+    qkv = _rand((B * T, 3 * H), cuda, 1.0, 9).bfloat16()
+    kl = torch.tensor(lens, dtype=torch.int32, device=cuda)
+    ctx = ops.attention(qkv, kl, B, T, heads)
+    q, k, v = qkv.float().view(B, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    s = q @ k.transpose(-1, -2)                      # q is expected pre-scaled
+    mask = torch.arange(T, device=cuda)[None, :] < kl[:, None]
+    s = s.masked_fill(~mask[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * T, H)
+    torch.testing.assert_close(ctx.float(), ref, atol=2e-2, rtol=2e-2)
+
+
+def test_heads_lowpass_losses(cuda):
+    B, T, H, V = 2, 150, 1024, 46
+    h = _rand((B, T, H), cuda, 1.0, 10)
+    tvw, tvb = _rand((9, H), cuda, 0.03, 11), _rand((9,), cuda, 0.03, 12)
+    pw, pb = _rand((V, H), cuda, 0.03, 13), _rand((V,), cuda, 0.03, 14)
+    taps = oheads.lowpass_taps().to(cuda)
+    tv_raw, logits, am = ops.heads(h.view(B * T, H), tvw, tvb, ops.ACT_TANH, pw, pb, ops.ACT_LEAKY)
+    r_raw, r_tv, r_logits = oheads.aptai_heads(h.cpu(), tvw.cpu(), tvb.cpu(), pw.cpu(), pb.cpu(), taps.cpu())
+    torch.testing.assert_close(tv_raw.cpu().view(B, T, 9), r_raw, atol=2e-5, rtol=1e-4)
+    torch.testing.assert_close(logits.cpu().view(B, T, V), r_logits, atol=2e-5, rtol=1e-4)
+    assert torch.equal(am.cpu().view(B, T), torch.argmax(logits.cpu().view(B, T, V), -1))
+    tv = ops.lowpass(tv_raw.view(B, T, 9), taps)
+    torch.testing.assert_close(tv.cpu(), oheads.lowpass(tv_raw.cpu().view(B, T, 9), taps.cpu()), atol=1e-6, rtol=1e-5)
+    # losses
+    g = torch.Generator().manual_seed(15)
+    phn = torch.randint(1, V, (B, T), generator=g)
+    phn[1, 100:] = 0
+    tgt = torch.randn((B, T, 9), generator=g)
+    tgt[1, 100:] = -100.0
+    out = ops.masked_mse_ce(tv.view(B * T, 9), tgt.to(cuda).view(B * T, 9).contiguous(), logits, phn.to(cuda).view(-1))
+    loss, mse, ce = oheads.aptai_losses(tv.cpu(), logits.cpu().view(B, T, V), phn, tgt)
+    torch.testing.assert_close(out.cpu(), torch.stack([loss, mse, ce]), atol=1e-5, rtol=1e-5)
+
+
+def _ctc_case(B, T, V, Smax, seed, repeats=False):
+    rng = np.random.default_rng(seed)
+    logits = rng.standard_normal((B, T, V)).astype(np.float32) * 2
+    tl = rng.integers(1, Smax + 1, size=B).astype(np.int32)
+    il = rng.integers(max(2, T // 2), T + 1, size=B).astype(np.int32)
+    il[0] = T
+    tg = np.full((B, Smax), -100, dtype=np.int32)
+    for b in range(B):
+        tg[b, : tl[b]] = rng.integers(1, V, size=tl[b])
+        if repeats and tl[b] > 3:
+            tg[b, 1] = tg[b, 0]
+            tg[b, 3] = tg[b, 2]
+    return logits, tg, il, tl
+
+
+@pytest.mark.parametrize("B,T,V,Smax,rep", [(4, 60, 12, 9, True), (16, 399, 46, 59, False), (3, 50, 46, 100, True)])
+def test_logsoftmax_ctc(cuda, B, T, V, Smax, rep):
+    logits, tg, il, tl = _ctc_case(B, T, V, Smax, 3, rep)
+    if B >= 3:
+        tl[1] = min(Smax, il[1] + 1)            # infeasible: more labels than frames -> zero_infinity
+        tg[1, : tl[1]] = 1 + (np.arange(tl[1]) % (V - 1))
+    o = octc.ctc_loss_grad(logits, tg, il, tl, blank=0, zero_infinity=True, reduction="mean")
+    scale = torch.from_numpy(o["scale"].astype(np.float32)).to(cuda)
+    r = ops.logsoftmax_ctc(torch.from_numpy(logits).to(cuda), torch.from_numpy(tg).to(cuda),
+                           torch.from_numpy(il).to(cuda), torch.from_numpy(tl).to(cuda), blank=0, zero_infinity=True,
+                           scale=scale, want_log_probs=True, want_grad=True)
+    nll = r["nll"].cpu().numpy()
+    np.testing.assert_allclose(nll, o["nll"], rtol=1e-3, atol=1e-3)
+    assert abs(float(r["loss_sum"].cpu()) - o["loss"]) <= 1e-3 * abs(o["loss"]) + 1e-5
+    np.testing.assert_allclose(r["log_probs"].cpu().numpy(), o["log_probs"], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(r["grad"].cpu().numpy(), o["grad"], rtol=1e-3, atol=2e-5)
+
+
+def test_forward_sum(cuda):
+    """ForwardSumLoss (models/modules.py:77-117): prepended blank column, per-utterance class count."""
+    rng = np.random.default_rng(5)
+    B, T, N = 3, 80, 60
+    att = torch.log_softmax(torch.from_numpy(rng.standard_normal((B, T, N)).astype(np.float32)), -1)
+    text = np.array([30, 59, 5], dtype=np.int32)
+    mel = np.array([80, 70, 33], dtype=np.int32)
+    loss_ref, nll_ref = octc.forward_sum_loss(att[:, None].numpy(), text, mel, -1.0)
+    tg = torch.arange(1, N + 1, dtype=torch.int32)[None].repeat(B, 1).contiguous().to(cuda)
+    scale = torch.from_numpy((1.0 / (np.maximum(text, 1) * B)).astype(np.float32)).to(cuda)
+    r = ops.logsoftmax_ctc(att.to(cuda).contiguous(), tg, torch.from_numpy(mel).to(cuda), torch.from_numpy(text).to(cuda),
+                           blank=0, zero_infinity=True, scale=scale, want_log_probs=False, prepend_blank=True,
+                           blank_value=-1.0, vocab_len=torch.from_numpy(text + 1).to(cuda))
+    np.testing.assert_allclose(r["nll"].cpu().numpy(), nll_ref, rtol=1e-3)
+    assert abs(float(r["loss_sum"].cpu()) - loss_ref) <= 1e-3 * abs(loss_ref)
+
+
+@pytest.mark.parametrize("B,T,C,Smax", [(64, 399, 46, 59), (8, 40, 5, 12), (4, 999, 46, 100)])
+def test_viterbi_bit_exact(cuda, B, T, C, Smax):
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((B, T, C)).astype(np.float32)
+    x[1] = 0.0                                             # all ties
+    x[2] = rng.integers(0, 3, size=(T, C)).astype(np.float32)   # heavy ties
+    lp = torch.log_softmax(torch.from_numpy(x), -1)
+    tl = rng.integers(1, Smax + 1, size=B).astype(np.int32)
+    il = rng.integers(max(2 * Smax, T // 2), T + 1, size=B).astype(np.int32) if T >= 4 * Smax else np.full(B, T, np.int32)
+    il[0] = T
+    tg = np.zeros((B, Smax), dtype=np.int32)
+    for b in range(B):
+        tl[b] = min(tl[b], il[b] // 2)
+        tg[b, : tl[b]] = rng.integers(1, C, size=tl[b])
+        if tl[b] > 2:
+            tg[b, 1] = tg[b, 0]
+    paths, scores, status = ops.ctc_viterbi(lp.to(cuda).contiguous(), torch.from_numpy(tg).to(cuda),
+                                            torch.from_numpy(il).to(cuda), torch.from_numpy(tl).to(cuda), blank=0)
+    paths, scores, status = paths.cpu().numpy(), scores.cpu().numpy(), status.cpu().numpy()
+    for b in range(B):
+        p, s = octc.viterbi_align(lp[b, : il[b]].numpy(), tg[b, : tl[b]], blank=0)
+        assert status[b] == 0
+        assert np.array_equal(paths[b, : il[b]], p), f"utt {b}: path mismatch"
+        assert np.array_equal(scores[b, : il[b]], s), f"utt {b}: score mismatch"
+        assert (paths[b, il[b]:] == -1).all()
+
+
+def test_viterbi_known_answer_and_infeasible(cuda):
+    # uniform(T=6,C=3), targets [1,2] -> [1,2,2,2,2,2]
+    lp = torch.log_softmax(torch.zeros((2, 6, 3)), -1).to(cuda)
+    tg = torch.tensor([[1, 2, 0, 0, 0, 0, 0], [1, 1, 1, 1, 1, 1, 1]], dtype=torch.int32, device=cuda)
+    il = torch.tensor([6, 6], dtype=torch.int32, device=cuda)
+    tl = torch.tensor([2, 7], dtype=torch.int32, device=cuda)
+    paths, _, status = ops.ctc_viterbi(lp, tg, il, tl, blank=0)
+    assert paths[0].tolist() == [1, 2, 2, 2, 2, 2]
+    assert status.tolist() == [0, 1]
+
+
+def test_greedy(cuda):
+    rng = np.random.default_rng(13)
+    B, T, V = 5, 200, 46
+    x = rng.standard_normal((B, T, V)).astype(np.float32)
+    x[:, :, 0] += 1.5
+    lens = np.array([200, 150, 1, 77, 33], dtype=np.int32)
+    tok, frm, n = ops.ctc_greedy(torch.from_numpy(x).to(cuda), torch.from_numpy(lens).to(cuda), blank=0)
+    for b in range(B):
+        t_ref, f_ref = octc.greedy_decode(x[b, : lens[b]], blank=0)
+        nb = int(n[b])
+        assert nb == len(t_ref)
+        assert np.array_equal(tok[b, :nb].cpu().numpy(), t_ref)
+        assert np.array_equal(frm[b, :nb].cpu().numpy(), f_ref)
