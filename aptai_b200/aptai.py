@@ -1,0 +1,90 @@
+"""Drop-in for the reference's models/aptai.py (class APTAI) on the aptai_b200 kernels.
+
+Same constructor, same `forward` / `get_aptai_output` / `get_config` signatures, return keys and state_dict layout
+(`wav2vec2.*`, `tv_head.2.*`, `phn_head.2.*`, `tv_lowpass.lowpass.weight`).  The reference hard-codes a 24x1024
+backbone (`hidden_states[24]`, `nn.Linear(1024, ...)`, models/aptai.py:46,54,81,141); here both come from the
+config (`hidden_states[num_hidden_layers]`, `hidden_size`), which is identical for the 24x1024 case.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .backbone import Wav2Vec2Backbone
+from .modules import LowPassFilterLayer
+
+TV_NAMES = ("LA", "LP", "JA", "TTCL", "TTCD", "TMCL", "TMCD", "TBCL", "TBCD")
+
+
+class APTAI(nn.Module):
+    def __init__(self, device, vocab, huggingface_model_id, pretrain_cfg, cache_dir, phn_drop=0.1, tv_drop=0.1,
+                 freeze_feature_encoder=True):
+        super().__init__()
+        self.device = device
+        self.vocab = vocab
+        self.huggingface_model_id = huggingface_model_id
+        self.pretrain_cfg = pretrain_cfg
+        self.wav2vec2 = Wav2Vec2Backbone.from_pretrained(huggingface_model_id, config=pretrain_cfg,
+                                                         cache_dir=cache_dir).to(self.device)
+        self.wav2vec2.gradient_checkpointing_enable()
+        if freeze_feature_encoder:
+            self.wav2vec2.freeze_feature_encoder()
+        H = self.wav2vec2.cfg.hidden_size
+        # parameter containers with the reference's Sequential indices (Dropout, activation, Linear)
+        self.tv_head = nn.Sequential(nn.Dropout(tv_drop), nn.Tanh(), nn.Linear(H, 9))
+        self.tv_lowpass = LowPassFilterLayer(self.device, 10, 49, 9)
+        self.phn_head = nn.Sequential(nn.Dropout(phn_drop), nn.LeakyReLU(), nn.Linear(H, 46))
+
+    # ---------------------------------------------------------------------------------------------- kernels
+    @torch.no_grad()
+    def _heads(self, audio_inputs, audio_lengths):
+        """backbone -> fused TV/phoneme heads (+argmax) -> low-pass.  Returns tv [B,T,9], logits [B,T,46], pred [B,T]."""
+        if self.training and (self.tv_head[0].p > 0 or self.phn_head[0].p > 0):
+            raise NotImplementedError("aptai_b200: training-mode dropout/backward is not built yet; call .eval()")
+        out = self.wav2vec2(audio_inputs, attention_mask=audio_lengths.reshape(-1)[:, None], return_dict=True,
+                            output_hidden_states=False)
+        h = out.last_hidden_state                       # == hidden_states[num_hidden_layers]
+        B, T, H = h.shape
+        tvl, phl = self.tv_head[2], self.phn_head[2]
+        f = lambda p: p.detach().float().contiguous()
+        tv_raw, logits, pred = ops.heads(h.view(B * T, H), f(tvl.weight), f(tvl.bias), ops.ACT_TANH, f(phl.weight),
+                                         f(phl.bias), ops.ACT_LEAKY)
+        tv = self.tv_lowpass(tv_raw.view(B, T, 9))
+        return tv, logits.view(B, T, -1), pred.view(B, T)
+
+    def forward(self, epoch, audio_inputs, audio_lengths, phn_frames_49hz, LA, LP, JA, TTCL, TTCD, TMCL, TMCD, TBCL,
+                TBCD):
+        """models/aptai.py:58-115.  Loss values come from the fused masked-MSE/CE kernel."""
+        tv_targets = torch.stack([LA, LP, JA, TTCL, TTCD, TMCL, TMCD, TBCL, TBCD], dim=-1).float().contiguous()
+        tv, logits, pred = self._heads(audio_inputs, audio_lengths)
+        B, T, V = logits.shape
+        res = ops.masked_mse_ce(tv.view(B * T, 9), tv_targets.view(B * T, 9).to(tv.device),
+                                logits.view(B * T, V), phn_frames_49hz.reshape(-1).to(device=tv.device,
+                                                                                     dtype=torch.int64).contiguous())
+        return {"loss": res[0], "mse_loss": res[1], "ce_loss": res[2], "tvs_pred": tv, "phn_fc_pred": pred}
+
+    def get_config(self):
+        return {"device": self.device, "vocab": self.vocab, "huggingface_model_id": self.huggingface_model_id,
+                "pretrain_cfg": self.pretrain_cfg}
+
+    def get_aptai_output(self, wav):
+        """models/aptai.py:125-179 (including the (46,T,1) shape of `phn_fc_probs`, Appendix B)."""
+        self.eval()
+        dev = next(self.wav2vec2.parameters()).device
+        with torch.no_grad():
+            if type(wav) is torch.Tensor:
+                wav = wav[0]
+            wav_input = torch.as_tensor(np.asarray(wav), dtype=torch.float32).reshape(1, -1).to(dev)
+            wav_len = torch.tensor([wav_input.shape[1]], dtype=torch.int64, device=dev)
+            tv, logits, pred = self._heads(wav_input, wav_len)
+            probs = ops.softmax_rows(logits.contiguous())
+            tvs = tv[0].cpu().numpy()
+            tvs_pred = {n: list(tvs[:, i]) for i, n in enumerate(TV_NAMES)}
+            return {
+                "phn_fc_probs": probs.permute(2, 1, 0).cpu().numpy(),       # `.T` of a (1,T,46) tensor
+                "phn_fc_logits": logits[0].cpu().numpy(),
+                "phn_fc_pred": pred[0].cpu().numpy(),
+                "tvs_pred": tvs_pred,
+            }

@@ -143,6 +143,15 @@ class _Plan:
                 ln2_w=f(l.final_layer_norm.weight), ln2_b=f(l.final_layer_norm.bias)))
 
 
+_IN_MEMORY = {}
+
+
+def register_in_memory_checkpoint(name: str, state_dict) -> str:
+    """Offline stand-in for a hub id: `from_pretrained(name, ...)` loads this state dict (tests, benchmarks)."""
+    _IN_MEMORY[name] = state_dict
+    return name
+
+
 class Wav2Vec2Backbone(nn.Module):
     def __init__(self, config):
         super().__init__()
@@ -167,7 +176,9 @@ class Wav2Vec2Backbone(nn.Module):
             raise ValueError("Wav2Vec2Backbone.from_pretrained needs config=")
         m = cls(config)
         path = str(model_id)
-        if os.path.isdir(path):
+        if path in _IN_MEMORY:
+            m.load_state_dict(_IN_MEMORY[path], strict=True)
+        elif os.path.isdir(path):
             st = os.path.join(path, "model.safetensors")
             pt = os.path.join(path, "pytorch_model.bin")
             if os.path.exists(st):

@@ -254,6 +254,27 @@ __global__ void lowpass_kernel(const float* __restrict__ x, int T, int C, const 
   y[i] = static_cast<float>(acc);
 }
 
+// ---------------------------------------------------------------------------------------------- row softmax
+__global__ void softmax_rows_kernel(const float* __restrict__ x, long long rows, int V, int log_out,
+                                    float* __restrict__ y) {
+  // one warp per row (V is small: 46 phoneme classes or 60 phoneme slots)
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * V;
+  float m = -INFINITY;
+  for (int c = lane; c < V; c += 32) m = fmaxf(m, xr[c]);
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float s = 0.f;
+  for (int c = lane; c < V; c += 32) s += expf(xr[c] - m);
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float ls = logf(s);
+  for (int c = lane; c < V; c += 32) {
+    const float d = xr[c] - m;
+    y[row * V + c] = log_out ? d - ls : expf(d) / s;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- masked MSE + CE
 // accum: [0] sum sq err, [1] count tv, [2] sum ce, [3] count ce   (doubles)
 __global__ void mse_ce_kernel(const float* __restrict__ tv_pred, const float* __restrict__ tv_tgt,
@@ -381,6 +402,14 @@ extern "C" int aptai_lowpass_fir(const float* x, int B, int T, int C, const doub
   lowpass_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, ntaps * sizeof(double),
                    reinterpret_cast<cudaStream_t>(stream)>>>(x, T, C, taps, ntaps, y, total);
   return after_launch("lowpass_fir");
+}
+
+extern "C" int aptai_softmax_rows(const float* x, int64_t rows, int V, int log_out, float* y, void* stream) {
+  if (int rc = check_arch()) return rc;
+  APTAI_REQUIRE(x && y && rows >= 1 && V >= 1, "softmax_rows: bad arguments");
+  softmax_rows_kernel<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      x, rows, V, log_out, y);
+  return after_launch("softmax_rows");
 }
 
 extern "C" int aptai_masked_mse_ce(const float* tv_pred, const float* tv_tgt, const float* logits,

@@ -209,6 +209,15 @@ def lowpass(x: torch.Tensor, taps: torch.Tensor) -> torch.Tensor:
     return y
 
 
+def softmax_rows(x: torch.Tensor, log: bool = False) -> torch.Tensor:
+    _req(x, F32, "x")
+    V = x.shape[-1]
+    y = torch.empty_like(x)
+    check(_lib.load().aptai_softmax_rows(x.data_ptr(), x.numel() // V, V, int(log), y.data_ptr(), _stream()),
+          "softmax_rows")
+    return y
+
+
 def masked_mse_ce(tv_pred, tv_tgt, logits, phn_tgt) -> torch.Tensor:
     _req(tv_pred, F32, "tv_pred"); _req(tv_tgt, F32, "tv_tgt"); _req(logits, F32, "logits"); _req(phn_tgt, I64, "phn")
     rows = phn_tgt.numel()

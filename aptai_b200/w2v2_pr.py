@@ -1,0 +1,175 @@
+"""Drop-in for the reference's models/w2v2_pr.py (class Wav2Vec2_PR) on the aptai_b200 kernels.
+
+State dict: `wav2vec2.*`, `pr_head.{weight,bias}`.  `forward` = backbone -> Linear(H, vocab) -> fused
+log_softmax + CTC loss (mean, zero_infinity, blank from the config).  The target lengths are counted on the device
+(the reference loops over device scalars, models/w2v2_pr.py:62-70), and the conv encoder runs once in
+`get_embeddings` (the reference runs it twice, :129).
+
+Decoding: the reference builds a torchaudio/flashlight lexicon-free beam decoder on every call
+(:143-155); flashlight-text is not installable here, so the decoder is injectable (`phoneme_decoder=`) and
+defaults to the on-device greedy CTC collapse (with no LM and max-merge the best beam is the
+greedy path).  The flashlight wrapper is parity-unpinned.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .backbone import Wav2Vec2Backbone
+from .config import W2V2Config
+
+
+def idx_phonemes(vocab, seq):
+    """utility.py:200-210."""
+    keys, vals = list(vocab.keys()), list(vocab.values())
+    return [keys[vals.index(int(i))] for i in seq]
+
+
+class Wav2Vec2_PR(nn.Module):
+    def __init__(self, pretrain_cfg, cache_dir, huggingface_model_id, vocab=None,
+                 phoneme_decoder: Optional[Callable] = None):
+        super().__init__()
+        self.cache_dir = cache_dir
+        self.huggingface_model_id = huggingface_model_id
+        self.pretrain_cfg = pretrain_cfg
+        self.wav2vec2 = Wav2Vec2Backbone.from_pretrained(huggingface_model_id, config=pretrain_cfg,
+                                                         cache_dir=cache_dir)
+        self.wav2vec2.gradient_checkpointing_enable()
+        cfg = self.wav2vec2.cfg
+        self.dropout = nn.Dropout(cfg.final_dropout)
+        self.pr_head = nn.Linear(cfg.hidden_size, cfg.vocab_size)       # parameter container
+        self.vocab = vocab
+        self.phoneme_decoder = phoneme_decoder
+
+    # ---------------------------------------------------------------------------------------------- kernels
+    @torch.no_grad()
+    def _logits(self, input_values, input_lengths, output_hidden_states=False):
+        if self.training and self.dropout.p > 0:
+            raise NotImplementedError("aptai_b200: training-mode dropout/backward is not built yet; call .eval()")
+        out = self.wav2vec2(input_values, attention_mask=input_lengths.reshape(-1)[:, None], return_dict=True,
+                            output_hidden_states=output_hidden_states)
+        h = out.last_hidden_state
+        logits = self._head(h)
+        return out, h, logits
+
+    def _head(self, h):
+        B, T, H = h.shape
+        f = lambda p: p.detach().float().contiguous()
+        _, logits, _ = ops.heads(h.reshape(B * T, H).contiguous(), None, None, 0, f(self.pr_head.weight),
+                                 f(self.pr_head.bias), ops.ACT_NONE, want_argmax=False)
+        return logits.view(B, T, -1)
+
+    def forward(self, input_values, input_lengths, phoneme_labels, want_grad=False):
+        """models/w2v2_pr.py:40-88.  `want_grad=True` additionally returns d loss / d phoneme_logits from the
+        fused kernel (key 'grad_logits'), the implementation-independent quantity of SURVEY.md §3.3."""
+        cfg = self.wav2vec2.cfg
+        out, h, logits = self._logits(input_values, input_lengths)
+        dev = h.device
+        B, T, V = logits.shape
+        state_lens = self.wav2vec2._get_feat_extract_output_lengths(input_lengths.reshape(-1).to(dev))
+        labels = phoneme_labels.to(device=dev, dtype=torch.int32).contiguous()
+        target_lengths = (labels >= 0).sum(-1).to(torch.int32).contiguous()
+        if cfg.ctc_loss_reduction == "mean":
+            scale = 1.0 / (target_lengths.clamp(min=1).float() * B)
+        elif cfg.ctc_loss_reduction == "sum":
+            scale = torch.ones((B,), dtype=torch.float32, device=dev)
+        else:
+            raise ValueError(f"unsupported ctc_loss_reduction {cfg.ctc_loss_reduction!r}")
+        r = ops.logsoftmax_ctc(logits.contiguous(), labels, state_lens.to(torch.int32).contiguous(), target_lengths,
+                               blank=int(cfg.blank), zero_infinity=bool(cfg.ctc_zero_infinity),
+                               scale=scale.contiguous(), want_log_probs=True, want_grad=want_grad)
+        res = {"loss": r["loss_sum"][0], "phoneme_logits": logits, "log_probs": r["log_probs"], "hidden_states": h}
+        if want_grad:
+            res["grad_logits"] = r["grad"]
+        return res
+
+    def _decode(self, phoneme_logits, frame_lens=None):
+        """List of int arrays, one per utterance.  Default: greedy collapse over all frames (the reference passes
+        no lengths to its decoder either, :155)."""
+        if self.phoneme_decoder is not None:
+            return [np.asarray(x) for x in self.phoneme_decoder(phoneme_logits)]
+        blank = int(self.wav2vec2.cfg.blank)
+        tok, _, n = ops.ctc_greedy(phoneme_logits.contiguous(), None, blank=blank)
+        tok, n = tok.cpu().numpy(), n.cpu().numpy()
+        return [tok[b, : n[b]].astype(np.int64) for b in range(tok.shape[0])]
+
+    def get_embeddings(self, audio_inputs, audio_lengths):
+        """models/w2v2_pr.py:124-167."""
+        self.eval()
+        with torch.no_grad():
+            out, h, logits = self._logits(audio_inputs, audio_lengths)
+            frame_seq_lens = self.wav2vec2._get_feat_extract_output_lengths(audio_lengths)
+            phn_seq_idx = self._decode(logits)
+            return {
+                "features_hidden": out.extract_features.float().permute(0, 2, 1),
+                "last_transf_hidden": h.permute(0, 2, 1),
+                "phoneme_logits": logits.cpu().numpy().transpose(0, 2, 1),
+                "phn_pred_seq_idx": phn_seq_idx,
+                "frame_seq_lens": frame_seq_lens.cpu().numpy(),
+            }
+
+    def get_embeddings_grad(self, audio_inputs, audio_lengths, vocab, intermediate_hidden, latter_hidden):
+        """models/w2v2_pr.py:91-121 (values only: no autograd graph is recorded in this round)."""
+        out = self.wav2vec2(audio_inputs, attention_mask=audio_lengths.reshape(-1)[:, None], return_dict=True,
+                            output_hidden_states=True)
+        last = out.last_hidden_state
+        inter = out.hidden_states[intermediate_hidden]
+        latter = out.hidden_states[latter_hidden]
+        return {
+            "features_hidden": out.extract_features.float().permute(0, 2, 1),
+            "last_transf_hidden": last.permute(0, 2, 1),
+            "phoneme_logits_last": self._head(last),
+            "phoneme_logits_inter": self._head(inter.contiguous()),
+            "phoneme_logits_latter": self._head(latter.contiguous()),
+            "intermediate_hidden": inter.permute(0, 2, 1),
+            "latter_hidden": latter.permute(0, 2, 1),
+        }
+
+    def _single(self, wav):
+        dev = next(self.wav2vec2.parameters()).device
+        if type(wav) is torch.Tensor:
+            wav = wav[0]
+        wav_input = torch.as_tensor(np.asarray(wav), dtype=torch.float32).reshape(1, -1).to(dev)
+        wav_len = torch.tensor([wav_input.shape[1]], dtype=torch.int64, device=dev)
+        _, _, logits = self._logits(wav_input, wav_len)
+        return wav_input, logits
+
+    def get_ctc_logits(self, wav):
+        """models/w2v2_pr.py:170-188."""
+        self.eval()
+        with torch.no_grad():
+            _, logits = self._single(wav)
+            return logits[0].cpu().numpy()
+
+    def pred_phn_seq(self, wav, vocab):
+        """models/w2v2_pr.py:238-277."""
+        self.eval()
+        with torch.no_grad():
+            _, logits = self._single(wav)
+            idx = self._decode(logits)[0]
+            return {"phn_seq_idx": idx, "phn_seq_ipa": idx_phonemes(vocab, idx)}
+
+    def predict_phonemes_durations(self, wav, vocab):
+        """models/w2v2_pr.py:191-235: token time stamps = first frame of each token * seconds per frame."""
+        self.eval()
+        with torch.no_grad():
+            wav_input, logits = self._single(wav)
+            frame_sec_ratio = wav_input.shape[1] / logits.shape[1] / 16000
+            blank = int(self.wav2vec2.cfg.blank)
+            tok, frm, n = ops.ctc_greedy(logits.contiguous(), None, blank=blank)
+            n0 = int(n[0])
+            idx = tok[0, :n0].cpu().numpy()
+            ts = frm[0, :n0].cpu().numpy()
+            return {"phn_seq_idx": idx, "phn_seq_ipa": idx_phonemes(vocab, idx),
+                    "phn_seq_dur": [t * frame_sec_ratio for t in ts]}
+
+    def get_config(self):
+        return {"huggingface_model_id": self.huggingface_model_id, "cache_dir": self.cache_dir,
+                "pretrain_cfg": self.pretrain_cfg}
+
+    def freeze_feature_encoder(self):            # the reference's version lacks `self` (models/w2v2_pr.py:290-291)
+        self.wav2vec2.freeze_feature_encoder()

@@ -122,6 +122,10 @@ int aptai_heads(const float* h, int64_t rows, int H, const float* wa, const floa
  * accumulation of the fp64 taps, fp32 in/out [B][T][C]. */
 int aptai_lowpass_fir(const float* x, int B, int T, int C, const double* taps, int ntaps, float* y, void* stream);
 
+/* softmax (log_out=0) or log_softmax (log_out=1) over the last dim of fp32 [rows][V]
+ * (models/aptai.py:105,148 F.softmax; models/force_aptai.py:130 log_softmax). */
+int aptai_softmax_rows(const float* x, int64_t rows, int V, int log_out, float* y, void* stream);
+
 /* masked MSE + cross entropy of APTAI.forward (models/aptai.py:89-102).  out3 = {loss, mse, ce}. */
 int aptai_masked_mse_ce(const float* tv_pred, const float* tv_tgt, const float* logits, const int64_t* phn_tgt,
                         int64_t rows, int ntv, int V, float* accum_ws, float* out3, void* stream);
