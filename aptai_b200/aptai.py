@@ -65,6 +65,21 @@ class APTAI(nn.Module):
                                                                                      dtype=torch.int64).contiguous())
         return {"loss": res[0], "mse_loss": res[1], "ce_loss": res[2], "tvs_pred": tv, "phn_fc_pred": pred}
 
+    @torch.no_grad()
+    def predict(self, audio_inputs, audio_lengths, phn_targets=None, phn_target_lens=None, blank=0):
+        """Batched inference (additive API; the reference only offers the single-utterance `get_aptai_output`).
+        Returns tvs_pred [B,T,9], phn_fc_logits [B,T,46], phn_fc_pred [B,T]; with known phoneme sequences
+        (`phn_targets` int32 [B,S], `phn_target_lens` int32 [B]) also the CTC-Viterbi forced alignment of the
+        phoneme log-probs: align_paths int32 [B,T] (-1 beyond each utterance), align_scores, align_status."""
+        tv, logits, pred = self._heads(audio_inputs, audio_lengths)
+        out = {"tvs_pred": tv, "phn_fc_logits": logits, "phn_fc_pred": pred}
+        if phn_targets is not None:
+            lp = ops.softmax_rows(logits.contiguous(), log=True)
+            flen = self.wav2vec2._get_feat_extract_output_lengths(audio_lengths.reshape(-1)).to(torch.int32).contiguous()
+            paths, scores, status = ops.ctc_viterbi(lp, phn_targets, flen, phn_target_lens, blank=blank)
+            out.update(align_paths=paths, align_scores=scores, align_status=status, log_probs=lp)
+        return out
+
     def get_config(self):
         return {"device": self.device, "vocab": self.vocab, "huggingface_model_id": self.huggingface_model_id,
                 "pretrain_cfg": self.pretrain_cfg}

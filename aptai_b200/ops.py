@@ -40,8 +40,20 @@ def alloc_rows_bf16(B: int, T: int, C: int, device, slack_rows: int = 2) -> torc
     return flat[: B * T * C].view(B, T, C)
 
 
+_gemm_hook = None
+
+
+def set_gemm_hook(hook) -> None:
+    """bench.py's roofline leg: `hook(args)` returns a callable invoked after the launch (CUDA-event bracketing)."""
+    global _gemm_hook
+    _gemm_hook = hook
+
+
 def gemm_raw(args: GemmArgs) -> None:
+    done = _gemm_hook(args) if _gemm_hook is not None else None
     check(_lib.load().aptai_gemm_bf16(C.byref(args), _stream()), "gemm_bf16")
+    if done is not None:
+        done()
 
 
 def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, *, act: int = 0,

@@ -41,7 +41,7 @@ def test_tiny_encoder_matches_oracle(cuda, variant):
         assert err < 6e-2, f"{variant}: hidden[{i}] max abs err {err}"
     # padded frames are zeroed before the encoder but still computed afterwards (HF:679-682): compare all frames
     err = (out.last_hidden_state.cpu() - ref[-1]).abs()
-    assert err.mean().item() < 6e-3
+    assert err.mean().item() < 1e-2     # bf16 operands: SURVEY.md Appendix D measures hidden max|d| 2.4e-2..4e-2
 
 
 @pytest.mark.parametrize("variant,H,heads,F", [("layer", 1024, 16, 4096), ("group", 768, 12, 3072)])
@@ -52,4 +52,4 @@ def test_full_width_two_layers(cuda, variant, H, heads, F):
     lens = [32000, 20000]
     ref, out = _run(cfg, lens, 32000, cuda)
     err = (out.last_hidden_state.cpu() - ref[-1]).abs()
-    assert err.max().item() < 6e-2 and err.mean().item() < 6e-3, (err.max().item(), err.mean().item())
+    assert err.max().item() < 6e-2 and err.mean().item() < 1e-2, (err.max().item(), err.mean().item())
