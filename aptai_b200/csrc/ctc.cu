@@ -535,10 +535,10 @@ extern "C" int aptai_ctc_viterbi_f32(const float* log_probs, const int32_t* targ
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaError_t e = cudaSuccess;
   if (ni == 4) {
-    if (smem > 48 * 1024) e = cudaFuncSetAttribute(viterbi_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (smem > 32 * 1024) e = cudaFuncSetAttribute(viterbi_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e == cudaSuccess) viterbi_kernel<4><<<B, 32, smem, st>>>(a);
   } else {
-    if (smem > 48 * 1024) e = cudaFuncSetAttribute(viterbi_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (smem > 32 * 1024) e = cudaFuncSetAttribute(viterbi_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e == cudaSuccess) viterbi_kernel<8><<<B, 32, smem, st>>>(a);
   }
   if (e != cudaSuccess) {

@@ -38,13 +38,15 @@ struct GemmParams {
   float ln_eps;
 };
 
-template <int BN>
+template <int BN, bool CTA2>
 struct GemmCfg {
   static constexpr int UN = BN > 256 ? 256 : BN;                 // N of one tcgen05.mma
-  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int NPAIR = CTA2 ? 2 : 1;                     // CTAs cooperating on one tile (cta_group)
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;          // per CTA: its own 128 rows of A
+  static constexpr int B_ROWS = UN / NPAIR;                      // rows of one B sub-tile held by this CTA
+  static constexpr int B_BYTES = (BN / NPAIR) * BLOCK_K * 2;     // per CTA: its share of the B columns
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN >= 512 ? 2 : (BN >= 256 ? 4 : 6);
+  static constexpr int STAGES = STAGE_BYTES > 64 * 1024 ? 2 : (STAGE_BYTES > 40 * 1024 ? 4 : 6);
   static constexpr int ACC_STRIDE = BN < 64 ? 64 : BN;
   static constexpr int ACC_STAGES = (2 * ACC_STRIDE <= 512) ? 2 : 1;
   static constexpr int TMEM_COLS = ACC_STAGES * ACC_STRIDE <= 128 ? 128 : (ACC_STAGES * ACC_STRIDE <= 256 ? 256 : 512);
@@ -61,11 +63,9 @@ __device__ __forceinline__ void tmem_ld_chunk<32>(uint32_t taddr, uint32_t (&r)[
 template <>
 __device__ __forceinline__ void tmem_ld_chunk<8>(uint32_t taddr, uint32_t (&r)[8]) { tmem_ld8(taddr, r); }
 
-template <int BN, bool LN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const GemmParams p) {
-  using C = GemmCfg<BN>;
+template <int BN, bool LN, bool CTA2>
+__device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p) {
+  using C = GemmCfg<BN, CTA2>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -77,6 +77,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // CTA pair (cta_group::2): rank 0 is the leader and issues every MMA; each CTA owns 128 rows of the 256-row
+  // tile (its own TMEM lanes) and stages its own A rows plus half of the B columns.
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+  const int tile0 = CTA2 ? (blockIdx.x >> 1) : blockIdx.x;
+  const int tile_step = CTA2 ? (gridDim.x >> 1) : gridDim.x;
+  constexpr int TILE_M = BLOCK_M * C::NPAIR;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -89,13 +95,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], EPI_WARPS);
+      mbar_init(&tempty_bar[i], EPI_WARPS * C::NPAIR);
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, C::TMEM_COLS);
+  if (warp == 2) {
+    if (CTA2) tmem_alloc_cg2(tmem_slot, C::TMEM_COLS);
+    else tmem_alloc(tmem_slot, C::TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all();
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -104,20 +114,35 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
         const int n_blk = tile % p.n_tiles;
         const int mt = tile / p.n_tiles;
         const int seg = mt / p.m_tiles_per_seg;
-        const int r0 = (mt - seg * p.m_tiles_per_seg) * BLOCK_M;
+        const int r0 = (mt - seg * p.m_tiles_per_seg) * TILE_M + static_cast<int>(rank) * BLOCK_M;
         const int a_col0 = n_blk * p.a_col_per_nblk;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
-          mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           const int tap = kb / p.kb_per_tap;
           const int kc = kb - tap * p.kb_per_tap;
           const int tq = tap / p.P;
+          if (CTA2) {
+            // both CTAs' bytes are counted on the LEADER's barrier; only the leader arms it
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+            const uint32_t fb = map_to_cta(&full_bar[stage], 0);
+            tma_load_4d_cg2(&tmA, fb, sa, kc * BLOCK_K + a_col0, tap - tq * p.P, r0 + tq, seg);
+#pragma unroll
+            for (int nh = 0; nh < BN / C::UN; ++nh)
+              tma_load_2d_cg2(&tmB, fb, sb + nh * C::B_ROWS * BLOCK_K * 2, kb * BLOCK_K,
+                              n_blk * BN + nh * C::UN + static_cast<int>(rank) * C::B_ROWS);
+            if (++stage == C::STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
+          mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           tma_load_4d(&tmA, &full_bar[stage], sa, kc * BLOCK_K + a_col0, tap - tq * p.P, r0 + tq, seg);
 #pragma unroll
           for (int nh = 0; nh < BN / C::UN; ++nh)
@@ -131,13 +156,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
-      constexpr uint32_t IDESC = umma_idesc_bf16(BLOCK_M, C::UN);
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t IDESC = umma_idesc_bf16(TILE_M, C::UN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * C::ACC_STRIDE;
@@ -151,17 +176,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             const uint64_t adesc = umma_desc_sw128(a_base + k * UMMA_K * 2);
 #pragma unroll
             for (int nh = 0; nh < BN / C::UN; ++nh) {
-              const uint64_t bdesc = umma_desc_sw128(b_base + nh * C::UN * BLOCK_K * 2 + k * UMMA_K * 2);
-              umma_bf16(d_tmem + nh * C::UN, adesc, bdesc, IDESC, (kb | k) != 0 ? 1u : 0u);
+              const uint64_t bdesc = umma_desc_sw128(b_base + nh * C::B_ROWS * BLOCK_K * 2 + k * UMMA_K * 2);
+              if (CTA2) umma_bf16_cg2(d_tmem + nh * C::UN, adesc, bdesc, IDESC, (kb | k) != 0 ? 1u : 0u);
+              else umma_bf16(d_tmem + nh * C::UN, adesc, bdesc, IDESC, (kb | k) != 0 ? 1u : 0u);
             }
           }
-          umma_commit(&empty_bar[stage]);   // smem slot reusable once these MMAs have read it
+          // smem slot reusable (in both CTAs of the pair) once these MMAs have read it
+          if (CTA2) umma_commit_cg2(&empty_bar[stage], 0x3);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[acc]);       // accumulator complete -> epilogue
+        if (CTA2) umma_commit_cg2(&tfull_bar[acc], 0x3);   // accumulator complete -> epilogue warps of both CTAs
+        else umma_commit(&tfull_bar[acc]);
         if (C::ACC_STAGES == 2) {
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
@@ -179,12 +208,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     int acc = 0;
     uint32_t acc_phase = 0;
     int ln_buf = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    const uint32_t tempty_leader0 = CTA2 ? map_to_cta(&tempty_bar[0], 0) : 0u;
+    for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
       const int n_blk = tile % p.n_tiles;
       const int mt = tile / p.n_tiles;
       const int seg = mt / p.m_tiles_per_seg;
       const int row_in_tile = q * 32 + lane;
-      const int r = (mt - seg * p.m_tiles_per_seg) * BLOCK_M + row_in_tile;
+      const int r = (mt - seg * p.m_tiles_per_seg) * TILE_M + static_cast<int>(rank) * BLOCK_M + row_in_tile;
       const bool valid_row = r < p.rows_per_seg;
       const long long out_row = static_cast<long long>(seg) * p.out_seg_stride + r;
       bool zero_row = false;
@@ -291,7 +321,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       // all tcgen05.ld of this warp have completed (wait::ld above) -> hand the accumulator back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (CTA2) mbar_arrive_cluster(tempty_leader0 + acc * 8);
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       if (C::ACC_STAGES == 2) {
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
@@ -302,16 +335,52 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all();
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    if (CTA2) tmem_dealloc_cg2(tmem_base, C::TMEM_COLS);
+    else tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 
 template <int BN, bool LN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                         const GemmParams p) {
+  gemm_body<BN, LN, false>(tmA, tmB, p);
+}
+
+// CTA-pair variant: cluster of 2, tcgen05.mma.cta_group::2 (M = 256), half of B per CTA
+template <int BN, bool LN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                              const GemmParams p) {
+  gemm_body<BN, LN, true>(tmA, tmB, p);
+}
+
+template <int BN, bool LN>
+static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  using C = GemmCfg<BN, true>;
+  auto kern = gemm_bf16_tcgen05_2cta_kernel<BN, LN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("gemm(2cta): cudaFuncSetAttribute(%d bytes): %s", C::SMEM_BYTES, cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    attr_set = true;
+  }
+  int clusters = num_sms() / 2;
+  if (p.num_tiles < clusters) clusters = p.num_tiles;
+  kern<<<2 * clusters, GEMM_THREADS, C::SMEM_BYTES, st>>>(ta, tb, p);
+  return after_launch("gemm_bf16_tcgen05_2cta");
+}
+
+template <int BN, bool LN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-  using C = GemmCfg<BN>;
+  using C = GemmCfg<BN, false>;
   auto kern = gemm_bf16_tcgen05_kernel<BN, LN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -357,6 +426,13 @@ extern "C" int aptai_gemm_bf16(const aptai_gemm_args* g, void* stream) {
   APTAI_REQUIRE(bn != 512 || g->ln, "gemm: block_n 512 is the fused-LayerNorm tile");
   const long long K = static_cast<long long>(g->taps) * g->kb_per_tap * BLOCK_K;
 
+  // CTA-pair (cta_group::2) tiles halve the B traffic per SM; they need a wide N tile and enough 256-row tiles
+  bool pair = false;
+  if (bn >= 256) {
+    const long long tiles2 = static_cast<long long>(g->segs) * ((g->rows_per_seg + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) *
+                             (g->N / bn);
+    pair = g->cta_pair == 2 || (g->cta_pair == 0 && tiles2 >= 2LL * (num_sms() / 2));
+  }
   CUtensorMap ta, tb;
   {
     const uint64_t r2 = (static_cast<uint64_t>(g->a_rows) + g->P - 1) / g->P;
@@ -372,7 +448,7 @@ extern "C" int aptai_gemm_bf16(const aptai_gemm_args* g, void* stream) {
   {
     uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(g->N)};
     uint64_t strides[1] = {static_cast<uint64_t>(K) * 2};
-    uint32_t box[2] = {BLOCK_K, static_cast<uint32_t>(bn > 256 ? 256 : bn)};
+    uint32_t box[2] = {BLOCK_K, static_cast<uint32_t>((bn > 256 ? 256 : bn) / (pair ? 2 : 1))};
     if (int rc = encode_tmap_bf16(&tb, g->w, 2, dims, strides, box, 1)) return rc;
   }
   GemmParams p;
@@ -381,7 +457,8 @@ extern "C" int aptai_gemm_bf16(const aptai_gemm_args* g, void* stream) {
   p.P = g->P;
   p.a_col_per_nblk = g->a_col_per_nblk;
   p.rows_per_seg = g->rows_per_seg;
-  p.m_tiles_per_seg = (g->rows_per_seg + BLOCK_M - 1) / BLOCK_M;
+  const int tile_m = pair ? 2 * BLOCK_M : BLOCK_M;
+  p.m_tiles_per_seg = (g->rows_per_seg + tile_m - 1) / tile_m;
   p.n_tiles = g->N / bn;
   p.num_tiles = g->segs * p.m_tiles_per_seg * p.n_tiles;
   p.bias = g->bias;
@@ -397,9 +474,9 @@ extern "C" int aptai_gemm_bf16(const aptai_gemm_args* g, void* stream) {
   p.act = g->act;
   p.ln_eps = g->ln_eps;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (g->ln) return launch_gemm<512, true>(ta, tb, p, st);
+  if (g->ln) return pair ? launch_gemm_2cta<512, true>(ta, tb, p, st) : launch_gemm<512, true>(ta, tb, p, st);
   switch (bn) {
-    case 256: return launch_gemm<256, false>(ta, tb, p, st);
+    case 256: return pair ? launch_gemm_2cta<256, false>(ta, tb, p, st) : launch_gemm<256, false>(ta, tb, p, st);
     case 128: return launch_gemm<128, false>(ta, tb, p, st);
     case 64: return launch_gemm<64, false>(ta, tb, p, st);
     case 48: return launch_gemm<48, false>(ta, tb, p, st);

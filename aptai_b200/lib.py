@@ -23,7 +23,7 @@ class GemmArgs(C.Structure):
         ("w", c_void_p), ("N", C.c_int32), ("block_n", C.c_int32), ("segs", C.c_int32), ("rows_per_seg", C.c_int32),
         ("bias", c_void_p), ("gamma", c_void_p), ("beta", c_void_p), ("residual", c_void_p),
         ("out_f32", c_void_p), ("out_bf16", c_void_p), ("ldo", c_i64), ("out_seg_stride", c_i64),
-        ("seg_valid_rows", c_void_p), ("mask_seg_rows", C.c_int32), ("act", C.c_int32), ("ln", C.c_int32), ("ln_eps", c_float),
+        ("seg_valid_rows", c_void_p), ("mask_seg_rows", C.c_int32), ("act", C.c_int32), ("ln", C.c_int32), ("ln_eps", c_float), ("cta_pair", C.c_int32),
     ]
 
 

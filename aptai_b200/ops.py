@@ -60,7 +60,7 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
            residual: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None,
            out_bf16: Optional[torch.Tensor] = None, want_f32: bool = False, want_bf16: bool = True,
            seg_rows: Optional[int] = None, seg_valid_rows: Optional[torch.Tensor] = None,
-           block_n: int = 0):
+           block_n: int = 0, cta_pair: int = 0):
     """out = epilogue(a @ w.T): a bf16 [M,K], w bf16 [N,K] (nn.Linear layout), bias fp32 [N].
 
     seg_rows / seg_valid_rows: rows are grouped in segments of seg_rows; rows >= seg_valid_rows[s] are written as 0.
@@ -89,14 +89,14 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     g.gamma = None; g.beta = None
     g.residual = _ptr(_req(residual, F32, "residual")) if residual is not None else None
     g.out_f32 = _ptr(out_f32); g.out_bf16 = _ptr(out_bf16); g.ldo = N
-    g.act = act; g.ln = 0; g.ln_eps = 0.0
+    g.act = act; g.ln = 0; g.ln_eps = 0.0; g.cta_pair = cta_pair
     gemm_raw(g)
     return out_f32, out_bf16
 
 
 def conv_igemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], k: int, stride: int, *,
                ln_gamma: Optional[torch.Tensor] = None, ln_beta: Optional[torch.Tensor] = None,
-               eps: float = 1e-5, act: int = 1, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+               eps: float = 1e-5, act: int = 1, out: Optional[torch.Tensor] = None, cta_pair: int = 0) -> torch.Tensor:
     """Strided conv1d as implicit GEMM.  x bf16 [B,T_in,C] channels-last, w bf16 [N, k*C] (tap-major K), out bf16
     [B,T_out,N]; epilogue = (+bias) -> (LayerNorm over N, if gamma) -> GELU."""
     _req(x, BF16, "x"); _req(w, BF16, "w")
@@ -114,6 +114,7 @@ def conv_igemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], k
     g.gamma = _ptr(ln_gamma); g.beta = _ptr(ln_beta); g.residual = None
     g.out_f32 = None; g.out_bf16 = out.data_ptr(); g.ldo = N; g.out_seg_stride = T_out
     g.seg_valid_rows = None; g.mask_seg_rows = 0; g.act = act; g.ln = 1 if ln_gamma is not None else 0; g.ln_eps = eps
+    g.cta_pair = cta_pair
     gemm_raw(g)
     return out
 

@@ -77,6 +77,7 @@ typedef struct aptai_gemm_args {
   int32_t act;            /* 0 none, 1 erf-GELU */
   int32_t ln;             /* 0/1: LayerNorm over the full row (requires N == 512) */
   float ln_eps;
+  int32_t cta_pair;       /* 0 auto, 1 single-CTA tiles (128 x BN), 2 CTA-pair tiles (256 x BN, cta_group::2) */
 } aptai_gemm_args;
 
 int aptai_gemm_bf16(const aptai_gemm_args* args, void* stream);

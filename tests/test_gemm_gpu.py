@@ -22,13 +22,14 @@ def _close_bf16(out, ref, what, atol=2e-2, rtol=2e-2):
     assert bad == 0, f"{what}: {bad} mismatches, max err {err.max().item():.4g}"
 
 
+@pytest.mark.parametrize("pair", [1, 2])
 @pytest.mark.parametrize("M,K,N", [(128, 64, 256), (300, 512, 1024), (1000, 1024, 3072), (777, 768, 2304),
-                                   (129, 256, 128), (64, 128, 64), (5000, 4096, 1024)])
-def test_linear_bias(cuda, M, K, N):
+                                   (129, 256, 128), (64, 128, 64), (5000, 4096, 1024), (40000, 1024, 1024)])
+def test_linear_bias(cuda, M, K, N, pair):
     a = _rand((M, K), cuda, 1.0, 1).bfloat16()
     w = _rand((N, K), cuda, 0.05, 2).bfloat16()
     b = _rand((N,), cuda, 0.5, 3)
-    o32, o16 = ops.linear(a, w, b, want_f32=True, want_bf16=True)
+    o32, o16 = ops.linear(a, w, b, want_f32=True, want_bf16=True, cta_pair=pair)
     ref = a.float() @ w.float().t() + b
     torch.testing.assert_close(o32, ref, atol=2e-3, rtol=2e-3)
     _close_bf16(o16, ref, "bf16 out")
@@ -56,9 +57,10 @@ def test_linear_gelu_residual_mask(cuda):
     torch.testing.assert_close(h.view(B, T, N), ref, atol=2e-3, rtol=2e-3)
 
 
+@pytest.mark.parametrize("pair", [1, 2])
 @pytest.mark.parametrize("k,T_in,B,ln", [(3, 801, 2, True), (3, 640, 3, False), (2, 399, 2, True), (2, 130, 1, False),
                                          (3, 2563, 2, True)])
-def test_conv_igemm(cuda, k, T_in, B, ln):
+def test_conv_igemm(cuda, k, T_in, B, ln, pair):
     C = 512
     x = ops.alloc_rows_bf16(B, T_in, C, cuda)
     x.copy_(_rand((B, T_in, C), cuda, 1.0, 8).bfloat16())
@@ -67,7 +69,7 @@ def test_conv_igemm(cuda, k, T_in, B, ln):
     gam = 1 + _rand((C,), cuda, 0.1, 11)
     bet = _rand((C,), cuda, 0.1, 12)
     wk = w.permute(0, 2, 1).reshape(C, k * C).bfloat16().contiguous()
-    y = ops.conv_igemm(x, wk, bias, k, 2, ln_gamma=gam if ln else None, ln_beta=bet if ln else None, act=1)
+    y = ops.conv_igemm(x, wk, bias, k, 2, ln_gamma=gam if ln else None, ln_beta=bet if ln else None, act=1, cta_pair=pair)
     ref = F.conv1d(x.float().transpose(1, 2), w.bfloat16().float(), bias, stride=2)
     if ln:
         ref = F.layer_norm(ref.transpose(1, 2), (C,), gam, bet, 1e-5).transpose(1, 2)

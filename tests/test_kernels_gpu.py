@@ -146,7 +146,7 @@ def test_forward_sum(cuda):
     assert abs(float(r["loss_sum"].cpu()) - loss_ref) <= 1e-3 * abs(loss_ref)
 
 
-@pytest.mark.parametrize("B,T,C,Smax", [(64, 399, 46, 59), (8, 40, 5, 12), (4, 999, 46, 100)])
+@pytest.mark.parametrize("B,T,C,Smax", [(64, 399, 46, 59), (8, 40, 5, 12), (4, 999, 46, 100), (3, 765, 46, 59)])
 def test_viterbi_bit_exact(cuda, B, T, C, Smax):
     rng = np.random.default_rng(11)
     x = rng.standard_normal((B, T, C)).astype(np.float32)
