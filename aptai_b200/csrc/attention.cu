@@ -1,3 +1,5 @@
+// Legacy-tensor-path (mma.sync) attention, kept only as the A/B baseline of the tcgen05 kernel in attention_tc.cu
+// (entry point aptai_attention_fwd_mma; the product path calls aptai_attention_fwd).
 // Padding-masked fused attention for the wav2vec2 encoder (HF:500-549; SDPA, non-causal, key-padding mask).
 //
 // Flash-style: one CTA = 64 query rows of one (utterance, head); K/V streamed in 64-key tiles through a
@@ -202,7 +204,7 @@ attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __res
 
 using namespace aptai;
 
-extern "C" int aptai_attention_fwd(const void* qkv, void* ctx, const int32_t* key_len, int B, int T, int heads,
+extern "C" int aptai_attention_fwd_mma(const void* qkv, void* ctx, const int32_t* key_len, int B, int T, int heads,
                                    void* stream) {
   if (int rc = check_arch()) return rc;
   APTAI_REQUIRE(qkv && ctx, "attention: null pointer");
@@ -211,5 +213,5 @@ extern "C" int aptai_attention_fwd(const void* qkv, void* ctx, const int32_t* ke
   dim3 grid((T + AT_BQ - 1) / AT_BQ, heads, B);
   attention_fwd_kernel<<<grid, AT_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(ctx), key_len, T, heads * AT_D);
-  return after_launch("attention_fwd");
+  return after_launch("attention_fwd_mma");
 }

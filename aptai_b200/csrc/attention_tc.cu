@@ -1,0 +1,340 @@
+// tcgen05 / TMEM fused attention forward (HF:500-549 with SDPA semantics: non-causal, key-padding mask).
+//
+// Persistent, warp-specialised, one work item = 128 query rows of one (utterance, head):
+//   warp 0      TMA producer   Q tile once per item; K_j / V_j tiles (128 keys x 64) through a 2-stage ring
+//   warp 1      MMA issuer     S_j = Q K_j^T  (M=128, N=n_j, K=64)   -> TMEM S buffer j%2   (double buffered)
+//                              O  += P_j V_j  (M=128, N=64,  K=n_j)  -> TMEM O, P_j from shared memory (bf16),
+//                                                                       V_j as an MN-major B operand
+//   warps 4..7  softmax        thread i owns query row i: tcgen05.ld of its S row, key-length mask, running max
+//                              with lazy rescaling of O (only when the max grows by more than 2^8), exp2, row sum,
+//                              P_j -> shared memory in the UMMA K-major SWIZZLE_128B layout; final O / l -> bf16
+// S_{j+1} is issued before P_j V_j so the tensor core overlaps the softmax of tile j.
+// q must be pre-scaled by head_dim^-0.5 (folded into the q projection at plan time); head_dim is 64.
+// Every query row is computed (padded queries attend to valid keys, HF:438-463); keys >= key_len[b] are masked.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace aptai {
+
+constexpr int AQ = 128;                 // query rows per work item
+constexpr int AK = 128;                 // keys per KV tile
+constexpr int AD = 64;                  // head dim
+constexpr int ATC_THREADS = 256;        // warps 0,1 (+2 TMEM alloc, 3 idle), 4..7 softmax
+constexpr int TILE_BYTES = AK * AD * 2; // 16 KB: Q, K_j, V_j tiles; one 64-key half of P
+constexpr int ATC_SMEM = 1024 + TILE_BYTES * (1 + 2 + 2 + 4) + 256;
+constexpr uint32_t TM_S = 0, TM_O = 256, TM_COLS = 512;
+constexpr float ATC_LOG2E = 1.4426950408889634f;
+constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units
+
+struct AttnParams {
+  const int* key_len;
+  __nv_bfloat16* ctx;
+  int B, T, heads, H, n_qt, items;
+};
+
+// MN-major SWIZZLE_128B descriptor for a B operand stored [k rows][64 mn-elements] (128 B per k row):
+// 8-row groups along K are 1024 B apart (SBO); a single 64-element MN block, so LBO is unused.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1024 >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(ATC_THREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + TILE_BYTES;          // [2]
+  uint8_t* sV = smem + 3 * TILE_BYTES;      // [2]
+  uint8_t* sP = smem + 5 * TILE_BYTES;      // [2][2 halves]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 9 * TILE_BYTES);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* kv_full = bars + 2;    // [2]
+  uint64_t* kv_empty = bars + 4;   // [2]
+  uint64_t* s_full = bars + 6;     // [2]
+  uint64_t* s_empty = bars + 8;    // [2]
+  uint64_t* p_full = bars + 10;    // [2]
+  uint64_t* p_empty = bars + 12;   // [2]  (P_j V_j complete)
+  uint64_t* o_full = bars + 14;
+  uint64_t* o_empty = bars + 15;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmQKV);
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, 4);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 4);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&p_empty[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, TM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      uint32_t g = 0, it = 0;
+      for (int w = blockIdx.x; w < p.items; w += gridDim.x, ++it) {
+        const int qt = w % p.n_qt;
+        const int bh = w / p.n_qt;
+        const int h = bh % p.heads, b = bh / p.heads;
+        const int klen = max(1, min(__ldg(p.key_len + b), p.T));
+        const int n = (klen + AK - 1) / AK;
+        const int row0 = b * p.T;
+        mbar_wait(q_empty, (it & 1) ^ 1);
+        mbar_expect_tx(q_full, TILE_BYTES);
+        tma_load_2d(&tmQKV, q_full, sQ, h * AD, row0 + qt * AQ);
+        for (int j = 0; j < n; ++j, ++g) {
+          const uint32_t s = g & 1, u = g >> 1;
+          mbar_wait(&kv_empty[s], (u & 1) ^ 1);
+          mbar_expect_tx(&kv_full[s], 2 * TILE_BYTES);
+          tma_load_2d(&tmQKV, &kv_full[s], sK + s * TILE_BYTES, p.H + h * AD, row0 + j * AK);
+          tma_load_2d(&tmQKV, &kv_full[s], sV + s * TILE_BYTES, 2 * p.H + h * AD, row0 + j * AK);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t IDESC_BASE = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(AQ >> 4) << 24);
+      constexpr uint32_t IDESC_PV = IDESC_BASE | (1u << 16) | (static_cast<uint32_t>(AD >> 3) << 17);   // B MN-major, N=64
+      uint32_t g = 0, it = 0;
+      for (int w = blockIdx.x; w < p.items; w += gridDim.x, ++it) {
+        const int bh = w / p.n_qt;
+        const int b = bh / p.heads;
+        const int klen = max(1, min(__ldg(p.key_len + b), p.T));
+        const int n = (klen + AK - 1) / AK;
+        mbar_wait(q_full, it & 1);
+        tc_fence_after();
+        const uint32_t q_addr = smem_u32(sQ);
+        for (int j = 0; j <= n; ++j) {
+          if (j < n) {
+            // S_j = Q K_j^T
+            const uint32_t gj = g + j, s = gj & 1, u = gj >> 1;
+            const int nj = min(AK, ((klen - j * AK) + 15) & ~15);
+            mbar_wait(&kv_full[s], u & 1);
+            mbar_wait(&s_empty[s], (u & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t k_addr = smem_u32(sK + s * TILE_BYTES);
+            const uint32_t idesc = IDESC_BASE | (static_cast<uint32_t>(nj >> 3) << 17);
+#pragma unroll
+            for (int k = 0; k < AD / 16; ++k)
+              umma_bf16(tmem_base + TM_S + s * AK, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32),
+                        idesc, k != 0 ? 1u : 0u);
+            umma_commit(&s_full[s]);
+            if (j == n - 1) umma_commit(q_empty);     // Q tile no longer needed once the last S is done
+          }
+          if (j >= 1) {
+            // O += P_{j-1} V_{j-1}
+            const int jj = j - 1;
+            const uint32_t gj = g + jj, s = gj & 1, u = gj >> 1;
+            const int nj = min(AK, ((klen - jj * AK) + 15) & ~15);
+            mbar_wait(&p_full[s], u & 1);
+            if (jj == 0) mbar_wait(o_empty, (it & 1) ^ 1);     // previous item's O has been read out
+            tc_fence_after();
+            const uint32_t p_addr = smem_u32(sP + s * 2 * TILE_BYTES);
+            const uint32_t v_addr = smem_u32(sV + s * TILE_BYTES);
+            for (int k = 0; k < nj / 16; ++k) {
+              const uint32_t pa = p_addr + (k >> 2) * TILE_BYTES + (k & 3) * 32;   // 64-key half, 16-key step
+              umma_bf16(tmem_base + TM_O, umma_desc_sw128(pa), umma_desc_sw128_mn(v_addr + k * 2048), IDESC_PV,
+                        (jj | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(&kv_empty[s]);
+            umma_commit(&p_empty[s]);
+            if (jj == n - 1) umma_commit(o_full);
+          }
+        }
+        g += n;
+      }
+    }
+  } else if (warp >= 4) {
+    // ---------------------------------------------------------------- softmax + output (thread = query row)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    uint32_t g = 0, it = 0;
+    for (int w = blockIdx.x; w < p.items; w += gridDim.x, ++it) {
+      const int qt = w % p.n_qt;
+      const int bh = w / p.n_qt;
+      const int h = bh % p.heads, b = bh / p.heads;
+      const int klen = max(1, min(__ldg(p.key_len + b), p.T));
+      const int n = (klen + AK - 1) / AK;
+      float m_used = -INFINITY, l = 0.f;
+      for (int j = 0; j < n; ++j, ++g) {
+        const uint32_t s = g & 1, u = g >> 1;
+        const int valid = min(AK, klen - j * AK);          // keys of this tile that exist
+        const int nchunk = (valid + 31) >> 5;
+        mbar_wait(&s_full[s], u & 1);
+        tc_fence_after();
+        const uint32_t t_s = t_lane + TM_S + s * AK;
+        // pass A: row max over the valid keys (base-2 domain)
+        float mx = -INFINITY;
+        for (int c = 0; c < nchunk; ++c) {
+          uint32_t r[32];
+          tmem_ld32(t_s + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+        }
+        mx *= ATC_LOG2E;
+        // lazy rescale: keep the stale max unless the new one exceeds it by more than 2^8
+        float factor = 1.f;
+        if (mx > m_used + RESCALE_THRESHOLD) {
+          factor = exp2f(m_used - mx);          // 0 on the first tile (m_used = -inf)
+          m_used = mx;
+        }
+        const bool need = (factor != 1.f) && (j > 0);
+        if (__any_sync(0xffffffffu, need)) {
+          // O must be complete (P_{j-1} V_{j-1} done) before it is rescaled in place
+          const uint32_t gp = g - 1;
+          mbar_wait(&p_empty[gp & 1], (gp >> 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld32(t_lane + TM_O + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * factor);
+            asm volatile(
+                "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+                "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+                ::"r"(t_lane + TM_O + c * 32), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]),
+                "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]),
+                "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]),
+                "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+                "r"(r[30]), "r"(r[31])
+                : "memory");
+          }
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        l *= factor;
+        // pass B: p = exp2(s*log2e - m_used); P -> shared memory (bf16, K-major SWIZZLE_128B, two 64-key halves)
+        mbar_wait(&p_empty[s], (u & 1) ^ 1);       // P_{j-2} V_{j-2} has consumed this P buffer
+        uint8_t* pbuf = sP + s * 2 * TILE_BYTES;
+        float rs = 0.f;
+        const int ncol16 = (valid + 15) >> 4;      // 16-key groups the P V MMA will read
+        for (int c = 0; c < nchunk; ++c) {
+          uint32_t r[32];
+          tmem_ld32(t_s + c * 32, r);
+          tmem_ld_wait();
+          float pv[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float e = exp2f(fmaf(__uint_as_float(r[i]), ATC_LOG2E, -m_used));
+            pv[i] = (c * 32 + i < valid) ? e : 0.f;
+            rs += pv[i];
+          }
+#pragma unroll
+          for (int u8 = 0; u8 < 4; ++u8) {          // four 16-byte units (8 keys each) per 32-key chunk
+            const int key0 = c * 32 + u8 * 8;
+            if ((key0 >> 4) < ncol16) {
+              const int half = key0 >> 6, unit = (key0 & 63) >> 3;
+              uint4 v4 = make_uint4(pack_bf16(pv[u8 * 8 + 0], pv[u8 * 8 + 1]), pack_bf16(pv[u8 * 8 + 2], pv[u8 * 8 + 3]),
+                                    pack_bf16(pv[u8 * 8 + 4], pv[u8 * 8 + 5]), pack_bf16(pv[u8 * 8 + 6], pv[u8 * 8 + 7]));
+              *reinterpret_cast<uint4*>(pbuf + half * TILE_BYTES + row * 128 + ((unit ^ (row & 7)) << 4)) = v4;
+            }
+          }
+        }
+        l += rs;
+        // S buffer consumed; P visible to the async proxy (tensor core)
+        tc_fence_before();
+        fence_async_proxy();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&s_empty[s]);
+          mbar_arrive(&p_full[s]);
+        }
+      }
+      // ---- output: O / l -> bf16
+      mbar_wait(o_full, it & 1);
+      tc_fence_after();
+      const float inv = 1.f / l;
+      const int qrow = qt * AQ + row;
+      __nv_bfloat16* out = p.ctx + (static_cast<long long>(b) * p.T + qrow) * p.H + h * AD;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld32(t_lane + TM_O + c * 32, r);
+        tmem_ld_wait();
+        if (qrow < p.T) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8)
+            *reinterpret_cast<uint4*>(out + c * 32 + i) =
+                make_uint4(pack_bf16(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv),
+                           pack_bf16(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv),
+                           pack_bf16(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv),
+                           pack_bf16(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TM_COLS);
+  }
+}
+
+}  // namespace aptai
+
+using namespace aptai;
+
+extern "C" int aptai_attention_fwd(const void* qkv, void* ctx, const int32_t* key_len, int B, int T, int heads,
+                                   void* stream) {
+  if (int rc = check_arch()) return rc;
+  APTAI_REQUIRE(qkv && ctx && key_len, "attention: null pointer");
+  APTAI_REQUIRE(B >= 1 && T >= 1 && heads >= 1, "attention: bad shape");
+  APTAI_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(ctx) & 15) == 0,
+                "attention: buffers must be 16-byte aligned");
+  const int H = heads * AD;
+  CUtensorMap tm;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(3) * H, static_cast<uint64_t>(B) * T};
+    uint64_t strides[1] = {static_cast<uint64_t>(3) * H * 2};
+    uint32_t box[2] = {AD, AK};
+    if (int rc = encode_tmap_bf16(&tm, qkv, 2, dims, strides, box, 1)) return rc;
+  }
+  AttnParams p;
+  p.key_len = key_len;
+  p.ctx = reinterpret_cast<__nv_bfloat16*>(ctx);
+  p.B = B; p.T = T; p.heads = heads; p.H = H;
+  p.n_qt = (T + AQ - 1) / AQ;
+  p.items = B * heads * p.n_qt;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);
+    if (e != cudaSuccess) {
+      set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    attr_set = true;
+  }
+  const int grid = p.items < num_sms() ? p.items : num_sms();
+  attention_tc_kernel<<<grid, ATC_THREADS, ATC_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tm, p);
+  return after_launch("attention_tc");
+}

@@ -183,16 +183,17 @@ def posconv_fold(g: torch.Tensor, v: torch.Tensor, cpad: int = 64) -> torch.Tens
 
 
 def attention(qkv: torch.Tensor, key_len: Optional[torch.Tensor], B: int, T: int, heads: int,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, legacy_mma: bool = False) -> torch.Tensor:
     _req(qkv, BF16, "qkv")
     H = heads * 64
     assert qkv.numel() == B * T * 3 * H
     if out is None:
         out = torch.empty((B * T, H), dtype=BF16, device=qkv.device)
-    if key_len is not None:
-        _req(key_len, I32, "key_len")
-    check(_lib.load().aptai_attention_fwd(qkv.data_ptr(), out.data_ptr(), _ptr(key_len), B, T, heads, _stream()),
-          "attention_fwd")
+    if key_len is None:
+        key_len = torch.full((B,), T, dtype=I32, device=qkv.device)
+    _req(key_len, I32, "key_len")
+    fn = _lib.load().aptai_attention_fwd_mma if legacy_mma else _lib.load().aptai_attention_fwd
+    check(fn(qkv.data_ptr(), out.data_ptr(), key_len.data_ptr(), B, T, heads, _stream()), "attention_fwd")
     return out
 
 

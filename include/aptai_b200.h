@@ -109,6 +109,8 @@ int aptai_posconv_fold(const float* g, const float* v, int H, int cin, int taps,
  * Keys t >= key_len[b] are masked; every query row is computed (padded queries attend to valid keys, HF:438-463).
  */
 int aptai_attention_fwd(const void* qkv, void* ctx, const int32_t* key_len, int B, int T, int heads, void* stream);
+/* same contract on the legacy mma.sync tensor path; A/B baseline for profiles/, not used by the product path */
+int aptai_attention_fwd_mma(const void* qkv, void* ctx, const int32_t* key_len, int B, int T, int heads, void* stream);
 
 /* ------------------------------------------------------------------ heads and post-processing ---------------
  * APTAI heads (models/aptai.py:43-55,83-86,105-106): tv = tanh(h) W_tv^T + b_tv (9), logits = leaky_relu(h)

@@ -57,13 +57,19 @@ def test_layernorm(cuda, cols, in_bf16):
     torch.testing.assert_close(o16.float(), ref.bfloat16().float(), atol=2e-2, rtol=1e-2)
 
 
-@pytest.mark.parametrize("B,T,heads,lens", [(2, 199, 16, [199, 150]), (3, 64, 12, [64, 1, 33]), (1, 999, 4, [999]),
-                                            (2, 130, 2, [70, 130])])
-def test_attention(cuda, B, T, heads, lens):
+@pytest.mark.parametrize("legacy", [False, True])
+@pytest.mark.parametrize("B,T,heads,lens,scale", [(2, 199, 16, [199, 150], 1.0), (3, 64, 12, [64, 1, 33], 1.0),
+                                                  (1, 999, 4, [999], 1.0), (2, 130, 2, [70, 130], 1.0),
+                                                  (40, 399, 16, None, 0.5), (2, 513, 2, [513, 400], 3.0)])
+def test_attention(cuda, B, T, heads, lens, scale, legacy):
     H = heads * 64
-    qkv = _rand((B * T, 3 * H), cuda, 1.0, 9).bfloat16()
+    qkv = _rand((B * T, 3 * H), cuda, scale, 9).bfloat16()
+    if lens is None:
+        lens = [T - (7 * b) % 200 for b in range(B)]
+    if scale > 1.0:
+        qkv[T // 2:, H: 2 * H] *= 4.0          # later keys score much higher: exercises the lazy O rescale
     kl = torch.tensor(lens, dtype=torch.int32, device=cuda)
-    ctx = ops.attention(qkv, kl, B, T, heads)
+    ctx = ops.attention(qkv, kl, B, T, heads, legacy_mma=legacy)
     q, k, v = qkv.float().view(B, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
     s = q @ k.transpose(-1, -2)                      # q is expected pre-scaled
     mask = torch.arange(T, device=cuda)[None, :] < kl[:, None]
