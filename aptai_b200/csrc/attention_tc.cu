@@ -1,14 +1,16 @@
 // tcgen05 / TMEM fused attention forward (HF:500-549 with SDPA semantics: non-causal, key-padding mask).
 //
-// Persistent, warp-specialised, one work item = 128 query rows of one (utterance, head):
+// Persistent, warp-specialised, one work item = 128 query rows of one (utterance, head); two CTAs are resident
+// per SM (256 TMEM columns and ~113 KB of shared memory each) so that one CTA's softmax (MUFU-bound) overlaps the
+// other's MMAs and loads:
 //   warp 0      TMA producer   Q tile once per item; K_j / V_j tiles (128 keys x 64) through a 2-stage ring
-//   warp 1      MMA issuer     S_j = Q K_j^T  (M=128, N=n_j, K=64)   -> TMEM S buffer j%2   (double buffered)
+//   warp 1      MMA issuer     S_j = Q K_j^T  (M=128, N=n_j, K=64)   -> TMEM S
 //                              O  += P_j V_j  (M=128, N=64,  K=n_j)  -> TMEM O, P_j from shared memory (bf16),
 //                                                                       V_j as an MN-major B operand
 //   warps 4..7  softmax        thread i owns query row i: tcgen05.ld of its S row, key-length mask, running max
 //                              with lazy rescaling of O (only when the max grows by more than 2^8), exp2, row sum,
 //                              P_j -> shared memory in the UMMA K-major SWIZZLE_128B layout; final O / l -> bf16
-// S_{j+1} is issued before P_j V_j so the tensor core overlaps the softmax of tile j.
+// S_{j+1} is issued right behind P_j (S is free once P_j is written) and ahead of P_j V_j.
 // q must be pre-scaled by head_dim^-0.5 (folded into the q projection at plan time); head_dim is 64.
 // Every query row is computed (padded queries attend to valid keys, HF:438-463); keys >= key_len[b] are masked.
 #include "common.h"
@@ -21,8 +23,9 @@ constexpr int AK = 128;                 // keys per KV tile
 constexpr int AD = 64;                  // head dim
 constexpr int ATC_THREADS = 256;        // warps 0,1 (+2 TMEM alloc, 3 idle), 4..7 softmax
 constexpr int TILE_BYTES = AK * AD * 2; // 16 KB: Q, K_j, V_j tiles; one 64-key half of P
-constexpr int ATC_SMEM = 1024 + TILE_BYTES * (1 + 2 + 2 + 4) + 256;
-constexpr uint32_t TM_S = 0, TM_O = 256, TM_COLS = 512;
+constexpr int ATC_TILES = 1 + 2 + 2 + 2;                       // Q, K[2], V[2], P (two 64-key halves)
+constexpr int ATC_SMEM = TILE_BYTES * ATC_TILES + 256 + 768;   // + barriers + alignment slack; 2 CTAs fit one SM
+constexpr uint32_t TM_S = 0, TM_O = 128, TM_COLS = 256;
 constexpr float ATC_LOG2E = 1.4426950408889634f;
 constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units
 
@@ -44,23 +47,26 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t saddr) {
   return d;
 }
 
-__global__ void __launch_bounds__(ATC_THREADS, 1)
+__global__ void __launch_bounds__(ATC_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
   uint8_t* sK = smem + TILE_BYTES;          // [2]
   uint8_t* sV = smem + 3 * TILE_BYTES;      // [2]
-  uint8_t* sP = smem + 5 * TILE_BYTES;      // [2][2 halves]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 9 * TILE_BYTES);
+  uint8_t* sP = smem + 5 * TILE_BYTES;      // [2 halves]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATC_TILES * TILE_BYTES);
+  if (threadIdx.x == 0 && (smem + ATC_TILES * TILE_BYTES + 256) > (smem_raw + ATC_SMEM)) {
+    printf("aptai attention: dynamic shared memory base misaligned beyond the slack\n");
+    __trap();
+  }
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
   uint64_t* kv_full = bars + 2;    // [2]
   uint64_t* kv_empty = bars + 4;   // [2]
-  uint64_t* s_full = bars + 6;     // [2]
-  uint64_t* s_empty = bars + 8;    // [2]
-  uint64_t* p_full = bars + 10;    // [2]
-  uint64_t* p_empty = bars + 12;   // [2]  (P_j V_j complete)
+  uint64_t* s_full = bars + 6;
+  uint64_t* p_full = bars + 10;    // P_j written (S consumed)
+  uint64_t* p_empty = bars + 12;   // P_j V_j complete
   uint64_t* o_full = bars + 14;
   uint64_t* o_empty = bars + 15;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
@@ -72,13 +78,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
     mbar_init(q_empty, 1);
     mbar_init(o_full, 1);
     mbar_init(o_empty, 4);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 4);
+    mbar_init(p_empty, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
-      mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 4);
-      mbar_init(&p_full[i], 4);
-      mbar_init(&p_empty[i], 1);
     }
     fence_mbar_init();
   }
@@ -125,32 +130,35 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
         mbar_wait(q_full, it & 1);
         tc_fence_after();
         const uint32_t q_addr = smem_u32(sQ);
+        // order: S_0 | P_0 ready -> S_1, P_0 V_0 | P_1 ready -> S_2, P_1 V_1 | ...
         for (int j = 0; j <= n; ++j) {
+          if (j >= 1) {
+            // P_{j-1} is in shared memory, and the softmax warps are done reading S_{j-1}
+            mbar_wait(p_full, (g + j - 1) & 1);
+          }
           if (j < n) {
             // S_j = Q K_j^T
             const uint32_t gj = g + j, s = gj & 1, u = gj >> 1;
             const int nj = min(AK, ((klen - j * AK) + 15) & ~15);
             mbar_wait(&kv_full[s], u & 1);
-            mbar_wait(&s_empty[s], (u & 1) ^ 1);
             tc_fence_after();
             const uint32_t k_addr = smem_u32(sK + s * TILE_BYTES);
             const uint32_t idesc = IDESC_BASE | (static_cast<uint32_t>(nj >> 3) << 17);
 #pragma unroll
             for (int k = 0; k < AD / 16; ++k)
-              umma_bf16(tmem_base + TM_S + s * AK, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32),
-                        idesc, k != 0 ? 1u : 0u);
-            umma_commit(&s_full[s]);
+              umma_bf16(tmem_base + TM_S, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), idesc,
+                        k != 0 ? 1u : 0u);
+            umma_commit(s_full);
             if (j == n - 1) umma_commit(q_empty);     // Q tile no longer needed once the last S is done
           }
           if (j >= 1) {
             // O += P_{j-1} V_{j-1}
             const int jj = j - 1;
-            const uint32_t gj = g + jj, s = gj & 1, u = gj >> 1;
+            const uint32_t gj = g + jj, s = gj & 1;
             const int nj = min(AK, ((klen - jj * AK) + 15) & ~15);
-            mbar_wait(&p_full[s], u & 1);
             if (jj == 0) mbar_wait(o_empty, (it & 1) ^ 1);     // previous item's O has been read out
             tc_fence_after();
-            const uint32_t p_addr = smem_u32(sP + s * 2 * TILE_BYTES);
+            const uint32_t p_addr = smem_u32(sP);
             const uint32_t v_addr = smem_u32(sV + s * TILE_BYTES);
             for (int k = 0; k < nj / 16; ++k) {
               const uint32_t pa = p_addr + (k >> 2) * TILE_BYTES + (k & 3) * 32;   // 64-key half, 16-key step
@@ -158,7 +166,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
                         (jj | k) != 0 ? 1u : 0u);
             }
             umma_commit(&kv_empty[s]);
-            umma_commit(&p_empty[s]);
+            umma_commit(p_empty);
             if (jj == n - 1) umma_commit(o_full);
           }
         }
@@ -179,23 +187,33 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
       const int n = (klen + AK - 1) / AK;
       float m_used = -INFINITY, l = 0.f;
       for (int j = 0; j < n; ++j, ++g) {
-        const uint32_t s = g & 1, u = g >> 1;
         const int valid = min(AK, klen - j * AK);          // keys of this tile that exist
         const int nchunk = (valid + 31) >> 5;
-        mbar_wait(&s_full[s], u & 1);
+        const bool full_tile = valid == AK;
+        mbar_wait(s_full, g & 1);
         tc_fence_after();
-        const uint32_t t_s = t_lane + TM_S + s * AK;
-        // pass A: row max over the valid keys (base-2 domain)
-        float mx = -INFINITY;
+        const uint32_t t_s = t_lane + TM_S;
+        // pass A: row max over the valid keys (four independent chains)
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
         for (int c = 0; c < nchunk; ++c) {
           uint32_t r[32];
           tmem_ld32(t_s + c * 32, r);
           tmem_ld_wait();
+          if (full_tile || (c + 1) * 32 <= valid) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+            for (int i = 0; i < 32; i += 4) {
+              mx0 = fmaxf(mx0, __uint_as_float(r[i]));
+              mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
+              mx2 = fmaxf(mx2, __uint_as_float(r[i + 2]));
+              mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < valid) mx0 = fmaxf(mx0, __uint_as_float(r[i]));
+          }
         }
-        mx *= ATC_LOG2E;
+        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * ATC_LOG2E;
         // lazy rescale: keep the stale max unless the new one exceeds it by more than 2^8
         float factor = 1.f;
         if (mx > m_used + RESCALE_THRESHOLD) {
@@ -203,10 +221,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
           m_used = mx;
         }
         const bool need = (factor != 1.f) && (j > 0);
+        // P_{j-1} V_{j-1} must be complete before O is rescaled in place and before P is overwritten
+        if (j > 0 || it > 0) mbar_wait(p_empty, (g - 1) & 1);
         if (__any_sync(0xffffffffu, need)) {
-          // O must be complete (P_{j-1} V_{j-1} done) before it is rescaled in place
-          const uint32_t gp = g - 1;
-          mbar_wait(&p_empty[gp & 1], (gp >> 1) & 1);
           tc_fence_after();
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
@@ -230,9 +247,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
         }
         l *= factor;
         // pass B: p = exp2(s*log2e - m_used); P -> shared memory (bf16, K-major SWIZZLE_128B, two 64-key halves)
-        mbar_wait(&p_empty[s], (u & 1) ^ 1);       // P_{j-2} V_{j-2} has consumed this P buffer
-        uint8_t* pbuf = sP + s * 2 * TILE_BYTES;
-        float rs = 0.f;
+        float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
         const int ncol16 = (valid + 15) >> 4;      // 16-key groups the P V MMA will read
         for (int c = 0; c < nchunk; ++c) {
           uint32_t r[32];
@@ -240,10 +255,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
           tmem_ld_wait();
           float pv[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float e = exp2f(fmaf(__uint_as_float(r[i]), ATC_LOG2E, -m_used));
-            pv[i] = (c * 32 + i < valid) ? e : 0.f;
-            rs += pv[i];
+          for (int i = 0; i < 32; ++i) pv[i] = exp2f(fmaf(__uint_as_float(r[i]), ATC_LOG2E, -m_used));
+          if (!(full_tile || (c + 1) * 32 <= valid)) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i >= valid) pv[i] = 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            rs0 += pv[i]; rs1 += pv[i + 1]; rs2 += pv[i + 2]; rs3 += pv[i + 3];
           }
 #pragma unroll
           for (int u8 = 0; u8 < 4; ++u8) {          // four 16-byte units (8 keys each) per 32-key chunk
@@ -252,19 +272,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
               const int half = key0 >> 6, unit = (key0 & 63) >> 3;
               uint4 v4 = make_uint4(pack_bf16(pv[u8 * 8 + 0], pv[u8 * 8 + 1]), pack_bf16(pv[u8 * 8 + 2], pv[u8 * 8 + 3]),
                                     pack_bf16(pv[u8 * 8 + 4], pv[u8 * 8 + 5]), pack_bf16(pv[u8 * 8 + 6], pv[u8 * 8 + 7]));
-              *reinterpret_cast<uint4*>(pbuf + half * TILE_BYTES + row * 128 + ((unit ^ (row & 7)) << 4)) = v4;
+              *reinterpret_cast<uint4*>(sP + half * TILE_BYTES + row * 128 + ((unit ^ (row & 7)) << 4)) = v4;
             }
           }
         }
-        l += rs;
-        // S buffer consumed; P visible to the async proxy (tensor core)
+        l += (rs0 + rs1) + (rs2 + rs3);
+        // S consumed; P visible to the async proxy (tensor core)
         tc_fence_before();
         fence_async_proxy();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&s_empty[s]);
-          mbar_arrive(&p_full[s]);
-        }
+        if (lane == 0) mbar_arrive(p_full);
       }
       // ---- output: O / l -> bf16
       mbar_wait(o_full, it & 1);
@@ -327,6 +344,7 @@ extern "C" int aptai_attention_fwd(const void* qkv, void* ctx, const int32_t* ke
   p.items = B * heads * p.n_qt;
   static bool attr_set = false;
   if (!attr_set) {
+    cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);
     if (e != cudaSuccess) {
       set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
@@ -334,7 +352,7 @@ extern "C" int aptai_attention_fwd(const void* qkv, void* ctx, const int32_t* ke
     }
     attr_set = true;
   }
-  const int grid = p.items < num_sms() ? p.items : num_sms();
+  const int grid = p.items < 2 * num_sms() ? p.items : 2 * num_sms();
   attention_tc_kernel<<<grid, ATC_THREADS, ATC_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tm, p);
   return after_launch("attention_tc");
 }

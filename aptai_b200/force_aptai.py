@@ -77,9 +77,8 @@ class Force_APTAI(nn.Module):
         phn_embs = self.phn_emb_layer(phn_pred_seq)
         phn_embs = self.pe_phn(phn_embs.permute(1, 0, 2)).permute(1, 0, 2)
         B, T, H = h.shape
-        fl = self.frame_lin                 # Linear(H,128) on the tcgen05 GEMM (bf16 operands, fp32 accumulate)
-        fh, _ = ops.linear(h.reshape(B * T, H).to(torch.bfloat16), fl.weight.detach().to(torch.bfloat16).contiguous(),
-                           fl.bias.detach().float().contiguous(), want_f32=True, want_bf16=False)
+        fl = self.frame_lin                 # Linear(H,128) on the tcgen05 GEMM, bf16x3 split (fp32-accurate)
+        fh = ops.linear_f32x3(h.reshape(B * T, H).contiguous(), fl.weight, fl.bias.detach().float().contiguous())
         frame_hidden_emb = self.frame_drop(fh.view(B, T, -1))
         att_out, energy = self.xatt(frame_hidden_emb, phn_embs, phn_pred_mask)
         att_mask = ((1 - phn_pred_mask) * -1000.0).unsqueeze(1)

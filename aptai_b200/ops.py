@@ -94,6 +94,22 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     return out_f32, out_bf16
 
 
+def linear_f32x3(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """fp32-accurate Linear on the bf16 tensor cores: x = x_hi + x_lo, w = w_hi + w_lo (bf16 pairs) and
+    out = [x_hi | x_lo | x_hi] @ [w_hi | w_hi | w_lo]^T (K tripled; the dropped x_lo*w_lo term is ~2^-18 relative).
+    For small projections whose input must not be re-quantised (Force_APTAI's frame_lin)."""
+    _req(x, F32, "x")
+    xh = x.to(BF16)
+    xl = (x - xh.float()).to(BF16)
+    wf = w.detach().float()
+    wh = wf.to(BF16)
+    wl = (wf - wh.float()).to(BF16)
+    a = torch.cat([xh, xl, xh], dim=1).contiguous()
+    ww = torch.cat([wh, wh, wl], dim=1).contiguous()
+    out, _ = linear(a, ww, bias, want_f32=True, want_bf16=False)
+    return out
+
+
 def conv_igemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], k: int, stride: int, *,
                ln_gamma: Optional[torch.Tensor] = None, ln_beta: Optional[torch.Tensor] = None,
                eps: float = 1e-5, act: int = 1, out: Optional[torch.Tensor] = None, cta_pair: int = 0) -> torch.Tensor:
