@@ -16,6 +16,8 @@
 #include "common.h"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 namespace aptai {
 
 constexpr int AQ = 128;                 // query rows per work item
@@ -24,7 +26,7 @@ constexpr int AD = 64;                  // head dim
 constexpr int ATC_THREADS = 256;        // warps 0,1 (+2 TMEM alloc, 3 idle), 4..7 softmax
 constexpr int TILE_BYTES = AK * AD * 2; // 16 KB: Q, K_j, V_j tiles; one 64-key half of P
 constexpr int ATC_TILES = 1 + 2 + 2 + 2;                       // Q, K[2], V[2], P (two 64-key halves)
-constexpr int ATC_SMEM = TILE_BYTES * ATC_TILES + 256 + 768;   // + barriers + alignment slack; 2 CTAs fit one SM
+constexpr int ATC_SMEM = TILE_BYTES * ATC_TILES + 256;         // + barriers; two CTAs fit one SM (2 x 112.25 KB)
 constexpr uint32_t TM_S = 0, TM_O = 128, TM_COLS = 256;
 constexpr float ATC_LOG2E = 1.4426950408889634f;
 constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units
@@ -34,6 +36,12 @@ struct AttnParams {
   __nv_bfloat16* ctx;
   int B, T, heads, H, n_qt, items;
 };
+
+__device__ __forceinline__ float ex2_approx(float x) {   // single MUFU.EX2 (flushes denormal results to 0)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // MN-major SWIZZLE_128B descriptor for a B operand stored [k rows][64 mn-elements] (128 B per k row):
 // 8-row groups along K are 1024 B apart (SBO); a single 64-element MN block, so LBO is unused.
@@ -49,15 +57,15 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t saddr) {
 
 __global__ void __launch_bounds__(ATC_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
   uint8_t* sQ = smem;
   uint8_t* sK = smem + TILE_BYTES;          // [2]
   uint8_t* sV = smem + 3 * TILE_BYTES;      // [2]
   uint8_t* sP = smem + 5 * TILE_BYTES;      // [2 halves]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATC_TILES * TILE_BYTES);
-  if (threadIdx.x == 0 && (smem + ATC_TILES * TILE_BYTES + 256) > (smem_raw + ATC_SMEM)) {
-    printf("aptai attention: dynamic shared memory base misaligned beyond the slack\n");
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("aptai attention: dynamic shared memory base is not 1024-byte aligned\n");
     __trap();
   }
   uint64_t* q_full = bars + 0;
@@ -255,7 +263,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
           tmem_ld_wait();
           float pv[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) pv[i] = exp2f(fmaf(__uint_as_float(r[i]), ATC_LOG2E, -m_used));
+          for (int i = 0; i < 32; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(r[i]), ATC_LOG2E, -m_used));
           if (!(full_tile || (c + 1) * 32 <= valid)) {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
@@ -352,7 +360,14 @@ extern "C" int aptai_attention_fwd(const void* qkv, void* ctx, const int32_t* ke
     }
     attr_set = true;
   }
-  const int grid = p.items < 2 * num_sms() ? p.items : 2 * num_sms();
+  static int ctas_per_sm = 0;
+  if (ctas_per_sm == 0) {
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, attention_tc_kernel, ATC_THREADS, ATC_SMEM);
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    if (ctas_per_sm > 2) ctas_per_sm = 2;
+    if (getenv("APTAI_DEBUG")) fprintf(stderr, "aptai attention: %d CTAs per SM\n", ctas_per_sm);
+  }
+  const int grid = p.items < ctas_per_sm * num_sms() ? p.items : ctas_per_sm * num_sms();
   attention_tc_kernel<<<grid, ATC_THREADS, ATC_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tm, p);
   return after_launch("attention_tc");
 }
