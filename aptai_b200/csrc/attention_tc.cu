@@ -1,9 +1,10 @@
 // tcgen05 / TMEM fused attention forward (HF:500-549 with SDPA semantics: non-causal, key-padding mask).
 //
 // Persistent, warp-specialised, one work item = 128 query rows of one (utterance, head); two CTAs are resident
-// per SM (256 TMEM columns and ~113 KB of shared memory each) so that one CTA's softmax (MUFU-bound) overlaps the
+// per SM (256 TMEM columns and ~80 KB of shared memory each) so that one CTA's softmax (MUFU-bound) overlaps the
 // other's MMAs and loads:
-//   warp 0      TMA producer   Q tile once per item; K_j / V_j tiles (128 keys x 64) through a 2-stage ring
+//   warp 0      TMA producer   Q tile once per item; K_j and V_j tiles (128 keys x 64), one buffer each: K_{j+1} is
+//                              fetched as soon as S_j has consumed K_j, V_{j+1} as soon as P_j V_j has consumed V_j
 //   warp 1      MMA issuer     S_j = Q K_j^T  (M=128, N=n_j, K=64)   -> TMEM S
 //                              O  += P_j V_j  (M=128, N=64,  K=n_j)  -> TMEM O, P_j from shared memory (bf16),
 //                                                                       V_j as an MN-major B operand
@@ -25,8 +26,8 @@ constexpr int AK = 128;                 // keys per KV tile
 constexpr int AD = 64;                  // head dim
 constexpr int ATC_THREADS = 256;        // warps 0,1 (+2 TMEM alloc, 3 idle), 4..7 softmax
 constexpr int TILE_BYTES = AK * AD * 2; // 16 KB: Q, K_j, V_j tiles; one 64-key half of P
-constexpr int ATC_TILES = 1 + 2 + 2 + 2;                       // Q, K[2], V[2], P (two 64-key halves)
-constexpr int ATC_SMEM = TILE_BYTES * ATC_TILES + 256;         // + barriers; two CTAs fit one SM (2 x 112.25 KB)
+constexpr int ATC_TILES = 1 + 1 + 1 + 2;                       // Q, K, V, P (two 64-key halves)
+constexpr int ATC_SMEM = TILE_BYTES * ATC_TILES + 256;         // + barriers; two CTAs fit one SM (2 x 80.25 KB)
 constexpr uint32_t TM_S = 0, TM_O = 128, TM_COLS = 256;
 constexpr float ATC_LOG2E = 1.4426950408889634f;
 constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units
@@ -60,9 +61,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   uint8_t* sQ = smem;
-  uint8_t* sK = smem + TILE_BYTES;          // [2]
-  uint8_t* sV = smem + 3 * TILE_BYTES;      // [2]
-  uint8_t* sP = smem + 5 * TILE_BYTES;      // [2 halves]
+  uint8_t* sK = smem + TILE_BYTES;
+  uint8_t* sV = smem + 2 * TILE_BYTES;
+  uint8_t* sP = smem + 3 * TILE_BYTES;      // [2 halves]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATC_TILES * TILE_BYTES);
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("aptai attention: dynamic shared memory base is not 1024-byte aligned\n");
@@ -70,8 +71,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
   }
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
-  uint64_t* kv_full = bars + 2;    // [2]
-  uint64_t* kv_empty = bars + 4;   // [2]
+  uint64_t* k_full = bars + 2;
+  uint64_t* k_empty = bars + 3;    // S_j complete
+  uint64_t* v_full = bars + 4;
+  uint64_t* v_empty = bars + 5;    // P_j V_j complete
   uint64_t* s_full = bars + 6;
   uint64_t* p_full = bars + 10;    // P_j written (S consumed)
   uint64_t* p_empty = bars + 12;   // P_j V_j complete
@@ -89,10 +92,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
     mbar_init(s_full, 1);
     mbar_init(p_full, 4);
     mbar_init(p_empty, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
-    }
+    mbar_init(k_full, 1);
+    mbar_init(k_empty, 1);
+    mbar_init(v_full, 1);
+    mbar_init(v_empty, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, TM_COLS);
@@ -116,11 +119,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
         mbar_expect_tx(q_full, TILE_BYTES);
         tma_load_2d(&tmQKV, q_full, sQ, h * AD, row0 + qt * AQ);
         for (int j = 0; j < n; ++j, ++g) {
-          const uint32_t s = g & 1, u = g >> 1;
-          mbar_wait(&kv_empty[s], (u & 1) ^ 1);
-          mbar_expect_tx(&kv_full[s], 2 * TILE_BYTES);
-          tma_load_2d(&tmQKV, &kv_full[s], sK + s * TILE_BYTES, p.H + h * AD, row0 + j * AK);
-          tma_load_2d(&tmQKV, &kv_full[s], sV + s * TILE_BYTES, 2 * p.H + h * AD, row0 + j * AK);
+          mbar_wait(k_empty, (g & 1) ^ 1);
+          mbar_expect_tx(k_full, TILE_BYTES);
+          tma_load_2d(&tmQKV, k_full, sK, p.H + h * AD, row0 + j * AK);
+          mbar_wait(v_empty, (g & 1) ^ 1);
+          mbar_expect_tx(v_full, TILE_BYTES);
+          tma_load_2d(&tmQKV, v_full, sV, 2 * p.H + h * AD, row0 + j * AK);
         }
       }
     }
@@ -146,34 +150,34 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
           }
           if (j < n) {
             // S_j = Q K_j^T
-            const uint32_t gj = g + j, s = gj & 1, u = gj >> 1;
             const int nj = min(AK, ((klen - j * AK) + 15) & ~15);
-            mbar_wait(&kv_full[s], u & 1);
+            mbar_wait(k_full, (g + j) & 1);
             tc_fence_after();
-            const uint32_t k_addr = smem_u32(sK + s * TILE_BYTES);
+            const uint32_t k_addr = smem_u32(sK);
             const uint32_t idesc = IDESC_BASE | (static_cast<uint32_t>(nj >> 3) << 17);
 #pragma unroll
             for (int k = 0; k < AD / 16; ++k)
               umma_bf16(tmem_base + TM_S, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), idesc,
                         k != 0 ? 1u : 0u);
             umma_commit(s_full);
+            umma_commit(k_empty);
             if (j == n - 1) umma_commit(q_empty);     // Q tile no longer needed once the last S is done
           }
           if (j >= 1) {
             // O += P_{j-1} V_{j-1}
             const int jj = j - 1;
-            const uint32_t gj = g + jj, s = gj & 1;
             const int nj = min(AK, ((klen - jj * AK) + 15) & ~15);
+            mbar_wait(v_full, (g + jj) & 1);
             if (jj == 0) mbar_wait(o_empty, (it & 1) ^ 1);     // previous item's O has been read out
             tc_fence_after();
             const uint32_t p_addr = smem_u32(sP);
-            const uint32_t v_addr = smem_u32(sV + s * TILE_BYTES);
+            const uint32_t v_addr = smem_u32(sV);
             for (int k = 0; k < nj / 16; ++k) {
               const uint32_t pa = p_addr + (k >> 2) * TILE_BYTES + (k & 3) * 32;   // 64-key half, 16-key step
               umma_bf16(tmem_base + TM_O, umma_desc_sw128(pa), umma_desc_sw128_mn(v_addr + k * 2048), IDESC_PV,
                         (jj | k) != 0 ? 1u : 0u);
             }
-            umma_commit(&kv_empty[s]);
+            umma_commit(v_empty);
             umma_commit(p_empty);
             if (jj == n - 1) umma_commit(o_full);
           }
