@@ -366,10 +366,12 @@ extern "C" int aptai_attention_fwd(const void* qkv, void* ctx, const int32_t* ke
   }
   static int ctas_per_sm = 0;
   if (ctas_per_sm == 0) {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, attention_tc_kernel, ATC_THREADS, ATC_SMEM);
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
-    if (ctas_per_sm > 2) ctas_per_sm = 2;
-    if (getenv("APTAI_DEBUG")) fprintf(stderr, "aptai attention: %d CTAs per SM\n", ctas_per_sm);
+    int n = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, attention_tc_kernel, ATC_THREADS, ATC_SMEM);
+    if (getenv("APTAI_DEBUG"))
+      fprintf(stderr, "aptai attention: occupancy query -> %d CTAs per SM (%s)\n", n, cudaGetErrorString(e));
+    cudaGetLastError();
+    ctas_per_sm = 2;      // two CTAs per SM are intended (80 KB smem, 256 TMEM columns, <= 128 registers each)
   }
   const int grid = p.items < ctas_per_sm * num_sms() ? p.items : ctas_per_sm * num_sms();
   attention_tc_kernel<<<grid, ATC_THREADS, ATC_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tm, p);
