@@ -1,17 +1,16 @@
 // tcgen05 / TMEM fused attention forward (HF:500-549 with SDPA semantics: non-causal, key-padding mask).
 //
 // Persistent, warp-specialised, one work item = 128 query rows of one (utterance, head); two CTAs are resident
-// per SM (256 TMEM columns and ~80 KB of shared memory each) so that one CTA's softmax (MUFU-bound) overlaps the
-// other's MMAs and loads:
-//   warp 0      TMA producer   Q tile once per item; K_j and V_j tiles (128 keys x 64), one buffer each: K_{j+1} is
-//                              fetched as soon as S_j has consumed K_j, V_{j+1} as soon as P_j V_j has consumed V_j
-//   warp 1      MMA issuer     S_j = Q K_j^T  (M=128, N=n_j, K=64)   -> TMEM S
-//                              O  += P_j V_j  (M=128, N=64,  K=n_j)  -> TMEM O, P_j from shared memory (bf16),
-//                                                                       V_j as an MN-major B operand
+// per SM (256 TMEM columns and 96 KB of shared memory each) so that the softmax warps of both keep the MUFU busy:
+//   warp 0      TMA producer   Q tile once per item; (K_j, V_j) tiles of 64 keys through a 3-stage ring
+//   warp 1      MMA issuer     S_j = Q K_j^T  (M=128, N=n_j<=64, K=64) -> TMEM S buffer j%2 (double buffered)
+//                              O  += P_j V_j  (M=128, N=64, K=n_j)     -> TMEM O; P_j (bf16) from shared memory,
+//                                                                         V_j as an MN-major B operand
 //   warps 4..7  softmax        thread i owns query row i: tcgen05.ld of its S row, key-length mask, running max
 //                              with lazy rescaling of O (only when the max grows by more than 2^8), exp2, row sum,
 //                              P_j -> shared memory in the UMMA K-major SWIZZLE_128B layout; final O / l -> bf16
-// S_{j+1} is issued right behind P_j (S is free once P_j is written) and ahead of P_j V_j.
+// S_{j+2} is issued as soon as P_j is written (S buffer j%2 free), so S_{j+1} is always ready when the softmax
+// warps finish tile j: they never wait on the tensor core in steady state.
 // q must be pre-scaled by head_dim^-0.5 (folded into the q projection at plan time); head_dim is 64.
 // Every query row is computed (padded queries attend to valid keys, HF:438-463); keys >= key_len[b] are masked.
 #include "common.h"
@@ -22,13 +21,16 @@
 namespace aptai {
 
 constexpr int AQ = 128;                 // query rows per work item
-constexpr int AK = 128;                 // keys per KV tile
+constexpr int AK = 64;                  // keys per KV tile
 constexpr int AD = 64;                  // head dim
 constexpr int ATC_THREADS = 256;        // warps 0,1 (+2 TMEM alloc, 3 idle), 4..7 softmax
-constexpr int TILE_BYTES = AK * AD * 2; // 16 KB: Q, K_j, V_j tiles; one 64-key half of P
-constexpr int ATC_TILES = 1 + 1 + 1 + 2;                       // Q, K, V, P (two 64-key halves)
-constexpr int ATC_SMEM = TILE_BYTES * ATC_TILES + 256;         // + barriers; two CTAs fit one SM (2 x 80.25 KB)
-constexpr uint32_t TM_S = 0, TM_O = 128, TM_COLS = 256;
+constexpr int Q_BYTES = AQ * AD * 2;    // 16 KB
+constexpr int KV_BYTES = AK * AD * 2;   // 8 KB per K or V tile
+constexpr int P_BYTES = AQ * AK * 2;    // 16 KB
+constexpr int KV_STAGES = 3;
+constexpr int ATC_DATA = Q_BYTES + KV_STAGES * 2 * KV_BYTES + 2 * P_BYTES;   // 96 KB
+constexpr int ATC_SMEM = ATC_DATA + 256;                                     // + barriers; two CTAs fit one SM
+constexpr uint32_t TM_S = 0, TM_O = 128, TM_COLS = 256;   // S double buffered (2 x 64 columns), O 64 columns
 constexpr float ATC_LOG2E = 1.4426950408889634f;
 constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units
 
@@ -57,45 +59,47 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t saddr) {
 }
 
 __global__ void __launch_bounds__(ATC_THREADS, 2)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams p) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw;
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                    const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
-  uint8_t* sK = smem + TILE_BYTES;
-  uint8_t* sV = smem + 2 * TILE_BYTES;
-  uint8_t* sP = smem + 3 * TILE_BYTES;      // [2 halves]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATC_TILES * TILE_BYTES);
+  uint8_t* sKV = smem + Q_BYTES;                               // [stage][K | V]
+  uint8_t* sP = smem + Q_BYTES + KV_STAGES * 2 * KV_BYTES;     // [2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATC_DATA);
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("aptai attention: dynamic shared memory base is not 1024-byte aligned\n");
     __trap();
   }
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
-  uint64_t* k_full = bars + 2;
-  uint64_t* k_empty = bars + 3;    // S_j complete
-  uint64_t* v_full = bars + 4;
-  uint64_t* v_empty = bars + 5;    // P_j V_j complete
-  uint64_t* s_full = bars + 6;
-  uint64_t* p_full = bars + 10;    // P_j written (S consumed)
-  uint64_t* p_empty = bars + 12;   // P_j V_j complete
-  uint64_t* o_full = bars + 14;
-  uint64_t* o_empty = bars + 15;
+  uint64_t* o_full = bars + 2;
+  uint64_t* o_empty = bars + 3;
+  uint64_t* kv_full = bars + 4;    // [3]
+  uint64_t* kv_empty = bars + 7;   // [3]  P_j V_j complete
+  uint64_t* s_full = bars + 10;    // [2]
+  uint64_t* p_full = bars + 12;    // [2]  P_j written (and S_j consumed)
+  uint64_t* p_empty = bars + 14;   // [2]  P_j V_j complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) tma_prefetch_desc(&tmQKV);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+  }
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
     mbar_init(o_full, 1);
     mbar_init(o_empty, 4);
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 4);
-    mbar_init(p_empty, 1);
-    mbar_init(k_full, 1);
-    mbar_init(k_empty, 1);
-    mbar_init(v_full, 1);
-    mbar_init(v_empty, 1);
+    for (int i = 0; i < KV_STAGES; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&p_empty[i], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, TM_COLS);
@@ -116,15 +120,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
         const int n = (klen + AK - 1) / AK;
         const int row0 = b * p.T;
         mbar_wait(q_empty, (it & 1) ^ 1);
-        mbar_expect_tx(q_full, TILE_BYTES);
-        tma_load_2d(&tmQKV, q_full, sQ, h * AD, row0 + qt * AQ);
+        mbar_expect_tx(q_full, Q_BYTES);
+        tma_load_2d(&tmQ, q_full, sQ, h * AD, row0 + qt * AQ);
         for (int j = 0; j < n; ++j, ++g) {
-          mbar_wait(k_empty, (g & 1) ^ 1);
-          mbar_expect_tx(k_full, TILE_BYTES);
-          tma_load_2d(&tmQKV, k_full, sK, p.H + h * AD, row0 + j * AK);
-          mbar_wait(v_empty, (g & 1) ^ 1);
-          mbar_expect_tx(v_full, TILE_BYTES);
-          tma_load_2d(&tmQKV, v_full, sV, 2 * p.H + h * AD, row0 + j * AK);
+          const uint32_t st = g % KV_STAGES, u = g / KV_STAGES;
+          mbar_wait(&kv_empty[st], (u & 1) ^ 1);
+          mbar_expect_tx(&kv_full[st], 2 * KV_BYTES);
+          tma_load_2d(&tmKV, &kv_full[st], sKV + st * 2 * KV_BYTES, p.H + h * AD, row0 + j * AK);
+          tma_load_2d(&tmKV, &kv_full[st], sKV + st * 2 * KV_BYTES + KV_BYTES, 2 * p.H + h * AD, row0 + j * AK);
         }
       }
     }
@@ -142,45 +145,37 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
         mbar_wait(q_full, it & 1);
         tc_fence_after();
         const uint32_t q_addr = smem_u32(sQ);
-        // order: S_0 | P_0 ready -> S_1, P_0 V_0 | P_1 ready -> S_2, P_1 V_1 | ...
-        for (int j = 0; j <= n; ++j) {
-          if (j >= 1) {
-            // P_{j-1} is in shared memory, and the softmax warps are done reading S_{j-1}
-            mbar_wait(p_full, (g + j - 1) & 1);
-          }
-          if (j < n) {
-            // S_j = Q K_j^T
-            const int nj = min(AK, ((klen - j * AK) + 15) & ~15);
-            mbar_wait(k_full, (g + j) & 1);
-            tc_fence_after();
-            const uint32_t k_addr = smem_u32(sK);
-            const uint32_t idesc = IDESC_BASE | (static_cast<uint32_t>(nj >> 3) << 17);
+        auto issue_s = [&](int j) {                       // S_j = Q K_j^T into S buffer (g+j)&1
+          const uint32_t gj = g + j, st = gj % KV_STAGES, u = gj / KV_STAGES;
+          const int nj = min(AK, ((klen - j * AK) + 15) & ~15);
+          mbar_wait(&kv_full[st], u & 1);
+          tc_fence_after();
+          const uint32_t k_addr = smem_u32(sKV + st * 2 * KV_BYTES);
+          const uint32_t idesc = IDESC_BASE | (static_cast<uint32_t>(nj >> 3) << 17);
 #pragma unroll
-            for (int k = 0; k < AD / 16; ++k)
-              umma_bf16(tmem_base + TM_S, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), idesc,
-                        k != 0 ? 1u : 0u);
-            umma_commit(s_full);
-            umma_commit(k_empty);
-            if (j == n - 1) umma_commit(q_empty);     // Q tile no longer needed once the last S is done
-          }
-          if (j >= 1) {
-            // O += P_{j-1} V_{j-1}
-            const int jj = j - 1;
-            const int nj = min(AK, ((klen - jj * AK) + 15) & ~15);
-            mbar_wait(v_full, (g + jj) & 1);
-            if (jj == 0) mbar_wait(o_empty, (it & 1) ^ 1);     // previous item's O has been read out
-            tc_fence_after();
-            const uint32_t p_addr = smem_u32(sP);
-            const uint32_t v_addr = smem_u32(sV);
-            for (int k = 0; k < nj / 16; ++k) {
-              const uint32_t pa = p_addr + (k >> 2) * TILE_BYTES + (k & 3) * 32;   // 64-key half, 16-key step
-              umma_bf16(tmem_base + TM_O, umma_desc_sw128(pa), umma_desc_sw128_mn(v_addr + k * 2048), IDESC_PV,
-                        (jj | k) != 0 ? 1u : 0u);
-            }
-            umma_commit(v_empty);
-            umma_commit(p_empty);
-            if (jj == n - 1) umma_commit(o_full);
-          }
+          for (int k = 0; k < AD / 16; ++k)
+            umma_bf16(tmem_base + TM_S + (gj & 1) * AK, umma_desc_sw128(q_addr + k * 32),
+                      umma_desc_sw128(k_addr + k * 32), idesc, k != 0 ? 1u : 0u);
+          umma_commit(&s_full[gj & 1]);
+          if (j == n - 1) umma_commit(q_empty);           // Q tile no longer needed once the last S is done
+        };
+        issue_s(0);
+        if (n > 1) issue_s(1);
+        for (int j = 0; j < n; ++j) {
+          const uint32_t gj = g + j, sb = gj & 1, st = gj % KV_STAGES;
+          const int nj = min(AK, ((klen - j * AK) + 15) & ~15);
+          mbar_wait(&p_full[sb], (gj >> 1) & 1);          // P_j in shared memory, S_j consumed
+          if (j + 2 < n) issue_s(j + 2);                  // refill the S buffer that just became free
+          if (j == 0) mbar_wait(o_empty, (it & 1) ^ 1);   // previous item's O has been read out
+          tc_fence_after();
+          const uint32_t p_addr = smem_u32(sP + sb * P_BYTES);
+          const uint32_t v_addr = smem_u32(sKV + st * 2 * KV_BYTES + KV_BYTES);
+          for (int k = 0; k < nj / 16; ++k)
+            umma_bf16(tmem_base + TM_O, umma_desc_sw128(p_addr + k * 32), umma_desc_sw128_mn(v_addr + k * 2048),
+                      IDESC_PV, (j | k) != 0 ? 1u : 0u);
+          umma_commit(&kv_empty[st]);
+          umma_commit(&p_empty[sb]);
+          if (j == n - 1) umma_commit(o_full);
         }
         g += n;
       }
@@ -199,30 +194,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
       const int n = (klen + AK - 1) / AK;
       float m_used = -INFINITY, l = 0.f;
       for (int j = 0; j < n; ++j, ++g) {
+        const uint32_t sb = g & 1, u = g >> 1;
         const int valid = min(AK, klen - j * AK);          // keys of this tile that exist
-        const int nchunk = (valid + 31) >> 5;
         const bool full_tile = valid == AK;
-        mbar_wait(s_full, g & 1);
+        mbar_wait(&s_full[sb], u & 1);
         tc_fence_after();
-        const uint32_t t_s = t_lane + TM_S;
-        // pass A: row max over the valid keys (four independent chains)
+        const uint32_t t_s = t_lane + TM_S + sb * AK;
+        uint32_t r0[32], r1[32];
+        tmem_ld32(t_s, r0);
+        tmem_ld32(t_s + 32, r1);
+        tmem_ld_wait();
+        // row max over the valid keys (four independent chains)
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-        for (int c = 0; c < nchunk; ++c) {
-          uint32_t r[32];
-          tmem_ld32(t_s + c * 32, r);
-          tmem_ld_wait();
-          if (full_tile || (c + 1) * 32 <= valid) {
+        if (full_tile) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              mx0 = fmaxf(mx0, __uint_as_float(r[i]));
-              mx1 = fmaxf(mx1, __uint_as_float(r[i + 1]));
-              mx2 = fmaxf(mx2, __uint_as_float(r[i + 2]));
-              mx3 = fmaxf(mx3, __uint_as_float(r[i + 3]));
-            }
-          } else {
+          for (int i = 0; i < 32; i += 4) {
+            mx0 = fmaxf(mx0, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
+            mx1 = fmaxf(mx1, fmaxf(__uint_as_float(r0[i + 1]), __uint_as_float(r1[i + 1])));
+            mx2 = fmaxf(mx2, fmaxf(__uint_as_float(r0[i + 2]), __uint_as_float(r1[i + 2])));
+            mx3 = fmaxf(mx3, fmaxf(__uint_as_float(r0[i + 3]), __uint_as_float(r1[i + 3])));
+          }
+        } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i < valid) mx0 = fmaxf(mx0, __uint_as_float(r[i]));
+          for (int i = 0; i < 32; ++i) {
+            if (i < valid) mx0 = fmaxf(mx0, __uint_as_float(r0[i]));
+            if (32 + i < valid) mx1 = fmaxf(mx1, __uint_as_float(r1[i]));
           }
         }
         const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * ATC_LOG2E;
@@ -233,9 +229,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
           m_used = mx;
         }
         const bool need = (factor != 1.f) && (j > 0);
-        // P_{j-1} V_{j-1} must be complete before O is rescaled in place and before P is overwritten
-        if (j > 0 || it > 0) mbar_wait(p_empty, (g - 1) & 1);
         if (__any_sync(0xffffffffu, need)) {
+          // O must be complete (P_{j-1} V_{j-1} done) before it is rescaled in place
+          const uint32_t gp = g - 1;
+          mbar_wait(&p_empty[gp & 1], (gp >> 1) & 1);
           tc_fence_after();
 #pragma unroll
           for (int c = 0; c < 2; ++c) {
@@ -258,17 +255,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
         l *= factor;
-        // pass B: p = exp2(s*log2e - m_used); P -> shared memory (bf16, K-major SWIZZLE_128B, two 64-key halves)
+        // p = exp2(s*log2e - m_used); P -> shared memory (bf16, K-major SWIZZLE_128B rows of 64 keys)
+        mbar_wait(&p_empty[sb], (u & 1) ^ 1);      // P_{j-2} V_{j-2} has consumed this P buffer
+        uint8_t* prow = sP + sb * P_BYTES + row * 128;
         float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
         const int ncol16 = (valid + 15) >> 4;      // 16-key groups the P V MMA will read
-        for (int c = 0; c < nchunk; ++c) {
-          uint32_t r[32];
-          tmem_ld32(t_s + c * 32, r);
-          tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
           float pv[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) pv[i] = ex2_approx(fmaf(__uint_as_float(r[i]), ATC_LOG2E, -m_used));
-          if (!(full_tile || (c + 1) * 32 <= valid)) {
+          for (int i = 0; i < 32; ++i)
+            pv[i] = ex2_approx(fmaf(__uint_as_float(c == 0 ? r0[i] : r1[i]), ATC_LOG2E, -m_used));
+          if (!full_tile) {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
               if (c * 32 + i >= valid) pv[i] = 0.f;
@@ -279,12 +277,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
           }
 #pragma unroll
           for (int u8 = 0; u8 < 4; ++u8) {          // four 16-byte units (8 keys each) per 32-key chunk
-            const int key0 = c * 32 + u8 * 8;
-            if ((key0 >> 4) < ncol16) {
-              const int half = key0 >> 6, unit = (key0 & 63) >> 3;
+            const int unit = c * 4 + u8;
+            if ((unit >> 1) < ncol16) {
               uint4 v4 = make_uint4(pack_bf16(pv[u8 * 8 + 0], pv[u8 * 8 + 1]), pack_bf16(pv[u8 * 8 + 2], pv[u8 * 8 + 3]),
                                     pack_bf16(pv[u8 * 8 + 4], pv[u8 * 8 + 5]), pack_bf16(pv[u8 * 8 + 6], pv[u8 * 8 + 7]));
-              *reinterpret_cast<uint4*>(sP + half * TILE_BYTES + row * 128 + ((unit ^ (row & 7)) << 4)) = v4;
+              *reinterpret_cast<uint4*>(prow + ((unit ^ (row & 7)) << 4)) = v4;
             }
           }
         }
@@ -293,7 +290,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const AttnParams 
         tc_fence_before();
         fence_async_proxy();
         __syncwarp();
-        if (lane == 0) mbar_arrive(p_full);
+        if (lane == 0) mbar_arrive(&p_full[sb]);
       }
       // ---- output: O / l -> bf16
       mbar_wait(o_full, it & 1);
@@ -341,12 +338,14 @@ extern "C" int aptai_attention_fwd(const void* qkv, void* ctx, const int32_t* ke
   APTAI_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(ctx) & 15) == 0,
                 "attention: buffers must be 16-byte aligned");
   const int H = heads * AD;
-  CUtensorMap tm;
+  CUtensorMap tmq, tmkv;
   {
     uint64_t dims[2] = {static_cast<uint64_t>(3) * H, static_cast<uint64_t>(B) * T};
     uint64_t strides[1] = {static_cast<uint64_t>(3) * H * 2};
-    uint32_t box[2] = {AD, AK};
-    if (int rc = encode_tmap_bf16(&tm, qkv, 2, dims, strides, box, 1)) return rc;
+    uint32_t boxq[2] = {AD, AQ};
+    uint32_t boxkv[2] = {AD, AK};
+    if (int rc = encode_tmap_bf16(&tmq, qkv, 2, dims, strides, boxq, 1)) return rc;
+    if (int rc = encode_tmap_bf16(&tmkv, qkv, 2, dims, strides, boxkv, 1)) return rc;
   }
   AttnParams p;
   p.key_len = key_len;
@@ -374,6 +373,6 @@ extern "C" int aptai_attention_fwd(const void* qkv, void* ctx, const int32_t* ke
     ctas_per_sm = 2;      // two CTAs per SM are intended (80 KB smem, 256 TMEM columns, <= 128 registers each)
   }
   const int grid = p.items < ctas_per_sm * num_sms() ? p.items : ctas_per_sm * num_sms();
-  attention_tc_kernel<<<grid, ATC_THREADS, ATC_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tm, p);
+  attention_tc_kernel<<<grid, ATC_THREADS, ATC_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tmq, tmkv, p);
   return after_launch("attention_tc");
 }
