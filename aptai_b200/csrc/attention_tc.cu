@@ -119,12 +119,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int klen = max(1, min(__ldg(p.key_len + b), p.T));
         const int n = (klen + AK - 1) / AK;
         const int row0 = b * p.T;
-        mbar_wait(q_empty, (it & 1) ^ 1);
+        mbar_wait_backoff(q_empty, (it & 1) ^ 1, 100);
         mbar_expect_tx(q_full, Q_BYTES);
         tma_load_2d(&tmQ, q_full, sQ, h * AD, row0 + qt * AQ);
         for (int j = 0; j < n; ++j, ++g) {
           const uint32_t st = g % KV_STAGES, u = g / KV_STAGES;
-          mbar_wait(&kv_empty[st], (u & 1) ^ 1);
+          mbar_wait_backoff(&kv_empty[st], (u & 1) ^ 1, 100);
           mbar_expect_tx(&kv_full[st], 2 * KV_BYTES);
           tma_load_2d(&tmKV, &kv_full[st], sKV + st * 2 * KV_BYTES, p.H + h * AD, row0 + j * AK);
           tma_load_2d(&tmKV, &kv_full[st], sKV + st * 2 * KV_BYTES + KV_BYTES, 2 * p.H + h * AD, row0 + j * AK);
@@ -164,7 +164,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int j = 0; j < n; ++j) {
           const uint32_t gj = g + j, sb = gj & 1, st = gj % KV_STAGES;
           const int nj = min(AK, ((klen - j * AK) + 15) & ~15);
-          mbar_wait(&p_full[sb], (gj >> 1) & 1);          // P_j in shared memory, S_j consumed
+          mbar_wait_backoff(&p_full[sb], (gj >> 1) & 1, 32);   // P_j in shared memory, S_j consumed
           if (j + 2 < n) issue_s(j + 2);                  // refill the S buffer that just became free
           if (j == 0) mbar_wait(o_empty, (it & 1) ^ 1);   // previous item's O has been read out
           tc_fence_after();

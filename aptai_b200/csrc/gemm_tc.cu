@@ -121,7 +121,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         const int r0 = (mt - seg * p.m_tiles_per_seg) * TILE_M + static_cast<int>(rank) * BLOCK_M;
         const int a_col0 = n_blk * p.a_col_per_nblk;
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait_backoff(&empty_bar[stage], phase ^ 1, 64);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
           const int tap = kb / p.kb_per_tap;

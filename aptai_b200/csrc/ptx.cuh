@@ -63,6 +63,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// wait with back-off for single-thread roles whose wake-up latency is not critical (TMA producers): the spin loop
+// would otherwise steal issue slots from the compute warps that share its scheduler
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (++spins > (APTAI_SPIN_LIMIT >> 4)) {
+      printf("aptai: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+
 // ---------------------------------------------------------------- proxies / fences
 __device__ __forceinline__ void fence_async_proxy() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
