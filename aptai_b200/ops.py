@@ -167,7 +167,9 @@ def conv0(wav: torch.Tensor, w: torch.Tensor, bias, gamma, beta, norm: int, eps:
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5, *, want_f32=False,
               want_bf16=True, out_f32=None, out_bf16=None):
-    assert x.dtype in (F32, BF16) and x.is_cuda and x.is_contiguous()
+    if not x.is_cuda:
+        raise RuntimeError("aptai_b200: layernorm input must be a CUDA tensor (there is no CPU path)")
+    assert x.dtype in (F32, BF16) and x.is_contiguous()
     cols = x.shape[-1]
     rows = x.numel() // cols
     if want_f32 and out_f32 is None:

@@ -1,0 +1,97 @@
+"""CPU suite (no GPU): C-ABI surface, host-side bucketing/sharding logic, drop-in module layout, and the
+world_size-2 gloo run of the utterance-sharded path's host logic."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from helpers import ROOT, VOCAB, cfg_base, cfg_large
+from aptai_b200 import sweep
+from aptai_b200.config import W2V2Config
+
+
+def test_cabi_library_loads_and_exports_every_declared_symbol():
+    import __graft_entry__ as ge
+    ge.build()
+    from aptai_b200 import lib
+    L = lib.load()
+    hdr = open(os.path.join(ROOT, "include", "aptai_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(aptai_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/aptai_b200.h but not exported"
+        assert name in lib.PROTOTYPES, f"{name} has no ctypes prototype in aptai_b200/lib.py"
+    assert L.aptai_version() >= 100
+    assert isinstance(lib.last_error(), str)
+
+
+def test_compute_entry_points_fail_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from aptai_b200 import lib
+    L = lib.load()
+    rc = L.aptai_layernorm(None, 0, 1, 512, None, None, 1e-5, None, None, None)
+    assert rc != 0
+    assert "CUDA" in lib.last_error() or "device" in lib.last_error()
+    from aptai_b200 import ops
+    with pytest.raises(RuntimeError):
+        ops.layernorm(torch.zeros(4, 512), torch.ones(512), torch.zeros(512))       # CPU tensor: no CPU path
+
+
+def test_backbone_state_dict_layout_matches_hf_names():
+    from aptai_b200.backbone import Wav2Vec2Backbone
+    for cfg, n in ((cfg_base(), 211), (cfg_large(), 422)):
+        m = Wav2Vec2Backbone(cfg)
+        keys = list(m.state_dict().keys())
+        assert len(keys) == n
+        assert "encoder.pos_conv_embed.conv.parametrizations.weight.original0" in keys
+        assert "feature_projection.projection.weight" in keys
+    total = sum(p.numel() for p in Wav2Vec2Backbone(cfg_base()).parameters())
+    assert total == 94371712                      # SURVEY.md §8c known answer (base)
+
+
+def test_hf_config_objects_are_accepted():
+    from transformers import Wav2Vec2Config
+    hf = Wav2Vec2Config(vocab_size=46, hidden_size=1024, num_hidden_layers=24, num_attention_heads=16,
+                        intermediate_size=4096, feat_extract_norm="layer", conv_bias=True, do_stable_layer_norm=True)
+    c = W2V2Config.from_any(hf)
+    assert c.hidden_size == 1024 and c.do_stable_layer_norm and c.conv_kernel == (10, 3, 3, 3, 3, 2, 2)
+    c.validate_for_kernels()
+
+
+def test_bucketing_and_lpt_sharding():
+    cfg = cfg_large()
+    lengths = sweep.synth_durations(4096, 2.0, 20.0, seed=0)
+    assert min(lengths) >= 32000 and max(lengths) <= 320000
+    batches = sweep.make_batches(cfg, lengths, bucket_width=32, max_rows=49152)
+    seen = sorted(i for b in batches for i in b.indices)
+    assert seen == list(range(4096))                                   # every utterance exactly once
+    for b in batches:
+        Ts = [cfg.conv_out_length(lengths[i]) for i in b.indices]
+        assert max(Ts) - min(Ts) <= 32 and len(b.indices) * b.frames <= 49152
+        assert b.frames == max(Ts)
+    padded = sum(len(b.indices) * b.frames for b in batches)
+    valid = sum(cfg.conv_out_length(l) for l in lengths)
+    assert padded / valid < 1.03
+    shards = sweep.shard_lpt(batches, 8)
+    loads = [sum(b.flops for b in s) for s in shards]
+    assert max(loads) / min(loads) < 1.10   # 50 coarse batches over 8 ranks
+    assert sorted(i for s in shards for b in s for i in b.indices) == list(range(4096))
+    # closed-form FLOPs: large, 8 s -> 303.06 GFLOP
+    assert abs(sweep.flops_utt(cfg, 128000) / 1e9 - 303.06) < 0.5
+
+
+def test_two_rank_gloo_sharded_run():
+    """world_size 2 on CPU (gloo): each rank takes its LPT shard, the shards partition the workload, and the
+    max-over-ranks reduction used by bench.py works."""
+    script = os.path.join(ROOT, "tests", "_gloo_worker.py")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29731", script], capture_output=True,
+                       text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "GLOO_OK" in r.stdout
