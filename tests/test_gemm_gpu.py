@@ -102,3 +102,13 @@ def test_posconv(cuda, H, groups, T, B):
                    groups=groups)[:, :, :-1]
     ref = x + F.gelu(pos).transpose(1, 2)
     torch.testing.assert_close(h.view(B, T, H), ref, atol=5e-3, rtol=5e-3)
+
+
+def test_gelu_accuracy(cuda):
+    """erf-GELU of the GEMM epilogue against the fp64 definition (identity weights, fp32 output)."""
+    x = torch.linspace(-8, 8, 64 * 512, device=cuda).view(512, 64)
+    a = x.bfloat16()
+    w = torch.eye(64, device=cuda).bfloat16()
+    o32, _ = ops.linear(a, w, None, act=1, want_f32=True, want_bf16=False)
+    ref = torch.nn.functional.gelu(a.double())
+    assert (o32.double() - ref).abs().max().item() < 1e-6
