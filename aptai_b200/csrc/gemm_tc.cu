@@ -261,14 +261,16 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         rstd = rsqrtf(var + p.ln_eps);
       }
 
+      // software pipeline: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
+      uint32_t nxt[CH];
+      tmem_ld_chunk<CH>(t_row + half * HALF_N, nxt);
       for (int c = half * HALF_N; c < (half + 1) * HALF_N; c += CH) {
-        uint32_t regs[CH];
-        tmem_ld_chunk<CH>(t_row + c, regs);
         tmem_ld_wait();
         float v[CH];
         const int n0 = n_tile0 + c;
 #pragma unroll
-        for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(regs[i]);
+        for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(nxt[i]);
+        if (c + CH < (half + 1) * HALF_N) tmem_ld_chunk<CH>(t_row + c + CH, nxt);
         if (p.bias) {
 #pragma unroll
           for (int i = 0; i < CH; i += 4) {

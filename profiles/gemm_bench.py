@@ -37,8 +37,13 @@ for M, K, N, name in shapes:
     b = torch.randn((N,), device=dev)
     out = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
     res = {}
+    act = 1 if name.startswith("ffn1") else 0
+    resid = torch.randn((M, N), device=dev) if name.startswith(("out", "ffn2")) else None
     for pair in (1, 2):
-        ms = timeit(lambda: ops.linear(a, w, b, out_bf16=out, cta_pair=pair))
+        if resid is not None:
+            ms = timeit(lambda: ops.linear(a, w, b, residual=resid, out_f32=resid, want_bf16=False, cta_pair=pair))
+        else:
+            ms = timeit(lambda: ops.linear(a, w, b, out_bf16=out, act=act, cta_pair=pair))
         res[pair] = 2.0 * M * N * K / ms / 1e9
     ms = timeit(lambda: torch.nn.functional.linear(a, w, b.bfloat16()))
-    print(f"{name:10s} M={M:6d} K={K:5d} N={N:5d}  single {res[1]:7.1f}  pair {res[2]:7.1f}  cublas {2.0 * M * N * K / ms / 1e9:7.1f} TFLOP/s")
+    print(f"{name:10s}{" +gelu" if act else (" +res32" if resid is not None else "")} M={M:6d} K={K:5d} N={N:5d}  single {res[1]:7.1f}  pair {res[2]:7.1f}  cublas {2.0 * M * N * K / ms / 1e9:7.1f} TFLOP/s")
