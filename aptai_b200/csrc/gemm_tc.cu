@@ -225,6 +225,24 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       const long long out_off = out_row * p.ldo;
       const int n_tile0 = n_blk * BN;
 
+      if (p.residual != nullptr) {
+        // pull the NEXT tile's residual rows towards L2 while this tile is processed: the fp32 residual stream
+        // makes the K=1024 projections memory-bound, and two epilogue warps per scheduler cannot keep enough
+        // HBM requests in flight on their own
+        const int nt = tile + tile_step;
+        if (nt < p.num_tiles) {
+          const int nmt = nt / p.n_tiles;
+          const int nseg = nmt / p.m_tiles_per_seg;
+          const int nr = (nmt - nseg * p.m_tiles_per_seg) * TILE_M + static_cast<int>(rank) * BLOCK_M + row_in_tile;
+          if (nr < p.rows_per_seg) {
+            const float* np_ = p.residual + (static_cast<long long>(nseg) * p.out_seg_stride + nr) * p.ldo +
+                               (nt % p.n_tiles) * BN + half * HALF_N;
+#pragma unroll
+            for (int i = 0; i < HALF_N * 4 / 128; ++i)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(np_ + i * 32));
+          }
+        }
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * C::ACC_STRIDE;
