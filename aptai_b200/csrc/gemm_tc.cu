@@ -279,74 +279,6 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         rstd = rsqrtf(var + p.ln_eps);
       }
 
-      if constexpr (!LN && (BN % 64 == 0)) {
-        // ---- fragment-layout epilogue: 16x256b TMEM loads put four neighbouring threads on one 32-byte sector
-        // of an output row, so the fp32 residual loads and the stores are sector-coalesced (the row-per-thread
-        // 32x32b layout costs 32 L1 tag look-ups per instruction and made the K=1024 projections LSU-bound).
-        const int g8 = lane >> 2, j2 = (lane & 3) * 2;
-        const int r_base = (mt - seg * p.m_tiles_per_seg) * TILE_M + static_cast<int>(rank) * BLOCK_M + q * 32;
-        long long roff[4];
-        bool rvalid[4], rzero[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int rr = r_base + (i >> 1) * 16 + (i & 1) * 8 + g8;
-          rvalid[i] = rr < p.rows_per_seg;
-          const long long orow = static_cast<long long>(seg) * p.out_seg_stride + rr;
-          rzero[i] = false;
-          if (p.seg_valid_rows != nullptr && rvalid[i]) {
-            const long long ms = orow / p.mask_seg_rows;
-            rzero[i] = (orow - ms * p.mask_seg_rows) >= __ldg(p.seg_valid_rows + ms);
-          }
-          roff[i] = orow * p.ldo;
-        }
-        const uint32_t t_q = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * C::ACC_STRIDE;
-        uint32_t fa[16], fb[16];
-        tmem_ld_frag16x32(t_q + half * HALF_N, fa);
-        tmem_ld_frag16x32(t_q + (16u << 16) + half * HALF_N, fb);
-        for (int c = half * HALF_N; c < (half + 1) * HALF_N; c += 32) {
-          tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            v[i] = __uint_as_float(fa[i]);
-            v[16 + i] = __uint_as_float(fb[i]);
-          }
-          if (c + 32 < (half + 1) * HALF_N) {
-            tmem_ld_frag16x32(t_q + c + 32, fa);
-            tmem_ld_frag16x32(t_q + (16u << 16) + c + 32, fb);
-          }
-          const int n0 = n_tile0 + c + j2;
-          // v[h*16 + 4k + 2*rh + e] = (row r_base + h*16 + rh*8 + g8, column n0 + 8k + e)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            float2 b2 = make_float2(0.f, 0.f);
-            if (p.bias) b2 = __ldg(reinterpret_cast<const float2*>(p.bias + n0 + 8 * k));
-#pragma unroll
-            for (int hr = 0; hr < 4; ++hr) {
-              const int idx = (hr >> 1) * 16 + 4 * k + (hr & 1) * 2;
-              float x0 = v[idx] + b2.x, x1 = v[idx + 1] + b2.y;
-              if (p.act == 1) {
-                x0 = gelu_erf(x0);
-                x1 = gelu_erf(x1);
-              }
-              if (rvalid[hr]) {
-                const long long o = roff[hr] + n0 + 8 * k;
-                if (p.residual) {
-                  const float2 r2 = __ldg(reinterpret_cast<const float2*>(p.residual + o));
-                  x0 += r2.x;
-                  x1 += r2.y;
-                }
-                if (rzero[hr]) {
-                  x0 = 0.f;
-                  x1 = 0.f;
-                }
-                if (p.out_f32) *reinterpret_cast<float2*>(p.out_f32 + o) = make_float2(x0, x1);
-                if (p.out_bf16) *reinterpret_cast<uint32_t*>(p.out_bf16 + o) = pack_bf16(x0, x1);
-              }
-            }
-          }
-        }
-      } else {
       // software pipeline: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
       uint32_t nxt[CH];
       tmem_ld_chunk<CH>(t_row + half * HALF_N, nxt);
@@ -405,7 +337,6 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
                                      pack_bf16(v[i + 4], v[i + 5]), pack_bf16(v[i + 6], v[i + 7]));
           }
         }
-      }
       }
       // all tcgen05.ld of this warp have completed (wait::ld above) -> hand the accumulator back to the MMA warp
       tc_fence_before();

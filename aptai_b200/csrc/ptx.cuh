@@ -195,18 +195,6 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
       : "r"(taddr)
       : "memory");
 }
-// 16 lanes x 256 bit, 4 repetitions = 16 rows x 32 columns in the MMA-accumulator fragment layout:
-// thread t holds, for k = 0..3, r[4k+0..1] = (row t/4, cols 8k + 2(t%4) + {0,1}) and r[4k+2..3] = (row t/4 + 8, same
-// cols): four neighbouring threads cover one 32-byte sector of a row, so global accesses are sector-coalesced.
-__device__ __forceinline__ void tmem_ld_frag16x32(uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- UMMA descriptors
