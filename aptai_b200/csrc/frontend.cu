@@ -201,7 +201,8 @@ conv0_kernel(const float* __restrict__ wav, long long L, int T0, const float* __
       y0 = fmaf(y0, g0, e0);
       y1 = fmaf(y1, g1, e1);
     }
-    o[static_cast<long long>(f) * (C0 / 2)] = __floats2bfloat162_rn(gelu_erf(y0), gelu_erf(y1));
+    gelu_erf2(y0, y1);
+    o[static_cast<long long>(f) * (C0 / 2)] = __floats2bfloat162_rn(y0, y1);
   }
 }
 

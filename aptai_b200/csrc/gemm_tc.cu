@@ -309,7 +309,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         }
         if (p.act == 1) {
 #pragma unroll
-          for (int i = 0; i < CH; ++i) v[i] = gelu_erf(v[i]);
+          for (int i = 0; i < CH; i += 2) gelu_erf2(v[i], v[i + 1]);
         }
         if (valid_row) {
           if (p.residual) {

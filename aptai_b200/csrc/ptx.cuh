@@ -267,6 +267,50 @@ __device__ __forceinline__ float gelu_erf(float x) {
   const float h = 0.5f * t * p * e;           // 0.5 * erfc(|x| / sqrt(2))
   return x * (x > 0.f ? 1.0f - h : h);
 }
+// Two GELUs at once on the packed fp32x2 FMA path of sm_100 (FFMA2 / FMUL2): the polynomial part costs half the
+// FMA-pipe issue slots of the scalar version; the MUFU ops stay scalar.  Same formula, same accuracy.
+__device__ __forceinline__ uint64_t f32x2_pack(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void f32x2_unpack(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t f32x2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f32x2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+  const uint64_t x = f32x2_pack(x0, x1);
+  const uint64_t ax = f32x2_pack(fabsf(x0), fabsf(x1));
+  float d0, d1, t0, t1, e0, e1, a0, a1;
+  f32x2_unpack(f32x2_fma(ax, f32x2_pack(0.3275911f * 0.70710678118654752440f, 0.3275911f * 0.70710678118654752440f),
+                         f32x2_pack(1.0f, 1.0f)), d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  f32x2_unpack(f32x2_mul(f32x2_mul(x, x), f32x2_pack(-0.5f * 1.4426950408889634f, -0.5f * 1.4426950408889634f)), a0, a1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  const uint64_t t = f32x2_pack(t0, t1);
+  uint64_t p = f32x2_fma(t, f32x2_pack(0.5f * 1.061405429f, 0.5f * 1.061405429f),
+                         f32x2_pack(0.5f * -1.453152027f, 0.5f * -1.453152027f));
+  p = f32x2_fma(t, p, f32x2_pack(0.5f * 1.421413741f, 0.5f * 1.421413741f));
+  p = f32x2_fma(t, p, f32x2_pack(0.5f * -0.284496736f, 0.5f * -0.284496736f));
+  p = f32x2_fma(t, p, f32x2_pack(0.5f * 0.254829592f, 0.5f * 0.254829592f));
+  const uint64_t h = f32x2_mul(f32x2_mul(t, p), f32x2_pack(e0, e1));    // 0.5 * erfc(|x| / sqrt(2))
+  float r0, r1;
+  f32x2_unpack(f32x2_mul(x, h), r0, r1);
+  x0 = x0 > 0.f ? x0 - r0 : r0;
+  x1 = x1 > 0.f ? x1 - r1 : r1;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
