@@ -53,7 +53,8 @@ struct GemmCfg {
   static constexpr int CHUNK = (BN % 64 == 0) ? 32 : 8;          // columns per tcgen05.ld in the epilogue
   static constexpr int BAR_BYTES = 256;
   static constexpr int LN_BYTES = 2 * 2 * BLOCK_M * sizeof(float2);
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES + LN_BYTES;
+  static constexpr int STG_BYTES = BN >= 512 ? 0 : 8 * 4096;     // 4 KB transpose buffer per epilogue warp
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES + LN_BYTES + STG_BYTES;
 };
 
 template <int CH>
@@ -311,6 +312,69 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
 #pragma unroll
           for (int i = 0; i < CH; i += 2) gelu_erf2(v[i], v[i + 1]);
         }
+        if constexpr (!LN && CH == 32) {
+          // ---- coalesced path: transpose through a warp-private, XOR-swizzled 4 KB buffer so that every global
+          // access covers whole 128-byte (fp32) / 64-byte (bf16) row segments instead of 32 different rows
+          float* stg = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES + C::LN_BYTES) +
+                       (warp - EPI_WARP0) * 1024;
+          const int r_first = r - lane;                                  // first row of this warp's 32-row group
+          const long long off0 = out_off - static_cast<long long>(lane) * p.ldo + n0;
+          const int lrow = lane >> 3, lunit = lane & 7;
+          if (p.residual) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = i * 4 + lrow;
+              float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (r_first + rr < p.rows_per_seg)
+                x = __ldg(reinterpret_cast<const float4*>(p.residual + off0 + rr * p.ldo + lunit * 4));
+              *reinterpret_cast<float4*>(stg + rr * 32 + ((lunit ^ (rr & 7)) << 2)) = x;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float4 r4 = *reinterpret_cast<const float4*>(stg + lane * 32 + ((u ^ (lane & 7)) << 2));
+              v[4 * u] += r4.x; v[4 * u + 1] += r4.y; v[4 * u + 2] += r4.z; v[4 * u + 3] += r4.w;
+            }
+            __syncwarp();
+          }
+          if (zero_row) {
+#pragma unroll
+            for (int i = 0; i < CH; ++i) v[i] = 0.f;
+          }
+          if (p.out_f32) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              *reinterpret_cast<float4*>(stg + lane * 32 + ((u ^ (lane & 7)) << 2)) =
+                  make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int rr = i * 4 + lrow;
+              const float4 x = *reinterpret_cast<const float4*>(stg + rr * 32 + ((lunit ^ (rr & 7)) << 2));
+              if (r_first + rr < p.rows_per_seg)
+                *reinterpret_cast<float4*>(p.out_f32 + off0 + rr * p.ldo + lunit * 4) = x;
+            }
+            __syncwarp();
+          }
+          if (p.out_bf16) {
+            uint4* sb = reinterpret_cast<uint4*>(stg);                    // 128-byte row pitch, units 0..3 used
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              sb[lane * 8 + (u ^ (lane & 7))] =
+                  make_uint4(pack_bf16(v[8 * u], v[8 * u + 1]), pack_bf16(v[8 * u + 2], v[8 * u + 3]),
+                             pack_bf16(v[8 * u + 4], v[8 * u + 5]), pack_bf16(v[8 * u + 6], v[8 * u + 7]));
+            __syncwarp();
+            const int bu = lane & 3;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = i * 8 + ((lane >> 2) & 1) * 4 + (lane >> 3);
+              const uint4 x = sb[rr * 8 + (bu ^ (rr & 7))];
+              if (r_first + rr < p.rows_per_seg)
+                *reinterpret_cast<uint4*>(p.out_bf16 + off0 + rr * p.ldo + bu * 8) = x;
+            }
+            __syncwarp();
+          }
+        } else {
         if (valid_row) {
           if (p.residual) {
             const float4* rp = reinterpret_cast<const float4*>(p.residual + out_off + n0);
@@ -336,6 +400,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
               op[i / 8] = make_uint4(pack_bf16(v[i], v[i + 1]), pack_bf16(v[i + 2], v[i + 3]),
                                      pack_bf16(v[i + 4], v[i + 5]), pack_bf16(v[i + 6], v[i + 7]));
           }
+        }
         }
       }
       // all tcgen05.ld of this warp have completed (wait::ld above) -> hand the accumulator back to the MMA warp
