@@ -52,7 +52,7 @@ struct GemmCfg {
   static constexpr int TMEM_COLS = ACC_STAGES * ACC_STRIDE <= 128 ? 128 : (ACC_STAGES * ACC_STRIDE <= 256 ? 256 : 512);
   static constexpr int CHUNK = (BN % 64 == 0) ? 32 : 8;          // columns per tcgen05.ld in the epilogue
   static constexpr int BAR_BYTES = 256;
-  static constexpr int LN_BYTES = 2 * 2 * BLOCK_M * sizeof(float2);
+  static constexpr int LN_BYTES = BN >= 512 ? 2 * 2 * BLOCK_M * sizeof(float2) : 0;   // LN statistics exchange
   static constexpr int STG_BYTES = BN >= 512 ? 0 : 8 * 4096;     // 4 KB transpose buffer per epilogue warp
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES + LN_BYTES + STG_BYTES;
 };
