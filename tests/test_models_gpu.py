@@ -93,7 +93,12 @@ def test_aptai_forward_vs_reference(aptai_large, cuda):
     out = aptai_large(0, wav, torch.tensor(lens, device=cuda), torch.from_numpy(g["g2_phn"]).to(cuda),
                       *[tvt[:, :, i].contiguous() for i in range(9)])
     tvs = out["tvs_pred"].cpu().numpy()
-    assert np.abs(tvs - g["g2_tvs"]).max() <= 1e-2
+    # valid frames only: frames beyond an utterance's length are masked out by every consumer of the reference
+    # (tv_pad_mask, models/aptai.py:72,89-93); the all-frames figure is reported for information
+    d_valid = max(float(np.abs(tvs[b, :n] - g["g2_tvs"][b, :n]).max()) for b, n in enumerate([99, 74]))
+    _report("aptai_forward_b2_tv", {"tv_max_abs_valid_frames": d_valid,
+                                    "tv_max_abs_all_frames": float(np.abs(tvs - g["g2_tvs"]).max())})
+    assert d_valid <= 1e-2, d_valid
     for b, n in enumerate([99, 74]):
         assert pearson(tvs[b, :n], g["g2_tvs"][b, :n]).min() >= 0.999
     losses = np.asarray([float(out["loss"]), float(out["mse_loss"]), float(out["ce_loss"])])
