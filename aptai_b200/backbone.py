@@ -30,7 +30,7 @@ import torch.nn as nn
 from . import ops
 from .config import W2V2Config
 
-BF16, F32, I32 = torch.bfloat16, torch.float32, torch.int32
+BF16, F16, F32, I32 = torch.bfloat16, torch.float16, torch.float32, torch.int32
 
 
 # ----------------------------------------------------------------------------------------- parameter containers
@@ -111,16 +111,17 @@ class _Plan:
         dev = m.masked_spec_embed.device
         f = lambda t: t.detach().to(device=dev, dtype=F32).contiguous()
         b = lambda t: t.detach().to(device=dev, dtype=BF16).contiguous()
+        h = lambda t: t.detach().to(device=dev, dtype=F16).contiguous()   # conv stack / projection operands
         cl = m.feature_extractor.conv_layers
         self.conv0_w = f(cl[0].conv.weight.reshape(cfg.conv_dim[0], cfg.conv_kernel[0]))
         self.conv_b = [f(l.conv.bias) if l.conv.bias is not None else None for l in cl]
         self.conv_ln_w = [f(l.layer_norm.weight) if hasattr(l, "layer_norm") else None for l in cl]
         self.conv_ln_b = [f(l.layer_norm.bias) if hasattr(l, "layer_norm") else None for l in cl]
         # conv i >= 1: [out][in][k] -> [out][k][in]  (K index = tap*C_in + c)
-        self.conv_w = [None] + [b(l.conv.weight.permute(0, 2, 1).reshape(l.conv.weight.shape[0], -1)) for l in cl[1:]]
+        self.conv_w = [None] + [h(l.conv.weight.permute(0, 2, 1).reshape(l.conv.weight.shape[0], -1)) for l in cl[1:]]
         fp = m.feature_projection
         self.fp_ln_w, self.fp_ln_b = f(fp.layer_norm.weight), f(fp.layer_norm.bias)
-        self.fp_w, self.fp_b = b(fp.projection.weight), f(fp.projection.bias)
+        self.fp_w, self.fp_b = h(fp.projection.weight), f(fp.projection.bias)
         pc = m.encoder.pos_conv_embed.conv
         g = f(pc.parametrizations.weight.original0)
         v = f(pc.parametrizations.weight.original1)
@@ -232,14 +233,16 @@ class Wav2Vec2Backbone(nn.Module):
         cfg, P = self.cfg, self.plan()
         B, L = wav.shape
         norm = 1 if cfg.feat_extract_norm == "layer" else 2
-        y = ops.conv0(wav, P.conv0_w, P.conv_b[0], P.conv_ln_w[0], P.conv_ln_b[0], norm)
+        # feature encoder + projection run on fp16 operands (activations are O(1) after the norms; three more
+        # mantissa bits than bf16 at the same tensor-core rate); the transformer runs on bf16 operands
+        y = ops.conv0(wav, P.conv0_w, P.conv_b[0], P.conv_ln_w[0], P.conv_ln_b[0], norm, out_dtype=F16)
         for i in range(1, len(cfg.conv_kernel)):
             y = _conv_layer(y, P, i, cfg)
         T = y.shape[1]
         M = B * T
         H = cfg.hidden_size
         feats = y
-        _, xn = ops.layernorm(y.view(M, -1), P.fp_ln_w, P.fp_ln_b, cfg.layer_norm_eps)
+        _, xn = ops.layernorm(y.view(M, -1), P.fp_ln_w, P.fp_ln_b, cfg.layer_norm_eps, out16_dtype=F16)
         h, _ = ops.linear(xn, P.fp_w, P.fp_b, want_f32=True, want_bf16=False, seg_rows=T, seg_valid_rows=frame_lens)
         taps = cfg.num_conv_pos_embeddings
         hp = ops.cast_pad(h.view(B, T, H), taps // 2)

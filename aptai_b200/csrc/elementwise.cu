@@ -9,23 +9,29 @@ namespace aptai {
 
 // ---------------------------------------------------------------------------------------------- LayerNorm
 // One warp per row; the row lives in registers (NV float4 per lane), exact two-pass statistics in fp32.
-template <int NV, bool IN_BF16>
+template <int NV, int IN_FMT>   // IN_FMT: 0 fp32, 1 bf16, 2 fp16
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const void* __restrict__ xin, long long rows, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, float* __restrict__ out_f32,
-                 __nv_bfloat16* __restrict__ out_bf16) {
+                 __nv_bfloat16* __restrict__ out_bf16, int out16_fp16) {
   constexpr int COLS = NV * 128;
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   float4 v[NV];
-  if (IN_BF16) {
+  if (IN_FMT != 0) {
     const uint2* p = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(xin) + row * COLS);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const uint2 u = __ldg(p + i * 32 + lane);
-      const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-      const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+      float2 a, b;
+      if (IN_FMT == 1) {
+        a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+        b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+      } else {
+        a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+        b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+      }
       v[i] = make_float4(a.x, a.y, b.x, b.y);
     }
   } else {
@@ -59,21 +65,19 @@ layernorm_kernel(const void* __restrict__ xin, long long rows, const float* __re
     if (out_f32) reinterpret_cast<float4*>(out_f32 + row * COLS)[i * 32 + lane] = y;
     if (out_bf16)
       reinterpret_cast<uint2*>(out_bf16 + row * COLS)[i * 32 + lane] =
-          make_uint2(pack_bf16(y.x, y.y), pack_bf16(y.z, y.w));
+          make_uint2(pack_h16(y.x, y.y, out16_fp16), pack_h16(y.z, y.w, out16_fp16));
   }
 }
 
 template <int NV>
-static void launch_ln(const void* x, int x_is_bf16, long long rows, const float* gamma, const float* beta, float eps,
-                      float* of, void* ob, cudaStream_t st) {
+static void launch_ln(const void* x, int x_fmt, long long rows, const float* gamma, const float* beta, float eps,
+                      float* of, void* ob, int o16, cudaStream_t st) {
   const int wpb = 8;
   const unsigned grid = static_cast<unsigned>((rows + wpb - 1) / wpb);
-  if (x_is_bf16)
-    layernorm_kernel<NV, true><<<grid, wpb * 32, 0, st>>>(x, rows, gamma, beta, eps, of,
-                                                           reinterpret_cast<__nv_bfloat16*>(ob));
-  else
-    layernorm_kernel<NV, false><<<grid, wpb * 32, 0, st>>>(x, rows, gamma, beta, eps, of,
-                                                            reinterpret_cast<__nv_bfloat16*>(ob));
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ob);
+  if (x_fmt == 1) layernorm_kernel<NV, 1><<<grid, wpb * 32, 0, st>>>(x, rows, gamma, beta, eps, of, o, o16);
+  else if (x_fmt == 2) layernorm_kernel<NV, 2><<<grid, wpb * 32, 0, st>>>(x, rows, gamma, beta, eps, of, o, o16);
+  else layernorm_kernel<NV, 0><<<grid, wpb * 32, 0, st>>>(x, rows, gamma, beta, eps, of, o, o16);
 }
 
 // ---------------------------------------------------------------------------------------------- cast + halo pad
@@ -329,20 +333,22 @@ __global__ void mse_ce_finalize_kernel(const double* __restrict__ accum, float* 
 
 using namespace aptai;
 
-extern "C" int aptai_layernorm(const void* x, int x_is_bf16, int64_t rows, int cols, const float* gamma,
-                               const float* beta, float eps, float* out_f32, void* out_bf16, void* stream) {
+extern "C" int aptai_layernorm(const void* x, int x_fmt, int64_t rows, int cols, const float* gamma,
+                               const float* beta, float eps, float* out_f32, void* out_bf16, int out16_fp16,
+                               void* stream) {
   if (int rc = check_arch()) return rc;
   APTAI_REQUIRE(x && gamma && beta && (out_f32 || out_bf16), "layernorm: null pointer");
   APTAI_REQUIRE(rows >= 1, "layernorm: rows=%lld", (long long)rows);
+  APTAI_REQUIRE(x_fmt >= 0 && x_fmt <= 2, "layernorm: x_fmt must be 0 (f32), 1 (bf16) or 2 (fp16)");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (cols) {
-    case 128: launch_ln<1>(x, x_is_bf16, rows, gamma, beta, eps, out_f32, out_bf16, st); break;
-    case 256: launch_ln<2>(x, x_is_bf16, rows, gamma, beta, eps, out_f32, out_bf16, st); break;
-    case 384: launch_ln<3>(x, x_is_bf16, rows, gamma, beta, eps, out_f32, out_bf16, st); break;
-    case 512: launch_ln<4>(x, x_is_bf16, rows, gamma, beta, eps, out_f32, out_bf16, st); break;
-    case 768: launch_ln<6>(x, x_is_bf16, rows, gamma, beta, eps, out_f32, out_bf16, st); break;
-    case 1024: launch_ln<8>(x, x_is_bf16, rows, gamma, beta, eps, out_f32, out_bf16, st); break;
-    case 1280: launch_ln<10>(x, x_is_bf16, rows, gamma, beta, eps, out_f32, out_bf16, st); break;
+    case 128: launch_ln<1>(x, x_fmt, rows, gamma, beta, eps, out_f32, out_bf16, out16_fp16, st); break;
+    case 256: launch_ln<2>(x, x_fmt, rows, gamma, beta, eps, out_f32, out_bf16, out16_fp16, st); break;
+    case 384: launch_ln<3>(x, x_fmt, rows, gamma, beta, eps, out_f32, out_bf16, out16_fp16, st); break;
+    case 512: launch_ln<4>(x, x_fmt, rows, gamma, beta, eps, out_f32, out_bf16, out16_fp16, st); break;
+    case 768: launch_ln<6>(x, x_fmt, rows, gamma, beta, eps, out_f32, out_bf16, out16_fp16, st); break;
+    case 1024: launch_ln<8>(x, x_fmt, rows, gamma, beta, eps, out_f32, out_bf16, out16_fp16, st); break;
+    case 1280: launch_ln<10>(x, x_fmt, rows, gamma, beta, eps, out_f32, out_bf16, out16_fp16, st); break;
     default:
       set_error("layernorm: unsupported width %d (128, 256, 384, 512, 768, 1024, 1280)", cols);
       return APTAI_ERR_ARG;

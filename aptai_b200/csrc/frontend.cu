@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(256)
 conv0_kernel(const float* __restrict__ wav, long long L, int T0, const float* __restrict__ w,
              const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
              const float* __restrict__ consts, const float* __restrict__ affine, float eps,
-             __nv_bfloat16* __restrict__ out) {
+             __nv_bfloat16* __restrict__ out, int out_fp16) {
   __shared__ float xs[FT * S0 + K0];
   __shared__ float2 fstat[FT];
   const int b = blockIdx.y;
@@ -183,7 +183,7 @@ conv0_kernel(const float* __restrict__ wav, long long L, int T0, const float* __
     g1 = affine[(b * C0 + c + 1) * 2]; e1 = affine[(b * C0 + c + 1) * 2 + 1];
     b0 = 0.f; b1 = 0.f;   // folded into the shift
   }
-  __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(out + (static_cast<long long>(b) * T0 + t0) * C0 + c);
+  uint32_t* o = reinterpret_cast<uint32_t*>(out + (static_cast<long long>(b) * T0 + t0) * C0 + c);
   for (int f = 0; f < nf; ++f) {
     const float* xf = xs + f * S0;
     float y0 = b0, y1 = b1;
@@ -202,7 +202,7 @@ conv0_kernel(const float* __restrict__ wav, long long L, int T0, const float* __
       y1 = fmaf(y1, g1, e1);
     }
     gelu_erf2(y0, y1);
-    o[static_cast<long long>(f) * (C0 / 2)] = __floats2bfloat162_rn(y0, y1);
+    o[static_cast<long long>(f) * (C0 / 2)] = pack_h16(y0, y1, out_fp16);
   }
 }
 
@@ -212,7 +212,7 @@ using namespace aptai;
 
 extern "C" int aptai_conv0_norm_gelu(const float* wav, int B, int64_t L, const float* w, const float* bias,
                                      const float* gamma, const float* beta, int norm, float eps, void* out_bf16,
-                                     int T0, float* stats_ws, void* stream) {
+                                     int T0, float* stats_ws, int out_fp16, void* stream) {
   if (int rc = check_arch()) return rc;
   APTAI_REQUIRE(wav && w && out_bf16, "conv0: null pointer");
   APTAI_REQUIRE(B >= 1 && L >= K0, "conv0: bad shape B=%d L=%lld", B, (long long)L);
@@ -225,7 +225,7 @@ extern "C" int aptai_conv0_norm_gelu(const float* wav, int B, int64_t L, const f
   if (norm == 1) {
     conv0_ln_consts_kernel<<<1, 128, 0, st>>>(w, bias, stats_ws);
     if (int rc = after_launch("conv0_ln_consts")) return rc;
-    conv0_kernel<1><<<grid, 256, 0, st>>>(wav, L, T0, w, bias, gamma, beta, stats_ws, nullptr, eps, out);
+    conv0_kernel<1><<<grid, 256, 0, st>>>(wav, L, T0, w, bias, gamma, beta, stats_ws, nullptr, eps, out, out_fp16);
   } else if (norm == 2) {
     // stats_ws: [B*65] doubles of moments, then [B*512*2] floats of scale/shift
     double* mom = reinterpret_cast<double*>(stats_ws);
@@ -241,9 +241,9 @@ extern "C" int aptai_conv0_norm_gelu(const float* wav, int B, int64_t L, const f
     if (int rc = after_launch("conv0_gn_moments")) return rc;
     conv0_gn_affine_kernel<<<B, C0, 0, st>>>(mom, w, bias, gamma, beta, T0, eps, affine);
     if (int rc = after_launch("conv0_gn_affine")) return rc;
-    conv0_kernel<2><<<grid, 256, 0, st>>>(wav, L, T0, w, bias, gamma, beta, nullptr, affine, eps, out);
+    conv0_kernel<2><<<grid, 256, 0, st>>>(wav, L, T0, w, bias, gamma, beta, nullptr, affine, eps, out, out_fp16);
   } else {
-    conv0_kernel<0><<<grid, 256, 0, st>>>(wav, L, T0, w, bias, gamma, beta, nullptr, nullptr, eps, out);
+    conv0_kernel<0><<<grid, 256, 0, st>>>(wav, L, T0, w, bias, gamma, beta, nullptr, nullptr, eps, out, out_fp16);
   }
   return after_launch("conv0_norm_gelu");
 }

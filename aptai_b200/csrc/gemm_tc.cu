@@ -36,6 +36,7 @@ struct GemmParams {
   int mask_seg_rows;
   int act;
   float ln_eps;
+  int fp16;   // operands and the 16-bit output are IEEE fp16 instead of bf16
 };
 
 template <int BN, bool CTA2>
@@ -158,7 +159,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0 && rank == 0) {
-      constexpr uint32_t IDESC = umma_idesc_bf16(TILE_M, C::UN);
+      const uint32_t IDESC = p.fp16 ? umma_idesc_f16(TILE_M, C::UN) : umma_idesc_bf16(TILE_M, C::UN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -361,8 +362,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
 #pragma unroll
             for (int u = 0; u < 4; ++u)
               sb[lane * 8 + (u ^ (lane & 7))] =
-                  make_uint4(pack_bf16(v[8 * u], v[8 * u + 1]), pack_bf16(v[8 * u + 2], v[8 * u + 3]),
-                             pack_bf16(v[8 * u + 4], v[8 * u + 5]), pack_bf16(v[8 * u + 6], v[8 * u + 7]));
+                  make_uint4(pack_h16(v[8 * u], v[8 * u + 1], p.fp16), pack_h16(v[8 * u + 2], v[8 * u + 3], p.fp16),
+                             pack_h16(v[8 * u + 4], v[8 * u + 5], p.fp16), pack_h16(v[8 * u + 6], v[8 * u + 7], p.fp16));
             __syncwarp();
             const int bu = lane & 3;
 #pragma unroll
@@ -397,8 +398,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
             uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + out_off + n0);
 #pragma unroll
             for (int i = 0; i < CH; i += 8)
-              op[i / 8] = make_uint4(pack_bf16(v[i], v[i + 1]), pack_bf16(v[i + 2], v[i + 3]),
-                                     pack_bf16(v[i + 4], v[i + 5]), pack_bf16(v[i + 6], v[i + 7]));
+              op[i / 8] = make_uint4(pack_h16(v[i], v[i + 1], p.fp16), pack_h16(v[i + 2], v[i + 3], p.fp16),
+                                     pack_h16(v[i + 4], v[i + 5], p.fp16), pack_h16(v[i + 6], v[i + 7], p.fp16));
           }
         }
         }
@@ -558,6 +559,7 @@ extern "C" int aptai_gemm_bf16(const aptai_gemm_args* g, void* stream) {
   p.mask_seg_rows = g->mask_seg_rows;
   p.act = g->act;
   p.ln_eps = g->ln_eps;
+  p.fp16 = g->half_fmt ? 1 : 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (g->ln) return pair ? launch_gemm_2cta<512, true>(ta, tb, p, st) : launch_gemm<512, true>(ta, tb, p, st);
   switch (bn) {

@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -217,6 +218,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
+// same with IEEE fp16 operands (a_format = b_format = 0): used by the conv stack, whose activations are O(1)
+// after LayerNorm/GELU and profit from fp16's three extra mantissa bits (TV parity margin)
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; one thread issues for the CTA.
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -311,9 +317,17 @@ __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
   x1 = x1 > 0.f ? x1 - r1 : r1;
 }
 
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__device__ __forceinline__ uint32_t pack_h16(float a, float b, int fp16) {
+  return fp16 ? pack_f16(a, b) : pack_bf16(a, b);
 }
 
 }  // namespace aptai

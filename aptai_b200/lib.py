@@ -23,7 +23,7 @@ class GemmArgs(C.Structure):
         ("w", c_void_p), ("N", C.c_int32), ("block_n", C.c_int32), ("segs", C.c_int32), ("rows_per_seg", C.c_int32),
         ("bias", c_void_p), ("gamma", c_void_p), ("beta", c_void_p), ("residual", c_void_p),
         ("out_f32", c_void_p), ("out_bf16", c_void_p), ("ldo", c_i64), ("out_seg_stride", c_i64),
-        ("seg_valid_rows", c_void_p), ("mask_seg_rows", C.c_int32), ("act", C.c_int32), ("ln", C.c_int32), ("ln_eps", c_float), ("cta_pair", C.c_int32),
+        ("seg_valid_rows", c_void_p), ("mask_seg_rows", C.c_int32), ("act", C.c_int32), ("ln", C.c_int32), ("ln_eps", c_float), ("cta_pair", C.c_int32), ("half_fmt", C.c_int32),
     ]
 
 
@@ -34,9 +34,9 @@ PROTOTYPES = {
     "aptai_launch_count": (c_i64, []),
     "aptai_gemm_bf16": (c_int, [C.POINTER(GemmArgs), c_void_p]),
     "aptai_conv0_norm_gelu": (c_int, [c_void_p, c_int, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float,
-                                      c_void_p, c_int, c_void_p, c_void_p]),
+                                      c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "aptai_layernorm": (c_int, [c_void_p, c_int, c_i64, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
-                                c_void_p]),
+                                c_int, c_void_p]),
     "aptai_cast_pad_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "aptai_posconv_fold": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "aptai_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

@@ -11,7 +11,18 @@ import torch
 from . import lib as _lib
 from .lib import GemmArgs, check
 
-BF16, F32, I32, I64, F64 = torch.bfloat16, torch.float32, torch.int32, torch.int64, torch.float64
+BF16, F16, F32, I32, I64, F64 = torch.bfloat16, torch.float16, torch.float32, torch.int32, torch.int64, torch.float64
+
+
+def _h16(t: torch.Tensor, name: str) -> int:
+    """16-bit operand format of a tensor: 0 = bf16, 1 = fp16."""
+    if not t.is_cuda:
+        raise RuntimeError(f"aptai_b200: {name} must be a CUDA tensor (there is no CPU path)")
+    if t.dtype not in (BF16, F16):
+        raise TypeError(f"aptai_b200: {name} must be bfloat16 or float16, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"aptai_b200: {name} must be contiguous")
+    return int(t.dtype == F16)
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -32,10 +43,10 @@ def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
     return t
 
 
-def alloc_rows_bf16(B: int, T: int, C: int, device, slack_rows: int = 2) -> torch.Tensor:
+def alloc_rows_bf16(B: int, T: int, C: int, device, slack_rows: int = 2, dtype=None) -> torch.Tensor:
     """bf16 [B,T,C] view of a flat buffer with `slack_rows` zeroed rows behind it: the strided (conv) TMA view of
     the next layer may address one row past the last utterance, and must not leave the allocation."""
-    flat = torch.empty((B * T + slack_rows) * C, dtype=BF16, device=device)
+    flat = torch.empty((B * T + slack_rows) * C, dtype=dtype or BF16, device=device)
     flat[B * T * C:].zero_()
     return flat[: B * T * C].view(B, T, C)
 
@@ -65,7 +76,9 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
 
     seg_rows / seg_valid_rows: rows are grouped in segments of seg_rows; rows >= seg_valid_rows[s] are written as 0.
     """
-    _req(a, BF16, "a"); _req(w, BF16, "w")
+    fmt = _h16(a, "a")
+    if _h16(w, "w") != fmt:
+        raise TypeError("linear: a and w must have the same 16-bit dtype")
     M, K = a.shape
     N, K2 = w.shape
     if K != K2 or K % 64:
@@ -73,7 +86,7 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     if want_f32 and out_f32 is None:
         out_f32 = torch.empty((M, N), dtype=F32, device=a.device)
     if want_bf16 and out_bf16 is None:
-        out_bf16 = torch.empty((M, N), dtype=BF16, device=a.device)
+        out_bf16 = torch.empty((M, N), dtype=a.dtype, device=a.device)
     g = GemmArgs()
     g.a = a.data_ptr(); g.a_row_stride = K; g.a_cols = K; g.P = 1; g.taps = 1; g.kb_per_tap = K // 64
     g.a_col_per_nblk = 0
@@ -89,7 +102,7 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     g.gamma = None; g.beta = None
     g.residual = _ptr(_req(residual, F32, "residual")) if residual is not None else None
     g.out_f32 = _ptr(out_f32); g.out_bf16 = _ptr(out_bf16); g.ldo = N
-    g.act = act; g.ln = 0; g.ln_eps = 0.0; g.cta_pair = cta_pair
+    g.act = act; g.ln = 0; g.ln_eps = 0.0; g.cta_pair = cta_pair; g.half_fmt = fmt
     gemm_raw(g)
     return out_f32, out_bf16
 
@@ -115,13 +128,15 @@ def conv_igemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], k
                eps: float = 1e-5, act: int = 1, out: Optional[torch.Tensor] = None, cta_pair: int = 0) -> torch.Tensor:
     """Strided conv1d as implicit GEMM.  x bf16 [B,T_in,C] channels-last, w bf16 [N, k*C] (tap-major K), out bf16
     [B,T_out,N]; epilogue = (+bias) -> (LayerNorm over N, if gamma) -> GELU."""
-    _req(x, BF16, "x"); _req(w, BF16, "w")
+    fmt = _h16(x, "x")
+    if _h16(w, "w") != fmt:
+        raise TypeError("conv_igemm: x and w must have the same 16-bit dtype")
     B, T_in, Cc = x.shape
     N = w.shape[0]
     assert w.shape[1] == k * Cc and Cc % 64 == 0
     T_out = (T_in - k) // stride + 1
     if out is None:
-        out = alloc_rows_bf16(B, T_out, N, x.device)
+        out = alloc_rows_bf16(B, T_out, N, x.device, dtype=x.dtype)
     g = GemmArgs()
     g.a = x.data_ptr(); g.a_row_stride = Cc; g.a_seg_stride = T_in * Cc; g.a_rows = T_in; g.a_cols = Cc
     g.P = stride; g.taps = k; g.kb_per_tap = Cc // 64; g.a_col_per_nblk = 0
@@ -130,7 +145,7 @@ def conv_igemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], k
     g.gamma = _ptr(ln_gamma); g.beta = _ptr(ln_beta); g.residual = None
     g.out_f32 = None; g.out_bf16 = out.data_ptr(); g.ldo = N; g.out_seg_stride = T_out
     g.seg_valid_rows = None; g.mask_seg_rows = 0; g.act = act; g.ln = 1 if ln_gamma is not None else 0; g.ln_eps = eps
-    g.cta_pair = cta_pair
+    g.cta_pair = cta_pair; g.half_fmt = fmt
     gemm_raw(g)
     return out
 
@@ -149,35 +164,39 @@ def posconv(x_pad: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, residual: 
     g.w = w.data_ptr(); g.N = H; g.block_n = gw; g.segs = B; g.rows_per_seg = T
     g.bias = bias.data_ptr(); g.gamma = None; g.beta = None; g.residual = residual.data_ptr()
     g.out_f32 = out_f32.data_ptr(); g.out_bf16 = None; g.ldo = H; g.out_seg_stride = T
-    g.seg_valid_rows = None; g.mask_seg_rows = 0; g.act = 1; g.ln = 0; g.ln_eps = 0.0
+    g.seg_valid_rows = None; g.mask_seg_rows = 0; g.act = 1; g.ln = 0; g.ln_eps = 0.0; g.cta_pair = 0; g.half_fmt = 0
     gemm_raw(g)
     return out_f32
 
 
-def conv0(wav: torch.Tensor, w: torch.Tensor, bias, gamma, beta, norm: int, eps: float = 1e-5) -> torch.Tensor:
+def conv0(wav: torch.Tensor, w: torch.Tensor, bias, gamma, beta, norm: int, eps: float = 1e-5,
+          out_dtype=None) -> torch.Tensor:
     _req(wav, F32, "wav"); _req(w, F32, "w")
     B, L = wav.shape
     T0 = (L - 10) // 5 + 1
-    out = alloc_rows_bf16(B, T0, 512, wav.device)
+    out = alloc_rows_bf16(B, T0, 512, wav.device, dtype=out_dtype or BF16)
     ws = torch.empty((max(256, B * (65 * 2 + 1024) + 16),), dtype=F32, device=wav.device) if norm else None
     check(_lib.load().aptai_conv0_norm_gelu(wav.data_ptr(), B, L, w.data_ptr(), _ptr(bias), _ptr(gamma), _ptr(beta),
-                                            norm, eps, out.data_ptr(), T0, _ptr(ws), _stream()), "conv0_norm_gelu")
+                                            norm, eps, out.data_ptr(), T0, _ptr(ws), int(out.dtype == F16), _stream()),
+          "conv0_norm_gelu")
     return out
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5, *, want_f32=False,
-              want_bf16=True, out_f32=None, out_bf16=None):
+              want_bf16=True, out_f32=None, out_bf16=None, out16_dtype=None):
     if not x.is_cuda:
         raise RuntimeError("aptai_b200: layernorm input must be a CUDA tensor (there is no CPU path)")
-    assert x.dtype in (F32, BF16) and x.is_contiguous()
+    assert x.dtype in (F32, BF16, F16) and x.is_contiguous()
     cols = x.shape[-1]
     rows = x.numel() // cols
     if want_f32 and out_f32 is None:
         out_f32 = torch.empty(x.shape, dtype=F32, device=x.device)
     if want_bf16 and out_bf16 is None:
-        out_bf16 = torch.empty(x.shape, dtype=BF16, device=x.device)
-    check(_lib.load().aptai_layernorm(x.data_ptr(), int(x.dtype == BF16), rows, cols, gamma.data_ptr(),
-                                      beta.data_ptr(), eps, _ptr(out_f32), _ptr(out_bf16), _stream()), "layernorm")
+        out_bf16 = torch.empty(x.shape, dtype=out16_dtype or BF16, device=x.device)
+    x_fmt = {F32: 0, BF16: 1, F16: 2}[x.dtype]
+    o16 = int(out_bf16 is not None and out_bf16.dtype == F16)
+    check(_lib.load().aptai_layernorm(x.data_ptr(), x_fmt, rows, cols, gamma.data_ptr(), beta.data_ptr(), eps,
+                                      _ptr(out_f32), _ptr(out_bf16), o16, _stream()), "layernorm")
     return out_f32, out_bf16
 
 

@@ -78,6 +78,7 @@ typedef struct aptai_gemm_args {
   int32_t ln;             /* 0/1: LayerNorm over the full row (requires N == 512) */
   float ln_eps;
   int32_t cta_pair;       /* 0 auto, 1 single-CTA tiles (128 x BN), 2 CTA-pair tiles (256 x BN, cta_group::2) */
+  int32_t half_fmt;       /* 0: A, W and out_bf16 are bf16; 1: they are IEEE fp16 (conv stack / feature projection) */
 } aptai_gemm_args;
 
 int aptai_gemm_bf16(const aptai_gemm_args* args, void* stream);
@@ -90,11 +91,12 @@ int aptai_gemm_bf16(const aptai_gemm_args* args, void* stream);
  */
 int aptai_conv0_norm_gelu(const float* wav, int B, int64_t L, const float* w, const float* bias,
                           const float* gamma, const float* beta, int norm, float eps, void* out_bf16, int T0,
-                          float* stats_ws, void* stream);
+                          float* stats_ws, int out_fp16, void* stream);
 
-/* LayerNorm over the last dim (HF:431, 600-602, 639, 645, 692, 792): fp32 or bf16 in, fp32 and/or bf16 out. */
-int aptai_layernorm(const void* x, int x_is_bf16, int64_t rows, int cols, const float* gamma, const float* beta,
-                    float eps, float* out_f32, void* out_bf16, void* stream);
+/* LayerNorm over the last dim (HF:431, 600-602, 639, 645, 692, 792): fp32 / bf16 / fp16 in, fp32 and/or 16-bit
+ * (bf16, or fp16 when out16_fp16) out. */
+int aptai_layernorm(const void* x, int x_fmt /* 0 f32, 1 bf16, 2 fp16 */, int64_t rows, int cols, const float* gamma,
+                    const float* beta, float eps, float* out_f32, void* out_bf16, int out16_fp16, void* stream);
 
 /* fp32 [segs][rows][cols] -> bf16 [segs][halo+rows+halo][cols] with zeroed halo rows (HF:371-379 'same' pad). */
 int aptai_cast_pad_bf16(const float* x, int segs, int rows, int cols, int halo, void* out_bf16, void* stream);

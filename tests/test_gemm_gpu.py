@@ -60,17 +60,19 @@ def test_linear_gelu_residual_mask(cuda):
 @pytest.mark.parametrize("pair", [1, 2])
 @pytest.mark.parametrize("k,T_in,B,ln", [(3, 801, 2, True), (3, 640, 3, False), (2, 399, 2, True), (2, 130, 1, False),
                                          (3, 2563, 2, True)])
-def test_conv_igemm(cuda, k, T_in, B, ln, pair):
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_conv_igemm(cuda, k, T_in, B, ln, pair, dt):
     C = 512
-    x = ops.alloc_rows_bf16(B, T_in, C, cuda)
-    x.copy_(_rand((B, T_in, C), cuda, 1.0, 8).bfloat16())
+    x = ops.alloc_rows_bf16(B, T_in, C, cuda, dtype=dt)
+    x.copy_(_rand((B, T_in, C), cuda, 1.0, 8).to(dt))
     w = _rand((C, C, k), cuda, (2.0 / (C * k)) ** 0.5, 9)                  # torch layout [out][in][k]
     bias = _rand((C,), cuda, 0.1, 10)
     gam = 1 + _rand((C,), cuda, 0.1, 11)
     bet = _rand((C,), cuda, 0.1, 12)
-    wk = w.permute(0, 2, 1).reshape(C, k * C).bfloat16().contiguous()
+    wk = w.permute(0, 2, 1).reshape(C, k * C).to(dt).contiguous()
     y = ops.conv_igemm(x, wk, bias, k, 2, ln_gamma=gam if ln else None, ln_beta=bet if ln else None, act=1, cta_pair=pair)
-    ref = F.conv1d(x.float().transpose(1, 2), w.bfloat16().float(), bias, stride=2)
+    assert y.dtype == dt
+    ref = F.conv1d(x.float().transpose(1, 2), w.to(dt).float(), bias, stride=2)
     if ln:
         ref = F.layer_norm(ref.transpose(1, 2), (C,), gam, bet, 1e-5).transpose(1, 2)
     ref = F.gelu(ref).transpose(1, 2)

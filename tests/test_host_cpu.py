@@ -34,7 +34,7 @@ def test_compute_entry_points_fail_loudly_without_gpu():
         pytest.skip("GPU present")
     from aptai_b200 import lib
     L = lib.load()
-    rc = L.aptai_layernorm(None, 0, 1, 512, None, None, 1e-5, None, None, None)
+    rc = L.aptai_layernorm(None, 0, 1, 512, None, None, 1e-5, None, None, 0, None)
     assert rc != 0
     assert "CUDA" in lib.last_error() or "device" in lib.last_error()
     from aptai_b200 import ops

@@ -16,8 +16,9 @@ def _rand(shape, dev, scale=1.0, seed=0):
     return (torch.randn(shape, generator=g) * scale).to(dev)
 
 
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("norm,bias", [(1, True), (2, False), (2, True), (0, False)])
-def test_conv0(cuda, norm, bias):
+def test_conv0(cuda, norm, bias, dt):
     B, L = 3, 16000
     lens = [16000, 12345, 4000]
     wav = _rand((B, L), cuda, 0.1, 1)
@@ -27,7 +28,8 @@ def test_conv0(cuda, norm, bias):
     bs = _rand((512,), cuda, 0.2, 3) if bias else None
     gam = 1 + _rand((512,), cuda, 0.1, 4)
     bet = _rand((512,), cuda, 0.1, 5)
-    y = ops.conv0(wav, w.view(512, 10).contiguous(), bs, gam, bet, norm)
+    y = ops.conv0(wav, w.view(512, 10).contiguous(), bs, gam, bet, norm, out_dtype=dt)
+    assert y.dtype == dt
     ref = F.conv1d(wav[:, None], w, bs, stride=5)
     if norm == 1:
         ref = F.layer_norm(ref.transpose(1, 2), (512,), gam, bet, 1e-5).transpose(1, 2)
@@ -43,12 +45,20 @@ def test_conv0(cuda, norm, bias):
 
 
 @pytest.mark.parametrize("cols", [512, 768, 1024, 256])
-@pytest.mark.parametrize("in_bf16", [False, True])
+@pytest.mark.parametrize("in_bf16", [False, True, torch.float16])
 def test_layernorm(cuda, cols, in_bf16):
     rows = 1000
     x = _rand((rows, cols), cuda, 2.0, 6) + 0.5
-    if in_bf16:
+    if in_bf16 is True:
         x = x.bfloat16()
+    elif in_bf16 is torch.float16:
+        x = x.half()
+        o32, o16 = ops.layernorm(x, 1 + _rand((cols,), cuda, 0.1, 7), _rand((cols,), cuda, 0.1, 8), 1e-5, want_f32=True,
+                                 want_bf16=True, out16_dtype=torch.float16)
+        ref = F.layer_norm(x.float(), (cols,), 1 + _rand((cols,), cuda, 0.1, 7), _rand((cols,), cuda, 0.1, 8), 1e-5)
+        torch.testing.assert_close(o32, ref, atol=2e-5, rtol=2e-5)
+        torch.testing.assert_close(o16.float(), ref.half().float(), atol=3e-3, rtol=2e-3)
+        return
     g = 1 + _rand((cols,), cuda, 0.1, 7)
     b = _rand((cols,), cuda, 0.1, 8)
     o32, o16 = ops.layernorm(x, g, b, 1e-5, want_f32=True, want_bf16=True)
