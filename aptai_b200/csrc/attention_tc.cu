@@ -6,7 +6,7 @@
 //   warp 1      MMA issuer     S_j = Q K_j^T  (M=128, N=n_j<=64, K=64) -> TMEM S buffer j%2 (double buffered)
 //                              O  += P_j V_j  (M=128, N=64, K=n_j)     -> TMEM O; P_j (bf16) from shared memory,
 //                                                                         V_j as an MN-major B operand
-//   warps 4..7  softmax        thread i owns query row i: tcgen05.ld of its S row, key-length mask, running max
+//   warps 4..11 softmax        two threads per query row (32 of the tile's 64 keys each): tcgen05.ld, key-length mask, running max
 //                              with lazy rescaling of O (only when the max grows by more than 2^8), exp2, row sum,
 //                              P_j -> shared memory in the UMMA K-major SWIZZLE_128B layout; final O / l -> bf16
 // S_{j+2} is issued as soon as P_j is written (S buffer j%2 free), so S_{j+1} is always ready when the softmax
@@ -23,13 +23,14 @@ namespace aptai {
 constexpr int AQ = 128;                 // query rows per work item
 constexpr int AK = 64;                  // keys per KV tile
 constexpr int AD = 64;                  // head dim
-constexpr int ATC_THREADS = 256;        // warps 0,1 (+2 TMEM alloc, 3 idle), 4..7 softmax
+constexpr int ATC_THREADS = 384;        // warps 0,1 (+2 TMEM alloc, 3 idle), 4..11 softmax (2 warps per 32-row quadrant)
 constexpr int Q_BYTES = AQ * AD * 2;    // 16 KB
 constexpr int KV_BYTES = AK * AD * 2;   // 8 KB per K or V tile
 constexpr int P_BYTES = AQ * AK * 2;    // 16 KB
 constexpr int KV_STAGES = 3;
 constexpr int ATC_DATA = Q_BYTES + KV_STAGES * 2 * KV_BYTES + 2 * P_BYTES;   // 96 KB
-constexpr int ATC_SMEM = ATC_DATA + 256;                                     // + barriers; two CTAs fit one SM
+constexpr int ATC_XCH = 2 * 2 * AQ * 4;                                     // row-max / row-sum exchange between half-row threads
+constexpr int ATC_SMEM = ATC_DATA + 256 + ATC_XCH;                           // + barriers; two CTAs fit one SM
 constexpr uint32_t TM_S = 0, TM_O = 128, TM_COLS = 256;   // S double buffered (2 x 64 columns), O 64 columns
 constexpr float ATC_LOG2E = 1.4426950408889634f;
 constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units
@@ -80,6 +81,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* p_full = bars + 12;    // [2]  P_j written (and S_j consumed)
   uint64_t* p_empty = bars + 14;   // [2]  P_j V_j complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  float* xch = reinterpret_cast<float*>(smem + ATC_DATA + 256);   // [2 parity][2 halves][128 rows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -90,14 +92,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
     mbar_init(o_full, 1);
-    mbar_init(o_empty, 4);
+    mbar_init(o_empty, 8);
     for (int i = 0; i < KV_STAGES; ++i) {
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);
+      mbar_init(&p_full[i], 8);
       mbar_init(&p_empty[i], 1);
     }
     fence_mbar_init();
@@ -181,10 +183,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
     }
   } else if (warp >= 4) {
-    // ---------------------------------------------------------------- softmax + output (thread = query row)
+    // ---------------------------------------------------------------- softmax + output
+    // two threads per query row: warp w and warp w+4 share TMEM quadrant w%4; `half` selects 32 of the 64 keys of
+    // a tile (and 32 of the 64 output columns).  The row maximum is exchanged through shared memory.
     const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
     const int row = q * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t pair_bar = 1 + q;                       // named barrier of the two warps of this quadrant
     uint32_t g = 0, it = 0;
     for (int w = blockIdx.x; w < p.items; w += gridDim.x, ++it) {
       const int qt = w % p.n_qt;
@@ -195,34 +201,33 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       float m_used = -INFINITY, l = 0.f;
       for (int j = 0; j < n; ++j, ++g) {
         const uint32_t sb = g & 1, u = g >> 1;
-        const int valid = min(AK, klen - j * AK);          // keys of this tile that exist
-        const bool full_tile = valid == AK;
+        const int valid = min(AK, klen - j * AK) - half * 32;      // keys of MY 32-key half that exist (may be <= 0)
+        const bool full_half = valid >= 32;
         mbar_wait(&s_full[sb], u & 1);
         tc_fence_after();
-        const uint32_t t_s = t_lane + TM_S + sb * AK;
-        uint32_t r0[32], r1[32];
-        tmem_ld32(t_s, r0);
-        tmem_ld32(t_s + 32, r1);
+        uint32_t r0[32];
+        tmem_ld32(t_lane + TM_S + sb * AK + half * 32, r0);
         tmem_ld_wait();
-        // row max over the valid keys (four independent chains)
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-        if (full_tile) {
+        if (full_half) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
-            mx0 = fmaxf(mx0, fmaxf(__uint_as_float(r0[i]), __uint_as_float(r1[i])));
-            mx1 = fmaxf(mx1, fmaxf(__uint_as_float(r0[i + 1]), __uint_as_float(r1[i + 1])));
-            mx2 = fmaxf(mx2, fmaxf(__uint_as_float(r0[i + 2]), __uint_as_float(r1[i + 2])));
-            mx3 = fmaxf(mx3, fmaxf(__uint_as_float(r0[i + 3]), __uint_as_float(r1[i + 3])));
+            mx0 = fmaxf(mx0, __uint_as_float(r0[i]));
+            mx1 = fmaxf(mx1, __uint_as_float(r0[i + 1]));
+            mx2 = fmaxf(mx2, __uint_as_float(r0[i + 2]));
+            mx3 = fmaxf(mx3, __uint_as_float(r0[i + 3]));
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
+          for (int i = 0; i < 32; ++i)
             if (i < valid) mx0 = fmaxf(mx0, __uint_as_float(r0[i]));
-            if (32 + i < valid) mx1 = fmaxf(mx1, __uint_as_float(r1[i]));
-          }
         }
-        const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * ATC_LOG2E;
-        // lazy rescale: keep the stale max unless the new one exceeds it by more than 2^8
+        float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+        float* xm = xch + (g & 1) * 2 * AQ;
+        xm[half * AQ + row] = mx;
+        named_bar_sync(pair_bar, 64);
+        mx = fmaxf(mx, xm[(half ^ 1) * AQ + row]) * ATC_LOG2E;
+        // lazy rescale: keep the stale max unless the new one exceeds it by more than 2^8 (both halves decide alike)
         float factor = 1.f;
         if (mx > m_used + RESCALE_THRESHOLD) {
           factor = exp2f(m_used - mx);          // 0 on the first tile (m_used = -inf)
@@ -230,59 +235,47 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         const bool need = (factor != 1.f) && (j > 0);
         if (__any_sync(0xffffffffu, need)) {
-          // O must be complete (P_{j-1} V_{j-1} done) before it is rescaled in place
+          // O must be complete (P_{j-1} V_{j-1} done) before it is rescaled in place; each half owns 32 columns
           const uint32_t gp = g - 1;
           mbar_wait(&p_empty[gp & 1], (gp >> 1) & 1);
           tc_fence_after();
+          uint32_t r[32];
+          tmem_ld32(t_lane + TM_O + half * 32, r);
+          tmem_ld_wait();
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint32_t r[32];
-            tmem_ld32(t_lane + TM_O + c * 32, r);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * factor);
-            asm volatile(
-                "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-                "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-                "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-                ::"r"(t_lane + TM_O + c * 32), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]),
-                "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]),
-                "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]),
-                "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
-                "r"(r[30]), "r"(r[31])
-                : "memory");
-          }
+          for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * factor);
+          asm volatile(
+              "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+              "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+              "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+              ::"r"(t_lane + TM_O + half * 32), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]),
+              "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]),
+              "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]),
+              "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+              "r"(r[30]), "r"(r[31])
+              : "memory");
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
         l *= factor;
-        // p = exp2(s*log2e - m_used); P -> shared memory (bf16, K-major SWIZZLE_128B rows of 64 keys)
+        // p = exp2(s*log2e - m_used); my 32 keys -> 4 of the 8 sixteen-byte units of the row (K-major SWIZZLE_128B)
         mbar_wait(&p_empty[sb], (u & 1) ^ 1);      // P_{j-2} V_{j-2} has consumed this P buffer
         uint8_t* prow = sP + sb * P_BYTES + row * 128;
         float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
-        const int ncol16 = (valid + 15) >> 4;      // 16-key groups the P V MMA will read
+        const int ncol16 = (min(AK, klen - j * AK) + 15) >> 4;      // 16-key groups the P V MMA will read
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          float pv[32];
+        for (int u8 = 0; u8 < 4; ++u8) {             // 8 keys = one 16-byte unit at a time (short live ranges)
+          float pv[8];
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            pv[i] = ex2_approx(fmaf(__uint_as_float(c == 0 ? r0[i] : r1[i]), ATC_LOG2E, -m_used));
-          if (!full_tile) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (c * 32 + i >= valid) pv[i] = 0.f;
+          for (int i = 0; i < 8; ++i) {
+            pv[i] = ex2_approx(fmaf(__uint_as_float(r0[u8 * 8 + i]), ATC_LOG2E, -m_used));
+            if (!full_half && u8 * 8 + i >= valid) pv[i] = 0.f;
           }
-#pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            rs0 += pv[i]; rs1 += pv[i + 1]; rs2 += pv[i + 2]; rs3 += pv[i + 3];
-          }
-#pragma unroll
-          for (int u8 = 0; u8 < 4; ++u8) {          // four 16-byte units (8 keys each) per 32-key chunk
-            const int unit = c * 4 + u8;
-            if ((unit >> 1) < ncol16) {
-              uint4 v4 = make_uint4(pack_bf16(pv[u8 * 8 + 0], pv[u8 * 8 + 1]), pack_bf16(pv[u8 * 8 + 2], pv[u8 * 8 + 3]),
-                                    pack_bf16(pv[u8 * 8 + 4], pv[u8 * 8 + 5]), pack_bf16(pv[u8 * 8 + 6], pv[u8 * 8 + 7]));
-              *reinterpret_cast<uint4*>(prow + ((unit ^ (row & 7)) << 4)) = v4;
-            }
+          rs0 += pv[0] + pv[4]; rs1 += pv[1] + pv[5]; rs2 += pv[2] + pv[6]; rs3 += pv[3] + pv[7];
+          const int unit = half * 4 + u8;
+          if ((unit >> 1) < ncol16) {
+            uint4 v4 = make_uint4(pack_bf16(pv[0], pv[1]), pack_bf16(pv[2], pv[3]), pack_bf16(pv[4], pv[5]),
+                                  pack_bf16(pv[6], pv[7]));
+            *reinterpret_cast<uint4*>(prow + ((unit ^ (row & 7)) << 4)) = v4;
           }
         }
         l += (rs0 + rs1) + (rs2 + rs3);
@@ -292,21 +285,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[sb]);
       }
-      // ---- output: O / l -> bf16
+      // ---- output: O / l -> bf16 (each half owns 32 of the 64 columns; the row sum is exchanged first)
+      float* xl = xch + (it & 1) * 2 * AQ;
+      named_bar_sync(pair_bar, 64);                 // the max-exchange slots of this parity are free again
+      xl[half * AQ + row] = l;
+      named_bar_sync(pair_bar, 64);
+      const float inv = 1.f / (l + xl[(half ^ 1) * AQ + row]);
       mbar_wait(o_full, it & 1);
       tc_fence_after();
-      const float inv = 1.f / l;
       const int qrow = qt * AQ + row;
-      __nv_bfloat16* out = p.ctx + (static_cast<long long>(b) * p.T + qrow) * p.H + h * AD;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      __nv_bfloat16* out = p.ctx + (static_cast<long long>(b) * p.T + qrow) * p.H + h * AD + half * 32;
+      {
         uint32_t r[32];
-        tmem_ld32(t_lane + TM_O + c * 32, r);
+        tmem_ld32(t_lane + TM_O + half * 32, r);
         tmem_ld_wait();
         if (qrow < p.T) {
 #pragma unroll
           for (int i = 0; i < 32; i += 8)
-            *reinterpret_cast<uint4*>(out + c * 32 + i) =
+            *reinterpret_cast<uint4*>(out + i) =
                 make_uint4(pack_bf16(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv),
                            pack_bf16(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv),
                            pack_bf16(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv),
