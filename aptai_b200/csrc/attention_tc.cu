@@ -27,8 +27,8 @@ constexpr int ATC_THREADS = 384;        // warps 0,1 (+2 TMEM alloc, 3 idle), 4.
 constexpr int Q_BYTES = AQ * AD * 2;    // 16 KB
 constexpr int KV_BYTES = AK * AD * 2;   // 8 KB per K or V tile
 constexpr int P_BYTES = AQ * AK * 2;    // 16 KB
-constexpr int KV_STAGES = 4;            // K/V prefetch distance: TMA latency (~1 us) spans more than one softmax tile
-constexpr int ATC_DATA = Q_BYTES + KV_STAGES * 2 * KV_BYTES + P_BYTES;       // 96 KB
+constexpr int KV_STAGES = 3;
+constexpr int ATC_DATA = Q_BYTES + KV_STAGES * 2 * KV_BYTES + 2 * P_BYTES;   // 96 KB
 constexpr int ATC_XCH = 2 * 2 * AQ * 4;                                     // row-max / row-sum exchange between half-row threads
 constexpr int ATC_SMEM = ATC_DATA + 256 + ATC_XCH;                           // + barriers; two CTAs fit one SM
 constexpr uint32_t TM_S = 0, TM_O = 128, TM_COLS = 256;   // S double buffered (2 x 64 columns), O 64 columns
@@ -65,7 +65,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sQ = smem;
   uint8_t* sKV = smem + Q_BYTES;                               // [stage][K | V]
-  uint8_t* sP = smem + Q_BYTES + KV_STAGES * 2 * KV_BYTES;     // single buffer: P_j V_j is short
+  uint8_t* sP = smem + Q_BYTES + KV_STAGES * 2 * KV_BYTES;     // [2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATC_DATA);
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("aptai attention: dynamic shared memory base is not 1024-byte aligned\n");
@@ -75,11 +75,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* q_empty = bars + 1;
   uint64_t* o_full = bars + 2;
   uint64_t* o_empty = bars + 3;
-  uint64_t* kv_full = bars + 4;    // [4]
-  uint64_t* kv_empty = bars + 8;   // [4]  P_j V_j complete
-  uint64_t* s_full = bars + 12;    // [2]
-  uint64_t* p_full = bars + 14;    // P_j written (and S_j consumed)
-  uint64_t* p_empty = bars + 15;   // P_j V_j complete
+  uint64_t* kv_full = bars + 4;    // [3]
+  uint64_t* kv_empty = bars + 7;   // [3]  P_j V_j complete
+  uint64_t* s_full = bars + 10;    // [2]
+  uint64_t* p_full = bars + 12;    // [2]  P_j written (and S_j consumed)
+  uint64_t* p_empty = bars + 14;   // [2]  P_j V_j complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   float* xch = reinterpret_cast<float*>(smem + ATC_DATA + 256);   // [2 parity][2 halves][128 rows]
 
@@ -97,9 +97,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_init(&kv_full[i], 1);
       mbar_init(&kv_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) mbar_init(&s_full[i], 1);
-    mbar_init(p_full, 8);
-    mbar_init(p_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 8);
+      mbar_init(&p_empty[i], 1);
+    }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, TM_COLS);
@@ -164,17 +166,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int j = 0; j < n; ++j) {
           const uint32_t gj = g + j, sb = gj & 1, st = gj % KV_STAGES;
           const int nj = min(AK, ((klen - j * AK) + 15) & ~15);
-          mbar_wait_backoff(p_full, gj & 1, 32);               // P_j in shared memory, S_j consumed
+          mbar_wait_backoff(&p_full[sb], (gj >> 1) & 1, 32);   // P_j in shared memory, S_j consumed
           if (j + 2 < n) issue_s(j + 2);                  // refill the S buffer that just became free
           if (j == 0) mbar_wait(o_empty, (it & 1) ^ 1);   // previous item's O has been read out
           tc_fence_after();
-          const uint32_t p_addr = smem_u32(sP);
+          const uint32_t p_addr = smem_u32(sP + sb * P_BYTES);
           const uint32_t v_addr = smem_u32(sKV + st * 2 * KV_BYTES + KV_BYTES);
           for (int k = 0; k < nj / 16; ++k)
             umma_bf16(tmem_base + TM_O, umma_desc_sw128(p_addr + k * 32), umma_desc_sw128_mn(v_addr + k * 2048),
                       IDESC_PV, (j | k) != 0 ? 1u : 0u);
           umma_commit(&kv_empty[st]);
-          umma_commit(p_empty);
+          umma_commit(&p_empty[sb]);
           if (j == n - 1) umma_commit(o_full);
         }
         g += n;
@@ -234,7 +236,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const bool need = (factor != 1.f) && (j > 0);
         if (__any_sync(0xffffffffu, need)) {
           // O must be complete (P_{j-1} V_{j-1} done) before it is rescaled in place; each half owns 32 columns
-          mbar_wait(p_empty, (g - 1) & 1);
+          const uint32_t gp = g - 1;
+          mbar_wait(&p_empty[gp & 1], (gp >> 1) & 1);
           tc_fence_after();
           uint32_t r[32];
           tmem_ld32(t_lane + TM_O + half * 32, r);
@@ -255,8 +258,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         l *= factor;
         // p = exp2(s*log2e - m_used); my 32 keys -> 4 of the 8 sixteen-byte units of the row (K-major SWIZZLE_128B)
-        if (g > 0) mbar_wait(p_empty, (g - 1) & 1);   // P_{j-1} V_{j-1} has consumed the P buffer
-        uint8_t* prow = sP + row * 128;
+        mbar_wait(&p_empty[sb], (u & 1) ^ 1);      // P_{j-2} V_{j-2} has consumed this P buffer
+        uint8_t* prow = sP + sb * P_BYTES + row * 128;
         float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
         const int ncol16 = (min(AK, klen - j * AK) + 15) >> 4;      // 16-key groups the P V MMA will read
 #pragma unroll
@@ -280,7 +283,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tc_fence_before();
         fence_async_proxy();
         __syncwarp();
-        if (lane == 0) mbar_arrive(p_full);
+        if (lane == 0) mbar_arrive(&p_full[sb]);
       }
       // ---- output: O / l -> bf16 (each half owns 32 of the 64 columns; the row sum is exchanged first)
       float* xl = xch + (it & 1) * 2 * AQ;
