@@ -343,7 +343,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--utterances", type=int, default=4096)
-    ap.add_argument("--max-rows", type=int, default=49152)
+    ap.add_argument("--max-rows", type=int, default=75776)   # 4 x (74 CTA pairs x 256 rows)
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
