@@ -1,0 +1,146 @@
+// Fused cross-attention block of Force_APTAI (models/modules.py:129-153 + models/force_aptai.py:118-130):
+//   phn = Embedding(ids) + PE            (models/force_aptai.py:118-119, modules.py:233)
+//   q = W_q frame + b_q ; k = W_k phn + b_k
+//   energy = q k^T - 1000 * (1 - mask)   (unscaled, modules.py:144-146)
+//   att_out = LayerNorm_256(cat[softmax(energy) k, q])
+//   att = log_softmax(energy - 1000 * (1 - mask))   (mask applied a second time, force_aptai.py:128-130)
+// One CTA = 16 frames of one utterance; W_q and the utterance's 60 projected phoneme keys live in shared memory.
+// fp32 throughout: 60 keys x 128 dims is far below a tensor-core tile, and the alignment argmax wants fp32 energies.
+#include "common.h"
+#include "ptx.cuh"
+
+namespace aptai {
+
+constexpr int XA_D = 128;      // frame / phoneme / attention hidden dim
+constexpr int XA_N = 60;       // max phoneme sequence length
+constexpr int XA_F = 16;       // frames per CTA
+constexpr int XA_THREADS = 128;
+
+struct XAttnArgs {
+  const float* frame;     // [B][T][128]
+  const int* phn_ids;     // [B][60] (0 = padding)
+  const float* emb;       // [V][128]
+  const float* pe;        // [60][128]
+  const float* wq; const float* bq; const float* wk; const float* bk;   // [128][128], [128]
+  const float* ln_w; const float* ln_b;                                 // [256]
+  float* att_out;         // [B][T][256]
+  float* energy;          // [B][T][60]  (after the first mask)
+  float* att;             // [B][T][60]  log_softmax(energy + mask)
+  int B, T;
+  float eps;
+};
+
+__global__ void __launch_bounds__(XA_THREADS)
+xattn_kernel(const XAttnArgs a) {
+  extern __shared__ float sm[];
+  float* s_w = sm;                              // W_q, later reused row-wise: [128][129]
+  float* s_k = s_w + XA_D * (XA_D + 1);         // k_phn [60][129]
+  float* s_x = s_k + XA_N * (XA_D + 1);         // staging: phoneme embedding row / frame row [128]
+  float* s_q = s_x + XA_D;                      // q [128]
+  float* s_p = s_q + XA_D;                      // energies / probabilities [64]
+  float* s_o = s_p + 64;                        // att_out [128]
+  float* s_red = s_o + XA_D;                    // reductions [8]
+  __shared__ float s_mask[XA_N];
+  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int t0 = blockIdx.x * XA_F;
+  // ---- k = W_k (emb + pe) + b_k for the utterance's 60 slots
+  for (int i = tid; i < XA_D * XA_D; i += XA_THREADS) s_w[(i / XA_D) * (XA_D + 1) + (i % XA_D)] = a.wk[i];
+  if (tid < XA_N) s_mask[tid] = a.phn_ids[b * XA_N + tid] != 0 ? 0.f : -1000.f;
+  __syncthreads();
+  for (int n = 0; n < XA_N; ++n) {
+    const int id = a.phn_ids[b * XA_N + n];
+    s_x[tid] = a.emb[id * XA_D + tid] + a.pe[n * XA_D + tid];
+    __syncthreads();
+    float acc = a.bk[tid];
+#pragma unroll 8
+    for (int k = 0; k < XA_D; ++k) acc = fmaf(s_x[k], s_w[tid * (XA_D + 1) + k], acc);
+    s_k[n * (XA_D + 1) + tid] = acc;
+    __syncthreads();
+  }
+  for (int i = tid; i < XA_D * XA_D; i += XA_THREADS) s_w[(i / XA_D) * (XA_D + 1) + (i % XA_D)] = a.wq[i];
+  __syncthreads();
+  const float bq = a.bq[tid];
+  for (int f = 0; f < XA_F; ++f) {
+    const int t = t0 + f;
+    if (t >= a.T) break;                        // uniform across the CTA
+    const long long row = static_cast<long long>(b) * a.T + t;
+    s_x[tid] = a.frame[row * XA_D + tid];
+    __syncthreads();
+    float q = bq;
+#pragma unroll 8
+    for (int k = 0; k < XA_D; ++k) q = fmaf(s_x[k], s_w[tid * (XA_D + 1) + k], q);
+    s_q[tid] = q;
+    __syncthreads();
+    // energies (threads 0..59), first mask
+    float e = -INFINITY;
+    if (tid < XA_N) {
+      float acc = 0.f;
+#pragma unroll 8
+      for (int c = 0; c < XA_D; ++c) acc = fmaf(s_q[c], s_k[tid * (XA_D + 1) + c], acc);
+      e = acc + s_mask[tid];
+      a.energy[row * XA_N + tid] = e;
+      s_p[tid] = e;
+    }
+    __syncthreads();
+    // softmax(energy) and log_softmax(energy + mask) over the 60 slots: every thread scans the 60 values
+    float m1 = -INFINITY, m2 = -INFINITY;
+    for (int n = 0; n < XA_N; ++n) {
+      m1 = fmaxf(m1, s_p[n]);
+      m2 = fmaxf(m2, s_p[n] + s_mask[n]);
+    }
+    float z1 = 0.f, z2 = 0.f;
+    for (int n = 0; n < XA_N; ++n) {
+      z1 += expf(s_p[n] - m1);
+      z2 += expf(s_p[n] + s_mask[n] - m2);
+    }
+    if (tid < XA_N) a.att[row * XA_N + tid] = (e + s_mask[tid]) - m2 - logf(z2);
+    __syncthreads();
+    if (tid < XA_N) s_p[tid] = expf(e - m1) / z1;
+    __syncthreads();
+    float o = 0.f;
+    for (int n = 0; n < XA_N; ++n) o = fmaf(s_p[n], s_k[n * (XA_D + 1) + tid], o);
+    // LayerNorm over cat[att_out, q] (256 values: two per thread), exact two-pass statistics
+    float s = o + q;
+    for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if (lane == 0) s_red[warp] = s;
+    __syncthreads();
+    const float mean = (s_red[0] + s_red[1] + s_red[2] + s_red[3]) * (1.0f / 256);
+    float v = (o - mean) * (o - mean) + (q - mean) * (q - mean);
+    for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (lane == 0) s_red[4 + warp] = v;
+    __syncthreads();
+    const float rstd = rsqrtf((s_red[4] + s_red[5] + s_red[6] + s_red[7]) * (1.0f / 256) + a.eps);
+    a.att_out[row * 256 + tid] = fmaf((o - mean) * rstd, a.ln_w[tid], a.ln_b[tid]);
+    a.att_out[row * 256 + XA_D + tid] = fmaf((q - mean) * rstd, a.ln_w[XA_D + tid], a.ln_b[XA_D + tid]);
+    __syncthreads();
+  }
+}
+
+}  // namespace aptai
+
+using namespace aptai;
+
+extern "C" int aptai_cross_attention(const float* frame, const int32_t* phn_ids, const float* emb, int vocab,
+                                     const float* pe, const float* wq, const float* bq, const float* wk,
+                                     const float* bk, const float* ln_w, const float* ln_b, float eps, int B, int T,
+                                     float* att_out, float* energy, float* att, void* stream) {
+  if (int rc = check_arch()) return rc;
+  APTAI_REQUIRE(frame && phn_ids && emb && pe && wq && bq && wk && bk && ln_w && ln_b && att_out && energy && att,
+                "cross_attention: null pointer");
+  APTAI_REQUIRE(B >= 1 && T >= 1 && vocab >= 1 && B <= 65535, "cross_attention: bad shape");
+  XAttnArgs a;
+  a.frame = frame; a.phn_ids = phn_ids; a.emb = emb; a.pe = pe; a.wq = wq; a.bq = bq; a.wk = wk; a.bk = bk;
+  a.ln_w = ln_w; a.ln_b = ln_b; a.att_out = att_out; a.energy = energy; a.att = att; a.B = B; a.T = T; a.eps = eps;
+  const size_t smem = sizeof(float) * (XA_D * (XA_D + 1) + XA_N * (XA_D + 1) + XA_D + XA_D + 64 + XA_D + 8);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(xattn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) {
+      set_error("cross_attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    attr_set = true;
+  }
+  xattn_kernel<<<dim3((T + XA_F - 1) / XA_F, B), XA_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  return after_launch("cross_attention");
+}

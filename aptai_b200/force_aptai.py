@@ -74,15 +74,16 @@ class Force_APTAI(nn.Module):
             padded.append(np.pad(lst, (0, self.max_phn_seq_len - len(lst)), mode="constant"))
         phn_pred_seq = torch.tensor(np.stack(padded), dtype=torch.int32, device=dev)
         phn_pred_mask = (phn_pred_seq != 0).to(torch.int)
-        phn_embs = self.phn_emb_layer(phn_pred_seq)
-        phn_embs = self.pe_phn(phn_embs.permute(1, 0, 2)).permute(1, 0, 2)
         B, T, H = h.shape
         fl = self.frame_lin                 # Linear(H,128) on the tcgen05 GEMM, bf16x3 split (fp32-accurate)
         fh = ops.linear_f32x3(h.reshape(B * T, H).contiguous(), fl.weight, fl.bias.detach().float().contiguous())
-        frame_hidden_emb = self.frame_drop(fh.view(B, T, -1))
-        att_out, energy = self.xatt(frame_hidden_emb, phn_embs, phn_pred_mask)
-        att_mask = ((1 - phn_pred_mask) * -1000.0).unsqueeze(1)
-        att = ops.softmax_rows((energy + att_mask).contiguous(), log=True)     # mask applied twice, as the reference
+        # fused cross-attention kernel: embedding + PE, q/k projections, masked softmax, LayerNorm(256) and the
+        # log-softmax alignment matrix (eval mode: the two dropouts are identities)
+        xa = self.xatt
+        att_out, energy, att = ops.cross_attention(fh.view(B, T, -1), phn_pred_seq.contiguous(),
+                                                   self.phn_emb_layer.weight, self.pe_phn.pe[:, 0, :], xa.q.weight,
+                                                   xa.q.bias, xa.k.weight, xa.k.bias, xa.layer_norm.weight,
+                                                   xa.layer_norm.bias, xa.layer_norm.eps)
         return dict(h=h, logits=logits, frame_seq_lens=frame_seq_lens, phn_pred_list=phn_pred_list,
                     phn_seq_lens=phn_seq_lens, phn_pred_seq=phn_pred_seq, att_out=att_out, att=att)
 

@@ -131,6 +131,15 @@ int aptai_lowpass_fir(const float* x, int B, int T, int C, const double* taps, i
  * (models/aptai.py:105,148 F.softmax; models/force_aptai.py:130 log_softmax). */
 int aptai_softmax_rows(const float* x, int64_t rows, int V, int log_out, float* y, void* stream);
 
+/* Force_APTAI cross-attention block (models/force_aptai.py:118-130, models/modules.py:139-153), fp32:
+ * phn = emb[phn_ids] + pe; q = Wq frame + bq; k = Wk phn + bk; energy = q k^T - 1000*(ids==0);
+ * att_out = LayerNorm(cat[softmax(energy) k, q]) [B][T][256]; att = log_softmax(energy - 1000*(ids==0)) [B][T][60].
+ * frame fp32 [B][T][128]; phn_ids int32 [B][60]; emb [vocab][128]; pe [60][128]; Wq/Wk [128][128]. */
+int aptai_cross_attention(const float* frame, const int32_t* phn_ids, const float* emb, int vocab, const float* pe,
+                          const float* wq, const float* bq, const float* wk, const float* bk, const float* ln_w,
+                          const float* ln_b, float eps, int B, int T, float* att_out, float* energy, float* att,
+                          void* stream);
+
 /* masked MSE + cross entropy of APTAI.forward (models/aptai.py:89-102).  out3 = {loss, mse, ce}. */
 int aptai_masked_mse_ce(const float* tv_pred, const float* tv_tgt, const float* logits, const int64_t* phn_tgt,
                         int64_t rows, int ntv, int V, float* accum_ws, float* out3, void* stream);

@@ -213,3 +213,31 @@ def test_greedy(cuda):
         assert nb == len(t_ref)
         assert np.array_equal(tok[b, :nb].cpu().numpy(), t_ref)
         assert np.array_equal(frm[b, :nb].cpu().numpy(), f_ref)
+
+
+def test_cross_attention_block(cuda):
+    """Fused Force_APTAI cross-attention (embedding + PE + q/k + masked softmax + LayerNorm + log-softmax) against the
+    CPU restatement of models/modules.py:139-153 + models/force_aptai.py:118-130."""
+    g = torch.Generator().manual_seed(3)
+    B, T, V = 3, 70, 46
+    frame = torch.randn((B, T, 128), generator=g)
+    ids = torch.zeros((B, 60), dtype=torch.int32)
+    for b, n in enumerate([30, 59, 1]):
+        ids[b, :n] = torch.randint(1, V, (n,), generator=g).int()
+    emb = torch.randn((V, 128), generator=g) * 0.3
+    emb[0] = 0
+    pe = oheads.positional_encoding(128, 60)
+    wq, bq = torch.randn((128, 128), generator=g) * 0.09, torch.randn((128,), generator=g) * 0.02
+    wk, bk = torch.randn((128, 128), generator=g) * 0.09, torch.randn((128,), generator=g) * 0.02
+    lnw, lnb = 1 + 0.1 * torch.randn((256,), generator=g), 0.1 * torch.randn((256,), generator=g)
+    c = lambda t: t.to(cuda).contiguous()
+    att_out, energy, att = ops.cross_attention(c(frame), c(ids), c(emb), c(pe[:, 0, :]), c(wq), c(bq), c(wk), c(bk),
+                                               c(lnw), c(lnb))
+    mask = (ids != 0).int()
+    phn = torch.nn.functional.embedding(ids.long(), emb) + pe[:60, 0][None]
+    r_out, r_energy = oheads.cross_attention(frame, phn, mask, wq, bq, wk, bk, lnw, lnb)
+    r_att = torch.log_softmax(r_energy + ((1 - mask) * -1000.0).unsqueeze(1), dim=-1)
+    torch.testing.assert_close(energy.cpu(), r_energy, atol=2e-4, rtol=1e-4)
+    torch.testing.assert_close(att_out.cpu(), r_out, atol=2e-4, rtol=1e-4)
+    torch.testing.assert_close(att.cpu(), r_att, atol=2e-4, rtol=1e-4)
+    assert torch.equal(att.cpu().argmax(-1), r_att.argmax(-1))
