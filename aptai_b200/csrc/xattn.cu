@@ -18,7 +18,8 @@ constexpr int XA_THREADS = 128;
 
 struct XAttnArgs {
   const float* frame;     // [B][T][128]
-  const int* phn_ids;     // [B][60] (0 = padding)
+  const int* phn_ids;     // [B][60] (0 = padding); with phn_hidden: any non-zero = valid slot
+  const float* phn_hidden; // optional [B][60][128]: phoneme embeddings already computed (CrossAttention.forward)
   const float* emb;       // [V][128]
   const float* pe;        // [60][128]
   const float* wq; const float* bq; const float* wk; const float* bk;   // [128][128], [128]
@@ -49,7 +50,8 @@ xattn_kernel(const XAttnArgs a) {
   __syncthreads();
   for (int n = 0; n < XA_N; ++n) {
     const int id = a.phn_ids[b * XA_N + n];
-    s_x[tid] = a.emb[id * XA_D + tid] + a.pe[n * XA_D + tid];
+    s_x[tid] = a.phn_hidden ? a.phn_hidden[(static_cast<long long>(b) * XA_N + n) * XA_D + tid]
+                            : a.emb[id * XA_D + tid] + a.pe[n * XA_D + tid];
     __syncthreads();
     float acc = a.bk[tid];
 #pragma unroll 8
@@ -120,16 +122,17 @@ xattn_kernel(const XAttnArgs a) {
 
 using namespace aptai;
 
-extern "C" int aptai_cross_attention(const float* frame, const int32_t* phn_ids, const float* emb, int vocab,
-                                     const float* pe, const float* wq, const float* bq, const float* wk,
+extern "C" int aptai_cross_attention(const float* frame, const int32_t* phn_ids, const float* phn_hidden,
+                                     const float* emb, int vocab, const float* pe, const float* wq, const float* bq, const float* wk,
                                      const float* bk, const float* ln_w, const float* ln_b, float eps, int B, int T,
                                      float* att_out, float* energy, float* att, void* stream) {
   if (int rc = check_arch()) return rc;
-  APTAI_REQUIRE(frame && phn_ids && emb && pe && wq && bq && wk && bk && ln_w && ln_b && att_out && energy && att,
+  APTAI_REQUIRE(frame && phn_ids && wq && bq && wk && bk && ln_w && ln_b && att_out && energy && att,
                 "cross_attention: null pointer");
+  APTAI_REQUIRE(phn_hidden || (emb && pe), "cross_attention: need phn_hidden or (emb, pe)");
   APTAI_REQUIRE(B >= 1 && T >= 1 && vocab >= 1 && B <= 65535, "cross_attention: bad shape");
   XAttnArgs a;
-  a.frame = frame; a.phn_ids = phn_ids; a.emb = emb; a.pe = pe; a.wq = wq; a.bq = bq; a.wk = wk; a.bk = bk;
+  a.frame = frame; a.phn_ids = phn_ids; a.phn_hidden = phn_hidden; a.emb = emb; a.pe = pe; a.wq = wq; a.bq = bq; a.wk = wk; a.bk = bk;
   a.ln_w = ln_w; a.ln_b = ln_b; a.att_out = att_out; a.energy = energy; a.att = att; a.B = B; a.T = T; a.eps = eps;
   const size_t smem = sizeof(float) * (XA_D * (XA_D + 1) + XA_N * (XA_D + 1) + XA_D + XA_D + 64 + XA_D + 8);
   static bool attr_set = false;

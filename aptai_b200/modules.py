@@ -78,8 +78,8 @@ class ForwardSumLoss(nn.Module):
 
 class CrossAttention(nn.Module):
     """models/modules.py:129-153: q = W_q frame, k = W_k phn, energy = q k^T (unscaled) - 1000*pad,
-    out = LayerNorm(cat[softmax(energy) k, q]).  SURVEY.md §8f ranks the fused kernel for this block as a
-    'next' row; until then the 128-wide projections and the 60-key attention run as device torch ops."""
+    out = LayerNorm(cat[softmax(energy) k, q]).  One fused kernel (csrc/xattn.cu) for the 128-wide block with up to
+    60 phoneme slots that Force_APTAI instantiates; returns (att_out, energy) like the reference."""
 
     def __init__(self, frame_dim, phn_dim, att_dim):
         super().__init__()
@@ -88,14 +88,14 @@ class CrossAttention(nn.Module):
         self.layer_norm = nn.LayerNorm(att_dim * 2)
 
     def forward(self, frame_hidden, phn_hidden, labels_att_mask):
-        q_frame = self.q(frame_hidden)
-        k_phn = self.k(phn_hidden)
-        energy = torch.bmm(q_frame, k_phn.transpose(2, 1))
-        att_mask = (1 - labels_att_mask) * -1000.0
-        energy = energy + att_mask.unsqueeze(1)
-        att_matrix = torch.softmax(energy, dim=-1)
-        att_out = torch.bmm(att_matrix, k_phn)
-        att_out = self.layer_norm(torch.cat([att_out, q_frame], dim=-1))
+        if not (frame_hidden.shape[-1] == phn_hidden.shape[-1] == self.q.out_features == 128
+                and phn_hidden.shape[1] == 60):
+            raise NotImplementedError("aptai_b200 CrossAttention kernel is built for the 128-dim / 60-slot block of "
+                                      "Force_APTAI (models/force_aptai.py:28-41)")
+        att_out, energy, _ = ops.cross_attention(
+            frame_hidden.detach().float().contiguous(), labels_att_mask.to(torch.int32).contiguous(), None, None,
+            self.q.weight, self.q.bias, self.k.weight, self.k.bias, self.layer_norm.weight, self.layer_norm.bias,
+            self.layer_norm.eps, phn_hidden=phn_hidden.detach().float().contiguous())
         return att_out, energy
 
 

@@ -269,7 +269,7 @@ def softmax_rows(x: torch.Tensor, log: bool = False) -> torch.Tensor:
     return y
 
 
-def cross_attention(frame, phn_ids, emb, pe, wq, bq, wk, bk, ln_w, ln_b, eps: float = 1e-5):
+def cross_attention(frame, phn_ids, emb, pe, wq, bq, wk, bk, ln_w, ln_b, eps: float = 1e-5, phn_hidden=None):
     """Force_APTAI cross-attention block.  frame fp32 [B,T,128], phn_ids int32 [B,60] -> (att_out [B,T,256],
     energy [B,T,60], att = log_softmax(energy + mask) [B,T,60])."""
     _req(frame, F32, "frame"); _req(phn_ids, I32, "phn_ids")
@@ -280,9 +280,12 @@ def cross_attention(frame, phn_ids, emb, pe, wq, bq, wk, bk, ln_w, ln_b, eps: fl
     att_out = torch.empty((B, T, 256), dtype=F32, device=dev)
     energy = torch.empty((B, T, 60), dtype=F32, device=dev)
     att = torch.empty((B, T, 60), dtype=F32, device=dev)
-    emb = f(emb)
-    check(_lib.load().aptai_cross_attention(frame.data_ptr(), phn_ids.data_ptr(), emb.data_ptr(), emb.shape[0],
-                                            f(pe).data_ptr(), f(wq).data_ptr(), f(bq).data_ptr(), f(wk).data_ptr(),
+    emb = f(emb) if emb is not None else None
+    pe = f(pe) if pe is not None else None
+    ph = f(phn_hidden) if phn_hidden is not None else None
+    check(_lib.load().aptai_cross_attention(frame.data_ptr(), phn_ids.data_ptr(), _ptr(ph), _ptr(emb),
+                                            emb.shape[0] if emb is not None else 1,
+                                            _ptr(pe), f(wq).data_ptr(), f(bq).data_ptr(), f(wk).data_ptr(),
                                             f(bk).data_ptr(), f(ln_w).data_ptr(), f(ln_b).data_ptr(), eps, B, T,
                                             att_out.data_ptr(), energy.data_ptr(), att.data_ptr(), _stream()),
           "cross_attention")

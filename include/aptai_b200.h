@@ -135,7 +135,9 @@ int aptai_softmax_rows(const float* x, int64_t rows, int V, int log_out, float* 
  * phn = emb[phn_ids] + pe; q = Wq frame + bq; k = Wk phn + bk; energy = q k^T - 1000*(ids==0);
  * att_out = LayerNorm(cat[softmax(energy) k, q]) [B][T][256]; att = log_softmax(energy - 1000*(ids==0)) [B][T][60].
  * frame fp32 [B][T][128]; phn_ids int32 [B][60]; emb [vocab][128]; pe [60][128]; Wq/Wk [128][128]. */
-int aptai_cross_attention(const float* frame, const int32_t* phn_ids, const float* emb, int vocab, const float* pe,
+int aptai_cross_attention(const float* frame, const int32_t* phn_ids, const float* phn_hidden /* optional [B][60][128]:
+                          precomputed phoneme embeddings, then phn_ids is only the 0/non-0 padding mask */,
+                          const float* emb, int vocab, const float* pe,
                           const float* wq, const float* bq, const float* wk, const float* bk, const float* ln_w,
                           const float* ln_b, float eps, int B, int T, float* att_out, float* energy, float* att,
                           void* stream);

@@ -241,3 +241,13 @@ def test_cross_attention_block(cuda):
     torch.testing.assert_close(att_out.cpu(), r_out, atol=2e-4, rtol=1e-4)
     torch.testing.assert_close(att.cpu(), r_att, atol=2e-4, rtol=1e-4)
     assert torch.equal(att.cpu().argmax(-1), r_att.argmax(-1))
+    # module form (models/modules.py:129-153 signature): precomputed phoneme embeddings + 0/1 mask
+    from aptai_b200.modules import CrossAttention
+    m = CrossAttention(128, 128, 128)
+    with torch.no_grad():
+        m.q.weight.copy_(wq); m.q.bias.copy_(bq); m.k.weight.copy_(wk); m.k.bias.copy_(bk)
+        m.layer_norm.weight.copy_(lnw); m.layer_norm.bias.copy_(lnb)
+    m = m.to(cuda)
+    o2, e2 = m(c(frame), c(phn), c(mask))
+    torch.testing.assert_close(o2.cpu(), r_out, atol=2e-4, rtol=1e-4)
+    torch.testing.assert_close(e2.cpu(), r_energy, atol=2e-4, rtol=1e-4)
