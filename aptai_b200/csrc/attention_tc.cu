@@ -2,11 +2,11 @@
 //
 // Persistent, warp-specialised, one work item = 128 query rows of one (utterance, head); two CTAs are resident
 // per SM (256 TMEM columns and 96 KB of shared memory each) so that the softmax warps of both keep the MUFU busy:
-//   warp 0      TMA producer   Q tile once per item; (K_j, V_j) tiles of 64 keys through a 3-stage ring
-//   warp 1      MMA issuer     S_j = Q K_j^T  (M=128, N=n_j<=64, K=64) -> TMEM S buffer j%2 (double buffered)
+//   warp 8      TMA producer   Q tile once per item; (K_j, V_j) tiles of 64 keys through a 3-stage ring
+//   warp 9      MMA issuer     S_j = Q K_j^T  (M=128, N=n_j<=64, K=64) -> TMEM S buffer j%2 (double buffered)
 //                              O  += P_j V_j  (M=128, N=64, K=n_j)     -> TMEM O; P_j (bf16) from shared memory,
 //                                                                         V_j as an MN-major B operand
-//   warps 4..11 softmax        two threads per query row (32 of the tile's 64 keys each): tcgen05.ld, key-length mask, running max
+//   warps 0..7  softmax        two threads per query row (32 of the tile's 64 keys each): tcgen05.ld, key-length mask, running max
 //                              with lazy rescaling of O (only when the max grows by more than 2^8), exp2, row sum,
 //                              P_j -> shared memory in the UMMA K-major SWIZZLE_128B layout; final O / l -> bf16
 // S_{j+2} is issued as soon as P_j is written (S buffer j%2 free), so S_{j+1} is always ready when the softmax
@@ -23,7 +23,8 @@ namespace aptai {
 constexpr int AQ = 128;                 // query rows per work item
 constexpr int AK = 64;                  // keys per KV tile
 constexpr int AD = 64;                  // head dim
-constexpr int ATC_THREADS = 384;        // warps 0,1 (+2 TMEM alloc, 3 idle), 4..11 softmax (2 warps per 32-row quadrant)
+constexpr int ATC_THREADS = 384;        // warps 0..7 softmax (2 per 32-row quadrant), 8 TMA, 9 MMA, 10 TMEM alloc
+constexpr int W_TMA = 8, W_MMA = 9, W_ALLOC = 10;   // single-thread roles in the highest warp ids (issue priority)
 constexpr int Q_BYTES = AQ * AD * 2;    // 16 KB
 constexpr int KV_BYTES = AK * AD * 2;   // 8 KB per K or V tile
 constexpr int P_BYTES = AQ * AK * 2;    // 16 KB
@@ -84,11 +85,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   float* xch = reinterpret_cast<float*>(smem + ATC_DATA + 256);   // [2 parity][2 halves][128 rows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
+  if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == W_MMA && lane == 0) {
     mbar_init(q_full, 1);
     mbar_init(q_empty, 1);
     mbar_init(o_full, 1);
@@ -104,13 +105,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, TM_COLS);
+  if (warp == W_ALLOC) tmem_alloc(tmem_slot, TM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == W_TMA) {
     // ---------------------------------------------------------------- TMA producer
     if (lane == 0) {
       uint32_t g = 0, it = 0;
@@ -133,7 +134,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == W_MMA) {
     // ---------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       constexpr uint32_t IDESC_BASE = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(AQ >> 4) << 24);
@@ -182,12 +183,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         g += n;
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp < 8) {
     // ---------------------------------------------------------------- softmax + output
     // two threads per query row: warp w and warp w+4 share TMEM quadrant w%4; `half` selects 32 of the 64 keys of
     // a tile (and 32 of the 64 output columns).  The row maximum is exchanged through shared memory.
     const int q = warp & 3;
-    const int half = (warp - 4) >> 2;
+    const int half = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     const uint32_t pair_bar = 1 + q;                       // named barrier of the two warps of this quadrant
@@ -316,7 +317,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == W_ALLOC) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TM_COLS);
   }
