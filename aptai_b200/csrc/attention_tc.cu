@@ -40,7 +40,6 @@ struct AttnParams {
   const int* key_len;
   __nv_bfloat16* ctx;
   int B, T, heads, H, n_qt, items;
-  int dbg;   // ablation switches for profiles/attn_ablate.py (0 in the product path): 1 no exp, 2 no P store, 4 no S load
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {   // single MUFU.EX2 (flushes denormal results to 0)
@@ -208,13 +207,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_wait(&s_full[sb], u & 1);
         tc_fence_after();
         uint32_t r0[32];
-        if (!(p.dbg & 4)) {
-          tmem_ld32(t_lane + TM_S + sb * AK + half * 32, r0);
-          tmem_ld_wait();
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) r0[i] = __float_as_uint(0.01f * (lane + i));
-        }
+        tmem_ld32(t_lane + TM_S + sb * AK + half * 32, r0);
+        tmem_ld_wait();
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
         if (full_half) {
 #pragma unroll
@@ -274,13 +268,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           float pv[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float arg = fmaf(__uint_as_float(r0[u8 * 8 + i]), ATC_LOG2E, -m_used);
-            pv[i] = (p.dbg & 1) ? arg : ex2_approx(arg);
+            pv[i] = ex2_approx(fmaf(__uint_as_float(r0[u8 * 8 + i]), ATC_LOG2E, -m_used));
             if (!full_half && u8 * 8 + i >= valid) pv[i] = 0.f;
           }
           rs0 += pv[0] + pv[4]; rs1 += pv[1] + pv[5]; rs2 += pv[2] + pv[6]; rs3 += pv[3] + pv[7];
           const int unit = half * 4 + u8;
-          if ((unit >> 1) < ncol16 && !(p.dbg & 2)) {
+          if ((unit >> 1) < ncol16) {
             uint4 v4 = make_uint4(pack_bf16(pv[0], pv[1]), pack_bf16(pv[2], pv[3]), pack_bf16(pv[4], pv[5]),
                                   pack_bf16(pv[6], pv[7]));
             *reinterpret_cast<uint4*>(prow + ((unit ^ (row & 7)) << 4)) = v4;
@@ -357,7 +350,6 @@ extern "C" int aptai_attention_fwd(const void* qkv, void* ctx, const int32_t* ke
   p.B = B; p.T = T; p.heads = heads; p.H = H;
   p.n_qt = (T + AQ - 1) / AQ;
   p.items = B * heads * p.n_qt;
-  p.dbg = getenv("APTAI_ATTN_DBG") ? atoi(getenv("APTAI_ATTN_DBG")) : 0;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
