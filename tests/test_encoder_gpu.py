@@ -53,3 +53,37 @@ def test_full_width_two_layers(cuda, variant, H, heads, F):
     ref, out = _run(cfg, lens, 32000, cuda)
     err = (out.last_hidden_state.cpu() - ref[-1]).abs()
     assert err.max().item() < 6e-2 and err.mean().item() < 1e-2, (err.max().item(), err.mean().item())
+
+
+@pytest.mark.parametrize("variant", ["layer", "group"])
+def test_edge_lengths_ragged_and_minimal(cuda, variant):
+    """Ragged batch whose shortest utterance yields a single frame (400 samples -> T=1), next to a full-length one."""
+    cfg = _cfg(variant)
+    lens = [8000, 400, 3217]
+    ref, out = _run(cfg, lens, 8000, cuda)
+    T = ref[-1].shape[1]
+    assert T == 24 and out.last_hidden_state.shape == ref[-1].shape
+    err = (out.last_hidden_state.cpu() - ref[-1]).abs()
+    assert err.max().item() < 8e-2 and err.mean().item() < 1.2e-2, (err.max().item(), err.mean().item())
+
+
+def test_single_frame_utterance(cuda):
+    """The shortest legal input: 400 samples = one frame, batch of one (every conv layer produces 79..1 frames)."""
+    cfg = _cfg("layer")
+    ref, out = _run(cfg, [400], 400, cuda)
+    assert out.last_hidden_state.shape == (1, 1, cfg.hidden_size)
+    assert (out.last_hidden_state.cpu() - ref[-1]).abs().max().item() < 8e-2
+
+
+def test_maximum_length_20s(cuda):
+    """20 s = 320 000 samples -> 999 frames (8 attention KV tiles of 128 queries, 16 of 64 keys), padded partner of 2 s."""
+    cfg = _cfg("layer")
+    lens = [320000, 32000]
+    ref, out = _run(cfg, lens, 320000, cuda)
+    assert ref[-1].shape[1] == 999
+    err = (out.last_hidden_state.cpu() - ref[-1]).abs()
+    assert err.max().item() < 8e-2 and err.mean().item() < 1.2e-2, (err.max().item(), err.mean().item())
+    # valid frames of the short utterance must not depend on the 899 padded frames behind it ('layer' variant)
+    ref_s, out_s = _run(cfg, [32000], 32000, cuda)
+    d = (out.last_hidden_state[1, :99] - out_s.last_hidden_state[0, :99]).abs().max().item()
+    assert d < 3e-2, d
