@@ -51,7 +51,10 @@ struct GemmCfg {
   static constexpr int B_ROWS = UN / NPAIR;                      // rows of one B sub-tile held by this CTA
   static constexpr int B_BYTES = (BN / NPAIR) * BLOCK_K * 2;     // per CTA: its share of the B columns
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = STAGE_BYTES > 64 * 1024 ? 2 : (STAGE_BYTES > 40 * 1024 ? 4 : 6);
+  // narrow tiles (grouped pos-conv, N = 48/64): the tensor core is fed by ~100-cycle tcgen05.mma issues of only
+  // 32 cycles of work each, so two CTAs per SM (two issuing threads) are worth more than a deep ring
+  static constexpr int CTAS_PER_SM = (BN <= 64 && !CTA2) ? 2 : 1;
+  static constexpr int STAGES = CTAS_PER_SM == 2 ? 3 : (STAGE_BYTES > 64 * 1024 ? 2 : (STAGE_BYTES > 40 * 1024 ? 4 : 6));
   static constexpr int ACC_STRIDE = BN < 64 ? 64 : BN;
   static constexpr int ACC_STAGES = (2 * ACC_STRIDE <= 512) ? 2 : 1;
   static constexpr int TMEM_COLS = ACC_STAGES * ACC_STRIDE <= 128 ? 128 : (ACC_STAGES * ACC_STRIDE <= 256 ? 256 : 512);
@@ -435,7 +438,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
 }
 
 template <int BN, bool LN>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, (GemmCfg<BN, false>::CTAS_PER_SM))
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const GemmParams p) {
   gemm_body<BN, LN, false>(tmA, tmB, p);
@@ -481,7 +484,8 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
     }
     attr_set = true;
   }
-  int grid = p.num_tiles < num_sms() ? p.num_tiles : num_sms();
+  const int slots = num_sms() * C::CTAS_PER_SM;
+  int grid = p.num_tiles < slots ? p.num_tiles : slots;
   kern<<<grid, GEMM_THREADS, C::SMEM_BYTES, st>>>(ta, tb, p);
   return after_launch("gemm_bf16_tcgen05");
 }
