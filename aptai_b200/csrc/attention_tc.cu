@@ -3,8 +3,8 @@
 // Persistent, warp-specialised, one work item = 128 query rows of one (utterance, head); two CTAs are resident
 // per SM (256 TMEM columns and 96 KB of shared memory each) so that the softmax warps of both keep the MUFU busy:
 //   warp 8      TMA producer   Q tile once per item; (K_j, V_j) tiles of 64 keys through a 3-stage ring
-//   warp 9      MMA issuer     S_j = Q K_j^T  (M=128, N=n_j<=64, K=64) -> TMEM S buffer j%2 (double buffered)
-//                              O  += P_j V_j  (M=128, N=64, K=n_j)     -> TMEM O; P_j (bf16) from shared memory,
+//   warp 9      MMA issuer 1   S_j = Q K_j^T  (M=128, N=n_j<=64, K=64) -> TMEM S buffer j%2 (double buffered)
+//   warp 10     MMA issuer 2   O  += P_j V_j  (M=128, N=64, K=n_j)     -> TMEM O; P_j (bf16) from shared memory,
 //                                                                         V_j as an MN-major B operand
 //   warps 0..7  softmax        two threads per query row (32 of the tile's 64 keys each): tcgen05.ld, key-length mask, running max
 //                              with lazy rescaling of O (only when the max grows by more than 2^8), exp2, row sum,
@@ -23,8 +23,8 @@ namespace aptai {
 constexpr int AQ = 128;                 // query rows per work item
 constexpr int AK = 64;                  // keys per KV tile
 constexpr int AD = 64;                  // head dim
-constexpr int ATC_THREADS = 384;        // warps 0..7 softmax (2 per 32-row quadrant), 8 TMA, 9 MMA, 10 TMEM alloc
-constexpr int W_TMA = 8, W_MMA = 9, W_ALLOC = 10;   // single-thread roles in the highest warp ids (issue priority)
+constexpr int ATC_THREADS = 384;        // warps 0..7 softmax (2 per 32-row quadrant), 8 TMA, 9 S-MMA, 10 PV-MMA, 11 TMEM alloc
+constexpr int W_TMA = 8, W_MMA = 9, W_MMA2 = 10, W_ALLOC = 11;   // single-thread roles in the highest warp ids
 constexpr int Q_BYTES = AQ * AD * 2;    // 16 KB
 constexpr int KV_BYTES = AK * AD * 2;   // 8 KB per K or V tile
 constexpr int P_BYTES = AQ * AK * 2;    // 16 KB
@@ -135,10 +135,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
     }
   } else if (warp == W_MMA) {
-    // ---------------------------------------------------------------- MMA issuer
+    // ---------------------------------------------------------------- MMA issuer 1: S_j = Q K_j^T
+    // (two issuing threads per CTA: a tcgen05.mma issue costs the thread ~100 cycles but these N=64 MMAs are
+    //  only 32 cycles of tensor work, so a single issuer for S and PV was the bottleneck of the tile period)
     if (lane == 0) {
       constexpr uint32_t IDESC_BASE = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(AQ >> 4) << 24);
-      constexpr uint32_t IDESC_PV = IDESC_BASE | (1u << 16) | (static_cast<uint32_t>(AD >> 3) << 17);   // B MN-major, N=64
       uint32_t g = 0, it = 0;
       for (int w = blockIdx.x; w < p.items; w += gridDim.x, ++it) {
         const int bh = w / p.n_qt;
@@ -146,41 +147,52 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int klen = max(1, min(__ldg(p.key_len + b), p.T));
         const int n = (klen + AK - 1) / AK;
         mbar_wait(q_full, it & 1);
-        tc_fence_after();
         const uint32_t q_addr = smem_u32(sQ);
-        auto issue_s = [&](int j) {                       // S_j = Q K_j^T into S buffer (g+j)&1
-          const uint32_t gj = g + j, st = gj % KV_STAGES, u = gj / KV_STAGES;
+        for (int j = 0; j < n; ++j, ++g) {
+          const uint32_t st = g % KV_STAGES, u = g / KV_STAGES;
           const int nj = min(AK, ((klen - j * AK) + 15) & ~15);
+          // S buffer g&1 was last used by tile g-2: the softmax warps have consumed it once P_{g-2} is written
+          if (g >= 2) mbar_wait_backoff(&p_full[g & 1], ((g - 2) >> 1) & 1, 32);
           mbar_wait(&kv_full[st], u & 1);
           tc_fence_after();
           const uint32_t k_addr = smem_u32(sKV + st * 2 * KV_BYTES);
           const uint32_t idesc = IDESC_BASE | (static_cast<uint32_t>(nj >> 3) << 17);
 #pragma unroll
           for (int k = 0; k < AD / 16; ++k)
-            umma_bf16(tmem_base + TM_S + (gj & 1) * AK, umma_desc_sw128(q_addr + k * 32),
+            umma_bf16(tmem_base + TM_S + (g & 1) * AK, umma_desc_sw128(q_addr + k * 32),
                       umma_desc_sw128(k_addr + k * 32), idesc, k != 0 ? 1u : 0u);
-          umma_commit(&s_full[gj & 1]);
+          umma_commit(&s_full[g & 1]);
           if (j == n - 1) umma_commit(q_empty);           // Q tile no longer needed once the last S is done
-        };
-        issue_s(0);
-        if (n > 1) issue_s(1);
-        for (int j = 0; j < n; ++j) {
-          const uint32_t gj = g + j, sb = gj & 1, st = gj % KV_STAGES;
+        }
+      }
+    }
+  } else if (warp == W_MMA2) {
+    // ---------------------------------------------------------------- MMA issuer 2: O += P_j V_j
+    if (lane == 0) {
+      constexpr uint32_t IDESC_PV = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(AQ >> 4) << 24) |
+                                    (1u << 16) | (static_cast<uint32_t>(AD >> 3) << 17);   // B MN-major, N=64
+      uint32_t g = 0, it = 0;
+      for (int w = blockIdx.x; w < p.items; w += gridDim.x, ++it) {
+        const int bh = w / p.n_qt;
+        const int b = bh / p.heads;
+        const int klen = max(1, min(__ldg(p.key_len + b), p.T));
+        const int n = (klen + AK - 1) / AK;
+        for (int j = 0; j < n; ++j, ++g) {
+          const uint32_t sb = g & 1, st = g % KV_STAGES;
           const int nj = min(AK, ((klen - j * AK) + 15) & ~15);
-          mbar_wait_backoff(&p_full[sb], (gj >> 1) & 1, 32);   // P_j in shared memory, S_j consumed
-          if (j + 2 < n) issue_s(j + 2);                  // refill the S buffer that just became free
-          if (j == 0) mbar_wait(o_empty, (it & 1) ^ 1);   // previous item's O has been read out
+          mbar_wait_backoff(&p_full[sb], (g >> 1) & 1, 32);    // P_j in shared memory (S_j done long before)
+          mbar_wait(&kv_full[st], (g / KV_STAGES) & 1);        // V_j (already landed: S_j needed the same stage)
+          if (j == 0) mbar_wait(o_empty, (it & 1) ^ 1);        // previous item's O has been read out
           tc_fence_after();
           const uint32_t p_addr = smem_u32(sP + sb * P_BYTES);
           const uint32_t v_addr = smem_u32(sKV + st * 2 * KV_BYTES + KV_BYTES);
           for (int k = 0; k < nj / 16; ++k)
             umma_bf16(tmem_base + TM_O, umma_desc_sw128(p_addr + k * 32), umma_desc_sw128_mn(v_addr + k * 2048),
                       IDESC_PV, (j | k) != 0 ? 1u : 0u);
-          umma_commit(&kv_empty[st]);
+          umma_commit(&kv_empty[st]);        // K_j was consumed by S_j, which completed before P_j existed
           umma_commit(&p_empty[sb]);
           if (j == n - 1) umma_commit(o_full);
         }
-        g += n;
       }
     }
   } else if (warp < 8) {
