@@ -84,7 +84,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float2* ln_part = reinterpret_cast<float2*>(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES);
 
-  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // provably warp-uniform (uniform datapath)
+  const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   // CTA pair (cta_group::2): rank 0 is the leader and issues every MMA; each CTA owns 128 rows of the 256-row
   // tile (its own TMEM lanes) and stages its own A rows plus half of the B columns.
@@ -164,10 +164,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       }
     }
   } else if (warp == W_MMA) {
-    // ------------------------------------------------------------------ MMA issuer
-    // The whole warp runs the loop (warp-uniform control flow keeps the descriptors in uniform registers: with a
-    // single-lane branch every tcgen05.mma needed five R2UR moves); one elected lane issues.
-    if (rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0 && rank == 0) {
       const uint32_t IDESC = p.fp16 ? umma_idesc_f16(TILE_M, C::UN) : umma_idesc_bf16(TILE_M, C::UN);
       int stage = 0;
       uint32_t phase = 0;
@@ -182,31 +180,26 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + stage * C::STAGE_BYTES);
           const uint32_t b_base = a_base + C::A_BYTES;
-          if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-              const uint64_t adesc = umma_desc_sw128(a_base + k * UMMA_K * 2);
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t adesc = umma_desc_sw128(a_base + k * UMMA_K * 2);
 #pragma unroll
-              for (int nh = 0; nh < BN / C::UN; ++nh) {
-                const uint64_t bdesc = umma_desc_sw128(b_base + nh * C::B_ROWS * BLOCK_K * 2 + k * UMMA_K * 2);
-                if (CTA2) umma_bf16_cg2(d_tmem + nh * C::UN, adesc, bdesc, IDESC, (kb | k) != 0 ? 1u : 0u);
-                else umma_bf16(d_tmem + nh * C::UN, adesc, bdesc, IDESC, (kb | k) != 0 ? 1u : 0u);
-              }
-            }
-            // smem slot reusable (in both CTAs of the pair) once these MMAs have read it
-            if (CTA2) umma_commit_cg2(&empty_bar[stage], 0x3);
-            else umma_commit(&empty_bar[stage]);
-            if (kb == p.num_kb - 1) {
-              if (CTA2) umma_commit_cg2(&tfull_bar[acc], 0x3);   // accumulator complete -> epilogue warps of both CTAs
-              else umma_commit(&tfull_bar[acc]);
+            for (int nh = 0; nh < BN / C::UN; ++nh) {
+              const uint64_t bdesc = umma_desc_sw128(b_base + nh * C::B_ROWS * BLOCK_K * 2 + k * UMMA_K * 2);
+              if (CTA2) umma_bf16_cg2(d_tmem + nh * C::UN, adesc, bdesc, IDESC, (kb | k) != 0 ? 1u : 0u);
+              else umma_bf16(d_tmem + nh * C::UN, adesc, bdesc, IDESC, (kb | k) != 0 ? 1u : 0u);
             }
           }
-          __syncwarp();
+          // smem slot reusable (in both CTAs of the pair) once these MMAs have read it
+          if (CTA2) umma_commit_cg2(&empty_bar[stage], 0x3);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
+        if (CTA2) umma_commit_cg2(&tfull_bar[acc], 0x3);   // accumulator complete -> epilogue warps of both CTAs
+        else umma_commit(&tfull_bar[acc]);
         if (C::ACC_STAGES == 2) {
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
