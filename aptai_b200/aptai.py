@@ -14,6 +14,7 @@ import torch.nn as nn
 from . import ops
 from .backbone import Wav2Vec2Backbone
 from .modules import LowPassFilterLayer
+from .train import GradBuffer, attach_backward
 
 TV_NAMES = ("LA", "LP", "JA", "TTCL", "TTCD", "TMCL", "TMCD", "TBCL", "TBCD")
 
@@ -54,10 +55,67 @@ class APTAI(nn.Module):
         tv = self.tv_lowpass(tv_raw.view(B, T, 9))
         return tv, logits.view(B, T, -1), pred.view(B, T)
 
+    # ---------------------------------------------------------------------------------------------- training
+    def grad_buffer(self) -> GradBuffer:
+        """Flat fp32 gradient buffer; (re)attaches `p.grad` views when an optimizer's zero_grad(set_to_none=True)
+        dropped them (which also means: start from zero)."""
+        gb = getattr(self, "_grad_buffer", None)
+        if gb is None:
+            gb = GradBuffer(list(self.named_parameters()), self.wav2vec2.fused_grad_groups("wav2vec2."))
+            object.__setattr__(self, "_grad_buffer", gb)
+            return gb
+        dropped = False
+        for n, p in gb.params:
+            if not gb.owns(p):
+                dropped = True
+                p.grad = gb.flat[gb.offsets[n]: gb.offsets[n] + p.numel()].view(p.shape)
+        if dropped:
+            gb.zero()
+        return gb
+
+    def _forward_train(self, audio_inputs, audio_lengths, phn_targets, tv_targets):
+        """Training step forward: same kernels, activations kept; `loss.backward()` launches the backward kernels."""
+        if self.tv_head[0].p > 0 or self.phn_head[0].p > 0:
+            raise NotImplementedError("aptai_b200: head dropout is not built in the training path; use tv_drop=phn_drop=0")
+        w2v = self.wav2vec2
+        dev = next(w2v.parameters()).device
+        wav = audio_inputs.to(device=dev, dtype=torch.float32).contiguous()
+        lens = audio_lengths.reshape(-1).to(device=dev, dtype=torch.int64)
+        flen = w2v._get_feat_extract_output_lengths(lens).to(torch.int32).contiguous()
+        gb = self.grad_buffer()
+        last, sv = w2v.encode_train(wav, flen)
+        B, T, H = last.shape
+        h = last.view(B * T, H)
+        tvl, phl = self.tv_head[2], self.phn_head[2]
+        f = lambda p: p.detach().float().contiguous()
+        wa, ba, wb, bb = f(tvl.weight), f(tvl.bias), f(phl.weight), f(phl.bias)
+        tv_raw, logits, pred = ops.heads(h, wa, ba, ops.ACT_TANH, wb, bb, ops.ACT_LEAKY)
+        tv = self.tv_lowpass(tv_raw.view(B, T, 9))
+        taps = self.tv_lowpass.lowpass.weight.detach().reshape(-1).contiguous()
+        tvt = tv_targets.view(B * T, 9)
+        res, ws = ops.masked_mse_ce(tv.view(B * T, 9), tvt, logits, phn_targets, return_ws=True)
+
+        def run_backward(grad_out):
+            gs = grad_out.detach().reshape(1).to(device=dev, dtype=torch.float32)
+            d_tvlp, d_lg = ops.masked_mse_ce_bwd(tv.view(B * T, 9), tvt, logits, phn_targets, ws, gs)
+            d_tv = ops.lowpass(d_tvlp.view(B, T, 9), taps).view(B * T, 9)   # symmetric FIR: adjoint = the filter
+            dh = ops.heads_bwd(h, d_tv, wa, ops.ACT_TANH, gb.view("tv_head.2.weight"), gb.view("tv_head.2.bias"),
+                               d_lg, wb, ops.ACT_LEAKY, gb.view("phn_head.2.weight"), gb.view("phn_head.2.bias"))
+            w2v.backward(sv, dh, gb, prefix="wav2vec2.")
+
+        loss = attach_backward(res[0], tvl.weight, run_backward)
+        return {"loss": loss, "mse_loss": res[1], "ce_loss": res[2], "tvs_pred": tv, "phn_fc_pred": pred.view(B, T)}
+
     def forward(self, epoch, audio_inputs, audio_lengths, phn_frames_49hz, LA, LP, JA, TTCL, TTCD, TMCL, TMCD, TBCL,
                 TBCD):
-        """models/aptai.py:58-115.  Loss values come from the fused masked-MSE/CE kernel."""
+        """models/aptai.py:58-115.  Loss values come from the fused masked-MSE/CE kernel.  In training mode with
+        autograd enabled the returned loss carries the hand-written backward (train/train_aptai.py:440)."""
         tv_targets = torch.stack([LA, LP, JA, TTCL, TTCD, TMCL, TMCD, TBCL, TBCD], dim=-1).float().contiguous()
+        if self.training and torch.is_grad_enabled():
+            dev = next(self.wav2vec2.parameters()).device
+            return self._forward_train(audio_inputs, audio_lengths,
+                                       phn_frames_49hz.reshape(-1).to(device=dev, dtype=torch.int64).contiguous(),
+                                       tv_targets.to(dev))
         tv, logits, pred = self._heads(audio_inputs, audio_lengths)
         B, T, V = logits.shape
         res = ops.masked_mse_ce(tv.view(B * T, 9), tv_targets.view(B * T, 9).to(tv.device),

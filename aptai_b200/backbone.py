@@ -15,8 +15,12 @@ sm_100a kernels through `aptai_b200.ops`:
 
 Precision policy: bf16 GEMM/attention operands, fp32 accumulation, fp32 residual stream,
 LayerNorm statistics and softmax in fp32.
-Inference only in this round: the kernels have no backward, so `forward` runs under no_grad and refuses
-`self.training` with stochastic regularisers enabled.
+Training: `encode_train` runs the same kernels and keeps every activation the backward needs (no recomputation —
+the reference's gradient checkpointing exists to fit small GPUs, 180 GB of HBM3e holds a 32 x 8 s batch outright);
+`backward` runs the hand-written backward kernels (dgrad on transposed weights, MN-major tcgen05 wgrad, tcgen05
+attention backward, LayerNorm/GELU backward) into a flat gradient buffer.  The stochastic regularisers
+(SpecAugment, LayerDrop, dropout) and the backward of the conv feature encoder (frozen by the reference,
+models/aptai.py:39-40) are not built: `forward` refuses those configurations instead of silently differing.
 """
 from __future__ import annotations
 
@@ -144,6 +148,35 @@ class _Plan:
                 ln2_w=f(l.final_layer_norm.weight), ln2_b=f(l.final_layer_norm.bias)))
 
 
+class _TrainPlan:
+    """Backward-side operand copies: transposed bf16 weights for the dgrad GEMMs (dX = dY @ W is the forward kernel
+    on W^T), the unscaled fused QKV weight (dq is returned w.r.t. the unscaled q), a bf16 projection weight, and the
+    flipped / in-out-swapped folded pos-conv weight (transposed conv = the forward kernel on it)."""
+
+    def __init__(self, m: "Wav2Vec2Backbone"):
+        cfg = m.cfg
+        dev = m.masked_spec_embed.device
+        bt = lambda t: t.detach().to(device=dev, dtype=BF16).t().contiguous()
+        fp = m.feature_projection
+        self.fp_w = fp.projection.weight.detach().to(device=dev, dtype=BF16).contiguous()
+        self.fp_wt = bt(fp.projection.weight)
+        pc = m.encoder.pos_conv_embed.conv
+        g = pc.parametrizations.weight.original0.detach().to(device=dev, dtype=F32)
+        v = pc.parametrizations.weight.original1.detach().to(device=dev, dtype=F32)
+        H, gw, taps = v.shape
+        groups = H // gw
+        vt = v.view(groups, gw, gw, taps).permute(0, 2, 1, 3).flip(-1).reshape(H, gw, taps).contiguous()
+        self.pos_wt = ops.posconv_fold(g.flip(-1).contiguous(), vt, cpad=64)
+        self.pos_g, self.pos_v = g.contiguous(), v.contiguous()
+        self.layers = []
+        for l in m.encoder.layers:
+            a = l.attention
+            qkv = torch.cat([a.q_proj.weight.detach(), a.k_proj.weight.detach(), a.v_proj.weight.detach()], dim=0)
+            self.layers.append(SimpleNamespace(
+                qkv_wt=bt(qkv), o_wt=bt(a.out_proj.weight), ff1_wt=bt(l.feed_forward.intermediate_dense.weight),
+                ff2_wt=bt(l.feed_forward.output_dense.weight)))
+
+
 _IN_MEMORY = {}
 
 
@@ -166,6 +199,8 @@ class Wav2Vec2Backbone(nn.Module):
         self.encoder = _Encoder(cfg)
         self._plan: Optional[_Plan] = None
         self._plan_key = None
+        self._train_plan: Optional[_TrainPlan] = None
+        self._train_plan_key = None
         self._feature_encoder_frozen = False
 
     # ---- reference-facing helpers --------------------------------------------------------------------------
@@ -223,6 +258,185 @@ class Wav2Vec2Backbone(nn.Module):
                 self._plan = _Plan(self)
             self._plan_key = key
         return self._plan
+
+    def train_plan(self) -> _TrainPlan:
+        self.plan()
+        if self._train_plan is None or self._train_plan_key != self._plan_key:
+            with torch.no_grad():
+                self._train_plan = _TrainPlan(self)
+            self._train_plan_key = self._plan_key
+        return self._train_plan
+
+    def fused_grad_groups(self, prefix: str = ""):
+        """Parameter-name groups that must be adjacent in the flat gradient buffer (fused QKV wgrad)."""
+        groups = []
+        for i in range(len(self.encoder.layers)):
+            base = f"{prefix}encoder.layers.{i}.attention."
+            groups.append([base + "q_proj.weight", base + "k_proj.weight", base + "v_proj.weight"])
+            groups.append([base + "q_proj.bias", base + "k_proj.bias", base + "v_proj.bias"])
+        return groups
+
+    def check_trainable(self):
+        cfg = self.cfg
+        if cfg.apply_spec_augment or cfg.layerdrop > 0 or any(
+                getattr(cfg, k, 0.0) > 0 for k in ("hidden_dropout", "attention_dropout", "activation_dropout",
+                                                    "feat_proj_dropout")):
+            raise NotImplementedError("aptai_b200: the stochastic regularisers (SpecAugment / LayerDrop / dropout) of "
+                                      "the training path are not built; set them to 0 or call .eval()")
+        if any(p.requires_grad for p in self.feature_extractor.parameters()):
+            raise NotImplementedError("aptai_b200: the backward of the conv feature encoder is not built; call "
+                                      "freeze_feature_encoder() (the reference's default, models/aptai.py:39-40)")
+
+    # ---- training: forward that keeps activations, and the backward --------------------------------------------
+    @torch.no_grad()
+    def encode_train(self, wav: torch.Tensor, frame_lens: torch.Tensor):
+        """Same arithmetic as `encode` (the feature projection runs on bf16 instead of fp16 operands so that its
+        wgrad shares the bf16 kernel).  Returns (last_hidden fp32 [B,T,H], saved activations)."""
+        self.check_trainable()
+        cfg, P, TP = self.cfg, self.plan(), self.train_plan()
+        B, L = wav.shape
+        norm = 1 if cfg.feat_extract_norm == "layer" else 2
+        y = ops.conv0(wav, P.conv0_w, P.conv_b[0], P.conv_ln_w[0], P.conv_ln_b[0], norm, out_dtype=F16)
+        for i in range(1, len(cfg.conv_kernel)):
+            y = _conv_layer(y, P, i, cfg)
+        T = y.shape[1]
+        M, H = B * T, cfg.hidden_size
+        eps, heads = cfg.layer_norm_eps, cfg.num_attention_heads
+        taps, groups = cfg.num_conv_pos_embeddings, cfg.num_conv_pos_embedding_groups
+        sv = SimpleNamespace(B=B, T=T, frame_lens=frame_lens, layers=[])
+        sv.y32 = y.view(M, -1).float()
+        _, sv.xn = ops.layernorm(sv.y32, P.fp_ln_w, P.fp_ln_b, eps)
+        h0, _ = ops.linear(sv.xn, TP.fp_w, P.fp_b, want_f32=True, want_bf16=False, seg_rows=T,
+                           seg_valid_rows=frame_lens)
+        sv.hp = ops.cast_pad(h0.view(B, T, H), taps // 2)
+        sv.pos_pre = torch.empty((M, H), dtype=BF16, device=wav.device)
+        h = torch.empty_like(h0)
+        ops.posconv(sv.hp, P.pos_w, P.pos_b, h0, T, H, groups, taps, h, out_pre=sv.pos_pre)
+        F_ = cfg.intermediate_size
+
+        def attn(x):
+            _, qkv = ops.linear(x, lw.qkv_w, lw.qkv_b)
+            lse = torch.empty((B, heads, T), dtype=F32, device=wav.device)
+            ctx = ops.attention(qkv, frame_lens, B, T, heads, lse=lse)
+            return qkv, ctx, lse
+
+        def ffn1(x):
+            u = torch.empty((M, F_), dtype=BF16, device=wav.device)
+            _, g = ops.linear(x, lw.ff1_w, lw.ff1_b, act=1, out_pre=u)
+            return u, g
+
+        if cfg.do_stable_layer_norm:
+            for lw in P.layers:
+                _, x1 = ops.layernorm(h, lw.ln1_w, lw.ln1_b, eps)
+                qkv, ctx, lse = attn(x1)
+                hm, _ = ops.linear(ctx, lw.o_w, lw.o_b, residual=h, want_f32=True, want_bf16=False)
+                _, x2 = ops.layernorm(hm, lw.ln2_w, lw.ln2_b, eps)
+                u, g = ffn1(x2)
+                hn, _ = ops.linear(g, lw.ff2_w, lw.ff2_b, residual=hm, want_f32=True, want_bf16=False)
+                sv.layers.append(SimpleNamespace(h_in=h, x1=x1, qkv=qkv, ctx=ctx, lse=lse, h_mid=hm, x2=x2, u=u, g=g))
+                h = hn
+            sv.h_final_in = h
+            last, _ = ops.layernorm(h, P.enc_ln_w, P.enc_ln_b, eps, want_f32=True, want_bf16=False)
+        else:
+            sv.h_enc_in = h
+            h, x = ops.layernorm(h, P.enc_ln_w, P.enc_ln_b, eps, want_f32=True, want_bf16=True)
+            for lw in P.layers:
+                qkv, ctx, lse = attn(x)
+                t, _ = ops.linear(ctx, lw.o_w, lw.o_b, residual=h, want_f32=True, want_bf16=False)
+                h1, x1 = ops.layernorm(t, lw.ln1_w, lw.ln1_b, eps, want_f32=True, want_bf16=True)
+                u, g = ffn1(x1)
+                t2, _ = ops.linear(g, lw.ff2_w, lw.ff2_b, residual=h1, want_f32=True, want_bf16=False)
+                h2, x2 = ops.layernorm(t2, lw.ln2_w, lw.ln2_b, eps, want_f32=True, want_bf16=True)
+                sv.layers.append(SimpleNamespace(x_in=x, qkv=qkv, ctx=ctx, lse=lse, t=t, x1=x1, u=u, g=g, t2=t2))
+                h, x = h2, x2
+            last = h
+        return last.view(B, T, H), sv
+
+    @torch.no_grad()
+    def backward(self, sv, d_last: torch.Tensor, gb, prefix: str = "") -> None:
+        """Accumulate d loss / d parameter for every trainable parameter of the backbone into the GradBuffer `gb`
+        (whose parameter names carry `prefix`), given d loss / d last_hidden (fp32 [B*T, H])."""
+        cfg, P, TP = self.cfg, self.plan(), self.train_plan()
+        B, T, flen = sv.B, sv.T, sv.frame_lens
+        M, H = B * T, cfg.hidden_size
+        eps, heads = cfg.layer_norm_eps, cfg.num_attention_heads
+        taps, groups = cfg.num_conv_pos_embeddings, cfg.num_conv_pos_embedding_groups
+        q_scale = float(cfg.head_dim) ** -0.5
+        G = lambda name: gb.view(prefix + name)
+        d_last = d_last.reshape(M, H).contiguous()
+
+        def lin_grads(dy_b, x_b, name):
+            ops.wgrad(dy_b, x_b, G(name + ".weight"))
+            ops.colsum(dy_b, G(name + ".bias"))
+
+        def attn_block(i, s, lt, dctx_src_b, x_in_b):
+            """out-proj dgrad -> attention backward -> fused QKV wgrad; returns dqkv."""
+            base = f"encoder.layers.{i}.attention."
+            lin_grads(dctx_src_b, s.ctx, base + "out_proj")
+            _, dctx = ops.linear(dctx_src_b, lt.o_wt, None)
+            dqkv = ops.attention_bwd(s.qkv, s.ctx, dctx, s.lse, flen, B, T, heads, q_scale)
+            names_w = [prefix + base + n + ".weight" for n in ("q_proj", "k_proj", "v_proj")]
+            names_b = [prefix + base + n + ".bias" for n in ("q_proj", "k_proj", "v_proj")]
+            ops.wgrad(dqkv, x_in_b, gb.fused(names_w, (3 * H, H)))
+            ops.colsum(dqkv, gb.fused(names_b, (3 * H,)))
+            return dqkv
+
+        nl = len(sv.layers)
+        if cfg.do_stable_layer_norm:
+            dh32, dhb = ops.layernorm_bwd(d_last, sv.h_final_in, P.enc_ln_w, eps, dgamma=G("encoder.layer_norm.weight"),
+                                          dbeta=G("encoder.layer_norm.bias"), want_bf16=True)
+            for i in range(nl - 1, -1, -1):
+                s, lw, lt = sv.layers[i], P.layers[i], TP.layers[i]
+                base = f"encoder.layers.{i}."
+                lin_grads(dhb, s.g, base + "feed_forward.output_dense")
+                _, du = ops.linear(dhb, lt.ff2_wt, None, act=2, aux=s.u)
+                lin_grads(du, s.x2, base + "feed_forward.intermediate_dense")
+                dx2, _ = ops.linear(du, lt.ff1_wt, None, want_f32=True, want_bf16=False)
+                dhm32, dhmb = ops.layernorm_bwd(dx2, s.h_mid, lw.ln2_w, eps, dres=dh32,
+                                                dgamma=G(base + "final_layer_norm.weight"),
+                                                dbeta=G(base + "final_layer_norm.bias"), want_bf16=True)
+                dqkv = attn_block(i, s, lt, dhmb, s.x1)
+                dx1, _ = ops.linear(dqkv, lt.qkv_wt, None, want_f32=True, want_bf16=False)
+                dh32, dhb = ops.layernorm_bwd(dx1, s.h_in, lw.ln1_w, eps, dres=dhm32,
+                                              dgamma=G(base + "layer_norm.weight"), dbeta=G(base + "layer_norm.bias"),
+                                              want_bf16=True)
+                sv.layers[i] = None
+        else:
+            dh32 = d_last
+            for i in range(nl - 1, -1, -1):
+                s, lw, lt = sv.layers[i], P.layers[i], TP.layers[i]
+                base = f"encoder.layers.{i}."
+                dt2, dt2b = ops.layernorm_bwd(dh32, s.t2, lw.ln2_w, eps, dgamma=G(base + "final_layer_norm.weight"),
+                                              dbeta=G(base + "final_layer_norm.bias"), want_bf16=True)
+                lin_grads(dt2b, s.g, base + "feed_forward.output_dense")
+                _, du = ops.linear(dt2b, lt.ff2_wt, None, act=2, aux=s.u)
+                lin_grads(du, s.x1, base + "feed_forward.intermediate_dense")
+                dh1, _ = ops.linear(du, lt.ff1_wt, None, residual=dt2, want_f32=True, want_bf16=False)
+                dt, dtb = ops.layernorm_bwd(dh1, s.t, lw.ln1_w, eps, dgamma=G(base + "layer_norm.weight"),
+                                            dbeta=G(base + "layer_norm.bias"), want_bf16=True)
+                dqkv = attn_block(i, s, lt, dtb, s.x_in)
+                dh32, _ = ops.linear(dqkv, lt.qkv_wt, None, residual=dt, want_f32=True, want_bf16=False)
+                sv.layers[i] = None
+            dh32, _ = ops.layernorm_bwd(dh32, sv.h_enc_in, P.enc_ln_w, eps, dgamma=G("encoder.layer_norm.weight"),
+                                        dbeta=G("encoder.layer_norm.bias"))
+        # positional conv: h1 = h0 + gelu(conv(h0) + b)
+        pc = "encoder.pos_conv_embed.conv."
+        dpre32 = ops.gelu_bwd(dh32, sv.pos_pre)
+        dpre_b = ops.scale_cast_bf16(dpre32)
+        ops.colsum(dpre_b, G(pc + "bias"))
+        dwf = ops.posconv_wgrad(dpre_b.view(B, T, H), sv.hp, groups, taps)
+        ops.posconv_weightnorm_bwd(dwf, TP.pos_g, TP.pos_v, G(pc + "parametrizations.weight.original0"),
+                                   G(pc + "parametrizations.weight.original1"))
+        dpre_pad = ops.cast_pad(dpre32.view(B, T, H), taps // 2)
+        dh0 = torch.empty_like(dh32)
+        ops.posconv(dpre_pad, TP.pos_wt, None, dh32, T, H, groups, taps, dh0, act=0, row_shift=1,
+                    seg_valid_rows=flen)       # padded frames were zeroed after the projection (HF:678,754)
+        # feature projection + its LayerNorm (the conv encoder below is frozen)
+        dh0b = ops.scale_cast_bf16(dh0)
+        lin_grads(dh0b, sv.xn, "feature_projection.projection")
+        dxn, _ = ops.linear(dh0b, TP.fp_wt, None, want_f32=True, want_bf16=False)
+        ops.layernorm_bwd(dxn, sv.y32, P.fp_ln_w, eps, dgamma=G("feature_projection.layer_norm.weight"),
+                          dbeta=G("feature_projection.layer_norm.bias"))
 
     # ---- the hot path ----------------------------------------------------------------------------------------
     @torch.no_grad()

@@ -1,0 +1,374 @@
+// Backward of the padding-masked self-attention (HF:500-549 via SDPA; autograd of softmax(q k^T + mask) v) on
+// tcgen05 / TMEM / TMA for sm_100a.
+//
+// Work item = (utterance b, head h, block of 128 keys).  K_j and V_j stay in shared memory, dK_j and dV_j accumulate
+// in TMEM over all 128-query tiles i; per tile:
+//
+//   MMA:      S^T  = K_j Q_i^T           dP^T = V_j dO_i^T                       (TMEM, 2 x 128 columns)
+//   compute:  P^T  = exp2(S^T log2e - lse_i)      dS^T = P^T * (dP^T - D_i)      (bf16 -> shared memory, SW128 K-major)
+//   MMA:      dV_j += P^T dO_i     dK_j += dS^T Q_i     dQ_ij = dS K_j           (TMEM 64 columns each)
+//   compute:  dQ_ij -> fp32 red.global.add into dq32[B*T][H]   (partial sums over the key blocks)
+//
+// Every transposition is a descriptor bit: Q_i / dO_i are K-major B operands for S^T / dP^T and MN-major B operands
+// for dK / dV; the dS^T tile written once to shared memory is the K-major A operand of dK and the MN-major A operand
+// of dQ (two 64-query blocks, LBO = 16 KB).  lse (log2 domain) comes from the forward kernel, D = rowsum(dO * O)
+// from aptai_attention_bwd_dot.  q was pre-scaled by head_dim^-0.5 in the forward, so S needs no scale here; the
+// caller folds the scale into dq when it converts dq32 to bf16.
+#include "common.h"
+#include "ptx.cuh"
+
+#include <math.h>
+
+namespace aptai {
+
+constexpr int AB_T = 128;                 // queries per tile = keys per block
+constexpr int AB_D = 64;
+constexpr int AB_TILE = AB_T * AB_D * 2;  // 16 KB
+constexpr int AB_PT = AB_T * AB_T * 2;    // 32 KB (two [128][64] sub-tiles)
+constexpr int AB_DATA = 2 * AB_TILE /*K,V*/ + 4 * AB_TILE /*Q,dO x2*/ + 2 * AB_PT /*P^T, dS^T*/;   // 160 KB
+constexpr int AB_STATS = 2 * 2 * AB_T * 4;    // [buf][lse | D][128]
+constexpr int AB_SMEM = AB_DATA + AB_STATS + 256;
+constexpr int AB_THREADS = 352;               // warps 0..7 compute, 8 TMA, 9 MMA, 10 TMEM alloc
+constexpr int AB_W_TMA = 8, AB_W_MMA = 9, AB_W_ALLOC = 10;
+constexpr uint32_t TB_ST = 0, TB_DPT = 128, TB_DK = 256, TB_DV = 320, TB_DQ = 384;
+constexpr float AB_LOG2E = 1.4426950408889634f;
+
+struct AttnBwdParams {
+  const int* key_len;
+  const float* lse;     // [B][heads][T] log2-domain log-sum-exp of the forward
+  const float* dvec;    // [B][heads][T] rowsum(dO * O)
+  float* dq32;          // [B*T][H] fp32, zeroed by the caller
+  __nv_bfloat16* dqkv;  // [B*T][3H]: the k and v blocks are written here
+  int B, T, heads, H, n_t, items;
+};
+
+__device__ __forceinline__ uint64_t ab_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+__device__ __forceinline__ float ab_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                     const AttnBwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + AB_TILE;
+  uint8_t* sQ = smem + 2 * AB_TILE;          // [2]
+  uint8_t* sDO = smem + 4 * AB_TILE;         // [2]
+  uint8_t* sPT = smem + 6 * AB_TILE;
+  uint8_t* sDST = sPT + AB_PT;
+  float* stats = reinterpret_cast<float*>(smem + AB_DATA);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AB_DATA + AB_STATS);
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("aptai attention_bwd: dynamic shared memory base is not 1024-byte aligned\n");
+    __trap();
+  }
+  uint64_t* kv_full = bars + 0;
+  uint64_t* kv_empty = bars + 1;
+  uint64_t* qdo_full = bars + 2;    // [2]
+  uint64_t* qdo_empty = bars + 4;   // [2]
+  uint64_t* s_full = bars + 6;
+  uint64_t* pds_full = bars + 7;
+  uint64_t* dq_full = bars + 8;
+  uint64_t* dkv_full = bars + 9;
+  uint64_t* dkv_empty = bars + 10;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == AB_W_TMA && lane == 0) {
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmDO);
+  }
+  if (warp == AB_W_MMA && lane == 0) {
+    mbar_init(kv_full, 1);
+    mbar_init(kv_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qdo_full[i], 1);
+      mbar_init(&qdo_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(pds_full, 8);
+    mbar_init(dq_full, 1);
+    mbar_init(dkv_full, 1);
+    mbar_init(dkv_empty, 8);
+    fence_mbar_init();
+  }
+  if (warp == AB_W_ALLOC) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == AB_W_TMA) {
+    if (lane == 0) {
+      uint32_t g = 0, it = 0;
+      for (int w = blockIdx.x; w < p.items; w += gridDim.x) {
+        const int j = w % p.n_t;
+        const int bh = w / p.n_t;
+        const int h = bh % p.heads, b = bh / p.heads;
+        const int klen = max(1, min(__ldg(p.key_len + b), p.T));
+        if (j * AB_T >= klen) continue;
+        const int row0 = b * p.T;
+        mbar_wait_backoff(kv_empty, (it & 1) ^ 1, 64);
+        mbar_expect_tx(kv_full, 2 * AB_TILE);
+        tma_load_2d(&tmQKV, kv_full, sK, p.H + h * AB_D, row0 + j * AB_T);
+        tma_load_2d(&tmQKV, kv_full, sV, 2 * p.H + h * AB_D, row0 + j * AB_T);
+        for (int i = 0; i < p.n_t; ++i, ++g) {
+          const uint32_t buf = g & 1;
+          mbar_wait_backoff(&qdo_empty[buf], ((g >> 1) & 1) ^ 1, 64);
+          mbar_expect_tx(&qdo_full[buf], 2 * AB_TILE);
+          tma_load_2d(&tmQKV, &qdo_full[buf], sQ + buf * AB_TILE, h * AB_D, row0 + i * AB_T);
+          tma_load_2d(&tmDO, &qdo_full[buf], sDO + buf * AB_TILE, h * AB_D, row0 + i * AB_T);
+        }
+        ++it;
+      }
+    }
+  } else if (warp == AB_W_MMA) {
+    if (lane == 0) {
+      constexpr uint32_t ID_BASE = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(AB_T >> 4) << 24);
+      constexpr uint32_t ID_S = ID_BASE | (static_cast<uint32_t>(AB_T >> 3) << 17);                  // N=128, K-major
+      constexpr uint32_t ID_KV = ID_BASE | (1u << 16) | (static_cast<uint32_t>(AB_D >> 3) << 17);    // N=64, B MN-major
+      constexpr uint32_t ID_Q = ID_KV | (1u << 15);                                                   // A MN-major too
+      uint32_t g = 0, it = 0;
+      for (int w = blockIdx.x; w < p.items; w += gridDim.x) {
+        const int j = w % p.n_t;
+        const int b = (w / p.n_t) / p.heads;
+        const int klen = max(1, min(__ldg(p.key_len + b), p.T));
+        if (j * AB_T >= klen) continue;
+        mbar_wait(kv_full, it & 1);
+        const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
+        const uint32_t pt_addr = smem_u32(sPT), dst_addr = smem_u32(sDST);
+        for (int i = 0; i < p.n_t; ++i, ++g) {
+          const uint32_t buf = g & 1;
+          const uint32_t q_addr = smem_u32(sQ + buf * AB_TILE), do_addr = smem_u32(sDO + buf * AB_TILE);
+          mbar_wait(&qdo_full[buf], (g >> 1) & 1);
+          tc_fence_after();
+          // phase 1: S^T = K Q^T, dP^T = V dO^T   (the compute warps finished reading tile g-1's S^T/dP^T before
+          // pds_full(g-1), which this thread waited for below)
+#pragma unroll
+          for (int k = 0; k < AB_D / 16; ++k)
+            umma_bf16(tmem_base + TB_ST, umma_desc_sw128(k_addr + k * 32), umma_desc_sw128(q_addr + k * 32), ID_S,
+                      k != 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < AB_D / 16; ++k)
+            umma_bf16(tmem_base + TB_DPT, umma_desc_sw128(v_addr + k * 32), umma_desc_sw128(do_addr + k * 32), ID_S,
+                      k != 0 ? 1u : 0u);
+          umma_commit(s_full);
+          // phase 2 needs P^T / dS^T in shared memory
+          mbar_wait(pds_full, g & 1);
+          if (i == 0) mbar_wait(dkv_empty, (it & 1) ^ 1);      // previous item's dK/dV have been read out
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < AB_T / 16; ++k) {
+            const uint32_t a_off = (k >> 2) * (AB_PT / 2) + (k & 3) * 32;
+            umma_bf16(tmem_base + TB_DV, umma_desc_sw128(pt_addr + a_off), ab_desc_mn(do_addr + k * 2048, 1024), ID_KV,
+                      (i | k) != 0 ? 1u : 0u);
+          }
+#pragma unroll
+          for (int k = 0; k < AB_T / 16; ++k) {
+            const uint32_t a_off = (k >> 2) * (AB_PT / 2) + (k & 3) * 32;
+            umma_bf16(tmem_base + TB_DK, umma_desc_sw128(dst_addr + a_off), ab_desc_mn(q_addr + k * 2048, 1024), ID_KV,
+                      (i | k) != 0 ? 1u : 0u);
+          }
+#pragma unroll
+          for (int k = 0; k < AB_T / 16; ++k)
+            umma_bf16(tmem_base + TB_DQ, ab_desc_mn(dst_addr + k * 2048, AB_PT / 2), ab_desc_mn(k_addr + k * 2048, 1024),
+                      ID_Q, k != 0 ? 1u : 0u);
+          umma_commit(&qdo_empty[buf]);
+          umma_commit(dq_full);
+          if (i == p.n_t - 1) {
+            umma_commit(dkv_full);
+            umma_commit(kv_empty);
+          }
+        }
+        ++it;
+      }
+    }
+  } else if (warp < 8) {
+    const int q4 = warp & 3, hf = warp >> 2;
+    const int row = q4 * 32 + lane;                       // TMEM lane: key row (phase 1) / query row (dQ)
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
+    const int ctid = threadIdx.x;                         // 0..255
+    uint32_t g = 0, it = 0;
+    for (int w = blockIdx.x; w < p.items; w += gridDim.x) {
+      const int j = w % p.n_t;
+      const int bh = w / p.n_t;
+      const int h = bh % p.heads, b = bh / p.heads;
+      const int klen = max(1, min(__ldg(p.key_len + b), p.T));
+      const long long row0 = static_cast<long long>(b) * p.T;
+      const int key = j * AB_T + row;
+      __nv_bfloat16* dk_out = p.dqkv + (row0 + key) * 3 * p.H + p.H + h * AB_D + hf * 32;
+      __nv_bfloat16* dv_out = dk_out + p.H;
+      if (j * AB_T >= klen) {
+        // no valid key in this block: its dK / dV rows are zero
+        if (key < p.T) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) {
+            *reinterpret_cast<uint4*>(dk_out + i) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(dv_out + i) = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+        continue;
+      }
+      const bool key_ok = key < klen;
+      const float* lse_bh = p.lse + static_cast<long long>(bh) * p.T;
+      const float* d_bh = p.dvec + static_cast<long long>(bh) * p.T;
+      for (int i = 0; i < p.n_t; ++i, ++g) {
+        float* st = stats + (g & 1) * 2 * AB_T;
+        {
+          const int qi = i * AB_T + (ctid & 127);
+          if (ctid < 128) st[ctid] = qi < p.T ? __ldg(lse_bh + qi) : INFINITY;
+          else st[ctid] = qi < p.T ? __ldg(d_bh + qi) : 0.f;
+        }
+        named_bar_sync(1, 256);
+        mbar_wait(s_full, g & 1);
+        tc_fence_after();
+        uint8_t* pt_row = sPT + hf * (AB_PT / 2) + row * 128;
+        uint8_t* ds_row = sDST + hf * (AB_PT / 2) + row * 128;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t s[32], dp[32];
+          tmem_ld32(t_lane + TB_ST + hf * 64 + c * 32, s);
+          tmem_ld32(t_lane + TB_DPT + hf * 64 + c * 32, dp);
+          tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float pv[8], dv[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int qc = hf * 64 + c * 32 + u * 8 + e;
+              float pe = ab_ex2(fmaf(__uint_as_float(s[u * 8 + e]), AB_LOG2E, -st[qc]));
+              if (!key_ok) pe = 0.f;
+              pv[e] = pe;
+              dv[e] = pe * (__uint_as_float(dp[u * 8 + e]) - st[AB_T + qc]);
+            }
+            const int unit = (c * 4 + u) ^ (row & 7);
+            *reinterpret_cast<uint4*>(pt_row + (unit << 4)) =
+                make_uint4(pack_bf16(pv[0], pv[1]), pack_bf16(pv[2], pv[3]), pack_bf16(pv[4], pv[5]),
+                           pack_bf16(pv[6], pv[7]));
+            *reinterpret_cast<uint4*>(ds_row + (unit << 4)) =
+                make_uint4(pack_bf16(dv[0], dv[1]), pack_bf16(dv[2], dv[3]), pack_bf16(dv[4], dv[5]),
+                           pack_bf16(dv[6], dv[7]));
+          }
+        }
+        tc_fence_before();
+        fence_async_proxy();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pds_full);
+        // dQ partial of this (query tile, key block)
+        mbar_wait(dq_full, g & 1);
+        tc_fence_after();
+        {
+          uint32_t r[32];
+          tmem_ld32(t_lane + TB_DQ + hf * 32, r);
+          tmem_ld_wait();
+          const int qi = i * AB_T + row;
+          if (qi < p.T) {
+            float* dst = p.dq32 + (row0 + qi) * p.H + h * AB_D + hf * 32;
+#pragma unroll
+            for (int e = 0; e < 32; e += 4)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + e), "f"(__uint_as_float(r[e])),
+                           "f"(__uint_as_float(r[e + 1])), "f"(__uint_as_float(r[e + 2])),
+                           "f"(__uint_as_float(r[e + 3]))
+                           : "memory");
+          }
+        }
+        tc_fence_before();
+      }
+      // dK_j, dV_j
+      mbar_wait(dkv_full, it & 1);
+      tc_fence_after();
+      {
+        uint32_t rk[32], rv[32];
+        tmem_ld32(t_lane + TB_DK + hf * 32, rk);
+        tmem_ld32(t_lane + TB_DV + hf * 32, rv);
+        tmem_ld_wait();
+        if (key < p.T) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 8) {
+            *reinterpret_cast<uint4*>(dk_out + e) =
+                make_uint4(pack_bf16(__uint_as_float(rk[e]), __uint_as_float(rk[e + 1])),
+                           pack_bf16(__uint_as_float(rk[e + 2]), __uint_as_float(rk[e + 3])),
+                           pack_bf16(__uint_as_float(rk[e + 4]), __uint_as_float(rk[e + 5])),
+                           pack_bf16(__uint_as_float(rk[e + 6]), __uint_as_float(rk[e + 7])));
+            *reinterpret_cast<uint4*>(dv_out + e) =
+                make_uint4(pack_bf16(__uint_as_float(rv[e]), __uint_as_float(rv[e + 1])),
+                           pack_bf16(__uint_as_float(rv[e + 2]), __uint_as_float(rv[e + 3])),
+                           pack_bf16(__uint_as_float(rv[e + 4]), __uint_as_float(rv[e + 5])),
+                           pack_bf16(__uint_as_float(rv[e + 6]), __uint_as_float(rv[e + 7])));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dkv_empty);
+      ++it;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == AB_W_ALLOC) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace aptai
+
+using namespace aptai;
+
+extern "C" int aptai_attention_bwd(const void* qkv, const void* d_ctx, const float* lse, const float* dvec,
+                                   const int32_t* key_len, int B, int T, int heads, float* dq32, void* dqkv,
+                                   void* stream) {
+  if (int rc = check_arch()) return rc;
+  APTAI_REQUIRE(qkv && d_ctx && lse && dvec && key_len && dq32 && dqkv, "attention_bwd: null pointer");
+  APTAI_REQUIRE(B >= 1 && T >= 1 && heads >= 1, "attention_bwd: bad shape");
+  APTAI_REQUIRE(((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(d_ctx) |
+                  reinterpret_cast<uintptr_t>(dq32) | reinterpret_cast<uintptr_t>(dqkv)) & 15) == 0,
+                "attention_bwd: buffers must be 16-byte aligned");
+  const int H = heads * AB_D;
+  CUtensorMap tmq, tmdo;
+  uint32_t box[2] = {AB_D, AB_T};
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(3) * H, static_cast<uint64_t>(B) * T};
+    uint64_t strides[1] = {static_cast<uint64_t>(3) * H * 2};
+    if (int rc = encode_tmap_bf16(&tmq, qkv, 2, dims, strides, box, 1)) return rc;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(H), static_cast<uint64_t>(B) * T};
+    uint64_t strides[1] = {static_cast<uint64_t>(H) * 2};
+    if (int rc = encode_tmap_bf16(&tmdo, d_ctx, 2, dims, strides, box, 1)) return rc;
+  }
+  AttnBwdParams p;
+  p.key_len = key_len;
+  p.lse = lse;
+  p.dvec = dvec;
+  p.dq32 = dq32;
+  p.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
+  p.B = B; p.T = T; p.heads = heads; p.H = H;
+  p.n_t = (T + AB_T - 1) / AB_T;
+  p.items = B * heads * p.n_t;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+    if (e != cudaSuccess) {
+      set_error("attention_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    attr_set = true;
+  }
+  const int grid = p.items < num_sms() ? p.items : num_sms();
+  attention_bwd_kernel<<<grid, AB_THREADS, AB_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tmq, tmdo, p);
+  return after_launch("attention_bwd");
+}

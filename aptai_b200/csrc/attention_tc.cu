@@ -39,6 +39,7 @@ constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units
 struct AttnParams {
   const int* key_len;
   __nv_bfloat16* ctx;
+  float* lse;   // optional [B][heads][T]: log2-domain log-sum-exp per query row (kept for the backward pass)
   int B, T, heads, H, n_qt, items;
 };
 
@@ -303,10 +304,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       named_bar_sync(pair_bar, 64);                 // the max-exchange slots of this parity are free again
       xl[half * AQ + row] = l;
       named_bar_sync(pair_bar, 64);
-      const float inv = 1.f / (l + xl[(half ^ 1) * AQ + row]);
+      const float l_tot = l + xl[(half ^ 1) * AQ + row];
+      const float inv = 1.f / l_tot;
       mbar_wait(o_full, it & 1);
       tc_fence_after();
       const int qrow = qt * AQ + row;
+      if (p.lse != nullptr && half == 0 && qrow < p.T)
+        p.lse[(static_cast<long long>(b) * p.heads + h) * p.T + qrow] = m_used + log2f(l_tot);
       __nv_bfloat16* out = p.ctx + (static_cast<long long>(b) * p.T + qrow) * p.H + h * AD + half * 32;
       {
         uint32_t r[32];
@@ -339,8 +343,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
 using namespace aptai;
 
-extern "C" int aptai_attention_fwd(const void* qkv, void* ctx, const int32_t* key_len, int B, int T, int heads,
-                                   void* stream) {
+static int attention_fwd_impl(const void* qkv, void* ctx, float* lse, const int32_t* key_len, int B, int T, int heads,
+                              void* stream) {
   if (int rc = check_arch()) return rc;
   APTAI_REQUIRE(qkv && ctx && key_len, "attention: null pointer");
   APTAI_REQUIRE(B >= 1 && T >= 1 && heads >= 1, "attention: bad shape");
@@ -359,6 +363,7 @@ extern "C" int aptai_attention_fwd(const void* qkv, void* ctx, const int32_t* ke
   AttnParams p;
   p.key_len = key_len;
   p.ctx = reinterpret_cast<__nv_bfloat16*>(ctx);
+  p.lse = lse;
   p.B = B; p.T = T; p.heads = heads; p.H = H;
   p.n_qt = (T + AQ - 1) / AQ;
   p.items = B * heads * p.n_qt;
@@ -384,4 +389,15 @@ extern "C" int aptai_attention_fwd(const void* qkv, void* ctx, const int32_t* ke
   const int grid = p.items < ctas_per_sm * num_sms() ? p.items : ctas_per_sm * num_sms();
   attention_tc_kernel<<<grid, ATC_THREADS, ATC_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tmq, tmkv, p);
   return after_launch("attention_tc");
+}
+
+extern "C" int aptai_attention_fwd(const void* qkv, void* ctx, const int32_t* key_len, int B, int T, int heads,
+                                   void* stream) {
+  return attention_fwd_impl(qkv, ctx, nullptr, key_len, B, T, heads, stream);
+}
+
+extern "C" int aptai_attention_fwd_lse(const void* qkv, void* ctx, float* lse, const int32_t* key_len, int B, int T,
+                                       int heads, void* stream) {
+  APTAI_REQUIRE(lse != nullptr, "attention_fwd_lse: null lse");
+  return attention_fwd_impl(qkv, ctx, lse, key_len, B, T, heads, stream);
 }

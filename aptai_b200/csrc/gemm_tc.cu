@@ -41,6 +41,8 @@ struct GemmParams {
   int act;
   float ln_eps;
   int fp16;   // operands and the 16-bit output are IEEE fp16 instead of bf16
+  const __nv_bfloat16* aux;   // act == 2: pre-activation u saved by the forward pass; out = acc * gelu'(u)
+  __nv_bfloat16* out_pre;     // optional second 16-bit output: the value BEFORE the activation (training forward)
 };
 
 template <int BN, bool CTA2>
@@ -316,10 +318,6 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
             v[i + 3] = fmaf((v[i + 3] - mean) * rstd, g4.w, e4.w);
           }
         }
-        if (p.act == 1) {
-#pragma unroll
-          for (int i = 0; i < CH; i += 2) gelu_erf2(v[i], v[i + 1]);
-        }
         if constexpr (!LN && CH == 32) {
           // ---- coalesced path: transpose through a warp-private, XOR-swizzled 4 KB buffer so that every global
           // access covers whole 128-byte (fp32) / 64-byte (bf16) row segments instead of 32 different rows
@@ -328,6 +326,47 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
           const int r_first = r - lane;                                  // first row of this warp's 32-row group
           const long long off0 = out_off - static_cast<long long>(lane) * p.ldo + n0;
           const int lrow = lane >> 3, lunit = lane & 7;
+          // 16-bit store of v[] (thread = row) as whole 64-byte row segments
+          auto store16 = [&](__nv_bfloat16* dst) {
+            uint4* sb = reinterpret_cast<uint4*>(stg);                    // 128-byte row pitch, units 0..3 used
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              sb[lane * 8 + (u ^ (lane & 7))] =
+                  make_uint4(pack_h16(v[8 * u], v[8 * u + 1], p.fp16), pack_h16(v[8 * u + 2], v[8 * u + 3], p.fp16),
+                             pack_h16(v[8 * u + 4], v[8 * u + 5], p.fp16), pack_h16(v[8 * u + 6], v[8 * u + 7], p.fp16));
+            __syncwarp();
+            const int bu = lane & 3;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rr = i * 8 + ((lane >> 2) & 1) * 4 + (lane >> 3);
+              const uint4 x = sb[rr * 8 + (bu ^ (rr & 7))];
+              if (r_first + rr < p.rows_per_seg)
+                *reinterpret_cast<uint4*>(dst + off0 + rr * p.ldo + bu * 8) = x;
+            }
+            __syncwarp();
+          };
+          if (p.out_pre) store16(p.out_pre);
+          if (p.act == 1) {
+#pragma unroll
+            for (int i = 0; i < CH; i += 2) gelu_erf2(v[i], v[i + 1]);
+          } else if (p.act == 2) {
+            // dgrad through the GELU: v *= gelu'(u), u = the forward's pre-activation (bf16, row-per-thread loads:
+            // every 64-byte segment is used completely)
+            if (valid_row) {
+              const uint4* up = reinterpret_cast<const uint4*>(p.aux + out_off + n0);
+#pragma unroll
+              for (int i = 0; i < CH; i += 8) {
+                const uint4 u4 = __ldg(up + i / 8);
+                const uint32_t uw[4] = {u4.x, u4.y, u4.z, u4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 uf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uw[j]));
+                  v[i + 2 * j] *= gelu_erf_grad(uf.x);
+                  v[i + 2 * j + 1] *= gelu_erf_grad(uf.y);
+                }
+              }
+            }
+          }
           if (p.residual) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -364,25 +403,12 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
             }
             __syncwarp();
           }
-          if (p.out_bf16) {
-            uint4* sb = reinterpret_cast<uint4*>(stg);                    // 128-byte row pitch, units 0..3 used
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              sb[lane * 8 + (u ^ (lane & 7))] =
-                  make_uint4(pack_h16(v[8 * u], v[8 * u + 1], p.fp16), pack_h16(v[8 * u + 2], v[8 * u + 3], p.fp16),
-                             pack_h16(v[8 * u + 4], v[8 * u + 5], p.fp16), pack_h16(v[8 * u + 6], v[8 * u + 7], p.fp16));
-            __syncwarp();
-            const int bu = lane & 3;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int rr = i * 8 + ((lane >> 2) & 1) * 4 + (lane >> 3);
-              const uint4 x = sb[rr * 8 + (bu ^ (rr & 7))];
-              if (r_first + rr < p.rows_per_seg)
-                *reinterpret_cast<uint4*>(p.out_bf16 + off0 + rr * p.ldo + bu * 8) = x;
-            }
-            __syncwarp();
-          }
+          if (p.out_bf16) store16(p.out_bf16);
         } else {
+        if (p.act == 1) {
+#pragma unroll
+          for (int i = 0; i < CH; i += 2) gelu_erf2(v[i], v[i + 1]);
+        }
         if (valid_row) {
           if (p.residual) {
             const float4* rp = reinterpret_cast<const float4*>(p.residual + out_off + n0);
@@ -518,6 +544,9 @@ extern "C" int aptai_gemm_bf16(const aptai_gemm_args* g, void* stream) {
                 g->N);
   APTAI_REQUIRE(g->N % bn == 0, "gemm: N=%d not a multiple of block_n=%d", g->N, bn);
   APTAI_REQUIRE(bn != 512 || g->ln, "gemm: block_n 512 is the fused-LayerNorm tile");
+  APTAI_REQUIRE(g->act != 2 || (g->aux != nullptr && !g->ln && bn % 64 == 0),
+                "gemm: act=2 (GELU dgrad) needs aux and a 64-multiple tile without LayerNorm");
+  APTAI_REQUIRE(g->out_pre == nullptr || (!g->ln && bn % 64 == 0), "gemm: out_pre needs a 64-multiple tile, no LN");
   const long long K = static_cast<long long>(g->taps) * g->kb_per_tap * BLOCK_K;
 
   // CTA-pair (cta_group::2) tiles halve the B traffic per SM; they need a wide N tile and enough 256-row tiles
@@ -568,6 +597,8 @@ extern "C" int aptai_gemm_bf16(const aptai_gemm_args* g, void* stream) {
   p.act = g->act;
   p.ln_eps = g->ln_eps;
   p.fp16 = g->half_fmt ? 1 : 0;
+  p.aux = reinterpret_cast<const __nv_bfloat16*>(g->aux);
+  p.out_pre = reinterpret_cast<__nv_bfloat16*>(g->out_pre);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (g->ln) return pair ? launch_gemm_2cta<512, true>(ta, tb, p, st) : launch_gemm<512, true>(ta, tb, p, st);
   switch (bn) {

@@ -273,6 +273,20 @@ __device__ __forceinline__ float gelu_erf(float x) {
   const float h = 0.5f * t * p * e;           // 0.5 * erfc(|x| / sqrt(2))
   return x * (x > 0.f ? 1.0f - h : h);
 }
+// d/dx [x * Phi(x)] = Phi(x) + x * phi(x); same erfc approximation as gelu_erf (backward of HF ACT2FN['gelu'])
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));   // exp(-x^2/2)
+  float p = fmaf(t, 1.061405429f, -1.453152027f);
+  p = fmaf(t, p, 1.421413741f);
+  p = fmaf(t, p, -0.284496736f);
+  p = fmaf(t, p, 0.254829592f);
+  const float h = 0.5f * t * p * e;           // 0.5 * erfc(|x| / sqrt(2)) = 1 - Phi(|x|)
+  const float cdf = x > 0.f ? 1.0f - h : h;
+  return fmaf(x * e, 0.3989422804014327f, cdf);
+}
 // Two GELUs at once on the packed fp32x2 FMA path of sm_100 (FFMA2 / FMUL2): the polynomial part costs half the
 // FMA-pipe issue slots of the scalar version; the MUFU ops stay scalar.  Same formula, same accuracy.
 __device__ __forceinline__ uint64_t f32x2_pack(float a, float b) {

@@ -24,6 +24,7 @@ class GemmArgs(C.Structure):
         ("bias", c_void_p), ("gamma", c_void_p), ("beta", c_void_p), ("residual", c_void_p),
         ("out_f32", c_void_p), ("out_bf16", c_void_p), ("ldo", c_i64), ("out_seg_stride", c_i64),
         ("seg_valid_rows", c_void_p), ("mask_seg_rows", C.c_int32), ("act", C.c_int32), ("ln", C.c_int32), ("ln_eps", c_float), ("cta_pair", C.c_int32), ("half_fmt", C.c_int32),
+        ("aux", c_void_p), ("out_pre", c_void_p),
     ]
 
 
@@ -61,6 +62,27 @@ PROTOTYPES = {
                                       c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "aptai_ctc_greedy": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int,
                                  c_void_p]),
+    # ---- training step
+    "aptai_attention_fwd_lse": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "aptai_attention_bwd_dot": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "aptai_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                                    c_void_p, c_void_p]),
+    "aptai_scale_cast_bf16": (c_int, [c_void_p, c_i64, c_int, c_float, c_void_p, c_i64, c_void_p]),
+    "aptai_gemm_wgrad_bf16": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_i64, c_int, c_int, c_float, c_void_p, c_i64,
+                                      c_void_p]),
+    "aptai_posconv_wgrad_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "aptai_posconv_weightnorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p,
+                                             c_void_p, c_void_p, c_void_p]),
+    "aptai_gelu_bwd": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),
+    "aptai_colsum": (c_int, [c_void_p, c_int, c_i64, c_int, c_i64, c_float, c_void_p, c_void_p]),
+    "aptai_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_void_p, c_void_p]),
+    "aptai_heads_bwd": (c_int, [c_void_p, c_i64, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                                c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "aptai_masked_mse_ce_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p]),
+    "aptai_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                c_float, c_float, c_float, c_float, c_float, c_int, c_float, c_void_p]),
 }
 
 _lib = None

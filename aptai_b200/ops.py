@@ -71,7 +71,8 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
            residual: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None,
            out_bf16: Optional[torch.Tensor] = None, want_f32: bool = False, want_bf16: bool = True,
            seg_rows: Optional[int] = None, seg_valid_rows: Optional[torch.Tensor] = None,
-           block_n: int = 0, cta_pair: int = 0):
+           block_n: int = 0, cta_pair: int = 0, aux: Optional[torch.Tensor] = None,
+           out_pre: Optional[torch.Tensor] = None):
     """out = epilogue(a @ w.T): a bf16 [M,K], w bf16 [N,K] (nn.Linear layout), bias fp32 [N].
 
     seg_rows / seg_valid_rows: rows are grouped in segments of seg_rows; rows >= seg_valid_rows[s] are written as 0.
@@ -103,6 +104,14 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     g.residual = _ptr(_req(residual, F32, "residual")) if residual is not None else None
     g.out_f32 = _ptr(out_f32); g.out_bf16 = _ptr(out_bf16); g.ldo = N
     g.act = act; g.ln = 0; g.ln_eps = 0.0; g.cta_pair = cta_pair; g.half_fmt = fmt
+    if act == 2:
+        if aux is None or aux.shape != (M, N):
+            raise ValueError("linear: act=2 (GELU dgrad) needs aux of the output's shape")
+        g.aux = _req(aux, BF16, "aux").data_ptr()
+    if out_pre is not None:
+        if out_pre.shape != (M, N) or out_pre.dtype != a.dtype:
+            raise ValueError("linear: out_pre must match the 16-bit output")
+        g.out_pre = out_pre.data_ptr()
     gemm_raw(g)
     return out_f32, out_bf16
 
@@ -150,8 +159,9 @@ def conv_igemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], k
     return out
 
 
-def posconv(x_pad: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, residual: torch.Tensor, T: int, H: int,
-            groups: int, taps: int, out_f32: torch.Tensor) -> torch.Tensor:
+def posconv(x_pad: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], residual: Optional[torch.Tensor],
+            T: int, H: int, groups: int, taps: int, out_f32: torch.Tensor, *, out_pre: Optional[torch.Tensor] = None,
+            act: int = 1, row_shift: int = 0, seg_valid_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Grouped positional conv + bias + GELU + residual.  x_pad bf16 [B, T+2*halo, H] (halo = taps//2, zeroed),
     w bf16 [H, taps*64] (per output channel: tap-major, 64-padded group input channels)."""
     _req(x_pad, BF16, "x_pad"); _req(w, BF16, "w")
@@ -159,12 +169,19 @@ def posconv(x_pad: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, residual: 
     assert H2 == H and Tp == T + taps
     gw = H // groups
     g = GemmArgs()
-    g.a = x_pad.data_ptr(); g.a_row_stride = H; g.a_seg_stride = Tp * H; g.a_rows = Tp; g.a_cols = H
+    # row_shift: first physical row of every segment (the transposed conv of the backward pass reads the halo-padded
+    # gradient one row later than the forward reads its input)
+    g.a = x_pad.data_ptr() + row_shift * H * 2; g.a_row_stride = H; g.a_seg_stride = Tp * H
+    g.a_rows = Tp - row_shift; g.a_cols = H
     g.P = 1; g.taps = taps; g.kb_per_tap = 1; g.a_col_per_nblk = gw
     g.w = w.data_ptr(); g.N = H; g.block_n = gw; g.segs = B; g.rows_per_seg = T
-    g.bias = bias.data_ptr(); g.gamma = None; g.beta = None; g.residual = residual.data_ptr()
+    g.bias = _ptr(bias); g.gamma = None; g.beta = None; g.residual = _ptr(residual)
     g.out_f32 = out_f32.data_ptr(); g.out_bf16 = None; g.ldo = H; g.out_seg_stride = T
-    g.seg_valid_rows = None; g.mask_seg_rows = 0; g.act = 1; g.ln = 0; g.ln_eps = 0.0; g.cta_pair = 0; g.half_fmt = 0
+    g.seg_valid_rows = None; g.mask_seg_rows = 0; g.act = act; g.ln = 0; g.ln_eps = 0.0; g.cta_pair = 0; g.half_fmt = 0
+    if seg_valid_rows is not None:
+        g.seg_valid_rows = _req(seg_valid_rows, I32, "seg_valid_rows").data_ptr(); g.mask_seg_rows = T
+    if out_pre is not None:
+        g.out_pre = _req(out_pre, BF16, "out_pre").data_ptr()
     gemm_raw(g)
     return out_f32
 
@@ -220,7 +237,8 @@ def posconv_fold(g: torch.Tensor, v: torch.Tensor, cpad: int = 64) -> torch.Tens
 
 
 def attention(qkv: torch.Tensor, key_len: Optional[torch.Tensor], B: int, T: int, heads: int,
-              out: Optional[torch.Tensor] = None, legacy_mma: bool = False) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, legacy_mma: bool = False, lse: Optional[torch.Tensor] = None
+              ) -> torch.Tensor:
     _req(qkv, BF16, "qkv")
     H = heads * 64
     assert qkv.numel() == B * T * 3 * H
@@ -229,6 +247,12 @@ def attention(qkv: torch.Tensor, key_len: Optional[torch.Tensor], B: int, T: int
     if key_len is None:
         key_len = torch.full((B,), T, dtype=I32, device=qkv.device)
     _req(key_len, I32, "key_len")
+    if lse is not None:
+        _req(lse, F32, "lse")
+        assert lse.numel() == B * heads * T
+        check(_lib.load().aptai_attention_fwd_lse(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), key_len.data_ptr(),
+                                                  B, T, heads, _stream()), "attention_fwd_lse")
+        return out
     fn = _lib.load().aptai_attention_fwd_mma if legacy_mma else _lib.load().aptai_attention_fwd
     check(fn(qkv.data_ptr(), out.data_ptr(), key_len.data_ptr(), B, T, heads, _stream()), "attention_fwd")
     return out
@@ -292,7 +316,7 @@ def cross_attention(frame, phn_ids, emb, pe, wq, bq, wk, bk, ln_w, ln_b, eps: fl
     return att_out, energy, att
 
 
-def masked_mse_ce(tv_pred, tv_tgt, logits, phn_tgt) -> torch.Tensor:
+def masked_mse_ce(tv_pred, tv_tgt, logits, phn_tgt, return_ws: bool = False):
     _req(tv_pred, F32, "tv_pred"); _req(tv_tgt, F32, "tv_tgt"); _req(logits, F32, "logits"); _req(phn_tgt, I64, "phn")
     rows = phn_tgt.numel()
     ntv = tv_pred.shape[-1]
@@ -301,6 +325,8 @@ def masked_mse_ce(tv_pred, tv_tgt, logits, phn_tgt) -> torch.Tensor:
     out = torch.empty((3,), dtype=F32, device=logits.device)
     check(_lib.load().aptai_masked_mse_ce(tv_pred.data_ptr(), tv_tgt.data_ptr(), logits.data_ptr(), phn_tgt.data_ptr(),
                                           rows, ntv, V, ws.data_ptr(), out.data_ptr(), _stream()), "masked_mse_ce")
+    if return_ws:
+        return out, ws
     return out
 
 
@@ -367,3 +393,127 @@ def ctc_greedy(logits: torch.Tensor, input_len: Optional[torch.Tensor], blank: i
     check(_lib.load().aptai_ctc_greedy(logits.data_ptr(), B, T, V, _ptr(input_len), blank, tokens.data_ptr(),
                                        frames.data_ptr(), ntok.data_ptr(), maxtok, _stream()), "ctc_greedy")
     return tokens, frames, ntok
+
+
+# ============================================================================================ training step
+def attention_bwd(qkv: torch.Tensor, ctx: torch.Tensor, d_ctx: torch.Tensor, lse: torch.Tensor,
+                  key_len: torch.Tensor, B: int, T: int, heads: int, q_scale: float) -> torch.Tensor:
+    """Backward of `attention`: returns dqkv bf16 [B*T, 3H]; the q block is the gradient w.r.t. the UNSCALED q
+    (q_scale = head_dim^-0.5 folded in), matching the unscaled q_proj weight used for dgrad/wgrad."""
+    _req(qkv, BF16, "qkv"); _req(ctx, BF16, "ctx"); _req(d_ctx, BF16, "d_ctx"); _req(lse, F32, "lse")
+    _req(key_len, I32, "key_len")
+    H = heads * 64
+    M = B * T
+    dev = qkv.device
+    L = _lib.load()
+    dvec = torch.empty((B, heads, T), dtype=F32, device=dev)
+    check(L.aptai_attention_bwd_dot(d_ctx.data_ptr(), ctx.data_ptr(), B, T, heads, dvec.data_ptr(), _stream()),
+          "attention_bwd_dot")
+    dq32 = torch.zeros((M, H), dtype=F32, device=dev)
+    dqkv = torch.empty((M, 3 * H), dtype=BF16, device=dev)
+    check(L.aptai_attention_bwd(qkv.data_ptr(), d_ctx.data_ptr(), lse.data_ptr(), dvec.data_ptr(), key_len.data_ptr(),
+                                B, T, heads, dq32.data_ptr(), dqkv.data_ptr(), _stream()), "attention_bwd")
+    check(L.aptai_scale_cast_bf16(dq32.data_ptr(), M, H, float(q_scale), dqkv.data_ptr(), 3 * H, _stream()),
+          "scale_cast_bf16")
+    return dqkv
+
+
+def wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, scale: float = 1.0) -> None:
+    """dw[N,K] (fp32, contiguous rows) += scale * dy[M,N]^T @ x[M,K]   (bf16 operands)."""
+    _req(dy, BF16, "dy"); _req(x, BF16, "x"); _req(dw, F32, "dw")
+    M, N = dy.shape
+    M2, K = x.shape
+    if M != M2 or tuple(dw.shape) != (N, K):
+        raise ValueError(f"wgrad: shapes dy {tuple(dy.shape)}, x {tuple(x.shape)}, dw {tuple(dw.shape)}")
+    check(_lib.load().aptai_gemm_wgrad_bf16(dy.data_ptr(), N, x.data_ptr(), K, M, N, K, float(scale), dw.data_ptr(), K,
+                                            _stream()), "gemm_wgrad_bf16")
+
+
+def posconv_wgrad(dy: torch.Tensor, x_pad: torch.Tensor, groups: int, taps: int) -> torch.Tensor:
+    """Folded weight gradient [H, taps*64] fp32 of the grouped positional conv."""
+    _req(dy, BF16, "dy"); _req(x_pad, BF16, "x_pad")
+    B, T, H = dy.shape
+    assert x_pad.shape == (B, T + taps, H)
+    dwf = torch.zeros((H, taps * 64), dtype=F32, device=dy.device)
+    check(_lib.load().aptai_posconv_wgrad_bf16(dy.data_ptr(), x_pad.data_ptr(), B, T, H, groups, taps, dwf.data_ptr(),
+                                               _stream()), "posconv_wgrad_bf16")
+    return dwf
+
+
+def posconv_weightnorm_bwd(dwf: torch.Tensor, g: torch.Tensor, v: torch.Tensor, dg: torch.Tensor, dv: torch.Tensor):
+    _req(dwf, F32, "dwf"); _req(g, F32, "g"); _req(v, F32, "v"); _req(dg, F32, "dg"); _req(dv, F32, "dv")
+    H, cin, taps = v.shape
+    ws = torch.empty((2 * taps,), dtype=F64, device=v.device)
+    check(_lib.load().aptai_posconv_weightnorm_bwd(dwf.data_ptr(), g.data_ptr(), v.data_ptr(), H, cin, taps, 64,
+                                                   dg.data_ptr(), dv.data_ptr(), ws.data_ptr(), _stream()),
+          "posconv_weightnorm_bwd")
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor, scale: float = 1.0) -> None:
+    """out[N] (fp32) += scale * x.sum(0); x bf16 or fp32 [M,N]."""
+    if x.dtype not in (BF16, F32) or not x.is_cuda or not x.is_contiguous():
+        raise TypeError("colsum: x must be a contiguous CUDA bf16/fp32 tensor")
+    _req(out, F32, "out")
+    M, N = x.shape
+    assert out.numel() == N
+    check(_lib.load().aptai_colsum(x.data_ptr(), int(x.dtype == BF16), M, N, N, float(scale), out.data_ptr(),
+                                   _stream()), "colsum")
+
+
+def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, eps: float, *, dres=None, dgamma=None,
+                  dbeta=None, want_f32=True, want_bf16=False, out_f32=None):
+    """Returns (dx fp32 | None, dx bf16 | None); dx = dres + LN'(dy).  dgamma/dbeta accumulate."""
+    _req(dy, F32, "dy"); _req(x, F32, "x"); _req(gamma, F32, "gamma")
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    if want_f32 and out_f32 is None:
+        out_f32 = torch.empty(x.shape, dtype=F32, device=x.device)
+    ob = torch.empty(x.shape, dtype=BF16, device=x.device) if want_bf16 else None
+    check(_lib.load().aptai_layernorm_bwd(dy.data_ptr(), x.data_ptr(), rows, cols, gamma.data_ptr(), eps, _ptr(dres),
+                                          _ptr(out_f32), _ptr(ob), _ptr(dgamma), _ptr(dbeta), _stream()),
+          "layernorm_bwd")
+    return out_f32, ob
+
+
+def heads_bwd(h, da, wa, act_a, dwa, dba, db, wb, act_b, dwb, dbb, want_dh: bool = True):
+    _req(h, F32, "h")
+    rows, H = h.shape
+    na = 0 if da is None else da.shape[-1]
+    nb = 0 if db is None else db.shape[-1]
+    dh = torch.empty_like(h) if want_dh else None
+    check(_lib.load().aptai_heads_bwd(h.data_ptr(), rows, H, _ptr(da), na, _ptr(wa), act_a, _ptr(dwa), _ptr(dba),
+                                      _ptr(db), nb, _ptr(wb), act_b, _ptr(dwb), _ptr(dbb), _ptr(dh), _stream()),
+          "heads_bwd")
+    return dh
+
+
+def masked_mse_ce_bwd(tv_pred, tv_tgt, logits, phn_tgt, ws, grad_scale: Optional[torch.Tensor] = None):
+    rows = phn_tgt.numel()
+    ntv = tv_pred.shape[-1]
+    V = logits.shape[-1]
+    d_tv = torch.empty_like(tv_pred)
+    d_logits = torch.empty_like(logits)
+    check(_lib.load().aptai_masked_mse_ce_bwd(tv_pred.data_ptr(), tv_tgt.data_ptr(), logits.data_ptr(),
+                                              phn_tgt.data_ptr(), rows, ntv, V, ws.data_ptr(), _ptr(grad_scale),
+                                              d_tv.data_ptr(), d_logits.data_ptr(), _stream()), "masked_mse_ce_bwd")
+    return d_tv, d_logits
+
+
+def scale_cast_bf16(x: torch.Tensor, scale: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _req(x, F32, "x")
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    if out is None:
+        out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    check(_lib.load().aptai_scale_cast_bf16(x.data_ptr(), rows, cols, float(scale), out.data_ptr(), cols, _stream()),
+          "scale_cast_bf16")
+    return out
+
+
+def gelu_bwd(dy: torch.Tensor, pre: torch.Tensor) -> torch.Tensor:
+    """dy fp32 * gelu'(pre bf16) -> fp32."""
+    _req(dy, F32, "dy"); _req(pre, BF16, "pre")
+    assert dy.numel() == pre.numel()
+    out = torch.empty_like(dy)
+    check(_lib.load().aptai_gelu_bwd(dy.data_ptr(), pre.data_ptr(), dy.numel(), out.data_ptr(), _stream()), "gelu_bwd")
+    return out

@@ -21,6 +21,7 @@ import torch.nn as nn
 from . import ops
 from .backbone import Wav2Vec2Backbone
 from .config import W2V2Config
+from .train import GradBuffer, attach_backward
 
 
 def idx_phonemes(vocab, seq):
@@ -63,11 +64,42 @@ class Wav2Vec2_PR(nn.Module):
                                  f(self.pr_head.bias), ops.ACT_NONE, want_argmax=False)
         return logits.view(B, T, -1)
 
+    def grad_buffer(self) -> GradBuffer:
+        gb = getattr(self, "_grad_buffer", None)
+        if gb is None:
+            gb = GradBuffer(list(self.named_parameters()), self.wav2vec2.fused_grad_groups("wav2vec2."))
+            object.__setattr__(self, "_grad_buffer", gb)
+            return gb
+        dropped = False
+        for n, p in gb.params:
+            if not gb.owns(p):
+                dropped = True
+                p.grad = gb.flat[gb.offsets[n]: gb.offsets[n] + p.numel()].view(p.shape)
+        if dropped:
+            gb.zero()
+        return gb
+
     def forward(self, input_values, input_lengths, phoneme_labels, want_grad=False):
         """models/w2v2_pr.py:40-88.  `want_grad=True` additionally returns d loss / d phoneme_logits from the
-        fused kernel (key 'grad_logits'), the implementation-independent quantity of SURVEY.md §3.3."""
+        fused kernel (key 'grad_logits'), the implementation-independent quantity of SURVEY.md §3.3.
+        In training mode with autograd enabled, `loss.backward()` runs the hand-written backward kernels
+        (train/train_phoneme_recognizer.py: loss.backward(); optimizer.step())."""
         cfg = self.wav2vec2.cfg
-        out, h, logits = self._logits(input_values, input_lengths)
+        train = self.training and torch.is_grad_enabled()
+        sv = None
+        if train:
+            if self.dropout.p > 0:
+                raise NotImplementedError("aptai_b200: final_dropout is not built in the training path; set it to 0")
+            dev0 = next(self.wav2vec2.parameters()).device
+            wav = input_values.to(device=dev0, dtype=torch.float32).contiguous()
+            lens = input_lengths.reshape(-1).to(device=dev0, dtype=torch.int64)
+            flen = self.wav2vec2._get_feat_extract_output_lengths(lens).to(torch.int32).contiguous()
+            gb = self.grad_buffer()
+            h, sv = self.wav2vec2.encode_train(wav, flen)
+            logits = self._head(h)
+            want_grad = True
+        else:
+            out, h, logits = self._logits(input_values, input_lengths)
         dev = h.device
         B, T, V = logits.shape
         state_lens = self.wav2vec2._get_feat_extract_output_lengths(input_lengths.reshape(-1).to(dev))
@@ -85,6 +117,17 @@ class Wav2Vec2_PR(nn.Module):
         res = {"loss": r["loss_sum"][0], "phoneme_logits": logits, "log_probs": r["log_probs"], "hidden_states": h}
         if want_grad:
             res["grad_logits"] = r["grad"]
+        if train:
+            hm = h.reshape(B * T, -1)
+            w = self.pr_head.weight.detach().float().contiguous()
+
+            def run_backward(grad_out):
+                d_lg = (r["grad"] * grad_out.detach().to(device=dev, dtype=torch.float32)).view(B * T, V).contiguous()
+                dh = ops.heads_bwd(hm, None, None, 0, None, None, d_lg, w, ops.ACT_NONE, gb.view("pr_head.weight"),
+                                   gb.view("pr_head.bias"))
+                self.wav2vec2.backward(sv, dh, gb, prefix="wav2vec2.")
+
+            res["loss"] = attach_backward(res["loss"], self.pr_head.weight, run_backward)
         return res
 
     def _decode(self, phoneme_logits, frame_lens=None):

@@ -74,11 +74,14 @@ typedef struct aptai_gemm_args {
   int64_t out_seg_stride; /* output rows between segments */
   const int32_t* seg_valid_rows; /* [out_rows / mask_seg_rows] or NULL: valid rows per masking segment */
   int32_t mask_seg_rows;  /* output row o = s*out_seg_stride + r is zeroed when o % mask_seg_rows >= seg_valid_rows[o / mask_seg_rows] */
-  int32_t act;            /* 0 none, 1 erf-GELU */
+  int32_t act;            /* 0 none, 1 erf-GELU, 2 multiply by gelu'(aux) (backward) */
   int32_t ln;             /* 0/1: LayerNorm over the full row (requires N == 512) */
   float ln_eps;
   int32_t cta_pair;       /* 0 auto, 1 single-CTA tiles (128 x BN), 2 CTA-pair tiles (256 x BN, cta_group::2) */
   int32_t half_fmt;       /* 0: A, W and out_bf16 are bf16; 1: they are IEEE fp16 (conv stack / feature projection) */
+  const void* aux;        /* act=2 only: bf16, same row mapping/ldo as the outputs: out = acc * gelu'(aux)  (dgrad of
+                             HF:566-573 through the activation) */
+  void* out_pre;          /* optional 16-bit copy of the value before the activation (kept for the backward pass) */
 } aptai_gemm_args;
 
 int aptai_gemm_bf16(const aptai_gemm_args* args, void* stream);
@@ -179,6 +182,71 @@ int aptai_ctc_viterbi_f32(const float* log_probs, const int32_t* targets, const 
 /* greedy CTC collapse on device (argmax -> merge repeats -> drop blank); models/w2v2_pr.py:143-159 next-row. */
 int aptai_ctc_greedy(const float* logits, int B, int T, int V, const int32_t* input_len, int blank,
                      int32_t* tokens, int32_t* token_frames, int32_t* ntokens, int maxtok, void* stream);
+
+
+/* ================================================================== training step (backward + optimizer) =====
+ * The reference trains with torch autograd (train/train_aptai.py:431-443: zero_grad / loss.backward() /
+ * optimizer.step()); these entry points are the kernels that autograd would otherwise dispatch for the hot path.
+ * dgrad of a Linear is aptai_gemm_bf16 on the transposed weight (act=2 multiplies by gelu'(aux)).
+ */
+
+/* attention forward that also stores the log2-domain log-sum-exp per query row, lse fp32 [B][heads][T] */
+int aptai_attention_fwd_lse(const void* qkv, void* ctx, float* lse, const int32_t* key_len, int B, int T, int heads,
+                            void* stream);
+/* D[b][h][t] = sum_d d_ctx * ctx  (bf16 [B*T][heads*64] inputs), the softmax-backward row term */
+int aptai_attention_bwd_dot(const void* d_ctx, const void* ctx, int B, int T, int heads, float* D, void* stream);
+/* attention backward (autograd of HF:500-549).  qkv bf16 [B*T][3H] (q pre-scaled), d_ctx bf16 [B*T][H];
+ * writes dk, dv into the k / v blocks of dqkv (bf16 [B*T][3H]) and ACCUMULATES dq (w.r.t. the pre-scaled q) into
+ * dq32 fp32 [B*T][H], which the caller zeroes before and converts with aptai_scale_cast_bf16 afterwards. */
+int aptai_attention_bwd(const void* qkv, const void* d_ctx, const float* lse, const float* dvec,
+                        const int32_t* key_len, int B, int T, int heads, float* dq32, void* dqkv, void* stream);
+/* out_bf16[r][0..cols) (row pitch ldo) = scale * x[r][0..cols) */
+int aptai_scale_cast_bf16(const float* x, int64_t rows, int cols, float scale, void* out_bf16, int64_t ldo,
+                          void* stream);
+
+/* weight gradient of a Linear: dw[n][k] += scale * sum_m dy[m][n] * x[m][k]  (dy bf16 [M][N] pitch dy_ld,
+ * x bf16 [M][K] pitch x_ld, dw fp32 pitch dw_ld; split over frames, fp32 reductions) */
+int aptai_gemm_wgrad_bf16(const void* dy, int64_t dy_ld, const void* x, int64_t x_ld, int64_t M, int N, int K,
+                          float scale, float* dw, int64_t dw_ld, void* stream);
+/* weight gradient of the grouped positional conv (HF:329-368) in the folded layout of aptai_posconv_fold:
+ * dw_folded[o][tap*64 + c] += sum_{b,t} dy[b][t][o] * x_pad[b][t + tap][g(o)*gw + c]
+ * dy bf16 [B][T][H], x_pad bf16 [B][T + taps][H] (the forward's aptai_cast_pad_bf16 output). */
+int aptai_posconv_wgrad_bf16(const void* dy, const void* x_pad, int B, int T, int H, int groups, int taps,
+                             float* dw_folded, void* stream);
+/* weight-norm backward (torch parametrizations.weight_norm, dim=2): dg[taps] += , dv[H][cin][taps] += from the
+ * folded dW.  ws: 2*taps doubles. */
+int aptai_posconv_weightnorm_bwd(const float* dw_folded, const float* g, const float* v, int H, int cin, int taps,
+                                 int cpad, float* dg, float* dv, void* ws, void* stream);
+
+/* out[i] = dy[i] * gelu'(pre[i]) (backward of the positional conv's GELU, HF:366); pre bf16, n % 4 == 0 */
+int aptai_gelu_bwd(const float* dy, const void* pre_bf16, int64_t n, float* out, void* stream);
+
+/* out[n] += scale * sum_m x[m][n]  (bias gradients); x bf16 (x_bf16=1) or fp32, row pitch ld */
+int aptai_colsum(const void* x, int x_bf16, int64_t M, int N, int64_t ld, float scale, float* out, void* stream);
+
+/* LayerNorm backward (HF:431,600-602,639,645,692,792).  x = the forward's input (fp32), dy fp32; dx = dres + LN'(dy)
+ * written fp32 and/or bf16; dgamma/dbeta (optional, both or none) are accumulated (+=). */
+int aptai_layernorm_bwd(const float* dy, const float* x, int64_t rows, int cols, const float* gamma, float eps,
+                        const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, void* stream);
+
+/* backward of aptai_heads: dh = act_a'(h) (dA Wa) + act_b'(h) (dB Wb) (optional), dW += dOut^T act(h), db += colsum */
+int aptai_heads_bwd(const float* h, int64_t rows, int H, const float* da, int na, const float* wa, int act_a,
+                    float* dwa, float* dba, const float* db, int nb, const float* wb, int act_b, float* dwb,
+                    float* dbb, float* dh, void* stream);
+
+/* backward of aptai_masked_mse_ce w.r.t. tv_pred and logits; accum_ws is the forward's workspace (counts),
+ * grad_scale (optional device scalar) multiplies both. */
+int aptai_masked_mse_ce_bwd(const float* tv_pred, const float* tv_tgt, const float* logits, const int64_t* phn_tgt,
+                            int64_t rows, int ntv, int V, const float* accum_ws, const float* grad_scale, float* d_tv,
+                            float* d_logits, void* stream);
+
+/* torch.optim.Adam step (train/train_aptai.py:350-356) over a table of parameter tensors in one launch.
+ * params_dev: device array of fp32 pointers; offsets/numel: element offset of each tensor in the flat
+ * grad / exp_avg / exp_avg_sq buffers and its size; chunks_dev: {int32 tensor, int32 pad, int64 start}[n_chunks]. */
+int aptai_adam_step(void* const* params_dev, const int64_t* offsets_dev, const int64_t* numel_dev,
+                    const void* chunks_dev, int n_chunks, int chunk_elems, const float* grad, float* exp_avg,
+                    float* exp_avg_sq, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                    float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }
