@@ -14,7 +14,7 @@ import torch.nn as nn
 from . import ops
 from .backbone import Wav2Vec2Backbone
 from .modules import LowPassFilterLayer
-from .train import GradBuffer, attach_backward
+from .train import GradBuffer, GradReducer, attach_backward, broadcast_parameters
 
 TV_NAMES = ("LA", "LP", "JA", "TTCL", "TTCD", "TMCL", "TMCD", "TBCL", "TBCD")
 
@@ -56,6 +56,17 @@ class APTAI(nn.Module):
         return tv, logits.view(B, T, -1), pred.view(B, T)
 
     # ---------------------------------------------------------------------------------------------- training
+    def enable_data_parallel(self, group=None, layers_per_bucket: int = 4, broadcast: bool = True):
+        """Data-parallel training over `torch.distributed` (one process per GPU): weights are broadcast from rank 0
+        and every backward all-reduces (averages) the flat gradient buffer, bucketed by encoder layers and
+        overlapped with the remaining backward kernels (BASELINE config 4; the reference trains single-GPU)."""
+        if broadcast:
+            broadcast_parameters(self, 0, group)
+        gb = self.grad_buffer()
+        red = GradReducer(gb, "wav2vec2.encoder.layers.", len(self.wav2vec2.encoder.layers), layers_per_bucket, group)
+        object.__setattr__(self, "_reducer", red)
+        return red
+
     def grad_buffer(self) -> GradBuffer:
         """Flat fp32 gradient buffer; (re)attaches `p.grad` views when an optimizer's zero_grad(set_to_none=True)
         dropped them (which also means: start from zero)."""
@@ -101,7 +112,10 @@ class APTAI(nn.Module):
             d_tv = ops.lowpass(d_tvlp.view(B, T, 9), taps).view(B * T, 9)   # symmetric FIR: adjoint = the filter
             dh = ops.heads_bwd(h, d_tv, wa, ops.ACT_TANH, gb.view("tv_head.2.weight"), gb.view("tv_head.2.bias"),
                                d_lg, wb, ops.ACT_LEAKY, gb.view("phn_head.2.weight"), gb.view("phn_head.2.bias"))
-            w2v.backward(sv, dh, gb, prefix="wav2vec2.")
+            red = getattr(self, "_reducer", None)
+            w2v.backward(sv, dh, gb, prefix="wav2vec2.", on_layer_done=red.layer_done if red else None)
+            if red is not None:
+                red.finish()
 
         loss = attach_backward(res[0], tvl.weight, run_backward)
         return {"loss": loss, "mse_loss": res[1], "ce_loss": res[2], "tvs_pred": tv, "phn_fc_pred": pred.view(B, T)}

@@ -353,9 +353,10 @@ class Wav2Vec2Backbone(nn.Module):
         return last.view(B, T, H), sv
 
     @torch.no_grad()
-    def backward(self, sv, d_last: torch.Tensor, gb, prefix: str = "") -> None:
+    def backward(self, sv, d_last: torch.Tensor, gb, prefix: str = "", on_layer_done=None) -> None:
         """Accumulate d loss / d parameter for every trainable parameter of the backbone into the GradBuffer `gb`
-        (whose parameter names carry `prefix`), given d loss / d last_hidden (fp32 [B*T, H])."""
+        (whose parameter names carry `prefix`), given d loss / d last_hidden (fp32 [B*T, H]).  `on_layer_done(i)`
+        is called once layer i's gradients are final (data-parallel all-reduce overlap, train.GradReducer)."""
         cfg, P, TP = self.cfg, self.plan(), self.train_plan()
         B, T, flen = sv.B, sv.T, sv.frame_lens
         M, H = B * T, cfg.hidden_size
@@ -401,6 +402,8 @@ class Wav2Vec2Backbone(nn.Module):
                                               dgamma=G(base + "layer_norm.weight"), dbeta=G(base + "layer_norm.bias"),
                                               want_bf16=True)
                 sv.layers[i] = None
+                if on_layer_done is not None:
+                    on_layer_done(i)
         else:
             dh32 = d_last
             for i in range(nl - 1, -1, -1):
@@ -417,6 +420,8 @@ class Wav2Vec2Backbone(nn.Module):
                 dqkv = attn_block(i, s, lt, dtb, s.x_in)
                 dh32, _ = ops.linear(dqkv, lt.qkv_wt, None, residual=dt, want_f32=True, want_bf16=False)
                 sv.layers[i] = None
+                if on_layer_done is not None:
+                    on_layer_done(i)
             dh32, _ = ops.layernorm_bwd(dh32, sv.h_enc_in, P.enc_ln_w, eps, dgamma=G("encoder.layer_norm.weight"),
                                         dbeta=G("encoder.layer_norm.bias"))
         # positional conv: h1 = h0 + gelu(conv(h0) + b)

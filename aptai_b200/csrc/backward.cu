@@ -389,8 +389,9 @@ __global__ void gelu_bwd_kernel(const float* __restrict__ dy, const __nv_bfloat1
 }
 
 // ---------------------------------------------------------------------------------------------- fused Adam
-// torch.optim.Adam (train/train_aptai.py:350-356) over a table of tensors in one launch.  Gradients, exp_avg and
-// exp_avg_sq live in flat fp32 buffers (element offset off[i]); parameters stay the module's own tensors.
+// torch.optim.Adam (train/train_aptai.py:350-356) over a table of tensors in one launch.  Gradients live in one flat
+// fp32 buffer (element offset goff[i]), exp_avg / exp_avg_sq in two more (offset soff[i]); parameters stay the
+// module's own tensors.
 struct AdamChunk {
   int tensor;
   int _pad;
@@ -398,18 +399,20 @@ struct AdamChunk {
 };
 
 __global__ void __launch_bounds__(256)
-adam_kernel(float* const* __restrict__ params, const long long* __restrict__ off, const long long* __restrict__ numel,
-            const AdamChunk* __restrict__ chunks, int chunk_elems, const float* __restrict__ grad,
+adam_kernel(float* const* __restrict__ params, const long long* __restrict__ goff, const long long* __restrict__ soff,
+            const long long* __restrict__ numel, const AdamChunk* __restrict__ chunks, int chunk_elems,
+            const float* __restrict__ grad,
             float* __restrict__ m, float* __restrict__ v, float lr, float beta1, float beta2, float eps,
             float weight_decay, float bc1, float bc2_sqrt, float grad_scale) {
   const AdamChunk ck = chunks[blockIdx.x];
   float* p = params[ck.tensor];
   const long long n = numel[ck.tensor];
-  const long long base = off[ck.tensor];
+  const long long gbase = goff[ck.tensor];
+  const long long base = soff[ck.tensor];
   const long long end = min(n, ck.start + chunk_elems);
   const float step = lr / bc1;
   for (long long i = ck.start + threadIdx.x; i < end; i += 256) {
-    float g = grad[base + i] * grad_scale;
+    float g = grad[gbase + i] * grad_scale;
     const float w = p[i];
     if (weight_decay != 0.f) g = fmaf(weight_decay, w, g);
     const float mi = fmaf(beta1, m[base + i] - g, g);          // beta1*m + (1-beta1)*g  (lerp form, as torch)
@@ -555,19 +558,20 @@ extern "C" int aptai_gelu_bwd(const float* dy, const void* pre_bf16, int64_t n, 
   return after_launch("gelu_bwd");
 }
 
-extern "C" int aptai_adam_step(void* const* params_dev, const int64_t* offsets_dev, const int64_t* numel_dev,
-                               const void* chunks_dev, int n_chunks, int chunk_elems, const float* grad, float* exp_avg,
+extern "C" int aptai_adam_step(void* const* params_dev, const int64_t* grad_offsets_dev,
+                               const int64_t* state_offsets_dev, const int64_t* numel_dev, const void* chunks_dev, int n_chunks, int chunk_elems, const float* grad, float* exp_avg,
                                float* exp_avg_sq, float lr, float beta1, float beta2, float eps, float weight_decay,
                                int step, float grad_scale, void* stream) {
   if (int rc = check_arch()) return rc;
-  APTAI_REQUIRE(params_dev && offsets_dev && numel_dev && chunks_dev && grad && exp_avg && exp_avg_sq,
+  APTAI_REQUIRE(params_dev && grad_offsets_dev && state_offsets_dev && numel_dev && chunks_dev && grad && exp_avg &&
+                    exp_avg_sq,
                 "adam_step: null pointer");
   APTAI_REQUIRE(n_chunks >= 1 && chunk_elems >= 256 && step >= 1, "adam_step: bad arguments");
   const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
   const double bc2 = 1.0 - pow(static_cast<double>(beta2), step);
   adam_kernel<<<n_chunks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<float* const*>(params_dev), reinterpret_cast<const long long*>(offsets_dev),
-      reinterpret_cast<const long long*>(numel_dev), reinterpret_cast<const AdamChunk*>(chunks_dev), chunk_elems, grad,
+      reinterpret_cast<float* const*>(params_dev), reinterpret_cast<const long long*>(grad_offsets_dev),
+      reinterpret_cast<const long long*>(state_offsets_dev), reinterpret_cast<const long long*>(numel_dev), reinterpret_cast<const AdamChunk*>(chunks_dev), chunk_elems, grad,
       exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, static_cast<float>(bc1),
       static_cast<float>(sqrt(bc2)), grad_scale);
   return after_launch("adam_step");

@@ -405,6 +405,13 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
           }
           if (p.out_bf16) store16(p.out_bf16);
         } else {
+        if (!LN && p.out_pre && valid_row) {      // narrow tiles (48-wide groups): row-per-thread 16-byte stores
+          uint4* op = reinterpret_cast<uint4*>(p.out_pre + out_off + n0);
+#pragma unroll
+          for (int i = 0; i < CH; i += 8)
+            op[i / 8] = make_uint4(pack_h16(v[i], v[i + 1], p.fp16), pack_h16(v[i + 2], v[i + 3], p.fp16),
+                                   pack_h16(v[i + 4], v[i + 5], p.fp16), pack_h16(v[i + 6], v[i + 7], p.fp16));
+        }
         if (p.act == 1) {
 #pragma unroll
           for (int i = 0; i < CH; i += 2) gelu_erf2(v[i], v[i + 1]);
@@ -546,7 +553,7 @@ extern "C" int aptai_gemm_bf16(const aptai_gemm_args* g, void* stream) {
   APTAI_REQUIRE(bn != 512 || g->ln, "gemm: block_n 512 is the fused-LayerNorm tile");
   APTAI_REQUIRE(g->act != 2 || (g->aux != nullptr && !g->ln && bn % 64 == 0),
                 "gemm: act=2 (GELU dgrad) needs aux and a 64-multiple tile without LayerNorm");
-  APTAI_REQUIRE(g->out_pre == nullptr || (!g->ln && bn % 64 == 0), "gemm: out_pre needs a 64-multiple tile, no LN");
+  APTAI_REQUIRE(g->out_pre == nullptr || !g->ln, "gemm: out_pre is not available with the fused LayerNorm");
   const long long K = static_cast<long long>(g->taps) * g->kb_per_tap * BLOCK_K;
 
   // CTA-pair (cta_group::2) tiles halve the B traffic per SM; they need a wide N tile and enough 256-row tiles

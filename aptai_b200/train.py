@@ -105,17 +105,79 @@ class GradBuffer:
         return works
 
 
+class GradReducer:
+    """Data-parallel gradient exchange overlapped with the backward pass (BASELINE config 4).
+
+    The flat buffer is laid out in parameter order, so the gradients of encoder layers [i, i+k) are one contiguous
+    region that is final as soon as the backward has passed layer i: `layer_done(i)` launches an asynchronous
+    all-reduce of that region (NCCL runs it on its own stream over NVLink/NVSwitch while the remaining layers'
+    kernels keep the SMs busy); `finish()` reduces what is left (heads, positional conv, projection, norms) and
+    makes the compute stream wait for all of it.  Averaging uses NCCL's AVG reduction (SUM + divide elsewhere)."""
+
+    def __init__(self, gb: GradBuffer, layer_prefix: str, n_layers: int, layers_per_bucket: int = 4, group=None):
+        self.gb, self.group, self.k = gb, group, max(1, layers_per_bucket)
+        self.n_layers = n_layers
+        spans = []
+        for i in range(n_layers):
+            pre = f"{layer_prefix}{i}."
+            offs = [(gb.offsets[n], gb.offsets[n] + p.numel()) for n, p in gb.params if n.startswith(pre)]
+            spans.append((min(o[0] for o in offs), max(o[1] for o in offs)))
+        for a, b in zip(spans[:-1], spans[1:]):
+            if a[1] > b[0]:
+                raise RuntimeError("GradReducer: encoder layers are not laid out in order in the gradient buffer")
+        self.spans = spans
+        self.works = []
+        self._done = [False] * n_layers
+
+    def _launch(self, lo: int, hi: int) -> None:
+        if hi <= lo:
+            return
+        chunk = self.gb.flat[lo:hi]
+        world = dist.get_world_size(self.group)
+        if dist.get_backend(self.group) == "nccl":
+            self.works.append(dist.all_reduce(chunk, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+        else:
+            w = dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self.works.append((w, chunk, world))
+
+    def layer_done(self, i: int) -> None:
+        """Called by the backward after layer i's gradients are complete (layers arrive in decreasing order)."""
+        self._done[i] = True
+        if i % self.k == 0:
+            hi_layer = min(self.n_layers, i + self.k) - 1
+            self._launch(self.spans[i][0], self.spans[hi_layer][1])
+
+    def finish(self) -> None:
+        self._launch(0, self.spans[0][0])
+        self._launch(self.spans[-1][1], self.gb.numel)
+        for w in self.works:
+            if isinstance(w, tuple):
+                w[0].wait()
+                w[1].div_(w[2])
+            else:
+                w.wait()
+        self.works = []
+        self._done = [False] * self.n_layers
+
+
+def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> None:
+    """Every rank starts from rank `src`'s weights (DDP's construction-time broadcast)."""
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src=src, group=group)
+
+
 class FusedAdam(torch.optim.Optimizer):
     """torch.optim.Adam (the reference's optimizer, train/train_aptai.py:350-356) as ONE kernel launch per step.
 
     Same constructor arguments and update rule (L2 `weight_decay` added to the gradient, bias correction,
-    eps outside the square root); works with torch LR schedulers (reads `param_groups[0]['lr']`).  If the
-    parameters' `.grad` are not yet views of a `GradBuffer`, one is created."""
+    eps outside the square root); works with torch LR schedulers (reads `param_groups[0]['lr']`).
+    The gradients must live in one flat buffer — the models' `grad_buffer()` (attached on their first training
+    forward) or an explicit `GradBuffer`; the optimizer binds to whatever buffer the `.grad` views point into when
+    `step()` runs, so it can be constructed before the first forward exactly like torch.optim.Adam."""
 
     CHUNK = 1 << 16
 
-    def __init__(self, params: Iterable[torch.nn.Parameter], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
-                 grad_buffer: Optional[GradBuffer] = None):
+    def __init__(self, params: Iterable[torch.nn.Parameter], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         params = [p for p in params if p.requires_grad]
         if not params:
             raise ValueError("FusedAdam: no trainable parameters")
@@ -124,46 +186,72 @@ class FusedAdam(torch.optim.Optimizer):
             raise ValueError("FusedAdam: a single parameter group is supported")
         if not params[0].is_cuda:
             raise RuntimeError("FusedAdam: parameters must be on a CUDA (sm_100) device; there is no CPU path")
-        if grad_buffer is None or not all(grad_buffer.owns(p) for p in params):
-            grad_buffer = GradBuffer([(f"p{i}", p) for i, p in enumerate(params)])
-        self.gb = grad_buffer
-        dev = params[0].device
-        self._params = params
-        flat0 = self.gb.flat.data_ptr()
-        offs = [(p.grad.data_ptr() - flat0) // 4 for p in params]
-        nums = [p.numel() for p in params]
         for p in params:
             if not p.is_contiguous() or p.dtype != F32:
                 raise TypeError("FusedAdam: parameters must be contiguous fp32")
+        dev = params[0].device
+        self._params = params
+        nums = [p.numel() for p in params]
+        soffs, off = [], 0
+        for n in nums:
+            soffs.append(off)
+            off += (n + _ALIGN - 1) // _ALIGN * _ALIGN
         self._ptrs = torch.tensor([p.data_ptr() for p in params], dtype=torch.int64, device=dev)
-        self._offs = torch.tensor(offs, dtype=torch.int64, device=dev)
+        self._soffs = torch.tensor(soffs, dtype=torch.int64, device=dev)
         self._nums = torch.tensor(nums, dtype=torch.int64, device=dev)
-        chunks = []
-        for i, n in enumerate(nums):
-            for s in range(0, n, self.CHUNK):
-                chunks.append((i, s))
-        ck = torch.zeros((len(chunks), 2), dtype=torch.int64)
-        for j, (i, s) in enumerate(chunks):
-            ck[j, 0] = i            # int32 tensor index in the low word (little endian), padding word zero
-            ck[j, 1] = s
+        chunks = [(i, s) for i, n in enumerate(nums) for s in range(0, n, self.CHUNK)]
+        ck = torch.tensor(chunks, dtype=torch.int64).reshape(-1, 2)   # {int32 tensor | pad} (little endian), int64 start
         self._chunks = ck.to(dev)
         self._n_chunks = len(chunks)
-        self.exp_avg = torch.zeros_like(self.gb.flat)
-        self.exp_avg_sq = torch.zeros_like(self.gb.flat)
+        self.exp_avg = torch.zeros((off,), dtype=F32, device=dev)
+        self.exp_avg_sq = torch.zeros((off,), dtype=F32, device=dev)
         self._step = 0
         self.grad_scale = 1.0
+        self._bound = None        # (storage ptr, first grad ptr) the offsets below were computed for
+        self._goffs = None
+        self._gbase = 0
+
+    def _bind(self) -> bool:
+        """Locate the flat gradient buffer behind the parameters' .grad views; False if no gradient exists yet."""
+        grads = [p.grad for p in self._params]
+        if all(g is None for g in grads):
+            return False
+        if any(g is None for g in grads):
+            raise RuntimeError("FusedAdam: some parameters have no gradient; the fused step needs all of them in one "
+                               "flat buffer (model.grad_buffer() / GradBuffer)")
+        st = grads[0].untyped_storage().data_ptr()
+        key = (st, tuple(g.data_ptr() for g in grads[:4]), grads[-1].data_ptr())
+        if key == self._bound:
+            return True
+        for g in grads:
+            if g.untyped_storage().data_ptr() != st or g.dtype != F32 or not g.is_contiguous():
+                raise RuntimeError("FusedAdam: gradients must be contiguous fp32 views of ONE flat buffer "
+                                   "(model.grad_buffer() / GradBuffer)")
+        self._gbase = st
+        self._goffs = torch.tensor([(g.data_ptr() - st) // 4 for g in grads], dtype=torch.int64,
+                                   device=self._params[0].device)
+        self._bound = key
+        return True
 
     def zero_grad(self, set_to_none: bool = False) -> None:     # keep the views, clear the storage
-        self.gb.zero()
+        for p in self._params:
+            if p.grad is not None:
+                if self._bind():
+                    g0 = self._params[0].grad
+                    # one memset over the whole flat buffer instead of one per tensor
+                    torch.empty(0, dtype=F32, device=g0.device).set_(g0.untyped_storage()).zero_()
+                return
 
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
+        if not self._bind():
+            return loss
         g = self.param_groups[0]
         self._step += 1
-        check(_lib.load().aptai_adam_step(self._ptrs.data_ptr(), self._offs.data_ptr(), self._nums.data_ptr(),
-                                          self._chunks.data_ptr(), self._n_chunks, self.CHUNK,
-                                          self.gb.flat.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+        check(_lib.load().aptai_adam_step(self._ptrs.data_ptr(), self._goffs.data_ptr(), self._soffs.data_ptr(),
+                                          self._nums.data_ptr(), self._chunks.data_ptr(), self._n_chunks, self.CHUNK,
+                                          self._gbase, self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
                                           float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
                                           float(g["weight_decay"]), self._step, float(self.grad_scale), _stream()),
               "adam_step")

@@ -21,7 +21,7 @@ import torch.nn as nn
 from . import ops
 from .backbone import Wav2Vec2Backbone
 from .config import W2V2Config
-from .train import GradBuffer, attach_backward
+from .train import GradBuffer, GradReducer, attach_backward, broadcast_parameters
 
 
 def idx_phonemes(vocab, seq):
@@ -63,6 +63,17 @@ class Wav2Vec2_PR(nn.Module):
         _, logits, _ = ops.heads(h.reshape(B * T, H).contiguous(), None, None, 0, f(self.pr_head.weight),
                                  f(self.pr_head.bias), ops.ACT_NONE, want_argmax=False)
         return logits.view(B, T, -1)
+
+    def enable_data_parallel(self, group=None, layers_per_bucket: int = 4, broadcast: bool = True):
+        """Data-parallel training over `torch.distributed` (one process per GPU): weights are broadcast from rank 0
+        and every backward all-reduces (averages) the flat gradient buffer, bucketed by encoder layers and
+        overlapped with the remaining backward kernels (BASELINE config 4; the reference trains single-GPU)."""
+        if broadcast:
+            broadcast_parameters(self, 0, group)
+        gb = self.grad_buffer()
+        red = GradReducer(gb, "wav2vec2.encoder.layers.", len(self.wav2vec2.encoder.layers), layers_per_bucket, group)
+        object.__setattr__(self, "_reducer", red)
+        return red
 
     def grad_buffer(self) -> GradBuffer:
         gb = getattr(self, "_grad_buffer", None)
@@ -125,7 +136,10 @@ class Wav2Vec2_PR(nn.Module):
                 d_lg = (r["grad"] * grad_out.detach().to(device=dev, dtype=torch.float32)).view(B * T, V).contiguous()
                 dh = ops.heads_bwd(hm, None, None, 0, None, None, d_lg, w, ops.ACT_NONE, gb.view("pr_head.weight"),
                                    gb.view("pr_head.bias"))
-                self.wav2vec2.backward(sv, dh, gb, prefix="wav2vec2.")
+                red = getattr(self, "_reducer", None)
+                self.wav2vec2.backward(sv, dh, gb, prefix="wav2vec2.", on_layer_done=red.layer_done if red else None)
+                if red is not None:
+                    red.finish()
 
             res["loss"] = attach_backward(res["loss"], self.pr_head.weight, run_backward)
         return res

@@ -241,10 +241,11 @@ int aptai_masked_mse_ce_bwd(const float* tv_pred, const float* tv_tgt, const flo
                             float* d_logits, void* stream);
 
 /* torch.optim.Adam step (train/train_aptai.py:350-356) over a table of parameter tensors in one launch.
- * params_dev: device array of fp32 pointers; offsets/numel: element offset of each tensor in the flat
- * grad / exp_avg / exp_avg_sq buffers and its size; chunks_dev: {int32 tensor, int32 pad, int64 start}[n_chunks]. */
-int aptai_adam_step(void* const* params_dev, const int64_t* offsets_dev, const int64_t* numel_dev,
-                    const void* chunks_dev, int n_chunks, int chunk_elems, const float* grad, float* exp_avg,
+ * params_dev: device array of fp32 pointers; grad_offsets / state_offsets / numel: element offset of each tensor in
+ * the flat grad buffer, in the flat exp_avg / exp_avg_sq buffers, and its size;
+ * chunks_dev: {int32 tensor, int32 pad, int64 start}[n_chunks]. */
+int aptai_adam_step(void* const* params_dev, const int64_t* grad_offsets_dev, const int64_t* state_offsets_dev,
+                    const int64_t* numel_dev, const void* chunks_dev, int n_chunks, int chunk_elems, const float* grad, float* exp_avg,
                     float* exp_avg_sq, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                     float grad_scale, void* stream);
 

@@ -1,0 +1,77 @@
+"""world_size-2 gloo worker: the data-parallel gradient path (GradBuffer layout, GradReducer bucketing/averaging,
+parameter broadcast) on CPU tensors — host logic only, no kernels."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from aptai_b200.train import GradBuffer, GradReducer, broadcast_parameters  # noqa: E402
+
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+torch.manual_seed(rank)
+
+
+class Layer(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.k_proj = torch.nn.Linear(8, 8)
+        self.v_proj = torch.nn.Linear(8, 8)
+        self.q_proj = torch.nn.Linear(8, 8)
+        self.ff = torch.nn.Linear(8, 16)
+
+
+class Net(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.embed = torch.nn.Parameter(torch.randn(5))
+        self.layers = torch.nn.ModuleList([Layer() for _ in range(6)])
+        self.head = torch.nn.Linear(8, 3)
+
+
+net = Net()
+broadcast_parameters(net, 0)
+ref = [p.detach().clone() for p in net.parameters()]
+gathered = [torch.zeros_like(ref[3]) for _ in range(world)]
+dist.all_gather(gathered, ref[3])
+assert all(torch.equal(g, gathered[0]) for g in gathered), "weights must be identical after the broadcast"
+
+groups = []
+for i in range(6):
+    groups.append([f"layers.{i}.{n}.weight" for n in ("q_proj", "k_proj", "v_proj")])
+    groups.append([f"layers.{i}.{n}.bias" for n in ("q_proj", "k_proj", "v_proj")])
+gb = GradBuffer(list(net.named_parameters()), groups)
+# fused q/k/v gradients are adjacent and in q, k, v order
+fw = gb.fused(groups[0], (24, 8))
+fw[:8] = 1.0; fw[8:16] = 2.0; fw[16:] = 3.0
+L0 = net.layers[0]
+assert float(L0.q_proj.weight.grad.mean()) == 1.0 and float(L0.k_proj.weight.grad.mean()) == 2.0
+assert float(L0.v_proj.weight.grad.mean()) == 3.0
+gb.zero()
+# every parameter's grad is a view of the flat buffer
+for n, p in gb.params:
+    assert gb.owns(p), n
+
+red = GradReducer(gb, "layers.", 6, layers_per_bucket=4)
+for n, p in gb.params:
+    p.grad.fill_(float(rank + 1))
+for i in range(5, -1, -1):            # the backward visits the layers in decreasing order
+    red.layer_done(i)
+red.finish()
+expect = sum(range(1, world + 1)) / world
+for n, p in gb.params:
+    assert torch.allclose(p.grad, torch.full_like(p.grad, expect)), n
+# the plain (non-overlapped) reduction gives the same result
+for n, p in gb.params:
+    p.grad.fill_(float(rank + 1))
+for w in gb.allreduce(bucket_bytes=1024, async_op=True):
+    w.wait()
+for n, p in gb.params:
+    assert torch.allclose(p.grad, torch.full_like(p.grad, expect)), n
+dist.barrier()
+if rank == 0:
+    print("GLOO_DP_OK")
+dist.destroy_process_group()

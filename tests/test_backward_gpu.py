@@ -191,10 +191,11 @@ def test_heads_and_loss_bwd(cuda):
 
 
 def test_fused_adam_matches_torch(cuda):
-    from aptai_b200.train import FusedAdam
+    from aptai_b200.train import FusedAdam, GradBuffer
     shapes = [(1024, 1024), (1024,), (46, 1024), (3,), (70000,)]
     ps = [torch.nn.Parameter(_rand(s, cuda, 1.0, i)) for i, s in enumerate(shapes)]
     ref = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    GradBuffer([(f"p{i}", p) for i, p in enumerate(ps)])
     opt = FusedAdam(ps, lr=1e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.01)
     ropt = torch.optim.Adam(ref, lr=1e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.01)
     for step in range(3):

@@ -95,3 +95,15 @@ def test_two_rank_gloo_sharded_run():
                        text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "GLOO_OK" in r.stdout
+
+
+def test_two_rank_gloo_data_parallel_gradients():
+    """world_size 2 on CPU (gloo): flat gradient buffer layout, layer-bucketed overlapped all-reduce with averaging,
+    parameter broadcast — the host logic of the data-parallel training step (BASELINE config 4)."""
+    script = os.path.join(ROOT, "tests", "_gloo_dp_worker.py")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29741", script], capture_output=True,
+                       text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "GLOO_DP_OK" in r.stdout
