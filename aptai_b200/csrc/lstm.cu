@@ -1,0 +1,150 @@
+// Persistent bidirectional LSTM recurrence for Force_APTAI's RNN tail (models/modules.py:190-214: nn.LSTM(256, 256,
+// bidirectional) over packed sequences), sm_100a thread-block clusters + distributed shared memory.
+//
+// The input projection W_ih x_t + b_ih + b_hh of every frame and both directions is one GEMM done beforehand
+// (gates_in [B][T][2][4*H]).  This kernel runs the T sequential steps: one cluster of 8 CTAs per (direction, chunk of
+// 8 utterances); CTA c owns hidden units [32c, 32c+32): its 4 x 32 rows of W_hh (128 x 256 fp32 = 128 KB) stay in
+// shared memory for the whole sequence, h_{t-1} of the chunk (256 x 8 fp32) is replicated in every CTA and refreshed
+// each step by st.shared::cluster writes from the owners, one barrier.cluster per step.  fp32 FMA throughout (the
+// recurrence is latency-bound: T steps of a 256-deep dot product; tensor cores would not shorten the chain).
+//
+// Packed-sequence semantics (pack_padded_sequence / pad_packed_sequence): utterance b runs len[b] steps, the reverse
+// direction starts at its last valid frame, outputs beyond len[b] are zero.
+#include "common.h"
+#include "ptx.cuh"
+
+#include <math.h>
+
+namespace aptai {
+
+constexpr int LS_H = 256;          // hidden size (and input size) of Force_APTAI's LSTM
+constexpr int LS_CL = 8;           // CTAs per cluster
+constexpr int LS_U = LS_H / LS_CL; // hidden units per CTA
+constexpr int LS_R = 4 * LS_U;     // gate rows per CTA
+constexpr int LS_BC = 8;           // utterances per cluster
+constexpr int LS_THREADS = 256;
+constexpr int LS_SMEM = (LS_H * LS_R + 2 * LS_H * LS_BC + LS_R * LS_BC) * 4;   // W^T | h double buffer | gates
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+__global__ void __cluster_dims__(LS_CL, 1, 1) __launch_bounds__(LS_THREADS, 1)
+bilstm_kernel(const float* __restrict__ gates_in, const float* __restrict__ w_hh_f, const float* __restrict__ w_hh_r,
+              const int* __restrict__ lens, int B, int T, float* __restrict__ out) {
+  extern __shared__ __align__(16) float lsm[];
+  float* Wt = lsm;                          // [k][r]   r = gate*32 + unit
+  float* hbuf = Wt + LS_H * LS_R;           // [2][k][b]
+  float* gsm = hbuf + 2 * LS_H * LS_BC;     // [r][b]
+  const int tid = threadIdx.x;
+  const uint32_t rank = cluster_ctarank();
+  const int cid = blockIdx.x / LS_CL;       // cluster index = dir * n_chunks + chunk
+  const int n_chunks = (B + LS_BC - 1) / LS_BC;
+  const int dir = cid / n_chunks, chunk = cid - dir * n_chunks;
+  const int b0 = chunk * LS_BC;
+  const float* whh = dir ? w_hh_r : w_hh_f;
+
+  // W_hh slice, transposed so that the 128 gate rows are contiguous (conflict-free reads across a warp)
+  for (int i = tid; i < LS_R * LS_H; i += LS_THREADS) {
+    const int r = i / LS_H, k = i - r * LS_H;
+    const int gate = r / LS_U, u = r - gate * LS_U;
+    Wt[k * LS_R + r] = __ldg(whh + static_cast<long long>(gate * LS_H + rank * LS_U + u) * LS_H + k);
+  }
+  for (int i = tid; i < 2 * LS_H * LS_BC; i += LS_THREADS) hbuf[i] = 0.f;
+  __syncthreads();
+  cluster_sync_all();
+
+  int steps = 0;
+  for (int b = 0; b < LS_BC; ++b)
+    if (b0 + b < B) steps = max(steps, min(max(__ldg(lens + b0 + b), 0), T));
+
+  // matvec role: gate row r_mv for 4 utterances; pointwise role: (unit u_pw, utterance b_pw)
+  const int r_mv = tid & (LS_R - 1), bh = tid >> 7;
+  const int u_pw = tid & (LS_U - 1), b_pw = tid >> 5;
+  const int gb = b0 + b_pw;
+  const int my_len = gb < B ? min(max(__ldg(lens + gb), 0), T) : 0;
+  float c_state = 0.f;
+  uint32_t remote_h[LS_CL];
+#pragma unroll
+  for (int c = 0; c < LS_CL; ++c) remote_h[c] = map_to_cta(hbuf, c);
+
+  auto load_gin = [&](int s, float (&g)[4]) {
+    if (s < my_len) {
+      const int t = dir ? (my_len - 1 - s) : s;
+      const float* p = gates_in + ((static_cast<long long>(gb) * T + t) * 2 + dir) * (4 * LS_H) + rank * LS_U + u_pw;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) g[q] = __ldg(p + q * LS_H);
+    }
+  };
+  float gin[4] = {0.f, 0.f, 0.f, 0.f};
+  load_gin(0, gin);
+
+  for (int s = 0; s < steps; ++s) {
+    const float* hp = hbuf + (s & 1) * LS_H * LS_BC;
+    // recurrent matvec: acc[j] = sum_k W[r][k] * h[k][bh*4 + j]
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < LS_H; ++k) {
+      const float w = Wt[k * LS_R + r_mv];
+      const float4 h4 = *reinterpret_cast<const float4*>(hp + k * LS_BC + bh * 4);
+      a0 = fmaf(w, h4.x, a0); a1 = fmaf(w, h4.y, a1); a2 = fmaf(w, h4.z, a2); a3 = fmaf(w, h4.w, a3);
+    }
+    *reinterpret_cast<float4*>(gsm + r_mv * LS_BC + bh * 4) = make_float4(a0, a1, a2, a3);
+    float gnext[4] = {0.f, 0.f, 0.f, 0.f};
+    load_gin(s + 1, gnext);          // prefetch the next step's input projection under the barrier
+    __syncthreads();
+    // pointwise: torch gate order i, f, g, o
+    float h_new = 0.f;
+    const bool active = s < my_len;
+    if (active) {
+      const float gi = sigmoidf_(gsm[(0 * LS_U + u_pw) * LS_BC + b_pw] + gin[0]);
+      const float gf = sigmoidf_(gsm[(1 * LS_U + u_pw) * LS_BC + b_pw] + gin[1]);
+      const float gg = tanhf(gsm[(2 * LS_U + u_pw) * LS_BC + b_pw] + gin[2]);
+      const float go = sigmoidf_(gsm[(3 * LS_U + u_pw) * LS_BC + b_pw] + gin[3]);
+      c_state = fmaf(gf, c_state, gi * gg);
+      h_new = go * tanhf(c_state);
+      const int t = dir ? (my_len - 1 - s) : s;
+      out[(static_cast<long long>(gb) * T + t) * (2 * LS_H) + dir * LS_H + rank * LS_U + u_pw] = h_new;
+      // publish h_t[unit][b] to every CTA of the cluster (next step's buffer)
+      const uint32_t off = static_cast<uint32_t>((((s + 1) & 1) * LS_H * LS_BC + (rank * LS_U + u_pw) * LS_BC + b_pw) * 4);
+#pragma unroll
+      for (int c = 0; c < LS_CL; ++c) st_cluster_f32(remote_h[c] + off, h_new);
+    } else if (gb < B && s < T) {
+      out[(static_cast<long long>(gb) * T + s) * (2 * LS_H) + dir * LS_H + rank * LS_U + u_pw] = 0.f;   // padding frame
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) gin[q] = gnext[q];
+    cluster_sync_all();              // h_t visible everywhere; gsm reusable
+  }
+  // frames beyond the chunk's longest utterance
+  if (gb < B)
+    for (int t = steps; t < T; ++t)
+      out[(static_cast<long long>(gb) * T + t) * (2 * LS_H) + dir * LS_H + rank * LS_U + u_pw] = 0.f;
+  cluster_sync_all();                // no CTA exits while a peer may still write into its shared memory
+}
+
+}  // namespace aptai
+
+using namespace aptai;
+
+extern "C" int aptai_bilstm_256(const float* gates_in, const float* w_hh_fwd, const float* w_hh_rev,
+                                const int32_t* lens, int B, int T, float* out, void* stream) {
+  if (int rc = check_arch()) return rc;
+  APTAI_REQUIRE(gates_in && w_hh_fwd && w_hh_rev && lens && out, "bilstm: null pointer");
+  APTAI_REQUIRE(B >= 1 && T >= 1, "bilstm: bad shape");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(bilstm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LS_SMEM);
+    if (e != cudaSuccess) {
+      set_error("bilstm: cudaFuncSetAttribute(%d bytes): %s", LS_SMEM, cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    attr_set = true;
+  }
+  const int n_chunks = (B + LS_BC - 1) / LS_BC;
+  bilstm_kernel<<<2 * n_chunks * LS_CL, LS_THREADS, LS_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(
+      gates_in, w_hh_fwd, w_hh_rev, lens, B, T, out);
+  return after_launch("bilstm_256");
+}

@@ -102,7 +102,10 @@ class CrossAttention(nn.Module):
 class RNN(nn.Module):
     """models/modules.py:190-214: BiLSTM(256) -> Linear -> Dropout -> Tanh -> Linear(9).  The reference's packed
     path for batch > 1 raises NameError (`packed_putput`, modules.py:207); the intended `packed_output`
-    semantics are implemented.  The recurrence itself stays on cuDNN ('next' row)."""
+    semantics are implemented (per-utterance lengths, zeros beyond them; for batch 1 the reference runs the
+    whole padded row, which is the same thing with len = T).
+    Kernels: input projection = fp32-accurate tcgen05 GEMM, recurrence = persistent cluster kernel
+    (csrc/lstm.cu), Linear(512,256) = tcgen05 GEMM, Tanh + Linear(256,9) = the heads kernel."""
 
     def __init__(self, hidden_dim, out_dim, drop=0.1):
         super().__init__()
@@ -110,20 +113,22 @@ class RNN(nn.Module):
         self.linear = nn.Sequential(nn.Linear(2 * hidden_dim, hidden_dim), nn.Dropout(drop), nn.Tanh(),
                                     nn.Linear(hidden_dim, out_dim))
 
+    @torch.no_grad()
     def forward(self, embeddings, lens):
-        from torch.nn.utils.rnn import pack_padded_sequence, pad_packed_sequence
-        if embeddings.shape[0] > 1:
-            lens_cpu = torch.as_tensor(lens, dtype=torch.int64).cpu()
-            packed = pack_padded_sequence(embeddings, lens_cpu, batch_first=True, enforce_sorted=False)
-            packed_output, _ = self.lstm(packed)
-            out, _ = pad_packed_sequence(packed_output, batch_first=True, total_length=embeddings.shape[1])
-            hidden_tvs = out
-            out = self.linear(out)
+        if self.training and self.linear[1].p > 0:
+            raise NotImplementedError("aptai_b200: training-mode dropout/backward of the RNN tail is not built; .eval()")
+        x = embeddings.detach().float().contiguous()
+        B, T, D = x.shape
+        if B > 1:
+            ln = torch.as_tensor(lens, dtype=torch.int32).reshape(B).to(x.device).contiguous()
         else:
-            out, _ = self.lstm(embeddings)
-            hidden_tvs = out
-            out = self.linear(out)
-        return out, hidden_tvs
+            ln = torch.full((1,), T, dtype=torch.int32, device=x.device)
+        hidden = ops.bilstm_256(x, self.lstm, ln)
+        l0, l3 = self.linear[0], self.linear[3]
+        f = lambda p: p.detach().float().contiguous()
+        t = ops.linear_f32x3(hidden.view(B * T, -1), l0.weight, f(l0.bias))
+        out, _, _ = ops.heads(t, f(l3.weight), f(l3.bias), ops.ACT_TANH, None, None, 0, want_argmax=False)
+        return out.view(B, T, -1), hidden
 
 
 class PositionalEncoding(nn.Module):

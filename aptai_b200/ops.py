@@ -517,3 +517,22 @@ def gelu_bwd(dy: torch.Tensor, pre: torch.Tensor) -> torch.Tensor:
     out = torch.empty_like(dy)
     check(_lib.load().aptai_gelu_bwd(dy.data_ptr(), pre.data_ptr(), dy.numel(), out.data_ptr(), _stream()), "gelu_bwd")
     return out
+
+
+def bilstm_256(x: torch.Tensor, lstm: "torch.nn.LSTM", lens: torch.Tensor) -> torch.Tensor:
+    """Bidirectional single-layer LSTM(256 -> 256) over padded [B,T,256] fp32 input with per-utterance lengths
+    (packed-sequence semantics): input projection of both directions as one fp32-accurate tensor-core GEMM, the
+    recurrence in the cluster kernel.  Returns hidden fp32 [B,T,512]."""
+    _req(x, F32, "x"); _req(lens, I32, "lens")
+    B, T, D = x.shape
+    if D != 256 or lstm.hidden_size != 256 or not lstm.bidirectional or lstm.num_layers != 1:
+        raise NotImplementedError("aptai_b200 BiLSTM kernel is built for Force_APTAI's LSTM(256, 256, bidirectional)")
+    f = lambda t: t.detach().to(device=x.device, dtype=F32).contiguous()
+    w_ih = torch.cat([f(lstm.weight_ih_l0), f(lstm.weight_ih_l0_reverse)], dim=0)                  # [2048, 256]
+    b = torch.cat([f(lstm.bias_ih_l0) + f(lstm.bias_hh_l0), f(lstm.bias_ih_l0_reverse) + f(lstm.bias_hh_l0_reverse)])
+    gates = linear_f32x3(x.view(B * T, D), w_ih, b.contiguous())                                   # [B*T, 2048]
+    out = torch.empty((B, T, 512), dtype=F32, device=x.device)
+    check(_lib.load().aptai_bilstm_256(gates.data_ptr(), f(lstm.weight_hh_l0).data_ptr(),
+                                       f(lstm.weight_hh_l0_reverse).data_ptr(), lens.data_ptr(), B, T, out.data_ptr(),
+                                       _stream()), "bilstm_256")
+    return out

@@ -145,6 +145,13 @@ int aptai_cross_attention(const float* frame, const int32_t* phn_ids, const floa
                           const float* ln_b, float eps, int B, int T, float* att_out, float* energy, float* att,
                           void* stream);
 
+/* Recurrence of Force_APTAI's bidirectional LSTM (models/modules.py:197-211: nn.LSTM(256, 256, bidirectional,
+ * batch_first) over pack_padded_sequence).  gates_in fp32 [B][T][2][1024] = W_ih x_t + b_ih + b_hh per direction
+ * (torch gate order i,f,g,o), w_hh_* fp32 [1024][256], lens int32 [B]; out fp32 [B][T][512] (forward | reverse),
+ * zero beyond lens[b]. */
+int aptai_bilstm_256(const float* gates_in, const float* w_hh_fwd, const float* w_hh_rev, const int32_t* lens, int B,
+                     int T, float* out, void* stream);
+
 /* masked MSE + cross entropy of APTAI.forward (models/aptai.py:89-102).  out3 = {loss, mse, ce}. */
 int aptai_masked_mse_ce(const float* tv_pred, const float* tv_tgt, const float* logits, const int64_t* phn_tgt,
                         int64_t rows, int ntv, int V, float* accum_ws, float* out3, void* stream);

@@ -251,3 +251,27 @@ def test_cross_attention_block(cuda):
     o2, e2 = m(c(frame), c(phn), c(mask))
     torch.testing.assert_close(o2.cpu(), r_out, atol=2e-4, rtol=1e-4)
     torch.testing.assert_close(e2.cpu(), r_energy, atol=2e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("B,T,lens", [(1, 99, [99]), (3, 130, [130, 7, 64]), (9, 50, [50, 1, 50, 33, 2, 49, 17, 50, 25]),
+                                       (64, 399, None)])
+def test_bilstm_cluster_kernel_vs_torch(cuda, B, T, lens):
+    """Persistent cluster BiLSTM (csrc/lstm.cu) + RNN tail against torch nn.LSTM on packed sequences (CPU fp32):
+    models/modules.py:190-214 with the intended packed_output semantics."""
+    from torch.nn.utils.rnn import pack_padded_sequence, pad_packed_sequence
+    from aptai_b200.modules import RNN
+    torch.manual_seed(3)
+    rnn = RNN(256, 9, drop=0.0).eval()
+    g = torch.Generator().manual_seed(5)
+    if lens is None:
+        lens = torch.randint(60, T + 1, (B,), generator=g).tolist()
+        lens[0] = T
+    x = torch.randn((B, T, 256), generator=g)
+    with torch.no_grad():
+        packed = pack_padded_sequence(x, torch.tensor(lens), batch_first=True, enforce_sorted=False)
+        ref_h, _ = pad_packed_sequence(rnn.lstm(packed)[0], batch_first=True, total_length=T)
+        ref_out = rnn.linear(ref_h)
+    rnn = rnn.to(cuda)
+    out, hid = rnn(x.to(cuda), lens)
+    torch.testing.assert_close(hid.cpu(), ref_h, atol=2e-4, rtol=1e-3)
+    torch.testing.assert_close(out.cpu(), ref_out, atol=5e-4, rtol=1e-3)
