@@ -84,6 +84,17 @@ PROTOTYPES = {
                                         c_void_p, c_void_p, c_void_p]),
     "aptai_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                 c_float, c_float, c_float, c_float, c_float, c_int, c_float, c_void_p]),
+    # ---- callers' data formats
+    "aptai_collate_pad": (c_int, [c_void_p, c_int, c_void_p, c_int, c_i64, c_void_p, c_void_p, c_void_p]),
+    "aptai_resample_fir": (c_int, [c_void_p, c_void_p, c_int, c_i64, c_void_p, c_int, c_int, c_int, c_void_p, c_i64,
+                                   c_void_p]),
+    "aptai_interp_linear_f64": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "aptai_frames_to_segments": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                         c_int, c_void_p]),
+    "aptai_tv_metrics": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "aptai_boundary_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, C.c_double, c_void_p,
+                                     c_void_p]),
+    "aptai_frame_overlap": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
 }
 
 _lib = None

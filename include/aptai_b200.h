@@ -256,6 +256,36 @@ int aptai_adam_step(void* const* params_dev, const int64_t* grad_offsets_dev, co
                     float* exp_avg_sq, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                     float grad_scale, void* stream);
 
+/* ================================================================== callers' data formats ==
+ * Input side. */
+/* ragged -> padded batch (torch.nn.utils.rnn.pad_sequence(batch_first=True) of train/train_aptai.py:268-332):
+ * flat = the B sequences back to back (4- or 8-byte elements), offsets int64 [B+1]; out [B][Lmax], tail = pad value */
+int aptai_collate_pad(const void* flat, int elem_bytes, const int64_t* offsets, int B, int64_t Lmax,
+                      const void* pad_value_host, void* out, void* stream);
+/* polyphase FIR of torchaudio.functional.resample (data/dataset_hprc.py:68-72): kernel fp32 [nw][2*width+orig] from
+ * _get_sinc_resample_kernel (orig, nw already divided by their gcd); y[b][j] for j < ceil(nw*in_len[b]/orig), 0 after */
+int aptai_resample_fir(const float* x, const int64_t* in_len, int B, int64_t in_ld, const float* kernel, int orig,
+                       int nw, int width, float* y, int64_t out_ld, void* stream);
+/* interpolate_signal (data/dataset_hprc.py:2307-2313): scipy interp1d(arange(n), sig, 'linear', axis=0) evaluated at
+ * linspace(0, n-1, m); sig fp64 [n][C] -> out fp64 [m][C], bit-exact */
+int aptai_interp_linear_f64(const double* sig, int n, int C, int m, double* out, void* stream);
+/* Output side. */
+/* phn_frames2dur / phn_frame_id2phn (utility.py:539-566): run-length segments of frame labels int64 [B][T] over the
+ * first lens[b] frames: seg_start/seg_end (frames, end exclusive), seg_phn, nseg[b] (may exceed max_seg: truncated) */
+int aptai_frames_to_segments(const int64_t* frames, const int32_t* lens, int B, int T, int32_t* seg_start,
+                             int32_t* seg_end, int64_t* seg_phn, int32_t* nseg, int max_seg, void* stream);
+/* tvs_metric_rmse / tvs_metric_ppc (utility.py:393-444) per utterance and channel over the first lens[b] frames:
+ * gt, pred fp32 [B][T][C] -> rmse, pcc fp64 [B][C] (RMSE bit-exact with the reference's sequential fp64 sum) */
+int aptai_tv_metrics(const float* gt, const float* pred, const int32_t* lens, int B, int T, int C, double* rmse,
+                     double* pcc, void* stream);
+/* get_stats counters (utility.py:589-611): boundaries fp64 [B][maxn] (seconds) with counts ny/nyhat;
+ * counters int32 [B][4] = {precision_counter, recall_counter, len(yhat), len(y)} */
+int aptai_boundary_stats(const double* y, const int32_t* ny, const double* yhat, const int32_t* nyhat, int B, int maxn,
+                         double tolerance, int32_t* counters, void* stream);
+/* evaluate_overlap (utility.py:614-622): hits_counts uint64 [2] = {#equal frames, #frames} over the valid frames */
+int aptai_frame_overlap(const int64_t* a, const int64_t* b, const int32_t* lens, int B, int T, uint64_t* hits_counts,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif
