@@ -106,75 +106,122 @@ class _Encoder(nn.Module):
 
 
 # ----------------------------------------------------------------------------------------- kernel-side weights
-class _Plan:
-    """Kernel-ready copies of the parameters (bf16 GEMM operands, fused QKV, tap-major conv weights, folded
-    weight-norm).  Rebuilt whenever a parameter changes (load_state_dict, optimizer step, .to())."""
+class _WeightTable:
+    """Device table for `aptai_prepare_weights`: one launch turns the fp32 master weights into the kernels' operand
+    copies (bf16 [N][K], transposed bf16 [K][N], fused / scaled fp32 biases)."""
 
-    def __init__(self, m: "Wav2Vec2Backbone"):
+    def __init__(self, dev):
+        self.dev, self.rows, self.keep, self.tiles = dev, [], [], 0
+        self.table = None
+
+    def add(self, src, dst=None, dst_off=0, dst_ld=0, dst_t=None, dst_t_off=0, dst_t_ld=0, dst_f32=None, f32_off=0,
+            scale=1.0, scale_t=1.0):
+        src = src.detach()
+        if src.dtype != F32 or not src.is_contiguous() or src.device != self.dev:
+            raise TypeError("aptai_b200: master weights must be contiguous fp32 tensors on the model's CUDA device")
+        rows, cols = (1, src.numel()) if src.dim() == 1 else (src.shape[0], src.shape[1])
+        from .lib import PrepEntry
+        e = PrepEntry()
+        e.src = src.data_ptr()
+        e.dst = dst.data_ptr() + 2 * dst_off if dst is not None else None
+        e.dst_t = dst_t.data_ptr() + 2 * dst_t_off if dst_t is not None else None
+        e.dst_f32 = dst_f32.data_ptr() + 4 * f32_off if dst_f32 is not None else None
+        e.rows, e.cols, e.dst_ld, e.dst_t_ld = rows, cols, dst_ld or cols, dst_t_ld or rows
+        e.scale, e.scale_t = scale, scale_t
+        e.tiles_x = (cols + 31) // 32
+        e.tile0 = self.tiles
+        self.tiles += e.tiles_x * ((rows + 31) // 32)
+        self.rows.append(e)
+        self.keep.append((src, dst, dst_t, dst_f32))
+
+    def run(self):
+        import ctypes as C
+        from .lib import PrepEntry
+        if self.table is None:
+            arr = (PrepEntry * len(self.rows))(*self.rows)
+            raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone()
+            self.table = raw.to(self.dev)
+        ops.prepare_weights(self.table, len(self.rows), self.tiles)
+
+
+class _Plan:
+    """Kernel-ready copies of the parameters (bf16 GEMM operands, fused QKV with the softmax scale folded into q,
+    tap-major conv weights, folded weight-norm) in PERSISTENT buffers.  `refresh()` re-derives them from the fp32
+    master weights with one multi-tensor launch (after load_state_dict / every optimizer step); the table is rebuilt
+    only when a parameter's storage moves.  With `train=True` it also keeps what the backward needs: transposed bf16
+    weights for the dgrad GEMMs (dX = dY @ W is the forward kernel on W^T; the q block unscaled), a bf16 projection
+    weight, and the flipped / in-out-swapped folded pos-conv weight (transposed conv = the forward kernel on it)."""
+
+    def __init__(self, m: "Wav2Vec2Backbone", train: bool = False):
         cfg = m.cfg
         dev = m.masked_spec_embed.device
-        f = lambda t: t.detach().to(device=dev, dtype=F32).contiguous()
-        b = lambda t: t.detach().to(device=dev, dtype=BF16).contiguous()
-        h = lambda t: t.detach().to(device=dev, dtype=F16).contiguous()   # conv stack / projection operands
-        cl = m.feature_extractor.conv_layers
-        self.conv0_w = f(cl[0].conv.weight.reshape(cfg.conv_dim[0], cfg.conv_kernel[0]))
-        self.conv_b = [f(l.conv.bias) if l.conv.bias is not None else None for l in cl]
-        self.conv_ln_w = [f(l.layer_norm.weight) if hasattr(l, "layer_norm") else None for l in cl]
-        self.conv_ln_b = [f(l.layer_norm.bias) if hasattr(l, "layer_norm") else None for l in cl]
-        # conv i >= 1: [out][in][k] -> [out][k][in]  (K index = tap*C_in + c)
-        self.conv_w = [None] + [h(l.conv.weight.permute(0, 2, 1).reshape(l.conv.weight.shape[0], -1)) for l in cl[1:]]
+        self.train = train
+        f = lambda t: t.detach().to(device=dev, dtype=F32).contiguous()    # fp32 params: a view, tracks updates
+        self._f = f
+        self._conv_key = None
         fp = m.feature_projection
         self.fp_ln_w, self.fp_ln_b = f(fp.layer_norm.weight), f(fp.layer_norm.bias)
-        self.fp_w, self.fp_b = h(fp.projection.weight), f(fp.projection.bias)
+        self.fp_b = f(fp.projection.bias)
+        pc = m.encoder.pos_conv_embed.conv
+        self.pos_b = f(pc.bias)
+        self.enc_ln_w, self.enc_ln_b = f(m.encoder.layer_norm.weight), f(m.encoder.layer_norm.bias)
+        H, Fi = cfg.hidden_size, cfg.intermediate_size
+        scale = float(cfg.head_dim) ** -0.5     # folded into q (0.125 for head_dim 64: exact in bf16)
+        tb = _WeightTable(dev)
+        e16 = lambda *shape: torch.empty(shape, dtype=BF16, device=dev)
+        if train:
+            self.fp_w_bf16, self.fp_wt = e16(H, cfg.conv_dim[-1]), e16(cfg.conv_dim[-1], H)
+            tb.add(fp.projection.weight, dst=self.fp_w_bf16, dst_t=self.fp_wt)
+        self.layers = []
+        for l in m.encoder.layers:
+            a, ff = l.attention, l.feed_forward
+            ns = SimpleNamespace(
+                qkv_w=e16(3 * H, H), qkv_b=torch.empty((3 * H,), dtype=F32, device=dev), o_w=e16(H, H),
+                ff1_w=e16(Fi, H), ff2_w=e16(H, Fi), o_b=f(a.out_proj.bias), ff1_b=f(ff.intermediate_dense.bias),
+                ff2_b=f(ff.output_dense.bias), ln1_w=f(l.layer_norm.weight), ln1_b=f(l.layer_norm.bias),
+                ln2_w=f(l.final_layer_norm.weight), ln2_b=f(l.final_layer_norm.bias))
+            if train:
+                ns.qkv_wt, ns.o_wt, ns.ff1_wt, ns.ff2_wt = e16(H, 3 * H), e16(H, H), e16(H, Fi), e16(Fi, H)
+            for blk, (proj, sc) in enumerate(((a.q_proj, scale), (a.k_proj, 1.0), (a.v_proj, 1.0))):
+                tb.add(proj.weight, dst=ns.qkv_w, dst_off=blk * H * H, dst_ld=H, scale=sc,
+                       dst_t=ns.qkv_wt if train else None, dst_t_off=blk * H, dst_t_ld=3 * H, scale_t=1.0)
+                tb.add(proj.bias, dst_f32=ns.qkv_b, f32_off=blk * H, scale=sc)
+            tb.add(a.out_proj.weight, dst=ns.o_w, dst_t=ns.o_wt if train else None)
+            tb.add(ff.intermediate_dense.weight, dst=ns.ff1_w, dst_t=ns.ff1_wt if train else None)
+            tb.add(ff.output_dense.weight, dst=ns.ff2_w, dst_t=ns.ff2_wt if train else None)
+            self.layers.append(ns)
+        self._table = tb
+        self.refresh(m)
+
+    def refresh(self, m: "Wav2Vec2Backbone") -> None:
+        cfg = m.cfg
+        dev = m.masked_spec_embed.device
+        f = self._f
+        cl = m.feature_extractor.conv_layers
+        ck = tuple((p.data_ptr(), p._version) for p in m.feature_extractor.parameters()) + tuple(
+            (p.data_ptr(), p._version) for p in m.feature_projection.projection.parameters())
+        if ck != self._conv_key:      # frozen in training: re-derived only after load_state_dict / .to()
+            h = lambda t: t.detach().to(device=dev, dtype=F16).contiguous()   # conv stack / projection operands
+            self.conv0_w = f(cl[0].conv.weight.reshape(cfg.conv_dim[0], cfg.conv_kernel[0]))
+            self.conv_b = [f(l.conv.bias) if l.conv.bias is not None else None for l in cl]
+            self.conv_ln_w = [f(l.layer_norm.weight) if hasattr(l, "layer_norm") else None for l in cl]
+            self.conv_ln_b = [f(l.layer_norm.bias) if hasattr(l, "layer_norm") else None for l in cl]
+            # conv i >= 1: [out][in][k] -> [out][k][in]  (K index = tap*C_in + c)
+            self.conv_w = [None] + [h(l.conv.weight.permute(0, 2, 1).reshape(l.conv.weight.shape[0], -1))
+                                    for l in cl[1:]]
+            self.fp_w = h(m.feature_projection.projection.weight)
+            self._conv_key = ck
+        self._table.run()
         pc = m.encoder.pos_conv_embed.conv
         g = f(pc.parametrizations.weight.original0)
         v = f(pc.parametrizations.weight.original1)
         self.pos_w = ops.posconv_fold(g, v, cpad=64)
-        self.pos_b = f(pc.bias)
-        self.enc_ln_w, self.enc_ln_b = f(m.encoder.layer_norm.weight), f(m.encoder.layer_norm.bias)
-        scale = float(cfg.head_dim) ** -0.5     # folded into q (0.125 for head_dim 64: exact in bf16)
-        self.layers = []
-        for l in m.encoder.layers:
-            a = l.attention
-            qkv_w = torch.cat([a.q_proj.weight.detach().float() * scale, a.k_proj.weight.detach().float(),
-                               a.v_proj.weight.detach().float()], dim=0)
-            qkv_b = torch.cat([a.q_proj.bias.detach().float() * scale, a.k_proj.bias.detach().float(),
-                               a.v_proj.bias.detach().float()], dim=0)
-            self.layers.append(SimpleNamespace(
-                qkv_w=b(qkv_w), qkv_b=f(qkv_b), o_w=b(a.out_proj.weight), o_b=f(a.out_proj.bias),
-                ln1_w=f(l.layer_norm.weight), ln1_b=f(l.layer_norm.bias),
-                ff1_w=b(l.feed_forward.intermediate_dense.weight), ff1_b=f(l.feed_forward.intermediate_dense.bias),
-                ff2_w=b(l.feed_forward.output_dense.weight), ff2_b=f(l.feed_forward.output_dense.bias),
-                ln2_w=f(l.final_layer_norm.weight), ln2_b=f(l.final_layer_norm.bias)))
-
-
-class _TrainPlan:
-    """Backward-side operand copies: transposed bf16 weights for the dgrad GEMMs (dX = dY @ W is the forward kernel
-    on W^T), the unscaled fused QKV weight (dq is returned w.r.t. the unscaled q), a bf16 projection weight, and the
-    flipped / in-out-swapped folded pos-conv weight (transposed conv = the forward kernel on it)."""
-
-    def __init__(self, m: "Wav2Vec2Backbone"):
-        cfg = m.cfg
-        dev = m.masked_spec_embed.device
-        bt = lambda t: t.detach().to(device=dev, dtype=BF16).t().contiguous()
-        fp = m.feature_projection
-        self.fp_w = fp.projection.weight.detach().to(device=dev, dtype=BF16).contiguous()
-        self.fp_wt = bt(fp.projection.weight)
-        pc = m.encoder.pos_conv_embed.conv
-        g = pc.parametrizations.weight.original0.detach().to(device=dev, dtype=F32)
-        v = pc.parametrizations.weight.original1.detach().to(device=dev, dtype=F32)
-        H, gw, taps = v.shape
-        groups = H // gw
-        vt = v.view(groups, gw, gw, taps).permute(0, 2, 1, 3).flip(-1).reshape(H, gw, taps).contiguous()
-        self.pos_wt = ops.posconv_fold(g.flip(-1).contiguous(), vt, cpad=64)
-        self.pos_g, self.pos_v = g.contiguous(), v.contiguous()
-        self.layers = []
-        for l in m.encoder.layers:
-            a = l.attention
-            qkv = torch.cat([a.q_proj.weight.detach(), a.k_proj.weight.detach(), a.v_proj.weight.detach()], dim=0)
-            self.layers.append(SimpleNamespace(
-                qkv_wt=bt(qkv), o_wt=bt(a.out_proj.weight), ff1_wt=bt(l.feed_forward.intermediate_dense.weight),
-                ff2_wt=bt(l.feed_forward.output_dense.weight)))
+        if self.train:
+            Hh, gw, taps = v.shape
+            groups = Hh // gw
+            vt = v.view(groups, gw, gw, taps).permute(0, 2, 1, 3).flip(-1).reshape(Hh, gw, taps).contiguous()
+            self.pos_wt = ops.posconv_fold(g.flip(-1).contiguous(), vt, cpad=64)
+            self.pos_g, self.pos_v = g, v
 
 
 _IN_MEMORY = {}
@@ -199,8 +246,7 @@ class Wav2Vec2Backbone(nn.Module):
         self.encoder = _Encoder(cfg)
         self._plan: Optional[_Plan] = None
         self._plan_key = None
-        self._train_plan: Optional[_TrainPlan] = None
-        self._train_plan_key = None
+        self._plan_ptrs = None
         self._feature_encoder_frozen = False
 
     # ---- reference-facing helpers --------------------------------------------------------------------------
@@ -251,21 +297,21 @@ class Wav2Vec2Backbone(nn.Module):
         return n
 
     # ---- plan ------------------------------------------------------------------------------------------------
-    def plan(self) -> _Plan:
-        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
-        if self._plan is None or key != self._plan_key:
-            with torch.no_grad():
-                self._plan = _Plan(self)
-            self._plan_key = key
+    def plan(self, train: bool = False) -> _Plan:
+        params = list(self.parameters())
+        ptrs = tuple(p.data_ptr() for p in params)
+        vers = tuple(p._version for p in params)
+        P = self._plan
+        with torch.no_grad():
+            if P is None or ptrs != self._plan_ptrs or (train and not P.train):
+                self._plan = _Plan(self, train=train or (P is not None and P.train))
+            elif vers != self._plan_key:
+                P.refresh(self)
+        self._plan_ptrs, self._plan_key = ptrs, vers
         return self._plan
 
-    def train_plan(self) -> _TrainPlan:
-        self.plan()
-        if self._train_plan is None or self._train_plan_key != self._plan_key:
-            with torch.no_grad():
-                self._train_plan = _TrainPlan(self)
-            self._train_plan_key = self._plan_key
-        return self._train_plan
+    def train_plan(self) -> _Plan:
+        return self.plan(train=True)
 
     def fused_grad_groups(self, prefix: str = ""):
         """Parameter-name groups that must be adjacent in the flat gradient buffer (fused QKV wgrad)."""
@@ -293,7 +339,8 @@ class Wav2Vec2Backbone(nn.Module):
         """Same arithmetic as `encode` (the feature projection runs on bf16 instead of fp16 operands so that its
         wgrad shares the bf16 kernel).  Returns (last_hidden fp32 [B,T,H], saved activations)."""
         self.check_trainable()
-        cfg, P, TP = self.cfg, self.plan(), self.train_plan()
+        cfg = self.cfg
+        P = TP = self.train_plan()
         B, L = wav.shape
         norm = 1 if cfg.feat_extract_norm == "layer" else 2
         y = ops.conv0(wav, P.conv0_w, P.conv_b[0], P.conv_ln_w[0], P.conv_ln_b[0], norm, out_dtype=F16)
@@ -306,7 +353,7 @@ class Wav2Vec2Backbone(nn.Module):
         sv = SimpleNamespace(B=B, T=T, frame_lens=frame_lens, layers=[])
         sv.y32 = y.view(M, -1).float()
         _, sv.xn = ops.layernorm(sv.y32, P.fp_ln_w, P.fp_ln_b, eps)
-        h0, _ = ops.linear(sv.xn, TP.fp_w, P.fp_b, want_f32=True, want_bf16=False, seg_rows=T,
+        h0, _ = ops.linear(sv.xn, TP.fp_w_bf16, P.fp_b, want_f32=True, want_bf16=False, seg_rows=T,
                            seg_valid_rows=frame_lens)
         sv.hp = ops.cast_pad(h0.view(B, T, H), taps // 2)
         sv.pos_pre = torch.empty((M, H), dtype=BF16, device=wav.device)
@@ -357,7 +404,8 @@ class Wav2Vec2Backbone(nn.Module):
         """Accumulate d loss / d parameter for every trainable parameter of the backbone into the GradBuffer `gb`
         (whose parameter names carry `prefix`), given d loss / d last_hidden (fp32 [B*T, H]).  `on_layer_done(i)`
         is called once layer i's gradients are final (data-parallel all-reduce overlap, train.GradReducer)."""
-        cfg, P, TP = self.cfg, self.plan(), self.train_plan()
+        cfg = self.cfg
+        P = TP = self.train_plan()
         B, T, flen = sv.B, sv.T, sv.frame_lens
         M, H = B * T, cfg.hidden_size
         eps, heads = cfg.layer_norm_eps, cfg.num_attention_heads

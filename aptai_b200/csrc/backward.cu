@@ -388,6 +388,61 @@ __global__ void gelu_bwd_kernel(const float* __restrict__ dy, const __nv_bfloat1
   }
 }
 
+// ---------------------------------------------------------------------------------------------- weight preparation
+// After every optimizer step the fp32 master weights must be turned into the kernels' operand copies: bf16 [N][K] for
+// the forward GEMMs (q rows pre-scaled by head_dim^-0.5, q/k/v fused), bf16 [K][N] (transposed, unscaled) for the
+// dgrad GEMMs, fp32 fused biases.  One launch over a table of (source, destinations, scales) instead of ~800 small
+// cast / cat / transpose launches; each 32x32 tile is read once and written in both orientations.
+struct PrepEntry {
+  const float* src;          // [rows][cols] fp32, contiguous
+  __nv_bfloat16* dst;        // optional: dst[r * dst_ld + c] = scale * src
+  __nv_bfloat16* dst_t;      // optional: dst_t[c * dst_t_ld + r] = scale_t * src
+  float* dst_f32;            // optional: dst_f32[r * cols + c] = scale * src
+  int rows, cols, dst_ld, dst_t_ld;
+  float scale, scale_t;
+  int tile0;                 // first tile of this entry in the launch
+  int tiles_x;               // tiles per row of tiles
+};
+
+__global__ void __launch_bounds__(256)
+prepare_weights_kernel(const PrepEntry* __restrict__ entries, int n_entries) {
+  __shared__ float tile[32][33];
+  __shared__ PrepEntry e;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = n_entries - 1;
+    const int t = blockIdx.x;
+    while (lo < hi) {                       // last entry whose tile0 <= t
+      const int mid = (lo + hi + 1) >> 1;
+      if (entries[mid].tile0 <= t) lo = mid;
+      else hi = mid - 1;
+    }
+    e = entries[lo];
+  }
+  __syncthreads();
+  const int t = blockIdx.x - e.tile0;
+  const int r0 = (t / e.tiles_x) * 32, c0 = (t % e.tiles_x) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty + 8 * i, c = c0 + tx;
+    float v = 0.f;
+    if (r < e.rows && c < e.cols) {
+      v = __ldg(e.src + static_cast<long long>(r) * e.cols + c);
+      if (e.dst) e.dst[static_cast<long long>(r) * e.dst_ld + c] = __float2bfloat16(v * e.scale);
+      if (e.dst_f32) e.dst_f32[static_cast<long long>(r) * e.cols + c] = v * e.scale;
+    }
+    tile[ty + 8 * i][tx] = v;
+  }
+  if (e.dst_t == nullptr) return;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i, r = r0 + tx;
+    if (r < e.rows && c < e.cols)
+      e.dst_t[static_cast<long long>(c) * e.dst_t_ld + r] = __float2bfloat16(tile[tx][ty + 8 * i] * e.scale_t);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- fused Adam
 // torch.optim.Adam (train/train_aptai.py:350-356) over a table of tensors in one launch.  Gradients live in one flat
 // fp32 buffer (element offset goff[i]), exp_avg / exp_avg_sq in two more (offset soff[i]); parameters stay the
@@ -556,6 +611,15 @@ extern "C" int aptai_gelu_bwd(const float* dy, const void* pre_bf16, int64_t n, 
   gelu_bwd_kernel<<<gx, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       dy, reinterpret_cast<const __nv_bfloat16*>(pre_bf16), n4, out);
   return after_launch("gelu_bwd");
+}
+
+extern "C" int aptai_prepare_weights(const void* entries_dev, int n_entries, int total_tiles, void* stream) {
+  if (int rc = check_arch()) return rc;
+  APTAI_REQUIRE(entries_dev && n_entries >= 1 && total_tiles >= 1, "prepare_weights: bad arguments");
+  static_assert(sizeof(PrepEntry) == 64, "PrepEntry layout is part of the C ABI (aptai_b200/lib.py PrepEntry)");
+  prepare_weights_kernel<<<total_tiles, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const PrepEntry*>(entries_dev), n_entries);
+  return after_launch("prepare_weights");
 }
 
 extern "C" int aptai_adam_step(void* const* params_dev, const int64_t* grad_offsets_dev,

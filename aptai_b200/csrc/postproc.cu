@@ -53,13 +53,25 @@ __global__ void resample_fir_kernel(const float* __restrict__ x, const long long
 
 // ---------------------------------------------------------------------------------------------- linear interpolation
 // scipy.interpolate.interp1d(arange(n), sig, 'linear', axis=0)(linspace(0, n-1, m)), fp64, same operation order
-__global__ void interp_linear_kernel(const double* __restrict__ sig, int n, int C, int m, double step,
+// per_channel = 1: every column is interpolated as a 1-D signal, where scipy dispatches to numpy.interp
+// (slope * (x - x_lo) + y_lo, exact grid hits returned as is) — the reference's call pattern (dataset_hprc.py:2370)
+__global__ void interp_linear_kernel(const double* __restrict__ sig, int n, int C, int m, double step, int per_channel,
                                      double* __restrict__ out) {
   const long long total = static_cast<long long>(m) * C;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int r = static_cast<int>(i / C), c = static_cast<int>(i - static_cast<long long>(r) * C);
     const double xn = (r == m - 1 && m > 1) ? static_cast<double>(n - 1) : __dmul_rn(static_cast<double>(r), step);
+    if (per_channel) {
+      const int j = min(static_cast<int>(floor(xn)), n - 2);
+      const double yj = sig[static_cast<long long>(j) * C + c];
+      if (xn == static_cast<double>(n - 1)) out[i] = sig[static_cast<long long>(n - 1) * C + c];
+      else if (xn == static_cast<double>(j)) out[i] = yj;
+      else
+        out[i] = __dadd_rn(__dmul_rn(__ddiv_rn(__dsub_rn(sig[static_cast<long long>(j + 1) * C + c], yj), 1.0),
+                                     __dsub_rn(xn, static_cast<double>(j))), yj);
+      continue;
+    }
     int hi = static_cast<int>(ceil(xn));            // searchsorted(arange(n), xn, 'left')
     hi = min(max(hi, 1), n - 1);
     const int lo = hi - 1;
@@ -229,14 +241,15 @@ extern "C" int aptai_resample_fir(const float* x, const int64_t* in_len, int B, 
   return after_launch("resample_fir");
 }
 
-extern "C" int aptai_interp_linear_f64(const double* sig, int n, int C, int m, double* out, void* stream) {
+extern "C" int aptai_interp_linear_f64(const double* sig, int n, int C, int m, int per_channel, double* out,
+                                       void* stream) {
   if (int rc = check_arch()) return rc;
   APTAI_REQUIRE(sig && out && n >= 2 && C >= 1 && m >= 1, "interp_linear: need at least 2 input rows");
   const double step = m > 1 ? static_cast<double>(n - 1) / static_cast<double>(m - 1) : 0.0;   // numpy.linspace
   const long long total = static_cast<long long>(m) * C;
   int gx = static_cast<int>((total + 255) / 256);
   if (gx > 4096) gx = 4096;
-  interp_linear_kernel<<<gx, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(sig, n, C, m, step, out);
+  interp_linear_kernel<<<gx, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(sig, n, C, m, step, per_channel, out);
   return after_launch("interp_linear");
 }
 

@@ -28,6 +28,13 @@ class GemmArgs(C.Structure):
     ]
 
 
+class PrepEntry(C.Structure):
+    """struct aptai_prep_entry (include/aptai_b200.h), 64 bytes."""
+    _fields_ = [("src", c_void_p), ("dst", c_void_p), ("dst_t", c_void_p), ("dst_f32", c_void_p),
+                ("rows", C.c_int32), ("cols", C.c_int32), ("dst_ld", C.c_int32), ("dst_t_ld", C.c_int32),
+                ("scale", c_float), ("scale_t", c_float), ("tile0", C.c_int32), ("tiles_x", C.c_int32)]
+
+
 # name -> (restype, argtypes); every symbol include/aptai_b200.h declares
 PROTOTYPES = {
     "aptai_version": (c_int, []),
@@ -82,13 +89,14 @@ PROTOTYPES = {
                                 c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "aptai_masked_mse_ce_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_void_p]),
+    "aptai_prepare_weights": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "aptai_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                 c_float, c_float, c_float, c_float, c_float, c_int, c_float, c_void_p]),
     # ---- callers' data formats
     "aptai_collate_pad": (c_int, [c_void_p, c_int, c_void_p, c_int, c_i64, c_void_p, c_void_p, c_void_p]),
     "aptai_resample_fir": (c_int, [c_void_p, c_void_p, c_int, c_i64, c_void_p, c_int, c_int, c_int, c_void_p, c_i64,
                                    c_void_p]),
-    "aptai_interp_linear_f64": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "aptai_interp_linear_f64": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "aptai_frames_to_segments": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                          c_int, c_void_p]),
     "aptai_tv_metrics": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),

@@ -536,3 +536,8 @@ def bilstm_256(x: torch.Tensor, lstm: "torch.nn.LSTM", lens: torch.Tensor) -> to
                                        f(lstm.weight_hh_l0_reverse).data_ptr(), lens.data_ptr(), B, T, out.data_ptr(),
                                        _stream()), "bilstm_256")
     return out
+
+
+def prepare_weights(table: torch.Tensor, n_entries: int, total_tiles: int) -> None:
+    """Launch the multi-tensor weight preparation over a device table of `aptai_prep_entry` rows."""
+    check(_lib.load().aptai_prepare_weights(table.data_ptr(), n_entries, total_tiles, _stream()), "prepare_weights")

@@ -113,17 +113,21 @@ def resample(waveform: torch.Tensor, orig_freq: int, new_freq: int, lengths: Opt
     return y, torch.ceil(new * ln.double() / orig).long()
 
 
-def interpolate_signal(org_sig, tar_len: int):
-    """data/dataset_hprc.py:2307-2313 (scipy interp1d, linear, axis 0) in fp64 on the device; returns a numpy array
-    like the reference."""
+def interpolate_signal(org_sig, tar_len: int, per_channel: Optional[bool] = None):
+    """data/dataset_hprc.py:2307-2313 (scipy interp1d, linear, axis 0) in fp64 on the device, bit-exact; returns a
+    numpy array like the reference.  1-D input follows scipy's 1-D path (numpy.interp), which is how the reference
+    calls it (one trajectory at a time, dataset_hprc.py:2370); `per_channel=True` applies that path to every column
+    of a [n, C] array in one launch (all nine trajectories at once)."""
     dev = _dev()
     a = np.asarray(org_sig, dtype=np.float64)
+    if per_channel is None:
+        per_channel = a.ndim == 1
     shp = a.shape
     s = torch.from_numpy(a.reshape(shp[0], -1)).to(dev).contiguous()
     n, Cc = s.shape
     out = torch.empty((int(tar_len), Cc), dtype=F64, device=dev)
-    check(_lib.load().aptai_interp_linear_f64(s.data_ptr(), n, Cc, int(tar_len), out.data_ptr(), _stream()),
-          "interp_linear")
+    check(_lib.load().aptai_interp_linear_f64(s.data_ptr(), n, Cc, int(tar_len), int(bool(per_channel)),
+                                              out.data_ptr(), _stream()), "interp_linear")
     return out.cpu().numpy().reshape((int(tar_len),) + shp[1:])
 
 

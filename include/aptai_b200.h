@@ -247,6 +247,21 @@ int aptai_masked_mse_ce_bwd(const float* tv_pred, const float* tv_tgt, const flo
                             int64_t rows, int ntv, int V, const float* accum_ws, const float* grad_scale, float* d_tv,
                             float* d_logits, void* stream);
 
+/* Kernel-operand copies of the fp32 master weights in one launch (after load_state_dict / every optimizer step):
+ * per table entry dst[r][c] = bf16(scale*src[r][c]) (row pitch dst_ld), dst_t[c][r] = bf16(scale_t*src[r][c]) (row
+ * pitch dst_t_ld), dst_f32 = scale*src; any destination may be NULL.  tile0 = index of the entry's first 32x32
+ * tile, tiles_x = ceil(cols/32); total_tiles = sum over entries.  The table lives in device memory. */
+typedef struct aptai_prep_entry {
+  const float* src;
+  void* dst;
+  void* dst_t;
+  float* dst_f32;
+  int32_t rows, cols, dst_ld, dst_t_ld;
+  float scale, scale_t;
+  int32_t tile0, tiles_x;
+} aptai_prep_entry;
+int aptai_prepare_weights(const void* entries_dev, int n_entries, int total_tiles, void* stream);
+
 /* torch.optim.Adam step (train/train_aptai.py:350-356) over a table of parameter tensors in one launch.
  * params_dev: device array of fp32 pointers; grad_offsets / state_offsets / numel: element offset of each tensor in
  * the flat grad buffer, in the flat exp_avg / exp_avg_sq buffers, and its size;
@@ -267,8 +282,9 @@ int aptai_collate_pad(const void* flat, int elem_bytes, const int64_t* offsets, 
 int aptai_resample_fir(const float* x, const int64_t* in_len, int B, int64_t in_ld, const float* kernel, int orig,
                        int nw, int width, float* y, int64_t out_ld, void* stream);
 /* interpolate_signal (data/dataset_hprc.py:2307-2313): scipy interp1d(arange(n), sig, 'linear', axis=0) evaluated at
- * linspace(0, n-1, m); sig fp64 [n][C] -> out fp64 [m][C], bit-exact */
-int aptai_interp_linear_f64(const double* sig, int n, int C, int m, double* out, void* stream);
+ * linspace(0, n-1, m); sig fp64 [n][C] -> out fp64 [m][C], bit-exact.  per_channel=1: each column as a 1-D call (the
+ * reference's pattern, dataset_hprc.py:2370: scipy then uses numpy.interp's formula); 0: scipy's N-D formula */
+int aptai_interp_linear_f64(const double* sig, int n, int C, int m, int per_channel, double* out, void* stream);
 /* Output side. */
 /* phn_frames2dur / phn_frame_id2phn (utility.py:539-566): run-length segments of frame labels int64 [B][T] over the
  * first lens[b] frames: seg_start/seg_end (frames, end exclusive), seg_phn, nseg[b] (may exceed max_seg: truncated) */

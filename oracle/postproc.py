@@ -72,16 +72,28 @@ def evaluate_overlap(gt_f, p_f):
 
 def interpolate_signal(org_sig, tar_len):
     """data/dataset_hprc.py:2307-2313 = scipy interp1d(kind='linear', axis=0) on arange(n) evaluated at
-    linspace(0, n-1, tar_len) (scipy `_call_linear`: (x_new-x_lo)/(x_hi-x_lo) * y_hi + (x_hi-x_new)/(x_hi-x_lo) * y_lo)."""
-    sig0 = np.asarray(org_sig, dtype=np.float64)
-    sig = sig0.reshape(sig0.shape[0], -1)
+    linspace(0, n-1, tar_len).  The reference calls it per trajectory (1-D, dataset_hprc.py:2370,2411), where scipy
+    dispatches to numpy.interp: slope * (x - x_lo) + y_lo with exact hits returned as is; for N-D input scipy's
+    `_call_linear` computes (x_new-x_lo)/(x_hi-x_lo) * y_hi + (x_hi-x_new)/(x_hi-x_lo) * y_lo."""
+    sig = np.asarray(org_sig, dtype=np.float64)
     n = sig.shape[0]
     x_new = np.linspace(0, n - 1, tar_len)
+    if sig.ndim == 1:
+        out = np.empty(tar_len)
+        for i, x in enumerate(x_new):
+            j = min(int(np.floor(x)), n - 2)
+            if x == n - 1:
+                out[i] = sig[n - 1]
+            elif x == j:
+                out[i] = sig[j]
+            else:
+                out[i] = (sig[j + 1] - sig[j]) / 1.0 * (x - j) + sig[j]
+        return out
     hi = np.clip(np.searchsorted(np.arange(n), x_new), 1, n - 1)
     lo = hi - 1
     d = (hi - lo).astype(np.float64)
-    out = ((x_new - lo) / d)[:, None] * sig[hi] + ((hi - x_new) / d)[:, None] * sig[lo]
-    return out.reshape((tar_len,) + sig0.shape[1:])
+    bshape = (tar_len,) + (1,) * (sig.ndim - 1)
+    return ((x_new - lo) / d).reshape(bshape) * sig[hi] + ((hi - x_new) / d).reshape(bshape) * sig[lo]
 
 
 def pad_sequence(seqs, pad_value, dtype):

@@ -76,7 +76,11 @@ def test_boundary_stats_and_overlap_bit_exact(cuda):
 def test_interpolate_and_collate_bit_exact(cuda):
     assert np.array_equal(pp.interpolate_signal(G["i_sig"], 97), G["i_out_97"])
     assert np.array_equal(pp.interpolate_signal(G["i_sig"], 400), G["i_out_400"])
-    assert np.array_equal(pp.interpolate_signal(G["i_sig"][:, 0], 50), op.interpolate_signal(G["i_sig"][:, 0], 50))
+    for m in (50, 97, 211, 399):          # the reference's call pattern: one trajectory (1-D) at a time
+        assert np.array_equal(pp.interpolate_signal(G["i_sig"][:, 0], m), op.interpolate_signal(G["i_sig"][:, 0], m))
+    all9 = pp.interpolate_signal(G["i_sig"], 97, per_channel=True)
+    for c in range(9):
+        assert np.array_equal(all9[:, c], op.interpolate_signal(G["i_sig"][:, c], 97))
     batch = []
     for i in range(3):
         tv = G[f"c_tv{i}"]
