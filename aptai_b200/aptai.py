@@ -14,6 +14,7 @@ import torch.nn as nn
 from . import ops
 from .backbone import Wav2Vec2Backbone
 from .modules import LowPassFilterLayer
+from .graphs import GraphCache
 from .train import GradBuffer, GradReducer, attach_backward, broadcast_parameters
 
 TV_NAMES = ("LA", "LP", "JA", "TTCL", "TTCD", "TMCL", "TMCD", "TBCL", "TBCD")
@@ -156,6 +157,22 @@ class APTAI(nn.Module):
         return {"device": self.device, "vocab": self.vocab, "huggingface_model_id": self.huggingface_model_id,
                 "pretrain_cfg": self.pretrain_cfg}
 
+    use_cuda_graphs = True      # single-utterance calls are launch-bound: replay one CUDA graph per input length
+
+    def _single_graphed(self, wav_input, wav_len):
+        def fn(w, l):
+            tv, logits, pred = self._heads(w, l)
+            return tv, logits, pred, ops.softmax_rows(logits.contiguous())
+
+        if not self.use_cuda_graphs:
+            return fn(wav_input, wav_len)
+        cache = getattr(self, "_graph_cache", None)
+        if cache is None:
+            cache = GraphCache()
+            object.__setattr__(self, "_graph_cache", cache)
+        P = self.wav2vec2.plan()
+        return cache.run((id(P), P.generation, int(wav_input.shape[1])), fn, wav_input, wav_len)
+
     def get_aptai_output(self, wav):
         """models/aptai.py:125-179 (including the (46,T,1) shape of `phn_fc_probs`, Appendix B)."""
         self.eval()
@@ -165,8 +182,7 @@ class APTAI(nn.Module):
                 wav = wav[0]
             wav_input = torch.as_tensor(np.asarray(wav), dtype=torch.float32).reshape(1, -1).to(dev)
             wav_len = torch.tensor([wav_input.shape[1]], dtype=torch.int64, device=dev)
-            tv, logits, pred = self._heads(wav_input, wav_len)
-            probs = ops.softmax_rows(logits.contiguous())
+            tv, logits, pred, probs = self._single_graphed(wav_input, wav_len)
             tvs = tv[0].cpu().numpy()
             tvs_pred = {n: list(tvs[:, i]) for i, n in enumerate(TV_NAMES)}
             return {

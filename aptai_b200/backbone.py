@@ -211,16 +211,17 @@ class _Plan:
                                     for l in cl[1:]]
             self.fp_w = h(m.feature_projection.projection.weight)
             self._conv_key = ck
+            self.generation = getattr(self, "generation", 0) + 1      # buffers re-allocated: captured graphs are stale
         self._table.run()
         pc = m.encoder.pos_conv_embed.conv
         g = f(pc.parametrizations.weight.original0)
         v = f(pc.parametrizations.weight.original1)
-        self.pos_w = ops.posconv_fold(g, v, cpad=64)
+        self.pos_w = ops.posconv_fold(g, v, cpad=64, out=getattr(self, "pos_w", None))
         if self.train:
             Hh, gw, taps = v.shape
             groups = Hh // gw
             vt = v.view(groups, gw, gw, taps).permute(0, 2, 1, 3).flip(-1).reshape(Hh, gw, taps).contiguous()
-            self.pos_wt = ops.posconv_fold(g.flip(-1).contiguous(), vt, cpad=64)
+            self.pos_wt = ops.posconv_fold(g.flip(-1).contiguous(), vt, cpad=64, out=getattr(self, "pos_wt", None))
             self.pos_g, self.pos_v = g, v
 
 

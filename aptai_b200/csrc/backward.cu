@@ -12,42 +12,64 @@
 namespace aptai {
 
 // ---------------------------------------------------------------------------------------------- column sums
-// out[n] += scale * sum_m x[m][n].  Block = 64 columns x a slab of rows; 8 warps stride the rows, lanes own a
-// column pair; partial sums meet in shared memory and leave as one atomicAdd per column and block.
+// out[n] += scale * sum_m x[m][n].  Block = 8 warps x a slab of rows; a lane owns 8 (bf16) / 4 (fp32) adjacent columns
+// and reads them with one 16-byte load per row, four rows in flight; the warps' partial sums meet in shared memory
+// and leave as one atomicAdd per column and block.
 template <bool BF16IN>
 __global__ void __launch_bounds__(256)
 colsum_kernel(const void* __restrict__ xin, long long M, int N, long long ld, int rows_per_block, float scale,
               float* __restrict__ out) {
+  constexpr int CPL = BF16IN ? 8 : 4;            // columns per lane
+  constexpr int CPB = 32 * CPL;                  // columns per block
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int col = blockIdx.x * 64 + lane * 2;
+  const int col = blockIdx.x * CPB + lane * CPL;
   const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_block;
   const long long r1 = min(M, r0 + rows_per_block);
-  float s0 = 0.f, s1 = 0.f;
-  if (col < N) {
-    for (long long r = r0 + warp; r < r1; r += 8) {
-      if (BF16IN) {
-        const __nv_bfloat162 v =
-            *reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const __nv_bfloat16*>(xin) + r * ld + col);
-        const float2 f = __bfloat1622float2(v);
-        s0 += f.x;
-        s1 += f.y;
-      } else {
-        const float2 f = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(xin) + r * ld + col);
-        s0 += f.x;
-        s1 += f.y;
+  float acc[CPL];
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) acc[i] = 0.f;
+  auto add = [&](const uint4& u) {
+    if (BF16IN) {
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+        acc[2 * j] += f.x;
+        acc[2 * j + 1] += f.y;
       }
+    } else {
+      acc[0] += __uint_as_float(u.x); acc[1] += __uint_as_float(u.y);
+      acc[2] += __uint_as_float(u.z); acc[3] += __uint_as_float(u.w);
     }
+  };
+  if (col + CPL <= N) {
+    const char* base = reinterpret_cast<const char*>(xin) + static_cast<long long>(col) * (BF16IN ? 2 : 4);
+    const long long pitch = ld * (BF16IN ? 2 : 4);
+    long long r = r0 + warp;
+    for (; r + 24 < r1; r += 32) {               // rows r, r+8, r+16, r+24 of this warp in flight together
+      const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(base + r * pitch));
+      const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(base + (r + 8) * pitch));
+      const uint4 u2 = __ldg(reinterpret_cast<const uint4*>(base + (r + 16) * pitch));
+      const uint4 u3 = __ldg(reinterpret_cast<const uint4*>(base + (r + 24) * pitch));
+      add(u0); add(u1); add(u2); add(u3);
+    }
+    for (; r < r1; r += 8) add(__ldg(reinterpret_cast<const uint4*>(base + r * pitch)));
+  } else if (col < N) {                          // ragged right edge: scalar
+    for (long long r = r0 + warp; r < r1; r += 8)
+      for (int i = 0; i < CPL && col + i < N; ++i)
+        acc[i] += BF16IN ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(xin)[r * ld + col + i])
+                         : reinterpret_cast<const float*>(xin)[r * ld + col + i];
   }
-  __shared__ float red[8][64];
-  red[warp][lane * 2] = s0;
-  red[warp][lane * 2 + 1] = s1;
+  __shared__ float red[8][CPB];
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) red[warp][lane * CPL + i] = acc[i];
   __syncthreads();
-  if (threadIdx.x < 64) {
+  for (int c = threadIdx.x; c < CPB; c += 256) {
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-    const int c = blockIdx.x * 64 + threadIdx.x;
-    if (c < N) atomicAdd(out + c, s * scale);
+    for (int w = 0; w < 8; ++w) s += red[w][c];
+    const int gc = blockIdx.x * CPB + c;
+    if (gc < N) atomicAdd(out + gc, s * scale);
   }
 }
 
@@ -486,9 +508,17 @@ using namespace aptai;
 extern "C" int aptai_colsum(const void* x, int x_bf16, int64_t M, int N, int64_t ld, float scale, float* out,
                             void* stream) {
   if (int rc = check_arch()) return rc;
-  APTAI_REQUIRE(x && out && M >= 1 && N >= 2 && N % 2 == 0 && ld % 2 == 0, "colsum: bad arguments");
-  const int rpb = 256;
-  dim3 grid((N + 63) / 64, static_cast<unsigned>((M + rpb - 1) / rpb));
+  APTAI_REQUIRE(x && out && M >= 1 && N >= 1, "colsum: bad arguments");
+  APTAI_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && ld % (x_bf16 ? 8 : 4) == 0,
+                "colsum: x must be 16-byte aligned with a row pitch that is a multiple of 16 bytes");
+  const int cpb = x_bf16 ? 256 : 128;
+  // enough row slabs to fill the machine a few times over, at least 64 rows each
+  const int col_blocks = (N + cpb - 1) / cpb;
+  long long slabs = (4LL * num_sms() + col_blocks - 1) / col_blocks;
+  if (slabs > (M + 63) / 64) slabs = (M + 63) / 64;
+  if (slabs < 1) slabs = 1;
+  const int rpb = static_cast<int>((M + slabs - 1) / slabs);
+  dim3 grid(col_blocks, static_cast<unsigned>((M + rpb - 1) / rpb));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (x_bf16) colsum_kernel<true><<<grid, 256, 0, st>>>(x, M, N, ld, rpb, scale, out);
   else colsum_kernel<false><<<grid, 256, 0, st>>>(x, M, N, ld, rpb, scale, out);

@@ -225,11 +225,11 @@ def cast_pad(x: torch.Tensor, halo: int) -> torch.Tensor:
     return out
 
 
-def posconv_fold(g: torch.Tensor, v: torch.Tensor, cpad: int = 64) -> torch.Tensor:
+def posconv_fold(g: torch.Tensor, v: torch.Tensor, cpad: int = 64, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """weight_norm(dim=2) fold: g [1,1,taps], v [H, cin, taps] -> bf16 [H, taps*cpad]."""
     _req(g, F32, "g"); _req(v, F32, "v")
     H, cin, taps = v.shape
-    w = torch.empty((H, taps * cpad), dtype=BF16, device=v.device)
+    w = out if out is not None else torch.empty((H, taps * cpad), dtype=BF16, device=v.device)
     ws = torch.empty((taps,), dtype=F32, device=v.device)
     check(_lib.load().aptai_posconv_fold(g.data_ptr(), v.data_ptr(), H, cin, taps, cpad, w.data_ptr(), ws.data_ptr(),
                                          _stream()), "posconv_fold")

@@ -21,6 +21,7 @@ import torch.nn as nn
 from . import ops
 from .backbone import Wav2Vec2Backbone
 from .config import W2V2Config
+from .graphs import GraphCache
 from .train import GradBuffer, GradReducer, attach_backward, broadcast_parameters
 
 
@@ -192,8 +193,18 @@ class Wav2Vec2_PR(nn.Module):
             wav = wav[0]
         wav_input = torch.as_tensor(np.asarray(wav), dtype=torch.float32).reshape(1, -1).to(dev)
         wav_len = torch.tensor([wav_input.shape[1]], dtype=torch.int64, device=dev)
-        _, _, logits = self._logits(wav_input, wav_len)
+        if not self.use_cuda_graphs:
+            return wav_input, self._logits(wav_input, wav_len)[2]
+        cache = getattr(self, "_graph_cache", None)
+        if cache is None:
+            cache = GraphCache()
+            object.__setattr__(self, "_graph_cache", cache)
+        P = self.wav2vec2.plan()
+        (logits,) = cache.run((id(P), P.generation, int(wav_input.shape[1])),
+                              lambda w, l: (self._logits(w, l)[2],), wav_input, wav_len)
         return wav_input, logits
+
+    use_cuda_graphs = True      # single-utterance calls are launch-bound: replay one CUDA graph per input length
 
     def get_ctc_logits(self, wav):
         """models/w2v2_pr.py:170-188."""

@@ -207,3 +207,37 @@ def test_batched_equals_single_large(aptai_large, cuda):
     tv_b, lg_b, _ = aptai_large._heads(wav, torch.tensor(lens, device=cuda))
     tv_s, lg_s, _ = aptai_large._heads(wav[1:2, :24000].contiguous(), torch.tensor([24000], device=cuda))
     assert (lg_b[1, :74] - lg_s[0]).abs().max().item() < 2e-2
+
+
+def test_single_utterance_cuda_graph_replay_is_bit_identical(aptai_large, cuda):
+    """get_aptai_output: call 1 eager, call 2 captures a CUDA graph, later calls replay it — all bit-identical to the
+    eager path, also for a different waveform of the same length and across a weight refresh."""
+    wa = W.waveforms(1, 32000, None, seed=77)[0].numpy()
+    wb = W.waveforms(1, 32000, None, seed=78)[0].numpy()
+    aptai_large.use_cuda_graphs = False
+    ea, eb = aptai_large.get_aptai_output(wa), aptai_large.get_aptai_output(wb)
+    aptai_large.use_cuda_graphs = True
+    if hasattr(aptai_large, "_graph_cache"):
+        aptai_large._graph_cache.clear()
+    for i, (w, e) in enumerate([(wa, ea), (wa, ea), (wb, eb), (wa, ea), (wb, eb)]):
+        r = aptai_large.get_aptai_output(w)
+        assert np.array_equal(r["phn_fc_logits"], e["phn_fc_logits"]), i
+        assert np.array_equal(r["phn_fc_probs"], e["phn_fc_probs"]), i
+        assert np.array_equal(r["phn_fc_pred"], e["phn_fc_pred"]), i
+        assert r["tvs_pred"]["TBCD"] == e["tvs_pred"]["TBCD"], i
+    cache = aptai_large._graph_cache
+    assert any("graph" in v for v in cache._entries.values())
+    # weights change in place (same storage): the captured graph stays valid and sees the new values
+    p = aptai_large.wav2vec2.encoder.layers[3].feed_forward.output_dense.weight
+    with torch.no_grad():
+        old = p.detach().clone()
+        p.mul_(1.5)
+    r2 = aptai_large.get_aptai_output(wa)
+    aptai_large.use_cuda_graphs = False
+    e2 = aptai_large.get_aptai_output(wa)
+    aptai_large.use_cuda_graphs = True
+    assert np.array_equal(r2["phn_fc_logits"], e2["phn_fc_logits"])
+    assert not np.array_equal(r2["phn_fc_logits"], ea["phn_fc_logits"])
+    with torch.no_grad():
+        p.copy_(old)
+    assert np.array_equal(aptai_large.get_aptai_output(wa)["phn_fc_logits"], ea["phn_fc_logits"])
