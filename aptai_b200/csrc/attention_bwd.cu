@@ -28,8 +28,11 @@ constexpr int AB_PT = AB_T * AB_T * 2;    // 32 KB (two [128][64] sub-tiles)
 constexpr int AB_DATA = 2 * AB_TILE /*K,V*/ + 4 * AB_TILE /*Q,dO x2*/ + 2 * AB_PT /*P^T, dS^T*/;   // 160 KB
 constexpr int AB_STATS = 2 * 2 * AB_T * 4;    // [buf][lse | D][128]
 constexpr int AB_SMEM = AB_DATA + AB_STATS + 256;
-constexpr int AB_THREADS = 352;               // warps 0..7 compute, 8 TMA, 9 MMA, 10 TMEM alloc
-constexpr int AB_W_TMA = 8, AB_W_MMA = 9, AB_W_ALLOC = 10;
+// warps 0..7 compute, 8 TMA, 9 MMA (S^T, dP^T), 10 TMEM alloc, 11 / 12 / 13 MMA issuers of dV / dK / dQ: a tcgen05.mma
+// issue costs its thread ~100 cycles while an N=64 MMA is 32 cycles of tensor work, so the 24 phase-2 MMAs of a tile
+// are issued by three threads in parallel instead of one after the other
+constexpr int AB_THREADS = 448;
+constexpr int AB_W_TMA = 8, AB_W_MMA = 9, AB_W_ALLOC = 10, AB_W_DV = 11, AB_W_DK = 12, AB_W_DQ = 13;
 constexpr uint32_t TB_ST = 0, TB_DPT = 128, TB_DK = 256, TB_DV = 320, TB_DQ = 384;
 constexpr float AB_LOG2E = 1.4426950408889634f;
 
@@ -95,12 +98,12 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
     mbar_init(kv_empty, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&qdo_full[i], 1);
-      mbar_init(&qdo_empty[i], 1);
+      mbar_init(&qdo_empty[i], 3);      // dV, dK and dQ issuers have all consumed Q_i / dO_i / P^T / dS^T
     }
     mbar_init(s_full, 1);
     mbar_init(pds_full, 8);
     mbar_init(dq_full, 1);
-    mbar_init(dkv_full, 1);
+    mbar_init(dkv_full, 2);             // dV and dK issuers
     mbar_init(dkv_empty, 8);
     fence_mbar_init();
   }
@@ -135,11 +138,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       }
     }
   } else if (warp == AB_W_MMA) {
+    // ---------------------------------------------------------------- phase 1: S^T = K Q^T, dP^T = V dO^T
     if (lane == 0) {
-      constexpr uint32_t ID_BASE = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(AB_T >> 4) << 24);
-      constexpr uint32_t ID_S = ID_BASE | (static_cast<uint32_t>(AB_T >> 3) << 17);                  // N=128, K-major
-      constexpr uint32_t ID_KV = ID_BASE | (1u << 16) | (static_cast<uint32_t>(AB_D >> 3) << 17);    // N=64, B MN-major
-      constexpr uint32_t ID_Q = ID_KV | (1u << 15);                                                   // A MN-major too
+      constexpr uint32_t ID_S = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(AB_T >> 4) << 24) |
+                                (static_cast<uint32_t>(AB_T >> 3) << 17);                            // N=128, K-major
       uint32_t g = 0, it = 0;
       for (int w = blockIdx.x; w < p.items; w += gridDim.x) {
         const int j = w % p.n_t;
@@ -148,14 +150,13 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         if (j * AB_T >= klen) continue;
         mbar_wait(kv_full, it & 1);
         const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
-        const uint32_t pt_addr = smem_u32(sPT), dst_addr = smem_u32(sDST);
         for (int i = 0; i < p.n_t; ++i, ++g) {
           const uint32_t buf = g & 1;
           const uint32_t q_addr = smem_u32(sQ + buf * AB_TILE), do_addr = smem_u32(sDO + buf * AB_TILE);
           mbar_wait(&qdo_full[buf], (g >> 1) & 1);
+          // the compute warps have finished reading tile g-1's S^T / dP^T once its P^T / dS^T are published
+          if (g > 0) mbar_wait(pds_full, (g - 1) & 1);
           tc_fence_after();
-          // phase 1: S^T = K Q^T, dP^T = V dO^T   (the compute warps finished reading tile g-1's S^T/dP^T before
-          // pds_full(g-1), which this thread waited for below)
 #pragma unroll
           for (int k = 0; k < AB_D / 16; ++k)
             umma_bf16(tmem_base + TB_ST, umma_desc_sw128(k_addr + k * 32), umma_desc_sw128(q_addr + k * 32), ID_S,
@@ -165,31 +166,53 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
             umma_bf16(tmem_base + TB_DPT, umma_desc_sw128(v_addr + k * 32), umma_desc_sw128(do_addr + k * 32), ID_S,
                       k != 0 ? 1u : 0u);
           umma_commit(s_full);
-          // phase 2 needs P^T / dS^T in shared memory
-          mbar_wait(pds_full, g & 1);
-          if (i == 0) mbar_wait(dkv_empty, (it & 1) ^ 1);      // previous item's dK/dV have been read out
+        }
+        ++it;
+      }
+    }
+  } else if (warp == AB_W_DV || warp == AB_W_DK || warp == AB_W_DQ) {
+    // ---------------------------------------------------------------- phase 2: dV += P^T dO | dK += dS^T Q | dQ = dS K
+    if (lane == 0) {
+      constexpr uint32_t ID_BASE = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(AB_T >> 4) << 24);
+      constexpr uint32_t ID_KV = ID_BASE | (1u << 16) | (static_cast<uint32_t>(AB_D >> 3) << 17);    // N=64, B MN-major
+      constexpr uint32_t ID_Q = ID_KV | (1u << 15);                                                   // A MN-major too
+      uint32_t g = 0, it = 0;
+      for (int w = blockIdx.x; w < p.items; w += gridDim.x) {
+        const int j = w % p.n_t;
+        const int b = (w / p.n_t) / p.heads;
+        const int klen = max(1, min(__ldg(p.key_len + b), p.T));
+        if (j * AB_T >= klen) continue;
+        mbar_wait(kv_full, it & 1);
+        const uint32_t k_addr = smem_u32(sK);
+        const uint32_t pt_addr = smem_u32(sPT), dst_addr = smem_u32(sDST);
+        for (int i = 0; i < p.n_t; ++i, ++g) {
+          const uint32_t buf = g & 1;
+          const uint32_t q_addr = smem_u32(sQ + buf * AB_TILE), do_addr = smem_u32(sDO + buf * AB_TILE);
+          mbar_wait(&qdo_full[buf], (g >> 1) & 1);
+          mbar_wait(pds_full, g & 1);                          // P^T / dS^T of this tile are in shared memory
+          if (i == 0 && warp != AB_W_DQ) mbar_wait(dkv_empty, (it & 1) ^ 1);   // previous item's dK/dV were read out
           tc_fence_after();
+          if (warp == AB_W_DV) {
 #pragma unroll
-          for (int k = 0; k < AB_T / 16; ++k) {
-            const uint32_t a_off = (k >> 2) * (AB_PT / 2) + (k & 3) * 32;
-            umma_bf16(tmem_base + TB_DV, umma_desc_sw128(pt_addr + a_off), ab_desc_mn(do_addr + k * 2048, 1024), ID_KV,
-                      (i | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < AB_T / 16; ++k)
+              umma_bf16(tmem_base + TB_DV, umma_desc_sw128(pt_addr + (k >> 2) * (AB_PT / 2) + (k & 3) * 32),
+                        ab_desc_mn(do_addr + k * 2048, 1024), ID_KV, (i | k) != 0 ? 1u : 0u);
+          } else if (warp == AB_W_DK) {
+#pragma unroll
+            for (int k = 0; k < AB_T / 16; ++k)
+              umma_bf16(tmem_base + TB_DK, umma_desc_sw128(dst_addr + (k >> 2) * (AB_PT / 2) + (k & 3) * 32),
+                        ab_desc_mn(q_addr + k * 2048, 1024), ID_KV, (i | k) != 0 ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < AB_T / 16; ++k)
+              umma_bf16(tmem_base + TB_DQ, ab_desc_mn(dst_addr + k * 2048, AB_PT / 2),
+                        ab_desc_mn(k_addr + k * 2048, 1024), ID_Q, k != 0 ? 1u : 0u);
+            umma_commit(dq_full);
           }
-#pragma unroll
-          for (int k = 0; k < AB_T / 16; ++k) {
-            const uint32_t a_off = (k >> 2) * (AB_PT / 2) + (k & 3) * 32;
-            umma_bf16(tmem_base + TB_DK, umma_desc_sw128(dst_addr + a_off), ab_desc_mn(q_addr + k * 2048, 1024), ID_KV,
-                      (i | k) != 0 ? 1u : 0u);
-          }
-#pragma unroll
-          for (int k = 0; k < AB_T / 16; ++k)
-            umma_bf16(tmem_base + TB_DQ, ab_desc_mn(dst_addr + k * 2048, AB_PT / 2), ab_desc_mn(k_addr + k * 2048, 1024),
-                      ID_Q, k != 0 ? 1u : 0u);
           umma_commit(&qdo_empty[buf]);
-          umma_commit(dq_full);
           if (i == p.n_t - 1) {
-            umma_commit(dkv_full);
-            umma_commit(kv_empty);
+            if (warp != AB_W_DQ) umma_commit(dkv_full);
+            else umma_commit(kv_empty);        // S^T / dP^T of the last tile completed long before (s_full)
           }
         }
         ++it;
@@ -233,6 +256,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         }
         named_bar_sync(1, 256);
         mbar_wait(s_full, g & 1);
+        // P^T / dS^T of tile g-1 have been consumed by all three phase-2 issuers
+        if (g > 0) mbar_wait(&qdo_empty[(g - 1) & 1], ((g - 1) >> 1) & 1);
         tc_fence_after();
         uint8_t* pt_row = sPT + hf * (AB_PT / 2) + row * 128;
         uint8_t* ds_row = sDST + hf * (AB_PT / 2) + row * 128;

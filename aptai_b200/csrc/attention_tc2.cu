@@ -1,0 +1,409 @@
+// tcgen05 / TMEM fused attention forward, second generation: TWO 128-query tiles per CTA ping-pong on one K/V stream.
+//
+// The first-generation kernel (attention_tc.cu) is latency-bound per key tile: its eight softmax warps walk the chain
+// tcgen05.ld -> row max -> exp2 -> P store -> proxy fence -> mbarrier in lock step, so an SM only ever has two such
+// chains (two CTAs) in flight and the tensor pipe idles ~75 % of the time.  Here a work item is
+// 256 query rows of one (utterance, head):
+//   warp 8       TMA producer    Q0, Q1 once per item; (K_j, V_j) tiles of 64 keys through a 2-stage ring, shared by
+//                                both query tiles (half the K/V traffic per query)
+//   warp 9       MMA issuer 1    S_t = Q_t K_j^T for t = 0, 1      (TMEM: one 64-column S buffer per query tile)
+//   warp 10      MMA issuer 2    O_t += P_t V_j                    (TMEM: one 64-column O accumulator per query tile)
+//   warps 0..3   softmax group 0 one thread per query row of tile 0 (all 64 keys of the key tile: no cross-thread max)
+//   warps 4..7   softmax group 1 the same for tile 1
+// The two groups run independent chains, so with two CTAs per SM four chains overlap: while one group waits for its
+// next S tile, the others keep the MUFU and the tensor pipe busy.  S is read from TMEM twice (max pass, exp pass)
+// instead of being held in 64 registers, which keeps the kernel at two CTAs per SM.
+// Same contract as aptai_attention_fwd: q pre-scaled by head_dim^-0.5, every query row computed, keys >= key_len[b]
+// masked, lazy rescaling of O (threshold 2^8), optional log2-domain lse output for the backward pass.
+#include "common.h"
+#include "ptx.cuh"
+
+#include <stdlib.h>
+
+namespace aptai {
+
+constexpr int A2_Q = 128;                 // rows per query tile
+constexpr int A2_K = 64;                  // keys per key tile
+constexpr int A2_D = 64;
+constexpr int A2_THREADS = 384;           // warps 0..3 / 4..7 softmax groups, 8 TMA, 9 S-MMA, 10 PV-MMA, 11 TMEM alloc
+constexpr int A2_W_TMA = 8, A2_W_S = 9, A2_W_PV = 10, A2_W_ALLOC = 11;
+constexpr int A2_QB = A2_Q * A2_D * 2;    // 16 KB per Q tile
+constexpr int A2_KVB = A2_K * A2_D * 2;   // 8 KB per K or V tile
+constexpr int A2_PB = A2_Q * A2_K * 2;    // 16 KB per P tile
+constexpr int A2_STAGES = 2;
+constexpr int A2_DATA = 2 * A2_QB + A2_STAGES * 2 * A2_KVB + 2 * A2_PB;   // 96 KB
+constexpr int A2_SMEM = A2_DATA + 256;
+constexpr uint32_t A2_TS = 0, A2_TO = 128, A2_TCOLS = 256;   // S_t at t*64, O_t at 128 + t*64
+constexpr float A2_LOG2E = 1.4426950408889634f;
+constexpr float A2_RESCALE = 8.0f;
+
+struct Attn2Params {
+  const int* key_len;
+  __nv_bfloat16* ctx;
+  float* lse;
+  int B, T, heads, H, n_qp, items;
+};
+
+__device__ __forceinline__ float a2_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ uint64_t a2_desc_mn(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1024 >> 4) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+__device__ __forceinline__ void a2_tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+      "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+      "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(A2_THREADS, 2)
+attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                     const Attn2Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sQ = smem;                                   // [2 tiles]
+  uint8_t* sKV = smem + 2 * A2_QB;                      // [stage][K | V]
+  uint8_t* sP = sKV + A2_STAGES * 2 * A2_KVB;           // [2 tiles]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + A2_DATA);
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("aptai attention v2: dynamic shared memory base is not 1024-byte aligned\n");
+    __trap();
+  }
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* kv_full = bars + 2;     // [2]
+  uint64_t* kv_empty = bars + 4;    // [2]
+  uint64_t* s_full = bars + 6;      // [2] per query tile
+  uint64_t* p_full = bars + 8;      // [2] P_t written (and S_t consumed)
+  uint64_t* p_empty = bars + 10;    // [2] P_t V_j complete
+  uint64_t* o_full = bars + 12;     // [2]
+  uint64_t* o_empty = bars + 14;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == A2_W_TMA && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+  }
+  if (warp == A2_W_S && lane == 0) {
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&p_empty[i], 1);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&o_empty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == A2_W_ALLOC) tmem_alloc(tmem_slot, A2_TCOLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == A2_W_TMA) {
+    // ---------------------------------------------------------------- TMA producer
+    if (lane == 0) {
+      uint32_t g = 0, it = 0;
+      for (int w = blockIdx.x; w < p.items; w += gridDim.x, ++it) {
+        const int qp = w % p.n_qp;
+        const int bh = w / p.n_qp;
+        const int h = bh % p.heads, b = bh / p.heads;
+        const int klen = max(1, min(__ldg(p.key_len + b), p.T));
+        const int n = (klen + A2_K - 1) / A2_K;
+        const int row0 = b * p.T;
+        const bool two = qp * 2 * A2_Q + A2_Q < p.T;
+        mbar_wait_backoff(q_empty, (it & 1) ^ 1, 100);
+        mbar_expect_tx(q_full, two ? 2 * A2_QB : A2_QB);
+        tma_load_2d(&tmQ, q_full, sQ, h * A2_D, row0 + qp * 2 * A2_Q);
+        if (two) tma_load_2d(&tmQ, q_full, sQ + A2_QB, h * A2_D, row0 + qp * 2 * A2_Q + A2_Q);
+        for (int j = 0; j < n; ++j, ++g) {
+          const uint32_t st = g % A2_STAGES, u = g / A2_STAGES;
+          mbar_wait_backoff(&kv_empty[st], (u & 1) ^ 1, 100);
+          mbar_expect_tx(&kv_full[st], 2 * A2_KVB);
+          tma_load_2d(&tmKV, &kv_full[st], sKV + st * 2 * A2_KVB, p.H + h * A2_D, row0 + j * A2_K);
+          tma_load_2d(&tmKV, &kv_full[st], sKV + st * 2 * A2_KVB + A2_KVB, 2 * p.H + h * A2_D, row0 + j * A2_K);
+        }
+      }
+    }
+  } else if (warp == A2_W_S) {
+    // ---------------------------------------------------------------- MMA issuer 1: S_t = Q_t K_j^T
+    if (lane == 0) {
+      constexpr uint32_t IDESC_BASE = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(A2_Q >> 4) << 24);
+      uint32_t g = 0, it = 0;
+      uint32_t gt[2] = {0, 0};         // key tiles processed so far by each query tile (barrier phases)
+      for (int w = blockIdx.x; w < p.items; w += gridDim.x, ++it) {
+        const int qp = w % p.n_qp;
+        const int b = (w / p.n_qp) / p.heads;
+        const int klen = max(1, min(__ldg(p.key_len + b), p.T));
+        const int n = (klen + A2_K - 1) / A2_K;
+        const int nt = (qp * 2 * A2_Q + A2_Q < p.T) ? 2 : 1;
+        mbar_wait(q_full, it & 1);
+        for (int j = 0; j < n; ++j, ++g) {
+          const uint32_t st = g % A2_STAGES;
+          const int nj = min(A2_K, ((klen - j * A2_K) + 15) & ~15);
+          const uint32_t idesc = IDESC_BASE | (static_cast<uint32_t>(nj >> 3) << 17);
+          mbar_wait(&kv_full[st], (g / A2_STAGES) & 1);
+          const uint32_t k_addr = smem_u32(sKV + st * 2 * A2_KVB);
+          for (int t = 0; t < nt; ++t) {
+            // S_t is free once the softmax group has consumed the previous key tile (P written)
+            if (gt[t] >= 1) mbar_wait_backoff(&p_full[t], (gt[t] - 1) & 1, 32);
+            tc_fence_after();
+            const uint32_t q_addr = smem_u32(sQ + t * A2_QB);
+#pragma unroll
+            for (int k = 0; k < A2_D / 16; ++k)
+              umma_bf16(tmem_base + A2_TS + t * A2_K, umma_desc_sw128(q_addr + k * 32),
+                        umma_desc_sw128(k_addr + k * 32), idesc, k != 0 ? 1u : 0u);
+            umma_commit(&s_full[t]);
+            ++gt[t];
+          }
+          if (j == n - 1) umma_commit(q_empty);
+        }
+      }
+    }
+  } else if (warp == A2_W_PV) {
+    // ---------------------------------------------------------------- MMA issuer 2: O_t += P_t V_j
+    if (lane == 0) {
+      constexpr uint32_t IDESC_PV = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(A2_Q >> 4) << 24) |
+                                    (1u << 16) | (static_cast<uint32_t>(A2_D >> 3) << 17);   // B MN-major, N=64
+      uint32_t g = 0;
+      uint32_t gt[2] = {0, 0}, itt[2] = {0, 0};
+      for (int w = blockIdx.x; w < p.items; w += gridDim.x) {
+        const int qp = w % p.n_qp;
+        const int b = (w / p.n_qp) / p.heads;
+        const int klen = max(1, min(__ldg(p.key_len + b), p.T));
+        const int n = (klen + A2_K - 1) / A2_K;
+        const int nt = (qp * 2 * A2_Q + A2_Q < p.T) ? 2 : 1;
+        for (int j = 0; j < n; ++j, ++g) {
+          const uint32_t st = g % A2_STAGES;
+          const int nj = min(A2_K, ((klen - j * A2_K) + 15) & ~15);
+          mbar_wait(&kv_full[st], (g / A2_STAGES) & 1);
+          const uint32_t v_addr = smem_u32(sKV + st * 2 * A2_KVB + A2_KVB);
+          for (int t = 0; t < nt; ++t) {
+            mbar_wait_backoff(&p_full[t], gt[t] & 1, 32);
+            if (j == 0) mbar_wait(&o_empty[t], (itt[t] & 1) ^ 1);      // previous item's O_t has been read out
+            tc_fence_after();
+            const uint32_t p_addr = smem_u32(sP + t * A2_PB);
+            for (int k = 0; k < nj / 16; ++k)
+              umma_bf16(tmem_base + A2_TO + t * A2_D, umma_desc_sw128(p_addr + k * 32), a2_desc_mn(v_addr + k * 2048),
+                        IDESC_PV, (j | k) != 0 ? 1u : 0u);
+            umma_commit(&p_empty[t]);
+            if (j == n - 1) {
+              umma_commit(&o_full[t]);
+              ++itt[t];
+            }
+            ++gt[t];
+          }
+          umma_commit(&kv_empty[st]);      // K_j: both S_t(j) completed before their P_t(j) existed
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // ---------------------------------------------------------------- softmax groups: thread = one query row
+    const int t = warp >> 2;                       // query tile of this group
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16);
+    const uint32_t ts = t_lane + A2_TS + t * A2_K, to = t_lane + A2_TO + t * A2_D;
+    uint8_t* prow = sP + t * A2_PB + row * 128;
+    uint32_t g = 0, it = 0;                         // this tile's own counters
+    for (int w = blockIdx.x; w < p.items; w += gridDim.x) {
+      const int qp = w % p.n_qp;
+      const int bh = w / p.n_qp;
+      const int h = bh % p.heads, b = bh / p.heads;
+      if (t == 1 && !(qp * 2 * A2_Q + A2_Q < p.T)) continue;      // second tile lies beyond the utterance
+      const int klen = max(1, min(__ldg(p.key_len + b), p.T));
+      const int n = (klen + A2_K - 1) / A2_K;
+      float m_used = -INFINITY, l = 0.f;
+      for (int j = 0; j < n; ++j, ++g) {
+        const int valid = min(A2_K, klen - j * A2_K);            // keys of this tile that exist (>= 1)
+        mbar_wait(&s_full[t], g & 1);
+        tc_fence_after();
+        // pass 1: row maximum over the valid keys
+        float mx;
+        {
+          uint32_t r[32];
+          tmem_ld32(ts, r);
+          tmem_ld_wait();
+          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+          if (valid >= 32) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              m0 = fmaxf(m0, __uint_as_float(r[i]));     m1 = fmaxf(m1, __uint_as_float(r[i + 1]));
+              m2 = fmaxf(m2, __uint_as_float(r[i + 2])); m3 = fmaxf(m3, __uint_as_float(r[i + 3]));
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < valid) m0 = fmaxf(m0, __uint_as_float(r[i]));
+          }
+          if (valid > 32) {
+            tmem_ld32(ts + 32, r);
+            tmem_ld_wait();
+            if (valid >= 64) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                m0 = fmaxf(m0, __uint_as_float(r[i]));     m1 = fmaxf(m1, __uint_as_float(r[i + 1]));
+                m2 = fmaxf(m2, __uint_as_float(r[i + 2])); m3 = fmaxf(m3, __uint_as_float(r[i + 3]));
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (32 + i < valid) m0 = fmaxf(m0, __uint_as_float(r[i]));
+            }
+          }
+          mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * A2_LOG2E;
+        }
+        float factor = 1.f;
+        if (mx > m_used + A2_RESCALE) {
+          factor = exp2f(m_used - mx);            // 0 on the first tile (m_used = -inf)
+          m_used = mx;
+        }
+        // P_t (and O_t for a rescale) are free once P_t(j-1) V_(j-1) has completed
+        if (g >= 1) mbar_wait(&p_empty[t], (g - 1) & 1);
+        const bool need = (factor != 1.f) && (j > 0);
+        if (__any_sync(0xffffffffu, need)) {
+          tc_fence_after();
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint32_t r[32];
+            tmem_ld32(to + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * factor);
+            a2_tmem_st32(to + c * 32, r);
+          }
+        }
+        l *= factor;
+        // pass 2: p = exp2(s*log2e - m_used) -> bf16 -> shared memory (K-major SWIZZLE_128B), row sum
+        const int ncol16 = (valid + 15) >> 4;
+        float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (c * 32 < valid) {
+            uint32_t r[32];
+            tmem_ld32(ts + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int u8 = 0; u8 < 4; ++u8) {
+              float pv[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                pv[i] = a2_ex2(fmaf(__uint_as_float(r[u8 * 8 + i]), A2_LOG2E, -m_used));
+                if (c * 32 + u8 * 8 + i >= valid) pv[i] = 0.f;
+              }
+              rs0 += pv[0] + pv[4]; rs1 += pv[1] + pv[5]; rs2 += pv[2] + pv[6]; rs3 += pv[3] + pv[7];
+              const int unit = c * 4 + u8;
+              if ((unit >> 1) < ncol16)
+                *reinterpret_cast<uint4*>(prow + ((unit ^ (row & 7)) << 4)) =
+                    make_uint4(pack_bf16(pv[0], pv[1]), pack_bf16(pv[2], pv[3]), pack_bf16(pv[4], pv[5]),
+                               pack_bf16(pv[6], pv[7]));
+            }
+          }
+        }
+        l += (rs0 + rs1) + (rs2 + rs3);
+        tc_fence_before();
+        fence_async_proxy();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+      }
+      // ---- output: O_t / l -> bf16, lse
+      mbar_wait(&o_full[t], it & 1);
+      tc_fence_after();
+      const int qrow = qp * 2 * A2_Q + t * A2_Q + row;
+      const float inv = 1.f / l;
+      if (p.lse != nullptr && qrow < p.T)
+        p.lse[(static_cast<long long>(b) * p.heads + h) * p.T + qrow] = m_used + log2f(l);
+      __nv_bfloat16* out = p.ctx + (static_cast<long long>(b) * p.T + qrow) * p.H + h * A2_D;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t r[32];
+        tmem_ld32(to + c * 32, r);
+        tmem_ld_wait();
+        if (qrow < p.T) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8)
+            *reinterpret_cast<uint4*>(out + c * 32 + i) =
+                make_uint4(pack_bf16(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv),
+                           pack_bf16(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv),
+                           pack_bf16(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv),
+                           pack_bf16(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_empty[t]);
+      ++it;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == A2_W_ALLOC) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, A2_TCOLS);
+  }
+}
+
+}  // namespace aptai
+
+using namespace aptai;
+
+extern "C" int aptai_attention_fwd_v2(const void* qkv, void* ctx, float* lse, const int32_t* key_len, int B, int T,
+                                      int heads, void* stream) {
+  if (int rc = check_arch()) return rc;
+  APTAI_REQUIRE(qkv && ctx && key_len, "attention_v2: null pointer");
+  APTAI_REQUIRE(B >= 1 && T >= 1 && heads >= 1, "attention_v2: bad shape");
+  APTAI_REQUIRE((reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(ctx) & 15) == 0,
+                "attention_v2: buffers must be 16-byte aligned");
+  const int H = heads * A2_D;
+  CUtensorMap tmq, tmkv;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(3) * H, static_cast<uint64_t>(B) * T};
+    uint64_t strides[1] = {static_cast<uint64_t>(3) * H * 2};
+    uint32_t boxq[2] = {A2_D, A2_Q};
+    uint32_t boxkv[2] = {A2_D, A2_K};
+    if (int rc = encode_tmap_bf16(&tmq, qkv, 2, dims, strides, boxq, 1)) return rc;
+    if (int rc = encode_tmap_bf16(&tmkv, qkv, 2, dims, strides, boxkv, 1)) return rc;
+  }
+  Attn2Params p;
+  p.key_len = key_len;
+  p.ctx = reinterpret_cast<__nv_bfloat16*>(ctx);
+  p.lse = lse;
+  p.B = B; p.T = T; p.heads = heads; p.H = H;
+  p.n_qp = (T + 2 * A2_Q - 1) / (2 * A2_Q);
+  p.items = B * heads * p.n_qp;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaError_t e = cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM);
+    if (e != cudaSuccess) {
+      set_error("attention_v2: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    attr_set = true;
+  }
+  const int slots = 2 * num_sms();
+  const int grid = p.items < slots ? p.items : slots;
+  attention_tc2_kernel<<<grid, A2_THREADS, A2_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tmq, tmkv, p);
+  return after_launch("attention_tc2");
+}

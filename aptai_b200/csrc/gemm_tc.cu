@@ -350,22 +350,31 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
 #pragma unroll
             for (int i = 0; i < CH; i += 2) gelu_erf2(v[i], v[i + 1]);
           } else if (p.act == 2) {
-            // dgrad through the GELU: v *= gelu'(u), u = the forward's pre-activation (bf16, row-per-thread loads:
-            // every 64-byte segment is used completely)
-            if (valid_row) {
-              const uint4* up = reinterpret_cast<const uint4*>(p.aux + out_off + n0);
+            // dgrad through the GELU: v *= gelu'(u), u = the forward's pre-activation (bf16).  The 32x32 block of u is
+            // fetched as whole 64-byte row segments (4 lanes per row, 8 rows per instruction) and transposed through
+            // the warp's staging buffer, mirroring store16
+            uint4* sb = reinterpret_cast<uint4*>(stg);
+            const int bu = lane & 3;
 #pragma unroll
-              for (int i = 0; i < CH; i += 8) {
-                const uint4 u4 = __ldg(up + i / 8);
-                const uint32_t uw[4] = {u4.x, u4.y, u4.z, u4.w};
+            for (int i = 0; i < 4; ++i) {
+              const int rr = i * 8 + ((lane >> 2) & 1) * 4 + (lane >> 3);
+              uint4 x = make_uint4(0u, 0u, 0u, 0u);
+              if (r_first + rr < p.rows_per_seg)
+                x = __ldg(reinterpret_cast<const uint4*>(p.aux + off0 + rr * p.ldo + bu * 8));
+              sb[rr * 8 + (bu ^ (rr & 7))] = x;
+            }
+            __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float2 uf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uw[j]));
-                  v[i + 2 * j] *= gelu_erf_grad(uf.x);
-                  v[i + 2 * j + 1] *= gelu_erf_grad(uf.y);
-                }
+            for (int u = 0; u < 4; ++u) {
+              const uint4 u4 = sb[lane * 8 + (u ^ (lane & 7))];
+              const uint32_t uw[4] = {u4.x, u4.y, u4.z, u4.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 uf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uw[j]));
+                gelu_erf_grad2_mul(v[8 * u + 2 * j], v[8 * u + 2 * j + 1], uf.x, uf.y);
               }
             }
+            __syncwarp();
           }
           if (p.residual) {
 #pragma unroll

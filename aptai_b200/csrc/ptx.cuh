@@ -331,6 +331,32 @@ __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
   x1 = x1 > 0.f ? x1 - r1 : r1;
 }
 
+// Two GELU derivatives at once on the packed fp32x2 pipe: g0 *= gelu'(u0), g1 *= gelu'(u1)
+__device__ __forceinline__ void gelu_erf_grad2_mul(float& g0, float& g1, float u0, float u1) {
+  const uint64_t x = f32x2_pack(u0, u1);
+  const uint64_t ax = f32x2_pack(fabsf(u0), fabsf(u1));
+  float d0, d1, t0, t1, e0, e1, a0, a1;
+  f32x2_unpack(f32x2_fma(ax, f32x2_pack(0.3275911f * 0.70710678118654752440f, 0.3275911f * 0.70710678118654752440f),
+                         f32x2_pack(1.0f, 1.0f)), d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  f32x2_unpack(f32x2_mul(f32x2_mul(x, x), f32x2_pack(-0.5f * 1.4426950408889634f, -0.5f * 1.4426950408889634f)), a0, a1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+  const uint64_t t = f32x2_pack(t0, t1);
+  const uint64_t e = f32x2_pack(e0, e1);
+  uint64_t p = f32x2_fma(t, f32x2_pack(0.5f * 1.061405429f, 0.5f * 1.061405429f),
+                         f32x2_pack(0.5f * -1.453152027f, 0.5f * -1.453152027f));
+  p = f32x2_fma(t, p, f32x2_pack(0.5f * 1.421413741f, 0.5f * 1.421413741f));
+  p = f32x2_fma(t, p, f32x2_pack(0.5f * -0.284496736f, 0.5f * -0.284496736f));
+  p = f32x2_fma(t, p, f32x2_pack(0.5f * 0.254829592f, 0.5f * 0.254829592f));
+  float h0, h1;
+  f32x2_unpack(f32x2_mul(f32x2_mul(t, p), e), h0, h1);      // 0.5 * erfc(|x| / sqrt(2)) = 1 - Phi(|x|)
+  const uint64_t cdf = f32x2_pack(u0 > 0.f ? 1.0f - h0 : h0, u1 > 0.f ? 1.0f - h1 : h1);
+  const uint64_t d = f32x2_fma(f32x2_mul(x, e), f32x2_pack(0.3989422804014327f, 0.3989422804014327f), cdf);
+  f32x2_unpack(f32x2_mul(f32x2_pack(g0, g1), d), g0, g1);
+}
+
 __device__ __forceinline__ uint32_t pack_f16(float a, float b) {
   __half2 v = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -4,6 +4,7 @@ owns every buffer), launch on torch's current CUDA stream.  No arithmetic happen
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -236,9 +237,12 @@ def posconv_fold(g: torch.Tensor, v: torch.Tensor, cpad: int = 64, out: Optional
     return w
 
 
+ATTENTION_IMPL = int(os.environ.get("APTAI_ATTN_IMPL", "1"))   # 1: attention_tc.cu, 2: attention_tc2.cu (q-tile pairs)
+
+
 def attention(qkv: torch.Tensor, key_len: Optional[torch.Tensor], B: int, T: int, heads: int,
-              out: Optional[torch.Tensor] = None, legacy_mma: bool = False, lse: Optional[torch.Tensor] = None
-              ) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, legacy_mma: bool = False, lse: Optional[torch.Tensor] = None,
+              impl: Optional[int] = None) -> torch.Tensor:
     _req(qkv, BF16, "qkv")
     H = heads * 64
     assert qkv.numel() == B * T * 3 * H
@@ -250,6 +254,11 @@ def attention(qkv: torch.Tensor, key_len: Optional[torch.Tensor], B: int, T: int
     if lse is not None:
         _req(lse, F32, "lse")
         assert lse.numel() == B * heads * T
+    if (impl or ATTENTION_IMPL) == 2 and not legacy_mma:
+        check(_lib.load().aptai_attention_fwd_v2(qkv.data_ptr(), out.data_ptr(), _ptr(lse), key_len.data_ptr(), B, T,
+                                                 heads, _stream()), "attention_fwd_v2")
+        return out
+    if lse is not None:
         check(_lib.load().aptai_attention_fwd_lse(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), key_len.data_ptr(),
                                                   B, T, heads, _stream()), "attention_fwd_lse")
         return out

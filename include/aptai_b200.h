@@ -114,6 +114,10 @@ int aptai_posconv_fold(const float* g, const float* v, int H, int cin, int taps,
  * Keys t >= key_len[b] are masked; every query row is computed (padded queries attend to valid keys, HF:438-463).
  */
 int aptai_attention_fwd(const void* qkv, void* ctx, const int32_t* key_len, int B, int T, int heads, void* stream);
+/* second-generation tcgen05 kernel, same contract (+ optional lse, may be NULL): two 128-query tiles per CTA share one
+ * K/V stream and run independent softmax chains (csrc/attention_tc2.cu) */
+int aptai_attention_fwd_v2(const void* qkv, void* ctx, float* lse, const int32_t* key_len, int B, int T, int heads,
+                           void* stream);
 /* same contract on the legacy mma.sync tensor path; A/B baseline for profiles/, not used by the product path */
 int aptai_attention_fwd_mma(const void* qkv, void* ctx, const int32_t* key_len, int B, int T, int heads, void* stream);
 

@@ -67,10 +67,11 @@ def test_layernorm(cuda, cols, in_bf16):
     torch.testing.assert_close(o16.float(), ref.bfloat16().float(), atol=2e-2, rtol=1e-2)
 
 
-@pytest.mark.parametrize("legacy", [False, True])
+@pytest.mark.parametrize("legacy", [False, True, "v2"])
 @pytest.mark.parametrize("B,T,heads,lens,scale", [(2, 199, 16, [199, 150], 1.0), (3, 64, 12, [64, 1, 33], 1.0),
                                                   (1, 999, 4, [999], 1.0), (2, 130, 2, [70, 130], 1.0),
-                                                  (40, 399, 16, None, 0.5), (2, 513, 2, [513, 400], 3.0)])
+                                                  (40, 399, 16, None, 0.5), (2, 513, 2, [513, 400], 3.0),
+                                                  (3, 257, 2, [257, 256, 129], 1.0), (2, 128, 2, [128, 127], 1.0)])
 def test_attention(cuda, B, T, heads, lens, scale, legacy):
     H = heads * 64
     qkv = _rand((B * T, 3 * H), cuda, scale, 9).bfloat16()
@@ -79,13 +80,20 @@ def test_attention(cuda, B, T, heads, lens, scale, legacy):
     if scale > 1.0:
         qkv[T // 2:, H: 2 * H] *= 4.0          # later keys score much higher: exercises the lazy O rescale
     kl = torch.tensor(lens, dtype=torch.int32, device=cuda)
-    ctx = ops.attention(qkv, kl, B, T, heads, legacy_mma=legacy)
+    lse = None
+    if legacy == "v2":
+        lse = torch.empty((B, heads, T), dtype=torch.float32, device=cuda)
+        ctx = ops.attention(qkv, kl, B, T, heads, impl=2, lse=lse)
+    else:
+        ctx = ops.attention(qkv, kl, B, T, heads, legacy_mma=legacy, impl=1)
     q, k, v = qkv.float().view(B, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
     s = q @ k.transpose(-1, -2)                      # q is expected pre-scaled
     mask = torch.arange(T, device=cuda)[None, :] < kl[:, None]
     s = s.masked_fill(~mask[:, None, None, :], float("-inf"))
     ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * T, H)
     torch.testing.assert_close(ctx.float(), ref, atol=2e-2, rtol=2e-2)
+    if lse is not None:
+        torch.testing.assert_close(lse, torch.logsumexp(s, -1) * 1.4426950408889634, atol=2e-2, rtol=1e-3)
 
 
 def test_heads_lowpass_losses(cuda):
