@@ -8,6 +8,8 @@
 //                                both query tiles (half the K/V traffic per query)
 //   warp 9       MMA issuer 1    S_t = Q_t K_j^T for t = 0, 1      (TMEM: one 64-column S buffer per query tile)
 //   warp 10      MMA issuer 2    O_t += P_t V_j                    (TMEM: one 64-column O accumulator per query tile)
+//                (a single issuer per query tile doing both S_t and O_t measured 5 % slower: the ~100-cycle issue
+//                 cost of each tcgen05.mma makes two parallel issuing threads worth more than decoupled tiles)
 //   warps 0..3   softmax group 0 one thread per query row of tile 0 (all 64 keys of the key tile: no cross-thread max)
 //   warps 4..7   softmax group 1 the same for tile 1
 // The two groups run independent chains, so with two CTAs per SM four chains overlap: while one group waits for its
@@ -71,6 +73,55 @@ __device__ __forceinline__ void a2_tmem_st32(uint32_t taddr, const uint32_t (&r)
       "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// exp pass over one FULL 64-key tile of one query row: p = exp2(s*log2e - m_used) -> bf16 -> shared memory (K-major
+// SWIZZLE_128B), row sum, optionally the raw row maximum.  TMEM is read in four 16-column chunks, the load of chunk
+// c+1 in flight while chunk c is processed; packed fp32x2 math (FFMA2 / FADD2) for the exponent argument and the sum.
+template <bool TRACK_MAX>
+__device__ __forceinline__ void a2_exp_tile_full(uint32_t ts, float m_used, uint8_t* prow, int row, float& rowsum,
+                                                 float& rawmax) {
+  const uint64_t l2e = f32x2_pack(A2_LOG2E, A2_LOG2E), nm = f32x2_pack(-m_used, -m_used);
+  uint64_t acc0 = f32x2_pack(0.f, 0.f), acc1 = acc0;
+  float m0 = -INFINITY, m1 = -INFINITY;
+  uint32_t ra[16], rb[16];
+  auto process = [&](const uint32_t (&r)[16], int chunk) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      uint32_t wv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float s0 = __uint_as_float(r[u * 8 + 2 * i]), s1 = __uint_as_float(r[u * 8 + 2 * i + 1]);
+        if (TRACK_MAX) {
+          if (i & 1) m1 = fmaxf(fmaxf(m1, s0), s1);
+          else m0 = fmaxf(fmaxf(m0, s0), s1);
+        }
+        float a0, a1;
+        f32x2_unpack(f32x2_fma(f32x2_pack(s0, s1), l2e, nm), a0, a1);
+        const float p0 = a2_ex2(a0), p1 = a2_ex2(a1);
+        if (i & 1) acc1 = f32x2_add(acc1, f32x2_pack(p0, p1));
+        else acc0 = f32x2_add(acc0, f32x2_pack(p0, p1));
+        wv[i] = pack_bf16(p0, p1);
+      }
+      *reinterpret_cast<uint4*>(prow + (((chunk * 2 + u) ^ (row & 7)) << 4)) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+    }
+  };
+  tmem_ld16(ts, ra);
+  tmem_ld_wait();
+  tmem_ld16(ts + 16, rb);
+  process(ra, 0);
+  tmem_ld_wait();
+  tmem_ld16(ts + 32, ra);
+  process(rb, 1);
+  tmem_ld_wait();
+  tmem_ld16(ts + 48, rb);
+  process(ra, 2);
+  tmem_ld_wait();
+  process(rb, 3);
+  float r0, r1;
+  f32x2_unpack(f32x2_add(acc0, acc1), r0, r1);
+  rowsum = r0 + r1;
+  rawmax = fmaxf(m0, m1);
 }
 
 __global__ void __launch_bounds__(A2_THREADS, 2)
@@ -165,17 +216,27 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const uint32_t idesc = IDESC_BASE | (static_cast<uint32_t>(nj >> 3) << 17);
           mbar_wait(&kv_full[st], (g / A2_STAGES) & 1);
           const uint32_t k_addr = smem_u32(sKV + st * 2 * A2_KVB);
-          for (int t = 0; t < nt; ++t) {
-            // S_t is free once the softmax group has consumed the previous key tile (P written)
-            if (gt[t] >= 1) mbar_wait_backoff(&p_full[t], (gt[t] - 1) & 1, 32);
-            tc_fence_after();
-            const uint32_t q_addr = smem_u32(sQ + t * A2_QB);
+          // serve whichever query tile is ready first: S_t is free once its softmax group has consumed the previous
+          // key tile (P_t written); the two groups drift apart, a fixed order would make one wait for the other
+          uint32_t pending = nt == 2 ? 3u : 1u, spins = 0;
+          while (pending) {
+            for (int t = 0; t < nt; ++t) {
+              if (!(pending & (1u << t))) continue;
+              if (gt[t] >= 1 && !mbar_try_wait(&p_full[t], (gt[t] - 1) & 1)) continue;
+              tc_fence_after();
+              const uint32_t q_addr = smem_u32(sQ + t * A2_QB);
 #pragma unroll
-            for (int k = 0; k < A2_D / 16; ++k)
-              umma_bf16(tmem_base + A2_TS + t * A2_K, umma_desc_sw128(q_addr + k * 32),
-                        umma_desc_sw128(k_addr + k * 32), idesc, k != 0 ? 1u : 0u);
-            umma_commit(&s_full[t]);
-            ++gt[t];
+              for (int k = 0; k < A2_D / 16; ++k)
+                umma_bf16(tmem_base + A2_TS + t * A2_K, umma_desc_sw128(q_addr + k * 32),
+                          umma_desc_sw128(k_addr + k * 32), idesc, k != 0 ? 1u : 0u);
+              umma_commit(&s_full[t]);
+              ++gt[t];
+              pending &= ~(1u << t);
+            }
+            if (++spins > APTAI_SPIN_LIMIT) {
+              printf("aptai attention v2: S issuer timed out (block %d)\n", (int)blockIdx.x);
+              __trap();
+            }
           }
           if (j == n - 1) umma_commit(q_empty);
         }
@@ -199,20 +260,29 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           const int nj = min(A2_K, ((klen - j * A2_K) + 15) & ~15);
           mbar_wait(&kv_full[st], (g / A2_STAGES) & 1);
           const uint32_t v_addr = smem_u32(sKV + st * 2 * A2_KVB + A2_KVB);
-          for (int t = 0; t < nt; ++t) {
-            mbar_wait_backoff(&p_full[t], gt[t] & 1, 32);
-            if (j == 0) mbar_wait(&o_empty[t], (itt[t] & 1) ^ 1);      // previous item's O_t has been read out
-            tc_fence_after();
-            const uint32_t p_addr = smem_u32(sP + t * A2_PB);
-            for (int k = 0; k < nj / 16; ++k)
-              umma_bf16(tmem_base + A2_TO + t * A2_D, umma_desc_sw128(p_addr + k * 32), a2_desc_mn(v_addr + k * 2048),
-                        IDESC_PV, (j | k) != 0 ? 1u : 0u);
-            umma_commit(&p_empty[t]);
-            if (j == n - 1) {
-              umma_commit(&o_full[t]);
-              ++itt[t];
+          uint32_t pending = nt == 2 ? 3u : 1u, spins = 0;
+          while (pending) {
+            for (int t = 0; t < nt; ++t) {
+              if (!(pending & (1u << t))) continue;
+              if (!mbar_try_wait(&p_full[t], gt[t] & 1)) continue;
+              if (j == 0) mbar_wait(&o_empty[t], (itt[t] & 1) ^ 1);      // previous item's O_t has been read out
+              tc_fence_after();
+              const uint32_t p_addr = smem_u32(sP + t * A2_PB);
+              for (int k = 0; k < nj / 16; ++k)
+                umma_bf16(tmem_base + A2_TO + t * A2_D, umma_desc_sw128(p_addr + k * 32),
+                          a2_desc_mn(v_addr + k * 2048), IDESC_PV, (j | k) != 0 ? 1u : 0u);
+              umma_commit(&p_empty[t]);
+              if (j == n - 1) {
+                umma_commit(&o_full[t]);
+                ++itt[t];
+              }
+              ++gt[t];
+              pending &= ~(1u << t);
             }
-            ++gt[t];
+            if (++spins > APTAI_SPIN_LIMIT) {
+              printf("aptai attention v2: PV issuer timed out (block %d)\n", (int)blockIdx.x);
+              __trap();
+            }
           }
           umma_commit(&kv_empty[st]);      // K_j: both S_t(j) completed before their P_t(j) existed
         }
@@ -235,41 +305,58 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const int klen = max(1, min(__ldg(p.key_len + b), p.T));
       const int n = (klen + A2_K - 1) / A2_K;
       float m_used = -INFINITY, l = 0.f;
+      // a warp whose 32 query rows all lie beyond the utterance only keeps the barrier protocol going: its P rows stay
+      // stale, the matching O rows are never written
+      const bool warp_live = qp * 2 * A2_Q + t * A2_Q + q4 * 32 < p.T;
       for (int j = 0; j < n; ++j, ++g) {
         const int valid = min(A2_K, klen - j * A2_K);            // keys of this tile that exist (>= 1)
         mbar_wait(&s_full[t], g & 1);
+        if (!warp_live) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[t]);
+          continue;
+        }
         tc_fence_after();
+        // Steady state (full key tile, not the first of the item): ONE pass with the stale maximum — exp, P store and
+        // row sum while tracking the true maximum; it stands unless some row of the warp outgrew the lazy-rescale
+        // threshold (rare), in which case the tile is redone below with the new maximum.
+        bool done = false;
+        if (valid >= A2_K && j > 0) {
+          mbar_wait(&p_empty[t], (g - 1) & 1);           // P_t free: P_t(j-1) V_(j-1) has completed
+          float rsum, rmax;
+          a2_exp_tile_full<true>(ts, m_used, prow, row, rsum, rmax);
+          if (!__any_sync(0xffffffffu, rmax * A2_LOG2E > m_used + A2_RESCALE)) {
+            l += rsum;
+            done = true;
+          }
+        }
+        if (!done) {
         // pass 1: row maximum over the valid keys
         float mx;
         {
           uint32_t r[32];
-          tmem_ld32(ts, r);
-          tmem_ld_wait();
           float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-          if (valid >= 32) {
+          if (valid >= A2_K) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              m0 = fmaxf(m0, __uint_as_float(r[i]));     m1 = fmaxf(m1, __uint_as_float(r[i + 1]));
-              m2 = fmaxf(m2, __uint_as_float(r[i + 2])); m3 = fmaxf(m3, __uint_as_float(r[i + 3]));
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i < valid) m0 = fmaxf(m0, __uint_as_float(r[i]));
-          }
-          if (valid > 32) {
-            tmem_ld32(ts + 32, r);
-            tmem_ld_wait();
-            if (valid >= 64) {
+            for (int c = 0; c < 2; ++c) {
+              tmem_ld32(ts + c * 32, r);
+              tmem_ld_wait();
 #pragma unroll
               for (int i = 0; i < 32; i += 4) {
                 m0 = fmaxf(m0, __uint_as_float(r[i]));     m1 = fmaxf(m1, __uint_as_float(r[i + 1]));
                 m2 = fmaxf(m2, __uint_as_float(r[i + 2])); m3 = fmaxf(m3, __uint_as_float(r[i + 3]));
               }
-            } else {
+            }
+          } else {
 #pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (32 + i < valid) m0 = fmaxf(m0, __uint_as_float(r[i]));
+            for (int c = 0; c < 2; ++c) {
+              if (c * 32 < valid) {
+                tmem_ld32(ts + c * 32, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  if (c * 32 + i < valid) m0 = fmaxf(m0, __uint_as_float(r[i]));
+              }
             }
           }
           mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * A2_LOG2E;
@@ -295,33 +382,40 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           }
         }
         l *= factor;
-        // pass 2: p = exp2(s*log2e - m_used) -> bf16 -> shared memory (K-major SWIZZLE_128B), row sum
-        const int ncol16 = (valid + 15) >> 4;
+        // pass 2: p = exp2(s*log2e - m_used) -> bf16 -> shared memory (K-major SWIZZLE_128B), row sum.
+        // Full key tiles (all but the last of an utterance) take the path without per-element masking.
         float rs0 = 0.f, rs1 = 0.f, rs2 = 0.f, rs3 = 0.f;
+        if (valid >= A2_K) {
+          float rmax_unused;
+          a2_exp_tile_full<false>(ts, m_used, prow, row, rs0, rmax_unused);
+        } else {
+          const int ncol16 = (valid + 15) >> 4;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          if (c * 32 < valid) {
-            uint32_t r[32];
-            tmem_ld32(ts + c * 32, r);
-            tmem_ld_wait();
+          for (int c = 0; c < 2; ++c) {
+            if (c * 32 < valid) {
+              uint32_t r[32];
+              tmem_ld32(ts + c * 32, r);
+              tmem_ld_wait();
 #pragma unroll
-            for (int u8 = 0; u8 < 4; ++u8) {
-              float pv[8];
+              for (int u8 = 0; u8 < 4; ++u8) {
+                float pv[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                pv[i] = a2_ex2(fmaf(__uint_as_float(r[u8 * 8 + i]), A2_LOG2E, -m_used));
-                if (c * 32 + u8 * 8 + i >= valid) pv[i] = 0.f;
+                for (int i = 0; i < 8; ++i) {
+                  pv[i] = a2_ex2(fmaf(__uint_as_float(r[u8 * 8 + i]), A2_LOG2E, -m_used));
+                  if (c * 32 + u8 * 8 + i >= valid) pv[i] = 0.f;
+                }
+                rs0 += pv[0] + pv[4]; rs1 += pv[1] + pv[5]; rs2 += pv[2] + pv[6]; rs3 += pv[3] + pv[7];
+                const int unit = c * 4 + u8;
+                if ((unit >> 1) < ncol16)
+                  *reinterpret_cast<uint4*>(prow + ((unit ^ (row & 7)) << 4)) =
+                      make_uint4(pack_bf16(pv[0], pv[1]), pack_bf16(pv[2], pv[3]), pack_bf16(pv[4], pv[5]),
+                                 pack_bf16(pv[6], pv[7]));
               }
-              rs0 += pv[0] + pv[4]; rs1 += pv[1] + pv[5]; rs2 += pv[2] + pv[6]; rs3 += pv[3] + pv[7];
-              const int unit = c * 4 + u8;
-              if ((unit >> 1) < ncol16)
-                *reinterpret_cast<uint4*>(prow + ((unit ^ (row & 7)) << 4)) =
-                    make_uint4(pack_bf16(pv[0], pv[1]), pack_bf16(pv[2], pv[3]), pack_bf16(pv[4], pv[5]),
-                               pack_bf16(pv[6], pv[7]));
             }
           }
         }
         l += (rs0 + rs1) + (rs2 + rs3);
+        }   // !done
         tc_fence_before();
         fence_async_proxy();
         __syncwarp();

@@ -237,7 +237,9 @@ def posconv_fold(g: torch.Tensor, v: torch.Tensor, cpad: int = 64, out: Optional
     return w
 
 
-ATTENTION_IMPL = int(os.environ.get("APTAI_ATTN_IMPL", "1"))   # 1: attention_tc.cu, 2: attention_tc2.cu (q-tile pairs)
+# 0: by shape (attention_tc2.cu's query-tile pairs when an utterance has more than one 128-query tile, else
+# attention_tc.cu's two threads per row), 1 / 2: force one kernel (A/B runs in profiles/attn_bench.py)
+ATTENTION_IMPL = int(os.environ.get("APTAI_ATTN_IMPL", "0"))
 
 
 def attention(qkv: torch.Tensor, key_len: Optional[torch.Tensor], B: int, T: int, heads: int,
@@ -254,7 +256,8 @@ def attention(qkv: torch.Tensor, key_len: Optional[torch.Tensor], B: int, T: int
     if lse is not None:
         _req(lse, F32, "lse")
         assert lse.numel() == B * heads * T
-    if (impl or ATTENTION_IMPL) == 2 and not legacy_mma:
+    which = impl or ATTENTION_IMPL or (2 if T > 128 else 1)
+    if which == 2 and not legacy_mma:
         check(_lib.load().aptai_attention_fwd_v2(qkv.data_ptr(), out.data_ptr(), _ptr(lse), key_len.data_ptr(), B, T,
                                                  heads, _stream()), "attention_fwd_v2")
         return out
