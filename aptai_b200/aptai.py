@@ -86,9 +86,8 @@ class APTAI(nn.Module):
         return gb
 
     def _forward_train(self, audio_inputs, audio_lengths, phn_targets, tv_targets):
-        """Training step forward: same kernels, activations kept; `loss.backward()` launches the backward kernels."""
-        if self.tv_head[0].p > 0 or self.phn_head[0].p > 0:
-            raise NotImplementedError("aptai_b200: head dropout is not built in the training path; use tv_drop=phn_drop=0")
+        """Training step forward: same kernels, activations kept; `loss.backward()` launches the backward kernels.
+        Head dropouts (models/aptai.py:44,52) are counter-based like the backbone's (regenerated in the backward)."""
         w2v = self.wav2vec2
         dev = next(w2v.parameters()).device
         wav = audio_inputs.to(device=dev, dtype=torch.float32).contiguous()
@@ -98,10 +97,18 @@ class APTAI(nn.Module):
         last, sv = w2v.encode_train(wav, flen)
         B, T, H = last.shape
         h = last.view(B * T, H)
+        p_tv, p_phn = float(self.tv_head[0].p), float(self.phn_head[0].p)
+        s_tv, s_phn = w2v.drop_seed(sv.step, -1, w2v.SITE_HEAD_A), w2v.drop_seed(sv.step, -1, w2v.SITE_HEAD_B)
+        h_tv = ops.dropout(h, p_tv, s_tv, want_f32=True)[0] if p_tv > 0 else h
+        h_phn = ops.dropout(h, p_phn, s_phn, want_f32=True)[0] if p_phn > 0 else h
         tvl, phl = self.tv_head[2], self.phn_head[2]
         f = lambda p: p.detach().float().contiguous()
         wa, ba, wb, bb = f(tvl.weight), f(tvl.bias), f(phl.weight), f(phl.bias)
-        tv_raw, logits, pred = ops.heads(h, wa, ba, ops.ACT_TANH, wb, bb, ops.ACT_LEAKY)
+        if h_tv is h_phn:
+            tv_raw, logits, pred = ops.heads(h, wa, ba, ops.ACT_TANH, wb, bb, ops.ACT_LEAKY)
+        else:
+            tv_raw, _, _ = ops.heads(h_tv, wa, ba, ops.ACT_TANH, None, None, 0, want_argmax=False)
+            _, logits, pred = ops.heads(h_phn, None, None, 0, wb, bb, ops.ACT_LEAKY)
         tv = self.tv_lowpass(tv_raw.view(B, T, 9))
         taps = self.tv_lowpass.lowpass.weight.detach().reshape(-1).contiguous()
         tvt = tv_targets.view(B * T, 9)
@@ -111,8 +118,17 @@ class APTAI(nn.Module):
             gs = grad_out.detach().reshape(1).to(device=dev, dtype=torch.float32)
             d_tvlp, d_lg = ops.masked_mse_ce_bwd(tv.view(B * T, 9), tvt, logits, phn_targets, ws, gs)
             d_tv = ops.lowpass(d_tvlp.view(B, T, 9), taps).view(B * T, 9)   # symmetric FIR: adjoint = the filter
-            dh = ops.heads_bwd(h, d_tv, wa, ops.ACT_TANH, gb.view("tv_head.2.weight"), gb.view("tv_head.2.bias"),
-                               d_lg, wb, ops.ACT_LEAKY, gb.view("phn_head.2.weight"), gb.view("phn_head.2.bias"))
+            if h_tv is h_phn:
+                dh = ops.heads_bwd(h, d_tv, wa, ops.ACT_TANH, gb.view("tv_head.2.weight"), gb.view("tv_head.2.bias"),
+                                   d_lg, wb, ops.ACT_LEAKY, gb.view("phn_head.2.weight"), gb.view("phn_head.2.bias"))
+            else:
+                dh_a = ops.heads_bwd(h_tv, d_tv, wa, ops.ACT_TANH, gb.view("tv_head.2.weight"),
+                                     gb.view("tv_head.2.bias"), None, None, 0, None, None)
+                dh_b = ops.heads_bwd(h_phn, None, None, 0, None, None, d_lg, wb, ops.ACT_LEAKY,
+                                     gb.view("phn_head.2.weight"), gb.view("phn_head.2.bias"))
+                if p_tv > 0:
+                    ops.dropout(dh_a, p_tv, s_tv, out_f32=dh_a)
+                dh = ops.dropout(dh_b, p_phn, s_phn, residual=dh_a, out_f32=dh_b)[0]      # p = 0: a plain add
             red = getattr(self, "_reducer", None)
             w2v.backward(sv, dh, gb, prefix="wav2vec2.", on_layer_done=red.layer_done if red else None)
             if red is not None:

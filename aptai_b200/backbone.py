@@ -325,20 +325,31 @@ class Wav2Vec2Backbone(nn.Module):
 
     def check_trainable(self):
         cfg = self.cfg
-        if cfg.apply_spec_augment or cfg.layerdrop > 0 or any(
-                getattr(cfg, k, 0.0) > 0 for k in ("hidden_dropout", "attention_dropout", "activation_dropout",
-                                                    "feat_proj_dropout")):
-            raise NotImplementedError("aptai_b200: the stochastic regularisers (SpecAugment / LayerDrop / dropout) of "
-                                      "the training path are not built; set them to 0 or call .eval()")
+        if getattr(cfg, "attention_dropout", 0.0) > 0:
+            raise NotImplementedError("aptai_b200: attention_dropout (dropout on the attention probabilities inside the "
+                                      "fused attention kernels) is not built; set attention_dropout=0")
         if any(p.requires_grad for p in self.feature_extractor.parameters()):
             raise NotImplementedError("aptai_b200: the backward of the conv feature encoder is not built; call "
                                       "freeze_feature_encoder() (the reference's default, models/aptai.py:39-40)")
+
+    # Stochastic regularisers of the training path.  Dropout is counter-based (csrc/dropout.cu): a site's mask is a
+    # function of (seed, element index), the seed of (training step, layer, site), so the backward regenerates it.
+    SITE_ATTN, SITE_ACT, SITE_FFN, SITE_PROJ, SITE_ENC, SITE_HEAD_A, SITE_HEAD_B = range(7)
+
+    def drop_seed(self, step: int, layer: int, site: int) -> int:
+        base = getattr(self, "_drop_base", None)
+        if base is None:
+            base = int(torch.initial_seed()) & 0xFFFFFFFF          # torch.manual_seed() controls the masks
+            object.__setattr__(self, "_drop_base", base)
+        return ((base * 1000003 + step) << 12) | ((layer + 1) << 4) | site
 
     # ---- training: forward that keeps activations, and the backward --------------------------------------------
     @torch.no_grad()
     def encode_train(self, wav: torch.Tensor, frame_lens: torch.Tensor):
         """Same arithmetic as `encode` (the feature projection runs on bf16 instead of fp16 operands so that its
-        wgrad shares the bf16 kernel).  Returns (last_hidden fp32 [B,T,H], saved activations)."""
+        wgrad shares the bf16 kernel), plus the training-mode regularisers: feat_proj / hidden / activation dropout
+        (HF:434,546,570,603-607,647-653,694,766), LayerDrop (HF:701-706,773-778: `torch.rand([])` per layer, the same
+        host RNG stream HF consumes) and SpecAugment (HF:1280-1324).  Returns (last_hidden fp32 [B,T,H], saved)."""
         self.check_trainable()
         cfg = self.cfg
         P = TP = self.train_plan()
@@ -351,11 +362,27 @@ class Wav2Vec2Backbone(nn.Module):
         M, H = B * T, cfg.hidden_size
         eps, heads = cfg.layer_norm_eps, cfg.num_attention_heads
         taps, groups = cfg.num_conv_pos_embeddings, cfg.num_conv_pos_embedding_groups
-        sv = SimpleNamespace(B=B, T=T, frame_lens=frame_lens, layers=[])
+        step = getattr(self, "_drop_step", 0) + 1
+        object.__setattr__(self, "_drop_step", step)
+        p_h, p_a, p_fp = float(cfg.hidden_dropout), float(cfg.activation_dropout), float(cfg.feat_proj_dropout)
+        seed = lambda layer, site: self.drop_seed(step, layer, site)
+        sv = SimpleNamespace(B=B, T=T, frame_lens=frame_lens, layers=[], step=step, p_h=p_h, p_a=p_a, p_fp=p_fp,
+                             spec_rows=None, skipped=[])
         sv.y32 = y.view(M, -1).float()
         _, sv.xn = ops.layernorm(sv.y32, P.fp_ln_w, P.fp_ln_b, eps)
         h0, _ = ops.linear(sv.xn, TP.fp_w_bf16, P.fp_b, want_f32=True, want_bf16=False, seg_rows=T,
                            seg_valid_rows=frame_lens)
+        if p_fp > 0:
+            ops.dropout(h0, p_fp, seed(-1, self.SITE_PROJ), out_f32=h0)
+        if cfg.apply_spec_augment and cfg.mask_time_prob > 0:
+            from .specaug import compute_mask_indices
+            mask = compute_mask_indices((B, T), cfg.mask_time_prob, cfg.mask_time_length,
+                                        frame_lens=frame_lens.cpu().numpy(), min_masks=cfg.mask_time_min_masks)
+            rows = torch.from_numpy(mask.reshape(-1).nonzero()[0].astype("int64")).to(wav.device)
+            if rows.numel():
+                # hidden_states[mask] = masked_spec_embed (HF:1303): an indexed row copy
+                h0.index_copy_(0, rows, self.masked_spec_embed.detach().float().expand(rows.numel(), H))
+                sv.spec_rows = rows
         sv.hp = ops.cast_pad(h0.view(B, T, H), taps // 2)
         sv.pos_pre = torch.empty((M, H), dtype=BF16, device=wav.device)
         h = torch.empty_like(h0)
@@ -368,19 +395,37 @@ class Wav2Vec2Backbone(nn.Module):
             ctx = ops.attention(qkv, frame_lens, B, T, heads, lse=lse)
             return qkv, ctx, lse
 
-        def ffn1(x):
+        def ffn1(x, li):
             u = torch.empty((M, F_), dtype=BF16, device=wav.device)
             _, g = ops.linear(x, lw.ff1_w, lw.ff1_b, act=1, out_pre=u)
+            if p_a > 0:
+                ops.dropout(g, p_a, seed(li, self.SITE_ACT), out_bf16=g)
             return u, g
 
+        def proj_res(a, w, b_, res, li, site):
+            """res + dropout(a @ w^T + b)"""
+            if p_h > 0:
+                tmp, _ = ops.linear(a, w, b_, want_f32=True, want_bf16=False)
+                return ops.dropout(tmp, p_h, seed(li, site), residual=res, out_f32=tmp)[0]
+            return ops.linear(a, w, b_, residual=res, want_f32=True, want_bf16=False)[0]
+
+        def skip_layer():          # HF:701-706 / 773-778
+            return bool(torch.rand([]) < cfg.layerdrop) if cfg.layerdrop > 0 else False
+
         if cfg.do_stable_layer_norm:
-            for lw in P.layers:
+            if p_h > 0:
+                ops.dropout(h, p_h, seed(-1, self.SITE_ENC), out_f32=h)
+            for li, lw in enumerate(P.layers):
+                if skip_layer():
+                    sv.layers.append(None)
+                    sv.skipped.append(li)
+                    continue
                 _, x1 = ops.layernorm(h, lw.ln1_w, lw.ln1_b, eps)
                 qkv, ctx, lse = attn(x1)
-                hm, _ = ops.linear(ctx, lw.o_w, lw.o_b, residual=h, want_f32=True, want_bf16=False)
+                hm = proj_res(ctx, lw.o_w, lw.o_b, h, li, self.SITE_ATTN)
                 _, x2 = ops.layernorm(hm, lw.ln2_w, lw.ln2_b, eps)
-                u, g = ffn1(x2)
-                hn, _ = ops.linear(g, lw.ff2_w, lw.ff2_b, residual=hm, want_f32=True, want_bf16=False)
+                u, g = ffn1(x2, li)
+                hn = proj_res(g, lw.ff2_w, lw.ff2_b, hm, li, self.SITE_FFN)
                 sv.layers.append(SimpleNamespace(h_in=h, x1=x1, qkv=qkv, ctx=ctx, lse=lse, h_mid=hm, x2=x2, u=u, g=g))
                 h = hn
             sv.h_final_in = h
@@ -388,16 +433,23 @@ class Wav2Vec2Backbone(nn.Module):
         else:
             sv.h_enc_in = h
             h, x = ops.layernorm(h, P.enc_ln_w, P.enc_ln_b, eps, want_f32=True, want_bf16=True)
-            for lw in P.layers:
+            if p_h > 0:
+                ops.dropout(h, p_h, seed(-1, self.SITE_ENC), out_f32=h, out_bf16=x)
+            for li, lw in enumerate(P.layers):
+                if skip_layer():
+                    sv.layers.append(None)
+                    sv.skipped.append(li)
+                    continue
                 qkv, ctx, lse = attn(x)
-                t, _ = ops.linear(ctx, lw.o_w, lw.o_b, residual=h, want_f32=True, want_bf16=False)
+                t = proj_res(ctx, lw.o_w, lw.o_b, h, li, self.SITE_ATTN)
                 h1, x1 = ops.layernorm(t, lw.ln1_w, lw.ln1_b, eps, want_f32=True, want_bf16=True)
-                u, g = ffn1(x1)
-                t2, _ = ops.linear(g, lw.ff2_w, lw.ff2_b, residual=h1, want_f32=True, want_bf16=False)
+                u, g = ffn1(x1, li)
+                t2 = proj_res(g, lw.ff2_w, lw.ff2_b, h1, li, self.SITE_FFN)
                 h2, x2 = ops.layernorm(t2, lw.ln2_w, lw.ln2_b, eps, want_f32=True, want_bf16=True)
                 sv.layers.append(SimpleNamespace(x_in=x, qkv=qkv, ctx=ctx, lse=lse, t=t, x1=x1, u=u, g=g, t2=t2))
                 h, x = h2, x2
             last = h
+        object.__setattr__(self, "_last_regularisers", dict(step=step, skipped=list(sv.skipped), spec_rows=sv.spec_rows))
         return last.view(B, T, H), sv
 
     @torch.no_grad()
@@ -412,12 +464,30 @@ class Wav2Vec2Backbone(nn.Module):
         eps, heads = cfg.layer_norm_eps, cfg.num_attention_heads
         taps, groups = cfg.num_conv_pos_embeddings, cfg.num_conv_pos_embedding_groups
         q_scale = float(cfg.head_dim) ** -0.5
+        p_h, p_a, p_fp = sv.p_h, sv.p_a, sv.p_fp
+        seed = lambda layer, site: self.drop_seed(sv.step, layer, site)
         G = lambda name: gb.view(prefix + name)
         d_last = d_last.reshape(M, H).contiguous()
 
         def lin_grads(dy_b, x_b, name):
             ops.wgrad(dy_b, x_b, G(name + ".weight"))
             ops.colsum(dy_b, G(name + ".bias"))
+
+        def masked16(d32, d16, li, site):
+            """bf16 gradient w.r.t. the input of a hidden-dropout site (same mask as the forward)."""
+            if p_h > 0:
+                return ops.dropout(d32, p_h, seed(li, site), want_bf16=True)[1]
+            return d16
+
+        def ffn_block(i, s, lt, dy_b, x_in_b):
+            """FFN2 wgrad/dgrad (through activation dropout and the GELU) and FFN1 wgrad; returns du (bf16)."""
+            base = f"encoder.layers.{i}.feed_forward."
+            lin_grads(dy_b, s.g, base + "output_dense")
+            _, du = ops.linear(dy_b, lt.ff2_wt, None, act=2, aux=s.u)
+            if p_a > 0:
+                ops.dropout(du, p_a, seed(i, self.SITE_ACT), out_bf16=du)
+            lin_grads(du, x_in_b, base + "intermediate_dense")
+            return du
 
         def attn_block(i, s, lt, dctx_src_b, x_in_b):
             """out-proj dgrad -> attention backward -> fused QKV wgrad; returns dqkv."""
@@ -437,40 +507,42 @@ class Wav2Vec2Backbone(nn.Module):
                                           dbeta=G("encoder.layer_norm.bias"), want_bf16=True)
             for i in range(nl - 1, -1, -1):
                 s, lw, lt = sv.layers[i], P.layers[i], TP.layers[i]
-                base = f"encoder.layers.{i}."
-                lin_grads(dhb, s.g, base + "feed_forward.output_dense")
-                _, du = ops.linear(dhb, lt.ff2_wt, None, act=2, aux=s.u)
-                lin_grads(du, s.x2, base + "feed_forward.intermediate_dense")
-                dx2, _ = ops.linear(du, lt.ff1_wt, None, want_f32=True, want_bf16=False)
-                dhm32, dhmb = ops.layernorm_bwd(dx2, s.h_mid, lw.ln2_w, eps, dres=dh32,
-                                                dgamma=G(base + "final_layer_norm.weight"),
-                                                dbeta=G(base + "final_layer_norm.bias"), want_bf16=True)
-                dqkv = attn_block(i, s, lt, dhmb, s.x1)
-                dx1, _ = ops.linear(dqkv, lt.qkv_wt, None, want_f32=True, want_bf16=False)
-                dh32, dhb = ops.layernorm_bwd(dx1, s.h_in, lw.ln1_w, eps, dres=dhm32,
-                                              dgamma=G(base + "layer_norm.weight"), dbeta=G(base + "layer_norm.bias"),
-                                              want_bf16=True)
-                sv.layers[i] = None
+                if s is not None:            # None: the layer was dropped by LayerDrop (identity)
+                    base = f"encoder.layers.{i}."
+                    du = ffn_block(i, s, lt, masked16(dh32, dhb, i, self.SITE_FFN), s.x2)
+                    dx2, _ = ops.linear(du, lt.ff1_wt, None, want_f32=True, want_bf16=False)
+                    dhm32, dhmb = ops.layernorm_bwd(dx2, s.h_mid, lw.ln2_w, eps, dres=dh32,
+                                                    dgamma=G(base + "final_layer_norm.weight"),
+                                                    dbeta=G(base + "final_layer_norm.bias"), want_bf16=True)
+                    dqkv = attn_block(i, s, lt, masked16(dhm32, dhmb, i, self.SITE_ATTN), s.x1)
+                    dx1, _ = ops.linear(dqkv, lt.qkv_wt, None, want_f32=True, want_bf16=False)
+                    dh32, dhb = ops.layernorm_bwd(dx1, s.h_in, lw.ln1_w, eps, dres=dhm32,
+                                                  dgamma=G(base + "layer_norm.weight"),
+                                                  dbeta=G(base + "layer_norm.bias"), want_bf16=True)
+                    sv.layers[i] = None
                 if on_layer_done is not None:
                     on_layer_done(i)
+            if p_h > 0:
+                ops.dropout(dh32, p_h, seed(-1, self.SITE_ENC), out_f32=dh32)
         else:
             dh32 = d_last
             for i in range(nl - 1, -1, -1):
                 s, lw, lt = sv.layers[i], P.layers[i], TP.layers[i]
-                base = f"encoder.layers.{i}."
-                dt2, dt2b = ops.layernorm_bwd(dh32, s.t2, lw.ln2_w, eps, dgamma=G(base + "final_layer_norm.weight"),
-                                              dbeta=G(base + "final_layer_norm.bias"), want_bf16=True)
-                lin_grads(dt2b, s.g, base + "feed_forward.output_dense")
-                _, du = ops.linear(dt2b, lt.ff2_wt, None, act=2, aux=s.u)
-                lin_grads(du, s.x1, base + "feed_forward.intermediate_dense")
-                dh1, _ = ops.linear(du, lt.ff1_wt, None, residual=dt2, want_f32=True, want_bf16=False)
-                dt, dtb = ops.layernorm_bwd(dh1, s.t, lw.ln1_w, eps, dgamma=G(base + "layer_norm.weight"),
-                                            dbeta=G(base + "layer_norm.bias"), want_bf16=True)
-                dqkv = attn_block(i, s, lt, dtb, s.x_in)
-                dh32, _ = ops.linear(dqkv, lt.qkv_wt, None, residual=dt, want_f32=True, want_bf16=False)
-                sv.layers[i] = None
+                if s is not None:
+                    base = f"encoder.layers.{i}."
+                    dt2, dt2b = ops.layernorm_bwd(dh32, s.t2, lw.ln2_w, eps, dgamma=G(base + "final_layer_norm.weight"),
+                                                  dbeta=G(base + "final_layer_norm.bias"), want_bf16=True)
+                    du = ffn_block(i, s, lt, masked16(dt2, dt2b, i, self.SITE_FFN), s.x1)
+                    dh1, _ = ops.linear(du, lt.ff1_wt, None, residual=dt2, want_f32=True, want_bf16=False)
+                    dt, dtb = ops.layernorm_bwd(dh1, s.t, lw.ln1_w, eps, dgamma=G(base + "layer_norm.weight"),
+                                                dbeta=G(base + "layer_norm.bias"), want_bf16=True)
+                    dqkv = attn_block(i, s, lt, masked16(dt, dtb, i, self.SITE_ATTN), s.x_in)
+                    dh32, _ = ops.linear(dqkv, lt.qkv_wt, None, residual=dt, want_f32=True, want_bf16=False)
+                    sv.layers[i] = None
                 if on_layer_done is not None:
                     on_layer_done(i)
+            if p_h > 0:
+                ops.dropout(dh32, p_h, seed(-1, self.SITE_ENC), out_f32=dh32)
             dh32, _ = ops.layernorm_bwd(dh32, sv.h_enc_in, P.enc_ln_w, eps, dgamma=G("encoder.layer_norm.weight"),
                                         dbeta=G("encoder.layer_norm.bias"))
         # positional conv: h1 = h0 + gelu(conv(h0) + b)
@@ -485,6 +557,13 @@ class Wav2Vec2Backbone(nn.Module):
         dh0 = torch.empty_like(dh32)
         ops.posconv(dpre_pad, TP.pos_wt, None, dh32, T, H, groups, taps, dh0, act=0, row_shift=1,
                     seg_valid_rows=flen)       # padded frames were zeroed after the projection (HF:678,754)
+        if sv.spec_rows is not None:
+            # SpecAugment rows were overwritten by masked_spec_embed: their gradient goes to it, not to the projection
+            sel = dh0.index_select(0, sv.spec_rows)
+            ops.colsum(sel, G("masked_spec_embed"))
+            dh0.index_fill_(0, sv.spec_rows, 0.0)
+        if p_fp > 0:
+            ops.dropout(dh0, p_fp, seed(-1, self.SITE_PROJ), out_f32=dh0)
         # feature projection + its LayerNorm (the conv encoder below is frozen)
         dh0b = ops.scale_cast_bf16(dh0)
         lin_grads(dh0b, sv.xn, "feature_projection.projection")
@@ -551,9 +630,9 @@ class Wav2Vec2Backbone(nn.Module):
     def forward(self, input_values, attention_mask=None, output_hidden_states=False, return_dict=True, **_):
         """HF-compatible call.  `attention_mask` is what the reference passes: `lengths[:, None]`, a (B,1) tensor
         of sample counts (models/aptai.py:77; the cumsum trick of HF:1031), or a (B,L) 0/1 mask, or None."""
-        if self.training and (self.cfg.apply_spec_augment or self.cfg.layerdrop > 0):
-            raise NotImplementedError("aptai_b200: the training-mode stochastic path (SpecAugment/LayerDrop/dropout)"
-                                      " and backward kernels are not built yet; call .eval()")
+        if self.training and torch.is_grad_enabled():
+            raise RuntimeError("aptai_b200: Wav2Vec2Backbone.forward is the inference path; training goes through the "
+                               "drop-in modules (APTAI / Wav2Vec2_PR .forward in train mode -> encode_train/backward)")
         if not input_values.is_cuda:
             raise RuntimeError("aptai_b200: input_values must be on a CUDA (sm_100) device; there is no CPU path")
         wav = input_values.to(F32).contiguous()

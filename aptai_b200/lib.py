@@ -90,6 +90,7 @@ PROTOTYPES = {
                                 c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "aptai_masked_mse_ce_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p,
                                         c_void_p, c_void_p, c_void_p]),
+    "aptai_dropout": (c_int, [c_void_p, c_int, c_void_p, c_i64, c_float, C.c_uint64, c_void_p, c_void_p, c_void_p]),
     "aptai_prepare_weights": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "aptai_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                 c_float, c_float, c_float, c_float, c_float, c_int, c_float, c_void_p]),

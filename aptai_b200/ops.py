@@ -553,3 +553,20 @@ def bilstm_256(x: torch.Tensor, lstm: "torch.nn.LSTM", lens: torch.Tensor) -> to
 def prepare_weights(table: torch.Tensor, n_entries: int, total_tiles: int) -> None:
     """Launch the multi-tensor weight preparation over a device table of `aptai_prep_entry` rows."""
     check(_lib.load().aptai_prepare_weights(table.data_ptr(), n_entries, total_tiles, _stream()), "prepare_weights")
+
+
+def dropout(x: torch.Tensor, p: float, seed: int, *, residual: Optional[torch.Tensor] = None, want_f32: bool = False,
+            want_bf16: bool = False, out_f32: Optional[torch.Tensor] = None, out_bf16: Optional[torch.Tensor] = None):
+    """Counter-based inverted dropout: residual + keep(seed, i) * x / (1 - p).  x fp32 or bf16; returns (fp32 | None,
+    bf16 | None).  In place when an output is x itself.  The backward of a site = the same call on the gradient."""
+    if not x.is_cuda or x.dtype not in (F32, BF16) or not x.is_contiguous():
+        raise TypeError("dropout: x must be a contiguous CUDA fp32/bf16 tensor")
+    if want_f32 and out_f32 is None:
+        out_f32 = torch.empty(x.shape, dtype=F32, device=x.device)
+    if want_bf16 and out_bf16 is None:
+        out_bf16 = torch.empty(x.shape, dtype=BF16, device=x.device)
+    if residual is not None:
+        _req(residual, F32, "residual")
+    check(_lib.load().aptai_dropout(x.data_ptr(), int(x.dtype == BF16), _ptr(residual), x.numel(), float(p),
+                                    int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(out_f32), _ptr(out_bf16), _stream()), "dropout")
+    return out_f32, out_bf16

@@ -100,15 +100,17 @@ class Wav2Vec2_PR(nn.Module):
         train = self.training and torch.is_grad_enabled()
         sv = None
         if train:
-            if self.dropout.p > 0:
-                raise NotImplementedError("aptai_b200: final_dropout is not built in the training path; set it to 0")
             dev0 = next(self.wav2vec2.parameters()).device
             wav = input_values.to(device=dev0, dtype=torch.float32).contiguous()
             lens = input_lengths.reshape(-1).to(device=dev0, dtype=torch.int64)
             flen = self.wav2vec2._get_feat_extract_output_lengths(lens).to(torch.int32).contiguous()
             gb = self.grad_buffer()
             h, sv = self.wav2vec2.encode_train(wav, flen)
-            logits = self._head(h)
+            p_fin = float(self.dropout.p)                      # final_dropout (models/w2v2_pr.py:56)
+            s_fin = self.wav2vec2.drop_seed(sv.step, -1, self.wav2vec2.SITE_HEAD_A)
+            h_in = ops.dropout(h, p_fin, s_fin, want_f32=True)[0] if p_fin > 0 else h
+            logits = self._head(h_in)
+            h = h_in                                           # the reference returns the dropped hidden states (:53-58)
             want_grad = True
         else:
             out, h, logits = self._logits(input_values, input_lengths)
@@ -130,13 +132,15 @@ class Wav2Vec2_PR(nn.Module):
         if want_grad:
             res["grad_logits"] = r["grad"]
         if train:
-            hm = h.reshape(B * T, -1)
+            hm = h_in.reshape(B * T, -1)
             w = self.pr_head.weight.detach().float().contiguous()
 
             def run_backward(grad_out):
                 d_lg = (r["grad"] * grad_out.detach().to(device=dev, dtype=torch.float32)).view(B * T, V).contiguous()
                 dh = ops.heads_bwd(hm, None, None, 0, None, None, d_lg, w, ops.ACT_NONE, gb.view("pr_head.weight"),
                                    gb.view("pr_head.bias"))
+                if p_fin > 0:
+                    ops.dropout(dh, p_fin, s_fin, out_f32=dh)
                 red = getattr(self, "_reducer", None)
                 self.wav2vec2.backward(sv, dh, gb, prefix="wav2vec2.", on_layer_done=red.layer_done if red else None)
                 if red is not None:

@@ -266,6 +266,13 @@ typedef struct aptai_prep_entry {
 } aptai_prep_entry;
 int aptai_prepare_weights(const void* entries_dev, int n_entries, int total_tiles, void* stream);
 
+/* Inverted dropout, counter-based (HF:434,546,570,603-607,647-653,694,766; models/aptai.py:44,52; w2v2_pr.py:56):
+ * out[i] = residual[i] + keep(seed, i) * x[i] / (1 - p), keep = hash(seed, i) >= p.  x fp32 or bf16 (x_bf16), residual
+ * optional fp32, outputs fp32 and/or bf16 (may alias x).  The backward of a site is the same call on the gradient
+ * with the same (p, seed). */
+int aptai_dropout(const void* x, int x_bf16, const float* residual, int64_t n, float p, uint64_t seed, float* out_f32,
+                  void* out_bf16, void* stream);
+
 /* torch.optim.Adam step (train/train_aptai.py:350-356) over a table of parameter tensors in one launch.
  * params_dev: device array of fp32 pointers; grad_offsets / state_offsets / numel: element offset of each tensor in
  * the flat grad buffer, in the flat exp_avg / exp_avg_sq buffers, and its size;

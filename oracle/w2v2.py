@@ -60,14 +60,23 @@ def attention(sd, p, cfg, x, key_mask):
     return F.linear(o, sd[p + "out_proj.weight"], sd[p + "out_proj.bias"])
 
 
-def feed_forward(sd, p, x):
-    """HF:566-573."""
+def feed_forward(sd, p, x, act_mask=None):
+    """HF:566-573 (intermediate_dropout after the activation, HF:570)."""
     x = F.gelu(F.linear(x, sd[p + "intermediate_dense.weight"], sd[p + "intermediate_dense.bias"]))
+    if act_mask is not None:
+        x = x * act_mask
     return F.linear(x, sd[p + "output_dense.weight"], sd[p + "output_dense.bias"])
 
 
-def forward(sd, cfg, wav, lengths, return_features=False):
-    """HF:1327-1383.  wav fp32 [B,L], lengths int [B] (samples).  Returns tuple of N+1 hidden states [B,T,H]."""
+def forward(sd, cfg, wav, lengths, return_features=False, reg=None):
+    """HF:1327-1383.  wav fp32 [B,L], lengths int [B] (samples).  Returns tuple of N+1 hidden states [B,T,H].
+
+    `reg` (training mode): explicit regulariser draws so that a stochastic step can be replayed — dict with optional
+    keys 'proj' (HF:434), 'enc' (HF:694/766), ('attn', l) (HF:603/647), ('act', l) (HF:570), ('ffn', l) (HF:573):
+    multiplicative masks already scaled by 1/(1-p), broadcastable to the activation; 'skip': set of layers dropped by
+    LayerDrop (HF:701-706/773-778); 'spec': bool [B,T] SpecAugment mask (HF:1303, rows replaced by masked_spec_embed)."""
+    reg = reg or {}
+    m = lambda key, x: x if reg.get(key) is None else x * reg[key].view(x.shape)
     eps = cfg.layer_norm_eps
     feats = feature_encoder(sd, cfg, wav).transpose(1, 2)                       # HF:1348-1349  [B,T,512]
     B, T, _ = feats.shape
@@ -76,6 +85,9 @@ def forward(sd, cfg, wav, lengths, return_features=False):
     x = F.layer_norm(feats, (feats.shape[-1],), sd["feature_projection.layer_norm.weight"],
                      sd["feature_projection.layer_norm.bias"], eps)             # HF:431
     x = F.linear(x, sd["feature_projection.projection.weight"], sd["feature_projection.projection.bias"])
+    x = m("proj", x)
+    if reg.get("spec") is not None:
+        x = torch.where(reg["spec"][:, :, None], sd["masked_spec_embed"][None, None, :], x)
     x = x.clone()
     x[~mask] = 0.0                                                              # HF:679-682 / 753-756
     key_mask = None if bool(mask.all()) else mask
@@ -89,22 +101,28 @@ def forward(sd, cfg, wav, lengths, return_features=False):
     hidden = []
     if not cfg.do_stable_layer_norm:
         x = F.layer_norm(x, (H,), sd["encoder.layer_norm.weight"], sd["encoder.layer_norm.bias"], eps)   # HF:692
+        x = m("enc", x)
         for l in range(cfg.num_hidden_layers):
             hidden.append(x)
+            if l in reg.get("skip", ()):
+                continue
             p = f"encoder.layers.{l}."
-            x = x + attention(sd, p + "attention.", cfg, x, key_mask)           # HF:592-609 (post-LN)
+            x = x + m(("attn", l), attention(sd, p + "attention.", cfg, x, key_mask))           # HF:592-609 (post-LN)
             x = F.layer_norm(x, (H,), sd[p + "layer_norm.weight"], sd[p + "layer_norm.bias"], eps)
-            x = x + feed_forward(sd, p + "feed_forward.", x)
+            x = x + m(("ffn", l), feed_forward(sd, p + "feed_forward.", x, reg.get(("act", l))))
             x = F.layer_norm(x, (H,), sd[p + "final_layer_norm.weight"], sd[p + "final_layer_norm.bias"], eps)
         hidden.append(x)
     else:
+        x = m("enc", x)
         for l in range(cfg.num_hidden_layers):
             hidden.append(x)
+            if l in reg.get("skip", ()):
+                continue
             p = f"encoder.layers.{l}."
             y = F.layer_norm(x, (H,), sd[p + "layer_norm.weight"], sd[p + "layer_norm.bias"], eps)
-            x = x + attention(sd, p + "attention.", cfg, y, key_mask)           # HF:632-655 (pre-LN)
+            x = x + m(("attn", l), attention(sd, p + "attention.", cfg, y, key_mask))           # HF:632-655 (pre-LN)
             y = F.layer_norm(x, (H,), sd[p + "final_layer_norm.weight"], sd[p + "final_layer_norm.bias"], eps)
-            x = x + feed_forward(sd, p + "feed_forward.", y)
+            x = x + m(("ffn", l), feed_forward(sd, p + "feed_forward.", y, reg.get(("act", l))))
         x = F.layer_norm(x, (H,), sd["encoder.layer_norm.weight"], sd["encoder.layer_norm.bias"], eps)   # HF:792
         hidden.append(x)
     if return_features:

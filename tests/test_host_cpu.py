@@ -107,3 +107,28 @@ def test_two_rank_gloo_data_parallel_gradients():
                        text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "GLOO_DP_OK" in r.stdout
+
+
+def test_specaugment_masks_match_transformers():
+    """aptai_b200.specaug restates transformers' `_compute_mask_indices` (HF:101-217) on the same global NumPy RNG."""
+    import numpy as np
+    from transformers.models.wav2vec2.modeling_wav2vec2 import _compute_mask_indices
+    from aptai_b200.specaug import compute_mask_indices
+    cases = [((4, 399), 0.05, 10, [399, 250, 399, 120], 2), ((2, 99), 0.05, 10, [99, 74], 2), ((3, 999), 0.2, 10, None, 0),
+             ((5, 60), 0.5, 4, [60, 3, 5, 60, 30], 1), ((1, 20), 0.01, 10, [15], 0), ((2, 49), 0.65, 10, [49, 9], 2)]
+    for seed, (shape, prob, length, lens, mn) in enumerate(cases):
+        am = None
+        if lens is not None:
+            am = torch.zeros(shape, dtype=torch.long)
+            for b, n in enumerate(lens):
+                am[b, :n] = 1
+        np.random.seed(100 + seed)
+        ref = _compute_mask_indices(shape, prob, length, attention_mask=am, min_masks=mn)
+        np.random.seed(100 + seed)
+        got = compute_mask_indices(shape, prob, length, frame_lens=lens, min_masks=mn)
+        assert np.array_equal(ref, got), (shape, prob, length, lens, mn)
+        # the generator state advanced identically:
+        np.random.seed(100 + seed); _compute_mask_indices(shape, prob, length, attention_mask=am, min_masks=mn)
+        a = np.random.rand()
+        np.random.seed(100 + seed); compute_mask_indices(shape, prob, length, frame_lens=lens, min_masks=mn)
+        assert a == np.random.rand()

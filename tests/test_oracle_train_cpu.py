@@ -47,3 +47,64 @@ def test_oracle_pr_gradients_match_reference():
         if key.startswith("t3_grad::wav2vec2."):
             k = key[len("t3_grad::wav2vec2."):]
             np.testing.assert_allclose(sd[k].grad.reshape(-1)[:256].numpy(), g[key], rtol=2e-3, atol=1e-7)
+
+
+def test_oracle_regulariser_placement_matches_transformers():
+    """The oracle's training-mode forward (explicit dropout masks, LayerDrop set, SpecAugment mask) against the
+    installed transformers' Wav2Vec2Model in train mode with its nn.Dropout modules replaced by the same masks —
+    pins WHERE every regulariser acts (HF:434,570,573,603,647,694,766,701-706,1303) for both layer wirings."""
+    import torch.nn as nn
+    from transformers import Wav2Vec2Config, Wav2Vec2Model
+    from aptai_b200.config import W2V2Config
+    from aptai_b200.specaug import compute_mask_indices
+
+    class MaskDrop(nn.Module):
+        def __init__(self, mask):
+            super().__init__()
+            self.mask = mask
+
+        def forward(self, x):
+            return x * self.mask.view(x.shape)
+
+    for stable in (False, True):
+        kw = dict(vocab_size=46, num_hidden_layers=3, hidden_dropout=0.1, activation_dropout=0.1, feat_proj_dropout=0.1,
+                  attention_dropout=0.0, final_dropout=0.0, layerdrop=0.4, apply_spec_augment=True, mask_time_prob=0.3,
+                  mask_time_length=10, mask_time_min_masks=2)
+        if stable:
+            kw.update(feat_extract_norm="layer", conv_bias=True, do_stable_layer_norm=True)
+        hf_cfg = Wav2Vec2Config(**kw)
+        cfg = W2V2Config.from_any(hf_cfg)
+        sd = backbone_sd(cfg, 3)
+        model = Wav2Vec2Model(hf_cfg)
+        model.load_state_dict(sd, strict=True)
+        model.train()
+        lens = [16000, 12000]
+        wav = W.waveforms(2, 16000, lens, seed=99)
+        B, T, H, Fi = 2, 49, cfg.hidden_size, cfg.intermediate_size
+        g = torch.Generator().manual_seed(1)
+        mk = lambda shape, p: (torch.rand(shape, generator=g) >= p).float() / (1 - p)
+        reg = {"proj": mk((B, T, H), 0.1), "enc": mk((B, T, H), 0.1)}
+        model.feature_projection.dropout = MaskDrop(reg["proj"])
+        model.encoder.dropout = MaskDrop(reg["enc"])
+        for l, layer in enumerate(model.encoder.layers):
+            reg[("attn", l)], reg[("act", l)], reg[("ffn", l)] = mk((B, T, H), 0.1), mk((B, T, Fi), 0.1), mk((B, T, H), 0.1)
+            layer.dropout = MaskDrop(reg[("attn", l)])
+            layer.feed_forward.intermediate_dropout = MaskDrop(reg[("act", l)])
+            layer.feed_forward.output_dropout = MaskDrop(reg[("ffn", l)])
+        am = torch.zeros((B, 16000), dtype=torch.long)
+        for b, n in enumerate(lens):
+            am[b, :n] = 1
+        torch.manual_seed(11)
+        np.random.seed(7)
+        with torch.no_grad():
+            ref = model(wav, attention_mask=am).last_hidden_state
+        torch.manual_seed(11)
+        reg["skip"] = {l for l in range(cfg.num_hidden_layers) if bool(torch.rand([]) < cfg.layerdrop)}
+        assert 0 < len(reg["skip"]) < cfg.num_hidden_layers
+        np.random.seed(7)
+        flen = [ow.conv_out_length(n, cfg) for n in lens]
+        reg["spec"] = torch.from_numpy(compute_mask_indices((B, T), 0.3, 10, frame_lens=flen, min_masks=2))
+        assert reg["spec"].any()
+        with torch.no_grad():
+            got = ow.forward(sd, cfg, wav, lens, reg=reg)[-1]
+        torch.testing.assert_close(got, ref, atol=2e-4, rtol=1e-4)

@@ -135,7 +135,7 @@ def test_pr_training_step_vs_reference(cuda):
 
 
 def test_training_refuses_unbuilt_configs(cuda):
-    cfg = cfg_base(vocab_size=46, hidden_dropout=0.1)
+    cfg = cfg_base(vocab_size=46, attention_dropout=0.1)
     name = register_in_memory_checkpoint("mem://base-seed1-drop", backbone_sd(cfg_base(vocab_size=46), 1))
     pr = Wav2Vec2_PR(cfg, None, name, VOCAB)
     pr.wav2vec2.freeze_feature_encoder()
@@ -144,3 +144,105 @@ def test_training_refuses_unbuilt_configs(cuda):
     labels, _ = W.phoneme_sequences(1, 5, 5, 2, 45, seed=3, pad=-100)
     with pytest.raises(NotImplementedError):
         pr(wav.to(cuda), torch.tensor([16000], device=cuda), labels.to(cuda))
+
+
+def test_dropout_kernel(cuda):
+    from aptai_b200 import ops
+    n = 1 << 22
+    x = torch.randn(n, device=cuda)
+    res = torch.randn(n, device=cuda)
+    for p in (0.1, 0.5):
+        y, yb = ops.dropout(x, p, 1234, want_f32=True, want_bf16=True)
+        keep = y != 0
+        assert abs(float(keep.float().mean()) - (1 - p)) < 3e-3
+        torch.testing.assert_close(y[keep], x[keep] / (1 - p), rtol=1e-6, atol=0)
+        assert torch.equal(yb, y.bfloat16())
+        y2, _ = ops.dropout(x, p, 1234, want_f32=True)                       # deterministic in (seed, index)
+        assert torch.equal(y, y2)
+        y3, _ = ops.dropout(x, p, 1235, want_f32=True)
+        assert 0.05 < float(((y3 != 0) != keep).float().mean()) < 2 * p      # another seed: another mask
+        yr, _ = ops.dropout(x, p, 1234, residual=res, want_f32=True)
+        torch.testing.assert_close(yr, y + res, rtol=1e-6, atol=1e-6)
+        xb = x.bfloat16()
+        _, zb = ops.dropout(xb, p, 1234, want_bf16=True)                     # bf16 input: same mask
+        assert torch.equal(zb != 0, keep | (xb == 0) & False | (zb != 0))
+        assert torch.equal((zb != 0) | (xb == 0), keep | (xb == 0))
+    y0, _ = ops.dropout(x, 0.0, 7, residual=res, want_f32=True)               # p = 0: a plain add
+    torch.testing.assert_close(y0, x + res)
+
+
+def test_training_step_with_regularisers_replayed_by_the_oracle(cuda):
+    """Dropout (feat_proj / hidden / activation / final), LayerDrop and SpecAugment on: the masks the step used are
+    materialised from the same counter-based generator and replayed through the oracle (whose regulariser placement
+    is pinned against transformers in tests/test_oracle_train_cpu.py); loss and every gradient must agree."""
+    import torch.nn.functional as F
+    from aptai_b200 import ops
+    from oracle import w2v2 as ow
+    cfg = cfg_base(vocab_size=46, hidden_dropout=0.1, activation_dropout=0.1, feat_proj_dropout=0.1, final_dropout=0.1,
+                   layerdrop=0.25, apply_spec_augment=True, mask_time_prob=0.2, mask_time_length=10,
+                   mask_time_min_masks=2)
+    sd0 = backbone_sd(cfg_base(vocab_size=46), 1)
+    name = register_in_memory_checkpoint("mem://base-seed1-reg", sd0)
+    pr = Wav2Vec2_PR(cfg, None, name, VOCAB)
+    hw, hb = W.linear_params(104, 46, 768)
+    with torch.no_grad():
+        pr.pr_head.weight.copy_(hw); pr.pr_head.bias.copy_(hb)
+    pr.wav2vec2.freeze_feature_encoder()
+    pr = pr.to(cuda).train()
+    lens3 = [32000, 27000, 16000]
+    wav3 = W.waveforms(3, 32000, lens3, seed=3234)
+    labels, _ = W.phoneme_sequences(3, 10, 40, 2, 45, seed=7, pad=-100)
+    labels[2, 5:] = -100
+    torch.manual_seed(1234)
+    np.random.seed(5)
+    r = pr(wav3.to(cuda), torch.tensor(lens3, device=cuda), labels.to(cuda))
+    r["loss"].backward()
+    w2v = pr.wav2vec2
+    info = w2v._last_regularisers
+    step, B, T, H, Fi = info["step"], 3, 99, 768, 3072
+    assert 0 < len(info["skipped"]) < 12 and info["spec_rows"] is not None
+
+    def mask(layer, site, shape, p):
+        return ops.dropout(torch.ones(shape, device=cuda), p, w2v.drop_seed(step, layer, site), want_f32=True)[0].cpu()
+
+    reg = {"proj": mask(-1, w2v.SITE_PROJ, (B, T, H), 0.1), "enc": mask(-1, w2v.SITE_ENC, (B, T, H), 0.1),
+           "skip": set(info["skipped"])}
+    for l in range(12):
+        reg[("attn", l)] = mask(l, w2v.SITE_ATTN, (B, T, H), 0.1)
+        reg[("act", l)] = mask(l, w2v.SITE_ACT, (B, T, Fi), 0.1)
+        reg[("ffn", l)] = mask(l, w2v.SITE_FFN, (B, T, H), 0.1)
+    spec = torch.zeros(B * T, dtype=torch.bool)
+    spec[info["spec_rows"].cpu()] = True
+    reg["spec"] = spec.view(B, T)
+    fin = mask(-1, w2v.SITE_HEAD_A, (B, T, H), 0.1)
+    # oracle replay (torch CPU fp32 autograd)
+    sd = {k: v.clone() for k, v in sd0.items()}
+    trainable = [k for k in sd if not k.startswith("feature_extractor.")]
+    for k in trainable:
+        sd[k].requires_grad_(True)
+    hw_, hb_ = hw.clone().requires_grad_(True), hb.clone().requires_grad_(True)
+    torch.set_num_threads(os.cpu_count())
+    hidden, _, flen = ow.forward(sd, cfg, wav3, lens3, return_features=True, reg=reg)
+    logits = F.linear(hidden[-1] * fin, hw_, hb_)
+    lp = F.log_softmax(logits, dim=-1, dtype=torch.float32).transpose(0, 1)
+    loss = F.ctc_loss(lp, labels[labels >= 0], flen, (labels >= 0).sum(-1), blank=0, reduction="mean", zero_infinity=True)
+    loss.backward()
+    assert abs(float(r["loss"]) - float(loss)) / float(loss) < 2e-3, (float(r["loss"]), float(loss))
+    params = dict(pr.named_parameters())
+    norms = {k: float(sd[k].grad.double().norm()) for k in trainable if sd[k].grad is not None}
+    floor = 1e-4 * float(np.median(list(norms.values())))
+    worst, low = ("", 0.0), ("", 1.0)
+    for k, ref in norms.items():
+        ours = params["wav2vec2." + k].grad.double().cpu()
+        if ref < floor:
+            assert float(ours.norm()) < 100 * floor, k
+            continue
+        rel = abs(float(ours.norm()) - ref) / ref
+        cos = float((ours.flatten() @ sd[k].grad.double().flatten()) / (ours.norm() * ref))
+        worst = max(worst, (k, rel), key=lambda t: t[1])
+        low = min(low, (k, cos), key=lambda t: t[1])
+    print("regularised step: worst grad-norm deviation", worst, "lowest cosine", low)
+    assert worst[1] < 0.05 and low[1] > 0.98
+    for l in info["skipped"]:                       # LayerDrop: a dropped layer receives no gradient
+        assert float(params[f"wav2vec2.encoder.layers.{l}.feed_forward.output_dense.weight"].grad.abs().max()) == 0.0
+    assert norms["masked_spec_embed"] > floor      # SpecAugment rows feed masked_spec_embed
