@@ -246,3 +246,49 @@ def test_training_step_with_regularisers_replayed_by_the_oracle(cuda):
     for l in info["skipped"]:                       # LayerDrop: a dropped layer receives no gradient
         assert float(params[f"wav2vec2.encoder.layers.{l}.feed_forward.output_dense.weight"].grad.abs().max()) == 0.0
     assert norms["masked_spec_embed"] > floor      # SpecAugment rows feed masked_spec_embed
+
+
+def test_aptai_head_dropouts_replayed_by_the_oracle(cuda):
+    """APTAI with tv_drop / phn_drop (models/aptai.py:43-55): the two head masks are materialised and replayed."""
+    import torch.nn.functional as F
+    from aptai_b200 import ops
+    from oracle import heads as oh
+    from oracle import w2v2 as ow
+    cfg = cfg_base(vocab_size=46)
+    sd0 = backbone_sd(cfg, 1)
+    name = register_in_memory_checkpoint("mem://base-seed1-heads", sd0)
+    m = APTAI(cuda, VOCAB, name, cfg, None, phn_drop=0.2, tv_drop=0.1)
+    tvw, tvb = W.linear_params(111, 9, 768)
+    pw, pb = W.linear_params(112, 46, 768)
+    with torch.no_grad():
+        m.tv_head[2].weight.copy_(tvw); m.tv_head[2].bias.copy_(tvb)
+        m.phn_head[2].weight.copy_(pw); m.phn_head[2].bias.copy_(pb)
+    m = m.to(cuda).train()
+    wav, lens, phn, tvs = _g2_inputs()
+    out = m(0, wav.to(cuda), lens.to(cuda), phn.to(cuda), *[t.to(cuda) for t in tvs])
+    out["loss"].backward()
+    w2v = m.wav2vec2
+    step, B, T, H = w2v._last_regularisers["step"], 2, 99, 768
+    mk = lambda site, p: ops.dropout(torch.ones((B, T, H), device=cuda), p, w2v.drop_seed(step, -1, site),
+                                     want_f32=True)[0].cpu()
+    m_tv, m_phn = mk(w2v.SITE_HEAD_A, 0.1), mk(w2v.SITE_HEAD_B, 0.2)
+    sd = {k: v.clone() for k, v in sd0.items()}
+    trainable = [k for k in sd if not k.startswith("feature_extractor.") and k != "masked_spec_embed"]
+    for k in trainable:
+        sd[k].requires_grad_(True)
+    ws = [t.clone().requires_grad_(True) for t in (tvw, tvb, pw, pb)]
+    torch.set_num_threads(os.cpu_count())
+    h = ow.forward(sd, cfg, wav, lens.tolist())[-1]
+    tv = oh.lowpass(F.linear(torch.tanh(h * m_tv), ws[0], ws[1]), oh.lowpass_taps())
+    logits = F.linear(F.leaky_relu(h * m_phn), ws[2], ws[3])
+    loss, _, _ = oh.aptai_losses(tv, logits, phn, torch.stack(tvs, -1).float())
+    loss.backward()
+    assert abs(float(out["loss"]) - float(loss)) / float(loss) < 2e-3
+    params = dict(m.named_parameters())
+    for name_, ref in (("tv_head.2.weight", ws[0]), ("tv_head.2.bias", ws[1]), ("phn_head.2.weight", ws[2]),
+                       ("phn_head.2.bias", ws[3]), ("wav2vec2.encoder.layers.11.feed_forward.output_dense.weight",
+                                                    sd["encoder.layers.11.feed_forward.output_dense.weight"]),
+                       ("wav2vec2.encoder.layers.0.attention.v_proj.weight", sd["encoder.layers.0.attention.v_proj.weight"])):
+        ours, r = params[name_].grad.double().cpu().flatten(), ref.grad.double().flatten()
+        cos = float(ours @ r / (ours.norm() * r.norm()))
+        assert abs(float(ours.norm() / r.norm()) - 1) < 0.03 and cos > 0.995, (name_, float(ours.norm() / r.norm()), cos)
