@@ -324,17 +324,13 @@ class Wav2Vec2Backbone(nn.Module):
         return groups
 
     def check_trainable(self):
-        cfg = self.cfg
-        if getattr(cfg, "attention_dropout", 0.0) > 0:
-            raise NotImplementedError("aptai_b200: attention_dropout (dropout on the attention probabilities inside the "
-                                      "fused attention kernels) is not built; set attention_dropout=0")
         if any(p.requires_grad for p in self.feature_extractor.parameters()):
             raise NotImplementedError("aptai_b200: the backward of the conv feature encoder is not built; call "
                                       "freeze_feature_encoder() (the reference's default, models/aptai.py:39-40)")
 
     # Stochastic regularisers of the training path.  Dropout is counter-based (csrc/dropout.cu): a site's mask is a
     # function of (seed, element index), the seed of (training step, layer, site), so the backward regenerates it.
-    SITE_ATTN, SITE_ACT, SITE_FFN, SITE_PROJ, SITE_ENC, SITE_HEAD_A, SITE_HEAD_B = range(7)
+    SITE_ATTN, SITE_ACT, SITE_FFN, SITE_PROJ, SITE_ENC, SITE_HEAD_A, SITE_HEAD_B, SITE_ATTN_P = range(8)
 
     def drop_seed(self, step: int, layer: int, site: int) -> int:
         base = getattr(self, "_drop_base", None)
@@ -365,8 +361,9 @@ class Wav2Vec2Backbone(nn.Module):
         step = getattr(self, "_drop_step", 0) + 1
         object.__setattr__(self, "_drop_step", step)
         p_h, p_a, p_fp = float(cfg.hidden_dropout), float(cfg.activation_dropout), float(cfg.feat_proj_dropout)
+        p_at = float(cfg.attention_dropout)
         seed = lambda layer, site: self.drop_seed(step, layer, site)
-        sv = SimpleNamespace(B=B, T=T, frame_lens=frame_lens, layers=[], step=step, p_h=p_h, p_a=p_a, p_fp=p_fp,
+        sv = SimpleNamespace(B=B, T=T, frame_lens=frame_lens, layers=[], step=step, p_h=p_h, p_a=p_a, p_fp=p_fp, p_at=p_at,
                              spec_rows=None, skipped=[])
         sv.y32 = y.view(M, -1).float()
         _, sv.xn = ops.layernorm(sv.y32, P.fp_ln_w, P.fp_ln_b, eps)
@@ -389,10 +386,11 @@ class Wav2Vec2Backbone(nn.Module):
         ops.posconv(sv.hp, P.pos_w, P.pos_b, h0, T, H, groups, taps, h, out_pre=sv.pos_pre)
         F_ = cfg.intermediate_size
 
-        def attn(x):
+        def attn(x, li):
             _, qkv = ops.linear(x, lw.qkv_w, lw.qkv_b)
             lse = torch.empty((B, heads, T), dtype=F32, device=wav.device)
-            ctx = ops.attention(qkv, frame_lens, B, T, heads, lse=lse)
+            ctx = ops.attention(qkv, frame_lens, B, T, heads, lse=lse, drop_p=p_at,
+                                drop_seed=seed(li, self.SITE_ATTN_P))
             return qkv, ctx, lse
 
         def ffn1(x, li):
@@ -421,7 +419,7 @@ class Wav2Vec2Backbone(nn.Module):
                     sv.skipped.append(li)
                     continue
                 _, x1 = ops.layernorm(h, lw.ln1_w, lw.ln1_b, eps)
-                qkv, ctx, lse = attn(x1)
+                qkv, ctx, lse = attn(x1, li)
                 hm = proj_res(ctx, lw.o_w, lw.o_b, h, li, self.SITE_ATTN)
                 _, x2 = ops.layernorm(hm, lw.ln2_w, lw.ln2_b, eps)
                 u, g = ffn1(x2, li)
@@ -440,7 +438,7 @@ class Wav2Vec2Backbone(nn.Module):
                     sv.layers.append(None)
                     sv.skipped.append(li)
                     continue
-                qkv, ctx, lse = attn(x)
+                qkv, ctx, lse = attn(x, li)
                 t = proj_res(ctx, lw.o_w, lw.o_b, h, li, self.SITE_ATTN)
                 h1, x1 = ops.layernorm(t, lw.ln1_w, lw.ln1_b, eps, want_f32=True, want_bf16=True)
                 u, g = ffn1(x1, li)
@@ -494,7 +492,8 @@ class Wav2Vec2Backbone(nn.Module):
             base = f"encoder.layers.{i}.attention."
             lin_grads(dctx_src_b, s.ctx, base + "out_proj")
             _, dctx = ops.linear(dctx_src_b, lt.o_wt, None)
-            dqkv = ops.attention_bwd(s.qkv, s.ctx, dctx, s.lse, flen, B, T, heads, q_scale)
+            dqkv = ops.attention_bwd(s.qkv, s.ctx, dctx, s.lse, flen, B, T, heads, q_scale, drop_p=sv.p_at,
+                                     drop_seed=seed(i, self.SITE_ATTN_P))
             names_w = [prefix + base + n + ".weight" for n in ("q_proj", "k_proj", "v_proj")]
             names_b = [prefix + base + n + ".bias" for n in ("q_proj", "k_proj", "v_proj")]
             ops.wgrad(dqkv, x_in_b, gb.fused(names_w, (3 * H, H)))

@@ -43,6 +43,9 @@ struct AttnBwdParams {
   float* dq32;          // [B*T][H] fp32, zeroed by the caller
   __nv_bfloat16* dqkv;  // [B*T][3H]: the k and v blocks are written here
   int B, T, heads, H, n_t, items;
+  uint32_t drop_thresh24;      // attention-probability dropout of the forward (0 = off), same counter-based mask
+  float drop_inv_keep;
+  unsigned long long drop_seed;
 };
 
 __device__ __forceinline__ uint64_t ab_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
@@ -245,6 +248,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         continue;
       }
       const bool key_ok = key < klen;
+      const bool drop = p.drop_thresh24 != 0;
+      const uint32_t seed_bh = attn_drop_seed_bh(p.drop_seed, static_cast<uint32_t>(bh));
       const float* lse_bh = p.lse + static_cast<long long>(bh) * p.T;
       const float* d_bh = p.dvec + static_cast<long long>(bh) * p.T;
       for (int i = 0; i < p.n_t; ++i, ++g) {
@@ -275,8 +280,16 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
               const int qc = hf * 64 + c * 32 + u * 8 + e;
               float pe = ab_ex2(fmaf(__uint_as_float(s[u * 8 + e]), AB_LOG2E, -st[qc]));
               if (!key_ok) pe = 0.f;
-              pv[e] = pe;
-              dv[e] = pe * (__uint_as_float(dp[u * 8 + e]) - st[AB_T + qc]);
+              float dpe = __uint_as_float(dp[u * 8 + e]);
+              float pd = pe;                      // what fed P V in the forward: the dropped, rescaled probability
+              if (drop) {
+                const float mk = attn_drop_keep(seed_bh, static_cast<uint32_t>(i * AB_T + qc), static_cast<uint32_t>(key),
+                                                static_cast<uint32_t>(p.T), p.drop_thresh24) ? p.drop_inv_keep : 0.f;
+                pd *= mk;
+                dpe *= mk;
+              }
+              pv[e] = pd;
+              dv[e] = pe * (dpe - st[AB_T + qc]);
             }
             const int unit = (c * 4 + u) ^ (row & 7);
             *reinterpret_cast<uint4*>(pt_row + (unit << 4)) =
@@ -353,10 +366,27 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
 
 using namespace aptai;
 
+static int attention_bwd_impl(const void* qkv, const void* d_ctx, const float* lse, const float* dvec,
+                              const int32_t* key_len, int B, int T, int heads, float* dq32, void* dqkv, float drop_p,
+                              uint64_t drop_seed, void* stream);
+
 extern "C" int aptai_attention_bwd(const void* qkv, const void* d_ctx, const float* lse, const float* dvec,
                                    const int32_t* key_len, int B, int T, int heads, float* dq32, void* dqkv,
                                    void* stream) {
+  return attention_bwd_impl(qkv, d_ctx, lse, dvec, key_len, B, T, heads, dq32, dqkv, 0.f, 0, stream);
+}
+
+extern "C" int aptai_attention_bwd_dropout(const void* qkv, const void* d_ctx, const float* lse, const float* dvec,
+                                           const int32_t* key_len, int B, int T, int heads, float* dq32, void* dqkv,
+                                           float drop_p, uint64_t drop_seed, void* stream) {
+  return attention_bwd_impl(qkv, d_ctx, lse, dvec, key_len, B, T, heads, dq32, dqkv, drop_p, drop_seed, stream);
+}
+
+static int attention_bwd_impl(const void* qkv, const void* d_ctx, const float* lse, const float* dvec,
+                              const int32_t* key_len, int B, int T, int heads, float* dq32, void* dqkv, float drop_p,
+                              uint64_t drop_seed, void* stream) {
   if (int rc = check_arch()) return rc;
+  APTAI_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "attention_bwd: dropout p must be in [0, 1)");
   APTAI_REQUIRE(qkv && d_ctx && lse && dvec && key_len && dq32 && dqkv, "attention_bwd: null pointer");
   APTAI_REQUIRE(B >= 1 && T >= 1 && heads >= 1, "attention_bwd: bad shape");
   APTAI_REQUIRE(((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(d_ctx) |
@@ -384,6 +414,9 @@ extern "C" int aptai_attention_bwd(const void* qkv, const void* d_ctx, const flo
   p.B = B; p.T = T; p.heads = heads; p.H = H;
   p.n_t = (T + AB_T - 1) / AB_T;
   p.items = B * heads * p.n_t;
+  p.drop_thresh24 = static_cast<uint32_t>(static_cast<double>(drop_p) * 16777216.0);
+  p.drop_inv_keep = 1.0f / (1.0f - drop_p);
+  p.drop_seed = drop_seed;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);

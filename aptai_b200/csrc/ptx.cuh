@@ -362,6 +362,19 @@ __device__ __forceinline__ void gelu_erf_grad2_mul(float& g0, float& g1, float u
   f32x2_unpack(f32x2_mul(f32x2_pack(g0, g1), d), g0, g1);
 }
 
+// Attention-probability dropout (HF:461 `nn.functional.dropout(attn_weights, p)`): counter-based keep decision for
+// element (query q, key k) of one (utterance, head).  32-bit "lowbias32" mix: cheap enough for the softmax inner loop.
+__device__ __forceinline__ uint32_t attn_drop_mix(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint32_t attn_drop_seed_bh(uint64_t seed, uint32_t bh) {
+  return attn_drop_mix(static_cast<uint32_t>(seed) ^ (bh * 0x9E3779B9U)) ^ static_cast<uint32_t>(seed >> 32);
+}
+__device__ __forceinline__ bool attn_drop_keep(uint32_t seed_bh, uint32_t q, uint32_t k, uint32_t T, uint32_t thresh24) {
+  return (attn_drop_mix((q * T + k) ^ seed_bh) >> 8) >= thresh24;
+}
+
 __device__ __forceinline__ uint32_t pack_f16(float a, float b) {
   __half2 v = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);

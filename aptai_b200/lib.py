@@ -76,6 +76,11 @@ PROTOTYPES = {
     "aptai_attention_bwd_dot": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "aptai_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                     c_void_p, c_void_p]),
+    "aptai_attention_fwd_dropout": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                                            C.c_uint64, c_void_p]),
+    "aptai_attention_bwd_dropout": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                            c_void_p, c_void_p, c_float, C.c_uint64, c_void_p]),
+    "aptai_attention_dropout_mask": (c_int, [c_int, c_int, c_int, c_float, C.c_uint64, c_void_p, c_void_p]),
     "aptai_scale_cast_bf16": (c_int, [c_void_p, c_i64, c_int, c_float, c_void_p, c_i64, c_void_p]),
     "aptai_gemm_wgrad_bf16": (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_i64, c_int, c_int, c_float, c_void_p, c_i64,
                                       c_void_p]),

@@ -244,7 +244,7 @@ ATTENTION_IMPL = int(os.environ.get("APTAI_ATTN_IMPL", "0"))
 
 def attention(qkv: torch.Tensor, key_len: Optional[torch.Tensor], B: int, T: int, heads: int,
               out: Optional[torch.Tensor] = None, legacy_mma: bool = False, lse: Optional[torch.Tensor] = None,
-              impl: Optional[int] = None) -> torch.Tensor:
+              impl: Optional[int] = None, drop_p: float = 0.0, drop_seed: int = 0) -> torch.Tensor:
     _req(qkv, BF16, "qkv")
     H = heads * 64
     assert qkv.numel() == B * T * 3 * H
@@ -256,6 +256,11 @@ def attention(qkv: torch.Tensor, key_len: Optional[torch.Tensor], B: int, T: int
     if lse is not None:
         _req(lse, F32, "lse")
         assert lse.numel() == B * heads * T
+    if drop_p > 0:        # training: dropout on the attention probabilities lives in the query-tile-pair kernel
+        check(_lib.load().aptai_attention_fwd_dropout(qkv.data_ptr(), out.data_ptr(), _ptr(lse), key_len.data_ptr(), B,
+                                                      T, heads, float(drop_p), int(drop_seed) & 0xFFFFFFFFFFFFFFFF,
+                                                      _stream()), "attention_fwd_dropout")
+        return out
     which = impl or ATTENTION_IMPL or (2 if T > 128 else 1)
     if which == 2 and not legacy_mma:
         check(_lib.load().aptai_attention_fwd_v2(qkv.data_ptr(), out.data_ptr(), _ptr(lse), key_len.data_ptr(), B, T,
@@ -408,8 +413,17 @@ def ctc_greedy(logits: torch.Tensor, input_len: Optional[torch.Tensor], blank: i
 
 
 # ============================================================================================ training step
+def attention_dropout_mask(B: int, T: int, heads: int, drop_p: float, drop_seed: int, device) -> torch.Tensor:
+    """keep/(1-p) fp32 [B, heads, T, T] of the counter-based attention dropout (what a step with this seed used)."""
+    out = torch.empty((B, heads, T, T), dtype=F32, device=device)
+    check(_lib.load().aptai_attention_dropout_mask(B, T, heads, float(drop_p), int(drop_seed) & 0xFFFFFFFFFFFFFFFF,
+                                                   out.data_ptr(), _stream()), "attention_dropout_mask")
+    return out
+
+
 def attention_bwd(qkv: torch.Tensor, ctx: torch.Tensor, d_ctx: torch.Tensor, lse: torch.Tensor,
-                  key_len: torch.Tensor, B: int, T: int, heads: int, q_scale: float) -> torch.Tensor:
+                  key_len: torch.Tensor, B: int, T: int, heads: int, q_scale: float, drop_p: float = 0.0,
+                  drop_seed: int = 0) -> torch.Tensor:
     """Backward of `attention`: returns dqkv bf16 [B*T, 3H]; the q block is the gradient w.r.t. the UNSCALED q
     (q_scale = head_dim^-0.5 folded in), matching the unscaled q_proj weight used for dgrad/wgrad."""
     _req(qkv, BF16, "qkv"); _req(ctx, BF16, "ctx"); _req(d_ctx, BF16, "d_ctx"); _req(lse, F32, "lse")
@@ -423,8 +437,9 @@ def attention_bwd(qkv: torch.Tensor, ctx: torch.Tensor, d_ctx: torch.Tensor, lse
           "attention_bwd_dot")
     dq32 = torch.zeros((M, H), dtype=F32, device=dev)
     dqkv = torch.empty((M, 3 * H), dtype=BF16, device=dev)
-    check(L.aptai_attention_bwd(qkv.data_ptr(), d_ctx.data_ptr(), lse.data_ptr(), dvec.data_ptr(), key_len.data_ptr(),
-                                B, T, heads, dq32.data_ptr(), dqkv.data_ptr(), _stream()), "attention_bwd")
+    check(L.aptai_attention_bwd_dropout(qkv.data_ptr(), d_ctx.data_ptr(), lse.data_ptr(), dvec.data_ptr(),
+                                        key_len.data_ptr(), B, T, heads, dq32.data_ptr(), dqkv.data_ptr(), float(drop_p),
+                                        int(drop_seed) & 0xFFFFFFFFFFFFFFFF, _stream()), "attention_bwd")
     check(L.aptai_scale_cast_bf16(dq32.data_ptr(), M, H, float(q_scale), dqkv.data_ptr(), 3 * H, _stream()),
           "scale_cast_bf16")
     return dqkv

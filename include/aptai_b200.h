@@ -211,6 +211,15 @@ int aptai_attention_bwd_dot(const void* d_ctx, const void* ctx, int B, int T, in
  * dq32 fp32 [B*T][H], which the caller zeroes before and converts with aptai_scale_cast_bf16 afterwards. */
 int aptai_attention_bwd(const void* qkv, const void* d_ctx, const float* lse, const float* dvec,
                         const int32_t* key_len, int B, int T, int heads, float* dq32, void* dqkv, void* stream);
+/* Training-mode variants with dropout on the attention probabilities (HF:461): P is masked and rescaled by 1/(1-p)
+ * where it multiplies V, with a counter-based mask of (seed, utterance, head, query, key) that the backward regenerates;
+ * aptai_attention_dropout_mask materialises keep/(1-p) as fp32 [B][heads][T][T] (test replay). */
+int aptai_attention_fwd_dropout(const void* qkv, void* ctx, float* lse, const int32_t* key_len, int B, int T, int heads,
+                                float drop_p, uint64_t drop_seed, void* stream);
+int aptai_attention_bwd_dropout(const void* qkv, const void* d_ctx, const float* lse, const float* dvec,
+                                const int32_t* key_len, int B, int T, int heads, float* dq32, void* dqkv, float drop_p,
+                                uint64_t drop_seed, void* stream);
+int aptai_attention_dropout_mask(int B, int T, int heads, float drop_p, uint64_t drop_seed, float* out, void* stream);
 /* out_bf16[r][0..cols) (row pitch ldo) = scale * x[r][0..cols) */
 int aptai_scale_cast_bf16(const float* x, int64_t rows, int cols, float scale, void* out_bf16, int64_t ldo,
                           void* stream);

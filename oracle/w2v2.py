@@ -44,8 +44,9 @@ def pos_conv_weight(sd):
     return g * v / torch.linalg.vector_norm(v, dim=(0, 1), keepdim=True)
 
 
-def attention(sd, p, cfg, x, key_mask):
-    """HF:500-549 with SDPA semantics: softmax(q k^T / sqrt(d) + key-padding mask) v, fp32."""
+def attention(sd, p, cfg, x, key_mask, prob_mask=None):
+    """HF:500-549 with SDPA semantics: softmax(q k^T / sqrt(d) + key-padding mask) v, fp32; `prob_mask` [B,nh,T,T]
+    (already scaled by 1/(1-p)) replays dropout on the attention probabilities (HF:461)."""
     B, T, H = x.shape
     nh = cfg.num_attention_heads
     d = H // nh
@@ -56,6 +57,8 @@ def attention(sd, p, cfg, x, key_mask):
     if key_mask is not None:
         s = s.masked_fill(~key_mask[:, None, None, :], float("-inf"))
     a = torch.softmax(s, dim=-1)
+    if prob_mask is not None:
+        a = a * prob_mask
     o = torch.matmul(a, v).transpose(1, 2).reshape(B, T, H)
     return F.linear(o, sd[p + "out_proj.weight"], sd[p + "out_proj.bias"])
 
@@ -72,7 +75,8 @@ def forward(sd, cfg, wav, lengths, return_features=False, reg=None):
     """HF:1327-1383.  wav fp32 [B,L], lengths int [B] (samples).  Returns tuple of N+1 hidden states [B,T,H].
 
     `reg` (training mode): explicit regulariser draws so that a stochastic step can be replayed — dict with optional
-    keys 'proj' (HF:434), 'enc' (HF:694/766), ('attn', l) (HF:603/647), ('act', l) (HF:570), ('ffn', l) (HF:573):
+    keys 'proj' (HF:434), 'enc' (HF:694/766), ('attn', l) (HF:603/647), ('act', l) (HF:570), ('ffn', l) (HF:573),
+    ('attp', l) (HF:461, attention probabilities [B,nh,T,T]):
     multiplicative masks already scaled by 1/(1-p), broadcastable to the activation; 'skip': set of layers dropped by
     LayerDrop (HF:701-706/773-778); 'spec': bool [B,T] SpecAugment mask (HF:1303, rows replaced by masked_spec_embed)."""
     reg = reg or {}
@@ -107,7 +111,7 @@ def forward(sd, cfg, wav, lengths, return_features=False, reg=None):
             if l in reg.get("skip", ()):
                 continue
             p = f"encoder.layers.{l}."
-            x = x + m(("attn", l), attention(sd, p + "attention.", cfg, x, key_mask))           # HF:592-609 (post-LN)
+            x = x + m(("attn", l), attention(sd, p + "attention.", cfg, x, key_mask, reg.get(("attp", l))))   # HF:592-609 (post-LN)
             x = F.layer_norm(x, (H,), sd[p + "layer_norm.weight"], sd[p + "layer_norm.bias"], eps)
             x = x + m(("ffn", l), feed_forward(sd, p + "feed_forward.", x, reg.get(("act", l))))
             x = F.layer_norm(x, (H,), sd[p + "final_layer_norm.weight"], sd[p + "final_layer_norm.bias"], eps)
@@ -120,7 +124,7 @@ def forward(sd, cfg, wav, lengths, return_features=False, reg=None):
                 continue
             p = f"encoder.layers.{l}."
             y = F.layer_norm(x, (H,), sd[p + "layer_norm.weight"], sd[p + "layer_norm.bias"], eps)
-            x = x + m(("attn", l), attention(sd, p + "attention.", cfg, y, key_mask))           # HF:632-655 (pre-LN)
+            x = x + m(("attn", l), attention(sd, p + "attention.", cfg, y, key_mask, reg.get(("attp", l))))   # HF:632-655 (pre-LN)
             y = F.layer_norm(x, (H,), sd[p + "final_layer_norm.weight"], sd[p + "final_layer_norm.bias"], eps)
             x = x + m(("ffn", l), feed_forward(sd, p + "feed_forward.", y, reg.get(("act", l))))
         x = F.layer_norm(x, (H,), sd["encoder.layer_norm.weight"], sd["encoder.layer_norm.bias"], eps)   # HF:792

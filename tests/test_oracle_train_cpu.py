@@ -68,7 +68,7 @@ def test_oracle_regulariser_placement_matches_transformers():
 
     for stable in (False, True):
         kw = dict(vocab_size=46, num_hidden_layers=3, hidden_dropout=0.1, activation_dropout=0.1, feat_proj_dropout=0.1,
-                  attention_dropout=0.0, final_dropout=0.0, layerdrop=0.4, apply_spec_augment=True, mask_time_prob=0.3,
+                  attention_dropout=0.1, attn_implementation="eager", final_dropout=0.0, layerdrop=0.4, apply_spec_augment=True, mask_time_prob=0.3,
                   mask_time_length=10, mask_time_min_masks=2)
         if stable:
             kw.update(feat_extract_norm="layer", conv_bias=True, do_stable_layer_norm=True)
@@ -95,12 +95,29 @@ def test_oracle_regulariser_placement_matches_transformers():
         for b, n in enumerate(lens):
             am[b, :n] = 1
         torch.manual_seed(11)
-        np.random.seed(7)
-        with torch.no_grad():
-            ref = model(wav, attention_mask=am).last_hidden_state
-        torch.manual_seed(11)
         reg["skip"] = {l for l in range(cfg.num_hidden_layers) if bool(torch.rand([]) < cfg.layerdrop)}
         assert 0 < len(reg["skip"]) < cfg.num_hidden_layers
+        live = [l for l in range(cfg.num_hidden_layers) if l not in reg["skip"]]
+        for l in live:
+            reg[("attp", l)] = mk((B, cfg.num_attention_heads, T, T), 0.1)
+        # dropout on the attention probabilities is a functional call (HF:461): patch it to the same masks
+        orig_dropout, seen = F.dropout, []
+
+        def fake_dropout(x, p=0.5, training=True, inplace=False):
+            if x.dim() == 4 and training and p > 0:
+                seen.append(1)
+                return x * reg[("attp", live[len(seen) - 1])]
+            return orig_dropout(x, p, training, inplace)
+
+        torch.manual_seed(11)
+        np.random.seed(7)
+        torch.nn.functional.dropout = fake_dropout
+        try:
+            with torch.no_grad():
+                ref = model(wav, attention_mask=am).last_hidden_state
+        finally:
+            torch.nn.functional.dropout = orig_dropout
+        assert len(seen) == len(live)
         np.random.seed(7)
         flen = [ow.conv_out_length(n, cfg) for n in lens]
         reg["spec"] = torch.from_numpy(compute_mask_indices((B, T), 0.3, 10, frame_lens=flen, min_masks=2))

@@ -135,10 +135,9 @@ def test_pr_training_step_vs_reference(cuda):
 
 
 def test_training_refuses_unbuilt_configs(cuda):
-    cfg = cfg_base(vocab_size=46, attention_dropout=0.1)
+    cfg = cfg_base(vocab_size=46)
     name = register_in_memory_checkpoint("mem://base-seed1-drop", backbone_sd(cfg_base(vocab_size=46), 1))
-    pr = Wav2Vec2_PR(cfg, None, name, VOCAB)
-    pr.wav2vec2.freeze_feature_encoder()
+    pr = Wav2Vec2_PR(cfg, None, name, VOCAB)          # conv feature encoder NOT frozen: its backward is not built
     pr = pr.to(cuda).train()
     wav = W.waveforms(1, 16000, None, seed=1)
     labels, _ = W.phoneme_sequences(1, 5, 5, 2, 45, seed=3, pad=-100)
@@ -179,8 +178,8 @@ def test_training_step_with_regularisers_replayed_by_the_oracle(cuda):
     from aptai_b200 import ops
     from oracle import w2v2 as ow
     cfg = cfg_base(vocab_size=46, hidden_dropout=0.1, activation_dropout=0.1, feat_proj_dropout=0.1, final_dropout=0.1,
-                   layerdrop=0.25, apply_spec_augment=True, mask_time_prob=0.2, mask_time_length=10,
-                   mask_time_min_masks=2)
+                   attention_dropout=0.1, layerdrop=0.25, apply_spec_augment=True, mask_time_prob=0.2,
+                   mask_time_length=10, mask_time_min_masks=2)
     sd0 = backbone_sd(cfg_base(vocab_size=46), 1)
     name = register_in_memory_checkpoint("mem://base-seed1-reg", sd0)
     pr = Wav2Vec2_PR(cfg, None, name, VOCAB)
@@ -211,6 +210,7 @@ def test_training_step_with_regularisers_replayed_by_the_oracle(cuda):
         reg[("attn", l)] = mask(l, w2v.SITE_ATTN, (B, T, H), 0.1)
         reg[("act", l)] = mask(l, w2v.SITE_ACT, (B, T, Fi), 0.1)
         reg[("ffn", l)] = mask(l, w2v.SITE_FFN, (B, T, H), 0.1)
+        reg[("attp", l)] = ops.attention_dropout_mask(B, T, 12, 0.1, w2v.drop_seed(step, l, w2v.SITE_ATTN_P), cuda).cpu()
     spec = torch.zeros(B * T, dtype=torch.bool)
     spec[info["spec_rows"].cpu()] = True
     reg["spec"] = spec.view(B, T)
