@@ -56,13 +56,22 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--model", default="large", choices=["large", "base"])
+    ap.add_argument("--regularised", action="store_true",
+                    help="XLS-R's published training regularisers: hidden/attention dropout 0.1, layerdrop 0.1, "
+                         "SpecAugment mask_time_prob 0.075, head dropouts 0.1")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    cfg = (W2V2Config.large if args.model == "large" else W2V2Config.base)(**NO_REG)
+    reg = dict(NO_REG)
+    if args.regularised:
+        reg.update(hidden_dropout=0.1, attention_dropout=0.1, activation_dropout=0.0, feat_proj_dropout=0.0,
+                   final_dropout=0.1, layerdrop=0.1, apply_spec_augment=True, mask_time_prob=0.075, mask_time_length=10,
+                   mask_time_min_masks=2)
+    cfg = (W2V2Config.large if args.model == "large" else W2V2Config.base)(**reg)
+    hd = 0.1 if args.regularised else 0.0
     H = cfg.hidden_size
     name = register_in_memory_checkpoint("mem://train-bench", backbone_state_dict(cfg, 0))
     B = args.batch or (32 if args.config == 4 else 16)
@@ -70,7 +79,7 @@ def main():
     rng = np.random.Generator(np.random.PCG64(21 + rank))
     g = torch.Generator().manual_seed(1234 + rank)
     if args.config == 4:
-        model = APTAI(dev, VOCAB, name, cfg, None, phn_drop=0.0, tv_drop=0.0)
+        model = APTAI(dev, VOCAB, name, cfg, None, phn_drop=hd, tv_drop=hd)
         tvw, tvb = linear_params(101, 9, H)
         pw, pb = linear_params(102, 46, H)
         with torch.no_grad():
@@ -148,6 +157,7 @@ def main():
         print(json.dumps({
             "workload": f"config{args.config}: {'APTAI training step' if args.config == 4 else 'Wav2Vec2_PR CTC fwd+bwd+Adam'}"
                         f", {args.model} backbone, batch {B}/GPU, max 8 s, frozen conv encoder, fused Adam"
+                        + (", dropout 0.1 (hidden/attention/heads) + LayerDrop 0.1 + SpecAugment 0.075" if args.regularised else "")
                         + (", DP all-reduce overlapped with backward" if world > 1 else ""),
             "n_gpus": world, "ms_per_step": ms, "audio_s_per_s": world * audio_s / (ms * 1e-3),
             "fwd_ms": fwd, "bwd_ms": bwd, "opt_ms": optm, "model_tflops_per_gpu": fl / (ms * 1e-3) / 1e12,
