@@ -90,7 +90,7 @@ def test_aptai_training_step_vs_reference(cuda):
     opt = FusedAdam([p for p in m.parameters() if p.requires_grad], lr=1e-4)
     opt.zero_grad()
     out = m(*args)
-    losses = np.asarray([float(out["loss"]), float(out["mse_loss"]), float(out["ce_loss"])])
+    losses = np.asarray([float(out["loss"].detach()), float(out["mse_loss"]), float(out["ce_loss"])])
     np.testing.assert_allclose(losses, g["t2_losses"], rtol=2e-3)
     assert out["loss"].requires_grad
     out["loss"].backward()
@@ -128,7 +128,7 @@ def test_pr_training_step_vs_reference(cuda):
     labels, _ = W.phoneme_sequences(3, 10, 40, 2, 45, seed=7, pad=-100)
     labels[2, 5:] = -100
     r = pr(wav3.to(cuda), torch.tensor(lens3, device=cuda), labels.to(cuda))
-    assert abs(float(r["loss"]) - float(g["t3_loss"][0])) / float(g["t3_loss"][0]) < 1e-3
+    assert abs(float(r["loss"].detach()) - float(g["t3_loss"][0])) / float(g["t3_loss"][0]) < 1e-3
     r["loss"].backward()
     worst, low = _check_grads(pr, g, "t3")
     print("PR base: worst grad-norm deviation", worst, "lowest slice cosine", low)
@@ -227,7 +227,7 @@ def test_training_step_with_regularisers_replayed_by_the_oracle(cuda):
     lp = F.log_softmax(logits, dim=-1, dtype=torch.float32).transpose(0, 1)
     loss = F.ctc_loss(lp, labels[labels >= 0], flen, (labels >= 0).sum(-1), blank=0, reduction="mean", zero_infinity=True)
     loss.backward()
-    assert abs(float(r["loss"]) - float(loss)) / float(loss) < 2e-3, (float(r["loss"]), float(loss))
+    assert abs(float(r["loss"].detach()) - float(loss)) / float(loss) < 2e-3, (float(r["loss"].detach()), float(loss))
     params = dict(pr.named_parameters())
     norms = {k: float(sd[k].grad.double().norm()) for k in trainable if sd[k].grad is not None}
     floor = 1e-4 * float(np.median(list(norms.values())))
@@ -283,7 +283,7 @@ def test_aptai_head_dropouts_replayed_by_the_oracle(cuda):
     logits = F.linear(F.leaky_relu(h * m_phn), ws[2], ws[3])
     loss, _, _ = oh.aptai_losses(tv, logits, phn, torch.stack(tvs, -1).float())
     loss.backward()
-    assert abs(float(out["loss"]) - float(loss)) / float(loss) < 2e-3
+    assert abs(float(out["loss"].detach()) - float(loss.detach())) / float(loss.detach()) < 2e-3
     params = dict(m.named_parameters())
     for name_, ref in (("tv_head.2.weight", ws[0]), ("tv_head.2.bias", ws[1]), ("phn_head.2.weight", ws[2]),
                        ("phn_head.2.bias", ws[3]), ("wav2vec2.encoder.layers.11.feed_forward.output_dense.weight",
