@@ -17,6 +17,8 @@
 #include "common.h"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 namespace aptai {
 
 constexpr int TN_BM = 128;       // dY columns per tile  (UMMA M)
@@ -218,6 +220,212 @@ gemm_tn_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cluster of 2, tcgen05.mma.cta_group::2): 256 dY columns x 256 X columns per tile.  Each CTA stages
+// only ITS 128 dY columns (A half) and ITS 128 X columns (B half) per 64-frame block — 32 KB per stage instead of the
+// 48 KB of the single-CTA tile for the same tensor work per SM — which is what the single-CTA kernel is bound by
+// (L2 -> SM crossbar at ~12 TB/s, tensor pipe 53 %: profiles/r01_wgrad_tn_train_c4.md).  The leader CTA issues every
+// MMA; each CTA owns the 128 accumulator lanes of its dY columns and reduces them into the gradient itself.
+constexpr int TP_STAGES = 6;
+constexpr int TP_HALF_BYTES = TN_BK * 128 * 2;               // 16 KB: two 64x64 boxes
+constexpr int TP_STAGE_BYTES = 2 * TP_HALF_BYTES;            // A half + B half
+constexpr int TP_SMEM = 1024 + TP_STAGES * TP_STAGE_BYTES + 256;
+
+__device__ __forceinline__ void tma_load_3d_cg2(const CUtensorMap* m, uint32_t bar_cluster_addr, void* dst, int c0,
+                                                int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TN_THREADS, 1)
+gemm_tn_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                          const TnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TP_STAGES * TP_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + TP_STAGES;
+  uint64_t* tfull_bar = empty_bar + TP_STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int item0 = blockIdx.x >> 1, item_step = gridDim.x >> 1;
+
+  if (warp == TN_W_TMA && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == TN_W_MMA && lane == 0) {
+    for (int i = 0; i < TP_STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 16);        // 8 epilogue warps in each CTA of the pair
+    }
+    fence_mbar_init();
+  }
+  if (warp == TN_W_ALLOC) tmem_alloc_cg2(tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int tiles = p.n_tiles * p.k_tiles;
+
+  if (warp == TN_W_TMA) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = item0; item < p.items; item += item_step) {
+        const int tile = item % tiles, sp = item / tiles;
+        const int nt = tile / p.k_tiles, kt = tile - nt * p.k_tiles;
+        const int kb0 = static_cast<int>((static_cast<long long>(p.total_kb) * sp) / p.splits);
+        const int kb1 = static_cast<int>((static_cast<long long>(p.total_kb) * (sp + 1)) / p.splits);
+        const int a_col = nt * 256 + static_cast<int>(rank) * 128;
+        const int b_col = kt * 256 + static_cast<int>(rank) * 128;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const int m0 = kb * TN_BK;
+          mbar_wait_backoff(&empty_bar[stage], phase ^ 1, 64);
+          uint8_t* sa = smem + stage * TP_STAGE_BYTES;
+          uint8_t* sb = sa + TP_HALF_BYTES;
+          // both CTAs' bytes are counted on the LEADER's barrier; only the leader arms it
+          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * TP_STAGE_BYTES);
+          const uint32_t fb = map_to_cta(&full_bar[stage], 0);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) tma_load_3d_cg2(&tmA, fb, sa + j * 8192, a_col + j * 64, m0, 0);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) tma_load_3d_cg2(&tmB, fb, sb + j * 8192, b_col + j * 64, m0, 0);
+          if (++stage == TP_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == TN_W_MMA) {
+    if (lane == 0 && rank == 0) {
+      // D = f32, A = B = bf16, both MN-major, M = 256 (128 per CTA), N = 256 (128 per CTA)
+      constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
+                                 (static_cast<uint32_t>(256 >> 3) << 17) | (static_cast<uint32_t>(256 >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int item = item0; item < p.items; item += item_step) {
+        const int sp = item / tiles;
+        const int kb0 = static_cast<int>((static_cast<long long>(p.total_kb) * sp) / p.splits);
+        const int kb1 = static_cast<int>((static_cast<long long>(p.total_kb) * (sp + 1)) / p.splits);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + stage * TP_STAGE_BYTES);
+          const uint32_t b_base = a_base + TP_HALF_BYTES;
+#pragma unroll
+          for (int k = 0; k < TN_BK / 16; ++k)
+            umma_bf16_cg2(d_tmem, umma_desc_sw128_mn_blocks(a_base + k * 2048),
+                          umma_desc_sw128_mn_blocks(b_base + k * 2048), IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+          umma_commit_cg2(&empty_bar[stage], 0x3);
+          if (++stage == TP_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_cg2(&tfull_bar[acc], 0x3);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp < 8) {
+    const int q = warp & 3, half = warp >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t tempty_leader0 = map_to_cta(&tempty_bar[0], 0);
+    for (int item = item0; item < p.items; item += item_step) {
+      const int tile = item % tiles, sp = item / tiles;
+      const int nt = tile / p.k_tiles, kt = tile - nt * p.k_tiles;
+      const int kb0 = static_cast<int>((static_cast<long long>(p.total_kb) * sp) / p.splits);
+      const int kb1 = static_cast<int>((static_cast<long long>(p.total_kb) * (sp + 1)) / p.splits);
+      const int orow = nt * 256 + static_cast<int>(rank) * 128 + q * 32 + lane;
+      const bool row_ok = orow < p.out_rows;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      if (kb1 > kb0) {
+        const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * 256;
+        float* orp = p.out + static_cast<long long>(orow) * p.ldo + static_cast<long long>(kt) * 256;
+        const int col_lim = p.out_cols - kt * 256;
+        uint32_t nxt[32];
+        tmem_ld32(t_row + half * 128, nxt);
+#pragma unroll 1
+        for (int c = half * 128; c < (half + 1) * 128; c += 32) {
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(nxt[i]) * p.scale;
+          if (c + 32 < (half + 1) * 128) tmem_ld32(t_row + c + 32, nxt);
+          if (row_ok) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4)
+              if (c + i < col_lim) red_add_v4(orp + c + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tempty_leader0 + acc * 8);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == TN_W_ALLOC) {
+    tc_fence_after();
+    tmem_dealloc_cg2(tmem_base, 512);
+  }
+}
+
+// frame-dimension splits so that the work items fill `slots` concurrent workers in whole waves
+static int choose_splits(int tiles, int slots, int total_kb) {
+  int best = 1;
+  double best_eff = 0.0;
+  for (int s = 1; s <= 16; ++s) {
+    if (total_kb / s < 8 && s > 1) break;
+    const int items = tiles * s;
+    const int waves = (items + slots - 1) / slots;
+    const double eff = static_cast<double>(items) / (static_cast<double>(waves) * slots);
+    if (eff > best_eff + 0.02) {
+      best_eff = eff;
+      best = s;
+    }
+  }
+  return best;
+}
+
+static int launch_tn_pair(const CUtensorMap& ta, const CUtensorMap& tb, TnParams& p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tn_wgrad_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TP_SMEM);
+    if (e != cudaSuccess) {
+      set_error("gemm_wgrad(pair): cudaFuncSetAttribute(%d bytes): %s", TP_SMEM, cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    attr_set = true;
+  }
+  const int tiles = p.n_tiles * p.k_tiles;
+  const int clusters = num_sms() / 2;
+  p.splits = choose_splits(tiles, clusters, p.total_kb);
+  p.items = tiles * p.splits;
+  const int grid = 2 * (p.items < clusters ? p.items : clusters);
+  gemm_tn_wgrad_pair_kernel<<<grid, TN_THREADS, TP_SMEM, st>>>(ta, tb, p);
+  return after_launch("gemm_tn_wgrad_pair");
+}
+
 static int launch_tn(const CUtensorMap& ta, const CUtensorMap& tb, TnParams& p, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -293,6 +501,12 @@ extern "C" int aptai_gemm_wgrad_bf16(const void* dy, int64_t dy_ld, const void* 
   p.ldo = dw_ld;
   p.out = dw;
   p.scale = scale;
+  static const bool force_single = getenv("APTAI_WGRAD_SINGLE") != nullptr;      // A/B switch for profiles/
+  if (!force_single && N >= 256 && K >= 256) {
+    p.n_tiles = (N + 255) / 256;
+    p.k_tiles = (K + 255) / 256;
+    return launch_tn_pair(ta, tb, p, reinterpret_cast<cudaStream_t>(stream));
+  }
   return launch_tn(ta, tb, p, reinterpret_cast<cudaStream_t>(stream));
 }
 
