@@ -64,6 +64,7 @@ __device__ __forceinline__ float ab_ex2(float x) {
   return y;
 }
 
+template <bool DROP>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
                      const AttnBwdParams p) {
@@ -143,8 +144,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   } else if (warp == AB_W_MMA) {
     // ---------------------------------------------------------------- phase 1: S^T = K Q^T, dP^T = V dO^T
     if (lane == 0) {
-      constexpr uint32_t ID_S = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(AB_T >> 4) << 24) |
-                                (static_cast<uint32_t>(AB_T >> 3) << 17);                            // N=128, K-major
+      constexpr uint32_t ID_S0 = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(AB_T >> 4) << 24);   // K-major
       uint32_t g = 0, it = 0;
       for (int w = blockIdx.x; w < p.items; w += gridDim.x) {
         const int j = w % p.n_t;
@@ -160,6 +160,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           // the compute warps have finished reading tile g-1's S^T / dP^T once its P^T / dS^T are published
           if (g > 0) mbar_wait(pds_full, (g - 1) & 1);
           tc_fence_after();
+          // only the queries that exist (rounded up to 16): the last tile of an utterance is mostly padding
+          const int nq16 = (min(AB_T, p.T - i * AB_T) + 15) & ~15;
+          const uint32_t ID_S = ID_S0 | (static_cast<uint32_t>(nq16 >> 3) << 17);
 #pragma unroll
           for (int k = 0; k < AB_D / 16; ++k)
             umma_bf16(tmem_base + TB_ST, umma_desc_sw128(k_addr + k * 32), umma_desc_sw128(q_addr + k * 32), ID_S,
@@ -195,19 +198,18 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           mbar_wait(pds_full, g & 1);                          // P^T / dS^T of this tile are in shared memory
           if (i == 0 && warp != AB_W_DQ) mbar_wait(dkv_empty, (it & 1) ^ 1);   // previous item's dK/dV were read out
           tc_fence_after();
+          const int kq = ((min(AB_T, p.T - i * AB_T) + 15) & ~15) / 16;        // 16-query steps that exist
+          const int kk = ((min(AB_T, klen - j * AB_T) + 15) & ~15) / 16;       // 16-key steps that exist
           if (warp == AB_W_DV) {
-#pragma unroll
-            for (int k = 0; k < AB_T / 16; ++k)
+            for (int k = 0; k < kq; ++k)
               umma_bf16(tmem_base + TB_DV, umma_desc_sw128(pt_addr + (k >> 2) * (AB_PT / 2) + (k & 3) * 32),
                         ab_desc_mn(do_addr + k * 2048, 1024), ID_KV, (i | k) != 0 ? 1u : 0u);
           } else if (warp == AB_W_DK) {
-#pragma unroll
-            for (int k = 0; k < AB_T / 16; ++k)
+            for (int k = 0; k < kq; ++k)
               umma_bf16(tmem_base + TB_DK, umma_desc_sw128(dst_addr + (k >> 2) * (AB_PT / 2) + (k & 3) * 32),
                         ab_desc_mn(q_addr + k * 2048, 1024), ID_KV, (i | k) != 0 ? 1u : 0u);
           } else {
-#pragma unroll
-            for (int k = 0; k < AB_T / 16; ++k)
+            for (int k = 0; k < kk; ++k)
               umma_bf16(tmem_base + TB_DQ, ab_desc_mn(dst_addr + k * 2048, AB_PT / 2),
                         ab_desc_mn(k_addr + k * 2048, 1024), ID_Q, k != 0 ? 1u : 0u);
             umma_commit(dq_full);
@@ -248,7 +250,6 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         continue;
       }
       const bool key_ok = key < klen;
-      const bool drop = p.drop_thresh24 != 0;
       const uint32_t seed_bh = attn_drop_seed_bh(p.drop_seed, static_cast<uint32_t>(bh));
       const float* lse_bh = p.lse + static_cast<long long>(bh) * p.T;
       const float* d_bh = p.dvec + static_cast<long long>(bh) * p.T;
@@ -266,8 +267,23 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         tc_fence_after();
         uint8_t* pt_row = sPT + hf * (AB_PT / 2) + row * 128;
         uint8_t* ds_row = sDST + hf * (AB_PT / 2) + row * 128;
+        const int nq16 = (min(AB_T, p.T - i * AB_T) + 15) & ~15;
+        const int nk16 = (min(AB_T, klen - j * AB_T) + 15) & ~15;
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
+          // padding: query columns beyond the utterance are never read by dV / dK (their k-steps stop at nq16), key
+          // rows beyond nk16 are never read by dQ; key rows in [klen, nk16) must be zero
+          // (all decisions warp-uniform: tcgen05.ld below is a .sync.aligned instruction)
+          if (hf * 64 + c * 32 >= nq16 || q4 * 32 >= nk16) continue;
+          if (j * AB_T + q4 * 32 >= klen) {           // every key row of this warp is padding
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int unit = (c * 4 + u) ^ (row & 7);
+              *reinterpret_cast<uint4*>(pt_row + (unit << 4)) = make_uint4(0u, 0u, 0u, 0u);
+              *reinterpret_cast<uint4*>(ds_row + (unit << 4)) = make_uint4(0u, 0u, 0u, 0u);
+            }
+            continue;
+          }
           uint32_t s[32], dp[32];
           tmem_ld32(t_lane + TB_ST + hf * 64 + c * 32, s);
           tmem_ld32(t_lane + TB_DPT + hf * 64 + c * 32, dp);
@@ -282,7 +298,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
               if (!key_ok) pe = 0.f;
               float dpe = __uint_as_float(dp[u * 8 + e]);
               float pd = pe;                      // what fed P V in the forward: the dropped, rescaled probability
-              if (drop) {
+              if (DROP) {
                 const float mk = attn_drop_keep(seed_bh, static_cast<uint32_t>(i * AB_T + qc), static_cast<uint32_t>(key),
                                                 static_cast<uint32_t>(p.T), p.drop_thresh24) ? p.drop_inv_keep : 0.f;
                 pd *= mk;
@@ -332,7 +348,13 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         tmem_ld32(t_lane + TB_DK + hf * 32, rk);
         tmem_ld32(t_lane + TB_DV + hf * 32, rv);
         tmem_ld_wait();
-        if (key < p.T) {
+        if (key < p.T && !key_ok) {       // padded key: its accumulator rows are undefined (P^T rows not written)
+#pragma unroll
+          for (int e = 0; e < 32; e += 8) {
+            *reinterpret_cast<uint4*>(dk_out + e) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(dv_out + e) = make_uint4(0u, 0u, 0u, 0u);
+          }
+        } else if (key < p.T) {
 #pragma unroll
           for (int e = 0; e < 32; e += 8) {
             *reinterpret_cast<uint4*>(dk_out + e) =
@@ -419,14 +441,20 @@ static int attention_bwd_impl(const void* qkv, const void* d_ctx, const float* l
   p.drop_seed = drop_seed;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
-    if (e != cudaSuccess) {
-      set_error("attention_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      return static_cast<int>(e);
+    for (int v = 0; v < 2; ++v) {
+      const void* fn = v ? reinterpret_cast<const void*>(attention_bwd_kernel<true>)
+                         : reinterpret_cast<const void*>(attention_bwd_kernel<false>);
+      cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM);
+      if (e != cudaSuccess) {
+        set_error("attention_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        return static_cast<int>(e);
+      }
     }
     attr_set = true;
   }
   const int grid = p.items < num_sms() ? p.items : num_sms();
-  attention_bwd_kernel<<<grid, AB_THREADS, AB_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tmq, tmdo, p);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (drop_p > 0.f) attention_bwd_kernel<true><<<grid, AB_THREADS, AB_SMEM, st>>>(tmq, tmdo, p);
+  else attention_bwd_kernel<false><<<grid, AB_THREADS, AB_SMEM, st>>>(tmq, tmdo, p);
   return after_launch("attention_bwd");
 }
