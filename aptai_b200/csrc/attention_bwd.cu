@@ -25,7 +25,7 @@ constexpr int AB_T = 128;                 // queries per tile = keys per block
 constexpr int AB_D = 64;
 constexpr int AB_TILE = AB_T * AB_D * 2;  // 16 KB
 constexpr int AB_PT = AB_T * AB_T * 2;    // 32 KB (two [128][64] sub-tiles)
-constexpr int AB_DATA = 2 * AB_TILE /*K,V*/ + 4 * AB_TILE /*Q,dO x2*/ + 2 * AB_PT /*P^T, dS^T*/;   // 160 KB
+constexpr int AB_DATA = 2 * AB_TILE /*K,V*/ + 4 * AB_TILE /*Q,dO x2*/ + 4 * AB_PT /*P^T, dS^T x2*/;   // 224 KB
 constexpr int AB_STATS = 2 * 2 * AB_T * 4;    // [buf][lse | D][128]
 constexpr int AB_SMEM = AB_DATA + AB_STATS + 256;
 // warps 0..7 compute, 8 TMA, 9 MMA (S^T, dP^T), 10 TMEM alloc, 11 / 12 / 13 MMA issuers of dV / dK / dQ: a tcgen05.mma
@@ -73,8 +73,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   uint8_t* sV = smem + AB_TILE;
   uint8_t* sQ = smem + 2 * AB_TILE;          // [2]
   uint8_t* sDO = smem + 4 * AB_TILE;         // [2]
-  uint8_t* sPT = smem + 6 * AB_TILE;
-  uint8_t* sDST = sPT + AB_PT;
+  uint8_t* sPT = smem + 6 * AB_TILE;         // [2]  (double buffered like Q / dO: tile g uses buffer g & 1)
+  uint8_t* sDST = sPT + 2 * AB_PT;           // [2]
   float* stats = reinterpret_cast<float*>(smem + AB_DATA);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AB_DATA + AB_STATS);
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
@@ -86,11 +86,12 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   uint64_t* qdo_full = bars + 2;    // [2]
   uint64_t* qdo_empty = bars + 4;   // [2]
   uint64_t* s_full = bars + 6;
-  uint64_t* pds_full = bars + 7;
-  uint64_t* dq_full = bars + 8;
-  uint64_t* dkv_full = bars + 9;
-  uint64_t* dkv_empty = bars + 10;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* pds_full = bars + 7;    // [2]
+  uint64_t* dq_full = bars + 9;
+  uint64_t* dq_empty = bars + 10;
+  uint64_t* dkv_full = bars + 11;
+  uint64_t* dkv_empty = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == AB_W_TMA && lane == 0) {
@@ -105,8 +106,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       mbar_init(&qdo_empty[i], 3);      // dV, dK and dQ issuers have all consumed Q_i / dO_i / P^T / dS^T
     }
     mbar_init(s_full, 1);
-    mbar_init(pds_full, 8);
+    mbar_init(&pds_full[0], 8);
+    mbar_init(&pds_full[1], 8);
     mbar_init(dq_full, 1);
+    mbar_init(dq_empty, 8);
     mbar_init(dkv_full, 2);             // dV and dK issuers
     mbar_init(dkv_empty, 8);
     fence_mbar_init();
@@ -158,7 +161,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           const uint32_t q_addr = smem_u32(sQ + buf * AB_TILE), do_addr = smem_u32(sDO + buf * AB_TILE);
           mbar_wait(&qdo_full[buf], (g >> 1) & 1);
           // the compute warps have finished reading tile g-1's S^T / dP^T once its P^T / dS^T are published
-          if (g > 0) mbar_wait(pds_full, (g - 1) & 1);
+          if (g > 0) mbar_wait(&pds_full[(g - 1) & 1], ((g - 1) >> 1) & 1);
           tc_fence_after();
           // only the queries that exist (rounded up to 16): the last tile of an utterance is mostly padding
           const int nq16 = (min(AB_T, p.T - i * AB_T) + 15) & ~15;
@@ -190,12 +193,14 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         if (j * AB_T >= klen) continue;
         mbar_wait(kv_full, it & 1);
         const uint32_t k_addr = smem_u32(sK);
-        const uint32_t pt_addr = smem_u32(sPT), dst_addr = smem_u32(sDST);
         for (int i = 0; i < p.n_t; ++i, ++g) {
           const uint32_t buf = g & 1;
           const uint32_t q_addr = smem_u32(sQ + buf * AB_TILE), do_addr = smem_u32(sDO + buf * AB_TILE);
+          const uint32_t pt_addr = smem_u32(sPT + buf * AB_PT), dst_addr = smem_u32(sDST + buf * AB_PT);
           mbar_wait(&qdo_full[buf], (g >> 1) & 1);
-          mbar_wait(pds_full, g & 1);                          // P^T / dS^T of this tile are in shared memory
+          mbar_wait(&pds_full[buf], (g >> 1) & 1);             // P^T / dS^T of this tile are in shared memory
+          // the dQ accumulator is single: the compute warps must have read out the previous tile's dQ
+          if (warp == AB_W_DQ && g > 0) mbar_wait(dq_empty, (g - 1) & 1);
           if (i == 0 && warp != AB_W_DQ) mbar_wait(dkv_empty, (it & 1) ^ 1);   // previous item's dK/dV were read out
           tc_fence_after();
           const int kq = ((min(AB_T, p.T - i * AB_T) + 15) & ~15) / 16;        // 16-query steps that exist
@@ -253,6 +258,27 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       const uint32_t seed_bh = attn_drop_seed_bh(p.drop_seed, static_cast<uint32_t>(bh));
       const float* lse_bh = p.lse + static_cast<long long>(bh) * p.T;
       const float* d_bh = p.dvec + static_cast<long long>(bh) * p.T;
+      // dQ partial of (query tile qi_tile, this key block): TMEM -> fp32 vector reductions into dq32
+      auto dq_out = [&](int qi_tile, uint32_t gg) {
+        mbar_wait(dq_full, gg & 1);
+        tc_fence_after();
+        uint32_t r[32];
+        tmem_ld32(t_lane + TB_DQ + hf * 32, r);
+        tmem_ld_wait();
+        const int qi = qi_tile * AB_T + row;
+        if (qi < p.T) {
+          float* dst = p.dq32 + (row0 + qi) * p.H + h * AB_D + hf * 32;
+#pragma unroll
+          for (int e = 0; e < 32; e += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + e), "f"(__uint_as_float(r[e])),
+                         "f"(__uint_as_float(r[e + 1])), "f"(__uint_as_float(r[e + 2])),
+                         "f"(__uint_as_float(r[e + 3]))
+                         : "memory");
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dq_empty);
+      };
       for (int i = 0; i < p.n_t; ++i, ++g) {
         float* st = stats + (g & 1) * 2 * AB_T;
         {
@@ -261,12 +287,12 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           else st[ctid] = qi < p.T ? __ldg(d_bh + qi) : 0.f;
         }
         named_bar_sync(1, 256);
+        // s_full(g) implies that Q/dO of tile g were loaded, i.e. that the phase-2 MMAs of tile g-2 (the previous
+        // users of buffer g & 1, P^T / dS^T included) have completed
         mbar_wait(s_full, g & 1);
-        // P^T / dS^T of tile g-1 have been consumed by all three phase-2 issuers
-        if (g > 0) mbar_wait(&qdo_empty[(g - 1) & 1], ((g - 1) >> 1) & 1);
         tc_fence_after();
-        uint8_t* pt_row = sPT + hf * (AB_PT / 2) + row * 128;
-        uint8_t* ds_row = sDST + hf * (AB_PT / 2) + row * 128;
+        uint8_t* pt_row = sPT + (g & 1) * AB_PT + hf * (AB_PT / 2) + row * 128;
+        uint8_t* ds_row = sDST + (g & 1) * AB_PT + hf * (AB_PT / 2) + row * 128;
         const int nq16 = (min(AB_T, p.T - i * AB_T) + 15) & ~15;
         const int nk16 = (min(AB_T, klen - j * AB_T) + 15) & ~15;
 #pragma unroll
@@ -319,27 +345,11 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
         tc_fence_before();
         fence_async_proxy();
         __syncwarp();
-        if (lane == 0) mbar_arrive(pds_full);
-        // dQ partial of this (query tile, key block)
-        mbar_wait(dq_full, g & 1);
-        tc_fence_after();
-        {
-          uint32_t r[32];
-          tmem_ld32(t_lane + TB_DQ + hf * 32, r);
-          tmem_ld_wait();
-          const int qi = i * AB_T + row;
-          if (qi < p.T) {
-            float* dst = p.dq32 + (row0 + qi) * p.H + h * AB_D + hf * 32;
-#pragma unroll
-            for (int e = 0; e < 32; e += 4)
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + e), "f"(__uint_as_float(r[e])),
-                           "f"(__uint_as_float(r[e + 1])), "f"(__uint_as_float(r[e + 2])),
-                           "f"(__uint_as_float(r[e + 3]))
-                           : "memory");
-          }
-        }
-        tc_fence_before();
+        if (lane == 0) mbar_arrive(&pds_full[g & 1]);
+        // dQ of the PREVIOUS query tile: its MMAs ran on the tensor pipe while this tile's P^T / dS^T were computed
+        if (i > 0) dq_out(i - 1, g - 1);
       }
+      dq_out(p.n_t - 1, g - 1);
       // dK_j, dV_j
       mbar_wait(dkv_full, it & 1);
       tc_fence_after();
