@@ -361,24 +361,35 @@ __global__ void posconv_wn_apply_kernel(const float* __restrict__ dwf, const flo
 }
 
 // ---------------------------------------------------------------------------------------------- attention backward helpers
-// D[b][h][t] = sum_d dO[t][h*64+d] * O[t][h*64+d]   (one warp per (row, head); bf16 inputs [M][H])
+// D[b][h][t] = sum_d dO[t][h*64+d] * O[t][h*64+d]   (bf16 inputs [M][heads*64]).  One warp per row: a lane reads 16 bytes
+// (8 channels) of both tensors per step, 8 lanes cover one head and combine with three shuffles.
 __global__ void __launch_bounds__(256)
 attn_bwd_dot_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* __restrict__ O, int B, int T,
                     int heads, float* __restrict__ D) {
   const int lane = threadIdx.x & 31;
-  const long long item = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
-  const long long total = static_cast<long long>(B) * T * heads;
-  if (item >= total) return;
-  const int h = static_cast<int>(item % heads);
-  const long long row = item / heads;
-  const long long off = row * heads * 64 + h * 64 + lane * 2;
-  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dO + off));
-  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(O + off));
-  float s = a.x * b.x + a.y * b.y;
-  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) {
-    const long long b_ = row / T, t = row - b_ * T;
-    D[(b_ * heads + h) * T + t] = s;
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= static_cast<long long>(B) * T) return;
+  const int H = heads * 64;
+  const long long b_ = row / T, t = row - b_ * T;
+  const uint4* pa = reinterpret_cast<const uint4*>(dO + row * H);
+  const uint4* pb = reinterpret_cast<const uint4*>(O + row * H);
+  for (int c0 = 0; c0 < H; c0 += 256) {
+    const int c = c0 + lane * 8;
+    float s = 0.f;
+    if (c < H) {
+      const uint4 a = __ldg(pa + c / 8), b = __ldg(pb + c / 8);
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[j]));
+        const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bw[j]));
+        s = fmaf(x.x, y.x, fmaf(x.y, y.y, s));
+      }
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    if ((lane & 7) == 0 && c < H) D[(b_ * heads + c / 64) * T + t] = s;
   }
 }
 
@@ -614,7 +625,7 @@ extern "C" int aptai_attention_bwd_dot(const void* d_ctx, const void* ctx, int B
                                        void* stream) {
   if (int rc = check_arch()) return rc;
   APTAI_REQUIRE(d_ctx && ctx && D && B >= 1 && T >= 1 && heads >= 1, "attention_bwd_dot: bad arguments");
-  const long long total = static_cast<long long>(B) * T * heads;
+  const long long total = static_cast<long long>(B) * T;
   attn_bwd_dot_kernel<<<static_cast<unsigned>((total + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(d_ctx), reinterpret_cast<const __nv_bfloat16*>(ctx), B, T, heads, D);
   return after_launch("attention_bwd_dot");

@@ -78,7 +78,10 @@ template <int BN, bool LN, bool CTA2>
 __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p) {
   using C = GemmCfg<BN, CTA2>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment by POINTER arithmetic on the __shared__ array: going through an integer would make the
+  // compiler lose the address space and emit generic ST.E / LD.E for the epilogue's staging buffer (measured:
+  // long-scoreboard stalls on every staging access, profiles/r01_gemm_2cta_outproj_m75776.md)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
   uint64_t* tfull_bar = empty_bar + C::STAGES;
@@ -290,6 +293,21 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         rstd = rsqrtf(var + p.ln_eps);
       }
 
+      // residual block of the first chunk, requested before the accumulator is even complete (coalesced path)
+      float4 res_next[8];
+      if constexpr (!LN && CH == 32) {
+        if (p.residual) {
+          const int lrow0 = lane >> 3, lunit0 = lane & 7;
+          const long long offr = out_off - static_cast<long long>(lane) * p.ldo + n_tile0 + half * HALF_N;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + lrow0;
+            res_next[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r - lane + rr < p.rows_per_seg)
+              res_next[i] = __ldg(reinterpret_cast<const float4*>(p.residual + offr + rr * p.ldo + lunit0 * 4));
+          }
+        }
+      }
       // software pipeline: the tcgen05.ld of chunk c+1 is in flight while chunk c is processed
       uint32_t nxt[CH];
       tmem_ld_chunk<CH>(t_row + half * HALF_N, nxt);
@@ -377,15 +395,23 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
             __syncwarp();
           }
           if (p.residual) {
+            // the residual block of THIS chunk was requested one chunk ago (res_next): its global latency is hidden
+            // behind the previous chunk's work instead of being exposed four times per tile
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int rr = i * 4 + lrow;
-              float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (r_first + rr < p.rows_per_seg)
-                x = __ldg(reinterpret_cast<const float4*>(p.residual + off0 + rr * p.ldo + lunit * 4));
-              *reinterpret_cast<float4*>(stg + rr * 32 + ((lunit ^ (rr & 7)) << 2)) = x;
+              *reinterpret_cast<float4*>(stg + rr * 32 + ((lunit ^ (rr & 7)) << 2)) = res_next[i];
             }
             __syncwarp();
+            if (c + CH < (half + 1) * HALF_N) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int rr = i * 4 + lrow;
+                res_next[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r_first + rr < p.rows_per_seg)
+                  res_next[i] = __ldg(reinterpret_cast<const float4*>(p.residual + off0 + CH + rr * p.ldo + lunit * 4));
+              }
+            }
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               const float4 r4 = *reinterpret_cast<const float4*>(stg + lane * 32 + ((u ^ (lane & 7)) << 2));
@@ -457,7 +483,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (CTA2) mbar_arrive_cluster(tempty_leader0 + acc * 8);
+        if (CTA2) mbar_arrive_cluster_relaxed(tempty_leader0 + acc * 8);
         else mbar_arrive(&tempty_bar[acc]);
       }
       if (C::ACC_STAGES == 2) {

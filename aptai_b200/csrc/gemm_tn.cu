@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(TN_THREADS, 1)
 gemm_tn_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                      const TnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TN_STAGES * TN_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + TN_STAGES;
   uint64_t* tfull_bar = empty_bar + TN_STAGES;
@@ -243,7 +243,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TN_THREADS, 1)
 gemm_tn_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                           const TnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared address space
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + TP_STAGES * TP_STAGE_BYTES);
   uint64_t* empty_bar = full_bar + TP_STAGES;
   uint64_t* tfull_bar = empty_bar + TP_STAGES;

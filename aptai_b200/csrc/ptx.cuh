@@ -146,6 +146,12 @@ __device__ __forceinline__ uint32_t map_to_cta(const void* p, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
+// Relaxed variant for "accumulator drained" signals: the only accesses that must be ordered before the arrival are
+// this warp's tcgen05.ld (ordered by tcgen05.fence::before_thread_sync + wait::ld), not its global stores — the
+// release form makes the arriving thread wait for every outstanding global store of the epilogue first.
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t bar_cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
 
 // ---------------------------------------------------------------- TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {   // whole warp, .sync.aligned
