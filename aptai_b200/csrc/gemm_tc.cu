@@ -64,7 +64,11 @@ struct GemmCfg {
   static constexpr int BAR_BYTES = 256;
   static constexpr int LN_BYTES = BN >= 512 ? 2 * 2 * BLOCK_M * sizeof(float2) : 0;   // LN statistics exchange
   static constexpr int STG_BYTES = BN >= 512 ? 0 : 8 * 4096;     // 4 KB transpose buffer per epilogue warp
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES + LN_BYTES + STG_BYTES;
+  // fused-LayerNorm tile: bias | gamma | beta of the whole 512-wide row live in shared memory, loaded once per CTA
+  // (their per-element global loads were the top long-scoreboard stall of that epilogue: 27 % of the stall samples,
+  // profiles/r01_gemm_convln.md).  The other tiles have no shared memory left for it (4 stages + 32 KB staging).
+  static constexpr int VEC_BYTES = BN >= 512 ? 3 * 512 * 4 : 0;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES + LN_BYTES + STG_BYTES + VEC_BYTES;
 };
 
 template <int CH>
@@ -88,6 +92,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float2* ln_part = reinterpret_cast<float2*>(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES);
+  float* vecs = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES + C::LN_BYTES + C::STG_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -223,6 +228,15 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
     uint32_t acc_phase = 0;
     int ln_buf = 0;
     const uint32_t tempty_leader0 = CTA2 ? map_to_cta(&tempty_bar[0], 0) : 0u;
+    if constexpr (LN) {
+      for (int i = threadIdx.x; i < BN; i += EPI_THREADS) {
+        vecs[i] = p.bias ? __ldg(p.bias + i) : 0.f;
+        vecs[BN + i] = __ldg(p.gamma + i);
+        vecs[2 * BN + i] = __ldg(p.beta + i);
+      }
+      named_bar_sync(1, EPI_THREADS);
+    }
+
     for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
       const int n_blk = tile % p.n_tiles;
       const int mt = tile / p.n_tiles;
@@ -272,7 +286,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
 #pragma unroll
           for (int i = 0; i < CH; ++i) {
             float v = __uint_as_float(regs[i]);
-            if (p.bias) v += __ldg(p.bias + n_tile0 + c + i);
+            v += vecs[c + i];
             if (c == half * HALF_N && i == 0) pivot = v;
             const float d = v - pivot;
             s1 += d;
@@ -318,7 +332,13 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
 #pragma unroll
         for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(nxt[i]);
         if (c + CH < (half + 1) * HALF_N) tmem_ld_chunk<CH>(t_row + c + CH, nxt);
-        if (p.bias) {
+        if (LN) {
+#pragma unroll
+          for (int i = 0; i < CH; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(vecs + c + i);
+            v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+          }
+        } else if (p.bias) {
 #pragma unroll
           for (int i = 0; i < CH; i += 4) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
@@ -328,8 +348,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         if (LN) {
 #pragma unroll
           for (int i = 0; i < CH; i += 4) {
-            const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gamma + n0 + i));
-            const float4 e4 = __ldg(reinterpret_cast<const float4*>(p.beta + n0 + i));
+            const float4 g4 = *reinterpret_cast<const float4*>(vecs + BN + c + i);
+            const float4 e4 = *reinterpret_cast<const float4*>(vecs + 2 * BN + c + i);
             v[i] = fmaf((v[i] - mean) * rstd, g4.x, e4.x);
             v[i + 1] = fmaf((v[i + 1] - mean) * rstd, g4.y, e4.y);
             v[i + 2] = fmaf((v[i + 2] - mean) * rstd, g4.z, e4.z);
