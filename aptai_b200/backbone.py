@@ -210,6 +210,15 @@ class _Plan:
             self.conv_w = [None] + [h(l.conv.weight.permute(0, 2, 1).reshape(l.conv.weight.shape[0], -1))
                                     for l in cl[1:]]
             self.fp_w = h(m.feature_projection.projection.weight)
+            if self.train and any(p.requires_grad for p in m.feature_extractor.parameters()):
+                # unfrozen conv encoder: bf16 forward operands (the gradients flow in bf16, fp16 would underflow),
+                # per-tap transposed weights for the input-gradient GEMMs, conv-0's weight as [10][512]
+                bq = lambda t: t.detach().to(device=dev, dtype=BF16).contiguous()
+                self.conv_w_bf16 = [None] + [bq(l.conv.weight.permute(0, 2, 1).reshape(l.conv.weight.shape[0], -1))
+                                             for l in cl[1:]]
+                self.conv_wt = [None] + [[bq(l.conv.weight[:, :, tap].t()) for tap in range(l.conv.weight.shape[2])]
+                                         for l in cl[1:]]
+                self.conv0_wt = f(cl[0].conv.weight.reshape(cfg.conv_dim[0], cfg.conv_kernel[0]).t())
             self._conv_key = ck
             self.generation = getattr(self, "generation", 0) + 1      # buffers re-allocated: captured graphs are stale
         self._table.run()
@@ -324,9 +333,11 @@ class Wav2Vec2Backbone(nn.Module):
         return groups
 
     def check_trainable(self):
-        if any(p.requires_grad for p in self.feature_extractor.parameters()):
-            raise NotImplementedError("aptai_b200: the backward of the conv feature encoder is not built; call "
-                                      "freeze_feature_encoder() (the reference's default, models/aptai.py:39-40)")
+        if (any(p.requires_grad for p in self.feature_extractor.parameters())
+                and self.cfg.feat_extract_norm != "layer"):
+            raise NotImplementedError("aptai_b200: the backward of the conv feature encoder is built for the 'layer' "
+                                      "norm variant (XLS-R / large) only; call freeze_feature_encoder() for "
+                                      "feat_extract_norm='group' models (APTAI's default, models/aptai.py:39-40)")
 
     # Stochastic regularisers of the training path.  Dropout is counter-based (csrc/dropout.cu): a site's mask is a
     # function of (seed, element index), the seed of (training step, layer, site), so the backward regenerates it.
@@ -351,9 +362,22 @@ class Wav2Vec2Backbone(nn.Module):
         P = TP = self.train_plan()
         B, L = wav.shape
         norm = 1 if cfg.feat_extract_norm == "layer" else 2
-        y = ops.conv0(wav, P.conv0_w, P.conv_b[0], P.conv_ln_w[0], P.conv_ln_b[0], norm, out_dtype=F16)
-        for i in range(1, len(cfg.conv_kernel)):
-            y = _conv_layer(y, P, i, cfg)
+        train_conv = any(p.requires_grad for p in self.feature_extractor.parameters())
+        conv_sv = None
+        if train_conv:
+            # unfrozen conv encoder: bf16 operands, conv outputs z_i kept un-normalised, LayerNorm + GELU as a separate
+            # streaming kernel (the backward recomputes statistics and activations from z_i; conv 0 from the waveform)
+            y = ops.conv0(wav, P.conv0_w, P.conv_b[0], P.conv_ln_w[0], P.conv_ln_b[0], norm, out_dtype=BF16)
+            conv_sv = SimpleNamespace(wav=wav, ys=[y], zs=[None])
+            for i in range(1, len(cfg.conv_kernel)):
+                z = ops.conv_igemm(y, P.conv_w_bf16[i], P.conv_b[i], cfg.conv_kernel[i], cfg.conv_stride[i], act=0)
+                y = ops.ln_gelu_fwd(z, P.conv_ln_w[i], P.conv_ln_b[i])
+                conv_sv.zs.append(z)
+                conv_sv.ys.append(y)
+        else:
+            y = ops.conv0(wav, P.conv0_w, P.conv_b[0], P.conv_ln_w[0], P.conv_ln_b[0], norm, out_dtype=F16)
+            for i in range(1, len(cfg.conv_kernel)):
+                y = _conv_layer(y, P, i, cfg)
         T = y.shape[1]
         M, H = B * T, cfg.hidden_size
         eps, heads = cfg.layer_norm_eps, cfg.num_attention_heads
@@ -364,7 +388,7 @@ class Wav2Vec2Backbone(nn.Module):
         p_at = float(cfg.attention_dropout)
         seed = lambda layer, site: self.drop_seed(step, layer, site)
         sv = SimpleNamespace(B=B, T=T, frame_lens=frame_lens, layers=[], step=step, p_h=p_h, p_a=p_a, p_fp=p_fp, p_at=p_at,
-                             spec_rows=None, skipped=[])
+                             spec_rows=None, skipped=[], conv=conv_sv)
         sv.y32 = y.view(M, -1).float()
         _, sv.xn = ops.layernorm(sv.y32, P.fp_ln_w, P.fp_ln_b, eps)
         h0, _ = ops.linear(sv.xn, TP.fp_w_bf16, P.fp_b, want_f32=True, want_bf16=False, seg_rows=T,
@@ -567,8 +591,37 @@ class Wav2Vec2Backbone(nn.Module):
         dh0b = ops.scale_cast_bf16(dh0)
         lin_grads(dh0b, sv.xn, "feature_projection.projection")
         dxn, _ = ops.linear(dh0b, TP.fp_wt, None, want_f32=True, want_bf16=False)
-        ops.layernorm_bwd(dxn, sv.y32, P.fp_ln_w, eps, dgamma=G("feature_projection.layer_norm.weight"),
-                          dbeta=G("feature_projection.layer_norm.bias"))
+        dy, _ = ops.layernorm_bwd(dxn, sv.y32, P.fp_ln_w, eps, dgamma=G("feature_projection.layer_norm.weight"),
+                                  dbeta=G("feature_projection.layer_norm.bias"))
+        if sv.conv is None:
+            return                              # frozen conv feature encoder (models/aptai.py:39-40)
+        # ---- conv feature encoder (HF:275-299), layers 6..1 then layer 0
+        cs = sv.conv
+        rows_per_seg, pitch = T, T
+        for i in range(len(cfg.conv_kernel) - 1, 0, -1):
+            k, s_ = cfg.conv_kernel[i], cfg.conv_stride[i]
+            name = f"feature_extractor.conv_layers.{i}."
+            z, x_in = cs.zs[i], cs.ys[i - 1]
+            T_out, T_in = z.shape[1], x_in.shape[1]
+            dz = ops.ln_gelu_bwd(dy, rows_per_seg, pitch, B, P.conv_ln_w[i], P.conv_ln_b[i], 1e-5,
+                                 G(name + "layer_norm.weight"), G(name + "layer_norm.bias"), z=z)
+            if P.conv_b[i] is not None:
+                ops.colsum(dz, G(name + "conv.bias"))
+            dwf = ops.conv_wgrad(dz.view(B, T_out, -1), x_in, k, s_)
+            G(name + "conv.weight").add_(dwf.view(dwf.shape[0], k, -1).permute(0, 2, 1))
+            dy, pitch = ops.conv_dgrad(dz.view(B, T_out, -1), TP.conv_wt[i], k, s_, T_in)
+            rows_per_seg = T_in
+            cs.zs[i] = cs.ys[i] = None
+        name = "feature_extractor.conv_layers.0."
+        T0 = rows_per_seg
+        dz0 = ops.ln_gelu_bwd(dy, T0, pitch, B, P.conv_ln_w[0], P.conv_ln_b[0], 1e-5, G(name + "layer_norm.weight"),
+                              G(name + "layer_norm.bias"), wav=cs.wav, w0t=TP.conv0_wt, bias0=P.conv_b[0])
+        if P.conv_b[0] is not None:
+            ops.colsum(dz0, G(name + "conv.bias"))
+        X = ops.conv0_im2col(cs.wav, T0)
+        dw0 = torch.zeros((dz0.shape[1], 64), dtype=F32, device=dz0.device)
+        ops.wgrad(dz0, X, dw0)
+        G(name + "conv.weight").add_(dw0[:, : cfg.conv_kernel[0]].reshape(-1, 1, cfg.conv_kernel[0]))
 
     # ---- the hot path ----------------------------------------------------------------------------------------
     @torch.no_grad()

@@ -43,6 +43,8 @@ struct TnParams {
   long long ldo;
   float* out;
   float scale;
+  int conv_P, conv_cblks;               // strided conv (4-D B map: channel, row parity, row / P, utterance): P = stride,
+                                        // conv_cblks = 256-channel blocks per tap; 0 = plain 3-D B map
 };
 
 // MN-major SWIZZLE_128B operand: 64-element (128 B) rows along MN, 8-row groups along K 1024 B apart (SBO),
@@ -124,10 +126,18 @@ gemm_tn_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           mbar_expect_tx(&full_bar[stage], TN_STAGE_BYTES);
 #pragma unroll
           for (int j = 0; j < TN_BM / 64; ++j) tma_load_3d(&tmA, &full_bar[stage], sa + j * 8192, a_col + j * 64, m0, seg);
+          if (p.conv_P > 0) {
+            // output frame m of the conv reads input row m * P + tap: parity = tap % P, row / P = m + tap / P
+            const int tap = kt / p.conv_cblks, cb = (kt - tap * p.conv_cblks) * TN_BN;
 #pragma unroll
-          for (int j = 0; j < TN_BN / 64; ++j)
-            tma_load_3d(&tmB, &full_bar[stage], sb + j * 8192, b_col + j * p.b_col_box, m0 + b_row + j * p.b_row_box,
-                        seg);
+            for (int j = 0; j < TN_BN / 64; ++j)
+              tma_load_4d(&tmB, &full_bar[stage], sb + j * 8192, cb + j * 64, tap % p.conv_P, m0 + tap / p.conv_P, seg);
+          } else {
+#pragma unroll
+            for (int j = 0; j < TN_BN / 64; ++j)
+              tma_load_3d(&tmB, &full_bar[stage], sb + j * 8192, b_col + j * p.b_col_box,
+                          m0 + b_row + j * p.b_row_box, seg);
+          }
           if (++stage == TN_STAGES) {
             stage = 0;
             phase ^= 1;
@@ -501,6 +511,7 @@ extern "C" int aptai_gemm_wgrad_bf16(const void* dy, int64_t dy_ld, const void* 
   p.ldo = dw_ld;
   p.out = dw;
   p.scale = scale;
+  p.conv_P = 0; p.conv_cblks = 0;
   static const bool force_single = getenv("APTAI_WGRAD_SINGLE") != nullptr;      // A/B switch for profiles/
   if (!force_single && N >= 256 && K >= 256) {
     p.n_tiles = (N + 255) / 256;
@@ -547,5 +558,46 @@ extern "C" int aptai_posconv_wgrad_bf16(const void* dy, const void* x_pad, int B
   p.ldo = static_cast<long long>(taps) * 64;
   p.out = dw_folded;
   p.scale = 1.0f;
+  p.conv_P = 0; p.conv_cblks = 0;
+  return launch_tn(ta, tb, p, reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int aptai_conv_wgrad_bf16(const void* dz, const void* x, int B, int T_out, int T_in, int C, int ktaps,
+                                     int stride, float* dw_tapmajor, void* stream) {
+  if (int rc = check_arch()) return rc;
+  APTAI_REQUIRE(dz && x && dw_tapmajor, "conv_wgrad: null pointer");
+  APTAI_REQUIRE(B >= 1 && T_out >= 1 && ktaps >= 1 && stride >= 1 && C % 256 == 0, "conv_wgrad: bad shape (C % 256)");
+  APTAI_REQUIRE(static_cast<long long>(T_out - 1) * stride + ktaps <= T_in, "conv_wgrad: T_in too short");
+  CUtensorMap ta, tb;
+  {
+    uint32_t box[3] = {64, 64, 1};
+    uint64_t dims[3] = {static_cast<uint64_t>(C), static_cast<uint64_t>(T_out), static_cast<uint64_t>(B)};
+    uint64_t strides[2] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(C) * 2 * T_out};
+    if (int rc = encode_tmap_bf16(&ta, dz, 3, dims, strides, box, 1)) return rc;
+  }
+  {
+    // the forward GEMM's A view of the conv input: (channel, row parity, row / P, utterance)
+    uint32_t box[4] = {64, 1, 64, 1};
+    const uint64_t r2 = (static_cast<uint64_t>(T_in) + stride - 1) / stride;
+    uint64_t dims[4] = {static_cast<uint64_t>(C), static_cast<uint64_t>(stride), r2, static_cast<uint64_t>(B)};
+    uint64_t strides[3] = {static_cast<uint64_t>(C) * 2, static_cast<uint64_t>(C) * 2 * stride,
+                           static_cast<uint64_t>(C) * 2 * T_in};
+    if (int rc = encode_tmap_bf16(&tb, x, 4, dims, strides, box, 1)) return rc;
+  }
+  TnParams p;
+  p.n_tiles = (C + TN_BM - 1) / TN_BM;
+  p.conv_cblks = C / TN_BN;
+  p.k_tiles = ktaps * p.conv_cblks;
+  p.segs = B;
+  p.mblk_per_seg = (T_out + TN_BK - 1) / TN_BK;
+  p.total_kb = p.segs * p.mblk_per_seg;
+  p.a_col_step = TN_BM;
+  p.b_col_kt = 0; p.b_col_nt = 0; p.b_col_box = 0; p.b_row_kt = 0; p.b_row_box = 0;
+  p.out_rows_per_tile = TN_BM;
+  p.out_rows = C; p.out_cols = ktaps * C;
+  p.ldo = static_cast<long long>(ktaps) * C;
+  p.out = dw_tapmajor;
+  p.scale = 1.0f;
+  p.conv_P = stride;
   return launch_tn(ta, tb, p, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -585,3 +585,72 @@ def dropout(x: torch.Tensor, p: float, seed: int, *, residual: Optional[torch.Te
     check(_lib.load().aptai_dropout(x.data_ptr(), int(x.dtype == BF16), _ptr(residual), x.numel(), float(p),
                                     int(seed) & 0xFFFFFFFFFFFFFFFF, _ptr(out_f32), _ptr(out_bf16), _stream()), "dropout")
     return out_f32, out_bf16
+
+
+# ---- conv feature encoder, training path ('layer' norm variant) -------------------------------------------------
+def ln_gelu_fwd(z: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """y = GELU(LayerNorm_512(z)); z bf16 [B,T,512] -> y bf16 [B,T,512] (with the slack rows the strided TMA view needs)."""
+    _req(z, BF16, "z")
+    B, T, Cc = z.shape
+    assert Cc == 512
+    y = alloc_rows_bf16(B, T, Cc, z.device)
+    check(_lib.load().aptai_ln_gelu_fwd_512(z.data_ptr(), B * T, gamma.data_ptr(), beta.data_ptr(), eps, y.data_ptr(),
+                                            _stream()), "ln_gelu_fwd")
+    return y
+
+
+def ln_gelu_bwd(dy: torch.Tensor, rows_per_seg: int, seg_pitch: int, segs: int, gamma, beta, eps, dgamma, dbeta, *,
+                z: Optional[torch.Tensor] = None, wav: Optional[torch.Tensor] = None,
+                w0t: Optional[torch.Tensor] = None, bias0: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """dz bf16 [segs*rows_per_seg, 512] = LN'(dy * GELU'(LN(z))); dy fp32, logical row r of segment s at physical row
+    s*seg_pitch + r.  z given, or recomputed from the waveform for conv layer 0 (wav fp32 [B,L], w0t fp32 [10,512])."""
+    _req(dy, F32, "dy")
+    rows = segs * rows_per_seg
+    dz = torch.empty((rows, 512), dtype=BF16, device=dy.device)
+    check(_lib.load().aptai_ln_gelu_bwd_512(dy.data_ptr(), rows_per_seg, seg_pitch, _ptr(z), _ptr(wav),
+                                            wav.shape[1] if wav is not None else 0, _ptr(w0t), _ptr(bias0), rows,
+                                            gamma.data_ptr(), beta.data_ptr(), eps, dz.data_ptr(), dgamma.data_ptr(),
+                                            dbeta.data_ptr(), _stream()), "ln_gelu_bwd")
+    return dz
+
+
+def conv_wgrad(dz: torch.Tensor, x: torch.Tensor, k: int, stride: int) -> torch.Tensor:
+    """Tap-major weight gradient fp32 [C, k*C] of a strided conv layer: dz bf16 [B,T_out,C], x bf16 [B,T_in,C]."""
+    _req(dz, BF16, "dz"); _req(x, BF16, "x")
+    B, T_out, Cc = dz.shape
+    T_in = x.shape[1]
+    dwf = torch.zeros((Cc, k * Cc), dtype=F32, device=dz.device)
+    check(_lib.load().aptai_conv_wgrad_bf16(dz.data_ptr(), x.data_ptr(), B, T_out, T_in, Cc, k, stride, dwf.data_ptr(),
+                                            _stream()), "conv_wgrad_bf16")
+    return dwf
+
+
+def conv_dgrad(dz: torch.Tensor, wt_taps, k: int, stride: int, T_in: int):
+    """Input gradient of a strided conv layer as one GEMM per tap with strided output rows:
+    dx[b, t*stride + tap, c] (+)= sum_o dz[b,t,o] * W[o,c,tap].  dz bf16 [B,T_out,C]; wt_taps[tap] bf16 [C(c), C(o)].
+    Returns (dx fp32 [B, T_pad, C], T_pad): T_pad = T_in rounded up to the stride."""
+    _req(dz, BF16, "dz")
+    B, T_out, Cc = dz.shape
+    T_pad = (T_in + stride - 1) // stride * stride
+    dx = torch.zeros((B, T_pad, Cc), dtype=F32, device=dz.device)
+    for tap in range(k):
+        w = _req(wt_taps[tap], BF16, "wt")
+        g = GemmArgs()
+        g.a = dz.data_ptr(); g.a_row_stride = Cc; g.a_seg_stride = T_out * Cc; g.a_rows = T_out; g.a_cols = Cc
+        g.P = 1; g.taps = 1; g.kb_per_tap = Cc // 64; g.a_col_per_nblk = 0
+        g.w = w.data_ptr(); g.N = Cc; g.block_n = 0; g.segs = B; g.rows_per_seg = T_out
+        g.bias = None; g.gamma = None; g.beta = None
+        out = dx.data_ptr() + tap * Cc * 4
+        g.residual = out if tap >= stride else None          # taps congruent mod stride hit the same rows: accumulate
+        g.out_f32 = out; g.out_bf16 = None; g.ldo = stride * Cc; g.out_seg_stride = T_pad // stride
+        g.seg_valid_rows = None; g.mask_seg_rows = 0; g.act = 0; g.ln = 0; g.ln_eps = 0.0; g.cta_pair = 0; g.half_fmt = 0
+        gemm_raw(g)
+    return dx, T_pad
+
+
+def conv0_im2col(wav: torch.Tensor, T0: int) -> torch.Tensor:
+    _req(wav, F32, "wav")
+    B, L = wav.shape
+    X = torch.empty((B * T0, 64), dtype=BF16, device=wav.device)
+    check(_lib.load().aptai_conv0_im2col_bf16(wav.data_ptr(), B, L, T0, X.data_ptr(), _stream()), "conv0_im2col")
+    return X

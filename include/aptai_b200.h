@@ -233,6 +233,23 @@ int aptai_gemm_wgrad_bf16(const void* dy, int64_t dy_ld, const void* x, int64_t 
  * dy bf16 [B][T][H], x_pad bf16 [B][T + taps][H] (the forward's aptai_cast_pad_bf16 output). */
 int aptai_posconv_wgrad_bf16(const void* dy, const void* x_pad, int B, int T, int H, int groups, int taps,
                              float* dw_folded, void* stream);
+/* weight gradient of a strided conv layer of the feature encoder (HF:254-323) in the forward GEMM's tap-major layout:
+ * dw[o][tap*C + c] += sum_{b,t} dz[b][t][o] * x[b][t*stride + tap][c];  dz bf16 [B][T_out][C], x bf16 [B][T_in][C]
+ * (row T_in of the last utterance may be touched by the strided TMA view: keep the forward's slack rows). */
+int aptai_conv_wgrad_bf16(const void* dz, const void* x, int B, int T_out, int T_in, int C, int ktaps, int stride,
+                          float* dw_tapmajor, void* stream);
+/* conv feature encoder, 'layer' norm variant, training path: y = GELU(LayerNorm_512(z)) as a separate streaming kernel
+ * (forward), and its backward dz = LN'(dy * GELU'(LN(z))) with dgamma/dbeta accumulated.  dy fp32 with a row map
+ * (logical row r of segment s at physical row s*dy_seg_pitch + r).  For conv layer 0 pass z = NULL and wav / w0t
+ * ([10][512] transposed weight) / bias0: z is recomputed from the waveform (frame t reads samples 5t .. 5t+9). */
+int aptai_ln_gelu_fwd_512(const void* z_bf16, int64_t rows, const float* gamma, const float* beta, float eps,
+                          void* y_bf16, void* stream);
+int aptai_ln_gelu_bwd_512(const float* dy, int64_t dy_rows_per_seg, int64_t dy_seg_pitch, const void* z_bf16,
+                          const float* wav, int64_t wav_ld, const float* w0t, const float* bias0, int64_t rows,
+                          const float* gamma, const float* beta, float eps, void* dz_bf16, float* dgamma, float* dbeta,
+                          void* stream);
+/* X[b*T0 + t][0..63] = wav[b][5t .. 5t+9], 0-padded, bf16: B operand of conv-0's weight-gradient GEMM */
+int aptai_conv0_im2col_bf16(const float* wav, int B, int64_t L, int64_t T0, void* x_bf16, void* stream);
 /* weight-norm backward (torch parametrizations.weight_norm, dim=2): dg[taps] += , dv[H][cin][taps] += from the
  * folded dW.  ws: 2*taps doubles. */
 int aptai_posconv_weightnorm_bwd(const float* dw_folded, const float* g, const float* v, int H, int cin, int taps,

@@ -291,3 +291,51 @@ def test_aptai_head_dropouts_replayed_by_the_oracle(cuda):
         ours, r = params[name_].grad.double().cpu().flatten(), ref.grad.double().flatten()
         cos = float(ours @ r / (ours.norm() * r.norm()))
         assert abs(float(ours.norm() / r.norm()) - 1) < 0.03 and cos > 0.995, (name_, float(ours.norm() / r.norm()), cos)
+
+
+def test_unfrozen_conv_encoder_training_vs_oracle(cuda):
+    """Recogniser training with the conv feature encoder UNFROZEN (the reference's default,
+    train/train_phoneme_recognizer.py:170) on a 'layer'-norm backbone: gradients of all seven conv layers (weights,
+    biases, LayerNorms) and of the rest of the model against the oracle's autograd."""
+    import torch.nn.functional as F
+    from oracle import w2v2 as ow
+    cfg = cfg_large(vocab_size=46, num_hidden_layers=2)
+    sd0 = backbone_sd(cfg, 5)
+    name = register_in_memory_checkpoint("mem://large2-seed5-conv", sd0)
+    pr = Wav2Vec2_PR(cfg, None, name, VOCAB)
+    hw, hb = W.linear_params(105, 46, 1024)
+    with torch.no_grad():
+        pr.pr_head.weight.copy_(hw); pr.pr_head.bias.copy_(hb)
+    pr = pr.to(cuda).train()                                   # feature encoder NOT frozen
+    lens = [24000, 17000]
+    wav = W.waveforms(2, 24000, lens, seed=4321)
+    labels, _ = W.phoneme_sequences(2, 8, 20, 2, 45, seed=9, pad=-100)
+    r = pr(wav.to(cuda), torch.tensor(lens, device=cuda), labels.to(cuda))
+    r["loss"].backward()
+    sd = {k: v.clone() for k, v in sd0.items()}
+    trainable = [k for k in sd if k != "masked_spec_embed"]
+    for k in trainable:
+        sd[k].requires_grad_(True)
+    hw_, hb_ = hw.clone().requires_grad_(True), hb.clone().requires_grad_(True)
+    torch.set_num_threads(os.cpu_count())
+    hidden, _, flen = ow.forward(sd, cfg, wav, lens, return_features=True)
+    lp = F.log_softmax(F.linear(hidden[-1], hw_, hb_), dim=-1, dtype=torch.float32).transpose(0, 1)
+    loss = F.ctc_loss(lp, labels[labels >= 0], flen, (labels >= 0).sum(-1), blank=0, reduction="mean", zero_infinity=True)
+    loss.backward()
+    assert abs(float(r["loss"].detach()) - float(loss.detach())) / float(loss.detach()) < 2e-3
+    params = dict(pr.named_parameters())
+    norms = {k: float(sd[k].grad.double().norm()) for k in trainable}
+    floor = 1e-4 * float(np.median(list(norms.values())))
+    report = {}
+    for k, ref in norms.items():
+        ours = params["wav2vec2." + k].grad.double().cpu().flatten()
+        if ref < floor:
+            continue
+        g = sd[k].grad.double().flatten()
+        report[k] = (abs(float(ours.norm()) - ref) / ref, float(ours @ g / (ours.norm() * g.norm())))
+    conv = {k: v for k, v in report.items() if k.startswith("feature_extractor.")}
+    assert len(conv) >= 7 * 3          # 7 layers x (weight, LayerNorm weight, LayerNorm bias) at least
+    worst = max(report.items(), key=lambda t: t[1][0])
+    low = min(report.items(), key=lambda t: t[1][1])
+    print("unfrozen conv: worst grad-norm deviation", worst, "lowest cosine", low)
+    assert worst[1][0] < 0.05 and low[1][1] > 0.98
