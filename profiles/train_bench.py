@@ -56,6 +56,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--model", default="large", choices=["large", "base"])
+    ap.add_argument("--unfrozen", action="store_true",
+                    help="train the conv feature encoder too (the reference's default for the recogniser)")
     ap.add_argument("--regularised", action="store_true",
                     help="XLS-R's published training regularisers: hidden/attention dropout 0.1, layerdrop 0.1, "
                          "SpecAugment mask_time_prob 0.075, head dropouts 0.1")
@@ -89,7 +91,8 @@ def main():
         lens[0] = L
     else:
         model = Wav2Vec2_PR(cfg, None, name, VOCAB)
-        model.wav2vec2.freeze_feature_encoder()
+        if not args.unfrozen:
+            model.wav2vec2.freeze_feature_encoder()
         lens = np.full((B,), L)
     model = model.to(dev).train()
     wav = torch.empty((B, L)).normal_(0.0, 0.1, generator=g)
@@ -156,7 +159,8 @@ def main():
         fl = flops_train(cfg, [int(n) for n in lens])
         print(json.dumps({
             "workload": f"config{args.config}: {'APTAI training step' if args.config == 4 else 'Wav2Vec2_PR CTC fwd+bwd+Adam'}"
-                        f", {args.model} backbone, batch {B}/GPU, max 8 s, frozen conv encoder, fused Adam"
+                        f", {args.model} backbone, batch {B}/GPU, max 8 s, "
+                        f"{'conv encoder trained' if args.unfrozen and args.config == 2 else 'frozen conv encoder'}, fused Adam"
                         + (", dropout 0.1 (hidden/attention/heads) + LayerDrop 0.1 + SpecAugment 0.075" if args.regularised else "")
                         + (", DP all-reduce overlapped with backward" if world > 1 else ""),
             "n_gpus": world, "ms_per_step": ms, "audio_s_per_s": world * audio_s / (ms * 1e-3),
