@@ -333,11 +333,9 @@ class Wav2Vec2Backbone(nn.Module):
         return groups
 
     def check_trainable(self):
-        if (any(p.requires_grad for p in self.feature_extractor.parameters())
-                and self.cfg.feat_extract_norm != "layer"):
-            raise NotImplementedError("aptai_b200: the backward of the conv feature encoder is built for the 'layer' "
-                                      "norm variant (XLS-R / large) only; call freeze_feature_encoder() for "
-                                      "feat_extract_norm='group' models (APTAI's default, models/aptai.py:39-40)")
+        if self.cfg.apply_spec_augment and self.cfg.mask_feature_prob > 0:
+            raise NotImplementedError("aptai_b200: SpecAugment masking along the feature axis (mask_feature_prob > 0, "
+                                      "HF:1314-1322) is not built in the training path; set it to 0")
 
     # Stochastic regularisers of the training path.  Dropout is counter-based (csrc/dropout.cu): a site's mask is a
     # function of (seed, element index), the seed of (training step, layer, site), so the backward regenerates it.
@@ -367,11 +365,20 @@ class Wav2Vec2Backbone(nn.Module):
         if train_conv:
             # unfrozen conv encoder: bf16 operands, conv outputs z_i kept un-normalised, LayerNorm + GELU as a separate
             # streaming kernel (the backward recomputes statistics and activations from z_i; conv 0 from the waveform)
-            y = ops.conv0(wav, P.conv0_w, P.conv_b[0], P.conv_ln_w[0], P.conv_ln_b[0], norm, out_dtype=BF16)
-            conv_sv = SimpleNamespace(wav=wav, ys=[y], zs=[None])
+            y, ws0 = ops.conv0(wav, P.conv0_w, P.conv_b[0], P.conv_ln_w[0], P.conv_ln_b[0], norm, out_dtype=BF16,
+                               return_ws=True)
+            conv_sv = SimpleNamespace(wav=wav, ys=[y], zs=[None], affine=None)
+            if norm == 2:        # GroupNorm: per-(utterance, channel) scale / shift computed by the forward kernel
+                conv_sv.affine = ws0[B * 130: B * 130 + B * 1024]
             for i in range(1, len(cfg.conv_kernel)):
-                z = ops.conv_igemm(y, P.conv_w_bf16[i], P.conv_b[i], cfg.conv_kernel[i], cfg.conv_stride[i], act=0)
-                y = ops.ln_gelu_fwd(z, P.conv_ln_w[i], P.conv_ln_b[i])
+                if norm == 1:
+                    z = ops.conv_igemm(y, P.conv_w_bf16[i], P.conv_b[i], cfg.conv_kernel[i], cfg.conv_stride[i], act=0)
+                    y = ops.ln_gelu_fwd(z, P.conv_ln_w[i], P.conv_ln_b[i])
+                else:            # 'group' variant: layers 1..6 are conv -> GELU; keep the pre-activation
+                    T_o = (y.shape[1] - cfg.conv_kernel[i]) // cfg.conv_stride[i] + 1
+                    z = torch.empty((B, T_o, y.shape[2]), dtype=BF16, device=wav.device)
+                    y = ops.conv_igemm(y, P.conv_w_bf16[i], P.conv_b[i], cfg.conv_kernel[i], cfg.conv_stride[i], act=1,
+                                       out_pre=z)
                 conv_sv.zs.append(z)
                 conv_sv.ys.append(y)
         else:
@@ -603,8 +610,11 @@ class Wav2Vec2Backbone(nn.Module):
             name = f"feature_extractor.conv_layers.{i}."
             z, x_in = cs.zs[i], cs.ys[i - 1]
             T_out, T_in = z.shape[1], x_in.shape[1]
-            dz = ops.ln_gelu_bwd(dy, rows_per_seg, pitch, B, P.conv_ln_w[i], P.conv_ln_b[i], 1e-5,
-                                 G(name + "layer_norm.weight"), G(name + "layer_norm.bias"), z=z)
+            if cfg.feat_extract_norm == "layer":
+                dz = ops.ln_gelu_bwd(dy, rows_per_seg, pitch, B, P.conv_ln_w[i], P.conv_ln_b[i], 1e-5,
+                                     G(name + "layer_norm.weight"), G(name + "layer_norm.bias"), z=z)
+            else:
+                dz = ops.gelu_bwd_rows(dy, rows_per_seg, pitch, B, z.view(-1, z.shape[2]))
             if P.conv_b[i] is not None:
                 ops.colsum(dz, G(name + "conv.bias"))
             dwf = ops.conv_wgrad(dz.view(B, T_out, -1), x_in, k, s_)
@@ -614,8 +624,14 @@ class Wav2Vec2Backbone(nn.Module):
             cs.zs[i] = cs.ys[i] = None
         name = "feature_extractor.conv_layers.0."
         T0 = rows_per_seg
-        dz0 = ops.ln_gelu_bwd(dy, T0, pitch, B, P.conv_ln_w[0], P.conv_ln_b[0], 1e-5, G(name + "layer_norm.weight"),
-                              G(name + "layer_norm.bias"), wav=cs.wav, w0t=TP.conv0_wt, bias0=P.conv_b[0])
+        if cfg.feat_extract_norm == "layer":
+            dz0 = ops.ln_gelu_bwd(dy, T0, pitch, B, P.conv_ln_w[0], P.conv_ln_b[0], 1e-5, G(name + "layer_norm.weight"),
+                                  G(name + "layer_norm.bias"), wav=cs.wav, w0t=TP.conv0_wt, bias0=P.conv_b[0])
+        else:
+            dz0, sums = ops.conv0_groupnorm_bwd(dy, pitch, cs.wav, T0, P.conv0_w, cs.affine, P.conv_ln_w[0],
+                                                P.conv_ln_b[0])
+            G(name + "layer_norm.bias").add_(sums[:, :, 0].sum(0))
+            G(name + "layer_norm.weight").add_(sums[:, :, 1].sum(0))
         if P.conv_b[0] is not None:
             ops.colsum(dz0, G(name + "conv.bias"))
         X = ops.conv0_im2col(cs.wav, T0)

@@ -191,9 +191,124 @@ __global__ void conv0_im2col_kernel(const float* __restrict__ wav, long long wav
   }
 }
 
+// ---- 'group' norm variant (base models, HF:308-323: GroupNorm with one group per channel = statistics over time) ----
+// layers 1..6 have neither norm nor bias: dz = dy * GELU'(z)
+__global__ void gelu_bwd_rows_kernel(const float* __restrict__ dy, RowMap dy_map, const __nv_bfloat16* __restrict__ z,
+                                     long long rows, __nv_bfloat16* __restrict__ dz) {
+  const long long total = rows * (CB_C / 4);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / (CB_C / 4);
+    const int c4 = static_cast<int>(i - row * (CB_C / 4));
+    const float4 d = __ldg(reinterpret_cast<const float4*>(dy + phys_row(row, dy_map) * CB_C) + c4);
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(z) + i);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+    reinterpret_cast<uint2*>(dz)[i] = make_uint2(pack_bf16(d.x * gelu_erf_grad(a.x), d.y * gelu_erf_grad(a.y)),
+                                                 pack_bf16(d.z * gelu_erf_grad(b.x), d.w * gelu_erf_grad(b.y)));
+  }
+}
+
+// conv layer 0 with GroupNorm: y = GELU(a * zraw + e), a = gamma * rstd, e = (bias - mean) * a + beta per (utterance,
+// channel) (the forward's `affine` array), zraw recomputed from the waveform.  With g = dy * GELU'(ln):
+//   PASS 1: sums[b][c] = {sum_t g, sum_t g * xhat}         PASS 2: dz = a * (g - S1/T0 - xhat * S2/T0)   (bf16)
+// grid = (frame chunks, B), 256 threads, thread = channels c and c + 256.
+template <int PASS>
+__global__ void __launch_bounds__(256)
+conv0_gn_bwd_kernel(const float* __restrict__ dy, RowMap dy_map, const float* __restrict__ wav, long long wav_ld,
+                    const float* __restrict__ w0, const float* __restrict__ affine, const float* __restrict__ gamma,
+                    const float* __restrict__ beta, int T0, int frames_per_block, float* __restrict__ sums,
+                    __nv_bfloat16* __restrict__ dz) {
+  const int b = blockIdx.y;
+  const int t_begin = blockIdx.x * frames_per_block, t_end = min(T0, t_begin + frames_per_block);
+  float w[2][10], a[2], e[2], ig[2], bt[2], s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f}, m1[2], m2[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int c = threadIdx.x + h * 256;
+#pragma unroll
+    for (int k = 0; k < 10; ++k) w[h][k] = __ldg(w0 + c * 10 + k);
+    a[h] = affine[(static_cast<long long>(b) * CB_C + c) * 2];
+    e[h] = affine[(static_cast<long long>(b) * CB_C + c) * 2 + 1];
+    const float g = __ldg(gamma + c);
+    ig[h] = g != 0.f ? 1.0f / g : 0.f;
+    bt[h] = __ldg(beta + c);
+    if (PASS == 2) {
+      m1[h] = sums[(static_cast<long long>(b) * CB_C + c) * 2] / T0;
+      m2[h] = sums[(static_cast<long long>(b) * CB_C + c) * 2 + 1] / T0;
+    }
+  }
+  __shared__ float xs[16];
+  for (int t = t_begin; t < t_end; ++t) {
+    __syncthreads();
+    if (threadIdx.x < 10) xs[threadIdx.x] = __ldg(wav + b * wav_ld + 5LL * t + threadIdx.x);
+    __syncthreads();
+    const long long prow = phys_row(static_cast<long long>(b) * T0 + t, dy_map);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = threadIdx.x + h * 256;
+      float zr = 0.f;
+#pragma unroll
+      for (int k = 0; k < 10; ++k) zr = fmaf(w[h][k], xs[k], zr);
+      const float ln = fmaf(a[h], zr, e[h]);
+      const float xhat = (ln - bt[h]) * ig[h];
+      const float g = __ldg(dy + prow * CB_C + c) * gelu_erf_grad(ln);
+      if (PASS == 1) {
+        s1[h] += g;
+        s2[h] = fmaf(g, xhat, s2[h]);
+      } else {
+        dz[(static_cast<long long>(b) * T0 + t) * CB_C + c] = __float2bfloat16(a[h] * (g - m1[h] - xhat * m2[h]));
+      }
+    }
+  }
+  if (PASS == 1) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = threadIdx.x + h * 256;
+      atomicAdd(sums + (static_cast<long long>(b) * CB_C + c) * 2, s1[h]);
+      atomicAdd(sums + (static_cast<long long>(b) * CB_C + c) * 2 + 1, s2[h]);
+    }
+  }
+}
+
 }  // namespace aptai
 
 using namespace aptai;
+
+extern "C" int aptai_gelu_bwd_rows_512(const float* dy, int64_t dy_rows_per_seg, int64_t dy_seg_pitch, const void* z_bf16,
+                                       int64_t rows, void* dz_bf16, void* stream) {
+  if (int rc = check_arch()) return rc;
+  APTAI_REQUIRE(dy && z_bf16 && dz_bf16 && rows >= 1 && dy_rows_per_seg >= 1 && dy_seg_pitch >= dy_rows_per_seg,
+                "gelu_bwd_rows: bad arguments");
+  RowMap m{dy_rows_per_seg, dy_seg_pitch};
+  const long long total = rows * (CB_C / 4);
+  int gx = static_cast<int>((total + 255) / 256);
+  if (gx > 16384) gx = 16384;
+  gelu_bwd_rows_kernel<<<gx, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      dy, m, reinterpret_cast<const __nv_bfloat16*>(z_bf16), rows, reinterpret_cast<__nv_bfloat16*>(dz_bf16));
+  return after_launch("gelu_bwd_rows");
+}
+
+extern "C" int aptai_conv0_groupnorm_bwd(const float* dy, int64_t dy_seg_pitch, const float* wav, int B, int64_t L,
+                                         int T0, const float* w0, const float* affine, const float* gamma,
+                                         const float* beta, float* sums, void* dz_bf16, void* stream) {
+  if (int rc = check_arch()) return rc;
+  APTAI_REQUIRE(dy && wav && w0 && affine && gamma && beta && sums && dz_bf16, "conv0_groupnorm_bwd: null pointer");
+  APTAI_REQUIRE(B >= 1 && T0 >= 1 && dy_seg_pitch >= T0 && 5LL * (T0 - 1) + 10 <= L, "conv0_groupnorm_bwd: bad shape");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaMemsetAsync(sums, 0, static_cast<size_t>(B) * CB_C * 2 * sizeof(float), st);
+  if (e != cudaSuccess) {
+    set_error("conv0_groupnorm_bwd: memset: %s", cudaGetErrorString(e));
+    return static_cast<int>(e);
+  }
+  RowMap m{T0, dy_seg_pitch};
+  const int fpb = 128;
+  dim3 grid((T0 + fpb - 1) / fpb, B);
+  __nv_bfloat16* dz = reinterpret_cast<__nv_bfloat16*>(dz_bf16);
+  conv0_gn_bwd_kernel<1><<<grid, 256, 0, st>>>(dy, m, wav, L, w0, affine, gamma, beta, T0, fpb, sums, dz);
+  if (int rc = after_launch("conv0_gn_bwd_sums")) return rc;
+  conv0_gn_bwd_kernel<2><<<grid, 256, 0, st>>>(dy, m, wav, L, w0, affine, gamma, beta, T0, fpb, sums, dz);
+  return after_launch("conv0_gn_bwd");
+}
 
 extern "C" int aptai_ln_gelu_fwd_512(const void* z_bf16, int64_t rows, const float* gamma, const float* beta, float eps,
                                      void* y_bf16, void* stream) {

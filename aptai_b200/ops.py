@@ -135,7 +135,8 @@ def linear_f32x3(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor])
 
 def conv_igemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], k: int, stride: int, *,
                ln_gamma: Optional[torch.Tensor] = None, ln_beta: Optional[torch.Tensor] = None,
-               eps: float = 1e-5, act: int = 1, out: Optional[torch.Tensor] = None, cta_pair: int = 0) -> torch.Tensor:
+               eps: float = 1e-5, act: int = 1, out: Optional[torch.Tensor] = None, cta_pair: int = 0,
+               out_pre: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Strided conv1d as implicit GEMM.  x bf16 [B,T_in,C] channels-last, w bf16 [N, k*C] (tap-major K), out bf16
     [B,T_out,N]; epilogue = (+bias) -> (LayerNorm over N, if gamma) -> GELU."""
     fmt = _h16(x, "x")
@@ -156,6 +157,8 @@ def conv_igemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], k
     g.out_f32 = None; g.out_bf16 = out.data_ptr(); g.ldo = N; g.out_seg_stride = T_out
     g.seg_valid_rows = None; g.mask_seg_rows = 0; g.act = act; g.ln = 1 if ln_gamma is not None else 0; g.ln_eps = eps
     g.cta_pair = cta_pair; g.half_fmt = fmt
+    if out_pre is not None:
+        g.out_pre = _req(out_pre, x.dtype, "out_pre").data_ptr()
     gemm_raw(g)
     return out
 
@@ -188,7 +191,7 @@ def posconv(x_pad: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], 
 
 
 def conv0(wav: torch.Tensor, w: torch.Tensor, bias, gamma, beta, norm: int, eps: float = 1e-5,
-          out_dtype=None) -> torch.Tensor:
+          out_dtype=None, return_ws: bool = False):
     _req(wav, F32, "wav"); _req(w, F32, "w")
     B, L = wav.shape
     T0 = (L - 10) // 5 + 1
@@ -197,6 +200,8 @@ def conv0(wav: torch.Tensor, w: torch.Tensor, bias, gamma, beta, norm: int, eps:
     check(_lib.load().aptai_conv0_norm_gelu(wav.data_ptr(), B, L, w.data_ptr(), _ptr(bias), _ptr(gamma), _ptr(beta),
                                             norm, eps, out.data_ptr(), T0, _ptr(ws), int(out.dtype == F16), _stream()),
           "conv0_norm_gelu")
+    if return_ws:
+        return out, ws
     return out
 
 
@@ -654,3 +659,27 @@ def conv0_im2col(wav: torch.Tensor, T0: int) -> torch.Tensor:
     X = torch.empty((B * T0, 64), dtype=BF16, device=wav.device)
     check(_lib.load().aptai_conv0_im2col_bf16(wav.data_ptr(), B, L, T0, X.data_ptr(), _stream()), "conv0_im2col")
     return X
+
+
+def gelu_bwd_rows(dy: torch.Tensor, rows_per_seg: int, seg_pitch: int, segs: int, z: torch.Tensor) -> torch.Tensor:
+    """dz bf16 [segs*rows_per_seg, 512] = dy * GELU'(z) ('group' variant conv layers 1..6)."""
+    _req(dy, F32, "dy"); _req(z, BF16, "z")
+    rows = segs * rows_per_seg
+    dz = torch.empty((rows, 512), dtype=BF16, device=dy.device)
+    check(_lib.load().aptai_gelu_bwd_rows_512(dy.data_ptr(), rows_per_seg, seg_pitch, z.data_ptr(), rows, dz.data_ptr(),
+                                              _stream()), "gelu_bwd_rows")
+    return dz
+
+
+def conv0_groupnorm_bwd(dy: torch.Tensor, seg_pitch: int, wav: torch.Tensor, T0: int, w0: torch.Tensor,
+                        affine: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor):
+    """Backward of conv layer 0 + GroupNorm-over-time + GELU.  Returns (dz0 bf16 [B*T0, 512], sums fp32 [B, 512, 2] =
+    per-utterance {dbeta, dgamma} contributions)."""
+    _req(dy, F32, "dy"); _req(wav, F32, "wav"); _req(affine, F32, "affine")
+    B, L = wav.shape
+    sums = torch.empty((B, 512, 2), dtype=F32, device=wav.device)
+    dz = torch.empty((B * T0, 512), dtype=BF16, device=wav.device)
+    check(_lib.load().aptai_conv0_groupnorm_bwd(dy.data_ptr(), seg_pitch, wav.data_ptr(), B, L, T0, w0.data_ptr(),
+                                                affine.data_ptr(), gamma.data_ptr(), beta.data_ptr(), sums.data_ptr(),
+                                                dz.data_ptr(), _stream()), "conv0_groupnorm_bwd")
+    return dz, sums

@@ -248,6 +248,15 @@ int aptai_ln_gelu_bwd_512(const float* dy, int64_t dy_rows_per_seg, int64_t dy_s
                           const float* wav, int64_t wav_ld, const float* w0t, const float* bias0, int64_t rows,
                           const float* gamma, const float* beta, float eps, void* dz_bf16, float* dgamma, float* dbeta,
                           void* stream);
+/* 'group' norm variant (base models, HF:308-323).  Layers 1..6 (no norm, no bias): dz = dy * GELU'(z).  Conv layer 0 with
+ * GroupNorm over time: affine fp32 [B][512][2] = {gamma*rstd, (bias-mean)*gamma*rstd + beta} as produced by the forward
+ * (aptai_conv0_norm_gelu's stats_ws), sums fp32 [B][512][2] receives {sum_t g, sum_t g*xhat} (dbeta / dgamma per
+ * utterance), dz bf16 [B*T0][512]. */
+int aptai_gelu_bwd_rows_512(const float* dy, int64_t dy_rows_per_seg, int64_t dy_seg_pitch, const void* z_bf16,
+                            int64_t rows, void* dz_bf16, void* stream);
+int aptai_conv0_groupnorm_bwd(const float* dy, int64_t dy_seg_pitch, const float* wav, int B, int64_t L, int T0,
+                              const float* w0, const float* affine, const float* gamma, const float* beta, float* sums,
+                              void* dz_bf16, void* stream);
 /* X[b*T0 + t][0..63] = wav[b][5t .. 5t+9], 0-padded, bf16: B operand of conv-0's weight-gradient GEMM */
 int aptai_conv0_im2col_bf16(const float* wav, int B, int64_t L, int64_t T0, void* x_bf16, void* stream);
 /* weight-norm backward (torch parametrizations.weight_norm, dim=2): dg[taps] += , dv[H][cin][taps] += from the

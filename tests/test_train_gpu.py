@@ -135,9 +135,10 @@ def test_pr_training_step_vs_reference(cuda):
 
 
 def test_training_refuses_unbuilt_configs(cuda):
-    cfg = cfg_base(vocab_size=46)
+    cfg = cfg_base(vocab_size=46, apply_spec_augment=True, mask_feature_prob=0.1)   # feature-axis SpecAugment: not built
     name = register_in_memory_checkpoint("mem://base-seed1-drop", backbone_sd(cfg_base(vocab_size=46), 1))
-    pr = Wav2Vec2_PR(cfg, None, name, VOCAB)          # conv feature encoder NOT frozen: its backward is not built
+    pr = Wav2Vec2_PR(cfg, None, name, VOCAB)
+    pr.wav2vec2.freeze_feature_encoder()
     pr = pr.to(cuda).train()
     wav = W.waveforms(1, 16000, None, seed=1)
     labels, _ = W.phoneme_sequences(1, 5, 5, 2, 45, seed=3, pad=-100)
@@ -293,17 +294,19 @@ def test_aptai_head_dropouts_replayed_by_the_oracle(cuda):
         assert abs(float(ours.norm() / r.norm()) - 1) < 0.03 and cos > 0.995, (name_, float(ours.norm() / r.norm()), cos)
 
 
-def test_unfrozen_conv_encoder_training_vs_oracle(cuda):
+@pytest.mark.parametrize("variant", ["layer", "group"])
+def test_unfrozen_conv_encoder_training_vs_oracle(cuda, variant):
     """Recogniser training with the conv feature encoder UNFROZEN (the reference's default,
     train/train_phoneme_recognizer.py:170) on a 'layer'-norm backbone: gradients of all seven conv layers (weights,
     biases, LayerNorms) and of the rest of the model against the oracle's autograd."""
     import torch.nn.functional as F
     from oracle import w2v2 as ow
-    cfg = cfg_large(vocab_size=46, num_hidden_layers=2)
+    cfg = cfg_large(vocab_size=46, num_hidden_layers=2) if variant == "layer" else cfg_base(vocab_size=46,
+                                                                                             num_hidden_layers=2)
     sd0 = backbone_sd(cfg, 5)
-    name = register_in_memory_checkpoint("mem://large2-seed5-conv", sd0)
+    name = register_in_memory_checkpoint(f"mem://{variant}2-seed5-conv", sd0)
     pr = Wav2Vec2_PR(cfg, None, name, VOCAB)
-    hw, hb = W.linear_params(105, 46, 1024)
+    hw, hb = W.linear_params(105, 46, cfg.hidden_size)
     with torch.no_grad():
         pr.pr_head.weight.copy_(hw); pr.pr_head.bias.copy_(hb)
     pr = pr.to(cuda).train()                                   # feature encoder NOT frozen
@@ -334,7 +337,7 @@ def test_unfrozen_conv_encoder_training_vs_oracle(cuda):
         g = sd[k].grad.double().flatten()
         report[k] = (abs(float(ours.norm()) - ref) / ref, float(ours @ g / (ours.norm() * g.norm())))
     conv = {k: v for k, v in report.items() if k.startswith("feature_extractor.")}
-    assert len(conv) >= 7 * 3          # 7 layers x (weight, LayerNorm weight, LayerNorm bias) at least
+    assert len(conv) >= (7 * 3 if variant == "layer" else 7 + 2)     # conv weights (+ norms) of all seven layers
     worst = max(report.items(), key=lambda t: t[1][0])
     low = min(report.items(), key=lambda t: t[1][1])
     print("unfrozen conv: worst grad-norm deviation", worst, "lowest cosine", low)
