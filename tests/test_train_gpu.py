@@ -342,3 +342,50 @@ def test_unfrozen_conv_encoder_training_vs_oracle(cuda, variant):
     low = min(report.items(), key=lambda t: t[1][1])
     print("unfrozen conv: worst grad-norm deviation", worst, "lowest cosine", low)
     assert worst[1][0] < 0.05 and low[1][1] > 0.98
+
+
+@pytest.mark.parametrize("variant,lens", [("layer", [16000]), ("group", [320000]), ("layer", [100000, 6000, 52000])])
+def test_training_edge_shapes_vs_oracle(cuda, variant, lens):
+    """Edge shapes of the training step against the oracle's autograd (2-layer backbones, conv encoder frozen):
+    a single 1 s utterance (49 frames: fewer rows than one GEMM / wgrad tile), the 20 s maximum (999 frames: eight
+    attention tiles in both directions), and a ragged batch whose shortest utterance is 18 frames long."""
+    import torch.nn.functional as F
+    from oracle import w2v2 as ow
+    mk = cfg_large if variant == "layer" else cfg_base
+    cfg = mk(vocab_size=46, num_hidden_layers=2)
+    sd0 = backbone_sd(cfg, 6)
+    name = register_in_memory_checkpoint(f"mem://{variant}2-seed6-edge", sd0)
+    pr = Wav2Vec2_PR(cfg, None, name, VOCAB)
+    hw, hb = W.linear_params(106, 46, cfg.hidden_size)
+    with torch.no_grad():
+        pr.pr_head.weight.copy_(hw); pr.pr_head.bias.copy_(hb)
+    pr.wav2vec2.freeze_feature_encoder()
+    pr = pr.to(cuda).train()
+    B, L = len(lens), max(lens)
+    wav = W.waveforms(B, L, lens, seed=777)
+    labels, _ = W.phoneme_sequences(B, 3, 8, 2, 45, seed=13, pad=-100)
+    r = pr(wav.to(cuda), torch.tensor(lens, device=cuda), labels.to(cuda))
+    r["loss"].backward()
+    sd = {k: v.clone() for k, v in sd0.items()}
+    trainable = [k for k in sd if not k.startswith("feature_extractor.") and k != "masked_spec_embed"]
+    for k in trainable:
+        sd[k].requires_grad_(True)
+    torch.set_num_threads(os.cpu_count())
+    hidden, _, flen = ow.forward(sd, cfg, wav, lens, return_features=True)
+    lp = F.log_softmax(F.linear(hidden[-1], hw, hb), dim=-1, dtype=torch.float32).transpose(0, 1)
+    loss = F.ctc_loss(lp, labels[labels >= 0], flen, (labels >= 0).sum(-1), blank=0, reduction="mean", zero_infinity=True)
+    loss.backward()
+    assert abs(float(r["loss"].detach()) - float(loss.detach())) / float(loss.detach()) < 2e-3
+    params = dict(pr.named_parameters())
+    norms = {k: float(sd[k].grad.double().norm()) for k in trainable}
+    floor = 1e-4 * float(np.median(list(norms.values())))
+    worst, low = ("", 0.0), ("", 1.0)
+    for k, ref in norms.items():
+        if ref < floor:
+            continue
+        ours = params["wav2vec2." + k].grad.double().cpu().flatten()
+        g = sd[k].grad.double().flatten()
+        worst = max(worst, (k, abs(float(ours.norm()) - ref) / ref), key=lambda t: t[1])
+        low = min(low, (k, float(ours @ g / (ours.norm() * g.norm()))), key=lambda t: t[1])
+    print(f"edge {variant} {lens}: worst grad-norm deviation", worst, "lowest cosine", low)
+    assert worst[1] < 0.05 and low[1] > 0.98
