@@ -333,9 +333,7 @@ class Wav2Vec2Backbone(nn.Module):
         return groups
 
     def check_trainable(self):
-        if self.cfg.apply_spec_augment and self.cfg.mask_feature_prob > 0:
-            raise NotImplementedError("aptai_b200: SpecAugment masking along the feature axis (mask_feature_prob > 0, "
-                                      "HF:1314-1322) is not built in the training path; set it to 0")
+        """Every regulariser of the HF training forward is built; kept as the hook where an unbuilt one is refused."""
 
     # Stochastic regularisers of the training path.  Dropout is counter-based (csrc/dropout.cu): a site's mask is a
     # function of (seed, element index), the seed of (training step, layer, site), so the backward regenerates it.
@@ -395,7 +393,7 @@ class Wav2Vec2Backbone(nn.Module):
         p_at = float(cfg.attention_dropout)
         seed = lambda layer, site: self.drop_seed(step, layer, site)
         sv = SimpleNamespace(B=B, T=T, frame_lens=frame_lens, layers=[], step=step, p_h=p_h, p_a=p_a, p_fp=p_fp, p_at=p_at,
-                             spec_rows=None, skipped=[], conv=conv_sv)
+                             spec_rows=None, spec_keep=None, skipped=[], conv=conv_sv)
         sv.y32 = y.view(M, -1).float()
         _, sv.xn = ops.layernorm(sv.y32, P.fp_ln_w, P.fp_ln_b, eps)
         h0, _ = ops.linear(sv.xn, TP.fp_w_bf16, P.fp_b, want_f32=True, want_bf16=False, seg_rows=T,
@@ -411,6 +409,13 @@ class Wav2Vec2Backbone(nn.Module):
                 # hidden_states[mask] = masked_spec_embed (HF:1303): an indexed row copy
                 h0.index_copy_(0, rows, self.masked_spec_embed.detach().float().expand(rows.numel(), H))
                 sv.spec_rows = rows
+        if cfg.apply_spec_augment and cfg.mask_feature_prob > 0:
+            # feature-axis spans (HF:1314-1322): whole channels of an utterance zeroed, masked_spec_embed rows included
+            from .specaug import compute_mask_indices
+            fmask = compute_mask_indices((B, H), cfg.mask_feature_prob, cfg.mask_feature_length,
+                                         min_masks=cfg.mask_feature_min_masks)
+            sv.spec_keep = torch.from_numpy(~fmask).to(wav.device, F32).view(B, 1, H)
+            h0.view(B, T, H).mul_(sv.spec_keep)
         sv.hp = ops.cast_pad(h0.view(B, T, H), taps // 2)
         sv.pos_pre = torch.empty((M, H), dtype=BF16, device=wav.device)
         h = torch.empty_like(h0)
@@ -478,7 +483,8 @@ class Wav2Vec2Backbone(nn.Module):
                 sv.layers.append(SimpleNamespace(x_in=x, qkv=qkv, ctx=ctx, lse=lse, t=t, x1=x1, u=u, g=g, t2=t2))
                 h, x = h2, x2
             last = h
-        object.__setattr__(self, "_last_regularisers", dict(step=step, skipped=list(sv.skipped), spec_rows=sv.spec_rows))
+        object.__setattr__(self, "_last_regularisers", dict(step=step, skipped=list(sv.skipped), spec_rows=sv.spec_rows,
+                                                             spec_keep=sv.spec_keep))
         return last.view(B, T, H), sv
 
     @torch.no_grad()
@@ -587,6 +593,8 @@ class Wav2Vec2Backbone(nn.Module):
         dh0 = torch.empty_like(dh32)
         ops.posconv(dpre_pad, TP.pos_wt, None, dh32, T, H, groups, taps, dh0, act=0, row_shift=1,
                     seg_valid_rows=flen)       # padded frames were zeroed after the projection (HF:678,754)
+        if sv.spec_keep is not None:
+            dh0.view(sv.B, sv.T, -1).mul_(sv.spec_keep)
         if sv.spec_rows is not None:
             # SpecAugment rows were overwritten by masked_spec_embed: their gradient goes to it, not to the projection
             sel = dh0.index_select(0, sv.spec_rows)

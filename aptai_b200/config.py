@@ -40,7 +40,9 @@ class W2V2Config:
     mask_time_prob: float = 0.05
     mask_time_length: int = 10
     mask_time_min_masks: int = 2
-    mask_feature_prob: float = 0.0            # feature-axis SpecAugment: not built (0 in every config the reference uses)
+    mask_feature_prob: float = 0.0            # feature-axis SpecAugment (HF:1314-1322); 0 in every config the reference uses
+    mask_feature_length: int = 10
+    mask_feature_min_masks: int = 0
     # CTC (train/train_phoneme_recognizer.py:336-347)
     blank: int = 0
     ctc_loss_reduction: str = "mean"

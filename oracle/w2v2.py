@@ -78,7 +78,8 @@ def forward(sd, cfg, wav, lengths, return_features=False, reg=None):
     keys 'proj' (HF:434), 'enc' (HF:694/766), ('attn', l) (HF:603/647), ('act', l) (HF:570), ('ffn', l) (HF:573),
     ('attp', l) (HF:461, attention probabilities [B,nh,T,T]):
     multiplicative masks already scaled by 1/(1-p), broadcastable to the activation; 'skip': set of layers dropped by
-    LayerDrop (HF:701-706/773-778); 'spec': bool [B,T] SpecAugment mask (HF:1303, rows replaced by masked_spec_embed)."""
+    LayerDrop (HF:701-706/773-778); 'spec': bool [B,T] SpecAugment mask (HF:1303, rows replaced by masked_spec_embed);
+    'spec_feat': bool [B,H] feature-axis mask (HF:1314-1322, channels zeroed for the whole utterance)."""
     reg = reg or {}
     m = lambda key, x: x if reg.get(key) is None else x * reg[key].view(x.shape)
     eps = cfg.layer_norm_eps
@@ -92,6 +93,8 @@ def forward(sd, cfg, wav, lengths, return_features=False, reg=None):
     x = m("proj", x)
     if reg.get("spec") is not None:
         x = torch.where(reg["spec"][:, :, None], sd["masked_spec_embed"][None, None, :], x)
+    if reg.get("spec_feat") is not None:
+        x = x * (~reg["spec_feat"])[:, None, :].to(x.dtype)
     x = x.clone()
     x[~mask] = 0.0                                                              # HF:679-682 / 753-756
     key_mask = None if bool(mask.all()) else mask

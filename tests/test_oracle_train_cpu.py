@@ -69,7 +69,8 @@ def test_oracle_regulariser_placement_matches_transformers():
     for stable in (False, True):
         kw = dict(vocab_size=46, num_hidden_layers=3, hidden_dropout=0.1, activation_dropout=0.1, feat_proj_dropout=0.1,
                   attention_dropout=0.1, attn_implementation="eager", final_dropout=0.0, layerdrop=0.4, apply_spec_augment=True, mask_time_prob=0.3,
-                  mask_time_length=10, mask_time_min_masks=2)
+                  mask_time_length=10, mask_time_min_masks=2, mask_feature_prob=0.2, mask_feature_length=8,
+                  mask_feature_min_masks=1)
         if stable:
             kw.update(feat_extract_norm="layer", conv_bias=True, do_stable_layer_norm=True)
         hf_cfg = Wav2Vec2Config(**kw)
@@ -121,7 +122,8 @@ def test_oracle_regulariser_placement_matches_transformers():
         np.random.seed(7)
         flen = [ow.conv_out_length(n, cfg) for n in lens]
         reg["spec"] = torch.from_numpy(compute_mask_indices((B, T), 0.3, 10, frame_lens=flen, min_masks=2))
-        assert reg["spec"].any()
+        reg["spec_feat"] = torch.from_numpy(compute_mask_indices((B, H), 0.2, 8, min_masks=1))
+        assert reg["spec"].any() and reg["spec_feat"].any()
         with torch.no_grad():
             got = ow.forward(sd, cfg, wav, lens, reg=reg)[-1]
         torch.testing.assert_close(got, ref, atol=2e-4, rtol=1e-4)

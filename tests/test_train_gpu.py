@@ -134,18 +134,6 @@ def test_pr_training_step_vs_reference(cuda):
     print("PR base: worst grad-norm deviation", worst, "lowest slice cosine", low)
 
 
-def test_training_refuses_unbuilt_configs(cuda):
-    cfg = cfg_base(vocab_size=46, apply_spec_augment=True, mask_feature_prob=0.1)   # feature-axis SpecAugment: not built
-    name = register_in_memory_checkpoint("mem://base-seed1-drop", backbone_sd(cfg_base(vocab_size=46), 1))
-    pr = Wav2Vec2_PR(cfg, None, name, VOCAB)
-    pr.wav2vec2.freeze_feature_encoder()
-    pr = pr.to(cuda).train()
-    wav = W.waveforms(1, 16000, None, seed=1)
-    labels, _ = W.phoneme_sequences(1, 5, 5, 2, 45, seed=3, pad=-100)
-    with pytest.raises(NotImplementedError):
-        pr(wav.to(cuda), torch.tensor([16000], device=cuda), labels.to(cuda))
-
-
 def test_dropout_kernel(cuda):
     from aptai_b200 import ops
     n = 1 << 22
@@ -171,7 +159,7 @@ def test_dropout_kernel(cuda):
 
 
 def test_training_step_with_regularisers_replayed_by_the_oracle(cuda):
-    """Dropout (feat_proj / hidden / activation / final), LayerDrop and SpecAugment on: the masks the step used are
+    """Dropout (feat_proj / hidden / activation / final), LayerDrop and SpecAugment (time and feature axis) on: the masks the step used are
     materialised from the same counter-based generator and replayed through the oracle (whose regulariser placement
     is pinned against transformers in tests/test_oracle_train_cpu.py); loss and every gradient must agree."""
     import torch.nn.functional as F
@@ -179,7 +167,8 @@ def test_training_step_with_regularisers_replayed_by_the_oracle(cuda):
     from oracle import w2v2 as ow
     cfg = cfg_base(vocab_size=46, hidden_dropout=0.1, activation_dropout=0.1, feat_proj_dropout=0.1, final_dropout=0.1,
                    attention_dropout=0.1, layerdrop=0.25, apply_spec_augment=True, mask_time_prob=0.2,
-                   mask_time_length=10, mask_time_min_masks=2)
+                   mask_time_length=10, mask_time_min_masks=2, mask_feature_prob=0.1, mask_feature_length=16,
+                   mask_feature_min_masks=1)
     sd0 = backbone_sd(cfg_base(vocab_size=46), 1)
     name = register_in_memory_checkpoint("mem://base-seed1-reg", sd0)
     pr = Wav2Vec2_PR(cfg, None, name, VOCAB)
@@ -214,6 +203,8 @@ def test_training_step_with_regularisers_replayed_by_the_oracle(cuda):
     spec = torch.zeros(B * T, dtype=torch.bool)
     spec[info["spec_rows"].cpu()] = True
     reg["spec"] = spec.view(B, T)
+    reg["spec_feat"] = info["spec_keep"].view(B, H).cpu() == 0
+    assert reg["spec_feat"].any() and not reg["spec_feat"].all()
     fin = mask(-1, w2v.SITE_HEAD_A, (B, T, H), 0.1)
     # oracle replay (torch CPU fp32 autograd)
     sd = {k: v.clone() for k, v in sd0.items()}
