@@ -7,6 +7,8 @@ import ctypes as C
 import os
 from typing import Optional
 
+from types import SimpleNamespace
+
 import torch
 
 from . import lib as _lib
@@ -551,10 +553,11 @@ def gelu_bwd(dy: torch.Tensor, pre: torch.Tensor) -> torch.Tensor:
     return out
 
 
-def bilstm_256(x: torch.Tensor, lstm: "torch.nn.LSTM", lens: torch.Tensor) -> torch.Tensor:
+def bilstm_256(x: torch.Tensor, lstm: "torch.nn.LSTM", lens: torch.Tensor, save: bool = False):
     """Bidirectional single-layer LSTM(256 -> 256) over padded [B,T,256] fp32 input with per-utterance lengths
     (packed-sequence semantics): input projection of both directions as one fp32-accurate tensor-core GEMM, the
-    recurrence in the cluster kernel.  Returns hidden fp32 [B,T,512]."""
+    recurrence in the cluster kernel.  Returns hidden fp32 [B,T,512]; with `save` (training) also the namespace
+    `bilstm_256_bwd` needs (gate activations, cell states)."""
     _req(x, F32, "x"); _req(lens, I32, "lens")
     B, T, D = x.shape
     if D != 256 or lstm.hidden_size != 256 or not lstm.bidirectional or lstm.num_layers != 1:
@@ -564,10 +567,47 @@ def bilstm_256(x: torch.Tensor, lstm: "torch.nn.LSTM", lens: torch.Tensor) -> to
     b = torch.cat([f(lstm.bias_ih_l0) + f(lstm.bias_hh_l0), f(lstm.bias_ih_l0_reverse) + f(lstm.bias_hh_l0_reverse)])
     gates = linear_f32x3(x.view(B * T, D), w_ih, b.contiguous())                                   # [B*T, 2048]
     out = torch.empty((B, T, 512), dtype=F32, device=x.device)
-    check(_lib.load().aptai_bilstm_256(gates.data_ptr(), f(lstm.weight_hh_l0).data_ptr(),
-                                       f(lstm.weight_hh_l0_reverse).data_ptr(), lens.data_ptr(), B, T, out.data_ptr(),
-                                       _stream()), "bilstm_256")
+    whf, whr = f(lstm.weight_hh_l0), f(lstm.weight_hh_l0_reverse)
+    if save:
+        ga = torch.empty((B, T, 2, 1024), dtype=F32, device=x.device)
+        cs = torch.empty((B, T, 2, 256), dtype=F32, device=x.device)
+        check(_lib.load().aptai_bilstm_256_train(gates.data_ptr(), whf.data_ptr(), whr.data_ptr(), lens.data_ptr(), B, T,
+                                                 out.data_ptr(), ga.data_ptr(), cs.data_ptr(), _stream()),
+              "bilstm_256_train")
+        return out, SimpleNamespace(x=x, lens=lens, gates_act=ga, cells=cs, hidden=out, w_ih=w_ih, whf=whf, whr=whr)
+    check(_lib.load().aptai_bilstm_256(gates.data_ptr(), whf.data_ptr(), whr.data_ptr(), lens.data_ptr(), B, T,
+                                       out.data_ptr(), _stream()), "bilstm_256")
     return out
+
+
+def bilstm_256_bwd(sv, d_hidden: torch.Tensor, grads: dict) -> torch.Tensor:
+    """Backward of `bilstm_256(..., save=True)`: d_hidden fp32 [B,T,512] -> dx fp32 [B,T,256]; accumulates into the
+    fp32 gradient tensors grads['weight_ih_l0'], ['weight_hh_l0'], ['bias_ih_l0'], ['bias_hh_l0'] and their
+    '_reverse' twins.  Recurrence: the cluster BPTT kernel; weight / input gradients: tensor-core GEMMs on its output."""
+    _req(d_hidden, F32, "d_hidden")
+    B, T, _ = d_hidden.shape
+    M = B * T
+    dev = d_hidden.device
+    dG = torch.zeros((2, M, 1024), dtype=F32, device=dev)
+    check(_lib.load().aptai_bilstm_256_bwd(d_hidden.data_ptr(), sv.gates_act.data_ptr(), sv.cells.data_ptr(),
+                                           sv.whf.data_ptr(), sv.whr.data_ptr(), sv.lens.data_ptr(), B, T, dG.data_ptr(),
+                                           _stream()), "bilstm_256_bwd")
+    dGb = scale_cast_bf16(dG)
+    xb = scale_cast_bf16(sv.x.view(M, 256))
+    # h_{t-1} as seen by each direction: the forward chain reads the previous frame, the reverse chain the next one
+    hprev = torch.zeros((2, B, T, 256), dtype=F32, device=dev)
+    hprev[0, :, 1:] = sv.hidden[:, :-1, :256]
+    hprev[1, :, :-1] = sv.hidden[:, 1:, 256:]
+    hpb = scale_cast_bf16(hprev.view(2, M, 256))
+    dx = None
+    for d, sfx in enumerate(("", "_reverse")):
+        wgrad(dGb[d], xb, grads["weight_ih_l0" + sfx])
+        wgrad(dGb[d], hpb[d], grads["weight_hh_l0" + sfx])
+        colsum(dG[d], grads["bias_ih_l0" + sfx])
+        colsum(dG[d], grads["bias_hh_l0" + sfx])
+        wt = sv.w_ih[d * 1024:(d + 1) * 1024].t().contiguous().to(BF16)            # [256, 1024]
+        dx, _ = linear(dGb[d], wt, None, residual=dx, want_f32=True, want_bf16=False)
+    return dx.view(B, T, 256)
 
 
 def prepare_weights(table: torch.Tensor, n_entries: int, total_tiles: int) -> None:

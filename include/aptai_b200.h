@@ -155,6 +155,15 @@ int aptai_cross_attention(const float* frame, const int32_t* phn_ids, const floa
  * zero beyond lens[b]. */
 int aptai_bilstm_256(const float* gates_in, const float* w_hh_fwd, const float* w_hh_rev, const int32_t* lens, int B,
                      int T, float* out, void* stream);
+/* Training (train/train_force_aptai.py: loss.backward() through the nn.LSTM of models/modules.py:197): the same
+ * recurrence, also keeping the gate activations gates_act fp32 [B][T][2][1024] (i,f,g,o after sigmoid / tanh) and the
+ * cell states cells fp32 [B][T][2][256]; and the backward through time, which turns d_out fp32 [B][T][512] into the
+ * gradient of the pre-activation gates d_gates fp32 [2][B][T][1024] (direction-major; padding frames are left
+ * untouched: pre-zero it).  dW_ih, dW_hh, the bias gradients and dx are GEMMs on d_gates. */
+int aptai_bilstm_256_train(const float* gates_in, const float* w_hh_fwd, const float* w_hh_rev, const int32_t* lens,
+                           int B, int T, float* out, float* gates_act, float* cells, void* stream);
+int aptai_bilstm_256_bwd(const float* d_out, const float* gates_act, const float* cells, const float* w_hh_fwd,
+                         const float* w_hh_rev, const int32_t* lens, int B, int T, float* d_gates, void* stream);
 
 /* masked MSE + cross entropy of APTAI.forward (models/aptai.py:89-102).  out3 = {loss, mse, ce}. */
 int aptai_masked_mse_ce(const float* tv_pred, const float* tv_tgt, const float* logits, const int64_t* phn_tgt,

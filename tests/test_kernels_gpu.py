@@ -283,3 +283,37 @@ def test_bilstm_cluster_kernel_vs_torch(cuda, B, T, lens):
     out, hid = rnn(x.to(cuda), lens)
     torch.testing.assert_close(hid.cpu(), ref_h, atol=2e-4, rtol=1e-3)
     torch.testing.assert_close(out.cpu(), ref_out, atol=5e-4, rtol=1e-3)
+
+
+@pytest.mark.parametrize("B,T,lens", [(3, 40, [40, 17, 1]), (9, 120, None)])
+def test_bilstm_backward_through_time_vs_torch(cuda, B, T, lens):
+    """BPTT cluster kernel + the GEMMs on its gate gradients (ops.bilstm_256_bwd) against torch autograd through
+    nn.LSTM on packed sequences (CPU fp32): dx and all eight parameter gradients."""
+    from torch.nn.utils.rnn import pack_padded_sequence, pad_packed_sequence
+    from aptai_b200 import ops
+    torch.manual_seed(4)
+    lstm = torch.nn.LSTM(256, 256, bidirectional=True, num_layers=1, batch_first=True)
+    g = torch.Generator().manual_seed(6)
+    if lens is None:
+        lens = torch.randint(30, T + 1, (B,), generator=g).tolist()
+        lens[0] = T
+    x = torch.randn((B, T, 256), generator=g, requires_grad=True)
+    dh = torch.randn((B, T, 512), generator=g)
+    packed = pack_padded_sequence(x, torch.tensor(lens), batch_first=True, enforce_sorted=False)
+    ref_h, _ = pad_packed_sequence(lstm(packed)[0], batch_first=True, total_length=T)
+    (ref_h * dh).sum().backward()
+    ln = torch.tensor(lens, dtype=torch.int32, device=cuda)
+    hid, sv = ops.bilstm_256(x.detach().to(cuda), lstm, ln, save=True)
+    torch.testing.assert_close(hid.cpu(), ref_h.detach(), atol=2e-4, rtol=1e-3)
+    grads = {n: torch.zeros_like(p, device=cuda) for n, p in lstm.named_parameters()}
+    dx = ops.bilstm_256_bwd(sv, dh.to(cuda), grads)
+    torch.cuda.synchronize()
+
+    def close(name, got, ref):
+        got, ref = got.double().cpu().flatten(), ref.double().flatten()
+        rel = float((got - ref).norm() / ref.norm())
+        assert rel < 1e-2, (name, rel)
+        return rel
+
+    worst = max(close("dx", dx, x.grad), *[close(n, grads[n], p.grad) for n, p in lstm.named_parameters()])
+    print(f"BiLSTM backward B={B} T={T}: worst relative L2 error {worst:.2e}")
