@@ -5,9 +5,8 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import Optional
-
 from types import SimpleNamespace
+from typing import Optional
 
 import torch
 
@@ -338,6 +337,27 @@ def cross_attention(frame, phn_ids, emb, pe, wq, bq, wk, bk, ln_w, ln_b, eps: fl
                                             att_out.data_ptr(), energy.data_ptr(), att.data_ptr(), _stream()),
           "cross_attention")
     return att_out, energy, att
+
+
+def cross_attention_bwd(frame, phn_ids, phn_hidden, wq, bq, wk, bk, ln_w, eps, d_att_out, d_att, d_ln_w, d_ln_b):
+    """Backward of `cross_attention` (phn_hidden form).  Returns (d_q fp32 [B,T,128], d_k fp32 [B,60,128]): gradients
+    of the projected queries / keys; d_ln_w / d_ln_b (fp32 [256]) accumulate."""
+    _req(frame, F32, "frame"); _req(phn_ids, I32, "phn_ids"); _req(phn_hidden, F32, "phn_hidden")
+    _req(d_att_out, F32, "d_att_out"); _req(d_ln_w, F32, "d_ln_w"); _req(d_ln_b, F32, "d_ln_b")
+    B, T, D = frame.shape
+    assert D == 128 and phn_ids.shape == (B, 60) and d_att_out.shape == (B, T, 256)
+    if d_att is not None:
+        _req(d_att, F32, "d_att")
+        assert d_att.shape == (B, T, 60)
+    f = lambda t: t.detach().to(device=frame.device, dtype=F32).contiguous()
+    d_q = torch.empty((B, T, 128), dtype=F32, device=frame.device)
+    d_k = torch.zeros((B, 60, 128), dtype=F32, device=frame.device)
+    check(_lib.load().aptai_cross_attention_bwd(frame.data_ptr(), phn_ids.data_ptr(), phn_hidden.data_ptr(),
+                                                f(wq).data_ptr(), f(bq).data_ptr(), f(wk).data_ptr(), f(bk).data_ptr(),
+                                                f(ln_w).data_ptr(), eps, B, T, d_att_out.data_ptr(), _ptr(d_att),
+                                                d_q.data_ptr(), d_k.data_ptr(), d_ln_w.data_ptr(), d_ln_b.data_ptr(),
+                                                _stream()), "cross_attention_bwd")
+    return d_q, d_k
 
 
 def masked_mse_ce(tv_pred, tv_tgt, logits, phn_tgt, return_ws: bool = False):

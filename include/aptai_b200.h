@@ -149,6 +149,16 @@ int aptai_cross_attention(const float* frame, const int32_t* phn_ids, const floa
                           const float* ln_b, float eps, int B, int T, float* att_out, float* energy, float* att,
                           void* stream);
 
+/* Backward of the block for training (train/train_force_aptai.py: loss.backward() through CrossAttention and the
+ * log-softmax alignment matrix).  phn_hidden fp32 [B][60][128] = the phoneme embeddings the forward used (after the
+ * positional-encoding dropout).  d_att_out fp32 [B][T][256]; d_att fp32 [B][T][60] or NULL (gradient of att).
+ * d_q fp32 [B][T][128]: gradient of the projected queries (dW_q, db_q and d_frame are GEMMs on it); d_k fp32
+ * [B][60][128]: gradient of the projected keys, d_ln_w / d_ln_b fp32 [256]: all three ACCUMULATE (atomics). */
+int aptai_cross_attention_bwd(const float* frame, const int32_t* phn_ids, const float* phn_hidden, const float* wq,
+                              const float* bq, const float* wk, const float* bk, const float* ln_w, float eps, int B,
+                              int T, const float* d_att_out, const float* d_att, float* d_q, float* d_k,
+                              float* d_ln_w, float* d_ln_b, void* stream);
+
 /* Recurrence of Force_APTAI's bidirectional LSTM (models/modules.py:197-211: nn.LSTM(256, 256, bidirectional,
  * batch_first) over pack_padded_sequence).  gates_in fp32 [B][T][2][1024] = W_ih x_t + b_ih + b_hh per direction
  * (torch gate order i,f,g,o), w_hh_* fp32 [1024][256], lens int32 [B]; out fp32 [B][T][512] (forward | reverse),
