@@ -18,6 +18,7 @@ import torch.nn as nn
 from . import ops
 from .aptai import TV_NAMES
 from .modules import CrossAttention, ForwardSumLoss, LowPassFilterLayer, PositionalEncoding, RNN
+from .train import GradBuffer, attach_backward
 from .w2v2_pr import Wav2Vec2_PR
 
 
@@ -59,10 +60,12 @@ class Force_APTAI(nn.Module):
 
     # ---------------------------------------------------------------------------------------------- shared trunk
     @torch.no_grad()
-    def _trunk(self, audio_inputs, audio_lengths, phn_seqs=None):
-        if self.training:
-            raise NotImplementedError("aptai_b200: training-mode dropout/backward is not built yet; call .eval()")
+    def _recogniser(self, audio_inputs, audio_lengths, phn_seqs=None):
+        """Frozen recogniser in eval mode (the reference's get_embeddings switches it to eval and runs under no_grad,
+        models/w2v2_pr.py:125-127), CTC-decoded (or injected) phoneme sequences padded to 60 slots."""
         pr = self.w2v2_pr
+        if pr.training:
+            pr.eval()
         _, h, logits = pr._logits(audio_inputs, audio_lengths)
         dev = h.device
         frame_seq_lens = pr.wav2vec2._get_feat_extract_output_lengths(audio_lengths.reshape(-1)).cpu().tolist()
@@ -73,7 +76,12 @@ class Force_APTAI(nn.Module):
             assert len(lst) < self.max_phn_seq_len, "Need longer max phoneme sequence length."
             padded.append(np.pad(lst, (0, self.max_phn_seq_len - len(lst)), mode="constant"))
         phn_pred_seq = torch.tensor(np.stack(padded), dtype=torch.int32, device=dev)
-        phn_pred_mask = (phn_pred_seq != 0).to(torch.int)
+        return h, logits, frame_seq_lens, phn_pred_list, phn_seq_lens, phn_pred_seq
+
+    @torch.no_grad()
+    def _trunk(self, audio_inputs, audio_lengths, phn_seqs=None):
+        h, logits, frame_seq_lens, phn_pred_list, phn_seq_lens, phn_pred_seq = self._recogniser(
+            audio_inputs, audio_lengths, phn_seqs)
         B, T, H = h.shape
         fl = self.frame_lin                 # Linear(H,128) on the tcgen05 GEMM, bf16x3 split (fp32-accurate)
         fh = ops.linear_f32x3(h.reshape(B * T, H).contiguous(), fl.weight, fl.bias.detach().float().contiguous())
@@ -91,6 +99,8 @@ class Force_APTAI(nn.Module):
                 TMCL, TMCD, TBCL, TBCD, phn_seqs=None):
         """models/force_aptai.py:80-178."""
         tv_targets = torch.stack([LA, LP, JA, TTCL, TTCD, TMCL, TMCD, TBCL, TBCD], dim=-1).float()
+        if self.training:
+            return self._forward_train(audio_inputs, audio_lengths, tv_targets, phn_seqs)
         t = self._trunk(audio_inputs, audio_lengths, phn_seqs)
         att = t["att"]
         dev = att.device
@@ -108,6 +118,137 @@ class Force_APTAI(nn.Module):
         pred_frame_phns = [[int(x) for x in frame_phn[b, : t["frame_seq_lens"][b]]] for b in range(att.shape[0])]
         return {"loss": loss, "tv_loss": tv_loss, "align_loss": align_loss, "tvs_pred": tvs_out,
                 "pred_frame_phns": pred_frame_phns, "pred_ctc_phn_seq": t["phn_pred_list"]}
+
+
+    # ---------------------------------------------------------------------------------------------- training
+    def grad_buffer(self) -> GradBuffer:
+        """Flat fp32 gradient buffer over the trainable tail (the recogniser is frozen, models/force_aptai.py:76-78)."""
+        gb = getattr(self, "_grad_buffer", None)
+        if gb is None:
+            gb = GradBuffer(list(self.named_parameters()))
+            object.__setattr__(self, "_grad_buffer", gb)
+            return gb
+        dropped = False
+        for n, p in gb.params:
+            if not gb.owns(p):
+                dropped = True
+                p.grad = gb.flat[gb.offsets[n]: gb.offsets[n] + p.numel()].view(p.shape)
+        if dropped:
+            gb.zero()
+        return gb
+
+    def _drop_seed(self, site: int) -> int:
+        # sites 100..102 of the backbone's counter-based generator (frame_drop, pe_phn.dropout, rnn dropout)
+        return self.w2v2_pr.wav2vec2.drop_seed(self._drop_step, site, 0)
+
+    def _forward_train(self, audio_inputs, audio_lengths, tv_targets, phn_seqs=None):
+        with torch.no_grad():
+            loss_val, run_backward, out = self._train_step(audio_inputs, audio_lengths, tv_targets, phn_seqs)
+        out["loss"] = attach_backward(loss_val, self.frame_lin.weight, run_backward)
+        return out
+
+    def _train_step(self, audio_inputs, audio_lengths, tv_targets, phn_seqs=None):
+        """Training step of train/train_force_aptai.py: the forward keeps what the backward needs; `loss.backward()`
+        launches the hand-written backward of the tail (low-pass adjoint, head MLP, BiLSTM through time,
+        cross-attention, embedding, frame projection).  Dropouts (frame_drop 0.2, positional-encoding 0.2, RNN 0.1) are
+        counter-based like the backbone's and regenerated in the backward."""
+        h, logits, frame_seq_lens, phn_pred_list, phn_seq_lens, ids = self._recogniser(audio_inputs, audio_lengths,
+                                                                                       phn_seqs)
+        dev = h.device
+        B, T, H = h.shape
+        M = B * T
+        gb = self.grad_buffer()
+        object.__setattr__(self, "_drop_step", getattr(self, "_drop_step", 0) + 1)
+        f = lambda p: p.detach().float().contiguous()
+        fl, xa, rnn = self.frame_lin, self.xatt, self.rnn
+        p_f, p_pe, p_r = float(self.frame_drop.p), float(self.pe_phn.dropout.p), float(rnn.linear[1].p)
+        s_f, s_pe, s_r = self._drop_seed(100), self._drop_seed(101), self._drop_seed(102)
+        h2 = h.reshape(M, H).contiguous()
+        fh = ops.linear_f32x3(h2, fl.weight, f(fl.bias))
+        if p_f > 0:
+            ops.dropout(fh, p_f, s_f, out_f32=fh)
+        phn = (f(self.phn_emb_layer.weight)[ids.long()] + self.pe_phn.pe[:, 0, :].float()[None]).contiguous()
+        if p_pe > 0:
+            ops.dropout(phn, p_pe, s_pe, out_f32=phn)
+        att_out, _, att = ops.cross_attention(fh.view(B, T, -1), ids, None, None, xa.q.weight, xa.q.bias, xa.k.weight,
+                                              xa.k.bias, xa.layer_norm.weight, xa.layer_norm.bias, xa.layer_norm.eps,
+                                              phn_hidden=phn)
+        ln = (torch.as_tensor(frame_seq_lens, dtype=torch.int32).reshape(B).to(dev) if B > 1
+              else torch.full((1,), T, dtype=torch.int32, device=dev))
+        hidden, lsv = ops.bilstm_256(att_out, rnn.lstm, ln, save=True)
+        l0, l3 = rnn.linear[0], rnn.linear[3]
+        z1 = ops.linear_f32x3(hidden.view(M, -1), l0.weight, f(l0.bias))
+        if p_r > 0:
+            ops.dropout(z1, p_r, s_r, out_f32=z1)
+        w3 = f(l3.weight)
+        raw, _, _ = ops.heads(z1, w3, f(l3.bias), ops.ACT_TANH, None, None, 0, want_argmax=False)
+        taps = self.tv_lowpass.lowpass.weight.detach().reshape(-1).to(device=dev, dtype=torch.float64).contiguous()
+        tvs_out = ops.lowpass(raw.view(B, T, 9), taps)
+        tv_targets = tv_targets.to(dev)
+        tv_mask = tv_targets != -100.0
+        diff = torch.where(tv_mask, tvs_out - tv_targets, torch.zeros((), device=dev))
+        count = tv_mask.sum().clamp(min=1).float()
+        tv_loss = (diff * diff).sum() / count
+        # forward-sum loss with its gradient w.r.t. the alignment log-probs (models/modules.py:65-117)
+        text = torch.as_tensor(phn_seq_lens, dtype=torch.int32, device=dev).reshape(B).contiguous()
+        mel = torch.as_tensor(frame_seq_lens, dtype=torch.int32, device=dev).reshape(B).contiguous()
+        N = att.shape[2]
+        tg = torch.arange(1, N + 1, dtype=torch.int32, device=dev)[None].expand(B, N).contiguous()
+        scale = (1.0 / (text.clamp(min=1).float() * B)).contiguous()
+        r = ops.logsoftmax_ctc(att, tg, mel, text, blank=0, zero_infinity=True, scale=scale, want_log_probs=False,
+                               want_grad=True, prepend_blank=True, blank_value=float(self.align_loss.blank_logprob),
+                               vocab_len=(text + 1).contiguous())
+        align_loss = r["loss_sum"][0]
+        a = 0.4
+        loss_val = a * tv_loss + (1 - a) * align_loss
+        G = lambda name: gb.view(name)
+        bf = ops.scale_cast_bf16
+
+        def run_backward(grad_out):
+            gs = float(grad_out)
+            d_tvs = (diff * (2.0 * a * gs / count)).contiguous()
+            d_raw = ops.lowpass(d_tvs, taps).view(M, 9)                     # symmetric FIR: adjoint = the filter
+            d_z1 = ops.heads_bwd(z1, d_raw, w3, ops.ACT_TANH, G("rnn.linear.3.weight"), G("rnn.linear.3.bias"),
+                                 None, None, 0, None, None)
+            if p_r > 0:
+                ops.dropout(d_z1, p_r, s_r, out_f32=d_z1)
+            d_z1b = bf(d_z1)
+            ops.wgrad(d_z1b, bf(hidden.view(M, -1)), G("rnn.linear.0.weight"))
+            ops.colsum(d_z1, G("rnn.linear.0.bias"))
+            d_hidden, _ = ops.linear(d_z1b, f(l0.weight).t().contiguous().to(torch.bfloat16), None, want_f32=True,
+                                     want_bf16=False)
+            lg = {n: G("rnn.lstm." + n) for n, _ in rnn.lstm.named_parameters()}
+            d_att_out = ops.bilstm_256_bwd(lsv, d_hidden.view(B, T, -1), lg)
+            d_att = (r["grad"] * ((1 - a) * gs)).contiguous()
+            d_q, d_k = ops.cross_attention_bwd(fh.view(B, T, -1), ids, phn, xa.q.weight, xa.q.bias, xa.k.weight,
+                                               xa.k.bias, xa.layer_norm.weight, xa.layer_norm.eps,
+                                               d_att_out.contiguous(), d_att, G("xatt.layer_norm.weight"),
+                                               G("xatt.layer_norm.bias"))
+            d_qb, d_kb = bf(d_q.view(M, -1)), bf(d_k.view(B * N, -1))
+            ops.wgrad(d_qb, bf(fh), G("xatt.q.weight"))
+            ops.colsum(d_q.view(M, -1), G("xatt.q.bias"))
+            ops.wgrad(d_kb, bf(phn.view(B * N, -1)), G("xatt.k.weight"))
+            ops.colsum(d_k.view(B * N, -1), G("xatt.k.bias"))
+            d_fh, _ = ops.linear(d_qb, f(xa.q.weight).t().contiguous().to(torch.bfloat16), None, want_f32=True,
+                                 want_bf16=False)
+            if p_f > 0:
+                ops.dropout(d_fh, p_f, s_f, out_f32=d_fh)
+            ops.wgrad(bf(d_fh), bf(h2), G("frame_lin.weight"))
+            ops.colsum(d_fh, G("frame_lin.bias"))
+            d_phn, _ = ops.linear(d_kb, f(xa.k.weight).t().contiguous().to(torch.bfloat16), None, want_f32=True,
+                                  want_bf16=False)
+            if p_pe > 0:
+                ops.dropout(d_phn, p_pe, s_pe, out_f32=d_phn)
+            d_emb = G("phn_emb_layer.weight")
+            keep = (ids.view(-1) != 0)                                      # padding_idx = 0 receives no gradient
+            d_emb.index_add_(0, ids.view(-1).long()[keep], d_phn[keep])
+
+        align_out = torch.max(att, axis=2)[1]
+        frame_phn = torch.gather(ids.long(), 1, align_out).cpu().numpy()
+        pred_frame_phns = [[int(x) for x in frame_phn[b, : frame_seq_lens[b]]] for b in range(B)]
+        object.__setattr__(self, "_last_train", dict(step=self._drop_step, seeds=(s_f, s_pe, s_r)))
+        return loss_val, run_backward, {"loss": None, "tv_loss": tv_loss, "align_loss": align_loss, "tvs_pred": tvs_out,
+                                        "pred_frame_phns": pred_frame_phns, "pred_ctc_phn_seq": phn_pred_list}
 
     def get_config(self):
         return {"pr_model_path": self.pr_model_path, "w2v2_pr_cfg": self.w2v2_pr_cfg, "device": self.device,

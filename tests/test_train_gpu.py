@@ -380,3 +380,77 @@ def test_training_edge_shapes_vs_oracle(cuda, variant, lens):
         low = min(low, (k, float(ours @ g / (ours.norm() * g.norm()))), key=lambda t: t[1])
     print(f"edge {variant} {lens}: worst grad-norm deviation", worst, "lowest cosine", low)
     assert worst[1] < 0.05 and low[1] > 0.98
+
+
+@pytest.mark.parametrize("B,drop", [(1, False), (3, True)])
+def test_force_aptai_training_step_vs_oracle(cuda, B, drop):
+    """Force_APTAI in train mode (train/train_force_aptai.py): loss.backward() runs the hand-written backward of the
+    tail (low-pass adjoint, head MLP, BiLSTM through time, cross-attention, embedding, frame projection); the frozen
+    recogniser gets no gradient.  Oracle: oracle/force_tail.py (torch autograd on the CPU) fed with the recogniser's
+    hidden states, the same phoneme sequences and — for the stochastic case — the three dropout masks the step used,
+    materialised from the counter-based generator.  Followed by one fused Adam step."""
+    from helpers import force_tail_state
+    from aptai_b200 import Force_APTAI, ops
+    from oracle.force_tail import ForceTail
+    cfg = cfg_base(vocab_size=46)
+    name = register_in_memory_checkpoint("mem://base-seed1-force", backbone_sd(cfg, 1))
+    pr = Wav2Vec2_PR(cfg, None, name, VOCAB)
+    hw, hb = W.linear_params(103, 46, cfg.hidden_size)
+    with torch.no_grad():
+        pr.pr_head.weight.copy_(hw); pr.pr_head.bias.copy_(hb)
+    fa = Force_APTAI("unused", cuda, VOCAB, w2v2_pr=pr)
+    tail = force_tail_state(fa.state_dict())
+    fa.load_state_dict(tail, strict=False)
+    fa = fa.to(cuda).train()
+    if not drop:
+        fa.frame_drop.p = fa.pe_phn.dropout.p = fa.rnn.linear[1].p = 0.0
+    lens = [32000, 27000, 16000][:B]
+    wav = W.waveforms(B, 32000, lens, seed=4321)
+    seqs, _ = W.phoneme_sequences(B, 8, 30, 1, 45, seed=17, pad=0)
+    seqs = [np.asarray(s[s != 0], dtype=np.int64) for s in seqs.numpy()]
+    T = 99
+    g = torch.Generator().manual_seed(9)
+    tvt = torch.randn((B, T, 9), generator=g)
+    flen = [cfg.conv_out_length(n) for n in lens]
+    for b in range(B):
+        tvt[b, flen[b]:] = -100.0
+    opt = FusedAdam([p for p in fa.parameters() if p.requires_grad], lr=1e-3)
+    opt.zero_grad()
+    torch.manual_seed(77)
+    tv_cols = [tvt[:, :, i].contiguous().to(cuda) for i in range(9)]
+    res = fa(0, wav.to(cuda), torch.tensor(lens, device=cuda), None, None, *tv_cols, phn_seqs=seqs)
+    res["loss"].backward()
+    torch.cuda.synchronize()
+    assert all(p.grad is None for p in fa.w2v2_pr.parameters())
+    # ---- oracle replay
+    with torch.no_grad():
+        _, h, _ = pr._logits(wav.to(cuda), torch.tensor(lens, device=cuda))
+    ids = torch.zeros((B, 60), dtype=torch.int64)
+    for b, s in enumerate(seqs):
+        ids[b, : len(s)] = torch.from_numpy(s)
+    reg = {}
+    if drop:
+        s_f, s_pe, s_r = fa._last_train["seeds"]
+        mk = lambda shape, p, seed: ops.dropout(torch.ones(shape, device=cuda), p, seed, want_f32=True)[0].cpu()
+        reg = {"frame": mk((B, T, 128), 0.2, s_f), "pe": mk((B, 60, 128), 0.2, s_pe), "rnn": mk((B, T, 256), 0.1, s_r)}
+    ref = ForceTail(cfg.hidden_size, len(VOCAB))
+    ref.load_state_dict(tail, strict=True)
+    out = ref(h.cpu(), ids, flen, [len(s) for s in seqs], tvt, reg)
+    out["loss"].backward()
+    for k in ("loss", "tv_loss", "align_loss"):
+        assert abs(float(res[k].detach()) - float(out[k])) / abs(float(out[k])) < 2e-3, (k, float(res[k]), float(out[k]))
+    torch.testing.assert_close(res["tvs_pred"].cpu(), out["tvs"].detach(), atol=2e-3, rtol=1e-3)
+    params = dict(fa.named_parameters())
+    worst, low = ("", 0.0), ("", 1.0)
+    for k, p_ref in ref.named_parameters():
+        got, want = params[k].grad.double().cpu().flatten(), p_ref.grad.double().flatten()
+        rel = abs(float(got.norm()) - float(want.norm())) / float(want.norm())
+        cos = float(got @ want / (got.norm() * want.norm()))
+        worst = max(worst, (k, rel), key=lambda t: t[1])
+        low = min(low, (k, cos), key=lambda t: t[1])
+    print(f"Force_APTAI training B={B} dropout={drop}: worst grad-norm deviation", worst, "lowest cosine", low)
+    assert worst[1] < 0.03 and low[1] > 0.995
+    assert float(params["phn_emb_layer.weight"].grad[0].abs().max()) == 0.0          # padding_idx row
+    before = params["rnn.lstm.weight_hh_l0"].detach().clone()
+    opt.step()
+    assert not torch.equal(before, params["rnn.lstm.weight_hh_l0"].detach())
