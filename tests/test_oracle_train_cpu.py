@@ -127,3 +127,32 @@ def test_oracle_regulariser_placement_matches_transformers():
         with torch.no_grad():
             got = ow.forward(sd, cfg, wav, lens, reg=reg)[-1]
         torch.testing.assert_close(got, ref, atol=2e-4, rtol=1e-4)
+
+
+def test_oracle_force_tail_gradients_match_reference():
+    """oracle/force_tail.py (the checker of the Force_APTAI training tests) against the reference's own Force_APTAI
+    class in train mode (tests/golden/golden_force_train_v1.npz: batch 1, dropouts at p = 0, 24x1024 recogniser)."""
+    from helpers import VOCAB, cfg_large, force_tail_state
+    from oracle.force_tail import ForceTail
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_force_train_v1.npz"))
+    cfg = cfg_large(vocab_size=46)
+    wav = W.waveforms(1, 32000, None, seed=5151)
+    torch.set_num_threads(os.cpu_count())
+    with torch.no_grad():
+        h = ow.forward(backbone_sd(cfg, 0), cfg, wav, [32000])[-1]
+    ref = ForceTail(1024, len(VOCAB))
+    ref.load_state_dict(force_tail_state(ref.state_dict()), strict=True)
+    known = g["known"]
+    ids = torch.zeros((1, 60), dtype=torch.int64)
+    ids[0, : len(known)] = torch.from_numpy(known)
+    out = ref(h, ids, [99], [len(known)], torch.from_numpy(g["tvt"]))
+    out["loss"].backward()
+    np.testing.assert_allclose([float(out["loss"]), float(out["tv_loss"]), float(out["align_loss"])], g["losses"], rtol=2e-5)
+    norms = dict(zip([str(n) for n in g["grad_names"]], g["grad_norms"]))
+    params = dict(ref.named_parameters())
+    assert set(norms) == set(params)
+    for k, n_ref in norms.items():
+        got = params[k].grad
+        assert abs(float(got.double().norm()) - n_ref) <= 2e-4 * n_ref + 1e-9, k
+        sl = g[f"grad::{k}"]
+        np.testing.assert_allclose(got.reshape(-1)[:256].numpy(), sl, atol=2e-4 * float(np.abs(sl).max()) + 1e-9, rtol=2e-3)

@@ -438,7 +438,7 @@ def test_force_aptai_training_step_vs_oracle(cuda, B, drop):
     out = ref(h.cpu(), ids, flen, [len(s) for s in seqs], tvt, reg)
     out["loss"].backward()
     for k in ("loss", "tv_loss", "align_loss"):
-        assert abs(float(res[k].detach()) - float(out[k])) / abs(float(out[k])) < 2e-3, (k, float(res[k]), float(out[k]))
+        assert abs(float(res[k].detach()) - float(out[k].detach())) / abs(float(out[k].detach())) < 2e-3, (k, float(res[k].detach()), float(out[k].detach()))
     torch.testing.assert_close(res["tvs_pred"].cpu(), out["tvs"].detach(), atol=2e-3, rtol=1e-3)
     params = dict(fa.named_parameters())
     worst, low = ("", 0.0), ("", 1.0)
@@ -454,3 +454,38 @@ def test_force_aptai_training_step_vs_oracle(cuda, B, drop):
     before = params["rnn.lstm.weight_hh_l0"].detach().clone()
     opt.step()
     assert not torch.equal(before, params["rnn.lstm.weight_hh_l0"].detach())
+
+
+def test_force_aptai_training_step_vs_reference(cuda):
+    """Force_APTAI training step against gradients of the reference's own class (golden_force_train_v1.npz: batch 1,
+    24x1024 recogniser, dropouts at p = 0)."""
+    from helpers import force_tail_state
+    from aptai_b200 import Force_APTAI
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_force_train_v1.npz"))
+    cfg = cfg_large(vocab_size=46)
+    name = register_in_memory_checkpoint("mem://large-seed0", backbone_sd(cfg, 0))
+    pr = Wav2Vec2_PR(cfg, None, name, VOCAB)
+    hw, hb = W.linear_params(103, 46, 1024)
+    with torch.no_grad():
+        pr.pr_head.weight.copy_(hw); pr.pr_head.bias.copy_(hb)
+    fa = Force_APTAI("unused", cuda, VOCAB, w2v2_pr=pr)
+    fa.load_state_dict(force_tail_state(fa.state_dict()), strict=False)
+    fa = fa.to(cuda).train()
+    fa.frame_drop.p = fa.pe_phn.dropout.p = fa.rnn.linear[1].p = 0.0
+    wav = W.waveforms(1, 32000, None, seed=5151)
+    tvt = torch.from_numpy(g["tvt"]).to(cuda)
+    res = fa(0, wav.to(cuda), torch.tensor([32000], device=cuda), None, None,
+             *[tvt[:, :, i].contiguous() for i in range(9)], phn_seqs=[g["known"]])
+    res["loss"].backward()
+    got = [float(res[k].detach()) for k in ("loss", "tv_loss", "align_loss")]
+    np.testing.assert_allclose(got, g["losses"], rtol=5e-3)
+    norms = dict(zip([str(n) for n in g["grad_names"]], g["grad_norms"]))
+    params = dict(fa.named_parameters())
+    worst, low = ("", 0.0), ("", 1.0)
+    for k, n_ref in norms.items():
+        gr = params[k].grad.double().cpu().flatten()
+        worst = max(worst, (k, abs(float(gr.norm()) - n_ref) / n_ref), key=lambda t: t[1])
+        sl = torch.from_numpy(g[f"grad::{k}"]).double()
+        low = min(low, (k, float(gr[:256] @ sl / (gr[:256].norm() * sl.norm()))), key=lambda t: t[1])
+    print("Force_APTAI training vs reference: worst grad-norm deviation", worst, "lowest slice cosine", low)
+    assert worst[1] < 0.05 and low[1] > 0.98
