@@ -4,6 +4,8 @@
   config 4: APTAI training step (articulatory regression + phoneme CE), 24x1024 backbone, batch 32 per GPU of 4-8 s
             utterances, frozen conv encoder, fused Adam, data-parallel gradient all-reduce overlapped with the backward
   config 2: Wav2Vec2_PR CTC forward + backward, batch 16 x 8 s
+  config 3: Force_APTAI training step (frozen recogniser forward in eval mode, tail forward + backward + Adam), batch
+            64 x 8 s with known phoneme sequences of 10-59 phonemes
 
   python profiles/train_bench.py --config 4 --steps 5
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29555 \
@@ -23,7 +25,7 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from aptai_b200 import APTAI, Wav2Vec2_PR, lib  # noqa: E402
+from aptai_b200 import APTAI, Force_APTAI, Wav2Vec2_PR, lib  # noqa: E402
 from aptai_b200.backbone import register_in_memory_checkpoint  # noqa: E402
 from aptai_b200.config import W2V2Config  # noqa: E402
 from aptai_b200.synth import backbone_state_dict, linear_params, phoneme_sequences  # noqa: E402
@@ -34,7 +36,7 @@ NO_REG = dict(hidden_dropout=0.0, activation_dropout=0.0, attention_dropout=0.0,
 VOCAB = {"(blank)": 0, "(...)": 1, **{f"p{i}": i for i in range(2, 46)}}
 
 
-def flops_train(cfg, lens):
+def flops_train(cfg, lens, mult=3.0):
     H, F, N = cfg.hidden_size, cfg.intermediate_size, cfg.num_hidden_layers
     conv = rest = 0.0
     for L in lens:
@@ -46,12 +48,12 @@ def flops_train(cfg, lens):
         T = t
         rest += 2.0 * T * cin * H + 2.0 * T * H * (H // cfg.num_conv_pos_embedding_groups) * cfg.num_conv_pos_embeddings
         rest += N * T * (8.0 * H * H + 4.0 * H * F) + N * 4.0 * T * T * H + 2.0 * T * H * 55
-    return conv + 3.0 * rest
+    return conv + mult * rest
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", type=int, default=4, choices=[2, 4])
+    ap.add_argument("--config", type=int, default=4, choices=[2, 3, 4])
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=0)
@@ -76,7 +78,7 @@ def main():
     hd = 0.1 if args.regularised else 0.0
     H = cfg.hidden_size
     name = register_in_memory_checkpoint("mem://train-bench", backbone_state_dict(cfg, 0))
-    B = args.batch or (32 if args.config == 4 else 16)
+    B = args.batch or {4: 32, 2: 16, 3: 64}[args.config]
     L = 128000
     rng = np.random.Generator(np.random.PCG64(21 + rank))
     g = torch.Generator().manual_seed(1234 + rank)
@@ -89,6 +91,9 @@ def main():
             model.phn_head[2].weight.copy_(pw); model.phn_head[2].bias.copy_(pb)
         lens = rng.integers(64000, 128001, size=B)
         lens[0] = L
+    elif args.config == 3:
+        model = Force_APTAI("unused", dev, VOCAB, w2v2_pr=Wav2Vec2_PR(cfg, None, name, VOCAB))
+        lens = np.full((B,), L)
     else:
         model = Wav2Vec2_PR(cfg, None, name, VOCAB)
         if not args.unfrozen:
@@ -100,7 +105,14 @@ def main():
         wav[b, int(lens[b]):] = 0
     flen = [cfg.conv_out_length(int(n)) for n in lens]
     T = cfg.conv_out_length(L)
-    if args.config == 4:
+    kwargs = {}
+    if args.config == 3:
+        tvt = torch.from_numpy(rng.standard_normal((B, T, 9), dtype=np.float32)).to(dev)
+        seqs, sl = phoneme_sequences(B, 10, 59, 1, 45, seed=11 + rank, pad=0)
+        kwargs["phn_seqs"] = [seqs[b, : int(sl[b])].numpy().astype(np.int64) for b in range(B)]
+        batch = (0, wav.to(dev), torch.as_tensor(lens).to(dev), None, None,
+                 *[tvt[:, :, i].contiguous() for i in range(9)])
+    elif args.config == 4:
         phn = np.zeros((B, T), dtype=np.int64)
         tvt = np.full((B, T, 9), -100.0, dtype=np.float32)
         for b in range(B):
@@ -122,7 +134,7 @@ def main():
         e = [ev() for _ in range(4)]
         e[0].record()
         opt.zero_grad()
-        out = model(*batch)
+        out = model(*batch, **kwargs)
         e[1].record()
         out["loss"].backward()
         e[2].record()
@@ -156,9 +168,10 @@ def main():
         bwd = np.mean([e[1].elapsed_time(e[2]) for e in times])
         optm = np.mean([e[2].elapsed_time(e[3]) for e in times])
         audio_s = float(sum(lens)) / 16000.0
-        fl = flops_train(cfg, [int(n) for n in lens])
+        fl = flops_train(cfg, [int(n) for n in lens], 1.0 if args.config == 3 else 3.0)   # config 3: frozen backbone
         print(json.dumps({
-            "workload": f"config{args.config}: {'APTAI training step' if args.config == 4 else 'Wav2Vec2_PR CTC fwd+bwd+Adam'}"
+            "workload": f"config{args.config}: " + {4: "APTAI training step", 2: "Wav2Vec2_PR CTC fwd+bwd+Adam",
+                                                    3: "Force_APTAI training step (frozen recogniser, trained tail)"}[args.config] +
                         f", {args.model} backbone, batch {B}/GPU, max 8 s, "
                         f"{'conv encoder trained' if args.unfrozen and args.config == 2 else 'frozen conv encoder'}, fused Adam"
                         + (", dropout 0.1 (hidden/attention/heads) + LayerDrop 0.1 + SpecAugment 0.075" if args.regularised else "")
