@@ -23,12 +23,16 @@ constexpr int LS_U = LS_H / LS_CL; // hidden units per CTA
 constexpr int LS_R = 4 * LS_U;     // gate rows per CTA
 constexpr int LS_BC = 8;           // utterances per cluster
 constexpr int LS_THREADS = 256;
-constexpr int LS_SMEM = (LS_H * LS_R + 2 * LS_H * LS_BC + LS_R * LS_BC) * 4;   // W^T | h double buffer | gates
+constexpr int LS_SMEM = (LS_H * LS_R + 2 * LS_H * LS_BC + LS_R * LS_BC + LS_U * LS_BC) * 4;   // W^T | h x2 | gates | stage
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, float4 v) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
 }
 
 __global__ void __cluster_dims__(LS_CL, 1, 1) __launch_bounds__(LS_THREADS, 1)
@@ -39,6 +43,7 @@ bilstm_kernel(const float* __restrict__ gates_in, const float* __restrict__ w_hh
   float* Wt = lsm;                          // [k][r]   r = gate*32 + unit
   float* hbuf = Wt + LS_H * LS_R;           // [2][k][b]
   float* gsm = hbuf + 2 * LS_H * LS_BC;     // [r][b]
+  float* stage = gsm + LS_R * LS_BC;        // [unit][b]: this CTA's slice of h_t before it is pushed to the cluster
   const int tid = threadIdx.x;
   const uint32_t rank = cluster_ctarank();
   const int cid = blockIdx.x / LS_CL;       // cluster index = dir * n_chunks + chunk
@@ -67,9 +72,7 @@ bilstm_kernel(const float* __restrict__ gates_in, const float* __restrict__ w_hh
   const int gb = b0 + b_pw;
   const int my_len = gb < B ? min(max(__ldg(lens + gb), 0), T) : 0;
   float c_state = 0.f;
-  uint32_t remote_h[LS_CL];
-#pragma unroll
-  for (int c = 0; c < LS_CL; ++c) remote_h[c] = map_to_cta(hbuf, c);
+  const uint32_t remote_h = map_to_cta(hbuf, tid >> 5);     // publishing role: warp w pushes to CTA w of the cluster
 
   auto load_gin = [&](int s, float (&g)[4]) {
     if (s < my_len) {
@@ -114,12 +117,20 @@ bilstm_kernel(const float* __restrict__ gates_in, const float* __restrict__ w_hh
         sg[0] = gi; sg[LS_H] = gf; sg[2 * LS_H] = gg; sg[3 * LS_H] = go;
         save_c[fr * LS_H + rank * LS_U + u_pw] = c_state;
       }
-      // publish h_t[unit][b] to every CTA of the cluster (next step's buffer)
-      const uint32_t off = static_cast<uint32_t>((((s + 1) & 1) * LS_H * LS_BC + (rank * LS_U + u_pw) * LS_BC + b_pw) * 4);
-#pragma unroll
-      for (int c = 0; c < LS_CL; ++c) st_cluster_f32(remote_h[c] + off, h_new);
     } else if (gb < B && s < T) {
       out[(static_cast<long long>(gb) * T + s) * (2 * LS_H) + dir * LS_H + rank * LS_U + u_pw] = 0.f;   // padding frame
+    }
+    // publish this CTA's slice of h_t (32 units x 8 utterances = 1 KB, contiguous in every replica) to all CTAs of the
+    // cluster as 16-byte st.shared::cluster (two per thread) instead of eight scalar remote stores per thread:
+    // the scalar version spent most of the step in the SM-to-SM network
+    stage[u_pw * LS_BC + b_pw] = h_new;            // finished utterances publish 0, nobody reads it
+    __syncthreads();
+    {
+      const int i = (tid & 31) * 2;
+      const uint32_t dst = remote_h +
+                           static_cast<uint32_t>((((s + 1) & 1) * LS_H * LS_BC + rank * LS_U * LS_BC) * 4) + i * 16;
+      st_cluster_v4(dst, *reinterpret_cast<const float4*>(stage + i * 4));
+      st_cluster_v4(dst + 16, *reinterpret_cast<const float4*>(stage + i * 4 + 4));
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) gin[q] = gnext[q];
@@ -225,8 +236,8 @@ bilstm_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ gat
         a[4] = fmaf(w, g1.x, a[4]); a[5] = fmaf(w, g1.y, a[5]); a[6] = fmaf(w, g1.z, a[6]); a[7] = fmaf(w, g1.w, a[7]);
       }
       const uint32_t dst = dst_part + static_cast<uint32_t>((((j + 1) & 1) * (LS_CL * LS_U * LS_BC)) * 4);
-#pragma unroll
-      for (int b = 0; b < LS_BC; ++b) st_cluster_f32(dst + b * 4, a[b]);
+      st_cluster_v4(dst, make_float4(a[0], a[1], a[2], a[3]));
+      st_cluster_v4(dst + 16, make_float4(a[4], a[5], a[6], a[7]));
     }
     cluster_sync_all();              // partials visible at their owners; gsm reusable
   }
