@@ -5,8 +5,11 @@
 // (gates_in [B][T][2][4*H]).  This kernel runs the T sequential steps: one cluster of 8 CTAs per (direction, chunk of
 // 8 utterances); CTA c owns hidden units [32c, 32c+32): its 4 x 32 rows of W_hh (128 x 256 fp32 = 128 KB) stay in
 // shared memory for the whole sequence, h_{t-1} of the chunk (256 x 8 fp32) is replicated in every CTA and refreshed
-// each step by st.shared::cluster writes from the owners, one barrier.cluster per step.  fp32 FMA throughout (the
-// recurrence is latency-bound: T steps of a 256-deep dot product; tensor cores would not shorten the chain).
+// each step by 16-byte st.async pushes from the owners that complete_tx on the receiver's mbarrier: the data carries
+// the synchronisation, there is no barrier.cluster (and no MEMBAR.ALL.GPU) inside the loop.  fp32 FMA throughout (the
+// recurrence is latency-bound: T steps of a 256-deep dot product; tensor cores would not shorten the chain); the
+// matvec is blocked 4 rows x 8 utterances per thread because the shared-memory return path (128 B/clk), not the FMA
+// pipe, bounds it (profiles/r01_bilstm_fwd.md).
 //
 // Packed-sequence semantics (pack_padded_sequence / pad_packed_sequence): utterance b runs len[b] steps, the reverse
 // direction starts at its last valid frame, outputs beyond len[b] are zero.
@@ -23,17 +26,22 @@ constexpr int LS_U = LS_H / LS_CL; // hidden units per CTA
 constexpr int LS_R = 4 * LS_U;     // gate rows per CTA
 constexpr int LS_BC = 8;           // utterances per cluster
 constexpr int LS_THREADS = 256;
-constexpr int LS_SMEM = (LS_H * LS_R + 2 * LS_H * LS_BC + LS_R * LS_BC + LS_U * LS_BC) * 4;   // W^T | h x2 | gates | stage
+constexpr int LS_PART = 8 * LS_R * LS_BC;      // per-warp partial gate sums of the k-split matvec (32 KB)
+constexpr int LS_SMEM = (LS_H * LS_R + 2 * LS_H * LS_BC + LS_R * LS_BC + LS_U * LS_BC + LS_PART) * 4;   // W^T | h x2 | gates | stage | partials
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 __device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, float4 v) {
-  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
-               : "memory");
+// 16-byte store into a peer CTA's shared memory that signals the peer's mbarrier (complete_tx of 16 bytes): the data
+// itself carries the synchronisation, so the step needs neither barrier.cluster nor a release fence (a cluster-scope
+// release compiles to MEMBAR.ALL.GPU, which also waits for the step's global stores: ~5 us of a 10 us step)
+__device__ __forceinline__ void st_async_v4(uint32_t addr, float4 v, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.f32 [%0], {%1, %2, %3, %4}, [%5];"
+               ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"(mbar) : "memory");
 }
+constexpr uint32_t LS_STEP_BYTES = LS_CL * LS_U * LS_BC * 4;   // what one CTA receives per step: 1 KB from each of 8
 
 __global__ void __cluster_dims__(LS_CL, 1, 1) __launch_bounds__(LS_THREADS, 1)
 bilstm_kernel(const float* __restrict__ gates_in, const float* __restrict__ w_hh_f, const float* __restrict__ w_hh_r,
@@ -44,6 +52,8 @@ bilstm_kernel(const float* __restrict__ gates_in, const float* __restrict__ w_hh
   float* hbuf = Wt + LS_H * LS_R;           // [2][k][b]
   float* gsm = hbuf + 2 * LS_H * LS_BC;     // [r][b]
   float* stage = gsm + LS_R * LS_BC;        // [unit][b]: this CTA's slice of h_t before it is pushed to the cluster
+  float4* psm = reinterpret_cast<float4*>(stage + LS_U * LS_BC);   // [warp][(row%4, b/4)][lane]: k-split partial sums
+  __shared__ __align__(8) uint64_t hbar[2]; // hbar[p]: "all 8 slices of the h vector in hbuf[p] have landed"
   const int tid = threadIdx.x;
   const uint32_t rank = cluster_ctarank();
   const int cid = blockIdx.x / LS_CL;       // cluster index = dir * n_chunks + chunk
@@ -59,6 +69,13 @@ bilstm_kernel(const float* __restrict__ gates_in, const float* __restrict__ w_hh
     Wt[k * LS_R + r] = __ldg(whh + static_cast<long long>(gate * LS_H + rank * LS_U + u) * LS_H + k);
   }
   for (int i = tid; i < 2 * LS_H * LS_BC; i += LS_THREADS) hbuf[i] = 0.f;
+  if (tid == 0) {
+    mbar_init(&hbar[0], 1);
+    mbar_init(&hbar[1], 1);
+    fence_mbar_init();
+    mbar_expect_tx(&hbar[0], LS_STEP_BYTES);      // first phases: h_1 lands in buffer 1, h_2 in buffer 0
+    mbar_expect_tx(&hbar[1], LS_STEP_BYTES);
+  }
   __syncthreads();
   cluster_sync_all();
 
@@ -66,13 +83,14 @@ bilstm_kernel(const float* __restrict__ gates_in, const float* __restrict__ w_hh
   for (int b = 0; b < LS_BC; ++b)
     if (b0 + b < B) steps = max(steps, min(max(__ldg(lens + b0 + b), 0), T));
 
-  // matvec role: gate row r_mv for 4 utterances; pointwise role: (unit u_pw, utterance b_pw)
-  const int r_mv = tid & (LS_R - 1), bh = tid >> 7;
+  // pointwise role: (unit u_pw, utterance b_pw)
+  const int lane = tid & 31, warp = tid >> 5;
   const int u_pw = tid & (LS_U - 1), b_pw = tid >> 5;
   const int gb = b0 + b_pw;
   const int my_len = gb < B ? min(max(__ldg(lens + gb), 0), T) : 0;
   float c_state = 0.f;
   const uint32_t remote_h = map_to_cta(hbuf, tid >> 5);     // publishing role: warp w pushes to CTA w of the cluster
+  const uint32_t remote_bar = map_to_cta(hbar, tid >> 5);
 
   auto load_gin = [&](int s, float (&g)[4]) {
     if (s < my_len) {
@@ -87,15 +105,54 @@ bilstm_kernel(const float* __restrict__ gates_in, const float* __restrict__ w_hh
 
   for (int s = 0; s < steps; ++s) {
     const float* hp = hbuf + (s & 1) * LS_H * LS_BC;
-    // recurrent matvec: acc[j] = sum_k W[r][k] * h[k][bh*4 + j]
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 8
-    for (int k = 0; k < LS_H; ++k) {
-      const float w = Wt[k * LS_R + r_mv];
-      const float4 h4 = *reinterpret_cast<const float4*>(hp + k * LS_BC + bh * 4);
-      a0 = fmaf(w, h4.x, a0); a1 = fmaf(w, h4.y, a1); a2 = fmaf(w, h4.z, a2); a3 = fmaf(w, h4.w, a3);
+    if (s > 0) {
+      // h_s complete in buffer s&1 (use number (s-1)/2 or s/2-1 of that barrier); re-arm it for its next use
+      mbar_wait(&hbar[s & 1], (s & 1) ? ((s - 1) >> 1) & 1 : ((s >> 1) - 1) & 1);
+      __syncthreads();               // everybody is past the wait before the barrier is re-armed into its next phase
+      if (tid == 0) mbar_expect_tx(&hbar[s & 1], LS_STEP_BYTES);
     }
-    *reinterpret_cast<float4*>(gsm + r_mv * LS_BC + bh * 4) = make_float4(a0, a1, a2, a3);
+    // recurrent matvec, k split across the 8 warps: warp w owns k in [32w, 32w+32), lane l the four gate rows
+    // 4l..4l+3 (one LDS.128 of W^T) for all 8 utterances (two broadcast LDS.128 of h): 48 bytes returned from shared
+    // memory per 32 FMAs.  (One row x 4 utterances per thread over all k returned 20 bytes per 4 FMAs, and the
+    // 128 B/clk shared-memory return path, not the FMA pipe, set the step time: profiles/r01_bilstm_fwd.md.)
+    {
+      float acc[4][LS_BC];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int b = 0; b < LS_BC; ++b) acc[i][b] = 0.f;
+      const float* wp = Wt + (warp * 32) * LS_R + lane * 4;
+      const float* hq = hp + (warp * 32) * LS_BC;
+#pragma unroll 4
+      for (int kk = 0; kk < 32; ++kk) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wp + kk * LS_R);
+        const float4 h0 = *reinterpret_cast<const float4*>(hq + kk * LS_BC);
+        const float4 h1 = *reinterpret_cast<const float4*>(hq + kk * LS_BC + 4);
+        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+        const float hv[LS_BC] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int b = 0; b < LS_BC; ++b) acc[i][b] = fmaf(wv[i], hv[b], acc[i][b]);
+      }
+      float4* pw = psm + warp * 256;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        pw[(i * 2 + 0) * 32 + lane] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        pw[(i * 2 + 1) * 32 + lane] = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+      }
+    }
+    __syncthreads();
+    {   // reduce the 8 partials of slot tid = (row%4, b/4, lane) and put the sum where the pointwise role reads it
+      float4 sum = psm[tid];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) {
+        const float4 v = psm[w * 256 + tid];
+        sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+      }
+      const int l = tid & 31, iq = tid >> 5;
+      *reinterpret_cast<float4*>(gsm + (4 * l + (iq >> 1)) * LS_BC + 4 * (iq & 1)) = sum;
+    }
     float gnext[4] = {0.f, 0.f, 0.f, 0.f};
     load_gin(s + 1, gnext);          // prefetch the next step's input projection under the barrier
     __syncthreads();
@@ -121,20 +178,21 @@ bilstm_kernel(const float* __restrict__ gates_in, const float* __restrict__ w_hh
       out[(static_cast<long long>(gb) * T + s) * (2 * LS_H) + dir * LS_H + rank * LS_U + u_pw] = 0.f;   // padding frame
     }
     // publish this CTA's slice of h_t (32 units x 8 utterances = 1 KB, contiguous in every replica) to all CTAs of the
-    // cluster as 16-byte st.shared::cluster (two per thread) instead of eight scalar remote stores per thread:
-    // the scalar version spent most of the step in the SM-to-SM network
+    // cluster: two 16-byte st.async per thread (warp w serves CTA w), each completing 16 bytes on the receiver's barrier
     stage[u_pw * LS_BC + b_pw] = h_new;            // finished utterances publish 0, nobody reads it
     __syncthreads();
-    {
+    if (s + 1 < steps) {
       const int i = (tid & 31) * 2;
       const uint32_t dst = remote_h +
                            static_cast<uint32_t>((((s + 1) & 1) * LS_H * LS_BC + rank * LS_U * LS_BC) * 4) + i * 16;
-      st_cluster_v4(dst, *reinterpret_cast<const float4*>(stage + i * 4));
-      st_cluster_v4(dst + 16, *reinterpret_cast<const float4*>(stage + i * 4 + 4));
+      const uint32_t bar = remote_bar + ((s + 1) & 1) * 8;
+      st_async_v4(dst, *reinterpret_cast<const float4*>(stage + i * 4), bar);
+      st_async_v4(dst + 16, *reinterpret_cast<const float4*>(stage + i * 4 + 4), bar);
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) gin[q] = gnext[q];
-    cluster_sync_all();              // h_t visible everywhere; gsm reusable
+    // no cluster barrier: a peer can only overwrite hbuf[s&1] (with h_{s+2}) after it has received this CTA's
+    // h_{s+1}, which is sent after this step's matvec has read hbuf[s&1]
   }
   // frames beyond the chunk's longest utterance
   if (gb < B)
@@ -148,11 +206,12 @@ bilstm_kernel(const float* __restrict__ gates_in, const float* __restrict__ w_hh
 // owns hidden units [32c, 32c+32) and keeps its 128 rows of W_hh in shared memory.  Step s (descending):
 //   pointwise (unit, utterance):  dh = d_out[t] + dh_rec;  gate gradients from the saved activations and cell states
 //   matvec:   partial[k][b] = sum over the CTA's 128 gate rows of dgate[r][b] * W_hh[r][k]   for ALL 256 units k
-//   exchange: the partial of unit k goes to the CTA that owns k (st.shared::cluster), which sums the 8 partials at the
-//             start of the next step -> dh_rec.  One barrier.cluster per step, partial buffers double-buffered.
+//   exchange: the partial of unit k goes to the CTA that owns k (16-byte st.async completing on the owner's mbarrier),
+//             which sums the 8 partials at the start of the next step -> dh_rec.  Partial buffers double-buffered; no
+//             barrier.cluster inside the loop.
 // Output: the pre-activation gate gradients dG [2][B][T][1024] (zero on padding frames; the caller pre-zeroes it),
 // from which dW_ih, dW_hh, the biases and dx are tensor-core GEMMs.
-constexpr int LB_SMEM = (LS_R * LS_H + LS_R * LS_BC + 2 * LS_CL * LS_U * LS_BC) * 4;   // W | dgates | partials
+constexpr int LB_SMEM = (LS_R * LS_H + LS_R * LS_BC + 2 * LS_CL * LS_U * LS_BC + 4 * LS_H * LS_BC) * 4;   // W | dgates | received partials | row-split partials
 
 __global__ void __cluster_dims__(LS_CL, 1, 1) __launch_bounds__(LS_THREADS, 1)
 bilstm_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ gates_act, const float* __restrict__ cells,
@@ -162,6 +221,8 @@ bilstm_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ gat
   float* W = lsm;                           // [r][k]   r = gate*32 + unit (rows of W_hh owned by this CTA)
   float* gsm = W + LS_R * LS_H;             // [r][b]   gate gradients of this step
   float* part = gsm + LS_R * LS_BC;         // [2][src CTA][unit][b]
+  float4* psm = reinterpret_cast<float4*>(part + 2 * LS_CL * LS_U * LS_BC);   // [row group][k half][(k%4, b/4)][lane]
+  __shared__ __align__(8) uint64_t pbar[2]; // pbar[p]: "all 8 partials in part[p] have landed"
   const int tid = threadIdx.x;
   const uint32_t rank = cluster_ctarank();
   const int cid = blockIdx.x / LS_CL;
@@ -175,6 +236,13 @@ bilstm_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ gat
     W[i] = __ldg(whh + static_cast<long long>(gate * LS_H + rank * LS_U + u) * LS_H + k);
   }
   for (int i = tid; i < 2 * LS_CL * LS_U * LS_BC; i += LS_THREADS) part[i] = 0.f;
+  if (tid == 0) {
+    mbar_init(&pbar[0], 1);
+    mbar_init(&pbar[1], 1);
+    fence_mbar_init();
+    mbar_expect_tx(&pbar[0], LS_STEP_BYTES);
+    mbar_expect_tx(&pbar[1], LS_STEP_BYTES);
+  }
   __syncthreads();
   cluster_sync_all();
 
@@ -185,13 +253,16 @@ bilstm_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ gat
   const int gb = b0 + b_pw;
   const int my_len = gb < B ? min(max(__ldg(lens + gb), 0), T) : 0;
   const int unit = rank * LS_U + u_pw;
-  // exchange role: thread tid = unit k of the whole layer; its partial goes to CTA k / 32, slot [rank][k % 32][*]
-  const uint32_t dst_part = map_to_cta(part, tid / LS_U) +
-                            static_cast<uint32_t>(((rank * LS_U + (tid & (LS_U - 1))) * LS_BC) * 4);
+  const int lane = tid & 31, warp = tid >> 5;
   float dc_state = 0.f;
 
   for (int j = 0, s = steps - 1; s >= 0; --s, ++j) {
     const float* pin = part + (j & 1) * (LS_CL * LS_U * LS_BC);
+    if (j > 0) {
+      mbar_wait(&pbar[j & 1], (j & 1) ? ((j - 1) >> 1) & 1 : ((j >> 1) - 1) & 1);
+      __syncthreads();               // also: the previous matvec is done with gsm
+      if (tid == 0) mbar_expect_tx(&pbar[j & 1], LS_STEP_BYTES);
+    }
     float di = 0.f, df = 0.f, dg = 0.f, dgo = 0.f;
     if (s < my_len) {
       const int t = dir ? (my_len - 1 - s) : s;
@@ -223,23 +294,54 @@ bilstm_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ gat
     gsm[(3 * LS_U + u_pw) * LS_BC + b_pw] = dgo;
     __syncthreads();
     if (s > 0) {
-      // partial dh_rec of unit k = tid over this CTA's 128 gate rows, for the 8 utterances
-      float a[LS_BC];
+      // partial dh_rec over this CTA's 128 gate rows, split like the forward's matvec: warp w owns the 32 rows of
+      // group w/2 and the 128 units of half w%2, lane l the units 4l..4l+3 (one LDS.128 of W) for all 8 utterances
+      float acc[4][LS_BC];
 #pragma unroll
-      for (int b = 0; b < LS_BC; ++b) a[b] = 0.f;
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int b = 0; b < LS_BC; ++b) acc[i][b] = 0.f;
+      const int kb = warp & 1, rg = warp >> 1;
+      const float* wp = W + (rg * 32) * LS_H + kb * 128 + lane * 4;
+      const float* gp = gsm + (rg * 32) * LS_BC;
 #pragma unroll 4
-      for (int r = 0; r < LS_R; ++r) {
-        const float w = W[r * LS_H + tid];
-        const float4 g0 = *reinterpret_cast<const float4*>(gsm + r * LS_BC);
-        const float4 g1 = *reinterpret_cast<const float4*>(gsm + r * LS_BC + 4);
-        a[0] = fmaf(w, g0.x, a[0]); a[1] = fmaf(w, g0.y, a[1]); a[2] = fmaf(w, g0.z, a[2]); a[3] = fmaf(w, g0.w, a[3]);
-        a[4] = fmaf(w, g1.x, a[4]); a[5] = fmaf(w, g1.y, a[5]); a[6] = fmaf(w, g1.z, a[6]); a[7] = fmaf(w, g1.w, a[7]);
+      for (int rr = 0; rr < 32; ++rr) {
+        const float4 w4 = *reinterpret_cast<const float4*>(wp + rr * LS_H);
+        const float4 g0 = *reinterpret_cast<const float4*>(gp + rr * LS_BC);
+        const float4 g1 = *reinterpret_cast<const float4*>(gp + rr * LS_BC + 4);
+        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+        const float gv[LS_BC] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int b = 0; b < LS_BC; ++b) acc[i][b] = fmaf(wv[i], gv[b], acc[i][b]);
       }
-      const uint32_t dst = dst_part + static_cast<uint32_t>((((j + 1) & 1) * (LS_CL * LS_U * LS_BC)) * 4);
-      st_cluster_v4(dst, make_float4(a[0], a[1], a[2], a[3]));
-      st_cluster_v4(dst + 16, make_float4(a[4], a[5], a[6], a[7]));
+      float4* pw = psm + rg * 512 + kb * 256;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        pw[(i * 2 + 0) * 32 + lane] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        pw[(i * 2 + 1) * 32 + lane] = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+      }
+      __syncthreads();
+      // sum the 4 row groups of slots tid and tid + 256 and send each 16-byte result to the CTA that owns its unit
+#pragma unroll
+      for (int hslot = 0; hslot < 2; ++hslot) {
+        const int slot = tid + 256 * hslot;
+        float4 sum = psm[slot];
+#pragma unroll
+        for (int g = 1; g < 4; ++g) {
+          const float4 v = psm[g * 512 + slot];
+          sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+        }
+        const int iq = (slot >> 5) & 7;
+        const int k = (slot >> 8) * 128 + 4 * (slot & 31) + (iq >> 1);
+        const uint32_t owner = static_cast<uint32_t>(k / LS_U);
+        const uint32_t dst = map_to_cta(part, owner) +
+                             static_cast<uint32_t>((((j + 1) & 1) * (LS_CL * LS_U * LS_BC) +
+                                                    (rank * LS_U + (k & (LS_U - 1))) * LS_BC + 4 * (iq & 1)) * 4);
+        st_async_v4(dst, sum, map_to_cta(pbar, owner) + ((j + 1) & 1) * 8);
+      }
     }
-    cluster_sync_all();              // partials visible at their owners; gsm reusable
   }
   cluster_sync_all();
 }
