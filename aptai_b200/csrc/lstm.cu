@@ -105,6 +105,8 @@ bilstm_kernel(const float* __restrict__ gates_in, const float* __restrict__ w_hh
 
   for (int s = 0; s < steps; ++s) {
     const float* hp = hbuf + (s & 1) * LS_H * LS_BC;
+    float gnext[4] = {0.f, 0.f, 0.f, 0.f};
+    load_gin(s + 1, gnext);          // the next step's input projection (DRAM latency hidden behind this whole step)
     if (s > 0) {
       // h_s complete in buffer s&1 (use number (s-1)/2 or s/2-1 of that barrier); re-arm it for its next use
       mbar_wait(&hbar[s & 1], (s & 1) ? ((s - 1) >> 1) & 1 : ((s >> 1) - 1) & 1);
@@ -153,8 +155,6 @@ bilstm_kernel(const float* __restrict__ gates_in, const float* __restrict__ w_hh
       const int l = tid & 31, iq = tid >> 5;
       *reinterpret_cast<float4*>(gsm + (4 * l + (iq >> 1)) * LS_BC + 4 * (iq & 1)) = sum;
     }
-    float gnext[4] = {0.f, 0.f, 0.f, 0.f};
-    load_gin(s + 1, gnext);          // prefetch the next step's input projection under the barrier
     __syncthreads();
     // pointwise: torch gate order i, f, g, o
     float h_new = 0.f;
@@ -255,9 +255,30 @@ bilstm_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ gat
   const int unit = rank * LS_U + u_pw;
   const int lane = tid & 31, warp = tid >> 5;
   float dc_state = 0.f;
+  // saved activations of one step for this (unit, utterance): d_out, i, f, g, o, c_t, c_{t-1}; fetched one step ahead
+  // so that their DRAM latency hides behind the previous step instead of heading every step
+  auto load_step = [&](int s, float (&v)[7]) {
+#pragma unroll
+    for (int q = 0; q < 7; ++q) v[q] = 0.f;
+    if (s >= 0 && s < my_len) {
+      const int t = dir ? (my_len - 1 - s) : s;
+      const long long fr = (static_cast<long long>(gb) * T + t) * 2 + dir;
+      v[0] = __ldg(d_out + (static_cast<long long>(gb) * T + t) * (2 * LS_H) + dir * LS_H + unit);
+      const float* ga = gates_act + fr * (4 * LS_H) + unit;
+      v[1] = __ldg(ga); v[2] = __ldg(ga + LS_H); v[3] = __ldg(ga + 2 * LS_H); v[4] = __ldg(ga + 3 * LS_H);
+      v[5] = __ldg(cells + fr * LS_H + unit);
+      if (s > 0) {
+        const int tp = dir ? t + 1 : t - 1;
+        v[6] = __ldg(cells + ((static_cast<long long>(gb) * T + tp) * 2 + dir) * LS_H + unit);
+      }
+    }
+  };
+  float cur[7], nxt[7];
+  load_step(steps - 1, cur);
 
   for (int j = 0, s = steps - 1; s >= 0; --s, ++j) {
     const float* pin = part + (j & 1) * (LS_CL * LS_U * LS_BC);
+    load_step(s - 1, nxt);
     if (j > 0) {
       mbar_wait(&pbar[j & 1], (j & 1) ? ((j - 1) >> 1) & 1 : ((j >> 1) - 1) & 1);
       __syncthreads();               // also: the previous matvec is done with gsm
@@ -266,18 +287,10 @@ bilstm_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ gat
     float di = 0.f, df = 0.f, dg = 0.f, dgo = 0.f;
     if (s < my_len) {
       const int t = dir ? (my_len - 1 - s) : s;
-      const long long fr = (static_cast<long long>(gb) * T + t) * 2 + dir;
-      float dh = __ldg(d_out + (static_cast<long long>(gb) * T + t) * (2 * LS_H) + dir * LS_H + unit);
+      float dh = cur[0];
 #pragma unroll
       for (int c = 0; c < LS_CL; ++c) dh += pin[(c * LS_U + u_pw) * LS_BC + b_pw];
-      const float* ga = gates_act + fr * (4 * LS_H) + unit;
-      const float gi = __ldg(ga), gf = __ldg(ga + LS_H), gg = __ldg(ga + 2 * LS_H), go = __ldg(ga + 3 * LS_H);
-      const float c_t = __ldg(cells + fr * LS_H + unit);
-      float c_prev = 0.f;
-      if (s > 0) {
-        const int tp = dir ? t + 1 : t - 1;
-        c_prev = __ldg(cells + ((static_cast<long long>(gb) * T + tp) * 2 + dir) * LS_H + unit);
-      }
+      const float gi = cur[1], gf = cur[2], gg = cur[3], go = cur[4], c_t = cur[5], c_prev = cur[6];
       const float tc = tanhf(c_t);
       const float dc = fmaf(dh * go, 1.0f - tc * tc, dc_state);
       dgo = dh * tc * go * (1.0f - go);
@@ -342,6 +355,8 @@ bilstm_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ gat
         st_async_v4(dst, sum, map_to_cta(pbar, owner) + ((j + 1) & 1) * 8);
       }
     }
+#pragma unroll
+    for (int q = 0; q < 7; ++q) cur[q] = nxt[q];
   }
   cluster_sync_all();
 }

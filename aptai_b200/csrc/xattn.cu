@@ -13,7 +13,7 @@ namespace aptai {
 
 constexpr int XA_D = 128;      // frame / phoneme / attention hidden dim
 constexpr int XA_N = 60;       // max phoneme sequence length
-constexpr int XA_F = 16;       // frames per CTA
+constexpr int XA_F = 16;       // frames per CTA when the grid would otherwise not fill the GPU; 64 for large batches
 constexpr int XA_THREADS = 128;
 
 struct XAttnArgs {
@@ -29,6 +29,8 @@ struct XAttnArgs {
   float* att;             // [B][T][60]  log_softmax(energy + mask)
   int B, T;
   float eps;
+  int frames;             // frames per CTA: the 60 key projections are recomputed per CTA (2/3 of a 16-frame CTA's FMAs),
+                          // so large batches amortise them over 64 frames
 };
 
 __global__ void __launch_bounds__(XA_THREADS)
@@ -43,7 +45,7 @@ xattn_kernel(const XAttnArgs a) {
   float* s_red = s_o + XA_D;                    // reductions [8]
   __shared__ float s_mask[XA_N];
   const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int t0 = blockIdx.x * XA_F;
+  const int t0 = blockIdx.x * a.frames;
   // ---- k = W_k (emb + pe) + b_k for the utterance's 60 slots
   for (int i = tid; i < XA_D * XA_D; i += XA_THREADS) s_w[(i / XA_D) * (XA_D + 1) + (i % XA_D)] = a.wk[i];
   if (tid < XA_N) s_mask[tid] = a.phn_ids[b * XA_N + tid] != 0 ? 0.f : -1000.f;
@@ -62,7 +64,7 @@ xattn_kernel(const XAttnArgs a) {
   for (int i = tid; i < XA_D * XA_D; i += XA_THREADS) s_w[(i / XA_D) * (XA_D + 1) + (i % XA_D)] = a.wq[i];
   __syncthreads();
   const float bq = a.bq[tid];
-  for (int f = 0; f < XA_F; ++f) {
+  for (int f = 0; f < a.frames; ++f) {
     const int t = t0 + f;
     if (t >= a.T) break;                        // uniform across the CTA
     const long long row = static_cast<long long>(b) * a.T + t;
@@ -158,7 +160,7 @@ xattn_bwd_kernel(const XAttnBwdArgs g) {
   float* s_pd = s_da + 64;                      // p * d_p [64]
   __shared__ float s_mask[XA_N];
   const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int t0 = blockIdx.x * XA_F;
+  const int t0 = blockIdx.x * a.frames;
   for (int i = tid; i < XA_D * XA_D; i += XA_THREADS) s_w[(i / XA_D) * (XA_D + 1) + (i % XA_D)] = a.wk[i];
   if (tid < XA_N) s_mask[tid] = a.phn_ids[b * XA_N + tid] != 0 ? 0.f : -1000.f;
   if (tid < 64) { s_de[tid] = 0.f; s_da[tid] = 0.f; s_pd[tid] = 0.f; }
@@ -182,7 +184,7 @@ xattn_bwd_kernel(const XAttnBwdArgs g) {
 #pragma unroll
   for (int n = 0; n < XA_N; ++n) dk[n] = 0.f;
   float dgw_o = 0.f, dgw_q = 0.f, dgb_o = 0.f, dgb_q = 0.f;
-  for (int f = 0; f < XA_F; ++f) {
+  for (int f = 0; f < a.frames; ++f) {
     const int t = t0 + f;
     if (t >= a.T) break;                        // uniform across the CTA
     const long long row = static_cast<long long>(b) * a.T + t;
@@ -270,6 +272,12 @@ xattn_bwd_kernel(const XAttnBwdArgs g) {
 
 using namespace aptai;
 
+static int xa_frames_per_cta(int B, int T) {
+  // 64 frames per CTA once that still gives every SM three CTAs, else 16 (single utterances, small batches)
+  const long long ctas64 = static_cast<long long>(B) * ((T + 63) / 64);
+  return ctas64 >= 3LL * num_sms() ? 64 : XA_F;
+}
+
 extern "C" int aptai_cross_attention(const float* frame, const int32_t* phn_ids, const float* phn_hidden,
                                      const float* emb, int vocab, const float* pe, const float* wq, const float* bq, const float* wk,
                                      const float* bk, const float* ln_w, const float* ln_b, float eps, int B, int T,
@@ -292,7 +300,8 @@ extern "C" int aptai_cross_attention(const float* frame, const int32_t* phn_ids,
     }
     attr_set = true;
   }
-  xattn_kernel<<<dim3((T + XA_F - 1) / XA_F, B), XA_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  a.frames = xa_frames_per_cta(B, T);
+  xattn_kernel<<<dim3((T + a.frames - 1) / a.frames, B), XA_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
   return after_launch("cross_attention");
 }
 
@@ -321,6 +330,7 @@ extern "C" int aptai_cross_attention_bwd(const float* frame, const int32_t* phn_
     }
     attr_set = true;
   }
-  xattn_bwd_kernel<<<dim3((T + XA_F - 1) / XA_F, B), XA_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(g);
+  a.frames = xa_frames_per_cta(B, T);
+  xattn_bwd_kernel<<<dim3((T + a.frames - 1) / a.frames, B), XA_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(g);
   return after_launch("cross_attention_bwd");
 }
