@@ -1,5 +1,5 @@
-"""Wall-clock / CUDA-event timings of BASELINE.json configs 1-3 at their full sizes on one B200 (inference halves;
-backward kernels are not built yet) with size-independent property checks.  Prints one JSON line per config."""
+"""Wall-clock / CUDA-event timings of BASELINE.json configs 1-3 at their full sizes on one B200 (inference halves; the
+training steps are timed by profiles/train_bench.py) with size-independent property checks.  Prints one JSON line per config."""
 import json
 import os
 import sys
@@ -71,7 +71,7 @@ g = r["grad_logits"]
 assert torch.isfinite(r["loss"]) and float(g.sum(-1).abs().max()) < 1e-4
 assert float(g[1, 374:].abs().max()) == 0.0                 # frames beyond the 7.5 s utterance: exactly zero
 ms = ev_time(lambda: pr(wav, lt, labels.to(dev), want_grad=True))
-print(json.dumps({"config": 2, "what": "Wav2Vec2_PR.forward B=16x8s 24x1024 (+CTC loss and d loss/d logits; no encoder backward yet)",
+print(json.dumps({"config": 2, "what": "Wav2Vec2_PR.forward B=16x8s 24x1024 (+CTC loss and d loss/d logits; full training step: train_bench.py)",
                   "ms": ms, "audio_s_per_s": sum(lens) / 16000 / (ms * 1e-3), "loss": float(r["loss"])}))
 
 # ---- config 3: Force_APTAI forced alignment, B=64 x 8 s, known phoneme sequences
