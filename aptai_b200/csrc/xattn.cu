@@ -33,20 +33,10 @@ struct XAttnArgs {
                           // so large batches amortise them over 64 frames
 };
 
-__global__ void __launch_bounds__(XA_THREADS)
-xattn_kernel(const XAttnArgs a) {
-  extern __shared__ float sm[];
-  float* s_w = sm;                              // W_q, later reused row-wise: [128][129]
-  float* s_k = s_w + XA_D * (XA_D + 1);         // k_phn [60][129]
-  float* s_x = s_k + XA_N * (XA_D + 1);         // staging: phoneme embedding row / frame row [128]
-  float* s_q = s_x + XA_D;                      // q [128]
-  float* s_p = s_q + XA_D;                      // energies / probabilities [64]
-  float* s_o = s_p + 64;                        // att_out [128]
-  float* s_red = s_o + XA_D;                    // reductions [8]
-  __shared__ float s_mask[XA_N];
-  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int t0 = blockIdx.x * a.frames;
-  // ---- k = W_k (emb + pe) + b_k for the utterance's 60 slots
+// CTA prologue shared by the forward and the backward: padding mask, k = W_k (emb + pe) + b_k for the utterance's 60
+// slots into s_k, then W_q into s_w (both as [128][129]).  Ends with a CTA barrier.
+__device__ __forceinline__ void xa_project_keys(const XAttnArgs& a, int b, int tid, float* s_w, float* s_k, float* s_x,
+                                                float* s_mask) {
   for (int i = tid; i < XA_D * XA_D; i += XA_THREADS) s_w[(i / XA_D) * (XA_D + 1) + (i % XA_D)] = a.wk[i];
   if (tid < XA_N) s_mask[tid] = a.phn_ids[b * XA_N + tid] != 0 ? 0.f : -1000.f;
   __syncthreads();
@@ -63,6 +53,23 @@ xattn_kernel(const XAttnArgs a) {
   }
   for (int i = tid; i < XA_D * XA_D; i += XA_THREADS) s_w[(i / XA_D) * (XA_D + 1) + (i % XA_D)] = a.wq[i];
   __syncthreads();
+}
+
+__global__ void __launch_bounds__(XA_THREADS)
+xattn_kernel(const XAttnArgs a) {
+  extern __shared__ float sm[];
+  float* s_w = sm;                              // W_q, later reused row-wise: [128][129]
+  float* s_k = s_w + XA_D * (XA_D + 1);         // k_phn [60][129]
+  float* s_x = s_k + XA_N * (XA_D + 1);         // staging: phoneme embedding row / frame row [128]
+  float* s_q = s_x + XA_D;                      // q [128]
+  float* s_p = s_q + XA_D;                      // energies / probabilities [64]
+  float* s_o = s_p + 64;                        // att_out [128]
+  float* s_red = s_o + XA_D;                    // reductions [8]
+  __shared__ float s_mask[XA_N];
+  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int t0 = blockIdx.x * a.frames;
+  // ---- k = W_k (emb + pe) + b_k for the utterance's 60 slots
+  xa_project_keys(a, b, tid, s_w, s_k, s_x, s_mask);
   const float bq = a.bq[tid];
   for (int f = 0; f < a.frames; ++f) {
     const int t = t0 + f;
@@ -161,23 +168,8 @@ xattn_bwd_kernel(const XAttnBwdArgs g) {
   __shared__ float s_mask[XA_N];
   const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t0 = blockIdx.x * a.frames;
-  for (int i = tid; i < XA_D * XA_D; i += XA_THREADS) s_w[(i / XA_D) * (XA_D + 1) + (i % XA_D)] = a.wk[i];
-  if (tid < XA_N) s_mask[tid] = a.phn_ids[b * XA_N + tid] != 0 ? 0.f : -1000.f;
   if (tid < 64) { s_de[tid] = 0.f; s_da[tid] = 0.f; s_pd[tid] = 0.f; }
-  __syncthreads();
-  for (int n = 0; n < XA_N; ++n) {
-    const int id = a.phn_ids[b * XA_N + n];
-    s_x[tid] = a.phn_hidden ? a.phn_hidden[(static_cast<long long>(b) * XA_N + n) * XA_D + tid]
-                            : a.emb[id * XA_D + tid] + a.pe[n * XA_D + tid];
-    __syncthreads();
-    float acc = a.bk[tid];
-#pragma unroll 8
-    for (int k = 0; k < XA_D; ++k) acc = fmaf(s_x[k], s_w[tid * (XA_D + 1) + k], acc);
-    s_k[n * (XA_D + 1) + tid] = acc;
-    __syncthreads();
-  }
-  for (int i = tid; i < XA_D * XA_D; i += XA_THREADS) s_w[(i / XA_D) * (XA_D + 1) + (i % XA_D)] = a.wq[i];
-  __syncthreads();
+  xa_project_keys(a, b, tid, s_w, s_k, s_x, s_mask);
   const float bq = a.bq[tid];
   const float lw_o = a.ln_w[tid], lw_q = a.ln_w[XA_D + tid];
   float dk[XA_N];

@@ -205,8 +205,8 @@ class Force_APTAI(nn.Module):
         bf = ops.scale_cast_bf16
 
         def run_backward(grad_out):
-            gs = float(grad_out)
-            d_tvs = (diff * (2.0 * a * gs / count)).contiguous()
+            gs = grad_out.detach().to(device=dev, dtype=torch.float32)       # upstream scalar, kept on the device
+            d_tvs = (diff * (gs * (2.0 * a) / count)).contiguous()
             d_raw = ops.lowpass(d_tvs, taps).view(M, 9)                     # symmetric FIR: adjoint = the filter
             d_z1 = ops.heads_bwd(z1, d_raw, w3, ops.ACT_TANH, G("rnn.linear.3.weight"), G("rnn.linear.3.bias"),
                                  None, None, 0, None, None)
@@ -219,7 +219,7 @@ class Force_APTAI(nn.Module):
                                      want_bf16=False)
             lg = {n: G("rnn.lstm." + n) for n, _ in rnn.lstm.named_parameters()}
             d_att_out = ops.bilstm_256_bwd(lsv, d_hidden.view(B, T, -1), lg)
-            d_att = (r["grad"] * ((1 - a) * gs)).contiguous()
+            d_att = (r["grad"] * (gs * (1 - a))).contiguous()
             d_q, d_k = ops.cross_attention_bwd(fh.view(B, T, -1), ids, phn, xa.q.weight, xa.q.bias, xa.k.weight,
                                                xa.k.bias, xa.layer_norm.weight, xa.layer_norm.eps,
                                                d_att_out.contiguous(), d_att, G("xatt.layer_norm.weight"),
