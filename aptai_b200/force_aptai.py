@@ -18,7 +18,7 @@ import torch.nn as nn
 from . import ops
 from .aptai import TV_NAMES
 from .modules import CrossAttention, ForwardSumLoss, LowPassFilterLayer, PositionalEncoding, RNN
-from .train import GradBuffer, attach_backward
+from .train import GradBuffer, attach_backward, broadcast_parameters
 from .w2v2_pr import Wav2Vec2_PR
 
 
@@ -137,6 +137,15 @@ class Force_APTAI(nn.Module):
             gb.zero()
         return gb
 
+    def enable_data_parallel(self, group=None, broadcast: bool = True):
+        """Data-parallel training of the tail over `torch.distributed` (one process per GPU; the reference trains on
+        one GPU): weights broadcast from rank 0, and every backward ends with one NCCL all-reduce (average) of the flat
+        5 MB gradient buffer — too small to be worth bucketing or overlapping."""
+        if broadcast:
+            broadcast_parameters(self, 0, group)
+        object.__setattr__(self, "_dp", (True, group))
+        return self.grad_buffer()
+
     def _drop_seed(self, site: int) -> int:
         # sites 100..102 of the backbone's counter-based generator (frame_drop, pe_phn.dropout, rnn dropout)
         return self.w2v2_pr.wav2vec2.drop_seed(self._drop_step, site, 0)
@@ -242,6 +251,9 @@ class Force_APTAI(nn.Module):
             d_emb = G("phn_emb_layer.weight")
             keep = (ids.view(-1) != 0)                                      # padding_idx = 0 receives no gradient
             d_emb.index_add_(0, ids.view(-1).long()[keep], d_phn[keep])
+            dp = getattr(self, "_dp", None)
+            if dp is not None:
+                gb.allreduce(group=dp[1], average=True)
 
         align_out = torch.max(att, axis=2)[1]
         frame_phn = torch.gather(ids.long(), 1, align_out).cpu().numpy()

@@ -67,7 +67,50 @@ assert err < 1e-4, f"rank {rank}: all-reduced gradient differs from the mean of 
 opt.step()
 dist.all_gather(gathered, probe.detach())
 assert all(torch.equal(g, gathered[0]) for g in gathered), "weights diverged after the data-parallel step"
+
+# ---- Force_APTAI: the tail's flat gradient buffer is averaged by one all-reduce at the end of the backward
+from aptai_b200 import Force_APTAI, Wav2Vec2_PR  # noqa: E402
+
+torch.manual_seed(100 + rank)                                                        # different tail init per rank
+fa = Force_APTAI("unused", dev, vocab, w2v2_pr=Wav2Vec2_PR(cfg, None, name, vocab)).to(dev).train()
+fa.frame_drop.p = fa.pe_phn.dropout.p = fa.rnn.linear[1].p = 0.0
+
+
+def fbatch(r):
+    rng = np.random.Generator(np.random.PCG64(70 + r))
+    lens = [32000, 24000]
+    wav = waveforms(2, 32000, lens, seed=950 + 10 * r)
+    tvt = torch.from_numpy(rng.standard_normal((2, 99, 9), dtype=np.float32)).to(dev)
+    seqs = [rng.integers(1, 46, size=int(n)).astype(np.int64) for n in rng.integers(8, 30, size=2)]
+    return (0, wav.to(dev), torch.tensor(lens, device=dev), None, None,
+            *[tvt[:, :, i].contiguous() for i in range(9)]), seqs
+
+
+fgb = fa.enable_data_parallel()
+fprobe = fa.rnn.lstm.weight_hh_l0
+fg = [torch.empty_like(fprobe) for _ in range(world)]
+dist.all_gather(fg, fprobe.detach())
+assert all(torch.equal(g, fg[0]) for g in fg), "Force_APTAI weights differ after the broadcast"
+dp = fa._dp
+object.__setattr__(fa, "_dp", None)
+fref = torch.zeros_like(fgb.flat)
+for r in range(world):
+    fgb.zero()
+    args, seqs = fbatch(r)
+    fa(*args, phn_seqs=seqs)["loss"].backward()
+    fref += fgb.flat / world
+object.__setattr__(fa, "_dp", dp)
+fopt = FusedAdam([p for p in fa.parameters() if p.requires_grad], lr=1e-4)
+fopt.zero_grad()
+args, seqs = fbatch(rank)
+fa(*args, phn_seqs=seqs)["loss"].backward()
+torch.cuda.synchronize()
+ferr = float((fgb.flat - fref).norm() / fref.norm())
+assert ferr < 1e-4, f"rank {rank}: Force_APTAI all-reduced gradient differs from the mean ({ferr:.2e})"
+fopt.step()
+dist.all_gather(fg, fprobe.detach())
+assert all(torch.equal(g, fg[0]) for g in fg), "Force_APTAI weights diverged after the data-parallel step"
 dist.barrier()
 if rank == 0:
-    print(f"NCCL_DP_OK world={world} grad_rel_err={err:.2e}")
+    print(f"NCCL_DP_OK world={world} grad_rel_err={err:.2e} force_grad_rel_err={ferr:.2e}")
 dist.destroy_process_group()
