@@ -356,3 +356,35 @@ def test_cross_attention_backward_vs_autograd(cuda, B, T):
     for name, got, ref in (("d_q", dq, q.grad), ("d_k", dk, k.grad), ("d_ln_w", dlw, lnw.grad), ("d_ln_b", dlb, lnb.grad)):
         rel = float((got.cpu().double() - ref.double()).norm() / ref.double().norm())
         assert rel < 1e-4, (name, rel)
+
+
+def test_bilstm_backward_full_size_linearity(cuda):
+    """BASELINE config-3 size (64 utterances x 399 frames, ragged): the CPU autograd oracle takes too long here, so
+    the check is the size-independent property of a backward pass — it is linear in the upstream gradient:
+    bwd(2 a - 3 b) == 2 bwd(a) - 3 bwd(b) for dx and every parameter gradient — plus exact zeros on padding frames."""
+    from aptai_b200 import ops
+    torch.manual_seed(8)
+    B, T = 64, 399
+    lstm = torch.nn.LSTM(256, 256, bidirectional=True, num_layers=1, batch_first=True).to(cuda)
+    g = torch.Generator().manual_seed(12)
+    lens = torch.randint(200, T + 1, (B,), generator=g).tolist()
+    lens[0], lens[1] = T, 1
+    ln = torch.tensor(lens, dtype=torch.int32, device=cuda)
+    x = torch.randn((B, T, 256), generator=g).to(cuda)
+    _, sv = ops.bilstm_256(x, lstm, ln, save=True)
+    a, b = torch.randn((B, T, 512), generator=g).to(cuda), torch.randn((B, T, 512), generator=g).to(cuda)
+
+    def run(dh):
+        grads = {n: torch.zeros_like(p) for n, p in lstm.named_parameters()}
+        return ops.bilstm_256_bwd(sv, dh.contiguous(), grads), grads
+
+    (dxa, ga), (dxb, gb_), (dxc, gc) = run(a), run(b), run(2 * a - 3 * b)
+    rel = lambda got, want: float((got - want).double().norm() / want.double().norm())
+    # bf16 operands in the gradient GEMMs: each pass rounds its gate gradients independently (2^-9 per element)
+    worst = rel(dxc, 2 * dxa - 3 * dxb)
+    for n in ga:
+        worst = max(worst, rel(gc[n], 2 * ga[n] - 3 * gb_[n]))
+    print(f"BiLSTM backward 64x399 linearity: worst relative L2 deviation {worst:.2e}")
+    assert worst < 1e-2
+    for bi in (1, 5, 33):
+        assert float(dxc[bi, lens[bi]:].abs().max()) == 0.0
