@@ -118,11 +118,12 @@ bilstm_kernel(const float* __restrict__ gates_in, const float* __restrict__ w_hh
     // memory per 32 FMAs.  (One row x 4 utterances per thread over all k returned 20 bytes per 4 FMAs, and the
     // 128 B/clk shared-memory return path, not the FMA pipe, set the step time: profiles/r01_bilstm_fwd.md.)
     {
-      float acc[4][LS_BC];
+      // packed fp32x2 FMAs (FFMA2): utterance pairs share one instruction, the issue slots of the 4x8 tile halve
+      uint64_t acc2[4][LS_BC / 2];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int b = 0; b < LS_BC; ++b) acc[i][b] = 0.f;
+        for (int b = 0; b < LS_BC / 2; ++b) acc2[i][b] = 0ull;
       const float* wp = Wt + (warp * 32) * LS_R + lane * 4;
       const float* hq = hp + (warp * 32) * LS_BC;
 #pragma unroll 4
@@ -130,13 +131,20 @@ bilstm_kernel(const float* __restrict__ gates_in, const float* __restrict__ w_hh
         const float4 w4 = *reinterpret_cast<const float4*>(wp + kk * LS_R);
         const float4 h0 = *reinterpret_cast<const float4*>(hq + kk * LS_BC);
         const float4 h1 = *reinterpret_cast<const float4*>(hq + kk * LS_BC + 4);
-        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
-        const float hv[LS_BC] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        const uint64_t wv[4] = {f32x2_pack(w4.x, w4.x), f32x2_pack(w4.y, w4.y), f32x2_pack(w4.z, w4.z),
+                                f32x2_pack(w4.w, w4.w)};
+        const uint64_t hv[LS_BC / 2] = {f32x2_pack(h0.x, h0.y), f32x2_pack(h0.z, h0.w), f32x2_pack(h1.x, h1.y),
+                                        f32x2_pack(h1.z, h1.w)};
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int b = 0; b < LS_BC; ++b) acc[i][b] = fmaf(wv[i], hv[b], acc[i][b]);
+          for (int b = 0; b < LS_BC / 2; ++b) acc2[i][b] = f32x2_fma(wv[i], hv[b], acc2[i][b]);
       }
+      float acc[4][LS_BC];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int b = 0; b < LS_BC / 2; ++b) f32x2_unpack(acc2[i][b], acc[i][2 * b], acc[i][2 * b + 1]);
       float4* pw = psm + warp * 256;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -309,11 +317,11 @@ bilstm_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ gat
     if (s > 0) {
       // partial dh_rec over this CTA's 128 gate rows, split like the forward's matvec: warp w owns the 32 rows of
       // group w/2 and the 128 units of half w%2, lane l the units 4l..4l+3 (one LDS.128 of W) for all 8 utterances
-      float acc[4][LS_BC];
+      uint64_t acc2[4][LS_BC / 2];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int b = 0; b < LS_BC; ++b) acc[i][b] = 0.f;
+        for (int b = 0; b < LS_BC / 2; ++b) acc2[i][b] = 0ull;
       const int kb = warp & 1, rg = warp >> 1;
       const float* wp = W + (rg * 32) * LS_H + kb * 128 + lane * 4;
       const float* gp = gsm + (rg * 32) * LS_BC;
@@ -322,13 +330,20 @@ bilstm_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ gat
         const float4 w4 = *reinterpret_cast<const float4*>(wp + rr * LS_H);
         const float4 g0 = *reinterpret_cast<const float4*>(gp + rr * LS_BC);
         const float4 g1 = *reinterpret_cast<const float4*>(gp + rr * LS_BC + 4);
-        const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
-        const float gv[LS_BC] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const uint64_t wv[4] = {f32x2_pack(w4.x, w4.x), f32x2_pack(w4.y, w4.y), f32x2_pack(w4.z, w4.z),
+                                f32x2_pack(w4.w, w4.w)};
+        const uint64_t gv[LS_BC / 2] = {f32x2_pack(g0.x, g0.y), f32x2_pack(g0.z, g0.w), f32x2_pack(g1.x, g1.y),
+                                        f32x2_pack(g1.z, g1.w)};
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int b = 0; b < LS_BC; ++b) acc[i][b] = fmaf(wv[i], gv[b], acc[i][b]);
+          for (int b = 0; b < LS_BC / 2; ++b) acc2[i][b] = f32x2_fma(wv[i], gv[b], acc2[i][b]);
       }
+      float acc[4][LS_BC];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int b = 0; b < LS_BC / 2; ++b) f32x2_unpack(acc2[i][b], acc[i][2 * b], acc[i][2 * b + 1]);
       float4* pw = psm + rg * 512 + kb * 256;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
