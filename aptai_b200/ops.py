@@ -623,8 +623,10 @@ def bilstm_256_bwd(sv, d_hidden: torch.Tensor, grads: dict) -> torch.Tensor:
     for d, sfx in enumerate(("", "_reverse")):
         wgrad(dGb[d], xb, grads["weight_ih_l0" + sfx])
         wgrad(dGb[d], hpb[d], grads["weight_hh_l0" + sfx])
-        colsum(dG[d], grads["bias_ih_l0" + sfx])
-        colsum(dG[d], grads["bias_hh_l0" + sfx])
+        db = torch.zeros((1024,), dtype=F32, device=dev)       # b_ih and b_hh enter the gates as a sum: same gradient
+        colsum(dG[d], db)
+        grads["bias_ih_l0" + sfx].add_(db)
+        grads["bias_hh_l0" + sfx].add_(db)
         wt = sv.w_ih[d * 1024:(d + 1) * 1024].t().contiguous().to(BF16)            # [256, 1024]
         dx, _ = linear(dGb[d], wt, None, residual=dx, want_f32=True, want_bf16=False)
     return dx.view(B, T, 256)
