@@ -114,3 +114,17 @@ def test_ctc_oracle_vs_torch():
     assert abs(o["loss"] - loss.item()) < 1e-9
     np.testing.assert_allclose(o["grad"], logits.grad.numpy(), atol=1e-12)
     assert o["nll"][3] == 0.0
+
+
+def test_force_tail_forward_sum_agrees_with_numpy_oracle_and_reference():
+    """oracle/force_tail.py's differentiable forward-sum loss (the checker of the Force_APTAI training tests) against
+    the NumPy restatement and against the reference's own ForwardSumLoss output stored in golden_v1 (G5)."""
+    import torch
+    from oracle.force_tail import forward_sum_loss
+    g = golden()
+    att = torch.from_numpy(np.asarray(g["g5_fs_in"], dtype=np.float32))
+    text, mel = [int(x) for x in g["g5_fs_text"]], [int(x) for x in g["g5_fs_mel"]]
+    loss_t = float(forward_sum_loss(att, text, mel, -1.0))
+    loss_n, _ = octc.forward_sum_loss(g["g5_fs_in"], g["g5_fs_text"], g["g5_fs_mel"], -1.0)
+    assert abs(loss_t - loss_n) < 1e-4 * abs(loss_n)
+    assert abs(loss_t - float(g["g5_fs_loss"][0])) < 1e-4 * abs(float(g["g5_fs_loss"][0]))
