@@ -108,3 +108,10 @@ print(json.dumps({"config": 3, "what": "Force_APTAI.forced_align B=64x8s (encode
 t3 = fa._trunk(wav3[:8], lt3[:8], seq_list[:8])
 print(json.dumps({"config": 3, "what": "Force_APTAI cross-attention alignment matrix B=8 (batch > 1 works; the reference raises NameError)",
                   "att_shape": list(t3["att"].shape)}))
+# the model's own forward at the same size: recogniser + cross-attention alignment matrix + BiLSTM + low-pass + losses
+tvt3 = torch.randn((B, 399, 9), generator=torch.Generator().manual_seed(5)).to(dev)
+tv_cols = [tvt3[:, :, i].contiguous() for i in range(9)]
+with torch.no_grad():
+    ms_f = ev_time(lambda: fa(0, wav3, lt3, None, None, *tv_cols, phn_seqs=seq_list))
+print(json.dumps({"config": 3, "what": "Force_APTAI.forward B=64x8s eval (recogniser + cross-attention + BiLSTM + low-pass + MSE / forward-sum losses + frame phonemes)",
+                  "ms": ms_f, "audio_s_per_s": sum(lens3) / 16000 / (ms_f * 1e-3)}))
