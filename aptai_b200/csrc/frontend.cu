@@ -141,18 +141,25 @@ conv0_kernel(const float* __restrict__ wav, long long L, int T0, const float* __
              const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
              const float* __restrict__ consts, const float* __restrict__ affine, float eps,
              __nv_bfloat16* __restrict__ out, int out_fp16) {
-  __shared__ float xs[FT * S0 + K0];
-  __shared__ float2 fstat[FT];
+  // every sample is kept twice, {x, x}: one 8-byte shared load feeds a packed fp32x2 FMA that advances the thread's
+  // two channels at once (the kernel is instruction-bound, profiles/r01_launches_b120x8s.md)
+  __shared__ __align__(16) float2 xs2[FT * S0 + K0];
+  __shared__ __align__(16) float4 fstat[FT];          // {-mean, -mean, rstd, rstd}
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * FT;
   const int nf = min(FT, T0 - t0);
   const float* x = wav + static_cast<long long>(b) * L + static_cast<long long>(t0) * S0;
   const int ns = (nf - 1) * S0 + K0;
-  for (int i = threadIdx.x; i < FT * S0 + K0; i += blockDim.x) xs[i] = i < ns ? x[i] : 0.f;
+  for (int i = threadIdx.x; i < FT * S0 + K0; i += blockDim.x) {
+    const float v = i < ns ? x[i] : 0.f;
+    xs2[i] = make_float2(v, v);
+  }
   __syncthreads();
   if (NORM == 1) {
     if (threadIdx.x < FT) {
-      const float* f = xs + threadIdx.x * S0;
+      float f[K0];
+#pragma unroll
+      for (int j = 0; j < K0; ++j) f[j] = xs2[threadIdx.x * S0 + j].x;
       float mean = consts[10];
       float var = consts[21];
 #pragma unroll
@@ -163,17 +170,15 @@ conv0_kernel(const float* __restrict__ wav, long long L, int T0, const float* __
         for (int k = 0; k < K0; ++k) acc = fmaf(consts[32 + j * K0 + k], f[k], acc);
         var = fmaf(acc, f[j], var);
       }
-      fstat[threadIdx.x] = make_float2(mean, rsqrtf(fmaxf(var, 0.f) + eps));
+      const float rstd = rsqrtf(fmaxf(var, 0.f) + eps);
+      fstat[threadIdx.x] = make_float4(-mean, -mean, rstd, rstd);
     }
     __syncthreads();
   }
   const int c = threadIdx.x * 2;
-  float w0[K0], w1[K0];
+  uint64_t w01[K0];
 #pragma unroll
-  for (int j = 0; j < K0; ++j) {
-    w0[j] = w[c * K0 + j];
-    w1[j] = w[(c + 1) * K0 + j];
-  }
+  for (int j = 0; j < K0; ++j) w01[j] = f32x2_pack(w[c * K0 + j], w[(c + 1) * K0 + j]);
   float b0 = bias ? bias[c] : 0.f, b1 = bias ? bias[c + 1] : 0.f;
   float g0 = 1.f, g1 = 1.f, e0 = 0.f, e1 = 0.f;
   if (NORM == 1) {
@@ -183,24 +188,22 @@ conv0_kernel(const float* __restrict__ wav, long long L, int T0, const float* __
     g1 = affine[(b * C0 + c + 1) * 2]; e1 = affine[(b * C0 + c + 1) * 2 + 1];
     b0 = 0.f; b1 = 0.f;   // folded into the shift
   }
+  const uint64_t b01 = f32x2_pack(b0, b1), g01 = f32x2_pack(g0, g1), e01 = f32x2_pack(e0, e1);
   uint32_t* o = reinterpret_cast<uint32_t*>(out + (static_cast<long long>(b) * T0 + t0) * C0 + c);
+  const uint64_t* xp = reinterpret_cast<const uint64_t*>(xs2);
   for (int f = 0; f < nf; ++f) {
-    const float* xf = xs + f * S0;
-    float y0 = b0, y1 = b1;
+    const uint64_t* xf = xp + f * S0;
+    uint64_t y = b01;
 #pragma unroll
-    for (int j = 0; j < K0; ++j) {
-      const float xv = xf[j];
-      y0 = fmaf(w0[j], xv, y0);
-      y1 = fmaf(w1[j], xv, y1);
-    }
+    for (int j = 0; j < K0; ++j) y = f32x2_fma(w01[j], xf[j], y);
     if (NORM == 1) {
-      const float2 st = fstat[f];
-      y0 = fmaf((y0 - st.x) * st.y, g0, e0);
-      y1 = fmaf((y1 - st.x) * st.y, g1, e1);
+      const ulonglong2 st = *reinterpret_cast<const ulonglong2*>(&fstat[f]);      // {-mean, -mean}, {rstd, rstd}
+      y = f32x2_fma(f32x2_mul(f32x2_add(y, st.x), st.y), g01, e01);
     } else if (NORM == 2) {
-      y0 = fmaf(y0, g0, e0);
-      y1 = fmaf(y1, g1, e1);
+      y = f32x2_fma(y, g01, e01);
     }
+    float y0, y1;
+    f32x2_unpack(y, y0, y1);
     gelu_erf2(y0, y1);
     o[static_cast<long long>(f) * (C0 / 2)] = pack_h16(y0, y1, out_fp16);
   }
