@@ -50,9 +50,9 @@ bilstm_kernel(const float* __restrict__ gates_in, const float* __restrict__ w_hh
   extern __shared__ __align__(16) float lsm[];
   float* Wt = lsm;                          // [k][r]   r = gate*32 + unit
   float* hbuf = Wt + LS_H * LS_R;           // [2][k][b]
-  float* gsm = hbuf + 2 * LS_H * LS_BC;     // [r][b]
+  float* gsm = hbuf + 2 * LS_H * LS_BC;     // [b][r]  recurrent part of the gates
   float* stage = gsm + LS_R * LS_BC;        // [unit][b]: this CTA's slice of h_t before it is pushed to the cluster
-  float4* psm = reinterpret_cast<float4*>(stage + LS_U * LS_BC);   // [warp][(row%4, b/4)][lane]: k-split partial sums
+  float4* psm = reinterpret_cast<float4*>(stage + LS_U * LS_BC);   // [warp][b][lane]: k-split partial sums
   __shared__ __align__(8) uint64_t hbar[2]; // hbar[p]: "all 8 slices of the h vector in hbuf[p] have landed"
   const int tid = threadIdx.x;
   const uint32_t rank = cluster_ctarank();
@@ -145,33 +145,30 @@ bilstm_kernel(const float* __restrict__ gates_in, const float* __restrict__ w_hh
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int b = 0; b < LS_BC / 2; ++b) f32x2_unpack(acc2[i][b], acc[i][2 * b], acc[i][2 * b + 1]);
-      float4* pw = psm + warp * 256;
+      float4* pw = psm + warp * 256;             // slot (utterance b, lane) = the lane's four rows of utterance b
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        pw[(i * 2 + 0) * 32 + lane] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-        pw[(i * 2 + 1) * 32 + lane] = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
-      }
+      for (int b = 0; b < LS_BC; ++b) pw[b * 32 + lane] = make_float4(acc[0][b], acc[1][b], acc[2][b], acc[3][b]);
     }
     __syncthreads();
-    {   // reduce the 8 partials of slot tid = (row%4, b/4, lane) and put the sum where the pointwise role reads it
+    {   // reduce the 8 partials of slot tid = (utterance, lane) into gsm[b][row]: every access of the reduction and
+        // of the pointwise role (row = gate * 32 + lane) is bank-conflict free
       float4 sum = psm[tid];
 #pragma unroll
       for (int w = 1; w < 8; ++w) {
         const float4 v = psm[w * 256 + tid];
         sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
       }
-      const int l = tid & 31, iq = tid >> 5;
-      *reinterpret_cast<float4*>(gsm + (4 * l + (iq >> 1)) * LS_BC + 4 * (iq & 1)) = sum;
+      *reinterpret_cast<float4*>(gsm + (tid >> 5) * LS_R + 4 * (tid & 31)) = sum;
     }
     __syncthreads();
     // pointwise: torch gate order i, f, g, o
     float h_new = 0.f;
     const bool active = s < my_len;
     if (active) {
-      const float gi = sigmoidf_(gsm[(0 * LS_U + u_pw) * LS_BC + b_pw] + gin[0]);
-      const float gf = sigmoidf_(gsm[(1 * LS_U + u_pw) * LS_BC + b_pw] + gin[1]);
-      const float gg = tanhf(gsm[(2 * LS_U + u_pw) * LS_BC + b_pw] + gin[2]);
-      const float go = sigmoidf_(gsm[(3 * LS_U + u_pw) * LS_BC + b_pw] + gin[3]);
+      const float gi = sigmoidf_(gsm[b_pw * LS_R + 0 * LS_U + u_pw] + gin[0]);
+      const float gf = sigmoidf_(gsm[b_pw * LS_R + 1 * LS_U + u_pw] + gin[1]);
+      const float gg = tanhf(gsm[b_pw * LS_R + 2 * LS_U + u_pw] + gin[2]);
+      const float go = sigmoidf_(gsm[b_pw * LS_R + 3 * LS_U + u_pw] + gin[3]);
       c_state = fmaf(gf, c_state, gi * gg);
       h_new = go * tanhf(c_state);
       const int t = dir ? (my_len - 1 - s) : s;
@@ -228,8 +225,8 @@ bilstm_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ gat
   extern __shared__ __align__(16) float lsm[];
   float* W = lsm;                           // [r][k]   r = gate*32 + unit (rows of W_hh owned by this CTA)
   float* gsm = W + LS_R * LS_H;             // [r][b]   gate gradients of this step
-  float* part = gsm + LS_R * LS_BC;         // [2][src CTA][unit][b]
-  float4* psm = reinterpret_cast<float4*>(part + 2 * LS_CL * LS_U * LS_BC);   // [row group][k half][(k%4, b/4)][lane]
+  float* part = gsm + LS_R * LS_BC;         // [2][src CTA][b][unit]
+  float4* psm = reinterpret_cast<float4*>(part + 2 * LS_CL * LS_U * LS_BC);   // [row group][k half][b][lane]
   __shared__ __align__(8) uint64_t pbar[2]; // pbar[p]: "all 8 partials in part[p] have landed"
   const int tid = threadIdx.x;
   const uint32_t rank = cluster_ctarank();
@@ -297,7 +294,7 @@ bilstm_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ gat
       const int t = dir ? (my_len - 1 - s) : s;
       float dh = cur[0];
 #pragma unroll
-      for (int c = 0; c < LS_CL; ++c) dh += pin[(c * LS_U + u_pw) * LS_BC + b_pw];
+      for (int c = 0; c < LS_CL; ++c) dh += pin[(c * LS_BC + b_pw) * LS_U + u_pw];
       const float gi = cur[1], gf = cur[2], gg = cur[3], go = cur[4], c_t = cur[5], c_prev = cur[6];
       const float tc = tanhf(c_t);
       const float dc = fmaf(dh * go, 1.0f - tc * tc, dc_state);
@@ -344,12 +341,11 @@ bilstm_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ gat
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int b = 0; b < LS_BC / 2; ++b) f32x2_unpack(acc2[i][b], acc[i][2 * b], acc[i][2 * b + 1]);
+      // slot (utterance b, lane) = the lane's four consecutive units of utterance b: the owner stores received
+      // partials as [src][b][unit], which its pointwise role (unit = lane) reads without bank conflicts
       float4* pw = psm + rg * 512 + kb * 256;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        pw[(i * 2 + 0) * 32 + lane] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-        pw[(i * 2 + 1) * 32 + lane] = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
-      }
+      for (int b = 0; b < LS_BC; ++b) pw[b * 32 + lane] = make_float4(acc[0][b], acc[1][b], acc[2][b], acc[3][b]);
       __syncthreads();
       // sum the 4 row groups of slots tid and tid + 256 and send each 16-byte result to the CTA that owns its unit
 #pragma unroll
@@ -361,12 +357,12 @@ bilstm_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ gat
           const float4 v = psm[g * 512 + slot];
           sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
         }
-        const int iq = (slot >> 5) & 7;
-        const int k = (slot >> 8) * 128 + 4 * (slot & 31) + (iq >> 1);
+        const int bq = (slot >> 5) & 7;                                  // utterance
+        const int k = (slot >> 8) * 128 + 4 * (slot & 31);               // first of the four units
         const uint32_t owner = static_cast<uint32_t>(k / LS_U);
         const uint32_t dst = map_to_cta(part, owner) +
                              static_cast<uint32_t>((((j + 1) & 1) * (LS_CL * LS_U * LS_BC) +
-                                                    (rank * LS_U + (k & (LS_U - 1))) * LS_BC + 4 * (iq & 1)) * 4);
+                                                    (rank * LS_BC + bq) * LS_U + (k & (LS_U - 1))) * 4);
         st_async_v4(dst, sum, map_to_cta(pbar, owner) + ((j + 1) & 1) * 8);
       }
     }
