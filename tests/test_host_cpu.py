@@ -132,3 +132,24 @@ def test_specaugment_masks_match_transformers():
         a = np.random.rand()
         np.random.seed(100 + seed); compute_mask_indices(shape, prob, length, frame_lens=lens, min_masks=mn)
         assert a == np.random.rand()
+
+
+def test_force_aptai_parameter_layout_matches_reference_counts():
+    """Drop-in boundary of Force_APTAI (models/force_aptai.py:20-78): 1 356 937 trainable tail parameters over the 21
+    tensors the reference trains, 315 485 921 frozen ones for the 24x1024 recogniser, and the
+    names the golden gradients of the reference's class are keyed by."""
+    import numpy as np
+    from aptai_b200 import Force_APTAI, Wav2Vec2_PR
+    from aptai_b200.backbone import register_in_memory_checkpoint
+    from helpers import ROOT, VOCAB, backbone_sd
+    cfg = cfg_large(vocab_size=46)
+    name = register_in_memory_checkpoint("mem://large-seed0-layout", backbone_sd(cfg, 0))
+    fa = Force_APTAI("unused", "cpu", VOCAB, w2v2_pr=Wav2Vec2_PR(cfg, None, name, VOCAB))
+    train = {n: p for n, p in fa.named_parameters() if p.requires_grad}
+    frozen = [p for p in fa.parameters() if not p.requires_grad]
+    assert sum(p.numel() for p in train.values()) == 1356937
+    assert sum(p.numel() for p in frozen) == 315485921          # recogniser + the 51 float64 low-pass taps
+    g = np.load(os.path.join(ROOT, "tests", "golden", "golden_force_train_v1.npz"))
+    assert sorted(train) == sorted(str(n) for n in g["grad_names"])
+    gb = fa.grad_buffer()                       # flat gradient storage: every trainable .grad is a view into it
+    assert all(gb.owns(p) for p in train.values()) and gb.numel >= 1356937
