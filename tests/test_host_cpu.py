@@ -153,3 +153,22 @@ def test_force_aptai_parameter_layout_matches_reference_counts():
     assert sorted(train) == sorted(str(n) for n in g["grad_names"])
     gb = fa.grad_buffer()                       # flat gradient storage: every trainable .grad is a view into it
     assert all(gb.owns(p) for p in train.values()) and gb.numel >= 1356937
+
+
+def test_aptai_and_pr_parameter_counts_match_reference():
+    """APTAI = backbone + 9 225 (TV head) + 47 150 (phoneme head) + 51 fp64 low-pass
+    taps; Wav2Vec2_PR = backbone + Linear(H, 46)."""
+    from aptai_b200 import APTAI, Wav2Vec2_PR
+    from aptai_b200.backbone import register_in_memory_checkpoint
+    from helpers import VOCAB, backbone_sd
+    cfg = cfg_large(vocab_size=46)
+    name = register_in_memory_checkpoint("mem://large-seed0-layout", backbone_sd(cfg, 0))
+    m = APTAI("cpu", VOCAB, name, cfg, None)
+    n_backbone = sum(p.numel() for p in m.wav2vec2.parameters())
+    assert sum(p.numel() for p in m.tv_head.parameters()) == 9225
+    assert sum(p.numel() for p in m.phn_head.parameters()) == 47150
+    assert m.tv_lowpass.lowpass.weight.dtype == torch.float64 and m.tv_lowpass.lowpass.weight.numel() == 51
+    assert sum(p.numel() for p in m.parameters()) == n_backbone + 9225 + 47150 + 51
+    pr = Wav2Vec2_PR(cfg, None, name, VOCAB)
+    assert sum(p.numel() for p in pr.parameters()) == n_backbone + 1024 * 46 + 46
+    assert n_backbone + 1024 * 46 + 46 + 51 == 315485921          # what Force_APTAI freezes (row a8)
