@@ -116,7 +116,9 @@ class RNN(nn.Module):
     @torch.no_grad()
     def forward(self, embeddings, lens):
         if self.training and self.linear[1].p > 0:
-            raise NotImplementedError("aptai_b200: training-mode dropout/backward of the RNN tail is not built; .eval()")
+            raise NotImplementedError("aptai_b200: as a standalone module RNN runs forward-only (no autograd graph); its "
+                                      "training path (dropout, BiLSTM backward through time) is driven by "
+                                      "Force_APTAI.forward in train mode — call .eval() for inference")
         x = embeddings.detach().float().contiguous()
         B, T, D = x.shape
         if B > 1:
