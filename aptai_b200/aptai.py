@@ -44,7 +44,8 @@ class APTAI(nn.Module):
     def _heads(self, audio_inputs, audio_lengths):
         """backbone -> fused TV/phoneme heads (+argmax) -> low-pass.  Returns tv [B,T,9], logits [B,T,46], pred [B,T]."""
         if self.training and (self.tv_head[0].p > 0 or self.phn_head[0].p > 0):
-            raise NotImplementedError("aptai_b200: training-mode dropout/backward is not built yet; call .eval()")
+            raise RuntimeError("aptai_b200: this is the inference path (no head dropout); in training mode call "
+                               "forward() with autograd enabled, or .eval() first")
         out = self.wav2vec2(audio_inputs, attention_mask=audio_lengths.reshape(-1)[:, None], return_dict=True,
                             output_hidden_states=False)
         h = out.last_hidden_state                       # == hidden_states[num_hidden_layers]

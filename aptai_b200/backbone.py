@@ -18,9 +18,12 @@ LayerNorm statistics and softmax in fp32.
 Training: `encode_train` runs the same kernels and keeps every activation the backward needs (no recomputation —
 the reference's gradient checkpointing exists to fit small GPUs, 180 GB of HBM3e holds a 32 x 8 s batch outright);
 `backward` runs the hand-written backward kernels (dgrad on transposed weights, MN-major tcgen05 wgrad, tcgen05
-attention backward, LayerNorm/GELU backward) into a flat gradient buffer.  The stochastic regularisers
-(SpecAugment, LayerDrop, dropout) and the backward of the conv feature encoder (frozen by the reference,
-models/aptai.py:39-40) are not built: `forward` refuses those configurations instead of silently differing.
+attention backward, LayerNorm/GELU backward) into a flat gradient buffer, including the stochastic regularisers
+of the HF training forward (counter-based dropout at every site, LayerDrop, SpecAugment along time and features)
+and the backward of the conv feature encoder when it is not frozen (the reference freezes it for APTAI,
+models/aptai.py:39-40, and trains it for the recogniser, train/train_phoneme_recognizer.py:170).
+`precision="f32x3"` (see `encode_f32x3`) is the accuracy mode: every contraction on bf16 hi/lo operand pairs
+(three tensor-core products per GEMM, ~2^-17 relative), fp32 everywhere else.
 """
 from __future__ import annotations
 
@@ -348,13 +351,22 @@ class Wav2Vec2Backbone(nn.Module):
 
     # ---- training: forward that keeps activations, and the backward --------------------------------------------
     @torch.no_grad()
-    def encode_train(self, wav: torch.Tensor, frame_lens: torch.Tensor):
+    def encode_train(self, wav: torch.Tensor, frame_lens: torch.Tensor, regularise: bool = True,
+                     collect_hidden: bool = False):
         """Same arithmetic as `encode` (the feature projection runs on bf16 instead of fp16 operands so that its
         wgrad shares the bf16 kernel), plus the training-mode regularisers: feat_proj / hidden / activation dropout
         (HF:434,546,570,603-607,647-653,694,766), LayerDrop (HF:701-706,773-778: `torch.rand([])` per layer, the same
-        host RNG stream HF consumes) and SpecAugment (HF:1280-1324).  Returns (last_hidden fp32 [B,T,H], saved)."""
+        host RNG stream HF consumes) and SpecAugment (HF:1280-1324).  Returns (last_hidden fp32 [B,T,H], saved).
+        `regularise=False`: a gradient-carrying forward of a module in eval mode (get_embeddings_grad);
+        `collect_hidden`: saved.hidden = the N+1 hidden states (HF `output_hidden_states`)."""
         self.check_trainable()
         cfg = self.cfg
+        if not regularise:
+            import copy
+            cfg = copy.copy(cfg)
+            cfg.hidden_dropout = cfg.activation_dropout = cfg.attention_dropout = cfg.feat_proj_dropout = 0.0
+            cfg.layerdrop = 0.0
+            cfg.apply_spec_augment = False
         P = TP = self.train_plan()
         B, L = wav.shape
         norm = 1 if cfg.feat_extract_norm == "layer" else 2
@@ -393,7 +405,8 @@ class Wav2Vec2Backbone(nn.Module):
         p_at = float(cfg.attention_dropout)
         seed = lambda layer, site: self.drop_seed(step, layer, site)
         sv = SimpleNamespace(B=B, T=T, frame_lens=frame_lens, layers=[], step=step, p_h=p_h, p_a=p_a, p_fp=p_fp, p_at=p_at,
-                             spec_rows=None, spec_keep=None, skipped=[], conv=conv_sv)
+                             spec_rows=None, spec_keep=None, skipped=[], conv=conv_sv, hidden=None, feats=y)
+        hidden = [] if collect_hidden else None
         sv.y32 = y.view(M, -1).float()
         _, sv.xn = ops.layernorm(sv.y32, P.fp_ln_w, P.fp_ln_b, eps)
         h0, _ = ops.linear(sv.xn, TP.fp_w_bf16, P.fp_b, want_f32=True, want_bf16=False, seg_rows=T,
@@ -450,6 +463,8 @@ class Wav2Vec2Backbone(nn.Module):
             if p_h > 0:
                 ops.dropout(h, p_h, seed(-1, self.SITE_ENC), out_f32=h)
             for li, lw in enumerate(P.layers):
+                if collect_hidden:
+                    hidden.append(h.view(B, T, H))
                 if skip_layer():
                     sv.layers.append(None)
                     sv.skipped.append(li)
@@ -470,6 +485,8 @@ class Wav2Vec2Backbone(nn.Module):
             if p_h > 0:
                 ops.dropout(h, p_h, seed(-1, self.SITE_ENC), out_f32=h, out_bf16=x)
             for li, lw in enumerate(P.layers):
+                if collect_hidden:
+                    hidden.append(h.view(B, T, H))
                 if skip_layer():
                     sv.layers.append(None)
                     sv.skipped.append(li)
@@ -485,13 +502,18 @@ class Wav2Vec2Backbone(nn.Module):
             last = h
         object.__setattr__(self, "_last_regularisers", dict(step=step, skipped=list(sv.skipped), spec_rows=sv.spec_rows,
                                                              spec_keep=sv.spec_keep))
+        if collect_hidden:
+            hidden.append(last.view(B, T, H))
+            sv.hidden = tuple(hidden)
         return last.view(B, T, H), sv
 
     @torch.no_grad()
-    def backward(self, sv, d_last: torch.Tensor, gb, prefix: str = "", on_layer_done=None) -> None:
+    def backward(self, sv, d_last: torch.Tensor, gb, prefix: str = "", on_layer_done=None, d_hidden=None) -> None:
         """Accumulate d loss / d parameter for every trainable parameter of the backbone into the GradBuffer `gb`
         (whose parameter names carry `prefix`), given d loss / d last_hidden (fp32 [B*T, H]).  `on_layer_done(i)`
-        is called once layer i's gradients are final (data-parallel all-reduce overlap, train.GradReducer)."""
+        is called once layer i's gradients are final (data-parallel all-reduce overlap, train.GradReducer).
+        `d_hidden`: {i: d loss / d hidden_states[i]} for losses that also read intermediate hidden states
+        (models/w2v2_pr.py:91-121).  Frees the saved activations as it consumes them."""
         cfg = self.cfg
         P = TP = self.train_plan()
         B, T, flen = sv.B, sv.T, sv.frame_lens
@@ -503,6 +525,9 @@ class Wav2Vec2Backbone(nn.Module):
         seed = lambda layer, site: self.drop_seed(sv.step, layer, site)
         G = lambda name: gb.view(prefix + name)
         d_last = d_last.reshape(M, H).contiguous()
+        d_hidden = {int(k): v.reshape(M, H).to(F32) for k, v in (d_hidden or {}).items() if v is not None}
+        if len(sv.layers) in d_hidden:
+            d_last = d_last + d_hidden.pop(len(sv.layers))
 
         def lin_grads(dy_b, x_b, name):
             ops.wgrad(dy_b, x_b, G(name + ".weight"))
@@ -556,6 +581,9 @@ class Wav2Vec2Backbone(nn.Module):
                                                   dgamma=G(base + "layer_norm.weight"),
                                                   dbeta=G(base + "layer_norm.bias"), want_bf16=True)
                     sv.layers[i] = None
+                if i in d_hidden:             # hidden_states[i] = the residual stream entering layer i
+                    dh32 = dh32 + d_hidden[i]
+                    dhb = ops.scale_cast_bf16(dh32)
                 if on_layer_done is not None:
                     on_layer_done(i)
             if p_h > 0:
@@ -564,6 +592,8 @@ class Wav2Vec2Backbone(nn.Module):
             dh32 = d_last
             for i in range(nl - 1, -1, -1):
                 s, lw, lt = sv.layers[i], P.layers[i], TP.layers[i]
+                if i + 1 in d_hidden:         # hidden_states[i+1] = the output of layer i
+                    dh32 = dh32 + d_hidden[i + 1]
                 if s is not None:
                     base = f"encoder.layers.{i}."
                     dt2, dt2b = ops.layernorm_bwd(dh32, s.t2, lw.ln2_w, eps, dgamma=G(base + "final_layer_norm.weight"),
@@ -577,6 +607,8 @@ class Wav2Vec2Backbone(nn.Module):
                     sv.layers[i] = None
                 if on_layer_done is not None:
                     on_layer_done(i)
+            if 0 in d_hidden:
+                dh32 = dh32 + d_hidden[0]
             if p_h > 0:
                 ops.dropout(dh32, p_h, seed(-1, self.SITE_ENC), out_f32=dh32)
             dh32, _ = ops.layernorm_bwd(dh32, sv.h_enc_in, P.enc_ln_w, eps, dgamma=G("encoder.layer_norm.weight"),
@@ -608,7 +640,14 @@ class Wav2Vec2Backbone(nn.Module):
         dxn, _ = ops.linear(dh0b, TP.fp_wt, None, want_f32=True, want_bf16=False)
         dy, _ = ops.layernorm_bwd(dxn, sv.y32, P.fp_ln_w, eps, dgamma=G("feature_projection.layer_norm.weight"),
                                   dbeta=G("feature_projection.layer_norm.bias"))
+        def release():
+            # the step is over: drop every saved activation (the closure that owns `sv` may outlive the backward when
+            # the caller keeps the loss tensor, train/train_aptai.py:446 `sum_train_loss += train_loss`)
+            for k in list(vars(sv)):
+                setattr(sv, k, None)
+
         if sv.conv is None:
+            release()
             return                              # frozen conv feature encoder (models/aptai.py:39-40)
         # ---- conv feature encoder (HF:275-299), layers 6..1 then layer 0
         cs = sv.conv
@@ -646,6 +685,8 @@ class Wav2Vec2Backbone(nn.Module):
         dw0 = torch.zeros((dz0.shape[1], 64), dtype=F32, device=dz0.device)
         ops.wgrad(dz0, X, dw0)
         G(name + "conv.weight").add_(dw0[:, : cfg.conv_kernel[0]].reshape(-1, 1, cfg.conv_kernel[0]))
+        cs.wav = cs.ys = cs.zs = cs.affine = None
+        release()
 
     # ---- the hot path ----------------------------------------------------------------------------------------
     @torch.no_grad()

@@ -396,13 +396,25 @@ viterbi_kernel(const VitArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------ greedy CTC
+// sil < 0: plain greedy collapse (argmax -> merge repeats -> drop blanks), token_frames = first frame of each token.
+// sil >= 0: the reference's decoder output (models/w2v2_pr.py:143-159 -> torchaudio _ctc_decoder.py:248-262 over
+// flashlight's raw path): the raw path is [sil] + per-frame argmax + [sil] (T+2 entries: the root hypothesis of
+// decodeBegin and the closing one of decodeEnd), merged / blank-filtered over those T+2 entries, and `timesteps`
+// index into the raw path (frame + 1).
 __global__ void __launch_bounds__(32)
-ctc_greedy_kernel(const float* __restrict__ logits, int T, int V, const int* __restrict__ input_len, int blank,
+ctc_greedy_kernel(const float* __restrict__ logits, int T, int V, const int* __restrict__ input_len, int blank, int sil,
                   int* __restrict__ tokens, int* __restrict__ token_frames, int* __restrict__ ntokens, int maxtok) {
   const int b = blockIdx.x, lane = threadIdx.x;
   const int Tb = input_len ? min(input_len[b], T) : T;
   const float* lg = logits + static_cast<long long>(b) * T * V;
-  int prev = -1, count = 0;
+  int* tk = tokens + static_cast<long long>(b) * maxtok;
+  int* tf = token_frames ? token_frames + static_cast<long long>(b) * maxtok : nullptr;
+  const int off = sil >= 0 ? 1 : 0;
+  int prev = sil >= 0 ? sil : -1, count = 0;
+  if (sil >= 0 && sil != blank) {
+    if (lane == 0) { tk[0] = sil; if (tf) tf[0] = 0; }
+    count = 1;
+  }
   for (int t0 = 0; t0 < Tb; t0 += 32) {
     const int t = t0 + lane;
     int tok = -1;
@@ -421,11 +433,15 @@ ctc_greedy_kernel(const float* __restrict__ logits, int T, int V, const int* __r
     const uint32_t mask = __ballot_sync(0xffffffffu, keep);
     const int pos = count + __popc(mask & ((1u << lane) - 1));
     if (keep && pos < maxtok) {
-      tokens[static_cast<long long>(b) * maxtok + pos] = tok;
-      if (token_frames) token_frames[static_cast<long long>(b) * maxtok + pos] = t;
+      tk[pos] = tok;
+      if (tf) tf[pos] = t + off;
     }
     count += __popc(mask);
-    prev = __shfl_sync(0xffffffffu, tok, 31);
+    prev = __shfl_sync(0xffffffffu, tok, min(31, Tb - 1 - t0));      // label of the last valid frame so far
+  }
+  if (sil >= 0 && sil != blank && prev != sil) {
+    if (lane == 0 && count < maxtok) { tk[count] = sil; if (tf) tf[count] = Tb + 1; }
+    count += 1;
   }
   if (lane == 0) ntokens[b] = count;
 }
@@ -553,7 +569,19 @@ extern "C" int aptai_ctc_greedy(const float* logits, int B, int T, int V, const 
   if (int rc = check_arch()) return rc;
   APTAI_REQUIRE(logits && tokens && ntokens, "ctc_greedy: null pointer");
   APTAI_REQUIRE(B >= 1 && T >= 1 && V >= 1 && maxtok >= 1, "ctc_greedy: bad shape");
-  ctc_greedy_kernel<<<B, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(logits, T, V, input_len, blank, tokens,
+  ctc_greedy_kernel<<<B, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(logits, T, V, input_len, blank, -1, tokens,
                                                                          token_frames, ntokens, maxtok);
   return after_launch("ctc_greedy");
+}
+
+extern "C" int aptai_ctc_decode_ref(const float* logits, int B, int T, int V, const int32_t* input_len, int blank,
+                                    int sil, int32_t* tokens, int32_t* timesteps, int32_t* ntokens, int maxtok,
+                                    void* stream) {
+  if (int rc = check_arch()) return rc;
+  APTAI_REQUIRE(logits && tokens && ntokens, "ctc_decode_ref: null pointer");
+  APTAI_REQUIRE(B >= 1 && T >= 1 && V >= 1 && maxtok >= T + 2, "ctc_decode_ref: bad shape (maxtok >= T + 2)");
+  APTAI_REQUIRE(sil >= 0 && sil < V && blank >= 0 && blank < V, "ctc_decode_ref: bad blank / sil id");
+  ctc_greedy_kernel<<<B, 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(logits, T, V, input_len, blank, sil, tokens,
+                                                                         timesteps, ntokens, maxtok);
+  return after_launch("ctc_decode_ref");
 }

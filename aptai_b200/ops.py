@@ -249,7 +249,7 @@ ATTENTION_IMPL = int(os.environ.get("APTAI_ATTN_IMPL", "0"))
 
 
 def attention(qkv: torch.Tensor, key_len: Optional[torch.Tensor], B: int, T: int, heads: int,
-              out: Optional[torch.Tensor] = None, legacy_mma: bool = False, lse: Optional[torch.Tensor] = None,
+              out: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None,
               impl: Optional[int] = None, drop_p: float = 0.0, drop_seed: int = 0) -> torch.Tensor:
     _req(qkv, BF16, "qkv")
     H = heads * 64
@@ -268,7 +268,7 @@ def attention(qkv: torch.Tensor, key_len: Optional[torch.Tensor], B: int, T: int
                                                       _stream()), "attention_fwd_dropout")
         return out
     which = impl or ATTENTION_IMPL or (2 if T > 128 else 1)
-    if which == 2 and not legacy_mma:
+    if which == 2:
         check(_lib.load().aptai_attention_fwd_v2(qkv.data_ptr(), out.data_ptr(), _ptr(lse), key_len.data_ptr(), B, T,
                                                  heads, _stream()), "attention_fwd_v2")
         return out
@@ -276,8 +276,7 @@ def attention(qkv: torch.Tensor, key_len: Optional[torch.Tensor], B: int, T: int
         check(_lib.load().aptai_attention_fwd_lse(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), key_len.data_ptr(),
                                                   B, T, heads, _stream()), "attention_fwd_lse")
         return out
-    fn = _lib.load().aptai_attention_fwd_mma if legacy_mma else _lib.load().aptai_attention_fwd
-    check(fn(qkv.data_ptr(), out.data_ptr(), key_len.data_ptr(), B, T, heads, _stream()), "attention_fwd")
+    check(_lib.load().aptai_attention_fwd(qkv.data_ptr(), out.data_ptr(), key_len.data_ptr(), B, T, heads, _stream()), "attention_fwd")
     return out
 
 
@@ -437,6 +436,21 @@ def ctc_greedy(logits: torch.Tensor, input_len: Optional[torch.Tensor], blank: i
     check(_lib.load().aptai_ctc_greedy(logits.data_ptr(), B, T, V, _ptr(input_len), blank, tokens.data_ptr(),
                                        frames.data_ptr(), ntok.data_ptr(), maxtok, _stream()), "ctc_greedy")
     return tokens, frames, ntok
+
+
+def ctc_decode_ref(logits: torch.Tensor, input_len: Optional[torch.Tensor], blank: int = 0, sil: int = 1):
+    """The reference's decoder output on device (`aptai_ctc_decode_ref`): tokens int32 [B,T+2] (leading / trailing
+    `sil`), timesteps int32 [B,T+2] (raw-path index = frame + 1), ntokens int32 [B]."""
+    _req(logits, F32, "logits")
+    B, T, V = logits.shape
+    dev = logits.device
+    maxtok = T + 2
+    tokens = torch.zeros((B, maxtok), dtype=I32, device=dev)
+    steps = torch.zeros((B, maxtok), dtype=I32, device=dev)
+    ntok = torch.empty((B,), dtype=I32, device=dev)
+    check(_lib.load().aptai_ctc_decode_ref(logits.data_ptr(), B, T, V, _ptr(input_len), blank, sil, tokens.data_ptr(),
+                                           steps.data_ptr(), ntok.data_ptr(), maxtok, _stream()), "ctc_decode_ref")
+    return tokens, steps, ntok
 
 
 # ============================================================================================ training step

@@ -193,12 +193,36 @@ def tvs_metric_rmse(tvs_gt, tvs_pred):
     return {k: float(v) for k, v in zip(TV_NAMES, rm[0].tolist())}
 
 
+class PearsonRResult(tuple):
+    """What `scipy.stats.pearsonr` returns, as far as the reference's callers use it: `.statistic`, `.pvalue`
+    (train/train_aptai.py:582-584,767-768) and tuple unpacking `(r, p)`."""
+
+    def __new__(cls, statistic: float, pvalue: float):
+        return super().__new__(cls, (statistic, pvalue))
+
+    statistic = property(lambda self: self[0])
+    pvalue = property(lambda self: self[1])
+    correlation = statistic
+
+
+def _pearson_pvalue(r: float, n: int) -> float:
+    """Two-sided p-value of scipy.stats.pearsonr: r ~ Beta(n/2-1, n/2-1) on [-1, 1] under the null hypothesis
+    (host arithmetic on one scalar per channel; the correlation itself comes from the device kernel)."""
+    if n < 3 or not math.isfinite(r):
+        return 1.0 if n == 2 else float("nan")
+    from scipy.special import betainc
+    a = n / 2.0 - 1.0
+    return float(min(1.0, 2.0 * betainc(a, a, (1.0 - min(1.0, abs(r))) / 2.0)))
+
+
 def tvs_metric_ppc(tvs_gt, tvs_pred):
-    """utility.py:422-444: dict channel -> Pearson r (the reference stores scipy's (r, p) result; r is returned)."""
+    """utility.py:422-444: dict channel -> scipy-style `pearsonr` result (`.statistic`, `.pvalue`, unpacks as a
+    tuple).  r is computed by the device kernel, the p-value on the host from (r, n)."""
     g = torch.as_tensor(np.asarray(tvs_gt, dtype=np.float32))[None]
     p = torch.as_tensor(np.asarray(tvs_pred, dtype=np.float32))[None]
-    _, pc = tv_metrics_batch(g, p, torch.tensor([g.shape[1]], dtype=I32))
-    return {k: float(v) for k, v in zip(TV_NAMES, pc[0].tolist())}
+    n = int(g.shape[1])
+    _, pc = tv_metrics_batch(g, p, torch.tensor([n], dtype=I32))
+    return {k: PearsonRResult(float(v), _pearson_pvalue(float(v), n)) for k, v in zip(TV_NAMES, pc[0].tolist())}
 
 
 def get_metrics(precision_counter, recall_counter, pred_counter, gt_counter):

@@ -162,8 +162,11 @@ class GradReducer:
 
 def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> None:
     """Every rank starts from rank `src`'s weights (DDP's construction-time broadcast)."""
-    for t in list(module.parameters()) + list(module.buffers()):
+    ts = list(module.parameters()) + list(module.buffers())
+    for t in ts:
         dist.broadcast(t.data, src=src, group=group)
+    # `.data` writes do not bump the version counters the kernel-weight cache (Wav2Vec2Backbone.plan) keys on
+    torch.autograd.graph.increment_version(ts)
 
 
 class FusedAdam(torch.optim.Optimizer):
@@ -198,6 +201,7 @@ class FusedAdam(torch.optim.Optimizer):
             off += (n + _ALIGN - 1) // _ALIGN * _ALIGN
         self._ptrs = torch.tensor([p.data_ptr() for p in params], dtype=torch.int64, device=dev)
         self._soffs = torch.tensor(soffs, dtype=torch.int64, device=dev)
+        self._soffs_host = soffs
         self._nums = torch.tensor(nums, dtype=torch.int64, device=dev)
         chunks = [(i, s) for i, n in enumerate(nums) for s in range(0, n, self.CHUNK)]
         ck = torch.tensor(chunks, dtype=torch.int64).reshape(-1, 2)   # {int32 tensor | pad} (little endian), int64 start
@@ -259,6 +263,47 @@ class FusedAdam(torch.optim.Optimizer):
         torch.autograd.graph.increment_version(self._params)
         return loss
 
+    # ---- checkpointing: torch.optim.Adam's layout, so optimizer.pt files are interchangeable with the reference's
+    # (train/train_phoneme_recognizer.py:396 loads it, :483 saves it)
+    def _moment_views(self, i: int):
+        off, n = int(self._soffs_host[i]), self._params[i].numel()
+        shape = self._params[i].shape
+        return self.exp_avg[off: off + n].view(shape), self.exp_avg_sq[off: off + n].view(shape)
+
+    def state_dict(self):
+        sd = super().state_dict()
+        state = {}
+        if self._step > 0:
+            for i in range(len(self._params)):
+                m, v = self._moment_views(i)
+                state[i] = {"step": torch.tensor(float(self._step)), "exp_avg": m.clone(), "exp_avg_sq": v.clone()}
+        sd["state"] = state
+        return sd
+
+    @torch.no_grad()
+    def load_state_dict(self, state_dict):
+        groups = state_dict["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(self._params):
+            raise ValueError("FusedAdam.load_state_dict: parameter groups do not match this optimizer")
+        for k, v in groups[0].items():
+            if k != "params":
+                self.param_groups[0][k] = v
+        state = state_dict.get("state", {})
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        steps = set()
+        for i, pid in enumerate(groups[0]["params"]):
+            st = state.get(pid, state.get(str(pid)))
+            if st is None:
+                continue
+            m, v = self._moment_views(i)
+            m.copy_(st["exp_avg"].to(m.device, F32).view_as(m))
+            v.copy_(st["exp_avg_sq"].to(v.device, F32).view_as(v))
+            steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError("FusedAdam.load_state_dict: per-parameter step counts differ; the fused step keeps one")
+        self._step = steps.pop() if steps else 0
+
 
 class _BackwardHook(torch.autograd.Function):
     """Makes `out['loss'].backward()` run the hand-written backward: the forward stores a closure that launches the
@@ -271,7 +316,14 @@ class _BackwardHook(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
-        ctx.run_backward(grad_out)
+        run, ctx.run_backward = ctx.run_backward, None
+        if run is None:
+            raise RuntimeError("aptai_b200: backward through this loss a second time (its activations were freed, "
+                               "as stock autograd does without retain_graph)")
+        # the closure owns every saved activation of the step: dropping it here frees them even if the caller keeps
+        # the loss tensor (and with it this node) alive, e.g. `sum_train_loss += train_loss`
+        # (train/train_aptai.py:446)
+        run(grad_out)
         return None, None, None
 
 

@@ -5,10 +5,13 @@ log_softmax + CTC loss (mean, zero_infinity, blank from the config).  The target
 (the reference loops over device scalars, models/w2v2_pr.py:62-70), and the conv encoder runs once in
 `get_embeddings` (the reference runs it twice, :129).
 
-Decoding: the reference builds a torchaudio/flashlight lexicon-free beam decoder on every call
-(:143-155); flashlight-text is not installable here, so the decoder is injectable (`phoneme_decoder=`) and
-defaults to the on-device greedy CTC collapse (with no LM and max-merge the best beam is the
-greedy path).  The flashlight wrapper is parity-unpinned.
+Decoding: the reference builds a torchaudio/flashlight lexicon-free beam decoder on every call (:143-155).  Here the
+default is the on-device `aptai_ctc_decode_ref` kernel, which reproduces that decoder's OUTPUT: with no LM and
+max-merge the best beam is the frame-wise argmax path, and flashlight's raw path carries a leading and a trailing
+`(...)` silence entry which torchaudio's `_get_tokens` / `_get_timesteps` collapse with the frame labels — so token
+lists start / end with the silence id and time stamps are frame + 1 (oracle/ctc_decode.py restates both layers;
+flashlight-text itself is not installable here, so that layer stays parity-unpinned).  Any other decoder can be
+injected (`phoneme_decoder=`).
 """
 from __future__ import annotations
 
@@ -23,6 +26,62 @@ from .backbone import Wav2Vec2Backbone
 from .config import W2V2Config
 from .graphs import GraphCache
 from .train import GradBuffer, GradReducer, attach_backward, broadcast_parameters
+
+BLANK_TOKEN, SIL_TOKEN = "(blank)", "(...)"          # models/w2v2_pr.py:152-153
+
+
+class _HiddenStatesFn(torch.autograd.Function):
+    """Gradient-carrying hidden states for `get_embeddings_grad`: autograd delivers d loss / d hidden_states and the
+    hand-written backbone backward accumulates the parameter gradients into the model's flat gradient buffer."""
+
+    @staticmethod
+    def forward(ctx, anchor, model, sv, idx, *hidden):
+        ctx.model, ctx.sv, ctx.idx = model, sv, idx
+        return tuple(h.detach().clone() for h in hidden)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        model, sv, idx = ctx.model, ctx.sv, ctx.idx
+        ctx.model = ctx.sv = None
+        if sv is None:
+            raise RuntimeError("aptai_b200: backward through get_embeddings_grad a second time")
+        w2v = model.wav2vec2
+        n = len(w2v.encoder.layers)
+        d_hidden = {}
+        for i, g in zip(idx, grads):
+            if g is not None:
+                i = i % (n + 1)
+                d_hidden[i] = d_hidden[i] + g.float() if i in d_hidden else g.float()
+        B, T, H = sv.B, sv.T, w2v.cfg.hidden_size
+        d_last = d_hidden.pop(n, None)
+        if d_last is None:
+            d_last = torch.zeros((B * T, H), dtype=torch.float32, device=sv.frame_lens.device)
+        w2v.backward(sv, d_last.contiguous(), model.grad_buffer(), prefix="wav2vec2.", d_hidden=d_hidden)
+        return (None,) * (4 + len(idx))
+
+
+class _HeadFn(torch.autograd.Function):
+    """pr_head (Linear H -> vocab) through the heads kernels, differentiable w.r.t. its input and parameters."""
+
+    @staticmethod
+    def forward(ctx, h, weight, bias):
+        B, T, H = h.shape
+        hm = h.detach().reshape(B * T, H).float().contiguous()
+        w = weight.detach().float().contiguous()
+        _, logits, _ = ops.heads(hm, None, None, 0, w, bias.detach().float().contiguous(), ops.ACT_NONE,
+                                 want_argmax=False)
+        ctx.save_for_backward(hm, w)
+        return logits.view(B, T, -1)
+
+    @staticmethod
+    def backward(ctx, d_logits):
+        hm, w = ctx.saved_tensors
+        B, T, V = d_logits.shape
+        dw = torch.zeros_like(w)
+        db = torch.zeros((V,), dtype=torch.float32, device=w.device)
+        dh = ops.heads_bwd(hm, None, None, 0, None, None, d_logits.reshape(B * T, V).float().contiguous(), w,
+                           ops.ACT_NONE, dw, db)
+        return dh.view(B, T, -1), dw, db
 
 
 def idx_phonemes(vocab, seq):
@@ -51,7 +110,8 @@ class Wav2Vec2_PR(nn.Module):
     @torch.no_grad()
     def _logits(self, input_values, input_lengths, output_hidden_states=False):
         if self.training and self.dropout.p > 0:
-            raise NotImplementedError("aptai_b200: training-mode dropout/backward is not built yet; call .eval()")
+            raise RuntimeError("aptai_b200: this is the inference path (no final dropout); in training mode call "
+                               "forward() with autograd enabled, or .eval() first")
         out = self.wav2vec2(input_values, attention_mask=input_lengths.reshape(-1)[:, None], return_dict=True,
                             output_hidden_states=output_hidden_states)
         h = out.last_hidden_state
@@ -149,15 +209,26 @@ class Wav2Vec2_PR(nn.Module):
             res["loss"] = attach_backward(res["loss"], self.pr_head.weight, run_backward)
         return res
 
-    def _decode(self, phoneme_logits, frame_lens=None):
-        """List of int arrays, one per utterance.  Default: greedy collapse over all frames (the reference passes
-        no lengths to its decoder either, :155)."""
+    def _token_ids(self, vocab=None):
+        """(blank, sil) ids as the reference's decoder sees them: positions in `list(vocab.keys())` (:144-153)."""
+        vocab = vocab if vocab is not None else self.vocab
+        if vocab is None:
+            return int(self.wav2vec2.cfg.blank), 1
+        keys = list(vocab.keys())
+        return keys.index(BLANK_TOKEN), keys.index(SIL_TOKEN)
+
+    def _decode(self, phoneme_logits, frame_lens=None, vocab=None, with_timesteps=False):
+        """List of int arrays, one per utterance: what `decoder(logits)[b][0].tokens` holds in the reference (all
+        frames are decoded: the reference passes no lengths to its decoder, :155)."""
         if self.phoneme_decoder is not None:
             return [np.asarray(x) for x in self.phoneme_decoder(phoneme_logits)]
-        blank = int(self.wav2vec2.cfg.blank)
-        tok, _, n = ops.ctc_greedy(phoneme_logits.contiguous(), None, blank=blank)
-        tok, n = tok.cpu().numpy(), n.cpu().numpy()
-        return [tok[b, : n[b]].astype(np.int64) for b in range(tok.shape[0])]
+        blank, sil = self._token_ids(vocab)
+        tok, steps, n = ops.ctc_decode_ref(phoneme_logits.contiguous(), frame_lens, blank=blank, sil=sil)
+        tok, steps, n = tok.cpu().numpy(), steps.cpu().numpy(), n.cpu().numpy()
+        toks = [tok[b, : n[b]].astype(np.int64) for b in range(tok.shape[0])]
+        if with_timesteps:
+            return toks, [steps[b, : n[b]].astype(np.int32) for b in range(tok.shape[0])]
+        return toks
 
     def get_embeddings(self, audio_inputs, audio_lengths):
         """models/w2v2_pr.py:124-167."""
@@ -175,18 +246,37 @@ class Wav2Vec2_PR(nn.Module):
             }
 
     def get_embeddings_grad(self, audio_inputs, audio_lengths, vocab, intermediate_hidden, latter_hidden):
-        """models/w2v2_pr.py:91-121 (values only: no autograd graph is recorded in this round)."""
-        out = self.wav2vec2(audio_inputs, attention_mask=audio_lengths.reshape(-1)[:, None], return_dict=True,
-                            output_hidden_states=True)
-        last = out.last_hidden_state
-        inter = out.hidden_states[intermediate_hidden]
-        latter = out.hidden_states[latter_hidden]
+        """models/w2v2_pr.py:91-121.  With autograd enabled the hidden states and logits carry gradients like the
+        reference's: `.backward()` of anything computed from them runs the hand-written backbone backward (into
+        `p.grad` of the backbone parameters, views of the flat gradient buffer) and the heads backward (pr_head).
+        The module's mode decides the regularisers, as in the reference (eval: none).  `features_hidden` is returned
+        detached."""
+        w2v = self.wav2vec2
+        if not torch.is_grad_enabled():
+            out = w2v(audio_inputs, attention_mask=audio_lengths.reshape(-1)[:, None], return_dict=True,
+                      output_hidden_states=True)
+            last, inter, latter = (out.last_hidden_state, out.hidden_states[intermediate_hidden],
+                                   out.hidden_states[latter_hidden])
+            feats = out.extract_features
+            head = lambda x: self._head(x.contiguous())
+        else:
+            dev = next(w2v.parameters()).device
+            wav = audio_inputs.to(device=dev, dtype=torch.float32).contiguous()
+            lens = audio_lengths.reshape(-1).to(device=dev, dtype=torch.int64)
+            flen = w2v._get_feat_extract_output_lengths(lens).to(torch.int32).contiguous()
+            self.grad_buffer()
+            _, sv = w2v.encode_train(wav, flen, regularise=self.training, collect_hidden=True)
+            idx = (len(w2v.encoder.layers), intermediate_hidden, latter_hidden)
+            feats = sv.feats
+            last, inter, latter = _HiddenStatesFn.apply(self.pr_head.weight, self, sv, idx,
+                                                        *[sv.hidden[i] for i in idx])
+            head = lambda x: _HeadFn.apply(x, self.pr_head.weight, self.pr_head.bias)
         return {
-            "features_hidden": out.extract_features.float().permute(0, 2, 1),
+            "features_hidden": feats.float().permute(0, 2, 1),
             "last_transf_hidden": last.permute(0, 2, 1),
-            "phoneme_logits_last": self._head(last),
-            "phoneme_logits_inter": self._head(inter.contiguous()),
-            "phoneme_logits_latter": self._head(latter.contiguous()),
+            "phoneme_logits_last": head(last),
+            "phoneme_logits_inter": head(inter),
+            "phoneme_logits_latter": head(latter),
             "intermediate_hidden": inter.permute(0, 2, 1),
             "latter_hidden": latter.permute(0, 2, 1),
         }
@@ -222,20 +312,20 @@ class Wav2Vec2_PR(nn.Module):
         self.eval()
         with torch.no_grad():
             _, logits = self._single(wav)
-            idx = self._decode(logits)[0]
+            idx = self._decode(logits, vocab=vocab)[0]
             return {"phn_seq_idx": idx, "phn_seq_ipa": idx_phonemes(vocab, idx)}
 
     def predict_phonemes_durations(self, wav, vocab):
-        """models/w2v2_pr.py:191-235: token time stamps = first frame of each token * seconds per frame."""
+        """models/w2v2_pr.py:191-235: time stamps = the decoder's `timesteps` (index of each token's first entry in
+        the raw path, i.e. frame + 1; 0 for the leading silence) * seconds per frame."""
         self.eval()
         with torch.no_grad():
             wav_input, logits = self._single(wav)
             frame_sec_ratio = wav_input.shape[1] / logits.shape[1] / 16000
-            blank = int(self.wav2vec2.cfg.blank)
-            tok, frm, n = ops.ctc_greedy(logits.contiguous(), None, blank=blank)
-            n0 = int(n[0])
-            idx = tok[0, :n0].cpu().numpy()
-            ts = frm[0, :n0].cpu().numpy()
+            if self.phoneme_decoder is not None:
+                raise NotImplementedError("predict_phonemes_durations needs the built-in decoder's time stamps")
+            toks, steps = self._decode(logits, vocab=vocab, with_timesteps=True)
+            idx, ts = toks[0], steps[0]
             return {"phn_seq_idx": idx, "phn_seq_ipa": idx_phonemes(vocab, idx),
                     "phn_seq_dur": [t * frame_sec_ratio for t in ts]}
 

@@ -118,8 +118,6 @@ int aptai_attention_fwd(const void* qkv, void* ctx, const int32_t* key_len, int 
  * K/V stream and run independent softmax chains (csrc/attention_tc2.cu) */
 int aptai_attention_fwd_v2(const void* qkv, void* ctx, float* lse, const int32_t* key_len, int B, int T, int heads,
                            void* stream);
-/* same contract on the legacy mma.sync tensor path; A/B baseline for profiles/, not used by the product path */
-int aptai_attention_fwd_mma(const void* qkv, void* ctx, const int32_t* key_len, int B, int T, int heads, void* stream);
 
 /* ------------------------------------------------------------------ heads and post-processing ---------------
  * APTAI heads (models/aptai.py:43-55,83-86,105-106): tv = tanh(h) W_tv^T + b_tv (9), logits = leaky_relu(h)
@@ -212,6 +210,16 @@ int aptai_ctc_viterbi_f32(const float* log_probs, const int32_t* targets, const 
 /* greedy CTC collapse on device (argmax -> merge repeats -> drop blank); models/w2v2_pr.py:143-159 next-row. */
 int aptai_ctc_greedy(const float* logits, int B, int T, int V, const int32_t* input_len, int blank,
                      int32_t* tokens, int32_t* token_frames, int32_t* ntokens, int maxtok, void* stream);
+
+/* The reference's lexicon-free CTC decode on device: replaces torchaudio.models.decoder.ctc_decoder(lexicon=None,
+ * lm=None, nbest=1, beam_size=10, beam_threshold=50, blank_token, sil_token)(logits)[b][0].{tokens, timesteps}
+ * (models/w2v2_pr.py:143-159, 209-229, 257-272; utility.py:448-471).  With no LM and max-merge the best beam is the
+ * frame-wise argmax path; flashlight's raw path carries a leading and a trailing `sil` entry (T + 2 entries), which
+ * torchaudio's _get_tokens / _get_timesteps (_ctc_decoder.py:248-262) collapse together with the frame labels:
+ * tokens int32 [B][maxtok] start / end with `sil`, timesteps int32 [B][maxtok] = frame + 1.  maxtok >= T + 2.
+ * input_len NULL = decode all T frames, as the reference does (it passes no lengths). */
+int aptai_ctc_decode_ref(const float* logits, int B, int T, int V, const int32_t* input_len, int blank, int sil,
+                         int32_t* tokens, int32_t* timesteps, int32_t* ntokens, int maxtok, void* stream);
 
 
 /* ================================================================== training step (backward + optimizer) =====

@@ -23,6 +23,5 @@ for B, T in [(120, 399), (493, 99), (48, 999), (80, 600)]:
     fl = 4.0 * B * heads * T * T * 64
     a = timeit(lambda: ops.attention(qkv, kl, B, T, heads, out=out, impl=1))
     c = timeit(lambda: ops.attention(qkv, kl, B, T, heads, out=out, impl=2))
-    b = timeit(lambda: ops.attention(qkv, kl, B, T, heads, out=out, legacy_mma=True))
     print(f"B={B:4d} T={T:4d}: tcgen05 v1 {a:7.3f} ms {fl / a / 1e9:7.1f} TFLOP/s | v2 (q-tile pairs) {c:7.3f} ms "
-          f"{fl / c / 1e9:7.1f} TFLOP/s | mma.sync {b:7.3f} ms {fl / b / 1e9:7.1f} TFLOP/s")
+          f"{fl / c / 1e9:7.1f} TFLOP/s")

@@ -24,6 +24,16 @@ def golden():
     return np.load(GOLDEN)
 
 
+_G2 = {}
+
+
+def golden2():
+    """Config-size fixtures from the reference's own classes (tests/golden/make_golden_v2.py)."""
+    if "g" not in _G2:
+        _G2["g"] = dict(np.load(os.path.join(ROOT, "tests", "golden", "golden_v2.npz")))
+    return _G2["g"]
+
+
 def cfg_large(**kw):
     return W2V2Config.large(**{**NO_REG, **kw})
 

@@ -67,7 +67,7 @@ def test_layernorm(cuda, cols, in_bf16):
     torch.testing.assert_close(o16.float(), ref.bfloat16().float(), atol=2e-2, rtol=1e-2)
 
 
-@pytest.mark.parametrize("legacy", [False, True, "v2"])
+@pytest.mark.parametrize("legacy", [False, "v2"])
 @pytest.mark.parametrize("B,T,heads,lens,scale", [(2, 199, 16, [199, 150], 1.0), (3, 64, 12, [64, 1, 33], 1.0),
                                                   (1, 999, 4, [999], 1.0), (2, 130, 2, [70, 130], 1.0),
                                                   (40, 399, 16, None, 0.5), (2, 513, 2, [513, 400], 3.0),
@@ -85,7 +85,7 @@ def test_attention(cuda, B, T, heads, lens, scale, legacy):
         lse = torch.empty((B, heads, T), dtype=torch.float32, device=cuda)
         ctx = ops.attention(qkv, kl, B, T, heads, impl=2, lse=lse)
     else:
-        ctx = ops.attention(qkv, kl, B, T, heads, legacy_mma=legacy, impl=1)
+        ctx = ops.attention(qkv, kl, B, T, heads, impl=1)
     q, k, v = qkv.float().view(B, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
     s = q @ k.transpose(-1, -2)                      # q is expected pre-scaled
     mask = torch.arange(T, device=cuda)[None, :] < kl[:, None]

@@ -128,3 +128,26 @@ def test_force_tail_forward_sum_agrees_with_numpy_oracle_and_reference():
     loss_n, _ = octc.forward_sum_loss(g["g5_fs_in"], g["g5_fs_text"], g["g5_fs_mel"], -1.0)
     assert abs(loss_t - loss_n) < 1e-4 * abs(loss_n)
     assert abs(loss_t - float(g["g5_fs_loss"][0])) < 1e-4 * abs(float(g["g5_fs_loss"][0]))
+
+
+def test_ctc_decode_restatement_beam_equals_greedy_wrap():
+    """oracle/ctc_decode.py: the restated flashlight lexicon-free beam search (beam 10, threshold 50, ZeroLM,
+    max-merge) returns the [sil] + frame-wise argmax + [sil] raw path, and torchaudio's token / time-stamp collapse of
+    that path gives leading / trailing silence ids and frame + 1 time stamps."""
+    from oracle import ctc_decode as D
+    g = np.random.default_rng(3)
+    for trial in range(40):
+        T, N = int(g.integers(1, 30)), int(g.integers(3, 9))
+        em = (g.standard_normal((T, N)) * (1.0 if trial % 2 else 0.05)).astype(np.float32)
+        raw = D.flashlight_lexfree_decode(em, blank=0, sil=1)
+        assert raw.shape == (T + 2,) and raw[0] == 1 and raw[-1] == 1
+        assert np.array_equal(raw, D.greedy_raw_path(em, 1)), trial
+    # known answers for the torchaudio layer (_ctc_decoder.py:248-262)
+    raw = [1, 0, 0, 5, 5, 0, 7, 1, 1]          # sil | . . 5 5 . 7 sil | sil   (path ends in silence: merged)
+    assert D.torchaudio_tokens(raw, 0).tolist() == [1, 5, 7, 1]
+    assert D.torchaudio_timesteps(raw, 0).tolist() == [0, 3, 6, 7]
+    raw = [1, 1, 4, 4, 0, 4, 1]                # path starts in silence: merged with the root entry
+    assert D.torchaudio_tokens(raw, 0).tolist() == [1, 4, 4, 1]
+    assert D.torchaudio_timesteps(raw, 0).tolist() == [0, 2, 5, 6]
+    tk, ts = D.reference_decode(np.eye(4, dtype=np.float32)[[2, 2, 0, 3]], blank=0, sil=1)
+    assert tk.tolist() == [1, 2, 3, 1] and ts.tolist() == [0, 1, 4, 5]

@@ -45,7 +45,14 @@ def test_tv_metrics(cuda):
     rm = pp.tvs_metric_rmse(G["m_gt"], G["m_pred"])
     pc = pp.tvs_metric_ppc(G["m_gt"], G["m_pred"])
     assert np.array_equal(np.asarray([rm[k] for k in NAMES]), G["m_rmse"])               # bit-exact
-    np.testing.assert_allclose(np.asarray([pc[k] for k in NAMES]), G["m_pcc"], rtol=1e-12)
+    np.testing.assert_allclose(np.asarray([pc[k].statistic for k in NAMES]), G["m_pcc"], rtol=1e-12)
+    # scipy-style result object, as the reference's validate/test loops read it (train/train_aptai.py:582-584)
+    from scipy.stats import pearsonr
+    for i, k in enumerate(NAMES):
+        r, pv = pc[k]
+        ref = pearsonr(G["m_gt"][:, i], G["m_pred"][:, i])
+        assert r == pc[k].statistic and pv == pc[k].pvalue
+        np.testing.assert_allclose(pv, ref.pvalue, rtol=1e-6, atol=1e-300)
     # batched with lengths
     rng = np.random.Generator(np.random.PCG64(4))
     gt = rng.standard_normal((5, 300, 9)).astype(np.float32)
