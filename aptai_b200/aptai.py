@@ -170,6 +170,11 @@ class APTAI(nn.Module):
             out.update(align_paths=paths, align_scores=scores, align_status=status, log_probs=lp)
         return out
 
+    def set_precision(self, precision: str):
+        """'bf16' (default) or 'f32x3' (accuracy mode of the encoder, aptai_b200/accurate.py; inference only)."""
+        self.wav2vec2.set_precision(precision)
+        return self
+
     def get_config(self):
         return {"device": self.device, "vocab": self.vocab, "huggingface_model_id": self.huggingface_model_id,
                 "pretrain_cfg": self.pretrain_cfg}
@@ -181,7 +186,7 @@ class APTAI(nn.Module):
             tv, logits, pred = self._heads(w, l)
             return tv, logits, pred, ops.softmax_rows(logits.contiguous())
 
-        if not self.use_cuda_graphs:
+        if not self.use_cuda_graphs or self.wav2vec2.precision != "bf16":
             return fn(wav_input, wav_len)
         cache = getattr(self, "_graph_cache", None)
         if cache is None:

@@ -257,6 +257,7 @@ class Wav2Vec2Backbone(nn.Module):
         self.feature_extractor = _FeatureExtractor(cfg)
         self.feature_projection = _FeatureProjection(cfg)
         self.encoder = _Encoder(cfg)
+        self.precision = "bf16"                    # "bf16" (default) | "f32x3" (accuracy mode, aptai_b200/accurate.py)
         self._plan: Optional[_Plan] = None
         self._plan_key = None
         self._plan_ptrs = None
@@ -293,6 +294,14 @@ class Wav2Vec2Backbone(nn.Module):
                 f"'{model_id}' is not a local directory; hub downloads are unavailable (no network). "
                 "Pass a directory written by save_pretrained().")
         return m
+
+    def set_precision(self, precision: str):
+        """'bf16': 16-bit tensor-core operands (default, the measured hot path).  'f32x3': accuracy mode — every
+        contraction on bf16 hi/lo operand pairs, fp32 elsewhere (inference only)."""
+        if precision not in ("bf16", "f32x3"):
+            raise ValueError(f"aptai_b200: unknown precision {precision!r} ('bf16' or 'f32x3')")
+        self.precision = precision
+        return self
 
     def gradient_checkpointing_enable(self, *a, **k):    # models/aptai.py:38 — no autograd graph to checkpoint here
         return None
@@ -694,6 +703,11 @@ class Wav2Vec2Backbone(nn.Module):
                want_features: bool = False):
         """wav fp32 [B,L] (CUDA), frame_lens int32 [B] (CUDA, valid frames per utterance).
         Returns (last_hidden fp32 [B,T,H], hidden tuple | None, features bf16 [B,T,512] | None)."""
+        if self.precision == "f32x3":
+            from . import accurate
+            return accurate.encode(self, wav, frame_lens, collect_hidden=collect_hidden, want_features=want_features)
+        if self.precision != "bf16":
+            raise ValueError(f"aptai_b200: unknown precision {self.precision!r} ('bf16' or 'f32x3')")
         cfg, P = self.cfg, self.plan()
         B, L = wav.shape
         norm = 1 if cfg.feat_extract_norm == "layer" else 2

@@ -209,9 +209,115 @@ conv0_kernel(const float* __restrict__ wav, long long L, int T0, const float* __
   }
 }
 
+// Accuracy mode (csrc/accurate.cu): the same layer with plain fp32 arithmetic (two-pass LayerNorm statistics over
+// the 512 channels of a frame, warp per frame) and a split-bf16 output [B][T0][hi 512 | lo 512 | hi 512] that feeds
+// conv layer 1 as a three-product implicit GEMM.  NORM as above.
+template <int NORM>
+__global__ void __launch_bounds__(256)
+conv0_accurate_kernel(const float* __restrict__ wav, long long L, int T0, const float* __restrict__ w,
+                      const float* __restrict__ bias, const float* __restrict__ gamma, const float* __restrict__ beta,
+                      const float* __restrict__ affine, float eps, __nv_bfloat16* __restrict__ out3) {
+  __shared__ float ws[K0][C0];                 // tap-major copy of the weights
+  for (int i = threadIdx.x; i < K0 * C0; i += blockDim.x) ws[i % K0][i / K0] = w[i];
+  __syncthreads();
+  const int b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int t = blockIdx.x * 64 + warp; t < min(T0, blockIdx.x * 64 + 64); t += 8) {
+    const float* x = wav + static_cast<long long>(b) * L + static_cast<long long>(t) * S0;
+    float xs[K0];
+#pragma unroll
+    for (int j = 0; j < K0; ++j) xs[j] = __ldg(x + j);
+    float y[16];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int c = 2 * lane + 64 * i + e;
+        float a = 0.f;
+#pragma unroll
+        for (int j = 0; j < K0; ++j) a = fmaf(ws[j][c], xs[j], a);
+        if (NORM == 2) a = fmaf(a, affine[(b * C0 + c) * 2], affine[(b * C0 + c) * 2 + 1]);
+        else if (bias) a += bias[c];
+        y[2 * i + e] = a;
+      }
+    }
+    if (NORM == 1) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) s += y[i];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s * (1.0f / C0);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float d = y[i] - mean;
+        q = fmaf(d, d, q);
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      const float rstd = 1.0f / sqrtf(q * (1.0f / C0) + eps);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = 2 * lane + 64 * i + e;
+          y[2 * i + e] = fmaf((y[2 * i + e] - mean) * rstd, gamma[c], beta[c]);
+        }
+    }
+    uint32_t* o = reinterpret_cast<uint32_t*>(out3 + (static_cast<long long>(b) * T0 + t) * 3 * C0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float g0 = gelu_erf(y[2 * i]), g1 = gelu_erf(y[2 * i + 1]);
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(g0), h1 = __float2bfloat16_rn(g1);
+      const uint32_t hi = pack_bf16(g0, g1);
+      const uint32_t lo = pack_bf16(g0 - __bfloat162float(h0), g1 - __bfloat162float(h1));
+      const int cp = lane + 32 * i;            // pair index
+      o[cp] = hi;
+      o[C0 / 2 + cp] = lo;
+      o[C0 + cp] = hi;
+    }
+  }
+}
+
 }  // namespace aptai
 
 using namespace aptai;
+
+extern "C" int aptai_conv0_accurate(const float* wav, int B, int64_t L, const float* w, const float* bias,
+                                    const float* gamma, const float* beta, int norm, float eps, void* out_split3,
+                                    int T0, float* stats_ws, void* stream) {
+  if (int rc = check_arch()) return rc;
+  APTAI_REQUIRE(wav && w && out_split3, "conv0_accurate: null pointer");
+  APTAI_REQUIRE(B >= 1 && L >= K0 && T0 == (L - K0) / S0 + 1, "conv0_accurate: bad shape B=%d L=%lld T0=%d", B,
+                (long long)L, T0);
+  APTAI_REQUIRE(norm >= 0 && norm <= 2, "conv0_accurate: norm must be 0, 1 or 2");
+  APTAI_REQUIRE(norm == 0 || (gamma && beta), "conv0_accurate: norm needs gamma and beta");
+  APTAI_REQUIRE(norm != 2 || stats_ws, "conv0_accurate: GroupNorm needs stats_ws");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid((T0 + 63) / 64, B);
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(out_split3);
+  if (norm == 2) {
+    double* mom = reinterpret_cast<double*>(stats_ws);
+    float* affine = reinterpret_cast<float*>(mom + static_cast<size_t>(B) * (K0 + NQ));
+    cudaError_t e = cudaMemsetAsync(mom, 0, sizeof(double) * B * (K0 + NQ), st);
+    if (e != cudaSuccess) {
+      set_error("conv0_accurate: memset: %s", cudaGetErrorString(e));
+      return static_cast<int>(e);
+    }
+    int chunks = (T0 + 256 * 8 - 1) / (256 * 8);
+    if (chunks > 64) chunks = 64;
+    conv0_gn_moments_kernel<<<dim3(chunks, B), 256, 0, st>>>(wav, L, T0, mom);
+    if (int rc = after_launch("conv0_gn_moments")) return rc;
+    conv0_gn_affine_kernel<<<B, C0, 0, st>>>(mom, w, bias, gamma, beta, T0, eps, affine);
+    if (int rc = after_launch("conv0_gn_affine")) return rc;
+    conv0_accurate_kernel<2><<<grid, 256, 0, st>>>(wav, L, T0, w, bias, gamma, beta, affine, eps, out);
+  } else if (norm == 1) {
+    conv0_accurate_kernel<1><<<grid, 256, 0, st>>>(wav, L, T0, w, bias, gamma, beta, nullptr, eps, out);
+  } else {
+    conv0_accurate_kernel<0><<<grid, 256, 0, st>>>(wav, L, T0, w, bias, gamma, beta, nullptr, eps, out);
+  }
+  return after_launch("conv0_accurate");
+}
 
 extern "C" int aptai_conv0_norm_gelu(const float* wav, int B, int64_t L, const float* w, const float* bias,
                                      const float* gamma, const float* beta, int norm, float eps, void* out_bf16,

@@ -58,6 +58,11 @@ class Force_APTAI(nn.Module):
         for param in self.w2v2_pr.parameters():
             param.requires_grad = False
 
+    def set_precision(self, precision: str):
+        """'bf16' (default) or 'f32x3': accuracy mode of the frozen recogniser's encoder (the tail is fp32 already)."""
+        self.w2v2_pr.set_precision(precision)
+        return self
+
     # ---------------------------------------------------------------------------------------------- shared trunk
     @torch.no_grad()
     def _recogniser(self, audio_inputs, audio_lengths, phn_seqs=None):

@@ -71,6 +71,16 @@ PROTOTYPES = {
                                  c_void_p]),
     "aptai_ctc_decode_ref": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                      c_int, c_void_p]),
+    "aptai_split3_bf16": (c_int, [c_void_p, c_i64, c_int, c_i64, c_int, c_float, c_void_p, c_void_p]),
+    "aptai_rowop_split3": (c_int, [c_void_p, c_i64, c_int, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p,
+                                   c_void_p, c_void_p]),
+    "aptai_conv0_accurate": (c_int, [c_void_p, c_int, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float,
+                                     c_void_p, c_int, c_void_p, c_void_p]),
+    "aptai_gelu_add_f32": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),
+    "aptai_cast_pad_split": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "aptai_posconv_fold_split": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                         c_void_p]),
+    "aptai_attention_fwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "aptai_cross_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                           c_void_p, c_void_p]),

@@ -137,9 +137,10 @@ def linear_f32x3(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor])
 def conv_igemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], k: int, stride: int, *,
                ln_gamma: Optional[torch.Tensor] = None, ln_beta: Optional[torch.Tensor] = None,
                eps: float = 1e-5, act: int = 1, out: Optional[torch.Tensor] = None, cta_pair: int = 0,
-               out_pre: Optional[torch.Tensor] = None) -> torch.Tensor:
+               out_pre: Optional[torch.Tensor] = None, out_f32: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Strided conv1d as implicit GEMM.  x bf16 [B,T_in,C] channels-last, w bf16 [N, k*C] (tap-major K), out bf16
-    [B,T_out,N]; epilogue = (+bias) -> (LayerNorm over N, if gamma) -> GELU."""
+    [B,T_out,N]; epilogue = (+bias) -> (LayerNorm over N, if gamma) -> GELU.  `out_f32` (fp32 [B,T_out,N]) replaces
+    the 16-bit output (accuracy mode)."""
     fmt = _h16(x, "x")
     if _h16(w, "w") != fmt:
         raise TypeError("conv_igemm: x and w must have the same 16-bit dtype")
@@ -147,7 +148,10 @@ def conv_igemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], k
     N = w.shape[0]
     assert w.shape[1] == k * Cc and Cc % 64 == 0
     T_out = (T_in - k) // stride + 1
-    if out is None:
+    if out_f32 is not None:
+        _req(out_f32, F32, "out_f32")
+        assert out_f32.shape == (B, T_out, N)
+    elif out is None:
         out = alloc_rows_bf16(B, T_out, N, x.device, dtype=x.dtype)
     g = GemmArgs()
     g.a = x.data_ptr(); g.a_row_stride = Cc; g.a_seg_stride = T_in * Cc; g.a_rows = T_in; g.a_cols = Cc
@@ -155,13 +159,14 @@ def conv_igemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], k
     g.w = w.data_ptr(); g.N = N; g.block_n = 0; g.segs = B; g.rows_per_seg = T_out
     g.bias = _ptr(bias)
     g.gamma = _ptr(ln_gamma); g.beta = _ptr(ln_beta); g.residual = None
-    g.out_f32 = None; g.out_bf16 = out.data_ptr(); g.ldo = N; g.out_seg_stride = T_out
+    g.out_f32 = _ptr(out_f32); g.out_bf16 = None if out_f32 is not None else out.data_ptr()
+    g.ldo = N; g.out_seg_stride = T_out
     g.seg_valid_rows = None; g.mask_seg_rows = 0; g.act = act; g.ln = 1 if ln_gamma is not None else 0; g.ln_eps = eps
     g.cta_pair = cta_pair; g.half_fmt = fmt
     if out_pre is not None:
         g.out_pre = _req(out_pre, x.dtype, "out_pre").data_ptr()
     gemm_raw(g)
-    return out
+    return out_f32 if out_f32 is not None else out
 
 
 def posconv(x_pad: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], residual: Optional[torch.Tensor],

@@ -222,6 +222,38 @@ int aptai_ctc_decode_ref(const float* logits, int B, int T, int V, const int32_t
                          int32_t* tokens, int32_t* timesteps, int32_t* ntokens, int maxtok, void* stream);
 
 
+/* ================================================================== accuracy mode ("f32x3") ==================
+ * Every contraction of the path as THREE bf16 tensor-core products on hi/lo operand pairs (x = x_hi + x_lo,
+ * w = w_hi + w_lo; x.w ~= x_hi.w_hi + x_lo.w_hi + x_hi.w_lo, ~2^-17 relative), fp32 everywhere else: the mode in
+ * which the north-star tolerances (phoneme argmax >= 99.9 %, CTC-type losses 1e-3) hold against the fp32
+ * reference.  The GEMMs are aptai_gemm_bf16 on operands laid out A' = [hi | lo | hi] (K tripled),
+ * W' = [hi | hi | lo]; these entry points are the streaming kernels around them (csrc/accurate.cu). */
+
+/* fp32 [rows][cols] (row stride ld_in) * scale -> bf16 [rows][3*cols]: [hi|lo|hi] (weight_layout 0) or [hi|hi|lo] */
+int aptai_split3_bf16(const float* x, int64_t rows, int cols, int64_t ld_in, int weight_layout, float scale,
+                      void* out_bf16, void* stream);
+/* per row: (LayerNorm, exact two-pass fp32 statistics; HF:431,600-602,639,645,692,792 and the conv LayerNorms
+ * HF:288-299) -> (erf-GELU) -> fp32 [rows][cols] and / or split bf16 [rows][3*cols].  cols in {512, 768, 1024}. */
+int aptai_rowop_split3(const float* x, int64_t rows, int cols, const float* gamma, const float* beta, float eps,
+                       int norm, int gelu, float* out_f32, void* out_split3, void* stream);
+/* conv layer 0 + norm + GELU (HF:281-323) in fp32 with split bf16 output [B][T0][3*512]; norm as in
+ * aptai_conv0_norm_gelu, stats_ws likewise (GroupNorm only). */
+int aptai_conv0_accurate(const float* wav, int B, int64_t L, const float* w, const float* bias, const float* gamma,
+                         const float* beta, int norm, float eps, void* out_split3, int T0, float* stats_ws,
+                         void* stream);
+/* out = res + gelu(x): tail of the positional conv embedding (HF:360-368 + residual add) */
+int aptai_gelu_add_f32(const float* x, const float* res, int64_t n, float* out, void* stream);
+/* fp32 [segs][rows][cols] -> zero-haloed bf16 hi and lo copies [segs][rows + 2*halo][cols] */
+int aptai_cast_pad_split(const float* x, int segs, int rows, int cols, int halo, void* hi_bf16, void* lo_bf16,
+                         void* stream);
+/* weight-norm fold of the positional conv (HF:336-358) with hi / lo bf16 outputs [H][taps*cpad] */
+int aptai_posconv_fold_split(const float* g, const float* v, int H, int cin, int taps, int cpad, void* w_hi, void* w_lo,
+                             float* norm_ws, void* stream);
+/* softmax(q k^T + key-length mask) v on fp32 operands (HF:500-549): qkv fp32 [B*T][3*heads*64] (q pre-scaled),
+ * ctx fp32 [B*T][heads*64] */
+int aptai_attention_fwd_f32(const float* qkv, float* ctx, const int32_t* key_len, int B, int T, int heads,
+                            void* stream);
+
 /* ================================================================== training step (backward + optimizer) =====
  * The reference trains with torch autograd (train/train_aptai.py:431-443: zero_grad / loss.backward() /
  * optimizer.step()); these entry points are the kernels that autograd would otherwise dispatch for the hot path.

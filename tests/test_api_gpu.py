@@ -173,7 +173,9 @@ def test_saved_activations_are_released_when_the_loss_is_kept(cuda):
         torch.cuda.synchronize()
         mem.append(torch.cuda.memory_allocated())
     assert total.requires_grad
-    assert max(mem[2:]) - min(mem[2:]) < (1 << 20), mem     # flat after the allocator warmed up
+    # flat once the allocator warmed up (the leak this guards against was ~300 MB per step at this size; the live
+    # set alternates by ~1 MB between odd and even steps)
+    assert max(mem[2:]) - min(mem[2:]) < (8 << 20), mem
 
 
 def test_fused_adam_state_dict_round_trip(cuda):

@@ -67,46 +67,64 @@ def test_aptai_state_dict_layout(aptai_large):
     assert len([k for k in sd if k.startswith("wav2vec2.")]) == 422
 
 
-def test_aptai_get_output_vs_reference(aptai_large):
+MODES = ["f32x3", "bf16"]     # accuracy mode: the north-star tolerances literally; default mode: see tests/test_parity_gpu.py
+
+
+def _with_precision(model, mode, fn):
+    model.set_precision(mode)
+    try:
+        return fn()
+    finally:
+        model.set_precision("bf16")
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_aptai_get_output_vs_reference(aptai_large, mode):
     g = golden()
     wav = W.waveforms(1, 32000, None, seed=1234)
-    r = aptai_large.get_aptai_output(wav[0].numpy())
+    r = _with_precision(aptai_large, mode, lambda: aptai_large.get_aptai_output(wav[0].numpy()))
     assert r["phn_fc_probs"].shape == g["g1_probs"].shape == (46, 99, 1)
     tvs = np.stack([np.asarray(r["tvs_pred"][k], dtype=np.float32) for k in TV], -1)
     d = np.abs(tvs - g["g1_tvs"]).max()
     pc = pearson(tvs, g["g1_tvs"])
-    raw, safe, err = _argmax_report(r["phn_fc_logits"], g["g1_logits"], "aptai_single_2s")
-    _report("aptai_single_2s_tv", {"tv_max_abs": float(d), "pearson_min": float(pc.min())})
+    raw, safe, err = _argmax_report(r["phn_fc_logits"], g["g1_logits"], f"aptai_single_2s[{mode}]")
+    _report(f"aptai_single_2s_tv[{mode}]", {"tv_max_abs": float(d), "pearson_min": float(pc.min())})
     assert d <= 1e-2, f"TV max-abs {d}"
     assert pc.min() >= 0.999, f"Pearson {pc.min()}"
     assert safe == 1.0
-    assert raw >= 0.95, raw            # north star 99.9 %: random-init near-tie frames, see DESIGN.md "Parity"
+    # north star: >= 99.9 % (literal in the accuracy mode; the default mode flips near-tie frames of the untrained
+    # head: full agreement is asserted above on every frame whose margin exceeds 4x the logit error)
+    assert raw >= (0.999 if mode == "f32x3" else 0.97), raw
     np.testing.assert_allclose(r["phn_fc_probs"][:, :, 0].T, torch.softmax(torch.from_numpy(r["phn_fc_logits"]), -1),
                                atol=1e-6)
 
 
-def test_aptai_forward_vs_reference(aptai_large, cuda):
+@pytest.mark.parametrize("mode", MODES)
+def test_aptai_forward_vs_reference(aptai_large, cuda, mode):
     g = golden()
     lens = [32000, 24000]
     wav = W.waveforms(2, 32000, lens, seed=2234).to(cuda)
     tvt = torch.from_numpy(g["g2_tvt"]).to(cuda)
-    out = aptai_large(0, wav, torch.tensor(lens, device=cuda), torch.from_numpy(g["g2_phn"]).to(cuda),
-                      *[tvt[:, :, i].contiguous() for i in range(9)])
+    out = _with_precision(aptai_large, mode, lambda: aptai_large(
+        0, wav, torch.tensor(lens, device=cuda), torch.from_numpy(g["g2_phn"]).to(cuda),
+        *[tvt[:, :, i].contiguous() for i in range(9)]))
     tvs = out["tvs_pred"].cpu().numpy()
     # valid frames only: frames beyond an utterance's length are masked out by every consumer of the reference
     # (tv_pad_mask, models/aptai.py:72,89-93); the all-frames figure is reported for information
     d_valid = max(float(np.abs(tvs[b, :n] - g["g2_tvs"][b, :n]).max()) for b, n in enumerate([99, 74]))
-    _report("aptai_forward_b2_tv", {"tv_max_abs_valid_frames": d_valid,
+    _report(f"aptai_forward_b2_tv[{mode}]", {"tv_max_abs_valid_frames": d_valid,
                                     "tv_max_abs_all_frames": float(np.abs(tvs - g["g2_tvs"]).max())})
     assert d_valid <= 1e-2, d_valid
     for b, n in enumerate([99, 74]):
         assert pearson(tvs[b, :n], g["g2_tvs"][b, :n]).min() >= 0.999
     losses = np.asarray([float(out["loss"]), float(out["mse_loss"]), float(out["ce_loss"])])
-    np.testing.assert_allclose(losses, g["g2_losses"], rtol=5e-3)
-    agree = float((out["phn_fc_pred"].cpu().numpy() == g["g2_pred"]).mean())
-    _report("aptai_forward_b2", {"argmax_agreement_raw": agree, "losses": losses.tolist(),
-                                 "ref_losses": g["g2_losses"].tolist()})
-    assert agree >= 0.95
+    np.testing.assert_allclose(losses, g["g2_losses"], rtol=1e-3 if mode == "f32x3" else 5e-3)
+    valid = np.zeros((2, 99), dtype=bool)
+    valid[0, :99] = valid[1, :74] = True
+    agree = float((out["phn_fc_pred"].cpu().numpy() == g["g2_pred"])[valid].mean())
+    _report(f"aptai_forward_b2[{mode}]", {"argmax_agreement_raw_valid_frames": agree, "losses": losses.tolist(),
+                                          "ref_losses": g["g2_losses"].tolist()})
+    assert agree >= (0.999 if mode == "f32x3" else 0.97), agree
 
 
 @pytest.fixture(scope="module")
@@ -148,17 +166,19 @@ def test_pr_forward_ctc_vs_reference(pr_base, cuda):
     assert np.abs(gl[1, 84:]).max() == 0 and np.abs(gl[2, 49:]).max() == 0   # exactly zero beyond the input length
 
 
-def test_pr_single_c1(pr_base):
-    """BASELINE config 1 shape: one 4 s utterance, base-sized backbone."""
+@pytest.mark.parametrize("mode", MODES)
+def test_pr_single_c1(pr_base, mode):
+    """BASELINE config 1 shape: one 4 s utterance, base-sized backbone ('group' norm, post-LN wiring)."""
     g = golden()
     wav = W.waveforms(1, 64000, None, seed=1234)
-    lg = pr_base.get_ctc_logits(wav[0].numpy())
+    lg = _with_precision(pr_base, mode, lambda: pr_base.get_ctc_logits(wav[0].numpy()))
     assert lg.shape == (199, 46)
-    raw, safe, err = _argmax_report(lg, g["c1_logits"], "pr_base_c1_4s")
-    assert err < 5e-2 and safe == 1.0 and raw >= 0.97
+    raw, safe, err = _argmax_report(lg, g["c1_logits"], f"pr_base_c1_4s[{mode}]")
+    assert err < 5e-2 and safe == 1.0 and raw >= (0.999 if mode == "f32x3" else 0.97), (raw, err)
 
 
-def test_force_aptai_vs_reference(cuda):
+@pytest.mark.parametrize("mode", MODES)
+def test_force_aptai_vs_reference(cuda, mode):
     g = golden()
     cfg = cfg_large()
     name = register_in_memory_checkpoint("mem://large-seed0", backbone_sd(cfg, 0))
@@ -170,7 +190,7 @@ def test_force_aptai_vs_reference(cuda):
     missing, unexpected = fa.load_state_dict(force_tail_state(fa.state_dict()), strict=False)
     assert not unexpected and all(k.startswith("w2v2_pr.") or k in ("pe_phn.pe", "tv_lowpass.lowpass.weight")
                                   for k in missing)
-    fa = fa.to(cuda).eval()
+    fa = fa.to(cuda).eval().set_precision(mode)
     wav = W.waveforms(1, 32000, None, seed=1234)
     known = g["g4_known"]
     al = fa.get_alignment(wav[0].numpy(), phn_seq=known)["alignment"]
@@ -186,10 +206,11 @@ def test_force_aptai_vs_reference(cuda):
     res = fa(0, wav.to(cuda), torch.tensor([32000], device=cuda), None, None,
              *[tvt[:, :, i].contiguous() for i in range(9)], phn_seqs=[known])
     losses = np.asarray([float(res["loss"]), float(res["tv_loss"]), float(res["align_loss"])])
-    _report("force_aptai_single", {"frame_argmax_agreement": agree, "tv_max_abs": d, "losses": losses.tolist(),
-                                   "ref_losses": g["g4_losses"].tolist()})
-    assert d <= 1e-2 and agree >= 0.95
-    np.testing.assert_allclose(losses, g["g4_losses"], rtol=1e-2)
+    _report(f"force_aptai_single[{mode}]", {"frame_argmax_agreement": agree, "tv_max_abs": d,
+                                            "losses": losses.tolist(), "ref_losses": g["g4_losses"].tolist()})
+    assert d <= 1e-2 and agree >= (0.999 if mode == "f32x3" else 0.95)
+    # align_loss is the CTC-based forward-sum loss: the north star's 1e-3 CTC tolerance, literal in the accuracy mode
+    np.testing.assert_allclose(losses, g["g4_losses"], rtol=1e-3 if mode == "f32x3" else 1e-2)
     # additive API: CTC-Viterbi alignment of the known sequence, bit-exact against the oracle on the SAME log-probs
     _, _, logits = pr._logits(wav.to(cuda), torch.tensor([32000], device=cuda))
     from aptai_b200 import ops

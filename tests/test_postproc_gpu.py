@@ -50,7 +50,7 @@ def test_tv_metrics(cuda):
     from scipy.stats import pearsonr
     for i, k in enumerate(NAMES):
         r, pv = pc[k]
-        ref = pearsonr(G["m_gt"][:, i], G["m_pred"][:, i])
+        ref = pearsonr(G["m_gt"][:, i].astype(np.float64), G["m_pred"][:, i].astype(np.float64))
         assert r == pc[k].statistic and pv == pc[k].pvalue
         np.testing.assert_allclose(pv, ref.pvalue, rtol=1e-6, atol=1e-300)
     # batched with lengths
