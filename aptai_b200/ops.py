@@ -248,9 +248,10 @@ def posconv_fold(g: torch.Tensor, v: torch.Tensor, cpad: int = 64, out: Optional
     return w
 
 
-# 0: by shape (attention_tc2.cu's query-tile pairs when an utterance has more than one 128-query tile, else
-# attention_tc.cu's two threads per row), 1 / 2: force one kernel (A/B runs in profiles/attn_bench.py)
+# 0: by shape (attention_v3.cu's query-tile pairs with P in TMEM when an utterance has more than one 128-query tile,
+# else attention_tc.cu's two threads per row), 1 / 2 / 3: force one kernel (A/B runs in profiles/attn_bench.py)
 ATTENTION_IMPL = int(os.environ.get("APTAI_ATTN_IMPL", "0"))
+ATTENTION_POLY8 = int(os.environ.get("APTAI_ATTN_POLY8", "3"))
 
 
 def attention(qkv: torch.Tensor, key_len: Optional[torch.Tensor], B: int, T: int, heads: int,
@@ -272,7 +273,11 @@ def attention(qkv: torch.Tensor, key_len: Optional[torch.Tensor], B: int, T: int
                                                       T, heads, float(drop_p), int(drop_seed) & 0xFFFFFFFFFFFFFFFF,
                                                       _stream()), "attention_fwd_dropout")
         return out
-    which = impl or ATTENTION_IMPL or (2 if T > 128 else 1)
+    which = impl or ATTENTION_IMPL or (3 if T > 128 else 1)
+    if which == 3:
+        check(_lib.load().aptai_attention_fwd_v3(qkv.data_ptr(), out.data_ptr(), _ptr(lse), key_len.data_ptr(), B, T,
+                                                 heads, ATTENTION_POLY8, _stream()), "attention_fwd_v3")
+        return out
     if which == 2:
         check(_lib.load().aptai_attention_fwd_v2(qkv.data_ptr(), out.data_ptr(), _ptr(lse), key_len.data_ptr(), B, T,
                                                  heads, _stream()), "attention_fwd_v2")

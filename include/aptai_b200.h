@@ -118,6 +118,11 @@ int aptai_attention_fwd(const void* qkv, void* ctx, const int32_t* key_len, int 
  * K/V stream and run independent softmax chains (csrc/attention_tc2.cu) */
 int aptai_attention_fwd_v2(const void* qkv, void* ctx, float* lse, const int32_t* key_len, int B, int T, int heads,
                            void* stream);
+/* third-generation kernel, same contract (csrc/attention_v3.cu): P stays in TMEM as the A operand of P V, three S
+ * buffers per query tile, part of the exponentials on the FMA pipe, TMA store of the context tile.
+ * poly8: exponential pairs per 8 evaluated by the polynomial (0, 2, 3, 4; any other value selects the default 3). */
+int aptai_attention_fwd_v3(const void* qkv, void* ctx, float* lse, const int32_t* key_len, int B, int T, int heads,
+                           int poly8, void* stream);
 
 /* ------------------------------------------------------------------ heads and post-processing ---------------
  * APTAI heads (models/aptai.py:43-55,83-86,105-106): tv = tanh(h) W_tv^T + b_tv (9), logits = leaky_relu(h)

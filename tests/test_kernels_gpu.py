@@ -67,16 +67,17 @@ def test_layernorm(cuda, cols, in_bf16):
     torch.testing.assert_close(o16.float(), ref.bfloat16().float(), atol=2e-2, rtol=1e-2)
 
 
-@pytest.mark.parametrize("legacy", [False, "v2"])
+@pytest.mark.parametrize("legacy", [False, "v2", "v3", "v3p0", "v3p4"])
 @pytest.mark.parametrize("B,T,heads,lens,scale", [(2, 199, 16, [199, 150], 1.0), (3, 64, 12, [64, 1, 33], 1.0),
                                                   (1, 999, 4, [999], 1.0), (2, 130, 2, [70, 130], 1.0),
                                                   (40, 399, 16, None, 0.5), (2, 513, 2, [513, 400], 3.0),
-                                                  (3, 257, 2, [257, 256, 129], 1.0), (2, 128, 2, [128, 127], 1.0)])
+                                                  (3, 257, 2, [257, 256, 129], 1.0), (2, 128, 2, [128, 127], 1.0),
+                                                  (24, 600, 16, None, 1.0), (150, 130, 4, None, 1.0)])
 def test_attention(cuda, B, T, heads, lens, scale, legacy):
     H = heads * 64
     qkv = _rand((B * T, 3 * H), cuda, scale, 9).bfloat16()
     if lens is None:
-        lens = [T - (7 * b) % 200 for b in range(B)]
+        lens = [max(1, T - (7 * b) % 200) for b in range(B)]
     if scale > 1.0:
         qkv[T // 2:, H: 2 * H] *= 4.0          # later keys score much higher: exercises the lazy O rescale
     kl = torch.tensor(lens, dtype=torch.int32, device=cuda)
@@ -84,6 +85,17 @@ def test_attention(cuda, B, T, heads, lens, scale, legacy):
     if legacy == "v2":
         lse = torch.empty((B, heads, T), dtype=torch.float32, device=cuda)
         ctx = ops.attention(qkv, kl, B, T, heads, impl=2, lse=lse)
+    elif legacy in ("v3", "v3p0", "v3p4"):
+        # third generation (P in TMEM, polynomial exponentials for 3 / 0 / 4 of every 8 pairs); context buffer
+        # pre-filled so that rows the TMA store must NOT touch (none here: every row < T is written) would show
+        lse = torch.empty((B, heads, T), dtype=torch.float32, device=cuda)
+        old = ops.ATTENTION_POLY8
+        ops.ATTENTION_POLY8 = {"v3": 3, "v3p0": 0, "v3p4": 4}[legacy]
+        try:
+            ctx = ops.attention(qkv, kl, B, T, heads, impl=3, lse=lse,
+                                out=torch.full((B * T, H), float("nan"), dtype=torch.bfloat16, device=cuda))
+        finally:
+            ops.ATTENTION_POLY8 = old
     else:
         ctx = ops.attention(qkv, kl, B, T, heads, impl=1)
     q, k, v = qkv.float().view(B, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
