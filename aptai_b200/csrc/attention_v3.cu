@@ -18,8 +18,10 @@
 //     P), which balances MUFU and issue slots;
 //   * the scores of a row-tile (64 fp32) are held in registers between the max pass and the exp pass (one CTA per SM
 //     leaves 168 registers per thread), so TMEM is read once and there is no stale-maximum redo path;
-//   * O leaves through shared memory and ONE TMA store per query tile (3-D tensor map (channel, frame, utterance):
-//     the box is clipped at the utterance's last frame, no per-row predicate).
+//   * O leaves through shared memory and one TMA store per softmax WARP (3-D tensor map (channel, frame, utterance),
+//     box 64 x 32 rows: clipped at the utterance's last frame, no per-row predicate, no barrier between warps); the
+//     read-out of an item's O is deferred into the first key tile of the next item, where the wait for the item's
+//     last P V hides behind that tile's softmax.
 // Same contract as aptai_attention_fwd_v2: q pre-scaled by head_dim^-0.5, keys >= key_len[b] masked, lazy rescaling
 // of O (threshold 2^8), optional log2-domain lse output for the backward pass.
 #include "common.h"
@@ -48,6 +50,7 @@ struct Attn3Params {
   const int* key_len;
   float* lse;
   int B, T, heads, n_qp, items, per_cta;
+  int idle_ns;              // issuer back-off when nothing is ready (0: poll hot)
 };
 
 // Work items (utterance b, head h, query-tile pair qp) in the order w = (b * heads + h) * n_qp + qp.  CTA c owns the
@@ -356,7 +359,13 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         if (progress) {
           idle = 0;
-        } else if (++idle > (APTAI_SPIN_LIMIT >> 2)) {
+        } else {
+          // nothing ready: sleep instead of polling hot — the issuer shares its scheduler with two softmax warps, and
+          // every group advances at the pace of its slowest warp (three S buffers of look-ahead absorb the delay)
+          if (p.idle_ns > 0) __nanosleep(p.idle_ns);
+          ++idle;
+        }
+        if (idle > (APTAI_SPIN_LIMIT >> 4)) {
           if (lane == 0) printf("aptai attention v3: MMA issuer %d timed out (block %d)\n", t, (int)blockIdx.x);
           __trap();
         }
@@ -371,7 +380,6 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t ts0 = t_lane + t * A3_NBUF * A3_K, to = t_lane + A3_TO + t * A3_D;
     uint8_t* so_tile = sO + t * A3_OB;
     uint8_t* so_row = so_tile + row * 128;
-    const bool wg_leader = (q4 == 0 && lane == 0);
     uint32_t buf = 0, par = 0, it_n = 0;
     const uint64_t l2e = f32x2_pack(A3_LOG2E, A3_LOG2E);
 
@@ -383,11 +391,13 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     float e_m = 0.f, e_l = 1.f;
     bool e_live = false;
     auto epilogue = [&]() {
-      if (wg_leader) tma_store_wait_read<0>();          // the previous store has finished reading sO[t]
-      named_bar_sync(1 + t, 128);
+      // per WARP: its 32 rows go out with its own TMA store (box 64 x 32), so the four warps of a group never wait
+      // for one another here — a group-wide barrier cost 12 % of the softmax warps' time (profiles/r02_attention_v3.md)
       mbar_wait(&o_full[t], it_n & 1);                  // every warp observes every phase (parity stays unambiguous)
       ++it_n;
       if (e_live) {
+        if (lane == 0) tma_store_wait_read<0>();        // this warp's previous store has finished reading its slab
+        __syncwarp();
         tc_fence_after();
         const int qrow = e_q0 + row;
         const float inv = 1.f / e_l;
@@ -407,12 +417,12 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 a3_pack_bf16(__uint_as_float(r[8 * u + 6]) * inv, __uint_as_float(r[8 * u + 7]) * inv));
         }
         tc_fence_before();
-      }
-      fence_async_proxy();
-      named_bar_sync(1 + t, 128);
-      if (wg_leader) {
-        tma_store_3d(&tmO, so_tile, e_h * A3_D, e_q0, e_b);
-        tma_store_commit();
+        fence_async_proxy();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tmO, so_tile + q4 * 32 * 128, e_h * A3_D, e_q0 + q4 * 32, e_b);
+          tma_store_commit();
+        }
       }
       pending = false;
     };
@@ -445,26 +455,29 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         tc_fence_after();
         uint32_t s[64];
-        {
-          uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[0]);
-          uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[32]);
-          tmem_ld32(ts, lo);
-          tmem_ld32(ts + 32, hi);
-          tmem_ld_wait();
-        }
+        uint32_t (&s_lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[0]);
+        uint32_t (&s_hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&s[32]);
+        tmem_ld32(ts, s_lo);
+        tmem_ld32(ts + 32, s_hi);
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+        auto max_pass = [&](int i0, int i1) {
+#pragma unroll
+          for (int i = i0; i < i1; i += 8) {
+            m0 = a3_max3(m0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
+            m1 = a3_max3(m1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
+            m2 = a3_max3(m2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
+            m3 = a3_max3(m3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
+          }
+        };
         const int valid = it.klen - j * A3_K;          // >= 1
-        if (valid < A3_K) {
+        tmem_ld_wait();
+        if (valid >= A3_K) {
+          max_pass(0, 64);
+        } else {
 #pragma unroll
           for (int i = 0; i < 64; ++i)
             if (i >= valid) s[i] = 0xff800000u;        // -inf
-        }
-        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 64; i += 8) {
-          m0 = a3_max3(m0, __uint_as_float(s[i]), __uint_as_float(s[i + 1]));
-          m1 = a3_max3(m1, __uint_as_float(s[i + 2]), __uint_as_float(s[i + 3]));
-          m2 = a3_max3(m2, __uint_as_float(s[i + 4]), __uint_as_float(s[i + 5]));
-          m3 = a3_max3(m3, __uint_as_float(s[i + 6]), __uint_as_float(s[i + 7]));
+          max_pass(0, 64);
         }
         const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * A3_LOG2E;
         float factor = 1.f;
@@ -518,7 +531,7 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       e_b = it.b; e_h = it.h; e_q0 = q0; e_m = m_used; e_l = l; e_live = warp_live;
     }
     if (pending) epilogue();
-    if (wg_leader) tma_store_wait_all<0>();
+    if (lane == 0) tma_store_wait_all<0>();
   }
   tc_fence_before();
   __syncthreads();
@@ -568,7 +581,8 @@ extern "C" int aptai_attention_fwd_v3(const void* qkv, void* ctx, float* lse, co
     if (int rc = encode_tmap_bf16(&tmkv, qkv, 3, dims, strides, boxkv, 1)) return rc;
     uint64_t odims[3] = {static_cast<uint64_t>(H), static_cast<uint64_t>(T), static_cast<uint64_t>(B)};
     uint64_t ostrides[2] = {static_cast<uint64_t>(H) * 2, static_cast<uint64_t>(H) * 2 * T};
-    if (int rc = encode_tmap_bf16(&tmo, ctx, 3, odims, ostrides, boxq, 1)) return rc;
+    uint32_t boxo[3] = {A3_D, 32, 1};          // one store per softmax warp (32 query rows)
+    if (int rc = encode_tmap_bf16(&tmo, ctx, 3, odims, ostrides, boxo, 1)) return rc;
   }
   Attn3Params p;
   p.key_len = key_len;
@@ -578,7 +592,8 @@ extern "C" int aptai_attention_fwd_v3(const void* qkv, void* ctx, float* lse, co
   p.items = B * heads * p.n_qp;
   p.per_cta = (p.items + num_sms() - 1) / num_sms();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  switch (poly8) {
+  p.idle_ns = (poly8 >> 8) & 0xffff;
+  switch (poly8 & 0xff) {
     case 0: return launch_attention_v3<0>(tmq, tmkv, tmo, p, st);
     case 2: return launch_attention_v3<2>(tmq, tmkv, tmo, p, st);
     case 4: return launch_attention_v3<4>(tmq, tmkv, tmo, p, st);
