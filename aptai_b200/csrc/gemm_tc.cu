@@ -94,11 +94,13 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
   float2* ln_part = reinterpret_cast<float2*>(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES);
   float* vecs = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES + C::LN_BYTES + C::STG_BYTES);
 
-  const int warp = threadIdx.x >> 5;
+  // warp index and cluster rank through a shuffle: provably warp-uniform for the compiler, so the single-issuer roles
+  // below keep their loop state, descriptors and addresses in uniform registers (see the MMA role)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   // CTA pair (cta_group::2): rank 0 is the leader and issues every MMA; each CTA owns 128 rows of the 256-row
   // tile (its own TMEM lanes) and stages its own A rows plus half of the B columns.
-  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+  const uint32_t rank = CTA2 ? __shfl_sync(0xffffffffu, cluster_ctarank(), 0) : 0u;
   const int tile0 = CTA2 ? (blockIdx.x >> 1) : blockIdx.x;
   const int tile_step = CTA2 ? (gridDim.x >> 1) : gridDim.x;
   constexpr int TILE_M = BLOCK_M * C::NPAIR;
@@ -129,8 +131,9 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == W_TMA) {
-    // ------------------------------------------------------------------ TMA producer (one thread)
-    if (lane == 0) {
+    // ------------------------------------------------------------------ TMA producer: the whole warp walks the loop
+    // converged, one elected lane issues
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
@@ -139,33 +142,35 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         const int seg = mt / p.m_tiles_per_seg;
         const int r0 = (mt - seg * p.m_tiles_per_seg) * TILE_M + static_cast<int>(rank) * BLOCK_M;
         const int a_col0 = n_blk * p.a_col_per_nblk;
+        int tap = 0, kc = 0;                       // k-block kb = tap * kb_per_tap + kc, advanced by increments
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait_backoff(&empty_bar[stage], phase ^ 1, 64);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
-          const int tap = kb / p.kb_per_tap;
-          const int kc = kb - tap * p.kb_per_tap;
-          const int tq = tap / p.P;
-          if (CTA2) {
-            // both CTAs' bytes are counted on the LEADER's barrier; only the leader arms it
-            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
-            const uint32_t fb = map_to_cta(&full_bar[stage], 0);
-            tma_load_4d_cg2(&tmA, fb, sa, kc * BLOCK_K + a_col0, tap - tq * p.P, r0 + tq, seg);
+          const int tq = p.P == 1 ? tap : tap / p.P;
+          if (elect_one()) {
+            if (CTA2) {
+              // both CTAs' bytes are counted on the LEADER's barrier; only the leader arms it
+              if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+              const uint32_t fb = map_to_cta(&full_bar[stage], 0);
+              tma_load_4d_cg2(&tmA, fb, sa, kc * BLOCK_K + a_col0, tap - tq * p.P, r0 + tq, seg);
 #pragma unroll
-            for (int nh = 0; nh < BN / C::UN; ++nh)
-              tma_load_2d_cg2(&tmB, fb, sb + nh * C::B_ROWS * BLOCK_K * 2, kb * BLOCK_K,
-                              n_blk * BN + nh * C::UN + static_cast<int>(rank) * C::B_ROWS);
-            if (++stage == C::STAGES) {
-              stage = 0;
-              phase ^= 1;
+              for (int nh = 0; nh < BN / C::UN; ++nh)
+                tma_load_2d_cg2(&tmB, fb, sb + nh * C::B_ROWS * BLOCK_K * 2, kb * BLOCK_K,
+                                n_blk * BN + nh * C::UN + static_cast<int>(rank) * C::B_ROWS);
+            } else {
+              mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+              tma_load_4d(&tmA, &full_bar[stage], sa, kc * BLOCK_K + a_col0, tap - tq * p.P, r0 + tq, seg);
+#pragma unroll
+              for (int nh = 0; nh < BN / C::UN; ++nh)
+                tma_load_2d(&tmB, &full_bar[stage], sb + nh * C::UN * BLOCK_K * 2, kb * BLOCK_K, n_blk * BN + nh * C::UN);
             }
-            continue;
           }
-          mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-          tma_load_4d(&tmA, &full_bar[stage], sa, kc * BLOCK_K + a_col0, tap - tq * p.P, r0 + tq, seg);
-#pragma unroll
-          for (int nh = 0; nh < BN / C::UN; ++nh)
-            tma_load_2d(&tmB, &full_bar[stage], sb + nh * C::UN * BLOCK_K * 2, kb * BLOCK_K, n_blk * BN + nh * C::UN);
+          __syncwarp();
+          if (++kc == p.kb_per_tap) {
+            kc = 0;
+            ++tap;
+          }
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
@@ -174,13 +179,18 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       }
     }
   } else if (warp == W_MMA) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0 && rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer: whole warp converged, one
+    // elected lane issues.  Under `if (lane == 0)` every tcgen05.mma cost ~21 SASS instructions (operands moved from
+    // per-thread to uniform registers through an R2UR.BROADCAST + ELECT + BRA.U.ANY loop): ~500 issue cycles per
+    // k-block against 512 cycles of tensor work for the 256x256x64 pair tile — the issuing thread was co-critical
+    // with the tensor pipe.  With warp-uniform control flow the loop state lives in uniform registers.
+    if (rank == 0) {
       const uint32_t IDESC = p.fp16 ? umma_idesc_f16(TILE_M, C::UN) : umma_idesc_bf16(TILE_M, C::UN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const uint32_t smem_base = smem_u32(smem);
       for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -188,28 +198,35 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t a_base = smem_base + stage * C::STAGE_BYTES;
           const uint32_t b_base = a_base + C::A_BYTES;
+          if (elect_one()) {
+            const uint64_t adesc0 = umma_desc_sw128(a_base);
+            const uint64_t bdesc0 = umma_desc_sw128(b_base);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t adesc = umma_desc_sw128(a_base + k * UMMA_K * 2);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
 #pragma unroll
-            for (int nh = 0; nh < BN / C::UN; ++nh) {
-              const uint64_t bdesc = umma_desc_sw128(b_base + nh * C::B_ROWS * BLOCK_K * 2 + k * UMMA_K * 2);
-              if (CTA2) umma_bf16_cg2(d_tmem + nh * C::UN, adesc, bdesc, IDESC, (kb | k) != 0 ? 1u : 0u);
-              else umma_bf16(d_tmem + nh * C::UN, adesc, bdesc, IDESC, (kb | k) != 0 ? 1u : 0u);
+              for (int nh = 0; nh < BN / C::UN; ++nh) {
+                const uint64_t adesc = adesc0 + (k * UMMA_K * 2 >> 4);
+                const uint64_t bdesc = bdesc0 + ((nh * C::B_ROWS * BLOCK_K * 2 + k * UMMA_K * 2) >> 4);
+                if (CTA2) umma_bf16_cg2(d_tmem + nh * C::UN, adesc, bdesc, IDESC, (kb | k) != 0 ? 1u : 0u);
+                else umma_bf16(d_tmem + nh * C::UN, adesc, bdesc, IDESC, (kb | k) != 0 ? 1u : 0u);
+              }
+            }
+            // smem slot reusable (in both CTAs of the pair) once these MMAs have read it
+            if (CTA2) umma_commit_cg2(&empty_bar[stage], 0x3);
+            else umma_commit(&empty_bar[stage]);
+            if (kb == p.num_kb - 1) {              // accumulator complete -> epilogue warps (of both CTAs)
+              if (CTA2) umma_commit_cg2(&tfull_bar[acc], 0x3);
+              else umma_commit(&tfull_bar[acc]);
             }
           }
-          // smem slot reusable (in both CTAs of the pair) once these MMAs have read it
-          if (CTA2) umma_commit_cg2(&empty_bar[stage], 0x3);
-          else umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == C::STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        if (CTA2) umma_commit_cg2(&tfull_bar[acc], 0x3);   // accumulator complete -> epilogue warps of both CTAs
-        else umma_commit(&tfull_bar[acc]);
         if (C::ACC_STAGES == 2) {
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
