@@ -204,7 +204,7 @@ conv0_kernel(const float* __restrict__ wav, long long L, int T0, const float* __
     }
     float y0, y1;
     f32x2_unpack(y, y0, y1);
-    gelu_erf2(y0, y1);
+    gelu_fast2(y0, y1);                  // 16-bit output: see gelu_fast2 (ptx.cuh)
     o[static_cast<long long>(f) * (C0 / 2)] = pack_h16(y0, y1, out_fp16);
   }
 }

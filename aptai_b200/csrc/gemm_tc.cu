@@ -43,6 +43,7 @@ struct GemmParams {
   int fp16;   // operands and the 16-bit output are IEEE fp16 instead of bf16
   const __nv_bfloat16* aux;   // act == 2: pre-activation u saved by the forward pass; out = acc * gelu'(u)
   __nv_bfloat16* out_pre;     // optional second 16-bit output: the value BEFORE the activation (training forward)
+  int tma16;                  // the single 16-bit output leaves through shared memory + TMA stores (tensor map tmC)
 };
 
 template <int BN, bool CTA2>
@@ -68,7 +69,16 @@ struct GemmCfg {
   // (their per-element global loads were the top long-scoreboard stall of that epilogue: 27 % of the stall samples,
   // profiles/r01_gemm_convln.md).  The other tiles have no shared memory left for it (4 stages + 32 KB staging).
   static constexpr int VEC_BYTES = BN >= 512 ? 3 * 512 * 4 : 0;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BAR_BYTES + LN_BYTES + STG_BYTES + VEC_BYTES;
+  // bias of the current N tile, double buffered by tile parity (the per-chunk __ldg of the bias was the top
+  // long-scoreboard stall of the FFN1 epilogue: 18 % of the epilogue warps' samples, profiles/r02_gemm_ffn.md)
+  static constexpr int BIAS_BYTES = (BN % 64 == 0 && BN < 512) ? 2 * BN * 4 : 0;
+  // layout: [stages | staging (1024-aligned: it is the source of SWIZZLE_128B TMA stores) | barriers | LN | vectors]
+  static constexpr int OFF_STG = STAGES * STAGE_BYTES;
+  static constexpr int OFF_BAR = OFF_STG + STG_BYTES;
+  static constexpr int OFF_LN = OFF_BAR + BAR_BYTES;
+  static constexpr int OFF_VEC = OFF_LN + LN_BYTES;
+  static constexpr int OFF_BIAS = OFF_VEC + VEC_BYTES;
+  static constexpr int SMEM_BYTES = OFF_BIAS + BIAS_BYTES;
 };
 
 template <int CH>
@@ -79,20 +89,24 @@ template <>
 __device__ __forceinline__ void tmem_ld_chunk<8>(uint32_t taddr, uint32_t (&r)[8]) { tmem_ld8(taddr, r); }
 
 template <int BN, bool LN, bool CTA2>
-__device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p) {
+__device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                                          const GemmParams& p) {
   using C = GemmCfg<BN, CTA2>;
-  extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment by POINTER arithmetic on the __shared__ array: going through an integer would make the
-  // compiler lose the address space and emit generic ST.E / LD.E for the epilogue's staging buffer (measured:
-  // long-scoreboard stalls on every staging access, profiles/r01_gemm_2cta_outproj_m75776.md)
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  // the dynamic shared memory window starts 1024-byte aligned (no static shared memory in this kernel); checked, not
+  // padded: the CTA-pair tile uses all but 768 bytes of the 227 KB
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("aptai gemm: dynamic shared memory base is not 1024-byte aligned\n");
+    __trap();
+  }
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
   uint64_t* empty_bar = full_bar + C::STAGES;
   uint64_t* tfull_bar = empty_bar + C::STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  float2* ln_part = reinterpret_cast<float2*>(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES);
-  float* vecs = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES + C::LN_BYTES + C::STG_BYTES);
+  float2* ln_part = reinterpret_cast<float2*>(smem + C::OFF_LN);
+  float* vecs = reinterpret_cast<float*>(smem + C::OFF_VEC);
+  float* bias_s = reinterpret_cast<float*>(smem + C::OFF_BIAS);
 
   // warp index and cluster rank through a shuffle: provably warp-uniform for the compiler, so the single-issuer roles
   // below keep their loop state, descriptors and addresses in uniform registers (see the MMA role)
@@ -108,6 +122,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
   if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma16) tma_prefetch_desc(&tmC);
   }
   if (warp == W_MMA && lane == 0) {
     for (int i = 0; i < C::STAGES; ++i) {
@@ -254,11 +269,21 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       named_bar_sync(1, EPI_THREADS);
     }
 
-    for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
+    uint32_t tpar = 0;                       // tile parity: bias buffer of this tile
+    for (int tile = tile0; tile < p.num_tiles; tile += tile_step, tpar ^= 1) {
       const int n_blk = tile % p.n_tiles;
       const int mt = tile / p.n_tiles;
       const int seg = mt / p.m_tiles_per_seg;
       const int row_in_tile = q * 32 + lane;
+      const float* bias_t = bias_s + tpar * BN;
+      if constexpr (C::BIAS_BYTES > 0) {
+        // this tile's bias -> shared memory, before the accumulator is awaited.  Double buffered: the barrier below
+        // keeps the eight warps within one tile of each other, so nobody still reads the buffer being refilled.
+        if (p.bias != nullptr) {
+          if (static_cast<int>(threadIdx.x) < BN) bias_s[tpar * BN + threadIdx.x] = __ldg(p.bias + n_blk * BN + threadIdx.x);
+          named_bar_sync(1, EPI_THREADS);
+        }
+      }
       const int r = (mt - seg * p.m_tiles_per_seg) * TILE_M + static_cast<int>(rank) * BLOCK_M + row_in_tile;
       const bool valid_row = r < p.rows_per_seg;
       const long long out_row = static_cast<long long>(seg) * p.out_seg_stride + r;
@@ -356,10 +381,18 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
             v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
           }
         } else if (p.bias) {
+          if constexpr (C::BIAS_BYTES > 0) {
 #pragma unroll
-          for (int i = 0; i < CH; i += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
-            v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+            for (int i = 0; i < CH; i += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_t + c + i);
+              v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < CH; i += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + i));
+              v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+            }
           }
         }
         if (LN) {
@@ -376,8 +409,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         if constexpr (!LN && CH == 32) {
           // ---- coalesced path: transpose through a warp-private, XOR-swizzled 4 KB buffer so that every global
           // access covers whole 128-byte (fp32) / 64-byte (bf16) row segments instead of 32 different rows
-          float* stg = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES + C::LN_BYTES) +
-                       warp * 1024;
+          float* stg = reinterpret_cast<float*>(smem + C::OFF_STG) + warp * 1024;
           const int r_first = r - lane;                                  // first row of this warp's 32-row group
           const long long off0 = out_off - static_cast<long long>(lane) * p.ldo + n0;
           const int lrow = lane >> 3, lunit = lane & 7;
@@ -400,10 +432,48 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
             }
             __syncwarp();
           };
+          if (p.tma16) {
+            // ---- single 16-bit output (QKV, FFN1, conv-free projections): two 32-column chunks fill one 32-row x
+            // 128-byte slab of the warp's staging buffer in the SWIZZLE_128B pattern, then ONE TMA store writes it
+            // (clipped at the segment's last row by the tensor map: no per-row predicate, no LDS / STG round trip)
+            if (p.act == 1) {
+#pragma unroll
+              for (int i = 0; i < CH; i += 2) gelu_fast2(v[i], v[i + 1]);
+            }
+            if (zero_row) {
+#pragma unroll
+              for (int i = 0; i < CH; ++i) v[i] = 0.f;
+            }
+            const int hsel = (c >> 5) & 1;                 // which half of the 128-byte row this chunk fills
+            if (hsel == 0) {
+              if (lane == 0) tma_store_wait_read<0>();     // the slab's previous store has been read out
+              __syncwarp();
+            }
+            uint4* sb = reinterpret_cast<uint4*>(stg);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              sb[lane * 8 + ((hsel * 4 + u) ^ (lane & 7))] =
+                  make_uint4(pack_h16(v[8 * u], v[8 * u + 1], p.fp16), pack_h16(v[8 * u + 2], v[8 * u + 3], p.fp16),
+                             pack_h16(v[8 * u + 4], v[8 * u + 5], p.fp16), pack_h16(v[8 * u + 6], v[8 * u + 7], p.fp16));
+            if (hsel == 1) {
+              fence_async_proxy();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_3d(&tmC, stg, n0 - 32, r_first, seg);
+                tma_store_commit();
+              }
+            }
+            continue;
+          }
           if (p.out_pre) store16(p.out_pre);
           if (p.act == 1) {
+            if (p.out_f32 == nullptr) {            // result only leaves in 16 bits: the cheap form (see gelu_fast2)
 #pragma unroll
-            for (int i = 0; i < CH; i += 2) gelu_erf2(v[i], v[i + 1]);
+              for (int i = 0; i < CH; i += 2) gelu_fast2(v[i], v[i + 1]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < CH; i += 2) gelu_erf2(v[i], v[i + 1]);
+            }
           } else if (p.act == 2) {
             // dgrad through the GELU: v *= gelu'(u), u = the forward's pre-activation (bf16).  The 32x32 block of u is
             // fetched as whole 64-byte row segments (4 lanes per row, 8 rows per instruction) and transposed through
@@ -485,8 +555,13 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
                                    pack_h16(v[i + 4], v[i + 5], p.fp16), pack_h16(v[i + 6], v[i + 7], p.fp16));
         }
         if (p.act == 1) {
+          if (p.out_f32 == nullptr) {
 #pragma unroll
-          for (int i = 0; i < CH; i += 2) gelu_erf2(v[i], v[i + 1]);
+            for (int i = 0; i < CH; i += 2) gelu_fast2(v[i], v[i + 1]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < CH; i += 2) gelu_erf2(v[i], v[i + 1]);
+          }
         }
         if (valid_row) {
           if (p.residual) {
@@ -532,6 +607,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
     }
   }
 
+  if (warp < EPI_WARPS && lane == 0 && p.tma16) tma_store_wait_all<0>();   // shared memory stays valid until read
   tc_fence_before();
   if (CTA2) cluster_sync_all();
   else __syncthreads();
@@ -545,20 +621,21 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
 template <int BN, bool LN>
 __global__ void __launch_bounds__(GEMM_THREADS, (GemmCfg<BN, false>::CTAS_PER_SM))
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                         const GemmParams p) {
-  gemm_body<BN, LN, false>(tmA, tmB, p);
+                         const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+  gemm_body<BN, LN, false>(tmA, tmB, tmC, p);
 }
 
 // CTA-pair variant: cluster of 2, tcgen05.mma.cta_group::2 (M = 256), half of B per CTA
 template <int BN, bool LN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                              const GemmParams p) {
-  gemm_body<BN, LN, true>(tmA, tmB, p);
+                              const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+  gemm_body<BN, LN, true>(tmA, tmB, tmC, p);
 }
 
 template <int BN, bool LN>
-static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
+                            cudaStream_t st) {
   using C = GemmCfg<BN, true>;
   auto kern = gemm_bf16_tcgen05_2cta_kernel<BN, LN>;
   static bool attr_set = false;
@@ -572,12 +649,13 @@ static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const 
   }
   int clusters = num_sms() / 2;
   if (p.num_tiles < clusters) clusters = p.num_tiles;
-  kern<<<2 * clusters, GEMM_THREADS, C::SMEM_BYTES, st>>>(ta, tb, p);
+  kern<<<2 * clusters, GEMM_THREADS, C::SMEM_BYTES, st>>>(ta, tb, tc, p);
   return after_launch("gemm_bf16_tcgen05_2cta");
 }
 
 template <int BN, bool LN>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
+                       cudaStream_t st) {
   using C = GemmCfg<BN, false>;
   auto kern = gemm_bf16_tcgen05_kernel<BN, LN>;
   static bool attr_set = false;
@@ -591,7 +669,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   }
   const int slots = num_sms() * C::CTAS_PER_SM;
   int grid = p.num_tiles < slots ? p.num_tiles : slots;
-  kern<<<grid, GEMM_THREADS, C::SMEM_BYTES, st>>>(ta, tb, p);
+  kern<<<grid, GEMM_THREADS, C::SMEM_BYTES, st>>>(ta, tb, tc, p);
   return after_launch("gemm_bf16_tcgen05");
 }
 
@@ -653,7 +731,20 @@ extern "C" int aptai_gemm_bf16(const aptai_gemm_args* g, void* stream) {
     uint32_t box[2] = {BLOCK_K, static_cast<uint32_t>((bn > 256 ? 256 : bn) / (pair ? 2 : 1))};
     if (int rc = encode_tmap_bf16(&tb, g->w, 2, dims, strides, box, 1)) return rc;
   }
+  // single 16-bit output without residual / second output: staged in shared memory and written by TMA stores
+  const bool tma16 = !g->ln && bn >= 128 && g->out_bf16 != nullptr && g->out_f32 == nullptr && g->out_pre == nullptr &&
+                     g->residual == nullptr && g->act != 2 && (reinterpret_cast<uintptr_t>(g->out_bf16) & 15) == 0;
+  CUtensorMap tc = ta;
+  if (tma16) {
+    uint64_t dims[3] = {static_cast<uint64_t>(g->N), static_cast<uint64_t>(g->rows_per_seg),
+                        static_cast<uint64_t>(g->segs)};
+    uint64_t strides[2] = {static_cast<uint64_t>(g->ldo) * 2,
+                           static_cast<uint64_t>(g->segs > 1 ? g->out_seg_stride : g->rows_per_seg) * g->ldo * 2};
+    uint32_t box[3] = {64, 32, 1};
+    if (int rc = encode_tmap_bf16(&tc, g->out_bf16, 3, dims, strides, box, 1)) return rc;
+  }
   GemmParams p;
+  p.tma16 = tma16 ? 1 : 0;
   p.num_kb = g->taps * g->kb_per_tap;
   p.kb_per_tap = g->kb_per_tap;
   p.P = g->P;
@@ -679,12 +770,12 @@ extern "C" int aptai_gemm_bf16(const aptai_gemm_args* g, void* stream) {
   p.aux = reinterpret_cast<const __nv_bfloat16*>(g->aux);
   p.out_pre = reinterpret_cast<__nv_bfloat16*>(g->out_pre);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (g->ln) return pair ? launch_gemm_2cta<512, true>(ta, tb, p, st) : launch_gemm<512, true>(ta, tb, p, st);
+  if (g->ln) return pair ? launch_gemm_2cta<512, true>(ta, tb, tc, p, st) : launch_gemm<512, true>(ta, tb, tc, p, st);
   switch (bn) {
-    case 256: return pair ? launch_gemm_2cta<256, false>(ta, tb, p, st) : launch_gemm<256, false>(ta, tb, p, st);
-    case 128: return launch_gemm<128, false>(ta, tb, p, st);
-    case 64: return launch_gemm<64, false>(ta, tb, p, st);
-    case 48: return launch_gemm<48, false>(ta, tb, p, st);
+    case 256: return pair ? launch_gemm_2cta<256, false>(ta, tb, tc, p, st) : launch_gemm<256, false>(ta, tb, tc, p, st);
+    case 128: return launch_gemm<128, false>(ta, tb, tc, p, st);
+    case 64: return launch_gemm<64, false>(ta, tb, tc, p, st);
+    case 48: return launch_gemm<48, false>(ta, tb, tc, p, st);
   }
   set_error("gemm: unreachable block_n %d", bn);
   return APTAI_ERR_ARG;

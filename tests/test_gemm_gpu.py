@@ -114,3 +114,11 @@ def test_gelu_accuracy(cuda):
     o32, _ = ops.linear(a, w, None, act=1, want_f32=True, want_bf16=False)
     ref = torch.nn.functional.gelu(a.double())
     assert (o32.double() - ref).abs().max().item() < 1e-6
+    # 16-bit outputs take the cheaper sigmoid-of-polynomial form (gelu_fast2, max abs error 2.6e-5 before rounding):
+    # within half a bf16 ulp (2^-8 relative) of the fp64 definition plus that bound, over the whole range incl. |x| >> 8
+    x = torch.cat([torch.linspace(-8, 8, 63 * 512), torch.linspace(-300, 300, 512)]).to(cuda).view(512, 64)
+    a = x.bfloat16()
+    _, o16 = ops.linear(a, w, None, act=1, want_f32=False, want_bf16=True)
+    ref = torch.nn.functional.gelu(a.double())
+    err = (o16.double() - ref).abs()
+    assert bool((err <= ref.abs() * 2.0 ** -8 + 3e-5).all()), float((err - ref.abs() * 2.0 ** -8).max())
