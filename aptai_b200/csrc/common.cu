@@ -72,8 +72,20 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
 
+static int encode_tmap_typed(CUtensorMap* map, CUtensorMapDataType dtype, const void* base, int rank,
+                             const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, int swizzle128);
+
 int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box, int swizzle128) {
+  return encode_tmap_typed(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, base, rank, dims, strides_bytes, box, swizzle128);
+}
+int encode_tmap_f32(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, int swizzle128) {
+  return encode_tmap_typed(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, base, rank, dims, strides_bytes, box, swizzle128);
+}
+
+static int encode_tmap_typed(CUtensorMap* map, CUtensorMapDataType dtype, const void* base, int rank,
+                             const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, int swizzle128) {
   if (!g_encode) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g_encode) {
@@ -97,7 +109,7 @@ int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_
     es[i] = 1;
   }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-  CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
+  CUresult r = g_encode(map, dtype, static_cast<cuuint32_t>(rank),
                         const_cast<void*>(base), gdim, gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

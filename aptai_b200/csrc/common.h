@@ -19,6 +19,8 @@ int after_launch(const char* what);     // cudaGetLastError -> status (+ launch 
 // cuTensorMapEncodeTiled through cudaGetDriverEntryPoint (no link-time libcuda dependency)
 int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box, int swizzle128);
+int encode_tmap_f32(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes /* rank-1 */, const uint32_t* box, int swizzle128);
 
 #define APTAI_REQUIRE(cond, ...)              \
   do {                                        \

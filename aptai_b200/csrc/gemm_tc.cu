@@ -44,6 +44,8 @@ struct GemmParams {
   const __nv_bfloat16* aux;   // act == 2: pre-activation u saved by the forward pass; out = acc * gelu'(u)
   __nv_bfloat16* out_pre;     // optional second 16-bit output: the value BEFORE the activation (training forward)
   int tma16;                  // the single 16-bit output leaves through shared memory + TMA stores (tensor map tmC)
+  int red32;                  // in-place fp32 residual update h += acc + bias as TMA reduce-add stores (tmC, fp32)
+  const float* l2_hint;       // red32: the rows the reduction will touch, prefetched into L2 one tile ahead
 };
 
 template <int BN, bool CTA2>
@@ -122,7 +124,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
   if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (p.tma16) tma_prefetch_desc(&tmC);
+    if (p.tma16 | p.red32) tma_prefetch_desc(&tmC);
   }
   if (warp == W_MMA && lane == 0) {
     for (int i = 0; i < C::STAGES; ++i) {
@@ -295,7 +297,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       const long long out_off = out_row * p.ldo;
       const int n_tile0 = n_blk * BN;
 
-      if (p.residual != nullptr) {
+      const float* resid_hint = p.residual != nullptr ? p.residual : p.l2_hint;
+      if (resid_hint != nullptr) {
         // pull the NEXT tile's residual rows towards L2 while this tile is processed: the fp32 residual stream
         // makes the K=1024 projections memory-bound, and two epilogue warps per scheduler cannot keep enough
         // HBM requests in flight on their own
@@ -305,7 +308,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
           const int nseg = nmt / p.m_tiles_per_seg;
           const int nr = (nmt - nseg * p.m_tiles_per_seg) * TILE_M + static_cast<int>(rank) * BLOCK_M + row_in_tile;
           if (nr < p.rows_per_seg) {
-            const float* np_ = p.residual + (static_cast<long long>(nseg) * p.out_seg_stride + nr) * p.ldo +
+            const float* np_ = resid_hint + (static_cast<long long>(nseg) * p.out_seg_stride + nr) * p.ldo +
                                (nt % p.n_tiles) * BN + half * HALF_N;
 #pragma unroll
             for (int i = 0; i < HALF_N * 4 / 128; ++i)
@@ -432,6 +435,23 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
             }
             __syncwarp();
           };
+          if (p.red32) {
+            // ---- in-place residual update h += acc + bias: the 32-row x 128-byte fp32 slab goes to the staging buffer
+            // and ONE TMA reduce-add store applies it at the L2 — the residual is never loaded into the SM
+            if (lane == 0) tma_store_wait_read<0>();       // the slab's previous store has been read out
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              *reinterpret_cast<float4*>(stg + lane * 32 + ((u ^ (lane & 7)) << 2)) =
+                  make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+            fence_async_proxy();
+            __syncwarp();
+            if (lane == 0) {
+              tma_reduce_add_3d(&tmC, stg, n0, r_first, seg);
+              tma_store_commit();
+            }
+            continue;
+          }
           if (p.tma16) {
             // ---- single 16-bit output (QKV, FFN1, conv-free projections): two 32-column chunks fill one 32-row x
             // 128-byte slab of the warp's staging buffer in the SWIZZLE_128B pattern, then ONE TMA store writes it
@@ -607,7 +627,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
     }
   }
 
-  if (warp < EPI_WARPS && lane == 0 && p.tma16) tma_store_wait_all<0>();   // shared memory stays valid until read
+  if (warp < EPI_WARPS && lane == 0 && (p.tma16 | p.red32)) tma_store_wait_all<0>();   // shared memory stays valid until read
   tc_fence_before();
   if (CTA2) cluster_sync_all();
   else __syncthreads();
@@ -743,8 +763,22 @@ extern "C" int aptai_gemm_bf16(const aptai_gemm_args* g, void* stream) {
     uint32_t box[3] = {64, 32, 1};
     if (int rc = encode_tmap_bf16(&tc, g->out_bf16, 3, dims, strides, box, 1)) return rc;
   }
+  // in-place fp32 residual update (out_f32 == residual, nothing else written): TMA reduce-add stores
+  const bool red32 = !g->ln && bn >= 64 && bn % 64 == 0 && g->out_f32 != nullptr && g->residual == g->out_f32 &&
+                     g->out_bf16 == nullptr && g->out_pre == nullptr && g->act == 0 && g->seg_valid_rows == nullptr &&
+                     (reinterpret_cast<uintptr_t>(g->out_f32) & 15) == 0 && g->ldo % 4 == 0;
+  if (red32) {
+    uint64_t dims[3] = {static_cast<uint64_t>(g->N), static_cast<uint64_t>(g->rows_per_seg),
+                        static_cast<uint64_t>(g->segs)};
+    uint64_t strides[2] = {static_cast<uint64_t>(g->ldo) * 4,
+                           static_cast<uint64_t>(g->segs > 1 ? g->out_seg_stride : g->rows_per_seg) * g->ldo * 4};
+    uint32_t box[3] = {32, 32, 1};
+    if (int rc = encode_tmap_f32(&tc, g->out_f32, 3, dims, strides, box, 1)) return rc;
+  }
   GemmParams p;
   p.tma16 = tma16 ? 1 : 0;
+  p.red32 = red32 ? 1 : 0;
+  p.l2_hint = red32 ? g->out_f32 : nullptr;
   p.num_kb = g->taps * g->kb_per_tap;
   p.kb_per_tap = g->kb_per_tap;
   p.P = g->P;
@@ -757,7 +791,7 @@ extern "C" int aptai_gemm_bf16(const aptai_gemm_args* g, void* stream) {
   p.bias = g->bias;
   p.gamma = g->gamma;
   p.beta = g->beta;
-  p.residual = g->residual;
+  p.residual = red32 ? nullptr : g->residual;
   p.out_f32 = g->out_f32;
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(g->out_bf16);
   p.ldo = g->ldo;
