@@ -93,7 +93,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   uint64_t* dkv_empty = bars + 12;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: provably warp-uniform, so the single-issuer roles (whole warp converged,
+  // elect.sync around the issue) keep loop state and descriptors in uniform registers (see gemm_tc.cu)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   if (warp == AB_W_TMA && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
@@ -121,38 +123,44 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == AB_W_TMA) {
-    if (lane == 0) {
+    {
       uint32_t g = 0, it = 0;
       for (int w = blockIdx.x; w < p.items; w += gridDim.x) {
         const int j = w % p.n_t;
         const int bh = w / p.n_t;
         const int h = bh % p.heads, b = bh / p.heads;
-        const int klen = max(1, min(__ldg(p.key_len + b), p.T));
+        const int klen = __shfl_sync(0xffffffffu, max(1, min(__ldg(p.key_len + b), p.T)), 0);
         if (j * AB_T >= klen) continue;
         const int row0 = b * p.T;
         mbar_wait_backoff(kv_empty, (it & 1) ^ 1, 64);
-        mbar_expect_tx(kv_full, 2 * AB_TILE);
-        tma_load_2d(&tmQKV, kv_full, sK, p.H + h * AB_D, row0 + j * AB_T);
-        tma_load_2d(&tmQKV, kv_full, sV, 2 * p.H + h * AB_D, row0 + j * AB_T);
+        if (elect_one()) {
+          mbar_expect_tx(kv_full, 2 * AB_TILE);
+          tma_load_2d(&tmQKV, kv_full, sK, p.H + h * AB_D, row0 + j * AB_T);
+          tma_load_2d(&tmQKV, kv_full, sV, 2 * p.H + h * AB_D, row0 + j * AB_T);
+        }
+        __syncwarp();
         for (int i = 0; i < p.n_t; ++i, ++g) {
           const uint32_t buf = g & 1;
           mbar_wait_backoff(&qdo_empty[buf], ((g >> 1) & 1) ^ 1, 64);
-          mbar_expect_tx(&qdo_full[buf], 2 * AB_TILE);
-          tma_load_2d(&tmQKV, &qdo_full[buf], sQ + buf * AB_TILE, h * AB_D, row0 + i * AB_T);
-          tma_load_2d(&tmDO, &qdo_full[buf], sDO + buf * AB_TILE, h * AB_D, row0 + i * AB_T);
+          if (elect_one()) {
+            mbar_expect_tx(&qdo_full[buf], 2 * AB_TILE);
+            tma_load_2d(&tmQKV, &qdo_full[buf], sQ + buf * AB_TILE, h * AB_D, row0 + i * AB_T);
+            tma_load_2d(&tmDO, &qdo_full[buf], sDO + buf * AB_TILE, h * AB_D, row0 + i * AB_T);
+          }
+          __syncwarp();
         }
         ++it;
       }
     }
   } else if (warp == AB_W_MMA) {
     // ---------------------------------------------------------------- phase 1: S^T = K Q^T, dP^T = V dO^T
-    if (lane == 0) {
+    {
       constexpr uint32_t ID_S0 = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(AB_T >> 4) << 24);   // K-major
       uint32_t g = 0, it = 0;
       for (int w = blockIdx.x; w < p.items; w += gridDim.x) {
         const int j = w % p.n_t;
         const int b = (w / p.n_t) / p.heads;
-        const int klen = max(1, min(__ldg(p.key_len + b), p.T));
+        const int klen = __shfl_sync(0xffffffffu, max(1, min(__ldg(p.key_len + b), p.T)), 0);
         if (j * AB_T >= klen) continue;
         mbar_wait(kv_full, it & 1);
         const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
@@ -166,22 +174,25 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           // only the queries that exist (rounded up to 16): the last tile of an utterance is mostly padding
           const int nq16 = (min(AB_T, p.T - i * AB_T) + 15) & ~15;
           const uint32_t ID_S = ID_S0 | (static_cast<uint32_t>(nq16 >> 3) << 17);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < AB_D / 16; ++k)
-            umma_bf16(tmem_base + TB_ST, umma_desc_sw128(k_addr + k * 32), umma_desc_sw128(q_addr + k * 32), ID_S,
-                      k != 0 ? 1u : 0u);
+            for (int k = 0; k < AB_D / 16; ++k)
+              umma_bf16(tmem_base + TB_ST, umma_desc_sw128(k_addr + k * 32), umma_desc_sw128(q_addr + k * 32), ID_S,
+                        k != 0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < AB_D / 16; ++k)
-            umma_bf16(tmem_base + TB_DPT, umma_desc_sw128(v_addr + k * 32), umma_desc_sw128(do_addr + k * 32), ID_S,
-                      k != 0 ? 1u : 0u);
-          umma_commit(s_full);
+            for (int k = 0; k < AB_D / 16; ++k)
+              umma_bf16(tmem_base + TB_DPT, umma_desc_sw128(v_addr + k * 32), umma_desc_sw128(do_addr + k * 32), ID_S,
+                        k != 0 ? 1u : 0u);
+            umma_commit(s_full);
+          }
+          __syncwarp();
         }
         ++it;
       }
     }
   } else if (warp == AB_W_DV || warp == AB_W_DK || warp == AB_W_DQ) {
     // ---------------------------------------------------------------- phase 2: dV += P^T dO | dK += dS^T Q | dQ = dS K
-    if (lane == 0) {
+    {
       constexpr uint32_t ID_BASE = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(AB_T >> 4) << 24);
       constexpr uint32_t ID_KV = ID_BASE | (1u << 16) | (static_cast<uint32_t>(AB_D >> 3) << 17);    // N=64, B MN-major
       constexpr uint32_t ID_Q = ID_KV | (1u << 15);                                                   // A MN-major too
@@ -189,7 +200,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
       for (int w = blockIdx.x; w < p.items; w += gridDim.x) {
         const int j = w % p.n_t;
         const int b = (w / p.n_t) / p.heads;
-        const int klen = max(1, min(__ldg(p.key_len + b), p.T));
+        const int klen = __shfl_sync(0xffffffffu, max(1, min(__ldg(p.key_len + b), p.T)), 0);
         if (j * AB_T >= klen) continue;
         mbar_wait(kv_full, it & 1);
         const uint32_t k_addr = smem_u32(sK);
@@ -205,25 +216,28 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_con
           tc_fence_after();
           const int kq = ((min(AB_T, p.T - i * AB_T) + 15) & ~15) / 16;        // 16-query steps that exist
           const int kk = ((min(AB_T, klen - j * AB_T) + 15) & ~15) / 16;       // 16-key steps that exist
-          if (warp == AB_W_DV) {
-            for (int k = 0; k < kq; ++k)
-              umma_bf16(tmem_base + TB_DV, umma_desc_sw128(pt_addr + (k >> 2) * (AB_PT / 2) + (k & 3) * 32),
-                        ab_desc_mn(do_addr + k * 2048, 1024), ID_KV, (i | k) != 0 ? 1u : 0u);
-          } else if (warp == AB_W_DK) {
-            for (int k = 0; k < kq; ++k)
-              umma_bf16(tmem_base + TB_DK, umma_desc_sw128(dst_addr + (k >> 2) * (AB_PT / 2) + (k & 3) * 32),
-                        ab_desc_mn(q_addr + k * 2048, 1024), ID_KV, (i | k) != 0 ? 1u : 0u);
-          } else {
-            for (int k = 0; k < kk; ++k)
-              umma_bf16(tmem_base + TB_DQ, ab_desc_mn(dst_addr + k * 2048, AB_PT / 2),
-                        ab_desc_mn(k_addr + k * 2048, 1024), ID_Q, k != 0 ? 1u : 0u);
-            umma_commit(dq_full);
+          if (elect_one()) {
+            if (warp == AB_W_DV) {
+              for (int k = 0; k < kq; ++k)
+                umma_bf16(tmem_base + TB_DV, umma_desc_sw128(pt_addr + (k >> 2) * (AB_PT / 2) + (k & 3) * 32),
+                          ab_desc_mn(do_addr + k * 2048, 1024), ID_KV, (i | k) != 0 ? 1u : 0u);
+            } else if (warp == AB_W_DK) {
+              for (int k = 0; k < kq; ++k)
+                umma_bf16(tmem_base + TB_DK, umma_desc_sw128(dst_addr + (k >> 2) * (AB_PT / 2) + (k & 3) * 32),
+                          ab_desc_mn(q_addr + k * 2048, 1024), ID_KV, (i | k) != 0 ? 1u : 0u);
+            } else {
+              for (int k = 0; k < kk; ++k)
+                umma_bf16(tmem_base + TB_DQ, ab_desc_mn(dst_addr + k * 2048, AB_PT / 2),
+                          ab_desc_mn(k_addr + k * 2048, 1024), ID_Q, k != 0 ? 1u : 0u);
+              umma_commit(dq_full);
+            }
+            umma_commit(&qdo_empty[buf]);
+            if (i == p.n_t - 1) {
+              if (warp != AB_W_DQ) umma_commit(dkv_full);
+              else umma_commit(kv_empty);        // S^T / dP^T of the last tile completed long before (s_full)
+            }
           }
-          umma_commit(&qdo_empty[buf]);
-          if (i == p.n_t - 1) {
-            if (warp != AB_W_DQ) umma_commit(dkv_full);
-            else umma_commit(kv_empty);        // S^T / dP^T of the last tile completed long before (s_full)
-          }
+          __syncwarp();
         }
         ++it;
       }

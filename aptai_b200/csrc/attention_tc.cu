@@ -85,7 +85,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   float* xch = reinterpret_cast<float*>(smem + ATC_DATA + 256);   // [2 parity][2 halves][128 rows]
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: provably warp-uniform (single-issuer roles: whole warp converged, elect.sync
+  // around the issue, loop state in uniform registers — see gemm_tc.cu)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
   if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
@@ -114,24 +116,30 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   if (warp == W_TMA) {
     // ---------------------------------------------------------------- TMA producer
-    if (lane == 0) {
+    {
       uint32_t g = 0, it = 0;
       for (int w = blockIdx.x; w < p.items; w += gridDim.x, ++it) {
         const int qt = w % p.n_qt;
         const int bh = w / p.n_qt;
         const int h = bh % p.heads, b = bh / p.heads;
-        const int klen = max(1, min(__ldg(p.key_len + b), p.T));
+        const int klen = __shfl_sync(0xffffffffu, max(1, min(__ldg(p.key_len + b), p.T)), 0);
         const int n = (klen + AK - 1) / AK;
         const int row0 = b * p.T;
         mbar_wait_backoff(q_empty, (it & 1) ^ 1, 100);
-        mbar_expect_tx(q_full, Q_BYTES);
-        tma_load_2d(&tmQ, q_full, sQ, h * AD, row0 + qt * AQ);
+        if (elect_one()) {
+          mbar_expect_tx(q_full, Q_BYTES);
+          tma_load_2d(&tmQ, q_full, sQ, h * AD, row0 + qt * AQ);
+        }
+        __syncwarp();
         for (int j = 0; j < n; ++j, ++g) {
           const uint32_t st = g % KV_STAGES, u = g / KV_STAGES;
           mbar_wait_backoff(&kv_empty[st], (u & 1) ^ 1, 100);
-          mbar_expect_tx(&kv_full[st], 2 * KV_BYTES);
-          tma_load_2d(&tmKV, &kv_full[st], sKV + st * 2 * KV_BYTES, p.H + h * AD, row0 + j * AK);
-          tma_load_2d(&tmKV, &kv_full[st], sKV + st * 2 * KV_BYTES + KV_BYTES, 2 * p.H + h * AD, row0 + j * AK);
+          if (elect_one()) {
+            mbar_expect_tx(&kv_full[st], 2 * KV_BYTES);
+            tma_load_2d(&tmKV, &kv_full[st], sKV + st * 2 * KV_BYTES, p.H + h * AD, row0 + j * AK);
+            tma_load_2d(&tmKV, &kv_full[st], sKV + st * 2 * KV_BYTES + KV_BYTES, 2 * p.H + h * AD, row0 + j * AK);
+          }
+          __syncwarp();
         }
       }
     }
@@ -139,13 +147,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // ---------------------------------------------------------------- MMA issuer 1: S_j = Q K_j^T
     // (two issuing threads per CTA: a tcgen05.mma issue costs the thread ~100 cycles but these N=64 MMAs are
     //  only 32 cycles of tensor work, so a single issuer for S and PV was the bottleneck of the tile period)
-    if (lane == 0) {
+    {
       constexpr uint32_t IDESC_BASE = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(AQ >> 4) << 24);
       uint32_t g = 0, it = 0;
       for (int w = blockIdx.x; w < p.items; w += gridDim.x, ++it) {
         const int bh = w / p.n_qt;
         const int b = bh / p.heads;
-        const int klen = max(1, min(__ldg(p.key_len + b), p.T));
+        const int klen = __shfl_sync(0xffffffffu, max(1, min(__ldg(p.key_len + b), p.T)), 0);
         const int n = (klen + AK - 1) / AK;
         mbar_wait(q_full, it & 1);
         const uint32_t q_addr = smem_u32(sQ);
@@ -158,25 +166,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tc_fence_after();
           const uint32_t k_addr = smem_u32(sKV + st * 2 * KV_BYTES);
           const uint32_t idesc = IDESC_BASE | (static_cast<uint32_t>(nj >> 3) << 17);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < AD / 16; ++k)
-            umma_bf16(tmem_base + TM_S + (g & 1) * AK, umma_desc_sw128(q_addr + k * 32),
-                      umma_desc_sw128(k_addr + k * 32), idesc, k != 0 ? 1u : 0u);
-          umma_commit(&s_full[g & 1]);
-          if (j == n - 1) umma_commit(q_empty);           // Q tile no longer needed once the last S is done
+            for (int k = 0; k < AD / 16; ++k)
+              umma_bf16(tmem_base + TM_S + (g & 1) * AK, umma_desc_sw128(q_addr + k * 32),
+                        umma_desc_sw128(k_addr + k * 32), idesc, k != 0 ? 1u : 0u);
+            umma_commit(&s_full[g & 1]);
+            if (j == n - 1) umma_commit(q_empty);           // Q tile no longer needed once the last S is done
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == W_MMA2) {
     // ---------------------------------------------------------------- MMA issuer 2: O += P_j V_j
-    if (lane == 0) {
+    {
       constexpr uint32_t IDESC_PV = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(AQ >> 4) << 24) |
                                     (1u << 16) | (static_cast<uint32_t>(AD >> 3) << 17);   // B MN-major, N=64
       uint32_t g = 0, it = 0;
       for (int w = blockIdx.x; w < p.items; w += gridDim.x, ++it) {
         const int bh = w / p.n_qt;
         const int b = bh / p.heads;
-        const int klen = max(1, min(__ldg(p.key_len + b), p.T));
+        const int klen = __shfl_sync(0xffffffffu, max(1, min(__ldg(p.key_len + b), p.T)), 0);
         const int n = (klen + AK - 1) / AK;
         for (int j = 0; j < n; ++j, ++g) {
           const uint32_t sb = g & 1, st = g % KV_STAGES;
@@ -187,12 +198,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tc_fence_after();
           const uint32_t p_addr = smem_u32(sP + sb * P_BYTES);
           const uint32_t v_addr = smem_u32(sKV + st * 2 * KV_BYTES + KV_BYTES);
-          for (int k = 0; k < nj / 16; ++k)
-            umma_bf16(tmem_base + TM_O, umma_desc_sw128(p_addr + k * 32), umma_desc_sw128_mn(v_addr + k * 2048),
-                      IDESC_PV, (j | k) != 0 ? 1u : 0u);
-          umma_commit(&kv_empty[st]);        // K_j was consumed by S_j, which completed before P_j existed
-          umma_commit(&p_empty[sb]);
-          if (j == n - 1) umma_commit(o_full);
+          if (elect_one()) {
+            for (int k = 0; k < nj / 16; ++k)
+              umma_bf16(tmem_base + TM_O, umma_desc_sw128(p_addr + k * 32), umma_desc_sw128_mn(v_addr + k * 2048),
+                        IDESC_PV, (j | k) != 0 ? 1u : 0u);
+            umma_commit(&kv_empty[st]);        // K_j was consumed by S_j, which completed before P_j existed
+            umma_commit(&p_empty[sb]);
+            if (j == n - 1) umma_commit(o_full);
+          }
+          __syncwarp();
         }
       }
     }

@@ -74,7 +74,9 @@ gemm_tn_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   uint64_t* tfull_bar = empty_bar + TN_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: provably warp-uniform, so the single-issuer roles keep their loop state in
+  // uniform registers (whole warp converged, elect.sync around the issue: see gemm_tc.cu)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
 
   if (warp == TN_W_TMA && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -99,7 +101,7 @@ gemm_tn_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
   const int tiles = p.n_tiles * p.k_tiles;
 
   if (warp == TN_W_TMA) {
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
@@ -116,21 +118,24 @@ gemm_tn_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           mbar_wait_backoff(&empty_bar[stage], phase ^ 1, 64);
           uint8_t* sa = smem + stage * TN_STAGE_BYTES;
           uint8_t* sb = sa + TN_A_BYTES;
-          mbar_expect_tx(&full_bar[stage], TN_STAGE_BYTES);
+          if (elect_one()) {
+            mbar_expect_tx(&full_bar[stage], TN_STAGE_BYTES);
 #pragma unroll
-          for (int j = 0; j < TN_BM / 64; ++j) tma_load_3d(&tmA, &full_bar[stage], sa + j * 8192, a_col + j * 64, m0, seg);
-          if (p.conv_P > 0) {
-            // output frame m of the conv reads input row m * P + tap: parity = tap % P, row / P = m + tap / P
-            const int tap = kt / p.conv_cblks, cb = (kt - tap * p.conv_cblks) * TN_BN;
+            for (int j = 0; j < TN_BM / 64; ++j) tma_load_3d(&tmA, &full_bar[stage], sa + j * 8192, a_col + j * 64, m0, seg);
+            if (p.conv_P > 0) {
+              // output frame m of the conv reads input row m * P + tap: parity = tap % P, row / P = m + tap / P
+              const int tap = kt / p.conv_cblks, cb = (kt - tap * p.conv_cblks) * TN_BN;
 #pragma unroll
-            for (int j = 0; j < TN_BN / 64; ++j)
-              tma_load_4d(&tmB, &full_bar[stage], sb + j * 8192, cb + j * 64, tap % p.conv_P, m0 + tap / p.conv_P, seg);
-          } else {
+              for (int j = 0; j < TN_BN / 64; ++j)
+                tma_load_4d(&tmB, &full_bar[stage], sb + j * 8192, cb + j * 64, tap % p.conv_P, m0 + tap / p.conv_P, seg);
+            } else {
 #pragma unroll
-            for (int j = 0; j < TN_BN / 64; ++j)
-              tma_load_3d(&tmB, &full_bar[stage], sb + j * 8192, b_col + j * p.b_col_box,
-                          m0 + b_row + j * p.b_row_box, seg);
+              for (int j = 0; j < TN_BN / 64; ++j)
+                tma_load_3d(&tmB, &full_bar[stage], sb + j * 8192, b_col + j * p.b_col_box,
+                            m0 + b_row + j * p.b_row_box, seg);
+            }
           }
+          __syncwarp();
           if (++stage == TN_STAGES) {
             stage = 0;
             phase ^= 1;
@@ -139,7 +144,7 @@ gemm_tn_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
       }
     }
   } else if (warp == TN_W_MMA) {
-    if (lane == 0) {
+    {
       // D = f32, A = B = bf16, both MN-major (bits 15, 16), N = 256, M = 128
       constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                                  (static_cast<uint32_t>(TN_BN >> 3) << 17) | (static_cast<uint32_t>(TN_BM >> 4) << 24);
@@ -159,17 +164,22 @@ gemm_tn_wgrad_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + stage * TN_STAGE_BYTES);
           const uint32_t b_base = a_base + TN_A_BYTES;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < TN_BK / 16; ++k)
-            umma_bf16(d_tmem, umma_desc_sw128_mn_blocks(a_base + k * 2048), umma_desc_sw128_mn_blocks(b_base + k * 2048),
-                      IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
-          umma_commit(&empty_bar[stage]);
+            for (int k = 0; k < TN_BK / 16; ++k)
+              umma_bf16(d_tmem, umma_desc_sw128_mn_blocks(a_base + k * 2048),
+                        umma_desc_sw128_mn_blocks(b_base + k * 2048), IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_commit(&empty_bar[stage]);
+            if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);
+          }
+          __syncwarp();
           if (++stage == TN_STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[acc]);
+        if (kb1 <= kb0 && elect_one()) umma_commit(&tfull_bar[acc]);     // empty split: nothing issued, release anyway
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -252,8 +262,8 @@ gemm_tn_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   uint64_t* tfull_bar = empty_bar + TP_STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+  const uint32_t rank = __shfl_sync(0xffffffffu, cluster_ctarank(), 0);
   const int item0 = blockIdx.x >> 1, item_step = gridDim.x >> 1;
 
   if (warp == TN_W_TMA && lane == 0) {
@@ -279,7 +289,7 @@ gemm_tn_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   const int tiles = p.n_tiles * p.k_tiles;
 
   if (warp == TN_W_TMA) {
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int item = item0; item < p.items; item += item_step) {
@@ -294,13 +304,16 @@ gemm_tn_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           mbar_wait_backoff(&empty_bar[stage], phase ^ 1, 64);
           uint8_t* sa = smem + stage * TP_STAGE_BYTES;
           uint8_t* sb = sa + TP_HALF_BYTES;
-          // both CTAs' bytes are counted on the LEADER's barrier; only the leader arms it
-          if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * TP_STAGE_BYTES);
-          const uint32_t fb = map_to_cta(&full_bar[stage], 0);
+          if (elect_one()) {
+            // both CTAs' bytes are counted on the LEADER's barrier; only the leader arms it
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * TP_STAGE_BYTES);
+            const uint32_t fb = map_to_cta(&full_bar[stage], 0);
 #pragma unroll
-          for (int j = 0; j < 2; ++j) tma_load_3d_cg2(&tmA, fb, sa + j * 8192, a_col + j * 64, m0, 0);
+            for (int j = 0; j < 2; ++j) tma_load_3d_cg2(&tmA, fb, sa + j * 8192, a_col + j * 64, m0, 0);
 #pragma unroll
-          for (int j = 0; j < 2; ++j) tma_load_3d_cg2(&tmB, fb, sb + j * 8192, b_col + j * 64, m0, 0);
+            for (int j = 0; j < 2; ++j) tma_load_3d_cg2(&tmB, fb, sb + j * 8192, b_col + j * 64, m0, 0);
+          }
+          __syncwarp();
           if (++stage == TP_STAGES) {
             stage = 0;
             phase ^= 1;
@@ -309,7 +322,7 @@ gemm_tn_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
       }
     }
   } else if (warp == TN_W_MMA) {
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
       // D = f32, A = B = bf16, both MN-major, M = 256 (128 per CTA), N = 256 (128 per CTA)
       constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                                  (static_cast<uint32_t>(256 >> 3) << 17) | (static_cast<uint32_t>(256 >> 4) << 24);
@@ -329,17 +342,22 @@ gemm_tn_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
           tc_fence_after();
           const uint32_t a_base = smem_u32(smem + stage * TP_STAGE_BYTES);
           const uint32_t b_base = a_base + TP_HALF_BYTES;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < TN_BK / 16; ++k)
-            umma_bf16_cg2(d_tmem, umma_desc_sw128_mn_blocks(a_base + k * 2048),
-                          umma_desc_sw128_mn_blocks(b_base + k * 2048), IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
-          umma_commit_cg2(&empty_bar[stage], 0x3);
+            for (int k = 0; k < TN_BK / 16; ++k)
+              umma_bf16_cg2(d_tmem, umma_desc_sw128_mn_blocks(a_base + k * 2048),
+                            umma_desc_sw128_mn_blocks(b_base + k * 2048), IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_commit_cg2(&empty_bar[stage], 0x3);
+            if (kb == kb1 - 1) umma_commit_cg2(&tfull_bar[acc], 0x3);
+          }
+          __syncwarp();
           if (++stage == TP_STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_cg2(&tfull_bar[acc], 0x3);
+        if (kb1 <= kb0 && elect_one()) umma_commit_cg2(&tfull_bar[acc], 0x3);   // empty split: release anyway
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
