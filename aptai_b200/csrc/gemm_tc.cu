@@ -59,14 +59,15 @@ struct GemmCfg {
   // narrow tiles (grouped pos-conv, N = 48/64): the tensor core is fed by ~100-cycle tcgen05.mma issues of only
   // 32 cycles of work each, so two CTAs per SM (two issuing threads) are worth more than a deep ring
   static constexpr int CTAS_PER_SM = (BN <= 64 && !CTA2) ? 2 : 1;
-  static constexpr int STAGES = CTAS_PER_SM == 2 ? 3 : (STAGE_BYTES > 64 * 1024 ? 2 : (STAGE_BYTES > 40 * 1024 ? 4 : 6));
+  // the fused-LayerNorm tile (BN = 512) gives one pipeline stage to the epilogue's TMA-store staging buffers
+  static constexpr int STAGES = CTAS_PER_SM == 2 ? 3 : (STAGE_BYTES > 64 * 1024 ? 2 : (STAGE_BYTES > 40 * 1024 ? (BN >= 512 ? 3 : 4) : 6));
   static constexpr int ACC_STRIDE = BN < 64 ? 64 : BN;
   static constexpr int ACC_STAGES = (2 * ACC_STRIDE <= 512) ? 2 : 1;
   static constexpr int TMEM_COLS = ACC_STAGES * ACC_STRIDE <= 128 ? 128 : (ACC_STAGES * ACC_STRIDE <= 256 ? 256 : 512);
   static constexpr int CHUNK = (BN % 64 == 0) ? 32 : 8;          // columns per tcgen05.ld in the epilogue
   static constexpr int BAR_BYTES = 256;
   static constexpr int LN_BYTES = BN >= 512 ? 2 * 2 * BLOCK_M * sizeof(float2) : 0;   // LN statistics exchange
-  static constexpr int STG_BYTES = BN >= 512 ? 0 : 8 * 4096;     // 4 KB transpose buffer per epilogue warp
+  static constexpr int STG_BYTES = 8 * 4096;                     // 4 KB staging buffer per epilogue warp
   // fused-LayerNorm tile: bias | gamma | beta of the whole 512-wide row live in shared memory, loaded once per CTA
   // (their per-element global loads were the top long-scoreboard stall of that epilogue: 27 % of the stall samples,
   // profiles/r01_gemm_convln.md).  The other tiles have no shared memory left for it (4 stages + 32 KB staging).
@@ -320,37 +321,111 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * C::ACC_STRIDE;
 
-      float mean = 0.f, rstd = 1.f;
-      if (LN) {
-        // pass 1: shifted single-pass statistics of (acc + bias) over this warp's half row, then Chan-combine
-        float pivot = 0.f, s1 = 0.f, s2 = 0.f;
-        for (int c = half * HALF_N; c < (half + 1) * HALF_N; c += CH) {
-          uint32_t regs[CH];
-          tmem_ld_chunk<CH>(t_row + c, regs);
+      if constexpr (LN) {
+        // ---- fused LayerNorm(512) + GELU tile: thread = one row x 256 columns (its half), two passes over TMEM with
+        // the tcgen05.ld of chunk c+1 in flight while chunk c is processed, packed fp32x2 math throughout, the
+        // bias / gamma / beta vectors from shared memory as float4.
+        // pass 1: shifted single-pass statistics of (acc + bias) over this half row, then Chan-combine with the other
+        constexpr int C0 = 0;
+        const int cb = half * HALF_N;
+        uint32_t nx[32];
+        tmem_ld32(t_row + cb, nx);
+        float pivot = 0.f;
+        uint64_t s1a = f32x2_pack(0.f, 0.f), s1b = s1a, s2a = s1a, s2b = s1a, npiv = s1a;
+        for (int c = cb; c < cb + HALF_N; c += 32) {
           tmem_ld_wait();
+          uint32_t r[32];
 #pragma unroll
-          for (int i = 0; i < CH; ++i) {
-            float v = __uint_as_float(regs[i]);
-            v += vecs[c + i];
-            if (c == half * HALF_N && i == 0) pivot = v;
-            const float d = v - pivot;
-            s1 += d;
-            s2 = fmaf(d, d, s2);
+          for (int i = 0; i < 32; ++i) r[i] = nx[i];
+          if (c + 32 < cb + HALF_N) tmem_ld32(t_row + c + 32, nx);
+          if (c == cb) {
+            pivot = __uint_as_float(r[0]) + vecs[cb];
+            npiv = f32x2_pack(-pivot, -pivot);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(vecs + c + i);
+            const uint64_t d0 = f32x2_add(f32x2_add(f32x2_pack(__uint_as_float(r[i]), __uint_as_float(r[i + 1])),
+                                                    f32x2_pack(b4.x, b4.y)), npiv);
+            const uint64_t d1 = f32x2_add(f32x2_add(f32x2_pack(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])),
+                                                    f32x2_pack(b4.z, b4.w)), npiv);
+            s1a = f32x2_add(s1a, d0);
+            s1b = f32x2_add(s1b, d1);
+            s2a = f32x2_fma(d0, d0, s2a);
+            s2b = f32x2_fma(d1, d1, s2b);
           }
         }
+        float s1x, s1y, s2x, s2y;
+        f32x2_unpack(f32x2_add(s1a, s1b), s1x, s1y);
+        f32x2_unpack(f32x2_add(s2a, s2b), s2x, s2y);
+        const float s1 = s1x + s1y, s2 = s2x + s2y;
         const float inv_n = 1.0f / HALF_N;
         const float mean_h = pivot + s1 * inv_n;
         const float m2_h = fmaxf(s2 - s1 * s1 * inv_n, 0.f);
         float2* buf = ln_part + ln_buf * 2 * BLOCK_M;
         buf[half * BLOCK_M + row_in_tile] = make_float2(mean_h, m2_h);
+        tmem_ld32(t_row + cb, nx);                     // first chunk of pass 2, in flight across the exchange
         named_bar_sync(1, EPI_THREADS);
         const float2 o = buf[(half ^ 1) * BLOCK_M + row_in_tile];
         ln_buf ^= 1;
         const float dm = mean_h - o.x;
-        mean = 0.5f * (mean_h + o.x);
+        const float mean = 0.5f * (mean_h + o.x);
         const float var = (m2_h + o.y + dm * dm * (0.5f * HALF_N)) * (1.0f / BN);
-        rstd = rsqrtf(var + p.ln_eps);
-      }
+        const float rstd = rsqrtf(var + p.ln_eps);
+        // pass 2: y = ((acc + bias) * rstd - mean * rstd) * gamma + beta -> GELU -> 16 bits -> staging slab (32 rows x
+        // 128 bytes per pair of chunks, SWIZZLE_128B) -> one TMA store per slab, clipped at the segment's last row
+        const uint64_t rs2 = f32x2_pack(rstd, rstd), nm2 = f32x2_pack(-mean * rstd, -mean * rstd);
+        uint4* sb = reinterpret_cast<uint4*>(smem + C::OFF_STG + warp * 4096);
+        const int r_first = r - lane;
+        for (int c = cb; c < cb + HALF_N; c += 32) {
+          tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(nx[i]);
+          if (c + 32 < cb + HALF_N) tmem_ld32(t_row + c + 32, nx);
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(vecs + c + i);
+            const float4 g4 = *reinterpret_cast<const float4*>(vecs + BN + c + i);
+            const float4 e4 = *reinterpret_cast<const float4*>(vecs + 2 * BN + c + i);
+            uint64_t t0 = f32x2_add(f32x2_pack(v[i], v[i + 1]), f32x2_pack(b4.x, b4.y));
+            uint64_t t1 = f32x2_add(f32x2_pack(v[i + 2], v[i + 3]), f32x2_pack(b4.z, b4.w));
+            t0 = f32x2_fma(f32x2_fma(t0, rs2, nm2), f32x2_pack(g4.x, g4.y), f32x2_pack(e4.x, e4.y));
+            t1 = f32x2_fma(f32x2_fma(t1, rs2, nm2), f32x2_pack(g4.z, g4.w), f32x2_pack(e4.z, e4.w));
+            f32x2_unpack(t0, v[i], v[i + 1]);
+            f32x2_unpack(t1, v[i + 2], v[i + 3]);
+          }
+          if (p.act == 1) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) gelu_fast2(v[i], v[i + 1]);
+          }
+          if (zero_row) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          }
+          const int hsel = (c >> 5) & 1;
+          if (hsel == 0) {
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            sb[lane * 8 + ((hsel * 4 + u) ^ (lane & 7))] =
+                make_uint4(pack_h16(v[8 * u], v[8 * u + 1], p.fp16), pack_h16(v[8 * u + 2], v[8 * u + 3], p.fp16),
+                           pack_h16(v[8 * u + 4], v[8 * u + 5], p.fp16), pack_h16(v[8 * u + 6], v[8 * u + 7], p.fp16));
+          if (hsel == 1) {
+            fence_async_proxy();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&tmC, sb, n_tile0 + c - 32, r_first, seg);
+              tma_store_commit();
+            }
+          }
+        }
+        (void)C0;
+      } else {
+      float mean = 0.f, rstd = 1.f;
+      (void)mean; (void)rstd;
 
       // residual block of the first chunk, requested before the accumulator is even complete (coalesced path)
       float4 res_next[8];
@@ -611,6 +686,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         }
         }
       }
+      }   // !LN
       // all tcgen05.ld of this warp have completed (wait::ld above) -> hand the accumulator back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -724,6 +800,9 @@ extern "C" int aptai_gemm_bf16(const aptai_gemm_args* g, void* stream) {
   APTAI_REQUIRE(g->act != 2 || (g->aux != nullptr && !g->ln && bn % 64 == 0),
                 "gemm: act=2 (GELU dgrad) needs aux and a 64-multiple tile without LayerNorm");
   APTAI_REQUIRE(g->out_pre == nullptr || !g->ln, "gemm: out_pre is not available with the fused LayerNorm");
+  APTAI_REQUIRE(!g->ln || (g->out_bf16 != nullptr && g->out_f32 == nullptr && g->residual == nullptr &&
+                           (reinterpret_cast<uintptr_t>(g->out_bf16) & 15) == 0),
+                "gemm: the fused-LayerNorm tile writes one 16-byte-aligned 16-bit output (TMA stores) and takes no residual");
   const long long K = static_cast<long long>(g->taps) * g->kb_per_tap * BLOCK_K;
 
   // CTA-pair (cta_group::2) tiles halve the B traffic per SM; they need a wide N tile and enough 256-row tiles
@@ -755,7 +834,7 @@ extern "C" int aptai_gemm_bf16(const aptai_gemm_args* g, void* stream) {
   const bool tma16 = !g->ln && bn >= 128 && g->out_bf16 != nullptr && g->out_f32 == nullptr && g->out_pre == nullptr &&
                      g->residual == nullptr && g->act != 2 && (reinterpret_cast<uintptr_t>(g->out_bf16) & 15) == 0;
   CUtensorMap tc = ta;
-  if (tma16) {
+  if (tma16 || g->ln) {
     uint64_t dims[3] = {static_cast<uint64_t>(g->N), static_cast<uint64_t>(g->rows_per_seg),
                         static_cast<uint64_t>(g->segs)};
     uint64_t strides[2] = {static_cast<uint64_t>(g->ldo) * 2,
@@ -776,7 +855,7 @@ extern "C" int aptai_gemm_bf16(const aptai_gemm_args* g, void* stream) {
     if (int rc = encode_tmap_f32(&tc, g->out_f32, 3, dims, strides, box, 1)) return rc;
   }
   GemmParams p;
-  p.tma16 = tma16 ? 1 : 0;
+  p.tma16 = (tma16 || g->ln) ? 1 : 0;
   p.red32 = red32 ? 1 : 0;
   p.l2_hint = red32 ? g->out_f32 : nullptr;
   p.num_kb = g->taps * g->kb_per_tap;
