@@ -316,9 +316,19 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # stdout carries exactly one JSON line: NCCL's banner ("NCCL version ...") goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries exactly one JSON line: NCCL prints its banner ("NCCL version ...") on fd 1 when the
+        # communicator is created, so fd 1 points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     from aptai_b200 import lib, ops
     cfg = W2V2Config.large(**NO_REG)
     lengths, batches = build_workload(cfg, args.utterances, seed=rank, max_rows=args.max_rows)
@@ -630,7 +640,11 @@ def train_leg(cfg, dev, rank, world, args):
         torch.cuda.synchronize()
         err = torch.tensor([float((gb.flat - ref).norm() / ref.norm())], dtype=torch.float64, device=dev)
         dist.all_reduce(err, op=dist.ReduceOp.MAX)
-        check = {"dp_grad_check": "ok" if float(err) < 1e-4 else "FAILED", "rel_err_max_over_ranks": float(err)}
+        # tolerance: the two gradients differ by the order of the fp32 atomics of the split-frame weight-gradient and
+        # dQ reductions, whose results are rounded to bf16 before the next GEMM (observed 1e-4 at this size; a wrong
+        # reduction — a missing rank, SUM instead of AVG — shows as >= 0.3)
+        check = {"dp_grad_check": "ok" if float(err) < 1e-3 else "FAILED", "rel_err_max_over_ranks": float(err),
+                 "dp_grad_check_tolerance": 1e-3}
         del ref
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
