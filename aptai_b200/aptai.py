@@ -93,7 +93,7 @@ class APTAI(nn.Module):
         dev = next(w2v.parameters()).device
         wav = audio_inputs.to(device=dev, dtype=torch.float32).contiguous()
         lens = audio_lengths.reshape(-1).to(device=dev, dtype=torch.int64)
-        flen = w2v._get_feat_extract_output_lengths(lens).to(torch.int32).contiguous()
+        flen = w2v.frame_lengths_i32(lens)
         gb = self.grad_buffer()
         last, sv = w2v.encode_train(wav, flen)
         B, T, H = last.shape
@@ -165,7 +165,7 @@ class APTAI(nn.Module):
         out = {"tvs_pred": tv, "phn_fc_logits": logits, "phn_fc_pred": pred}
         if phn_targets is not None:
             lp = ops.softmax_rows(logits.contiguous(), log=True)
-            flen = self.wav2vec2._get_feat_extract_output_lengths(audio_lengths.reshape(-1)).to(torch.int32).contiguous()
+            flen = self.wav2vec2.frame_lengths_i32(audio_lengths)
             paths, scores, status = ops.ctc_viterbi(lp, phn_targets, flen, phn_target_lens, blank=blank)
             out.update(align_paths=paths, align_scores=scores, align_status=status, log_probs=lp)
         return out

@@ -312,11 +312,23 @@ class Wav2Vec2Backbone(nn.Module):
         self._feature_encoder_frozen = True
 
     def _get_feat_extract_output_lengths(self, input_lengths):
-        """HF:1005-1024 on tensors or ints."""
+        """HF:1005-1024 on tensors or ints.  CUDA tensors go through one kernel launch (csrc/elementwise.cu
+        `frame_lengths_kernel`) instead of three ATen launches per conv layer."""
         n = input_lengths
+        if torch.is_tensor(n) and n.is_cuda and not n.is_floating_point():
+            shape = n.shape
+            o64, _ = ops.frame_lengths(n.reshape(-1).to(torch.int64).contiguous(), self.cfg.conv_kernel,
+                                       self.cfg.conv_stride, want_i32=False)
+            return o64.view(shape).to(n.dtype)
         for k, s in zip(self.cfg.conv_kernel, self.cfg.conv_stride):
             n = torch.div(n - k, s, rounding_mode="floor") + 1 if torch.is_tensor(n) else (n - k) // s + 1
         return n
+
+    def frame_lengths_i32(self, input_lengths: torch.Tensor) -> torch.Tensor:
+        """int32 [B] frame counts (the form every kernel takes) of sample counts on this module's device."""
+        dev = next(self.parameters()).device
+        lens = input_lengths.reshape(-1).to(device=dev, dtype=torch.int64).contiguous()
+        return ops.frame_lengths(lens, self.cfg.conv_kernel, self.cfg.conv_stride, want_i64=False)[1]
 
     # ---- plan ------------------------------------------------------------------------------------------------
     def plan(self, train: bool = False) -> _Plan:
@@ -774,7 +786,7 @@ class Wav2Vec2Backbone(nn.Module):
             am = attention_mask.reshape(B, -1)
             lens = am.sum(-1) if am.shape[1] == L and L > 1 else am[:, -1]
             lens = lens.to(device=wav.device, dtype=torch.int64)
-        flen = self._get_feat_extract_output_lengths(lens).to(I32).contiguous()
+        flen = self.frame_lengths_i32(lens)
         last, hidden, feats = self.encode(wav, flen, collect_hidden=output_hidden_states, want_features=True)
         out = SimpleNamespace(last_hidden_state=last, extract_features=feats, hidden_states=hidden, attentions=None)
         if not return_dict:

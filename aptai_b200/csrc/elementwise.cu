@@ -410,6 +410,46 @@ extern "C" int aptai_lowpass_fir(const float* x, int B, int T, int C, const doub
   return after_launch("lowpass_fir");
 }
 
+namespace aptai {
+// frames per utterance after the conv feature encoder: n <- floor((n - k) / s) + 1 per layer (HF:1005-1024
+// `_get_feat_extract_output_lengths`; floor division as torch.div(..., rounding_mode="floor"), so a too-short input goes
+// negative exactly like the reference).  One launch instead of 3 ATen kernels per conv layer.
+struct ConvGeom {
+  int n, k[8], s[8];
+};
+__global__ void frame_lengths_kernel(const long long* __restrict__ samples, int B, ConvGeom g,
+                                     long long* __restrict__ out64, int* __restrict__ out32) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  long long n = samples[b];
+  for (int i = 0; i < g.n; ++i) {
+    const long long d = n - g.k[i];
+    long long q = d / g.s[i];
+    if ((d % g.s[i] != 0) && ((d < 0) != (g.s[i] < 0))) --q;       // floor
+    n = q + 1;
+  }
+  if (out64) out64[b] = n;
+  if (out32) out32[b] = static_cast<int>(n);
+}
+}  // namespace aptai
+
+extern "C" int aptai_frame_lengths(const int64_t* samples, int B, const int32_t* kernels, const int32_t* strides,
+                                   int n_layers, int64_t* out_i64, int32_t* out_i32, void* stream) {
+  if (int rc = check_arch()) return rc;
+  APTAI_REQUIRE(samples && kernels && strides && (out_i64 || out_i32), "frame_lengths: null pointer");
+  APTAI_REQUIRE(B >= 1 && n_layers >= 1 && n_layers <= 8, "frame_lengths: B >= 1 and 1..8 conv layers");
+  ConvGeom g;
+  g.n = n_layers;
+  for (int i = 0; i < n_layers; ++i) {
+    APTAI_REQUIRE(strides[i] >= 1 && kernels[i] >= 1, "frame_lengths: bad conv geometry");
+    g.k[i] = kernels[i];
+    g.s[i] = strides[i];
+  }
+  frame_lengths_kernel<<<(B + 127) / 128, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const long long*>(samples), B, g, reinterpret_cast<long long*>(out_i64), out_i32);
+  return after_launch("frame_lengths");
+}
+
 extern "C" int aptai_softmax_rows(const float* x, int64_t rows, int V, int log_out, float* y, void* stream) {
   if (int rc = check_arch()) return rc;
   APTAI_REQUIRE(x && y && rows >= 1 && V >= 1, "softmax_rows: bad arguments");

@@ -314,7 +314,7 @@ class Force_APTAI(nn.Module):
             _, _, logits = pr._logits(audio_inputs, audio_lengths)
             log_probs = ops.softmax_rows(logits.contiguous(), log=True)
         B, T, V = log_probs.shape
-        flen = pr.wav2vec2._get_feat_extract_output_lengths(audio_lengths.reshape(-1).to(dev)).to(torch.int32)
+        flen = pr.wav2vec2.frame_lengths_i32(audio_lengths)
         Smax = max(1, max(len(s) for s in phn_seqs))
         tg = np.zeros((B, Smax), dtype=np.int32)
         for b, s in enumerate(phn_seqs):

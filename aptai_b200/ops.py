@@ -229,6 +229,21 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     return out_f32, out_bf16
 
 
+def frame_lengths(samples: torch.Tensor, kernels, strides, want_i64: bool = True, want_i32: bool = True):
+    """Frames per utterance after the conv feature encoder (HF:1005-1024), one launch.  samples: int64 [B] CUDA.
+    Returns (int64 [B] | None, int32 [B] | None)."""
+    _req(samples, torch.int64, "samples")
+    B = samples.numel()
+    nl = len(kernels)
+    ks = (C.c_int32 * nl)(*[int(k) for k in kernels])
+    ss = (C.c_int32 * nl)(*[int(v) for v in strides])
+    o64 = torch.empty((B,), dtype=torch.int64, device=samples.device) if want_i64 else None
+    o32 = torch.empty((B,), dtype=I32, device=samples.device) if want_i32 else None
+    check(_lib.load().aptai_frame_lengths(samples.data_ptr(), B, C.cast(ks, C.c_void_p), C.cast(ss, C.c_void_p), nl,
+                                          _ptr(o64), _ptr(o32), _stream()), "frame_lengths")
+    return o64, o32
+
+
 def cast_pad(x: torch.Tensor, halo: int) -> torch.Tensor:
     _req(x, F32, "x")
     B, T, H = x.shape

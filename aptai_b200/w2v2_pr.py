@@ -163,7 +163,7 @@ class Wav2Vec2_PR(nn.Module):
             dev0 = next(self.wav2vec2.parameters()).device
             wav = input_values.to(device=dev0, dtype=torch.float32).contiguous()
             lens = input_lengths.reshape(-1).to(device=dev0, dtype=torch.int64)
-            flen = self.wav2vec2._get_feat_extract_output_lengths(lens).to(torch.int32).contiguous()
+            flen = self.wav2vec2.frame_lengths_i32(lens)
             gb = self.grad_buffer()
             h, sv = self.wav2vec2.encode_train(wav, flen)
             p_fin = float(self.dropout.p)                      # final_dropout (models/w2v2_pr.py:56)
@@ -263,7 +263,7 @@ class Wav2Vec2_PR(nn.Module):
             dev = next(w2v.parameters()).device
             wav = audio_inputs.to(device=dev, dtype=torch.float32).contiguous()
             lens = audio_lengths.reshape(-1).to(device=dev, dtype=torch.int64)
-            flen = w2v._get_feat_extract_output_lengths(lens).to(torch.int32).contiguous()
+            flen = w2v.frame_lengths_i32(lens)
             self.grad_buffer()
             _, sv = w2v.encode_train(wav, flen, regularise=self.training, collect_hidden=True)
             idx = (len(w2v.encoder.layers), intermediate_hidden, latter_hidden)

@@ -140,6 +140,11 @@ int aptai_lowpass_fir(const float* x, int B, int T, int C, const double* taps, i
 /* softmax (log_out=0) or log_softmax (log_out=1) over the last dim of fp32 [rows][V]
  * (models/aptai.py:105,148 F.softmax; models/force_aptai.py:130 log_softmax). */
 int aptai_softmax_rows(const float* x, int64_t rows, int V, int log_out, float* y, void* stream);
+/* frames per utterance after the conv feature encoder (HF:1005-1024 `_get_feat_extract_output_lengths`, called by
+ * models/aptai.py:77 through transformers): samples int64 [B] -> out_i64 and/or out_i32 [B]; kernels / strides are HOST
+ * arrays of n_layers <= 8 entries. */
+int aptai_frame_lengths(const int64_t* samples, int B, const int32_t* kernels, const int32_t* strides, int n_layers,
+                        int64_t* out_i64, int32_t* out_i32, void* stream);
 
 /* Force_APTAI cross-attention block (models/force_aptai.py:118-130, models/modules.py:139-153), fp32:
  * phn = emb[phn_ids] + pe; q = Wq frame + bq; k = Wk phn + bk; energy = q k^T - 1000*(ids==0);

@@ -400,3 +400,17 @@ def test_bilstm_backward_full_size_linearity(cuda):
     assert worst < 1e-2
     for bi in (1, 5, 33):
         assert float(dxc[bi, lens[bi]:].abs().max()) == 0.0
+
+
+def test_frame_lengths_kernel(cuda):
+    """One-launch `_get_feat_extract_output_lengths` (HF:1005-1024) against the integer recurrence, incl. inputs too
+    short for the conv stack (floor division goes negative exactly like torch.div(..., rounding_mode='floor'))."""
+    from aptai_b200.config import W2V2Config
+    cfg = W2V2Config.large()
+    n = torch.tensor([16000, 400, 399, 128000, 320000, 25, 10, 1, 47999], dtype=torch.int64, device=cuda)
+    o64, o32 = ops.frame_lengths(n, cfg.conv_kernel, cfg.conv_stride)
+    ref = n.clone()
+    for k, s in zip(cfg.conv_kernel, cfg.conv_stride):
+        ref = torch.div(ref - k, s, rounding_mode="floor") + 1
+    assert torch.equal(o64, ref) and torch.equal(o32.long(), ref)
+    assert [cfg.conv_out_length(int(v)) for v in n[:5]] == o64[:5].tolist()
