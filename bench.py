@@ -429,11 +429,12 @@ def run_ours(args):
         peak_tf, peak_hbm, how = peaks()
         gemm_flops = args.steps * sum(sweep.gemm_flops_utt(cfg, l) for l in lengths)
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-        traffic, traffic_src = None, None
+        traffic, traffic_src, traffic_alg = None, None, None
         tp = os.path.join(ROOT, "profiles", "gemm_traffic.json")
         if os.path.exists(tp):
             tj = json.load(open(tp))
             traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+            traffic_alg = tj.get("algorithmic_bytes")
         line = {
             "metric": "audio-sec/sec APTAI fwd+align", "value": world * audio_s * args.steps / (ms_max * 1e-3),
             "unit": "audio-s/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -451,7 +452,8 @@ def run_ours(args):
             "clocks": clk,
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_kernel (all launches of the GEMM family)",
                          "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": how,
+                         "traffic": traffic, "traffic_source": traffic_src, "traffic_algorithmic_bytes": traffic_alg,
+                         "peak_source": how,
                          "flops": "valid frames only (SURVEY 8d closed form over the step's utterance lengths)",
                          "gemm_share_of_step": gemm_ms / ms, "gemm_launches": gemm_launches,
                          "whole_step_tflops": args.steps * sum(sweep.flops_utt(cfg, l) for l in lengths) / (ms * 1e-3) / 1e12},
