@@ -398,6 +398,21 @@ def masked_mse_ce(tv_pred, tv_tgt, logits, phn_tgt, return_ws: bool = False):
     return out
 
 
+CTC_MAX_LABELS = 127      # labels per utterance the fused CTC / Viterbi kernels hold (2S+1 states in registers)
+
+
+def _trim_targets(targets: torch.Tensor, target_len: torch.Tensor, what: str) -> torch.Tensor:
+    """The kernels' label limit applies to the LONGEST transcript, not to the padded width of the label tensor: a
+    batch padded wider than the limit is narrowed to max(target_len) (one device->host read, only in that case)."""
+    if targets.shape[1] <= CTC_MAX_LABELS:
+        return targets
+    m = max(1, int(target_len.max()))
+    if m > CTC_MAX_LABELS:
+        raise ValueError(f"{what}: a transcript of {m} labels exceeds the kernels' limit of {CTC_MAX_LABELS} labels per "
+                         "utterance (INTEGRATION.md, limits); split the utterance")
+    return targets[:, :m].contiguous()
+
+
 def logsoftmax_ctc(logits: torch.Tensor, targets: torch.Tensor, input_len: torch.Tensor, target_len: torch.Tensor, *,
                    blank: int = 0, zero_infinity: bool = True, scale: Optional[torch.Tensor] = None,
                    want_log_probs: bool = True, want_grad: bool = False, prepend_blank: bool = False,
@@ -406,6 +421,7 @@ def logsoftmax_ctc(logits: torch.Tensor, targets: torch.Tensor, input_len: torch
     _req(logits, F32, "logits"); _req(targets, I32, "targets")
     _req(input_len, I32, "input_len"); _req(target_len, I32, "target_len")
     B, T, V = logits.shape
+    targets = _trim_targets(targets, target_len, "logsoftmax_ctc")
     Smax = targets.shape[1]
     Veff = V + int(prepend_blank)
     dev = logits.device
@@ -436,6 +452,7 @@ def ctc_viterbi(log_probs: torch.Tensor, targets: torch.Tensor, input_len: torch
     _req(log_probs, F32, "log_probs"); _req(targets, I32, "targets")
     _req(input_len, I32, "input_len"); _req(target_len, I32, "target_len")
     B, T, Cc = log_probs.shape
+    targets = _trim_targets(targets, target_len, "ctc_viterbi")
     Smax = targets.shape[1]
     dev = log_probs.device
     L = _lib.load()
