@@ -41,20 +41,28 @@ class APTAI(nn.Module):
 
     # ---------------------------------------------------------------------------------------------- kernels
     @torch.no_grad()
-    def _heads(self, audio_inputs, audio_lengths):
-        """backbone -> fused TV/phoneme heads (+argmax) -> low-pass.  Returns tv [B,T,9], logits [B,T,46], pred [B,T]."""
+    def _heads(self, audio_inputs, audio_lengths, want_logp: bool = False):
+        """backbone -> ONE tail kernel (final LayerNorm + TV / phoneme heads + argmax [+ log-softmax]) -> low-pass.
+        Returns tv [B,T,9], logits [B,T,46], pred [B,T] (and log_probs [B,T,46] with `want_logp`)."""
         if self.training and (self.tv_head[0].p > 0 or self.phn_head[0].p > 0):
             raise RuntimeError("aptai_b200: this is the inference path (no head dropout); in training mode call "
                                "forward() with autograd enabled, or .eval() first")
-        out = self.wav2vec2(audio_inputs, attention_mask=audio_lengths.reshape(-1)[:, None], return_dict=True,
-                            output_hidden_states=False)
-        h = out.last_hidden_state                       # == hidden_states[num_hidden_layers]
+        w2v = self.wav2vec2
+        if not audio_inputs.is_cuda:
+            raise RuntimeError("aptai_b200: audio_inputs must be on a CUDA (sm_100) device; there is no CPU path")
+        wav = audio_inputs.to(torch.float32).contiguous()
+        flen = w2v.frame_lengths_i32(audio_lengths)
+        defer = w2v.defers_final_ln()
+        h, _, _ = w2v.encode(wav, flen, final_ln=not defer)
         B, T, H = h.shape
+        g, b, eps = w2v.final_ln_params() if defer else (None, None, 0.0)
         tvl, phl = self.tv_head[2], self.phn_head[2]
         f = lambda p: p.detach().float().contiguous()
-        tv_raw, logits, pred = ops.heads(h.view(B * T, H), f(tvl.weight), f(tvl.bias), ops.ACT_TANH, f(phl.weight),
-                                         f(phl.bias), ops.ACT_LEAKY)
+        tv_raw, logits, pred, logp, _ = ops.tail(h.view(B * T, H), g, b, eps, f(tvl.weight), f(tvl.bias), ops.ACT_TANH,
+                                                 f(phl.weight), f(phl.bias), ops.ACT_LEAKY, want_logp=want_logp)
         tv = self.tv_lowpass(tv_raw.view(B, T, 9))
+        if want_logp:
+            return tv, logits.view(B, T, -1), pred.view(B, T), logp.view(B, T, -1), flen
         return tv, logits.view(B, T, -1), pred.view(B, T)
 
     # ---------------------------------------------------------------------------------------------- training
@@ -161,13 +169,13 @@ class APTAI(nn.Module):
         Returns tvs_pred [B,T,9], phn_fc_logits [B,T,46], phn_fc_pred [B,T]; with known phoneme sequences
         (`phn_targets` int32 [B,S], `phn_target_lens` int32 [B]) also the CTC-Viterbi forced alignment of the
         phoneme log-probs: align_paths int32 [B,T] (-1 beyond each utterance), align_scores, align_status."""
-        tv, logits, pred = self._heads(audio_inputs, audio_lengths)
+        if phn_targets is None:
+            tv, logits, pred = self._heads(audio_inputs, audio_lengths)
+            return {"tvs_pred": tv, "phn_fc_logits": logits, "phn_fc_pred": pred}
+        tv, logits, pred, lp, flen = self._heads(audio_inputs, audio_lengths, want_logp=True)
         out = {"tvs_pred": tv, "phn_fc_logits": logits, "phn_fc_pred": pred}
-        if phn_targets is not None:
-            lp = ops.softmax_rows(logits.contiguous(), log=True)
-            flen = self.wav2vec2.frame_lengths_i32(audio_lengths)
-            paths, scores, status = ops.ctc_viterbi(lp, phn_targets, flen, phn_target_lens, blank=blank)
-            out.update(align_paths=paths, align_scores=scores, align_status=status, log_probs=lp)
+        paths, scores, status = ops.ctc_viterbi(lp, phn_targets, flen, phn_target_lens, blank=blank)
+        out.update(align_paths=paths, align_scores=scores, align_status=status, log_probs=lp)
         return out
 
     def set_precision(self, precision: str):

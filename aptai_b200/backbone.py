@@ -324,6 +324,16 @@ class Wav2Vec2Backbone(nn.Module):
             n = torch.div(n - k, s, rounding_mode="floor") + 1 if torch.is_tensor(n) else (n - k) // s + 1
         return n
 
+    def defers_final_ln(self) -> bool:
+        """True when `encode(final_ln=False)` really leaves the last LayerNorm to the caller (pre-LN encoder, default
+        precision)."""
+        return bool(self.cfg.do_stable_layer_norm) and self.precision == "bf16"
+
+    def final_ln_params(self):
+        """(gamma, beta, eps) of the encoder's last LayerNorm as the kernels take them (fp32, contiguous)."""
+        P = self.plan()
+        return P.enc_ln_w, P.enc_ln_b, self.cfg.layer_norm_eps
+
     def frame_lengths_i32(self, input_lengths: torch.Tensor) -> torch.Tensor:
         """int32 [B] frame counts (the form every kernel takes) of sample counts on this module's device."""
         dev = next(self.parameters()).device
@@ -712,9 +722,12 @@ class Wav2Vec2Backbone(nn.Module):
     # ---- the hot path ----------------------------------------------------------------------------------------
     @torch.no_grad()
     def encode(self, wav: torch.Tensor, frame_lens: torch.Tensor, *, collect_hidden: bool = False,
-               want_features: bool = False):
+               want_features: bool = False, final_ln: bool = True):
         """wav fp32 [B,L] (CUDA), frame_lens int32 [B] (CUDA, valid frames per utterance).
-        Returns (last_hidden fp32 [B,T,H], hidden tuple | None, features bf16 [B,T,512] | None)."""
+        Returns (last_hidden fp32 [B,T,H], hidden tuple | None, features bf16 [B,T,512] | None).
+        `final_ln=False` (pre-LN 'stable' encoders in the default precision, no hidden-state collection): the encoder's
+        last LayerNorm (HF:792) is left to the caller's fused tail kernel (`ops.tail`) — see `final_ln_params()` —
+        and `last_hidden` is the un-normalised residual stream."""
         if self.precision == "f32x3":
             from . import accurate
             return accurate.encode(self, wav, frame_lens, collect_hidden=collect_hidden, want_features=want_features)
@@ -764,7 +777,10 @@ class Wav2Vec2Backbone(nn.Module):
                 _, x = ops.layernorm(h, lw.ln2_w, lw.ln2_b, eps)
                 _, u = ops.linear(x, lw.ff1_w, lw.ff1_b, act=1)
                 ops.linear(u, lw.ff2_w, lw.ff2_b, residual=h, out_f32=h, want_bf16=False)
-            last, _ = ops.layernorm(h, P.enc_ln_w, P.enc_ln_b, eps, want_f32=True, want_bf16=False)
+            if final_ln or collect_hidden:
+                last, _ = ops.layernorm(h, P.enc_ln_w, P.enc_ln_b, eps, want_f32=True, want_bf16=False)
+            else:
+                last = h
         last = last.view(B, T, H)
         if collect_hidden:
             hidden.append(last)

@@ -399,6 +399,207 @@ extern "C" int aptai_heads(const float* h, int64_t rows, int H, const float* wa,
   return after_launch("heads");
 }
 
+namespace aptai {
+// ---------------------------------------------------------------------------------------------------------------
+// Tail of the APTAI / Wav2Vec2_PR forward in ONE kernel: (final LayerNorm of the pre-LN encoder: HF:792) -> both heads
+// (models/aptai.py:43-55: tv = W_tv tanh(h) + b, logits = W_phn leaky_relu(h) + b; w2v2_pr.py:58) -> argmax (first
+// maximum, aptai.py:105-106) -> log_softmax of the phoneme logits (the alignment stage's input).
+// CTA = 64 rows x 64 output slots (16 for head A, 48 for head B), 256 threads, thread tile 2 rows x 8 slots: per k one
+// 8-byte and two 16-byte shared loads feed 16 FMAs (the round-1 heads kernel fed 8 FMAs from 6 scalar loads and was
+// LDS-bound at 13 TFLOP/s).  Pass 0: warp per row, exact two-pass LayerNorm statistics in registers; the main loop
+// re-reads the rows (L2 hits: 256 KB per CTA) and normalises + activates them while staging the k-chunk.  fp32 FMA
+// throughout: N = 9 + 46 is too small for a tensor-core tile to pay, and the argmax parity needs fp32 logits.
+constexpr int TL_ROWS = 64, TL_KC = 32, TL_SLOTS = 64, TL_A = 16;
+
+__global__ void __launch_bounds__(256)
+tail_kernel(const float* __restrict__ h, long long rows, int H, const float* __restrict__ gamma,
+            const float* __restrict__ beta, float eps, const float* __restrict__ wa, const float* __restrict__ ba,
+            int na, int act_a, float* __restrict__ out_a, const float* __restrict__ wb, const float* __restrict__ bb,
+            int nb, int act_b, float* __restrict__ out_b, long long* __restrict__ argmax_b, float* __restrict__ logp_b,
+            float* __restrict__ h_norm) {
+  // pitches 66 / 68 words: the staging stores (8 lanes per row, k apart by 4) spread over banks instead of hitting one
+  __shared__ __align__(16) float hA[TL_KC][TL_ROWS + 2];  // [k][row]: a thread's two rows are one 8-byte load
+  __shared__ __align__(16) float hB[TL_KC][TL_ROWS + 2];
+  __shared__ __align__(16) float ws[TL_KC][TL_SLOTS + 4]; // [k][slot]: a thread's eight slots are two 16-byte loads
+  __shared__ float2 stat[TL_ROWS];                         // {mean, rstd}
+  __shared__ float res[TL_ROWS][TL_SLOTS + 1];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long row0 = static_cast<long long>(blockIdx.x) * TL_ROWS;
+  const bool ln = gamma != nullptr;
+  // ---- pass 0: LayerNorm statistics, warp per row (two-pass from registers: H <= 1024 -> 32 values per lane)
+  if (ln) {
+    for (int r = warp; r < TL_ROWS; r += 8) {
+      const long long row = row0 + r;
+      float v[32];
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = (i * 32 + lane) * 4;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < rows && k < H) x = __ldg(reinterpret_cast<const float4*>(h + row * H + k));
+        v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+        s += (x.x + x.y) + (x.z + x.w);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      const float mean = s / H;
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = (i * 32 + lane) * 4;
+        if (k < H) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float d = v[4 * i + j] - mean;
+            q = fmaf(d, d, q);
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      if (lane == 0) stat[r] = make_float2(mean, rsqrtf(q / H + eps));
+    }
+  } else if (tid < TL_ROWS) {
+    stat[tid] = make_float2(0.f, 1.f);
+  }
+  __syncthreads();
+  const int tx = tid & 7;            // slots tx*8 .. tx*8+7 (tx < 2: head A)
+  const int ty = tid >> 3;           // rows ty*2, ty*2+1
+  const bool is_a = tx < TL_A / 8;
+  float acc[2][8];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < H; k0 += TL_KC) {
+    // stage the k-chunk: 64 rows x 32 k of h (normalised, both activations) and 64 slots x 32 k of the weights
+    for (int i = tid; i < TL_ROWS * TL_KC / 4; i += 256) {
+      const int r = i / (TL_KC / 4), k4 = (i % (TL_KC / 4)) * 4;
+      const long long row = row0 + r;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < rows) x = __ldg(reinterpret_cast<const float4*>(h + row * H + k0 + k4));
+      float xv[4] = {x.x, x.y, x.z, x.w};
+      if (ln) {
+        const float2 st = stat[r];
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + k0 + k4));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + k0 + k4));
+        const float gv[4] = {g4.x, g4.y, g4.z, g4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) xv[j] = fmaf((xv[j] - st.x) * st.y, gv[j], bv[j]);
+        if (h_norm != nullptr && row < rows)
+          *reinterpret_cast<float4*>(h_norm + row * H + k0 + k4) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        hA[k4 + j][r] = head_act(xv[j], act_a);
+        hB[k4 + j][r] = head_act(xv[j], act_b);
+      }
+    }
+    for (int i = tid; i < TL_SLOTS * TL_KC / 4; i += 256) {
+      const int sl = i / (TL_KC / 4), k4 = (i % (TL_KC / 4)) * 4;
+      float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (sl < TL_A) {
+        if (sl < na) w4 = __ldg(reinterpret_cast<const float4*>(wa + static_cast<long long>(sl) * H + k0 + k4));
+      } else if (sl - TL_A < nb) {
+        w4 = __ldg(reinterpret_cast<const float4*>(wb + static_cast<long long>(sl - TL_A) * H + k0 + k4));
+      }
+      ws[k4][sl] = w4.x; ws[k4 + 1][sl] = w4.y; ws[k4 + 2][sl] = w4.z; ws[k4 + 3][sl] = w4.w;
+    }
+    __syncthreads();
+    const float (*hs)[TL_ROWS + 2] = is_a ? hA : hB;
+#pragma unroll 8
+    for (int k = 0; k < TL_KC; ++k) {
+      const float2 x = *reinterpret_cast<const float2*>(&hs[k][ty * 2]);
+      const float4 w0 = *reinterpret_cast<const float4*>(&ws[k][tx * 8]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&ws[k][tx * 8 + 4]);
+      const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[0][j] = fmaf(x.x, wv[j], acc[0][j]);
+        acc[1][j] = fmaf(x.y, wv[j], acc[1][j]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int sl = tx * 8 + j;
+    float bv = 0.f;
+    if (sl < TL_A) {
+      if (sl < na) bv = ba[sl];
+    } else if (sl - TL_A < nb) {
+      bv = bb[sl - TL_A];
+    }
+    res[ty * 2][sl] = acc[0][j] + bv;
+    res[ty * 2 + 1][sl] = acc[1][j] + bv;
+  }
+  __syncthreads();
+  for (int i = tid; i < TL_ROWS * TL_SLOTS; i += 256) {
+    const int r = i / TL_SLOTS, sl = i % TL_SLOTS;
+    const long long row = row0 + r;
+    if (row >= rows) continue;
+    if (sl < TL_A) {
+      if (sl < na) out_a[row * na + sl] = res[r][sl];
+    } else if (sl - TL_A < nb) {
+      out_b[row * nb + (sl - TL_A)] = res[r][sl];
+    }
+  }
+  // ---- argmax (first maximum) and log-softmax of head B: warp per row, lane = slots lane and lane + 32
+  if (nb > 0 && (argmax_b != nullptr || logp_b != nullptr)) {
+    for (int r = warp; r < TL_ROWS; r += 8) {
+      const long long row = row0 + r;
+      if (row >= rows) break;
+      const float v0 = lane < nb ? res[r][TL_A + lane] : -INFINITY;
+      const float v1 = lane + 32 < nb ? res[r][TL_A + lane + 32] : -INFINITY;
+      float bv = v0;
+      int bi = lane;
+      if (v1 > bv) {
+        bv = v1;
+        bi = lane + 32;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) {
+          bv = ov;
+          bi = oi;
+        }
+      }
+      if (argmax_b != nullptr && lane == 0) argmax_b[row] = bi;
+      if (logp_b != nullptr) {
+        float e = (lane < nb ? expf(v0 - bv) : 0.f) + (lane + 32 < nb ? expf(v1 - bv) : 0.f);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+        const float lse = bv + logf(e);
+        if (lane < nb) logp_b[row * nb + lane] = v0 - lse;
+        if (lane + 32 < nb) logp_b[row * nb + lane + 32] = v1 - lse;
+      }
+    }
+  }
+}
+}  // namespace aptai
+
+extern "C" int aptai_tail(const float* h, int64_t rows, int H, const float* ln_gamma, const float* ln_beta, float eps,
+                          const float* wa, const float* ba, int na, int act_a, float* out_a, const float* wb,
+                          const float* bb, int nb, int act_b, float* out_b, int64_t* argmax_b, float* logp_b,
+                          float* h_norm, void* stream) {
+  if (int rc = check_arch()) return rc;
+  APTAI_REQUIRE(h && rows >= 1, "tail: null input");
+  APTAI_REQUIRE(H >= TL_KC && H % TL_KC == 0 && H <= 1024, "tail: H must be a multiple of %d, at most 1024", TL_KC);
+  APTAI_REQUIRE((ln_gamma == nullptr) == (ln_beta == nullptr), "tail: LayerNorm needs gamma and beta");
+  APTAI_REQUIRE(na >= 0 && na <= TL_A && nb >= 0 && nb <= TL_SLOTS - TL_A, "tail: na <= %d and nb <= %d", TL_A,
+                TL_SLOTS - TL_A);
+  APTAI_REQUIRE(na == 0 || (wa && ba && out_a), "tail: head A pointers");
+  APTAI_REQUIRE(nb == 0 || (wb && bb && out_b), "tail: head B pointers");
+  APTAI_REQUIRE(h_norm == nullptr || ln_gamma != nullptr, "tail: h_norm is the LayerNorm output");
+  const unsigned grid = static_cast<unsigned>((rows + TL_ROWS - 1) / TL_ROWS);
+  tail_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      h, rows, H, ln_gamma, ln_beta, eps, wa, ba, na, act_a, out_a, wb, bb, nb, act_b, out_b,
+      reinterpret_cast<long long*>(argmax_b), logp_b, h_norm);
+  return after_launch("tail");
+}
+
 extern "C" int aptai_lowpass_fir(const float* x, int B, int T, int C, const double* taps, int ntaps, float* y,
                                  void* stream) {
   if (int rc = check_arch()) return rc;

@@ -322,6 +322,26 @@ def heads(h: torch.Tensor, wa, ba, act_a: int, wb, bb, act_b: int, want_argmax: 
     return oa, ob, am
 
 
+def tail(h: torch.Tensor, ln_gamma, ln_beta, eps: float, wa, ba, act_a: int, wb, bb, act_b: int, *,
+         want_argmax: bool = True, want_logp: bool = False, want_h_norm: bool = False):
+    """Fused tail: (final LayerNorm) -> heads A / B -> argmax -> log_softmax.  h fp32 [rows,H].
+    Returns (out_a | None, out_b | None, argmax int64 | None, logp | None, h_norm | None)."""
+    _req(h, F32, "h")
+    rows, H = h.shape
+    na = 0 if wa is None else wa.shape[0]
+    nb = 0 if wb is None else wb.shape[0]
+    dev = h.device
+    oa = torch.empty((rows, na), dtype=F32, device=dev) if na else None
+    ob = torch.empty((rows, nb), dtype=F32, device=dev) if nb else None
+    am = torch.empty((rows,), dtype=I64, device=dev) if (nb and want_argmax) else None
+    lp = torch.empty((rows, nb), dtype=F32, device=dev) if (nb and want_logp) else None
+    hn = torch.empty((rows, H), dtype=F32, device=dev) if (want_h_norm and ln_gamma is not None) else None
+    check(_lib.load().aptai_tail(h.data_ptr(), rows, H, _ptr(ln_gamma), _ptr(ln_beta), float(eps), _ptr(wa), _ptr(ba), na,
+                                 act_a, _ptr(oa), _ptr(wb), _ptr(bb), nb, act_b, _ptr(ob), _ptr(am), _ptr(lp), _ptr(hn),
+                                 _stream()), "tail")
+    return oa, ob, am, lp, hn
+
+
 def lowpass(x: torch.Tensor, taps: torch.Tensor) -> torch.Tensor:
     _req(x, F32, "x"); _req(taps, F64, "taps")
     B, T, Cc = x.shape

@@ -140,6 +140,13 @@ int aptai_lowpass_fir(const float* x, int B, int T, int C, const double* taps, i
 /* softmax (log_out=0) or log_softmax (log_out=1) over the last dim of fp32 [rows][V]
  * (models/aptai.py:105,148 F.softmax; models/force_aptai.py:130 log_softmax). */
 int aptai_softmax_rows(const float* x, int64_t rows, int V, int log_out, float* y, void* stream);
+/* Tail of the forward in one launch: optional final LayerNorm of the pre-LN encoder (HF:792; ln_gamma/ln_beta NULL = h is
+ * already normalised) -> both heads as in aptai_heads -> argmax of head B (may be NULL) -> log_softmax of head B (logp_b,
+ * may be NULL: the input of the alignment stage) -> optionally the normalised hidden state (h_norm fp32 [rows][H], may be
+ * NULL).  Replaces models/aptai.py:83-86,105-106 + the encoder's last LayerNorm + F.log_softmax.  H % 32 == 0, H <= 1024. */
+int aptai_tail(const float* h, int64_t rows, int H, const float* ln_gamma, const float* ln_beta, float eps,
+               const float* wa, const float* ba, int na, int act_a, float* out_a, const float* wb, const float* bb,
+               int nb, int act_b, float* out_b, int64_t* argmax_b, float* logp_b, float* h_norm, void* stream);
 /* frames per utterance after the conv feature encoder (HF:1005-1024 `_get_feat_extract_output_lengths`, called by
  * models/aptai.py:77 through transformers): samples int64 [B] -> out_i64 and/or out_i32 [B]; kernels / strides are HOST
  * arrays of n_layers <= 8 entries. */

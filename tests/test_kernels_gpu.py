@@ -414,3 +414,31 @@ def test_frame_lengths_kernel(cuda):
         ref = torch.div(ref - k, s, rounding_mode="floor") + 1
     assert torch.equal(o64, ref) and torch.equal(o32.long(), ref)
     assert [cfg.conv_out_length(int(v)) for v in n[:5]] == o64[:5].tolist()
+
+
+@pytest.mark.parametrize("rows,H,with_ln", [(150, 1024, True), (64, 768, True), (1000, 1024, False), (1, 1024, True)])
+def test_fused_tail(cuda, rows, H, with_ln):
+    """One-launch tail (final LayerNorm + both heads + argmax + log-softmax) against the separate kernels it
+    replaces and against torch: fp32 throughout, so logits agree to accumulation-order noise and the argmax /
+    log-softmax are consistent with the kernel's own logits."""
+    h = _rand((rows, H), cuda, 1.5, 30) + 0.3
+    g = 1 + _rand((H,), cuda, 0.1, 31)
+    b = _rand((H,), cuda, 0.1, 32)
+    tvw, tvb = _rand((9, H), cuda, 0.03, 33), _rand((9,), cuda, 0.03, 34)
+    pw, pb = _rand((46, H), cuda, 0.03, 35), _rand((46,), cuda, 0.03, 36)
+    oa, ob, am, lp, hn = ops.tail(h, g if with_ln else None, b if with_ln else None, 1e-5, tvw, tvb, ops.ACT_TANH, pw, pb,
+                                  ops.ACT_LEAKY, want_logp=True, want_h_norm=with_ln)
+    x = F.layer_norm(h, (H,), g, b, 1e-5) if with_ln else h
+    if with_ln:
+        torch.testing.assert_close(hn, x, atol=2e-5, rtol=2e-5)
+    ref_a = torch.tanh(x) @ tvw.t() + tvb
+    ref_b = F.leaky_relu(x, 0.01) @ pw.t() + pb
+    torch.testing.assert_close(oa, ref_a, atol=5e-5, rtol=1e-4)
+    torch.testing.assert_close(ob, ref_b, atol=5e-5, rtol=1e-4)
+    assert torch.equal(am, torch.argmax(ob, -1))
+    torch.testing.assert_close(lp, torch.log_softmax(ob, -1), atol=2e-6, rtol=1e-5)
+    # the kernels it replaces
+    xs = ops.layernorm(h, g, b, 1e-5, want_f32=True, want_bf16=False)[0] if with_ln else h
+    o2a, o2b, am2 = ops.heads(xs, tvw, tvb, ops.ACT_TANH, pw, pb, ops.ACT_LEAKY)
+    torch.testing.assert_close(oa, o2a, atol=5e-5, rtol=1e-4)
+    torch.testing.assert_close(ob, o2b, atol=5e-5, rtol=1e-4)
