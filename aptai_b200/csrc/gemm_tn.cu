@@ -244,14 +244,6 @@ constexpr int TP_HALF_BYTES = TN_BK * 128 * 2;               // 16 KB: two 64x64
 constexpr int TP_STAGE_BYTES = 2 * TP_HALF_BYTES;            // A half + B half
 constexpr int TP_SMEM = 1024 + TP_STAGES * TP_STAGE_BYTES + 256;
 
-__device__ __forceinline__ void tma_load_3d_cg2(const CUtensorMap* m, uint32_t bar_cluster_addr, void* dst, int c0,
-                                                int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TN_THREADS, 1)
 gemm_tn_wgrad_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                           const TnParams p) {

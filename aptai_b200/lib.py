@@ -56,6 +56,7 @@ PROTOTYPES = {
     "aptai_softmax_rows": (c_int, [c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p]),
     "aptai_tail": (c_int, [c_void_p, c_i64, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_void_p,
                            c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "aptai_posconv_slab": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "aptai_frame_lengths": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "aptai_cross_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p,

@@ -118,18 +118,24 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     return out_f32, out_bf16
 
 
+def split3_bf16(x: torch.Tensor, weight_layout: bool = False, scale: float = 1.0) -> torch.Tensor:
+    """fp32 [rows, cols] -> bf16 [rows, 3*cols] = [hi | lo | hi] (activations) or [hi | hi | lo] (weights)."""
+    _req(x, F32, "x")
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    out = torch.empty((rows, 3 * cols), dtype=BF16, device=x.device)
+    check(_lib.load().aptai_split3_bf16(x.data_ptr(), rows, cols, cols, int(weight_layout), float(scale),
+                                        out.data_ptr(), _stream()), "split3_bf16")
+    return out
+
+
 def linear_f32x3(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
     """fp32-accurate Linear on the bf16 tensor cores: x = x_hi + x_lo, w = w_hi + w_lo (bf16 pairs) and
     out = [x_hi | x_lo | x_hi] @ [w_hi | w_hi | w_lo]^T (K tripled; the dropped x_lo*w_lo term is ~2^-18 relative).
     For small projections whose input must not be re-quantised (Force_APTAI's frame_lin)."""
     _req(x, F32, "x")
-    xh = x.to(BF16)
-    xl = (x - xh.float()).to(BF16)
-    wf = w.detach().float()
-    wh = wf.to(BF16)
-    wl = (wf - wh.float()).to(BF16)
-    a = torch.cat([xh, xl, xh], dim=1).contiguous()
-    ww = torch.cat([wh, wh, wl], dim=1).contiguous()
+    a = split3_bf16(x, weight_layout=False)                 # one launch each (csrc/accurate.cu), no ATen chain
+    ww = split3_bf16(w.detach().float().contiguous(), weight_layout=True)
     out, _ = linear(a, ww, bias, want_f32=True, want_bf16=False)
     return out
 
@@ -178,6 +184,16 @@ def posconv(x_pad: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], 
     B, Tp, H2 = x_pad.shape
     assert H2 == H and Tp == T + taps
     gw = H // groups
+    if (POSCONV_SLAB and gw == 64 and taps == 128 and act == 1 and row_shift == 0 and out_pre is None
+            and seg_valid_rows is None and residual is not None and residual.data_ptr() == out_f32.data_ptr()):
+        # in-place h += gelu(conv + bias), 64-channel groups: the slab kernel loads every input row once
+        _req(out_f32, F32, "out_f32")
+        done = _gemm_hook(None) if _gemm_hook is not None else None       # part of the GEMM family (bench roofline leg)
+        check(_lib.load().aptai_posconv_slab(x_pad.data_ptr(), w.data_ptr(), _ptr(bias), out_f32.data_ptr(), B, T, H,
+                                             _stream()), "posconv_slab")
+        if done is not None:
+            done()
+        return out_f32
     g = GemmArgs()
     # row_shift: first physical row of every segment (the transposed conv of the backward pass reads the halo-padded
     # gradient one row later than the forward reads its input)
@@ -262,6 +278,8 @@ def posconv_fold(g: torch.Tensor, v: torch.Tensor, cpad: int = 64, out: Optional
                                          _stream()), "posconv_fold")
     return w
 
+
+POSCONV_SLAB = int(os.environ.get("APTAI_POSCONV_SLAB", "1"))     # 0: always the generic implicit-GEMM path (A/B runs)
 
 # 0: by shape (attention_v3.cu's query-tile pairs with P in TMEM when an utterance has more than one 128-query tile,
 # else attention_tc.cu's two threads per row), 1 / 2 / 3: force one kernel (A/B runs in profiles/attn_bench.py)

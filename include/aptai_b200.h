@@ -109,6 +109,13 @@ int aptai_cast_pad_bf16(const float* x, int segs, int rows, int cols, int halo, 
 int aptai_posconv_fold(const float* g, const float* v, int H, int cin, int taps, int cpad, void* w_bf16,
                        float* norm_ws, void* stream);
 
+/* Grouped positional conv for 64-channel groups (H % 64 == 0, 128 taps), in place on the fp32 hidden stream:
+ * h[b][t][:] += gelu(conv(x_pad)[b][t][:] + bias)  (HF:329-379; x_pad bf16 [B][T+128][H] from aptai_cast_pad_bf16,
+ * w_fold bf16 [H][128*64] from aptai_posconv_fold).  Every input row is loaded once per (256-frame block, group): the tap
+ * shift is a descriptor offset into a shared-memory slab (csrc/posconv_tc.cu). */
+int aptai_posconv_slab(const void* x_pad, const void* w_fold, const float* bias, float* h, int B, int T, int H,
+                       void* stream);
+
 /* ------------------------------------------------------------------ attention (HF:500-549, SDPA) ------------
  * qkv: bf16 [B*T][3*H] (q | k | v, q pre-scaled by head_dim^-0.5), ctx: bf16 [B*T][H], head_dim 64.
  * Keys t >= key_len[b] are masked; every query row is computed (padded queries attend to valid keys, HF:438-463).

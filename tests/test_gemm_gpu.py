@@ -122,3 +122,28 @@ def test_gelu_accuracy(cuda):
     ref = torch.nn.functional.gelu(a.double())
     err = (o16.double() - ref).abs()
     assert bool((err <= ref.abs() * 2.0 ** -8 + 3e-5).all()), float((err - ref.abs() * 2.0 ** -8).max())
+
+
+@pytest.mark.parametrize("T,B", [(399, 3), (256, 2), (257, 1), (600, 20), (1, 2)])
+def test_posconv_slab_matches_generic(cuda, T, B):
+    """The slab kernel (one load of every input row, tap shift as a descriptor offset with the SWIZZLE_128B base
+    offset) against the generic implicit-GEMM path on the same operands: same bf16 products, same fp32 accumulation
+    order per tap, so the two agree to fp32 rounding of the residual add."""
+    H, groups, taps = 1024, 16, 128
+    x = _rand((B, T, H), cuda, 1.0, 40)
+    v = _rand((H, H // groups, taps), cuda, 2 * (1.0 / (taps * H)) ** 0.5, 41)
+    g = torch.linalg.vector_norm(v, dim=(0, 1), keepdim=True) * (1 + _rand((1, 1, taps), cuda, 0.05, 42))
+    bias = _rand((H,), cuda, 0.1, 43)
+    wf = ops.posconv_fold(g.contiguous(), v.contiguous(), 64)
+    xp = ops.cast_pad(x, taps // 2)
+    h1 = x.clone().view(B * T, H)
+    h2 = x.clone().view(B * T, H)
+    old = ops.POSCONV_SLAB
+    try:
+        ops.POSCONV_SLAB = 1
+        ops.posconv(xp, wf, bias, h1, T, H, groups, taps, h1)
+        ops.POSCONV_SLAB = 0
+        ops.posconv(xp, wf, bias, h2, T, H, groups, taps, h2)
+    finally:
+        ops.POSCONV_SLAB = old
+    torch.testing.assert_close(h1, h2, atol=2e-6, rtol=2e-6)
