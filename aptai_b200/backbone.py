@@ -767,16 +767,20 @@ class Wav2Vec2Backbone(nn.Module):
                 h, x = ops.layernorm(t32, lw.ln2_w, lw.ln2_b, eps, want_f32=True, want_bf16=True)
             last = h
         else:
+            # every activation of a 75 k-row batch (h 300 MB, qkv 450 MB, u 600 MB) exceeds the 126 MB L2: consecutive
+            # kernels walk their rows in ALTERNATING directions, so each one starts on the rows its producer wrote last
+            serp = ops.Serpentine()
             for lw in P.layers:
                 if collect_hidden:
                     hidden.append(h.view(B, T, H).clone())
-                _, x = ops.layernorm(h, lw.ln1_w, lw.ln1_b, eps)
-                _, qkv = ops.linear(x, lw.qkv_w, lw.qkv_b)
-                ctx = ops.attention(qkv, frame_lens, B, T, heads)
-                ops.linear(ctx, lw.o_w, lw.o_b, residual=h, out_f32=h, want_bf16=False)
-                _, x = ops.layernorm(h, lw.ln2_w, lw.ln2_b, eps)
-                _, u = ops.linear(x, lw.ff1_w, lw.ff1_b, act=1)
-                ops.linear(u, lw.ff2_w, lw.ff2_b, residual=h, out_f32=h, want_bf16=False)
+                serp(); _, x = ops.layernorm(h, lw.ln1_w, lw.ln1_b, eps)
+                serp(); _, qkv = ops.linear(x, lw.qkv_w, lw.qkv_b)
+                serp(); ctx = ops.attention(qkv, frame_lens, B, T, heads)
+                serp(); ops.linear(ctx, lw.o_w, lw.o_b, residual=h, out_f32=h, want_bf16=False)
+                serp(); _, x = ops.layernorm(h, lw.ln2_w, lw.ln2_b, eps)
+                serp(); _, u = ops.linear(x, lw.ff1_w, lw.ff1_b, act=1)
+                serp(); ops.linear(u, lw.ff2_w, lw.ff2_b, residual=h, out_f32=h, want_bf16=False)
+            serp.done()
             if final_ln or collect_hidden:
                 last, _ = ops.layernorm(h, P.enc_ln_w, P.enc_ln_b, eps, want_f32=True, want_bf16=False)
             else:

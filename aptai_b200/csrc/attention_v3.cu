@@ -51,6 +51,7 @@ struct Attn3Params {
   float* lse;
   int B, T, heads, n_qp, items, per_cta;
   int idle_ns;              // issuer back-off when nothing is ready (0: poll hot)
+  int reverse;              // aptai_set_traversal: utterances from the last to the first
 };
 
 // Work items (utterance b, head h, query-tile pair qp) in the order w = (b * heads + h) * n_qp + qp.  CTA c owns the
@@ -58,12 +59,14 @@ struct Attn3Params {
 // single-thread roles' loops), and consecutive items of a CTA re-use the same K/V out of L2.
 struct A3Iter {
   int w, w_end, qp, h, b, klen, n;
+  int bp;                   // physical utterance index (B - 1 - b when the traversal is reversed)
   bool two;                 // the second 128-query tile of the pair exists
 };
 __device__ __forceinline__ void a3_iter_lengths(A3Iter& it, const Attn3Params& p) {
   // the shuffle makes the loaded length provably warp-uniform for the compiler (every role calls this with the whole
   // warp converged): loop bounds derived from it stay in uniform registers
-  it.klen = __shfl_sync(0xffffffffu, max(1, min(__ldg(p.key_len + it.b), p.T)), 0);
+  it.bp = p.reverse ? p.B - 1 - it.b : it.b;
+  it.klen = __shfl_sync(0xffffffffu, max(1, min(__ldg(p.key_len + it.bp), p.T)), 0);
   it.n = (it.klen + A3_K - 1) / A3_K;
 }
 __device__ __forceinline__ bool a3_iter_init(A3Iter& it, const Attn3Params& p) {
@@ -247,7 +250,7 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           mbar_wait_backoff(&q_empty[qb], ((qi0 >> 1) & 1) ^ 1, 100);
           if (elect_one()) {
             mbar_expect_tx(&q_full[qb], A3_QB);
-            tma_load_3d(&tmQ, &q_full[qb], sQ + qb * A3_QB, it.h * A3_D, it.qp * 2 * A3_Q, it.b);
+            tma_load_3d(&tmQ, &q_full[qb], sQ + qb * A3_QB, it.h * A3_D, it.qp * 2 * A3_Q, it.bp);
           }
           ++qi0;
         }
@@ -256,7 +259,7 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           mbar_wait_backoff(&q_empty[2 + qb], ((qi1 >> 1) & 1) ^ 1, 100);
           if (elect_one()) {
             mbar_expect_tx(&q_full[2 + qb], A3_QB);
-            tma_load_3d(&tmQ, &q_full[2 + qb], sQ + (2 + qb) * A3_QB, it.h * A3_D, it.qp * 2 * A3_Q + A3_Q, it.b);
+            tma_load_3d(&tmQ, &q_full[2 + qb], sQ + (2 + qb) * A3_QB, it.h * A3_D, it.qp * 2 * A3_Q + A3_Q, it.bp);
           }
           ++qi1;
         }
@@ -265,8 +268,8 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           if (elect_one()) {
             mbar_expect_tx(&kv_full[kst], 2 * A3_KVB);
             uint8_t* dst = sKV + kst * 2 * A3_KVB;
-            tma_load_3d(&tmKV, &kv_full[kst], dst, p.heads * A3_D + it.h * A3_D, j * A3_K, it.b);
-            tma_load_3d(&tmKV, &kv_full[kst], dst + A3_KVB, 2 * p.heads * A3_D + it.h * A3_D, j * A3_K, it.b);
+            tma_load_3d(&tmKV, &kv_full[kst], dst, p.heads * A3_D + it.h * A3_D, j * A3_K, it.bp);
+            tma_load_3d(&tmKV, &kv_full[kst], dst + A3_KVB, 2 * p.heads * A3_D + it.h * A3_D, j * A3_K, it.bp);
           }
           if (++kst == A3_STAGES) {
             kst = 0;
@@ -528,7 +531,7 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (lane == 0) mbar_arrive(pf);
       }
       pending = true;
-      e_b = it.b; e_h = it.h; e_q0 = q0; e_m = m_used; e_l = l; e_live = warp_live;
+      e_b = it.bp; e_h = it.h; e_q0 = q0; e_m = m_used; e_l = l; e_live = warp_live;
     }
     if (pending) epilogue();
     if (lane == 0) tma_store_wait_all<0>();
@@ -593,6 +596,7 @@ extern "C" int aptai_attention_fwd_v3(const void* qkv, void* ctx, float* lse, co
   p.per_cta = (p.items + num_sms() - 1) / num_sms();
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   p.idle_ns = (poly8 >> 8) & 0xffff;
+  p.reverse = traversal_reverse();
   switch (poly8 & 0xff) {
     case 0: return launch_attention_v3<0>(tmq, tmkv, tmo, p, st);
     case 2: return launch_attention_v3<2>(tmq, tmkv, tmo, p, st);

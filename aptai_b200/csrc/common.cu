@@ -8,6 +8,9 @@ namespace aptai {
 
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
+static thread_local int g_reverse = 0;
+
+int traversal_reverse() { return g_reverse; }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -129,4 +132,5 @@ extern "C" {
 int aptai_version(void) { return 100; }
 const char* aptai_last_error_string(void) { return aptai::g_err; }
 int64_t aptai_launch_count(void) { return aptai::g_launches.load(std::memory_order_relaxed); }
+void aptai_set_traversal(int reverse) { aptai::g_reverse = reverse ? 1 : 0; }
 }

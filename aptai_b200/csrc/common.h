@@ -13,6 +13,7 @@ namespace aptai {
 void set_error(const char* fmt, ...);
 int check_arch();                       // 0 if the current device is sm_100, else APTAI_ERR_ARCH (message set)
 int num_sms();
+int traversal_reverse();              // 1: the next launches walk their rows / tiles / items from the end (aptai_set_traversal)
 void count_launch(int n = 1);
 int after_launch(const char* what);     // cudaGetLastError -> status (+ launch counter)
 

@@ -13,11 +13,12 @@ template <int NV, int IN_FMT>   // IN_FMT: 0 fp32, 1 bf16, 2 fp16
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const void* __restrict__ xin, long long rows, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, float* __restrict__ out_f32,
-                 __nv_bfloat16* __restrict__ out_bf16, int out16_fp16) {
+                 __nv_bfloat16* __restrict__ out_bf16, int out16_fp16, int reverse) {
   constexpr int COLS = NV * 128;
   const int lane = threadIdx.x & 31;
-  const long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  long long row = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
+  if (reverse) row = rows - 1 - row;          // aptai_set_traversal: start on the rows the producer wrote last
   float4 v[NV];
   if (IN_FMT != 0) {
     const uint2* p = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(xin) + row * COLS);
@@ -75,9 +76,10 @@ static void launch_ln(const void* x, int x_fmt, long long rows, const float* gam
   const int wpb = 8;
   const unsigned grid = static_cast<unsigned>((rows + wpb - 1) / wpb);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ob);
-  if (x_fmt == 1) layernorm_kernel<NV, 1><<<grid, wpb * 32, 0, st>>>(x, rows, gamma, beta, eps, of, o, o16);
-  else if (x_fmt == 2) layernorm_kernel<NV, 2><<<grid, wpb * 32, 0, st>>>(x, rows, gamma, beta, eps, of, o, o16);
-  else layernorm_kernel<NV, 0><<<grid, wpb * 32, 0, st>>>(x, rows, gamma, beta, eps, of, o, o16);
+  const int rev = traversal_reverse();
+  if (x_fmt == 1) layernorm_kernel<NV, 1><<<grid, wpb * 32, 0, st>>>(x, rows, gamma, beta, eps, of, o, o16, rev);
+  else if (x_fmt == 2) layernorm_kernel<NV, 2><<<grid, wpb * 32, 0, st>>>(x, rows, gamma, beta, eps, of, o, o16, rev);
+  else layernorm_kernel<NV, 0><<<grid, wpb * 32, 0, st>>>(x, rows, gamma, beta, eps, of, o, o16, rev);
 }
 
 // ---------------------------------------------------------------------------------------------- cast + halo pad

@@ -42,6 +42,7 @@ struct GemmParams {
   const __nv_bfloat16* aux;   // act == 2: pre-activation u saved by the forward pass; out = acc * gelu'(u)
   __nv_bfloat16* out_pre;     // optional second 16-bit output: the value BEFORE the activation (training forward)
   int tma16;                  // the single 16-bit output leaves through shared memory + TMA stores (tensor map tmC)
+  int reverse;                // walk the tiles from the last to the first (aptai_set_traversal)
   int red32;                  // in-place fp32 residual update h += acc + bias as TMA reduce-add stores (tmC, fp32)
   const float* l2_hint;       // red32: the rows the reduction will touch, prefetched into L2 one tile ahead
 };
@@ -162,7 +163,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
     {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
+      for (int tile_i = tile0; tile_i < p.num_tiles; tile_i += tile_step) {
+        const int tile = p.reverse ? p.num_tiles - 1 - tile_i : tile_i;
         const int n_blk = tile % p.n_tiles;
         const int mt = tile / p.n_tiles;
         const int seg = mt / p.m_tiles_per_seg;
@@ -281,7 +283,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
     }
 
     uint32_t tpar = 0;                       // tile parity: bias buffer of this tile
-    for (int tile = tile0; tile < p.num_tiles; tile += tile_step, tpar ^= 1) {
+    for (int tile_i = tile0; tile_i < p.num_tiles; tile_i += tile_step, tpar ^= 1) {
+      const int tile = p.reverse ? p.num_tiles - 1 - tile_i : tile_i;
       const int n_blk = tile % p.n_tiles;
       const int mt = tile / p.n_tiles;
       const int seg = mt / p.m_tiles_per_seg;
@@ -311,8 +314,9 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         // pull the NEXT tile's residual rows towards L2 while this tile is processed: the fp32 residual stream
         // makes the K=1024 projections memory-bound, and two epilogue warps per scheduler cannot keep enough
         // HBM requests in flight on their own
-        const int nt = tile + tile_step;
-        if (nt < p.num_tiles) {
+        const int nt_i = tile_i + tile_step;
+        const int nt = p.reverse ? p.num_tiles - 1 - nt_i : nt_i;
+        if (nt_i < p.num_tiles) {
           const int nmt = nt / p.n_tiles;
           const int nseg = nmt / p.m_tiles_per_seg;
           const int nr = (nmt - nseg * p.m_tiles_per_seg) * TILE_M + static_cast<int>(rank) * BLOCK_M + row_in_tile;
@@ -873,6 +877,7 @@ extern "C" int aptai_gemm_bf16(const aptai_gemm_args* g, void* stream) {
   }
   GemmParams p;
   p.tma16 = (tma16 || g->ln) ? 1 : 0;
+  p.reverse = traversal_reverse();
   p.red32 = red32 ? 1 : 0;
   p.l2_hint = red32 ? g->out_f32 : nullptr;
   p.num_kb = g->taps * g->kb_per_tap;

@@ -279,6 +279,28 @@ def posconv_fold(g: torch.Tensor, v: torch.Tensor, cpad: int = 64, out: Optional
     return w
 
 
+SERPENTINE = int(os.environ.get("APTAI_SERPENTINE", "1"))         # 0: every kernel walks its rows front to back (A/B runs)
+
+
+def set_traversal(reverse: bool) -> None:
+    """Traversal hint for the next GEMM / LayerNorm / attention-v3 launches of this thread (include/aptai_b200.h)."""
+    _lib.load().aptai_set_traversal(1 if (reverse and SERPENTINE) else 0)
+
+
+class Serpentine:
+    """Alternates the traversal direction from one kernel of a chain to the next: `s()` before each launch."""
+
+    def __init__(self):
+        self.k = 0
+
+    def __call__(self):
+        set_traversal(bool(self.k & 1))
+        self.k += 1
+
+    def done(self):
+        set_traversal(False)
+
+
 POSCONV_SLAB = int(os.environ.get("APTAI_POSCONV_SLAB", "1"))     # 0: always the generic implicit-GEMM path (A/B runs)
 
 # 0: by shape (attention_v3.cu's query-tile pairs with P in TMEM when an utterance has more than one 128-query tile,

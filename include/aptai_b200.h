@@ -86,6 +86,12 @@ typedef struct aptai_gemm_args {
 
 int aptai_gemm_bf16(const aptai_gemm_args* args, void* stream);
 
+/* Traversal hint for the calling thread's NEXT launches of aptai_gemm_bf16 / aptai_layernorm / aptai_attention_fwd_v3:
+ * reverse != 0 makes them walk their output tiles / rows / utterances from the end.  Results are identical.  A chain of
+ * kernels whose activations exceed the 126 MB L2 (LayerNorm -> QKV -> attention -> out-proj -> ...) alternates the
+ * direction, so that every kernel STARTS on the rows its producer wrote LAST, which are still in L2. */
+void aptai_set_traversal(int reverse);
+
 /* ------------------------------------------------------------------ feature encoder front end ---------------
  * conv layer 0 (1 -> 512 channels, kernel 10, stride 5) + norm + GELU, channels-last bf16 output [B][T0][512].
  * norm=1: LayerNorm over channels per frame (HF:281-299).  norm=2: GroupNorm(512 groups) over time per
