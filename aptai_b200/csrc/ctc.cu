@@ -281,14 +281,21 @@ struct VitArgs {
   int* paths;           // [B][T]
   float* scores;        // [B][T]
   int* status;          // [B] 0 ok, 1 infeasible (T < L + R)
-  uint16_t* bp_global;  // ws [B][T][32] (used when the back-pointers do not fit in shared memory)
+  void* bp_global;      // ws [B][T][32] back-pointer words (used when they do not fit in shared memory)
   int bp_in_smem;
 };
+
+// back-pointer word of one lane and one frame: 2 bits per state, NI states
+template <int NI> struct BpWord { typedef uint16_t type; };
+template <> struct BpWord<16> { typedef uint32_t type; };
+template <> struct BpWord<32> { typedef uint64_t type; };
 
 template <int NI>
 __global__ void __launch_bounds__(32)
 viterbi_kernel(const VitArgs a) {
-  extern __shared__ uint16_t bp_sm[];
+  typedef typename BpWord<NI>::type bp_t;
+  extern __shared__ __align__(8) unsigned char bp_sm_raw[];
+  bp_t* bp_sm = reinterpret_cast<bp_t*>(bp_sm_raw);
   __shared__ int s_lab[32 * NI];
   const int b = blockIdx.x;
   const int lane = threadIdx.x;
@@ -299,7 +306,7 @@ viterbi_kernel(const VitArgs a) {
   const float* lp = a.lp + static_cast<long long>(b) * a.T * a.C;
   int* path = a.paths + static_cast<long long>(b) * a.T;
   float* score = a.scores ? a.scores + static_cast<long long>(b) * a.T : nullptr;
-  uint16_t* bp = a.bp_in_smem ? bp_sm : a.bp_global + static_cast<long long>(b) * a.T * 32;
+  bp_t* bp = a.bp_in_smem ? bp_sm : reinterpret_cast<bp_t*>(a.bp_global) + static_cast<long long>(b) * a.T * 32;
 
   for (int t = Tb + lane; t < a.T; t += 32) {
     path[t] = -1;
@@ -345,7 +352,7 @@ viterbi_kernel(const VitArgs a) {
     float p2 = __shfl_up_sync(0xffffffffu, cur[NI - 2], 1);
     if (lane == 0) { p1 = NEG_INF; p2 = NEG_INF; }
     float nw[NI];
-    uint32_t code = 0;
+    bp_t code = 0;
 #pragma unroll
     for (int i = 0; i < NI; ++i) {
       const float x0 = cur[i];
@@ -359,11 +366,11 @@ viterbi_kernel(const VitArgs a) {
       else { best = x0; c = 0; }
       const int s = lane * NI + i;
       nw[i] = (s < NS && best != NEG_INF) ? __fadd_rn(best, e[i]) : NEG_INF;
-      code |= c << (2 * i);
+      code |= static_cast<bp_t>(c) << (2 * i);
     }
 #pragma unroll
     for (int i = 0; i < NI; ++i) cur[i] = nw[i];
-    bp[static_cast<long long>(t) * 32 + lane] = static_cast<uint16_t>(code);
+    bp[static_cast<long long>(t) * 32 + lane] = code;
   }
   // final state: S-1 if alpha[S-1] > alpha[S-2] (strict) else S-2 ; S == 1 -> 0
   int s_fin = 0;
@@ -388,8 +395,8 @@ viterbi_kernel(const VitArgs a) {
       path[t] = l;
       if (score) score[t] = lp[static_cast<long long>(t) * a.C + l];
       if (t > 0) {
-        const uint32_t code = bp[static_cast<long long>(t) * 32 + s / NI];
-        s -= (code >> (2 * (s % NI))) & 3;
+        const bp_t code = bp[static_cast<long long>(t) * 32 + s / NI];
+        s -= static_cast<int>((code >> (2 * (s % NI))) & 3);
       }
     }
   }
@@ -446,7 +453,12 @@ ctc_greedy_kernel(const float* __restrict__ logits, int T, int V, const int* __r
   if (lane == 0) ntokens[b] = count;
 }
 
-static int ni_for_states(int Smax) { return (2 * Smax + 1 <= 128) ? 4 : ((2 * Smax + 1 <= 256) ? 8 : 0); }
+// states per lane: 2 * Smax + 1 states over 32 lanes (up to 511 labels; a 20 s utterance has 999 frames)
+static int ni_for_states(int Smax) {
+  const int ns = 2 * Smax + 1;
+  return ns <= 128 ? 4 : (ns <= 256 ? 8 : (ns <= 512 ? 16 : (ns <= 1024 ? 32 : 0)));
+}
+static size_t bp_word_bytes(int ni) { return ni <= 8 ? 2 : (ni == 16 ? 4 : 8); }
 
 }  // namespace aptai
 
@@ -476,7 +488,7 @@ extern "C" int aptai_logsoftmax_ctc_ex(const float* logits, int B, int T, int V,
   APTAI_REQUIRE(logits && targets && input_len && target_len && nll && ws, "ctc: null pointer");
   APTAI_REQUIRE(B >= 1 && T >= 1 && V >= 1 && Smax >= 1, "ctc: bad shape");
   const int ni = ni_for_states(Smax);
-  APTAI_REQUIRE(ni != 0, "ctc: Smax=%d exceeds the 127-label limit of the register-resident state vector", Smax);
+  APTAI_REQUIRE(ni != 0, "ctc: Smax=%d exceeds the 511-label limit of the register-resident state vector", Smax);
   const int Veff = V + (prepend_blank ? 1 : 0);
   APTAI_REQUIRE(blank >= 0 && blank < Veff, "ctc: blank index out of range");
   const size_t need = aptai_ctc_workspace_bytes(B, T, Smax);
@@ -501,7 +513,9 @@ extern "C" int aptai_logsoftmax_ctc_ex(const float* logits, int B, int T, int V,
   const size_t smem = sizeof(int) * (sp + sp) + sizeof(float) * (CTC_THREADS / 32) * (sp + Veff);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (ni == 4) ctc_kernel<4><<<B, CTC_THREADS, smem, st>>>(a);
-  else ctc_kernel<8><<<B, CTC_THREADS, smem, st>>>(a);
+  else if (ni == 8) ctc_kernel<8><<<B, CTC_THREADS, smem, st>>>(a);
+  else if (ni == 16) ctc_kernel<16><<<B, CTC_THREADS, smem, st>>>(a);
+  else ctc_kernel<32><<<B, CTC_THREADS, smem, st>>>(a);
   if (int rc = after_launch("logsoftmax_ctc")) return rc;
   if (loss_sum) {
     ctc_reduce_kernel<<<1, 32, 0, st>>>(nll, scale, B, loss_sum);
@@ -519,8 +533,8 @@ extern "C" int aptai_logsoftmax_ctc(const float* logits, int B, int T, int V, co
 }
 
 extern "C" size_t aptai_viterbi_workspace_bytes(int B, int T, int Smax) {
-  (void)Smax;
-  return align_up(sizeof(uint16_t) * static_cast<size_t>(B) * T * 32, 256);
+  const int ni = ni_for_states(Smax);
+  return align_up(bp_word_bytes(ni ? ni : 32) * static_cast<size_t>(B) * T * 32, 256);
 }
 
 extern "C" int aptai_ctc_viterbi_f32(const float* log_probs, const int32_t* targets, const int32_t* input_len,
@@ -532,14 +546,14 @@ extern "C" int aptai_ctc_viterbi_f32(const float* log_probs, const int32_t* targ
   APTAI_REQUIRE(B >= 1 && T >= 1 && C >= 1 && Smax >= 1, "viterbi: bad shape");
   APTAI_REQUIRE(blank >= 0 && blank < C, "viterbi: blank index out of range");
   const int ni = ni_for_states(Smax);
-  APTAI_REQUIRE(ni != 0, "viterbi: Smax=%d exceeds the 127-label limit", Smax);
+  APTAI_REQUIRE(ni != 0, "viterbi: Smax=%d exceeds the 511-label limit", Smax);
   VitArgs a;
   a.lp = log_probs; a.targets = targets; a.input_len = input_len; a.target_len = target_len;
   a.B = B; a.T = T; a.C = C; a.Smax = Smax; a.blank = blank;
   a.paths = paths; a.scores = scores; a.status = status;
-  const size_t bp_bytes = sizeof(uint16_t) * static_cast<size_t>(T) * 32;
+  const size_t bp_bytes = bp_word_bytes(ni) * static_cast<size_t>(T) * 32;
   a.bp_in_smem = bp_bytes <= 200 * 1024;
-  a.bp_global = reinterpret_cast<uint16_t*>(ws);
+  a.bp_global = ws;
   if (!a.bp_in_smem) {
     const size_t need = aptai_viterbi_workspace_bytes(B, T, Smax);
     if (!ws || ws_bytes < need) {
@@ -550,13 +564,17 @@ extern "C" int aptai_ctc_viterbi_f32(const float* log_probs, const int32_t* targ
   const size_t smem = a.bp_in_smem ? bp_bytes : 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   cudaError_t e = cudaSuccess;
-  if (ni == 4) {
-    if (smem > 32 * 1024) e = cudaFuncSetAttribute(viterbi_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e == cudaSuccess) viterbi_kernel<4><<<B, 32, smem, st>>>(a);
-  } else {
-    if (smem > 32 * 1024) e = cudaFuncSetAttribute(viterbi_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e == cudaSuccess) viterbi_kernel<8><<<B, 32, smem, st>>>(a);
-  }
+#define APTAI_VIT_LAUNCH(N)                                                                                          \
+  do {                                                                                                              \
+    if (smem > 32 * 1024)                                                                                           \
+      e = cudaFuncSetAttribute(viterbi_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);         \
+    if (e == cudaSuccess) viterbi_kernel<N><<<B, 32, smem, st>>>(a);                                                \
+  } while (0)
+  if (ni == 4) APTAI_VIT_LAUNCH(4);
+  else if (ni == 8) APTAI_VIT_LAUNCH(8);
+  else if (ni == 16) APTAI_VIT_LAUNCH(16);
+  else APTAI_VIT_LAUNCH(32);
+#undef APTAI_VIT_LAUNCH
   if (e != cudaSuccess) {
     set_error("viterbi: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     return static_cast<int>(e);

@@ -422,24 +422,27 @@ __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
 // erf-GELU for consumers that round the result to 16 bits: x * Phi(x) with Phi(x) = 1 / (1 + 2^(x q(min(x^2, 64)))),
 // q(t) = -log2(e) (c0 + c1 t + c2 t^2) the minimax fit of logit(Phi(x)) / x (max abs error 2.6e-5 against the fp64
 // definition over all x: a hundred times below the bf16 / fp16 rounding of any value that matters; x^2 is clamped so
-// that the fitted polynomial is never used beyond |x| = 8, where Phi is 0 or 1 to 1e-15).  7 instructions per
-// element on the packed fp32x2 pipe against 12 for gelu_erf2 — the FFN1 and conv epilogues are issue-bound on it.
+// that the fitted polynomial is never used beyond |x| = 8, where Phi is 0 or 1 to 1e-15).  Evaluated through ONE
+// MUFU per element: 1 / (1 + e^-z) = 0.5 + 0.5 tanh(z / 2), so x Phi(x) = hx + hx tanh(-ln2/2 * x q), hx = x / 2.
+// MUFU.TANH on sm_100 is far better than its 2^-11 specification on this argument range: measured on B200 against
+// fp64 (profiles/scripts/mufu_accuracy.cu) the tanh form has max abs error 3.0e-5 / rms 1.23e-5, the ex2 + rcp form
+// it replaces 2.5e-5 / 1.23e-5 (both are the fit's error).  5 packed + 4 scalar instructions per pair, 1 MUFU per
+// element instead of 2 — the conv-0 kernel and the FFN1 / conv epilogues are MUFU- and issue-bound on it.
 // fp32 outputs (and the accuracy mode) keep gelu_erf / gelu_erf2.
 __device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
   const uint64_t x = f32x2_pack(x0, x1);
-  float t0, t1, a0, a1, e0, e1, d0, d1, r0, r1;
+  float t0, t1, a0, a1, h0, h1;
   f32x2_unpack(f32x2_mul(x, x), t0, t1);
   const uint64_t t = f32x2_pack(fminf(t0, 64.f), fminf(t1, 64.f));
-  uint64_t q = f32x2_fma(t, f32x2_pack(0.0010148165747523308f, 0.0010148165747523308f),
-                         f32x2_pack(-0.10677912831306458f, -0.10677912831306458f));
-  q = f32x2_fma(q, t, f32x2_pack(-2.3011176586151123f, -2.3011176586151123f));
+  constexpr float K = -0.34657359027997264f;                       // -ln(2) / 2
+  uint64_t q = f32x2_fma(t, f32x2_pack(0.0010148165747523308f * K, 0.0010148165747523308f * K),
+                         f32x2_pack(-0.10677912831306458f * K, -0.10677912831306458f * K));
+  q = f32x2_fma(q, t, f32x2_pack(-2.3011176586151123f * K, -2.3011176586151123f * K));
   f32x2_unpack(f32x2_mul(q, x), a0, a1);
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
-  f32x2_unpack(f32x2_add(f32x2_pack(e0, e1), f32x2_pack(1.f, 1.f)), d0, d1);
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d0));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
-  f32x2_unpack(f32x2_mul(x, f32x2_pack(r0, r1)), x0, x1);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(h0) : "f"(a0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(h1) : "f"(a1));
+  const uint64_t hx = f32x2_mul(x, f32x2_pack(0.5f, 0.5f));
+  f32x2_unpack(f32x2_fma(hx, f32x2_pack(h0, h1), hx), x0, x1);
 }
 
 // Two GELU derivatives at once on the packed fp32x2 pipe: g0 *= gelu'(u0), g1 *= gelu'(u1)

@@ -458,13 +458,14 @@ def masked_mse_ce(tv_pred, tv_tgt, logits, phn_tgt, return_ws: bool = False):
     return out
 
 
-CTC_MAX_LABELS = 127      # labels per utterance the fused CTC / Viterbi kernels hold (2S+1 states in registers)
+CTC_MAX_LABELS = 511      # labels per utterance the fused CTC / Viterbi kernels hold (2S+1 states in registers, <= 32 per lane)
+CTC_FAST_LABELS = 127     # up to here (<= 8 states per lane) a padded label tensor is passed as is
 
 
 def _trim_targets(targets: torch.Tensor, target_len: torch.Tensor, what: str) -> torch.Tensor:
     """The kernels' label limit applies to the LONGEST transcript, not to the padded width of the label tensor: a
     batch padded wider than the limit is narrowed to max(target_len) (one device->host read, only in that case)."""
-    if targets.shape[1] <= CTC_MAX_LABELS:
+    if targets.shape[1] <= CTC_FAST_LABELS:
         return targets
     m = max(1, int(target_len.max()))
     if m > CTC_MAX_LABELS:
@@ -488,7 +489,7 @@ def logsoftmax_ctc(logits: torch.Tensor, targets: torch.Tensor, input_len: torch
     L = _lib.load()
     nbytes = L.aptai_ctc_workspace_bytes(B, T, Smax)
     if nbytes == 0:
-        raise ValueError(f"logsoftmax_ctc: Smax={Smax} unsupported (limit 127 labels)")
+        raise ValueError(f"logsoftmax_ctc: Smax={Smax} unsupported (limit {CTC_MAX_LABELS} labels)")
     ws = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
     nll = torch.empty((B,), dtype=F32, device=dev)
     loss_sum = torch.empty((1,), dtype=F32, device=dev)

@@ -213,6 +213,8 @@ int aptai_masked_mse_ce(const float* tv_pred, const float* tv_tgt, const float* 
  * targets int32 [B][Smax]; entries at s >= target_len[b] are ignored.  log_probs_tbv (optional) fp32 [T][B][V].
  * nll[b] = -log p(target|input) (0 where infeasible and zero_infinity).  grad (optional) fp32 [B][T][V] is
  * d(sum_b scale[b]*nll[b])/d logits, scale may be NULL (= 1).  Workspace: aptai_ctc_workspace_bytes().
+ * Smax <= 511 (the 2 * Smax + 1 DP states are register-resident, 4 / 8 / 16 / 32 per lane; the same limit holds for
+ * aptai_ctc_viterbi_f32); aptai_ctc_workspace_bytes() returns 0 beyond it.
  */
 size_t aptai_ctc_workspace_bytes(int B, int T, int Smax);
 int aptai_logsoftmax_ctc(const float* logits, int B, int T, int V, const int32_t* targets, int Smax,

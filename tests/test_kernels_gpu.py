@@ -147,9 +147,13 @@ def _ctc_case(B, T, V, Smax, seed, repeats=False):
     return logits, tg, il, tl
 
 
-@pytest.mark.parametrize("B,T,V,Smax,rep", [(4, 60, 12, 9, True), (16, 399, 46, 59, False), (3, 50, 46, 100, True)])
+@pytest.mark.parametrize("B,T,V,Smax,rep", [(4, 60, 12, 9, True), (16, 399, 46, 59, False), (3, 50, 46, 100, True),
+                                                (3, 999, 46, 200, True), (3, 999, 46, 450, True)])
 def test_logsoftmax_ctc(cuda, B, T, V, Smax, rep):
     logits, tg, il, tl = _ctc_case(B, T, V, Smax, 3, rep)
+    if Smax >= 200:                             # 16 / 32 states per lane: one full-width feasible transcript
+        tl[0] = Smax
+        tg[0] = 1 + (np.arange(Smax) * 7 % (V - 1))
     if B >= 3:
         tl[1] = min(Smax, il[1] + 1)            # infeasible: more labels than frames -> zero_infinity
         tg[1, : tl[1]] = 1 + (np.arange(tl[1]) % (V - 1))
@@ -182,7 +186,8 @@ def test_forward_sum(cuda):
     assert abs(float(r["loss_sum"].cpu()) - loss_ref) <= 1e-3 * abs(loss_ref)
 
 
-@pytest.mark.parametrize("B,T,C,Smax", [(64, 399, 46, 59), (8, 40, 5, 12), (4, 999, 46, 100), (3, 765, 46, 59)])
+@pytest.mark.parametrize("B,T,C,Smax", [(64, 399, 46, 59), (8, 40, 5, 12), (4, 999, 46, 100), (3, 765, 46, 59),
+                                        (4, 999, 46, 200), (4, 999, 46, 450)])
 def test_viterbi_bit_exact(cuda, B, T, C, Smax):
     rng = np.random.default_rng(11)
     x = rng.standard_normal((B, T, C)).astype(np.float32)
@@ -193,6 +198,8 @@ def test_viterbi_bit_exact(cuda, B, T, C, Smax):
     il = rng.integers(max(2 * Smax, T // 2), T + 1, size=B).astype(np.int32) if T >= 4 * Smax else np.full(B, T, np.int32)
     il[0] = T
     tg = np.zeros((B, Smax), dtype=np.int32)
+    if Smax >= 200:
+        tl[0] = Smax                                        # il[0] = T: the widest transcript is used in full
     for b in range(B):
         tl[b] = min(tl[b], il[b] // 2)
         tg[b, : tl[b]] = rng.integers(1, C, size=tl[b])
