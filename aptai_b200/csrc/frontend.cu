@@ -319,21 +319,40 @@ extern "C" int aptai_conv0_accurate(const float* wav, int B, int64_t L, const fl
   return after_launch("conv0_accurate");
 }
 
+namespace aptai {
+int conv0_tc_launch(const float* wav, int B, int64_t L, int T0, const float* w, const float* bias, const float* gamma,
+                    const float* beta, int norm, float eps, const float* consts, const float* affine, void* ws_b,
+                    void* out16, int out_fp16, cudaStream_t st);       // conv0_tc.cu
+}
+
+// stats_ws layout: [statistics: norm 1 -> 1 KB of closed-form constants; norm 2 -> B*65 doubles of moments +
+// B*512*2 floats of scale/shift; norm 0 -> nothing] then, 256-byte aligned, the 64 KB split weight operand of the
+// tensor-core kernel
+static size_t conv0_stats_bytes(int B, int norm) {
+  const size_t s = norm == 1 ? 1024 : (norm == 2 ? sizeof(double) * B * (K0 + NQ) + sizeof(float) * B * C0 * 2 : 0);
+  return (s + 255) / 256 * 256;
+}
+extern "C" size_t aptai_conv0_workspace_bytes(int B, int norm) { return conv0_stats_bytes(B, norm) + C0 * 64 * 2; }
+
 extern "C" int aptai_conv0_norm_gelu(const float* wav, int B, int64_t L, const float* w, const float* bias,
                                      const float* gamma, const float* beta, int norm, float eps, void* out_bf16,
-                                     int T0, float* stats_ws, int out_fp16, void* stream) {
+                                     int T0, float* stats_ws, int flags, void* stream) {
   if (int rc = check_arch()) return rc;
-  APTAI_REQUIRE(wav && w && out_bf16, "conv0: null pointer");
+  const int out_fp16 = flags & 1;
+  const bool simt = (flags & 2) != 0;
+  APTAI_REQUIRE(wav && w && out_bf16 && stats_ws, "conv0: null pointer");
   APTAI_REQUIRE(B >= 1 && L >= K0, "conv0: bad shape B=%d L=%lld", B, (long long)L);
   APTAI_REQUIRE(T0 == (L - K0) / S0 + 1, "conv0: T0=%d does not match L=%lld", T0, (long long)L);
   APTAI_REQUIRE(norm >= 0 && norm <= 2, "conv0: norm must be 0, 1 or 2");
-  APTAI_REQUIRE(norm == 0 || (gamma && beta && stats_ws), "conv0: norm needs gamma, beta and stats_ws");
+  APTAI_REQUIRE(norm == 0 || (gamma && beta), "conv0: norm needs gamma and beta");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid((T0 + FT - 1) / FT, B);
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  void* ws_b = reinterpret_cast<char*>(stats_ws) + conv0_stats_bytes(B, norm);
   if (norm == 1) {
     conv0_ln_consts_kernel<<<1, 128, 0, st>>>(w, bias, stats_ws);
     if (int rc = after_launch("conv0_ln_consts")) return rc;
+    if (!simt) return conv0_tc_launch(wav, B, L, T0, w, bias, gamma, beta, 1, eps, stats_ws, nullptr, ws_b, out, out_fp16, st);
     conv0_kernel<1><<<grid, 256, 0, st>>>(wav, L, T0, w, bias, gamma, beta, stats_ws, nullptr, eps, out, out_fp16);
   } else if (norm == 2) {
     // stats_ws: [B*65] doubles of moments, then [B*512*2] floats of scale/shift
@@ -350,8 +369,10 @@ extern "C" int aptai_conv0_norm_gelu(const float* wav, int B, int64_t L, const f
     if (int rc = after_launch("conv0_gn_moments")) return rc;
     conv0_gn_affine_kernel<<<B, C0, 0, st>>>(mom, w, bias, gamma, beta, T0, eps, affine);
     if (int rc = after_launch("conv0_gn_affine")) return rc;
+    if (!simt) return conv0_tc_launch(wav, B, L, T0, w, bias, gamma, beta, 2, eps, nullptr, affine, ws_b, out, out_fp16, st);
     conv0_kernel<2><<<grid, 256, 0, st>>>(wav, L, T0, w, bias, gamma, beta, nullptr, affine, eps, out, out_fp16);
   } else {
+    if (!simt) return conv0_tc_launch(wav, B, L, T0, w, bias, gamma, beta, 0, eps, nullptr, nullptr, ws_b, out, out_fp16, st);
     conv0_kernel<0><<<grid, 256, 0, st>>>(wav, L, T0, w, bias, gamma, beta, nullptr, nullptr, eps, out, out_fp16);
   }
   return after_launch("conv0_norm_gelu");

@@ -42,6 +42,7 @@ PROTOTYPES = {
     "aptai_launch_count": (c_i64, []),
     "aptai_gemm_bf16": (c_int, [C.POINTER(GemmArgs), c_void_p]),
     "aptai_set_traversal": (None, [c_int]),
+    "aptai_conv0_workspace_bytes": (c_size_t, [c_int, c_int]),
     "aptai_conv0_norm_gelu": (c_int, [c_void_p, c_int, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float,
                                       c_void_p, c_int, c_void_p, c_int, c_void_p]),
     "aptai_layernorm": (c_int, [c_void_p, c_int, c_i64, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p,

@@ -212,16 +212,20 @@ def posconv(x_pad: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], 
     return out_f32
 
 
+CONV0_TC = int(os.environ.get("APTAI_CONV0_TC", "1"))     # 0: the SIMT conv-0 kernel (A/B runs)
+
+
 def conv0(wav: torch.Tensor, w: torch.Tensor, bias, gamma, beta, norm: int, eps: float = 1e-5,
           out_dtype=None, return_ws: bool = False):
     _req(wav, F32, "wav"); _req(w, F32, "w")
     B, L = wav.shape
     T0 = (L - 10) // 5 + 1
     out = alloc_rows_bf16(B, T0, 512, wav.device, dtype=out_dtype or BF16)
-    ws = torch.empty((max(256, B * (65 * 2 + 1024) + 16),), dtype=F32, device=wav.device) if norm else None
-    check(_lib.load().aptai_conv0_norm_gelu(wav.data_ptr(), B, L, w.data_ptr(), _ptr(bias), _ptr(gamma), _ptr(beta),
-                                            norm, eps, out.data_ptr(), T0, _ptr(ws), int(out.dtype == F16), _stream()),
-          "conv0_norm_gelu")
+    L_ = _lib.load()
+    ws = torch.empty((L_.aptai_conv0_workspace_bytes(B, norm) // 4,), dtype=F32, device=wav.device)
+    flags = int(out.dtype == F16) | (0 if CONV0_TC else 2)
+    check(L_.aptai_conv0_norm_gelu(wav.data_ptr(), B, L, w.data_ptr(), _ptr(bias), _ptr(gamma), _ptr(beta),
+                                   norm, eps, out.data_ptr(), T0, ws.data_ptr(), flags, _stream()), "conv0_norm_gelu")
     if return_ws:
         return out, ws
     return out

@@ -96,11 +96,17 @@ void aptai_set_traversal(int reverse);
  * conv layer 0 (1 -> 512 channels, kernel 10, stride 5) + norm + GELU, channels-last bf16 output [B][T0][512].
  * norm=1: LayerNorm over channels per frame (HF:281-299).  norm=2: GroupNorm(512 groups) over time per
  * channel, statistics over all T0 frames of the padded row (HF:308-323).  norm=0: none (HF:260-272).
- * w is fp32 [512][10]; bias may be NULL.  stats_ws: 2*B*512 floats (norm=2 only).
+ * w is fp32 [512][10]; bias may be NULL.  stats_ws: aptai_conv0_workspace_bytes(B, norm) bytes, 256-byte aligned
+ * (normalisation statistics — for norm=2 B*65 doubles of waveform moments followed by the [B][512][2] scale / shift
+ * array the backward pass re-uses — then the 64 KB split-bf16 weight operand of the tensor-core kernel).
+ * flags: bit 0 = the 16-bit output is IEEE fp16 instead of bf16; bit 1 = run the SIMT kernel instead of the
+ * tcgen05 one (csrc/conv0_tc.cu: the K = 10 contraction on three-term split bf16 operands, fp32-exact to 2^-24) —
+ * for A/B measurements, the results agree to fp32 rounding.
  */
+size_t aptai_conv0_workspace_bytes(int B, int norm);
 int aptai_conv0_norm_gelu(const float* wav, int B, int64_t L, const float* w, const float* bias,
                           const float* gamma, const float* beta, int norm, float eps, void* out_bf16, int T0,
-                          float* stats_ws, int out_fp16, void* stream);
+                          float* stats_ws, int flags, void* stream);
 
 /* LayerNorm over the last dim (HF:431, 600-602, 639, 645, 692, 792): fp32 / bf16 / fp16 in, fp32 and/or 16-bit
  * (bf16, or fp16 when out16_fp16) out. */
