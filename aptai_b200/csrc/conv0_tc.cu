@@ -176,7 +176,7 @@ conv0_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const Conv0TcParams p
       const int b = tile / p.tiles_per_utt, ft = tile - b * p.tiles_per_utt;
       float* xs = reinterpret_cast<float*>(smem + OFF_X + s * X_BYTES);
       if (p.x_tma) {
-        mbar_wait(&x_full[s], u);
+        mbar_wait_backoff(&x_full[s], u, 100);
       } else {
         uint32_t bytes;
         const float* src = x_src(tile, bytes);
@@ -247,8 +247,10 @@ conv0_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const Conv0TcParams p
           row[i] = static_cast<uint32_t>(__bfloat16_as_ushort(e[2 * i])) |
                    (static_cast<uint32_t>(__bfloat16_as_ushort(e[2 * i + 1])) << 16);
       }
-      mbar_wait(&a_empty[s], u ^ 1);
-      mbar_wait(&st_empty[s], u ^ 1);
+      // the builders run up to two tiles ahead of the epilogue: wait with a back-off, their spinning would take issue
+      // slots from the epilogue warps (12 % of all issued instructions in the first capture)
+      mbar_wait_backoff(&a_empty[s], u ^ 1, 200);
+      mbar_wait_backoff(&st_empty[s], u ^ 1, 200);
       uint8_t* arow = smem + OFF_A + s * A_BYTES + bt * 128;
 #pragma unroll
       for (int j = 0; j < 8; ++j)
@@ -271,9 +273,10 @@ conv0_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const Conv0TcParams p
           g4 = make_float4(1.f, 1.f, 1.f, 1.f);
           e4 = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        // pre-halved: the epilogue's GELU takes x / 2 (gelu_fast2_half)
         float4* vec = reinterpret_cast<float4*>(smem + OFF_VEC + s * 2 * C0 * 4);
-        vec[bt] = g4;
-        vec[C0 / 4 + bt] = e4;
+        vec[bt] = make_float4(0.5f * g4.x, 0.5f * g4.y, 0.5f * g4.z, 0.5f * g4.w);
+        vec[C0 / 4 + bt] = make_float4(0.5f * e4.x, 0.5f * e4.y, 0.5f * e4.z, 0.5f * e4.w);
       }
       fence_async_proxy();                               // the A row is read by the tensor core (async proxy)
       mbar_arrive(&a_full[s]);
@@ -286,9 +289,9 @@ conv0_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const Conv0TcParams p
     for (int tile = tile0; tile < p.num_tiles; tile += tstep, ++k) {
       const int s = k & 1;
       const uint32_t u = static_cast<uint32_t>(k >> 1) & 1u;
-      mbar_wait(&a_full[s], u);
+      mbar_wait_backoff(&a_full[s], u, 32);
       for (int h = 0; h < 2; ++h) {
-        mbar_wait(&acc_empty[h], (static_cast<uint32_t>(k) & 1u) ^ 1u);
+        mbar_wait_backoff(&acc_empty[h], (static_cast<uint32_t>(k) & 1u) ^ 1u, 32);
         tc_fence_after();
         if (elect_one()) {
           const uint64_t adesc0 = umma_desc_sw128(smem_base + OFF_A + s * A_BYTES);
@@ -327,35 +330,23 @@ conv0_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const Conv0TcParams p
           nmr2 = f32x2_pack(st.y, st.y);
         }
         const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + h * 256 + cp * 128;
-        uint32_t nxt[32];
-        tmem_ld32(t_row, nxt);
-#pragma unroll 1
-        for (int ch = 0; ch < 4; ++ch) {
-          tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(nxt[i]);
-          if (ch + 1 < 4) {
-            tmem_ld32(t_row + (ch + 1) * 32, nxt);
-          } else {
-            // the last chunk of this half is in registers: hand the accumulator half back to the MMA issuer
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[h]);
-          }
+        // one 32-column chunk: normalise (the scale / shift vectors are pre-halved: the GELU wants x / 2), GELU, pack,
+        // stage; every second chunk completes a 32-row x 128-byte slab that one TMA store writes
+        auto process = [&](uint32_t (&r)[32], int ch) {
           const int c0 = h * 256 + cp * 128 + ch * 32;
+          float v[32];
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const float4 g4 = *reinterpret_cast<const float4*>(vecG + c0 + i);
             const float4 e4 = *reinterpret_cast<const float4*>(vecE + c0 + i);
-            uint64_t y01 = f32x2_fma(f32x2_pack(v[i], v[i + 1]), rs2, nmr2);
-            uint64_t y23 = f32x2_fma(f32x2_pack(v[i + 2], v[i + 3]), rs2, nmr2);
+            uint64_t y01 = f32x2_fma(f32x2_pack(__uint_as_float(r[i]), __uint_as_float(r[i + 1])), rs2, nmr2);
+            uint64_t y23 = f32x2_fma(f32x2_pack(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])), rs2, nmr2);
             y01 = f32x2_fma(y01, f32x2_pack(g4.x, g4.y), f32x2_pack(e4.x, e4.y));
             y23 = f32x2_fma(y23, f32x2_pack(g4.z, g4.w), f32x2_pack(e4.z, e4.w));
             f32x2_unpack(y01, v[i], v[i + 1]);
             f32x2_unpack(y23, v[i + 2], v[i + 3]);
-            gelu_fast2(v[i], v[i + 1]);
-            gelu_fast2(v[i + 2], v[i + 3]);
+            gelu_fast2_half(v[i], v[i + 1]);
+            gelu_fast2_half(v[i + 2], v[i + 3]);
           }
           const int hsel = ch & 1;               // which 64-byte half of the slab's 128-byte rows this chunk fills
           uint4* sb = reinterpret_cast<uint4*>(stg + slab * SLAB);
@@ -363,11 +354,10 @@ conv0_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const Conv0TcParams p
             if (lane == 0) tma_store_wait_read<1>();      // the store that last read THIS slab (two stores ago) is done
             __syncwarp();
           }
+          uint4 o16[4];
+          pack32_h16(v, o16, p.out_fp16);
 #pragma unroll
-          for (int uu = 0; uu < 4; ++uu)
-            sb[lane * 8 + ((hsel * 4 + uu) ^ (lane & 7))] =
-                make_uint4(pack_h16(v[8 * uu], v[8 * uu + 1], p.out_fp16), pack_h16(v[8 * uu + 2], v[8 * uu + 3], p.out_fp16),
-                           pack_h16(v[8 * uu + 4], v[8 * uu + 5], p.out_fp16), pack_h16(v[8 * uu + 6], v[8 * uu + 7], p.out_fp16));
+          for (int uu = 0; uu < 4; ++uu) sb[lane * 8 + ((hsel * 4 + uu) ^ (lane & 7))] = o16[uu];
           if (hsel == 1) {
             fence_async_proxy();
             __syncwarp();
@@ -377,7 +367,25 @@ conv0_tc_kernel(const __grid_constant__ CUtensorMap tmOut, const Conv0TcParams p
             }
             slab ^= 1;
           }
-        }
+        };
+        // two register arrays alternate: the tcgen05.ld of chunk c + 1 is in flight while chunk c is processed
+        uint32_t ra[32], rb[32];
+        tmem_ld32(t_row, ra);
+        tmem_ld_wait_regs(ra);
+        tmem_ld32(t_row + 32, rb);
+        process(ra, 0);
+        tmem_ld_wait_regs(rb);
+        tmem_ld32(t_row + 64, ra);
+        process(rb, 1);
+        tmem_ld_wait_regs(ra);
+        tmem_ld32(t_row + 96, rb);
+        process(ra, 2);
+        tmem_ld_wait_regs(rb);
+        // the last chunk of this half is in registers: hand the accumulator half back to the MMA issuer
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[h]);
+        process(rb, 3);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&st_empty[s]);          // statistics and vectors of this tile have been consumed

@@ -256,6 +256,17 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
       : "r"(taddr)
       : "memory");
 }
+// tcgen05.wait::ld that also names the 32 destination registers of the load it waits for: the compiler cannot schedule a
+// use of them above the wait, and needs no copies to keep two loads in flight in alternating register arrays
+__device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- UMMA descriptors
@@ -445,6 +456,25 @@ __device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
   f32x2_unpack(f32x2_fma(hx, f32x2_pack(h0, h1), hx), x0, x1);
 }
 
+// gelu_fast2 for callers that can produce HALF the argument for free (a normalisation whose scale / shift vectors are
+// pre-halved): h = x / 2 in, x Phi(x) = h + h tanh(h q'(h^2)) out, q' = gelu_fast2's polynomial re-scaled to t' = x^2 / 4.
+// One packed multiply fewer than gelu_fast2 (4 packed + 2 scalar + 2 MUFU per pair).
+__device__ __forceinline__ void gelu_fast2_half(float& h0, float& h1) {
+  const uint64_t h = f32x2_pack(h0, h1);
+  float t0, t1, a0, a1, th0, th1;
+  f32x2_unpack(f32x2_mul(h, h), t0, t1);
+  const uint64_t t = f32x2_pack(fminf(t0, 16.f), fminf(t1, 16.f));
+  constexpr float K = -0.34657359027997264f;                       // -ln(2) / 2
+  constexpr float C2 = 32.f * 0.0010148165747523308f * K, C1 = 8.f * -0.10677912831306458f * K,
+                  C0 = 2.f * -2.3011176586151123f * K;
+  uint64_t q = f32x2_fma(t, f32x2_pack(C2, C2), f32x2_pack(C1, C1));
+  q = f32x2_fma(q, t, f32x2_pack(C0, C0));
+  f32x2_unpack(f32x2_mul(q, h), a0, a1);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th0) : "f"(a0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th1) : "f"(a1));
+  f32x2_unpack(f32x2_fma(h, f32x2_pack(th0, th1), h), h0, h1);
+}
+
 // Two GELU derivatives at once on the packed fp32x2 pipe: g0 *= gelu'(u0), g1 *= gelu'(u1)
 __device__ __forceinline__ void gelu_erf_grad2_mul(float& g0, float& g1, float u0, float u1) {
   const uint64_t x = f32x2_pack(u0, u1);
@@ -495,6 +525,21 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 
 __device__ __forceinline__ uint32_t pack_h16(float a, float b, int fp16) {
   return fp16 ? pack_f16(a, b) : pack_bf16(a, b);
+}
+// 32 floats -> four 16-byte units of 16-bit values under ONE (warp-uniform) format branch: the per-pair select of
+// pack_h16 compiles to a predicated F2FP.F16 AND a predicated F2FP.BF16 per pair — two issue slots where one does work
+__device__ __forceinline__ void pack32_h16(const float (&v)[32], uint4 (&o)[4], int fp16) {
+  if (fp16) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      o[u] = make_uint4(pack_f16(v[8 * u], v[8 * u + 1]), pack_f16(v[8 * u + 2], v[8 * u + 3]),
+                        pack_f16(v[8 * u + 4], v[8 * u + 5]), pack_f16(v[8 * u + 6], v[8 * u + 7]));
+  } else {
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      o[u] = make_uint4(pack_bf16(v[8 * u], v[8 * u + 1]), pack_bf16(v[8 * u + 2], v[8 * u + 3]),
+                        pack_bf16(v[8 * u + 4], v[8 * u + 5]), pack_bf16(v[8 * u + 6], v[8 * u + 7]));
+  }
 }
 
 }  // namespace aptai
