@@ -47,7 +47,9 @@ struct GemmParams {
   const float* l2_hint;       // red32: the rows the reduction will touch, prefetched into L2 one tile ahead
 };
 
-template <int BN, bool CTA2>
+constexpr int LN_N = 512;     // row width of the fused-LayerNorm tiles (conv_dim)
+
+template <int BN, bool CTA2, bool LN = false>
 struct GemmCfg {
   // Epilogue warps.  The fused-LayerNorm tile (BN = 512) cannot double-buffer its accumulator (512 TMEM columns), so
   // MMA and epilogue alternate; 16 epilogue warps (four per TMEM lane quadrant, 128 columns each; the LN code below is
@@ -57,7 +59,7 @@ struct GemmCfg {
   static constexpr int EPI_W = 8;
   static constexpr int EPI_T = EPI_W * 32;
   static constexpr int W_TMA = EPI_W, W_MMA = EPI_W + 1, W_ALLOC = EPI_W + 2;
-  static constexpr int THREADS = BN >= 512 ? (EPI_W + 3) * 32 : 384;
+  static constexpr int THREADS = LN ? (EPI_W + 3) * 32 : 384;
   static constexpr int UN = BN > 256 ? 256 : BN;                 // N of one tcgen05.mma
   static constexpr int NPAIR = CTA2 ? 2 : 1;                     // CTAs cooperating on one tile (cta_group)
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;          // per CTA: its own 128 rows of A
@@ -68,21 +70,25 @@ struct GemmCfg {
   // 32 cycles of work each, so two CTAs per SM (two issuing threads) are worth more than a deep ring
   static constexpr int CTAS_PER_SM = (BN <= 64 && !CTA2) ? 2 : 1;
   // the fused-LayerNorm tile (BN = 512) gives one pipeline stage to the epilogue's TMA-store staging buffers
-  static constexpr int STAGES = CTAS_PER_SM == 2 ? 3 : (STAGE_BYTES > 64 * 1024 ? 2 : (STAGE_BYTES > 40 * 1024 ? (BN >= 512 ? 3 : 4) : 6));
+  // the half-split LayerNorm tile (LN, BN = 256: see gemm_body) fits five 32 KB stages (pair) / three 48 KB stages
+  // next to its staging, statistics and vector buffers
+  static constexpr int STAGES = CTAS_PER_SM == 2 ? 3
+                                : (LN && BN == 256) ? (CTA2 ? 5 : 3)
+                                : (STAGE_BYTES > 64 * 1024 ? 2 : (STAGE_BYTES > 40 * 1024 ? (BN >= 512 ? 3 : 4) : 6));
   static constexpr int ACC_STRIDE = BN < 64 ? 64 : BN;
   static constexpr int ACC_STAGES = (2 * ACC_STRIDE <= 512) ? 2 : 1;
   static constexpr int TMEM_COLS = ACC_STAGES * ACC_STRIDE <= 128 ? 128 : (ACC_STAGES * ACC_STRIDE <= 256 ? 256 : 512);
   static constexpr int CHUNK = (BN % 64 == 0) ? 32 : 8;          // columns per tcgen05.ld in the epilogue
   static constexpr int BAR_BYTES = 256;
-  static constexpr int LN_BYTES = BN >= 512 ? 2 * 4 * BLOCK_M * sizeof(float2) : 0;   // LN statistics exchange
+  static constexpr int LN_BYTES = LN ? 2 * 4 * BLOCK_M * sizeof(float2) : 0;   // LN statistics exchange
   static constexpr int STG_BYTES = EPI_W * 4096;                 // 4 KB staging buffer per epilogue warp
   // fused-LayerNorm tile: bias | gamma | beta of the whole 512-wide row live in shared memory, loaded once per CTA
   // (their per-element global loads were the top long-scoreboard stall of that epilogue: 27 % of the stall samples,
   // profiles/r01_gemm_convln.md).  The other tiles have no shared memory left for it (4 stages + 32 KB staging).
-  static constexpr int VEC_BYTES = BN >= 512 ? 3 * 512 * 4 : 0;
+  static constexpr int VEC_BYTES = LN ? 3 * LN_N * 4 : 0;
   // bias of the current N tile, double buffered by tile parity (the per-chunk __ldg of the bias was the top
   // long-scoreboard stall of the FFN1 epilogue: 18 % of the epilogue warps' samples, profiles/r02_gemm_ffn.md)
-  static constexpr int BIAS_BYTES = (BN % 64 == 0 && BN < 512) ? 2 * BN * 4 : 0;
+  static constexpr int BIAS_BYTES = (BN % 64 == 0 && !LN) ? 2 * BN * 4 : 0;
   // layout: [stages | staging (1024-aligned: it is the source of SWIZZLE_128B TMA stores) | barriers | LN | vectors]
   static constexpr int OFF_STG = STAGES * STAGE_BYTES;
   static constexpr int OFF_BAR = OFF_STG + STG_BYTES;
@@ -102,7 +108,14 @@ __device__ __forceinline__ void tmem_ld_chunk<8>(uint32_t taddr, uint32_t (&r)[8
 template <int BN, bool LN, bool CTA2>
 __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                                           const GemmParams& p) {
-  using C = GemmCfg<BN, CTA2>;
+  using C = GemmCfg<BN, CTA2, LN>;
+  // Half-split fused-LayerNorm tile (LN with BN = 256): the 512-wide row is produced as TWO 256-column accumulator
+  // halves, each over the whole K loop (the A k-blocks are fetched twice, from L2), so that the epilogue's statistics
+  // pass over half 0 runs under the MMAs of half 1 and its normalise / GELU / store pass over half 1 under the next
+  // tile's MMAs of half 0.  With the full-width tile (BN = 512) the accumulator fills the TMEM and MMA and epilogue
+  // alternate (tensor pipe 58 %, profiles/r02_gemm_convln.md).
+  constexpr bool LN2 = LN && BN == 256;
+  constexpr int NSUB = LN2 ? 2 : 1;            // accumulator halves per tile
   // the dynamic shared memory window starts 1024-byte aligned (no static shared memory in this kernel); checked, not
   // padded: the CTA-pair tile uses all but 768 bytes of the 227 KB
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -165,8 +178,9 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       uint32_t phase = 0;
       for (int tile_i = tile0; tile_i < p.num_tiles; tile_i += tile_step) {
         const int tile = p.reverse ? p.num_tiles - 1 - tile_i : tile_i;
-        const int n_blk = tile % p.n_tiles;
-        const int mt = tile / p.n_tiles;
+        for (int sub = 0; sub < NSUB; ++sub) {
+        const int n_blk = LN2 ? sub : tile % p.n_tiles;
+        const int mt = LN2 ? tile : tile / p.n_tiles;
         const int seg = mt / p.m_tiles_per_seg;
         const int r0 = (mt - seg * p.m_tiles_per_seg) * TILE_M + static_cast<int>(rank) * BLOCK_M;
         const int a_col0 = n_blk * p.a_col_per_nblk;
@@ -204,6 +218,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
             phase ^= 1;
           }
         }
+        }   // sub
       }
     }
   } else if (warp == W_MMA) {
@@ -220,6 +235,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       uint32_t acc_phase = 0;
       const uint32_t smem_base = smem_u32(smem);
       for (int tile = tile0; tile < p.num_tiles; tile += tile_step) {
+        for (int sub = 0; sub < NSUB; ++sub) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * C::ACC_STRIDE;
@@ -261,6 +277,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         } else {
           acc_phase ^= 1;
         }
+        }   // sub
       }
     }
   } else if (warp < EPI_WARPS) {
@@ -272,12 +289,14 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
     int acc = 0;
     uint32_t acc_phase = 0;
     int ln_buf = 0;
+    uint32_t ln2_phase = 0;                 // half-split LayerNorm tile: parity of tfull[0] / tfull[1] (one use per tile)
+    (void)ln2_phase;
     const uint32_t tempty_leader0 = CTA2 ? map_to_cta(&tempty_bar[0], 0) : 0u;
     if constexpr (LN) {
-      for (int i = threadIdx.x; i < BN; i += EPI_THREADS) {
+      for (int i = threadIdx.x; i < LN_N; i += EPI_THREADS) {
         vecs[i] = p.bias ? __ldg(p.bias + i) : 0.f;
-        vecs[BN + i] = __ldg(p.gamma + i);
-        vecs[2 * BN + i] = __ldg(p.beta + i);
+        vecs[LN_N + i] = __ldg(p.gamma + i);
+        vecs[2 * LN_N + i] = __ldg(p.beta + i);
       }
       named_bar_sync(1, EPI_THREADS);
     }
@@ -285,8 +304,8 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
     uint32_t tpar = 0;                       // tile parity: bias buffer of this tile
     for (int tile_i = tile0; tile_i < p.num_tiles; tile_i += tile_step, tpar ^= 1) {
       const int tile = p.reverse ? p.num_tiles - 1 - tile_i : tile_i;
-      const int n_blk = tile % p.n_tiles;
-      const int mt = tile / p.n_tiles;
+      const int n_blk = LN2 ? 0 : tile % p.n_tiles;
+      const int mt = LN2 ? tile : tile / p.n_tiles;
       const int seg = mt / p.m_tiles_per_seg;
       const int row_in_tile = q * 32 + lane;
       const float* bias_t = bias_s + tpar * BN;
@@ -329,11 +348,148 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
           }
         }
       }
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * C::ACC_STRIDE;
+      if constexpr (!LN2) {
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+      }
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (LN2 ? 0 : acc * C::ACC_STRIDE);
 
-      if constexpr (LN) {
+      if constexpr (LN2) {
+        // ---- half-split fused LayerNorm(512) + GELU tile: thread = one row x 128 columns of EACH 256-column
+        // accumulator half.  Pass 1 (shifted single-pass statistics of acc + bias) runs on half 0 while the tensor
+        // core still works on half 1; pass 2 (normalise, GELU, 16-bit slabs, TMA stores) releases half 0 to the next
+        // tile's MMAs before it turns to half 1.
+        constexpr int HN = 256;                               // columns per accumulator half
+        constexpr int NPART = EPI_WARPS / 4;                  // threads per row (2)
+        constexpr int PART_N = HN / NPART;                    // columns per thread and half (128)
+        const int part = warp >> 2;
+        const int cb = part * PART_N;
+        float pivot = 0.f;
+        uint64_t s1a = f32x2_pack(0.f, 0.f), s1b = s1a, s2a = s1a, s2b = s1a, npiv = s1a;
+        uint32_t nx[32];
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          mbar_wait(&tfull_bar[hh], ln2_phase);
+          tc_fence_after();
+          const uint32_t t_h = t_row + hh * HN + cb;
+          const float* bias_h = vecs + hh * HN + cb;
+          tmem_ld32(t_h, nx);
+          for (int c = 0; c < PART_N; c += 32) {
+            tmem_ld_wait();
+            uint32_t rr[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) rr[i] = nx[i];
+            if (c + 32 < PART_N) tmem_ld32(t_h + c + 32, nx);
+            if (hh == 0 && c == 0) {
+              pivot = __uint_as_float(rr[0]) + bias_h[0];
+              npiv = f32x2_pack(-pivot, -pivot);
+            }
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias_h + c + i);
+              const uint64_t d0 = f32x2_add(f32x2_add(f32x2_pack(__uint_as_float(rr[i]), __uint_as_float(rr[i + 1])),
+                                                      f32x2_pack(b4.x, b4.y)), npiv);
+              const uint64_t d1 = f32x2_add(f32x2_add(f32x2_pack(__uint_as_float(rr[i + 2]), __uint_as_float(rr[i + 3])),
+                                                      f32x2_pack(b4.z, b4.w)), npiv);
+              s1a = f32x2_add(s1a, d0);
+              s1b = f32x2_add(s1b, d1);
+              s2a = f32x2_fma(d0, d0, s2a);
+              s2b = f32x2_fma(d1, d1, s2b);
+            }
+          }
+        }
+        float s1x, s1y, s2x, s2y;
+        f32x2_unpack(f32x2_add(s1a, s1b), s1x, s1y);
+        f32x2_unpack(f32x2_add(s2a, s2b), s2x, s2y);
+        const float s1 = s1x + s1y, s2 = s2x + s2y;
+        constexpr float inv_n = 1.0f / (2 * PART_N);
+        const float mean_p = pivot + s1 * inv_n;
+        const float m2_p = fmaxf(s2 - s1 * s1 * inv_n, 0.f);
+        float2* buf = ln_part + ln_buf * NPART * BLOCK_M;
+        buf[part * BLOCK_M + row_in_tile] = make_float2(mean_p, m2_p);
+        tmem_ld32(t_row + cb, nx);                     // first chunk of pass 2, in flight across the exchange
+        named_bar_sync(1, EPI_THREADS);
+        ln_buf ^= 1;
+        float msum = 0.f, m2sum = 0.f;
+        float2 st[NPART];
+#pragma unroll
+        for (int k = 0; k < NPART; ++k) {
+          st[k] = buf[k * BLOCK_M + row_in_tile];
+          msum += st[k].x;
+          m2sum += st[k].y;
+        }
+        const float mean = msum * (1.0f / NPART);
+#pragma unroll
+        for (int k = 0; k < NPART; ++k)
+          m2sum = fmaf((st[k].x - mean) * (st[k].x - mean), static_cast<float>(2 * PART_N), m2sum);
+        const float var = m2sum * (1.0f / LN_N);
+        const float rstd = rsqrtf(var + p.ln_eps);
+        const uint64_t rs2 = f32x2_pack(rstd, rstd), nm2 = f32x2_pack(-mean * rstd, -mean * rstd);
+        uint4* sb = reinterpret_cast<uint4*>(smem + C::OFF_STG + warp * 4096);
+        const int r_first = r - lane;
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          const uint32_t t_h = t_row + hh * HN + cb;
+          const int col_h = hh * HN + cb;                  // first of this thread's 128 columns in the 512-wide row
+          if (hh == 1) tmem_ld32(t_h, nx);
+          for (int c = 0; c < PART_N; c += 32) {
+            tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(nx[i]);
+            if (c + 32 < PART_N) {
+              tmem_ld32(t_h + c + 32, nx);
+            } else {
+              // this half is in registers: hand it back to the MMA issuer (of the pair's leader)
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if (CTA2) mbar_arrive_cluster_relaxed(tempty_leader0 + hh * 8);
+                else mbar_arrive(&tempty_bar[hh]);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(vecs + col_h + c + i);
+              const float4 g4 = *reinterpret_cast<const float4*>(vecs + LN_N + col_h + c + i);
+              const float4 e4 = *reinterpret_cast<const float4*>(vecs + 2 * LN_N + col_h + c + i);
+              uint64_t t0 = f32x2_add(f32x2_pack(v[i], v[i + 1]), f32x2_pack(b4.x, b4.y));
+              uint64_t t1 = f32x2_add(f32x2_pack(v[i + 2], v[i + 3]), f32x2_pack(b4.z, b4.w));
+              t0 = f32x2_fma(f32x2_fma(t0, rs2, nm2), f32x2_pack(g4.x, g4.y), f32x2_pack(e4.x, e4.y));
+              t1 = f32x2_fma(f32x2_fma(t1, rs2, nm2), f32x2_pack(g4.z, g4.w), f32x2_pack(e4.z, e4.w));
+              f32x2_unpack(t0, v[i], v[i + 1]);
+              f32x2_unpack(t1, v[i + 2], v[i + 3]);
+            }
+            if (p.act == 1) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) gelu_fast2(v[i], v[i + 1]);
+            }
+            if (zero_row) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            }
+            const int hsel = (c >> 5) & 1;
+            if (hsel == 0) {
+              if (lane == 0) tma_store_wait_read<0>();
+              __syncwarp();
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              sb[lane * 8 + ((hsel * 4 + u) ^ (lane & 7))] =
+                  make_uint4(pack_h16(v[8 * u], v[8 * u + 1], p.fp16), pack_h16(v[8 * u + 2], v[8 * u + 3], p.fp16),
+                             pack_h16(v[8 * u + 4], v[8 * u + 5], p.fp16), pack_h16(v[8 * u + 6], v[8 * u + 7], p.fp16));
+            if (hsel == 1) {
+              fence_async_proxy();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_3d(&tmC, sb, col_h + c - 32, r_first, seg);
+                tma_store_commit();
+              }
+            }
+          }
+        }
+        ln2_phase ^= 1;
+      } else if constexpr (LN) {
         // ---- fused LayerNorm(512) + GELU tile: thread = one row x 256 columns (its half), two passes over TMEM with
         // the tcgen05.ld of chunk c+1 in flight while chunk c is processed, packed fp32x2 math throughout, the
         // bias / gamma / beta vectors from shared memory as float4.
@@ -708,6 +864,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         }
       }
       }   // !LN
+      if constexpr (!LN2) {
       // all tcgen05.ld of this warp have completed (wait::ld above) -> hand the accumulator back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -720,6 +877,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         if (acc == 0) acc_phase ^= 1;
       } else {
         acc_phase ^= 1;
+      }
       }
     }
   }
@@ -736,7 +894,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
 }
 
 template <int BN, bool LN>
-__global__ void __launch_bounds__((GemmCfg<BN, false>::THREADS), (GemmCfg<BN, false>::CTAS_PER_SM))
+__global__ void __launch_bounds__((GemmCfg<BN, false, LN>::THREADS), (GemmCfg<BN, false, LN>::CTAS_PER_SM))
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   gemm_body<BN, LN, false>(tmA, tmB, tmC, p);
@@ -744,7 +902,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 
 // CTA-pair variant: cluster of 2, tcgen05.mma.cta_group::2 (M = 256), half of B per CTA
 template <int BN, bool LN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((GemmCfg<BN, true>::THREADS), 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((GemmCfg<BN, true, LN>::THREADS), 1)
 gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                               const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   gemm_body<BN, LN, true>(tmA, tmB, tmC, p);
@@ -753,7 +911,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __g
 template <int BN, bool LN>
 static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
                             cudaStream_t st) {
-  using C = GemmCfg<BN, true>;
+  using C = GemmCfg<BN, true, LN>;
   auto kern = gemm_bf16_tcgen05_2cta_kernel<BN, LN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -773,7 +931,7 @@ static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const 
 template <int BN, bool LN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
                        cudaStream_t st) {
-  using C = GemmCfg<BN, false>;
+  using C = GemmCfg<BN, false, LN>;
   auto kern = gemm_bf16_tcgen05_kernel<BN, LN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -808,9 +966,11 @@ extern "C" int aptai_gemm_bf16(const aptai_gemm_args* g, void* stream) {
   APTAI_REQUIRE(g->seg_valid_rows == nullptr || g->mask_seg_rows >= 1, "gemm: mask_seg_rows must be >= 1");
   int bn = g->block_n;
   if (g->ln) {
-    APTAI_REQUIRE(g->N == 512 && (bn == 0 || bn == 512), "gemm: fused LayerNorm needs N == 512");
+    APTAI_REQUIRE(g->N == 512 && (bn == 0 || bn == 256 || bn == 512), "gemm: fused LayerNorm needs N == 512");
     APTAI_REQUIRE(g->gamma && g->beta, "gemm: fused LayerNorm needs gamma/beta");
-    bn = 512;
+    // block_n 0 / 256: the half-split tile (two 256-column accumulator halves per 512-wide row, epilogue overlapped
+    // with the MMAs); 512: the full-width tile (MMA and epilogue alternate) — kept for A/B measurements
+    if (bn == 0) bn = 256;
   } else if (bn == 0) {
     bn = (g->N % 256 == 0) ? 256 : (g->N % 128 == 0) ? 128 : (g->N % 64 == 0) ? 64 : (g->N % 48 == 0) ? 48 : 0;
   }
@@ -818,6 +978,8 @@ extern "C" int aptai_gemm_bf16(const aptai_gemm_args* g, void* stream) {
                 g->N);
   APTAI_REQUIRE(g->N % bn == 0, "gemm: N=%d not a multiple of block_n=%d", g->N, bn);
   APTAI_REQUIRE(bn != 512 || g->ln, "gemm: block_n 512 is the fused-LayerNorm tile");
+  const bool ln2 = g->ln && bn == 256;
+  const int n_tiles = ln2 ? 1 : g->N / bn;       // the half-split tile owns the whole row: its two halves are sub-tiles
   APTAI_REQUIRE(g->act != 2 || (g->aux != nullptr && !g->ln && bn % 64 == 0),
                 "gemm: act=2 (GELU dgrad) needs aux and a 64-multiple tile without LayerNorm");
   APTAI_REQUIRE(g->out_pre == nullptr || !g->ln, "gemm: out_pre is not available with the fused LayerNorm");
@@ -830,7 +992,7 @@ extern "C" int aptai_gemm_bf16(const aptai_gemm_args* g, void* stream) {
   bool pair = false;
   if (bn >= 256) {
     const long long tiles2 = static_cast<long long>(g->segs) * ((g->rows_per_seg + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) *
-                             (g->N / bn);
+                             n_tiles;
     pair = g->cta_pair == 2 || (g->cta_pair == 0 && tiles2 >= 2LL * (num_sms() / 2));
   }
   CUtensorMap ta, tb;
@@ -887,7 +1049,7 @@ extern "C" int aptai_gemm_bf16(const aptai_gemm_args* g, void* stream) {
   p.rows_per_seg = g->rows_per_seg;
   const int tile_m = pair ? 2 * BLOCK_M : BLOCK_M;
   p.m_tiles_per_seg = (g->rows_per_seg + tile_m - 1) / tile_m;
-  p.n_tiles = g->N / bn;
+  p.n_tiles = n_tiles;
   p.num_tiles = g->segs * p.m_tiles_per_seg * p.n_tiles;
   p.bias = g->bias;
   p.gamma = g->gamma;
@@ -905,6 +1067,7 @@ extern "C" int aptai_gemm_bf16(const aptai_gemm_args* g, void* stream) {
   p.aux = reinterpret_cast<const __nv_bfloat16*>(g->aux);
   p.out_pre = reinterpret_cast<__nv_bfloat16*>(g->out_pre);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (ln2) return pair ? launch_gemm_2cta<256, true>(ta, tb, tc, p, st) : launch_gemm<256, true>(ta, tb, tc, p, st);
   if (g->ln) return pair ? launch_gemm_2cta<512, true>(ta, tb, tc, p, st) : launch_gemm<512, true>(ta, tb, tc, p, st);
   switch (bn) {
     case 256: return pair ? launch_gemm_2cta<256, false>(ta, tb, tc, p, st) : launch_gemm<256, false>(ta, tb, tc, p, st);

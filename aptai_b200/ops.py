@@ -162,7 +162,8 @@ def conv_igemm(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], k
     g = GemmArgs()
     g.a = x.data_ptr(); g.a_row_stride = Cc; g.a_seg_stride = T_in * Cc; g.a_rows = T_in; g.a_cols = Cc
     g.P = stride; g.taps = k; g.kb_per_tap = Cc // 64; g.a_col_per_nblk = 0
-    g.w = w.data_ptr(); g.N = N; g.block_n = 0; g.segs = B; g.rows_per_seg = T_out
+    g.w = w.data_ptr(); g.N = N; g.block_n = CONV_LN_BLOCK_N if ln_gamma is not None else 0
+    g.segs = B; g.rows_per_seg = T_out
     g.bias = _ptr(bias)
     g.gamma = _ptr(ln_gamma); g.beta = _ptr(ln_beta); g.residual = None
     g.out_f32 = _ptr(out_f32); g.out_bf16 = None if out_f32 is not None else out.data_ptr()
@@ -212,6 +213,9 @@ def posconv(x_pad: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], 
     return out_f32
 
 
+# fused-LayerNorm conv tile: 0 / 256 = half-split (two 256-column accumulator halves, epilogue under the MMAs),
+# 512 = full-width tile (MMA and epilogue alternate); A/B runs
+CONV_LN_BLOCK_N = int(os.environ.get("APTAI_CONV_LN_BLOCK_N", "0"))
 CONV0_TC = int(os.environ.get("APTAI_CONV0_TC", "1"))     # 0: the SIMT conv-0 kernel (A/B runs)
 
 

@@ -61,7 +61,8 @@ typedef struct aptai_gemm_args {
   int32_t a_col_per_nblk; /* channel offset per n tile (grouped conv), else 0 */
   const void* w;          /* bf16 [N][K] */
   int32_t N;
-  int32_t block_n;        /* 0 = choose; otherwise one of 48, 64, 128, 256 (512 when ln=1) */
+  int32_t block_n;        /* 0 = choose; otherwise one of 48, 64, 128, 256.  ln=1: 0 / 256 = half-split row tile (two
+                             256-column accumulator halves, epilogue overlapped with the MMAs), 512 = full-width tile */
   int32_t segs;
   int32_t rows_per_seg;   /* output rows per segment */
   const float* bias;      /* [N] or NULL */
