@@ -137,14 +137,14 @@ class _WeightTable:
         self.rows.append(e)
         self.keep.append((src, dst, dst_t, dst_f32))
 
-    def run(self):
+    def run(self, half_fmt: int = 0):
         import ctypes as C
         from .lib import PrepEntry
         if self.table is None:
             arr = (PrepEntry * len(self.rows))(*self.rows)
             raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).clone()
             self.table = raw.to(self.dev)
-        ops.prepare_weights(self.table, len(self.rows), self.tiles)
+        ops.prepare_weights(self.table, len(self.rows), self.tiles, half_fmt)
 
 
 class _Plan:
@@ -155,10 +155,13 @@ class _Plan:
     weights for the dgrad GEMMs (dX = dY @ W is the forward kernel on W^T; the q block unscaled), a bf16 projection
     weight, and the flipped / in-out-swapped folded pos-conv weight (transposed conv = the forward kernel on it)."""
 
-    def __init__(self, m: "Wav2Vec2Backbone", train: bool = False):
+    def __init__(self, m: "Wav2Vec2Backbone", train: bool = False, half: int = 0):
         cfg = m.cfg
         dev = m.masked_spec_embed.device
+        if train and half:
+            raise ValueError("aptai_b200: the training plan keeps bf16 operands (fp16 gradients would underflow)")
         self.train = train
+        self.half = half          # 1: the transformer's operand copies are IEEE fp16 (precision="fp16", inference)
         f = lambda t: t.detach().to(device=dev, dtype=F32).contiguous()    # fp32 params: a view, tracks updates
         self._f = f
         self._conv_key = None
@@ -171,7 +174,7 @@ class _Plan:
         H, Fi = cfg.hidden_size, cfg.intermediate_size
         scale = float(cfg.head_dim) ** -0.5     # folded into q (0.125 for head_dim 64: exact in bf16)
         tb = _WeightTable(dev)
-        e16 = lambda *shape: torch.empty(shape, dtype=BF16, device=dev)
+        e16 = lambda *shape: torch.empty(shape, dtype=F16 if half else BF16, device=dev)
         if train:
             self.fp_w_bf16, self.fp_wt = e16(H, cfg.conv_dim[-1]), e16(cfg.conv_dim[-1], H)
             tb.add(fp.projection.weight, dst=self.fp_w_bf16, dst_t=self.fp_wt)
@@ -224,11 +227,12 @@ class _Plan:
                 self.conv0_wt = f(cl[0].conv.weight.reshape(cfg.conv_dim[0], cfg.conv_kernel[0]).t())
             self._conv_key = ck
             self.generation = getattr(self, "generation", 0) + 1      # buffers re-allocated: captured graphs are stale
-        self._table.run()
+        self._table.run(self.half)
         pc = m.encoder.pos_conv_embed.conv
         g = f(pc.parametrizations.weight.original0)
         v = f(pc.parametrizations.weight.original1)
-        self.pos_w = ops.posconv_fold(g, v, cpad=64, out=getattr(self, "pos_w", None))
+        self.pos_w = ops.posconv_fold(g, v, cpad=64, out=getattr(self, "pos_w", None),
+                                      dtype=F16 if self.half else BF16)
         if self.train:
             Hh, gw, taps = v.shape
             groups = Hh // gw
@@ -261,6 +265,9 @@ class Wav2Vec2Backbone(nn.Module):
         self._plan: Optional[_Plan] = None
         self._plan_key = None
         self._plan_ptrs = None
+        self._plan_h: Optional[_Plan] = None       # the fp16-operand inference plan lives beside the bf16 one
+        self._plan_h_key = None
+        self._plan_h_ptrs = None
         self._feature_encoder_frozen = False
 
     # ---- reference-facing helpers --------------------------------------------------------------------------
@@ -296,11 +303,14 @@ class Wav2Vec2Backbone(nn.Module):
         return m
 
     def set_precision(self, precision: str):
-        """'bf16': 16-bit tensor-core operands (default, the measured hot path).  'f32x3': accuracy mode — every
-        contraction on bf16 hi/lo operand pairs, fp32 elsewhere (inference only)."""
-        if precision not in ("bf16", "f32x3"):
-            raise ValueError(f"aptai_b200: unknown precision {precision!r} ('bf16' or 'f32x3')")
-        self.precision = precision
+        """'bf16': 16-bit tensor-core operands (default, the measured hot path).  'fp16': the same kernels on IEEE
+        fp16 operands (weights, activations, attention probabilities; fp32 accumulation, residual stream and
+        statistics as before) — same speed, 7x smaller logit / trajectory error (three more mantissa bits), for
+        checkpoints whose activations stay inside fp16's range (inference only; training keeps bf16).
+        'f32x3': accuracy mode — every contraction on bf16 hi/lo operand pairs, fp32 elsewhere (inference only)."""
+        if precision not in ("bf16", "fp16", "f32x3"):
+            raise ValueError(f"aptai_b200: unknown precision {precision!r} ('bf16', 'fp16' or 'f32x3')")
+        self.precision = precision       # the fp16 operand copies (0.6 GB for 24x1024) stay cached across mode switches
         return self
 
     def gradient_checkpointing_enable(self, *a, **k):    # models/aptai.py:38 — no autograd graph to checkpoint here
@@ -327,7 +337,7 @@ class Wav2Vec2Backbone(nn.Module):
     def defers_final_ln(self) -> bool:
         """True when `encode(final_ln=False)` really leaves the last LayerNorm to the caller (pre-LN encoder, default
         precision)."""
-        return bool(self.cfg.do_stable_layer_norm) and self.precision == "bf16"
+        return bool(self.cfg.do_stable_layer_norm) and self.precision in ("bf16", "fp16")
 
     def final_ln_params(self):
         """(gamma, beta, eps) of the encoder's last LayerNorm as the kernels take them (fp32, contiguous)."""
@@ -345,6 +355,15 @@ class Wav2Vec2Backbone(nn.Module):
         params = list(self.parameters())
         ptrs = tuple(p.data_ptr() for p in params)
         vers = tuple(p._version for p in params)
+        if self.precision == "fp16" and not train:
+            P = self._plan_h
+            with torch.no_grad():
+                if P is None or ptrs != self._plan_h_ptrs:
+                    self._plan_h = _Plan(self, half=1)
+                elif vers != self._plan_h_key:
+                    P.refresh(self)
+            self._plan_h_ptrs, self._plan_h_key = ptrs, vers
+            return self._plan_h
         P = self._plan
         with torch.no_grad():
             if P is None or ptrs != self._plan_ptrs or (train and not P.train):
@@ -731,9 +750,10 @@ class Wav2Vec2Backbone(nn.Module):
         if self.precision == "f32x3":
             from . import accurate
             return accurate.encode(self, wav, frame_lens, collect_hidden=collect_hidden, want_features=want_features)
-        if self.precision != "bf16":
-            raise ValueError(f"aptai_b200: unknown precision {self.precision!r} ('bf16' or 'f32x3')")
+        if self.precision not in ("bf16", "fp16"):
+            raise ValueError(f"aptai_b200: unknown precision {self.precision!r} ('bf16', 'fp16' or 'f32x3')")
         cfg, P = self.cfg, self.plan()
+        X16 = F16 if P.half else BF16          # operand format of the transformer (the conv stack is fp16 either way)
         B, L = wav.shape
         norm = 1 if cfg.feat_extract_norm == "layer" else 2
         # feature encoder + projection run on fp16 operands (activations are O(1) after the norms; three more
@@ -748,23 +768,23 @@ class Wav2Vec2Backbone(nn.Module):
         _, xn = ops.layernorm(y.view(M, -1), P.fp_ln_w, P.fp_ln_b, cfg.layer_norm_eps, out16_dtype=F16)
         h, _ = ops.linear(xn, P.fp_w, P.fp_b, want_f32=True, want_bf16=False, seg_rows=T, seg_valid_rows=frame_lens)
         taps = cfg.num_conv_pos_embeddings
-        hp = ops.cast_pad(h.view(B, T, H), taps // 2)
+        hp = ops.cast_pad(h.view(B, T, H), taps // 2, dtype=X16)
         ops.posconv(hp, P.pos_w, P.pos_b, h, T, H, cfg.num_conv_pos_embedding_groups, taps, h)
         hidden = [] if collect_hidden else None
         eps = cfg.layer_norm_eps
         heads = cfg.num_attention_heads
         if not cfg.do_stable_layer_norm:
-            h, x = ops.layernorm(h, P.enc_ln_w, P.enc_ln_b, eps, want_f32=True, want_bf16=True)
+            h, x = ops.layernorm(h, P.enc_ln_w, P.enc_ln_b, eps, want_f32=True, want_bf16=True, out16_dtype=X16)
             for lw in P.layers:
                 if collect_hidden:
                     hidden.append(h.view(B, T, H).clone())
                 _, qkv = ops.linear(x, lw.qkv_w, lw.qkv_b)
                 ctx = ops.attention(qkv, frame_lens, B, T, heads)
                 t32, _ = ops.linear(ctx, lw.o_w, lw.o_b, residual=h, want_f32=True, want_bf16=False)
-                h, x = ops.layernorm(t32, lw.ln1_w, lw.ln1_b, eps, want_f32=True, want_bf16=True)
+                h, x = ops.layernorm(t32, lw.ln1_w, lw.ln1_b, eps, want_f32=True, want_bf16=True, out16_dtype=X16)
                 _, u = ops.linear(x, lw.ff1_w, lw.ff1_b, act=1)
                 t32, _ = ops.linear(u, lw.ff2_w, lw.ff2_b, residual=h, want_f32=True, want_bf16=False)
-                h, x = ops.layernorm(t32, lw.ln2_w, lw.ln2_b, eps, want_f32=True, want_bf16=True)
+                h, x = ops.layernorm(t32, lw.ln2_w, lw.ln2_b, eps, want_f32=True, want_bf16=True, out16_dtype=X16)
             last = h
         else:
             # every activation of a 75 k-row batch (h 300 MB, qkv 450 MB, u 600 MB) exceeds the 126 MB L2: consecutive
@@ -773,11 +793,11 @@ class Wav2Vec2Backbone(nn.Module):
             for lw in P.layers:
                 if collect_hidden:
                     hidden.append(h.view(B, T, H).clone())
-                serp(); _, x = ops.layernorm(h, lw.ln1_w, lw.ln1_b, eps)
+                serp(); _, x = ops.layernorm(h, lw.ln1_w, lw.ln1_b, eps, out16_dtype=X16)
                 serp(); _, qkv = ops.linear(x, lw.qkv_w, lw.qkv_b)
                 serp(); ctx = ops.attention(qkv, frame_lens, B, T, heads)
                 serp(); ops.linear(ctx, lw.o_w, lw.o_b, residual=h, out_f32=h, want_bf16=False)
-                serp(); _, x = ops.layernorm(h, lw.ln2_w, lw.ln2_b, eps)
+                serp(); _, x = ops.layernorm(h, lw.ln2_w, lw.ln2_b, eps, out16_dtype=X16)
                 serp(); _, u = ops.linear(x, lw.ff1_w, lw.ff1_b, act=1)
                 serp(); ops.linear(u, lw.ff2_w, lw.ff2_b, residual=h, out_f32=h, want_bf16=False)
             serp.done()

@@ -61,6 +61,8 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t saddr) {
   return d;
 }
 
+// FP16: q / k / v, P and the context are IEEE fp16 instead of bf16 (precision="fp16")
+template <bool FP16>
 __global__ void __launch_bounds__(ATC_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                     const AttnParams p) {
@@ -148,7 +150,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // (two issuing threads per CTA: a tcgen05.mma issue costs the thread ~100 cycles but these N=64 MMAs are
     //  only 32 cycles of tensor work, so a single issuer for S and PV was the bottleneck of the tile period)
     {
-      constexpr uint32_t IDESC_BASE = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(AQ >> 4) << 24);
+      constexpr uint32_t FMT_AB = FP16 ? 0u : ((1u << 7) | (1u << 10));      // a_format / b_format: 0 = f16, 1 = bf16
+      constexpr uint32_t IDESC_BASE = (1u << 4) | FMT_AB | (static_cast<uint32_t>(AQ >> 4) << 24);
       uint32_t g = 0, it = 0;
       for (int w = blockIdx.x; w < p.items; w += gridDim.x, ++it) {
         const int bh = w / p.n_qt;
@@ -181,7 +184,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   } else if (warp == W_MMA2) {
     // ---------------------------------------------------------------- MMA issuer 2: O += P_j V_j
     {
-      constexpr uint32_t IDESC_PV = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(AQ >> 4) << 24) |
+      constexpr uint32_t FMT_AB = FP16 ? 0u : ((1u << 7) | (1u << 10));
+      constexpr uint32_t IDESC_PV = (1u << 4) | FMT_AB | (static_cast<uint32_t>(AQ >> 4) << 24) |
                                     (1u << 16) | (static_cast<uint32_t>(AD >> 3) << 17);   // B MN-major, N=64
       uint32_t g = 0, it = 0;
       for (int w = blockIdx.x; w < p.items; w += gridDim.x, ++it) {
@@ -301,8 +305,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           rs0 += pv[0] + pv[4]; rs1 += pv[1] + pv[5]; rs2 += pv[2] + pv[6]; rs3 += pv[3] + pv[7];
           const int unit = half * 4 + u8;
           if ((unit >> 1) < ncol16) {
-            uint4 v4 = make_uint4(pack_bf16(pv[0], pv[1]), pack_bf16(pv[2], pv[3]), pack_bf16(pv[4], pv[5]),
-                                  pack_bf16(pv[6], pv[7]));
+            uint4 v4 = make_uint4(pack_h16c<FP16>(pv[0], pv[1]), pack_h16c<FP16>(pv[2], pv[3]), pack_h16c<FP16>(pv[4], pv[5]),
+                                  pack_h16c<FP16>(pv[6], pv[7]));
             *reinterpret_cast<uint4*>(prow + ((unit ^ (row & 7)) << 4)) = v4;
           }
         }
@@ -334,10 +338,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
           for (int i = 0; i < 32; i += 8)
             *reinterpret_cast<uint4*>(out + i) =
-                make_uint4(pack_bf16(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv),
-                           pack_bf16(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv),
-                           pack_bf16(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv),
-                           pack_bf16(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv));
+                make_uint4(pack_h16c<FP16>(__uint_as_float(r[i]) * inv, __uint_as_float(r[i + 1]) * inv),
+                           pack_h16c<FP16>(__uint_as_float(r[i + 2]) * inv, __uint_as_float(r[i + 3]) * inv),
+                           pack_h16c<FP16>(__uint_as_float(r[i + 4]) * inv, __uint_as_float(r[i + 5]) * inv),
+                           pack_h16c<FP16>(__uint_as_float(r[i + 6]) * inv, __uint_as_float(r[i + 7]) * inv));
         }
       }
       tc_fence_before();
@@ -357,8 +361,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
 using namespace aptai;
 
+template <bool FP16>
 static int attention_fwd_impl(const void* qkv, void* ctx, float* lse, const int32_t* key_len, int B, int T, int heads,
                               void* stream) {
+  auto kern = attention_tc_kernel<FP16>;
   if (int rc = check_arch()) return rc;
   APTAI_REQUIRE(qkv && ctx && key_len, "attention: null pointer");
   APTAI_REQUIRE(B >= 1 && T >= 1 && heads >= 1, "attention: bad shape");
@@ -383,8 +389,8 @@ static int attention_fwd_impl(const void* qkv, void* ctx, float* lse, const int3
   p.items = B * heads * p.n_qt;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ATC_SMEM);
     if (e != cudaSuccess) {
       set_error("attention: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return static_cast<int>(e);
@@ -394,24 +400,30 @@ static int attention_fwd_impl(const void* qkv, void* ctx, float* lse, const int3
   static int ctas_per_sm = 0;
   if (ctas_per_sm == 0) {
     int n = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, attention_tc_kernel, ATC_THREADS, ATC_SMEM);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, ATC_THREADS, ATC_SMEM);
     if (getenv("APTAI_DEBUG"))
       fprintf(stderr, "aptai attention: occupancy query -> %d CTAs per SM (%s)\n", n, cudaGetErrorString(e));
     cudaGetLastError();
     ctas_per_sm = 2;      // two CTAs per SM are intended (80 KB smem, 256 TMEM columns, <= 128 registers each)
   }
   const int grid = p.items < ctas_per_sm * num_sms() ? p.items : ctas_per_sm * num_sms();
-  attention_tc_kernel<<<grid, ATC_THREADS, ATC_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tmq, tmkv, p);
+  kern<<<grid, ATC_THREADS, ATC_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tmq, tmkv, p);
   return after_launch("attention_tc");
 }
 
 extern "C" int aptai_attention_fwd(const void* qkv, void* ctx, const int32_t* key_len, int B, int T, int heads,
                                    void* stream) {
-  return attention_fwd_impl(qkv, ctx, nullptr, key_len, B, T, heads, stream);
+  return attention_fwd_impl<false>(qkv, ctx, nullptr, key_len, B, T, heads, stream);
+}
+
+extern "C" int aptai_attention_fwd_fmt(const void* qkv, void* ctx, float* lse, const int32_t* key_len, int B, int T,
+                                       int heads, int half_fmt, void* stream) {
+  return half_fmt ? attention_fwd_impl<true>(qkv, ctx, lse, key_len, B, T, heads, stream)
+                  : attention_fwd_impl<false>(qkv, ctx, lse, key_len, B, T, heads, stream);
 }
 
 extern "C" int aptai_attention_fwd_lse(const void* qkv, void* ctx, float* lse, const int32_t* key_len, int B, int T,
                                        int heads, void* stream) {
   APTAI_REQUIRE(lse != nullptr, "attention_fwd_lse: null lse");
-  return attention_fwd_impl(qkv, ctx, lse, key_len, B, T, heads, stream);
+  return attention_fwd_impl<false>(qkv, ctx, lse, key_len, B, T, heads, stream);
 }

@@ -160,9 +160,12 @@ __device__ __forceinline__ float a3_ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ uint32_t a3_pack_bf16(float lo, float hi) {
+// two fp32 -> one packed 16-bit pair in the kernel's operand format (bf16, or IEEE fp16 for precision="fp16")
+template <bool FP16>
+__device__ __forceinline__ uint32_t a3_pack16(float lo, float hi) {
   uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  if (FP16) asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
 // 2^x for two arguments on the FMA pipe.  x = n + f with n = floor(x) taken from the low mantissa bits of
@@ -185,8 +188,10 @@ __device__ __forceinline__ void a3_ex2_poly2(float x0, float x1, float& p0, floa
   p1 = __uint_as_float(__float_as_uint(q1) + (__float_as_uint(r1) << 23));
 }
 
-// POLY8 of every 8 exponential PAIRS go to the FMA pipe, the rest to the MUFU
-template <int POLY8>
+// POLY8 of every 8 exponential PAIRS go to the FMA pipe, the rest to the MUFU; FP16: q / k / v, P and the context
+// are IEEE fp16 instead of bf16 (same tensor-core rate, three more mantissa bits; P <= 1 and the 2^8 lazy-rescale
+// window keep the unnormalised P far inside fp16's range)
+template <int POLY8, bool FP16>
 __global__ void __launch_bounds__(A3_THREADS, 1)
 attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
                     const __grid_constant__ CUtensorMap tmO, const Attn3Params p) {
@@ -285,8 +290,9 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // instead of a register->uniform-register broadcast loop each
     {
       const int t = warp - A3_W_MMA0;
-      constexpr uint32_t IDESC_S = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(A3_Q >> 4) << 24);
-      constexpr uint32_t IDESC_PV = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(A3_Q >> 4) << 24) |
+      constexpr uint32_t FMT_AB = FP16 ? 0u : ((1u << 7) | (1u << 10));      // a_format / b_format: 0 = f16, 1 = bf16
+      constexpr uint32_t IDESC_S = (1u << 4) | FMT_AB | (static_cast<uint32_t>(A3_Q >> 4) << 24);
+      constexpr uint32_t IDESC_PV = (1u << 4) | FMT_AB | (static_cast<uint32_t>(A3_Q >> 4) << 24) |
                                     (1u << 16) | (static_cast<uint32_t>(A3_D >> 3) << 17);   // B MN-major, N = 64
       const uint32_t ts0 = tmem_base + t * A3_NBUF * A3_K;
       const uint32_t to = tmem_base + A3_TO + t * A3_D;
@@ -414,10 +420,10 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
           for (int u = 0; u < 4; ++u)
             *reinterpret_cast<uint4*>(so_row + (((c * 4 + u) ^ (row & 7)) << 4)) = make_uint4(
-                a3_pack_bf16(__uint_as_float(r[8 * u]) * inv, __uint_as_float(r[8 * u + 1]) * inv),
-                a3_pack_bf16(__uint_as_float(r[8 * u + 2]) * inv, __uint_as_float(r[8 * u + 3]) * inv),
-                a3_pack_bf16(__uint_as_float(r[8 * u + 4]) * inv, __uint_as_float(r[8 * u + 5]) * inv),
-                a3_pack_bf16(__uint_as_float(r[8 * u + 6]) * inv, __uint_as_float(r[8 * u + 7]) * inv));
+                a3_pack16<FP16>(__uint_as_float(r[8 * u]) * inv, __uint_as_float(r[8 * u + 1]) * inv),
+                a3_pack16<FP16>(__uint_as_float(r[8 * u + 2]) * inv, __uint_as_float(r[8 * u + 3]) * inv),
+                a3_pack16<FP16>(__uint_as_float(r[8 * u + 4]) * inv, __uint_as_float(r[8 * u + 5]) * inv),
+                a3_pack16<FP16>(__uint_as_float(r[8 * u + 6]) * inv, __uint_as_float(r[8 * u + 7]) * inv));
         }
         tc_fence_before();
         fence_async_proxy();
@@ -518,7 +524,7 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
           if (i & 1) acc1 = f32x2_add(acc1, f32x2_pack(p0, p1));
           else acc0 = f32x2_add(acc0, f32x2_pack(p0, p1));
-          pk[i] = a3_pack_bf16(p0, p1);
+          pk[i] = a3_pack16<FP16>(p0, p1);
         }
         float r0, r1;
         f32x2_unpack(f32x2_add(acc0, acc1), r0, r1);
@@ -548,10 +554,10 @@ attention_v3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
 using namespace aptai;
 
-template <int POLY8>
+template <int POLY8, bool FP16>
 static int launch_attention_v3(const CUtensorMap& tq, const CUtensorMap& tkv, const CUtensorMap& to,
                                const Attn3Params& p, cudaStream_t st) {
-  auto kern = attention_v3_kernel<POLY8>;
+  auto kern = attention_v3_kernel<POLY8, FP16>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, A3_SMEM);
@@ -597,10 +603,11 @@ extern "C" int aptai_attention_fwd_v3(const void* qkv, void* ctx, float* lse, co
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   p.idle_ns = (poly8 >> 8) & 0xffff;
   p.reverse = traversal_reverse();
+  if (poly8 & (1 << 24)) return launch_attention_v3<3, true>(tmq, tmkv, tmo, p, st);     // fp16 operands
   switch (poly8 & 0xff) {
-    case 0: return launch_attention_v3<0>(tmq, tmkv, tmo, p, st);
-    case 2: return launch_attention_v3<2>(tmq, tmkv, tmo, p, st);
-    case 4: return launch_attention_v3<4>(tmq, tmkv, tmo, p, st);
-    default: return launch_attention_v3<3>(tmq, tmkv, tmo, p, st);
+    case 0: return launch_attention_v3<0, false>(tmq, tmkv, tmo, p, st);
+    case 2: return launch_attention_v3<2, false>(tmq, tmkv, tmo, p, st);
+    case 4: return launch_attention_v3<4, false>(tmq, tmkv, tmo, p, st);
+    default: return launch_attention_v3<3, false>(tmq, tmkv, tmo, p, st);
   }
 }

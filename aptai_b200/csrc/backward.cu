@@ -437,8 +437,15 @@ struct PrepEntry {
   int tiles_x;               // tiles per row of tiles
 };
 
+// one fp32 -> the 16 bits of a bf16 (fp16 = 0) or IEEE fp16 (fp16 = 1) value, carried in the bf16 storage type
+__device__ __forceinline__ __nv_bfloat16 cvt_h16(float v, int fp16) {
+  if (!fp16) return __float2bfloat16(v);
+  const __half h = __float2half_rn(v);
+  return *reinterpret_cast<const __nv_bfloat16*>(&h);
+}
+
 __global__ void __launch_bounds__(256)
-prepare_weights_kernel(const PrepEntry* __restrict__ entries, int n_entries) {
+prepare_weights_kernel(const PrepEntry* __restrict__ entries, int n_entries, int fp16) {
   __shared__ float tile[32][33];
   __shared__ PrepEntry e;
   if (threadIdx.x == 0) {
@@ -461,7 +468,7 @@ prepare_weights_kernel(const PrepEntry* __restrict__ entries, int n_entries) {
     float v = 0.f;
     if (r < e.rows && c < e.cols) {
       v = __ldg(e.src + static_cast<long long>(r) * e.cols + c);
-      if (e.dst) e.dst[static_cast<long long>(r) * e.dst_ld + c] = __float2bfloat16(v * e.scale);
+      if (e.dst) e.dst[static_cast<long long>(r) * e.dst_ld + c] = cvt_h16(v * e.scale, fp16);
       if (e.dst_f32) e.dst_f32[static_cast<long long>(r) * e.cols + c] = v * e.scale;
     }
     tile[ty + 8 * i][tx] = v;
@@ -472,7 +479,7 @@ prepare_weights_kernel(const PrepEntry* __restrict__ entries, int n_entries) {
   for (int i = 0; i < 4; ++i) {
     const int c = c0 + ty + 8 * i, r = r0 + tx;
     if (r < e.rows && c < e.cols)
-      e.dst_t[static_cast<long long>(c) * e.dst_t_ld + r] = __float2bfloat16(tile[tx][ty + 8 * i] * e.scale_t);
+      e.dst_t[static_cast<long long>(c) * e.dst_t_ld + r] = cvt_h16(tile[tx][ty + 8 * i] * e.scale_t, fp16);
   }
 }
 
@@ -654,13 +661,18 @@ extern "C" int aptai_gelu_bwd(const float* dy, const void* pre_bf16, int64_t n, 
   return after_launch("gelu_bwd");
 }
 
-extern "C" int aptai_prepare_weights(const void* entries_dev, int n_entries, int total_tiles, void* stream) {
+extern "C" int aptai_prepare_weights_fmt(const void* entries_dev, int n_entries, int total_tiles, int half_fmt,
+                                         void* stream) {
   if (int rc = check_arch()) return rc;
   APTAI_REQUIRE(entries_dev && n_entries >= 1 && total_tiles >= 1, "prepare_weights: bad arguments");
   static_assert(sizeof(PrepEntry) == 64, "PrepEntry layout is part of the C ABI (aptai_b200/lib.py PrepEntry)");
   prepare_weights_kernel<<<total_tiles, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const PrepEntry*>(entries_dev), n_entries);
+      reinterpret_cast<const PrepEntry*>(entries_dev), n_entries, half_fmt ? 1 : 0);
   return after_launch("prepare_weights");
+}
+
+extern "C" int aptai_prepare_weights(const void* entries_dev, int n_entries, int total_tiles, void* stream) {
+  return aptai_prepare_weights_fmt(entries_dev, n_entries, total_tiles, 0, stream);
 }
 
 extern "C" int aptai_adam_step(void* const* params_dev, const int64_t* grad_offsets_dev,

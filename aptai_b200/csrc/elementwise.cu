@@ -84,7 +84,7 @@ static void launch_ln(const void* x, int x_fmt, long long rows, const float* gam
 
 // ---------------------------------------------------------------------------------------------- cast + halo pad
 __global__ void cast_pad_kernel(const float* __restrict__ x, int rows, int cols4, int halo,
-                                __nv_bfloat16* __restrict__ out) {
+                                __nv_bfloat16* __restrict__ out, int fp16) {
   // grid.y = segment; each thread moves 4 elements; halo rows are written as zeros
   const int seg = blockIdx.y;
   const long long prow = rows + 2 * halo;
@@ -97,7 +97,7 @@ __global__ void cast_pad_kernel(const float* __restrict__ x, int rows, int cols4
     uint2 u = make_uint2(0u, 0u);
     if (r >= 0 && r < rows) {
       const float4 v = __ldg(in + r * cols4 + (i % cols4));
-      u = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+      u = make_uint2(pack_h16(v.x, v.y, fp16), pack_h16(v.z, v.w, fp16));
     }
     o[i] = u;
   }
@@ -124,7 +124,7 @@ __global__ void posconv_norm_kernel(const float* __restrict__ v, int n_oc, int t
 
 __global__ void posconv_fold_kernel(const float* __restrict__ g, const float* __restrict__ v,
                                     const float* __restrict__ norm, int H, int cin, int taps, int cpad,
-                                    __nv_bfloat16* __restrict__ w) {
+                                    __nv_bfloat16* __restrict__ w, int fp16) {
   // w[o][j][c] = g[j] * v[o][c][j] / norm[j]   (c >= cin -> 0)
   const long long total = static_cast<long long>(H) * taps * cpad;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
@@ -134,7 +134,8 @@ __global__ void posconv_fold_kernel(const float* __restrict__ g, const float* __
     const long long o = i / (static_cast<long long>(cpad) * taps);
     float val = 0.f;
     if (c < cin) val = g[j] * v[(o * cin + c) * taps + j] / norm[j];
-    w[i] = __float2bfloat16(val);
+    if (fp16) reinterpret_cast<__half*>(w)[i] = __float2half_rn(val);
+    else w[i] = __float2bfloat16(val);
   }
 }
 
@@ -358,8 +359,8 @@ extern "C" int aptai_layernorm(const void* x, int x_fmt, int64_t rows, int cols,
   return after_launch("layernorm");
 }
 
-extern "C" int aptai_cast_pad_bf16(const float* x, int segs, int rows, int cols, int halo, void* out_bf16,
-                                   void* stream) {
+extern "C" int aptai_cast_pad_h16(const float* x, int segs, int rows, int cols, int halo, void* out_bf16,
+                                  int half_fmt, void* stream) {
   if (int rc = check_arch()) return rc;
   APTAI_REQUIRE(x && out_bf16, "cast_pad: null pointer");
   APTAI_REQUIRE(segs >= 1 && rows >= 1 && cols % 4 == 0 && halo >= 0, "cast_pad: bad shape");
@@ -367,12 +368,17 @@ extern "C" int aptai_cast_pad_bf16(const float* x, int segs, int rows, int cols,
   int gx = static_cast<int>((total + 255) / 256);
   if (gx > 4096) gx = 4096;
   cast_pad_kernel<<<dim3(gx, segs), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      x, rows, cols / 4, halo, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+      x, rows, cols / 4, halo, reinterpret_cast<__nv_bfloat16*>(out_bf16), half_fmt ? 1 : 0);
   return after_launch("cast_pad_bf16");
 }
 
-extern "C" int aptai_posconv_fold(const float* g, const float* v, int H, int cin, int taps, int cpad, void* w_bf16,
-                                  float* norm_ws, void* stream) {
+extern "C" int aptai_cast_pad_bf16(const float* x, int segs, int rows, int cols, int halo, void* out_bf16,
+                                   void* stream) {
+  return aptai_cast_pad_h16(x, segs, rows, cols, halo, out_bf16, 0, stream);
+}
+
+extern "C" int aptai_posconv_fold_fmt(const float* g, const float* v, int H, int cin, int taps, int cpad, void* w_bf16,
+                                      float* norm_ws, int half_fmt, void* stream) {
   if (int rc = check_arch()) return rc;
   APTAI_REQUIRE(g && v && w_bf16 && norm_ws, "posconv_fold: null pointer");
   APTAI_REQUIRE(cpad >= cin && H >= 1 && taps >= 1, "posconv_fold: bad shape");
@@ -382,8 +388,14 @@ extern "C" int aptai_posconv_fold(const float* g, const float* v, int H, int cin
   const long long total = static_cast<long long>(H) * taps * cpad;
   int gx = static_cast<int>((total + 255) / 256);
   if (gx > 8192) gx = 8192;
-  posconv_fold_kernel<<<gx, 256, 0, st>>>(g, v, norm_ws, H, cin, taps, cpad, reinterpret_cast<__nv_bfloat16*>(w_bf16));
+  posconv_fold_kernel<<<gx, 256, 0, st>>>(g, v, norm_ws, H, cin, taps, cpad, reinterpret_cast<__nv_bfloat16*>(w_bf16),
+                                          half_fmt ? 1 : 0);
   return after_launch("posconv_fold");
+}
+
+extern "C" int aptai_posconv_fold(const float* g, const float* v, int H, int cin, int taps, int cpad, void* w_bf16,
+                                  float* norm_ws, void* stream) {
+  return aptai_posconv_fold_fmt(g, v, H, cin, taps, cpad, w_bf16, norm_ws, 0, stream);
 }
 
 extern "C" int aptai_heads(const float* h, int64_t rows, int H, const float* wa, const float* ba, int na, int act_a,

@@ -39,6 +39,7 @@ constexpr int PC_W_TMA = 8, PC_W_MMA = 9;
 struct PosconvParams {
   const float* bias;
   int B, T, m_blocks, groups, items;
+  int fp16;                 // x_pad and w_fold are IEEE fp16 instead of bf16
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PC_THREADS, 1)
@@ -123,7 +124,7 @@ posconv_slab_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
   } else if (warp == PC_W_MMA) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA; whole warp, elected)
     if (rank == 0) {
-      constexpr uint32_t IDESC = umma_idesc_bf16(2 * PC_ROWS, PC_GW);
+      const uint32_t IDESC = p.fp16 ? umma_idesc_f16(2 * PC_ROWS, PC_GW) : umma_idesc_bf16(2 * PC_ROWS, PC_GW);
       const uint32_t smem_base = smem_u32(smem);
       uint32_t it = 0, stage = 0, phase = 0;
       for (int item = item0; item < p.items; item += item_step, ++it) {
@@ -221,8 +222,8 @@ posconv_slab_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_consta
 
 using namespace aptai;
 
-extern "C" int aptai_posconv_slab(const void* x_pad, const void* w_fold, const float* bias, float* h, int B, int T,
-                                  int H, void* stream) {
+extern "C" int aptai_posconv_slab_fmt(const void* x_pad, const void* w_fold, const float* bias, float* h, int B, int T,
+                                      int H, int half_fmt, void* stream) {
   if (int rc = check_arch()) return rc;
   APTAI_REQUIRE(x_pad && w_fold && h, "posconv_slab: null pointer");
   APTAI_REQUIRE(B >= 1 && T >= 1 && H >= PC_GW && H % PC_GW == 0, "posconv_slab: H must be a multiple of 64");
@@ -252,6 +253,7 @@ extern "C" int aptai_posconv_slab(const void* x_pad, const void* w_fold, const f
   }
   PosconvParams p;
   p.bias = bias;
+  p.fp16 = half_fmt ? 1 : 0;
   p.B = B; p.T = T;
   p.m_blocks = (T + 2 * PC_ROWS - 1) / (2 * PC_ROWS);
   p.groups = groups;
@@ -269,4 +271,9 @@ extern "C" int aptai_posconv_slab(const void* x_pad, const void* w_fold, const f
   if (p.items < clusters) clusters = p.items;
   posconv_slab_kernel<<<2 * clusters, PC_THREADS, PC_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(tx, tw, th, p);
   return after_launch("posconv_slab");
+}
+
+extern "C" int aptai_posconv_slab(const void* x_pad, const void* w_fold, const float* bias, float* h, int B, int T,
+                                  int H, void* stream) {
+  return aptai_posconv_slab_fmt(x_pad, w_fold, bias, h, B, T, H, 0, stream);
 }

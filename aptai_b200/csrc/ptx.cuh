@@ -523,6 +523,10 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+template <bool FP16>
+__device__ __forceinline__ uint32_t pack_h16c(float a, float b) {      // format fixed at compile time
+  return FP16 ? pack_f16(a, b) : pack_bf16(a, b);
+}
 __device__ __forceinline__ uint32_t pack_h16(float a, float b, int fp16) {
   return fp16 ? pack_f16(a, b) : pack_bf16(a, b);
 }

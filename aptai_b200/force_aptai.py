@@ -59,7 +59,8 @@ class Force_APTAI(nn.Module):
             param.requires_grad = False
 
     def set_precision(self, precision: str):
-        """'bf16' (default) or 'f32x3': accuracy mode of the frozen recogniser's encoder (the tail is fp32 already)."""
+        """'bf16' (default), 'fp16' (fp16 operands in the frozen recogniser's encoder, same speed) or 'f32x3' (its
+        accuracy mode); the tail is fp32 already."""
         self.w2v2_pr.set_precision(precision)
         return self
 

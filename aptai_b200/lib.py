@@ -48,7 +48,11 @@ PROTOTYPES = {
     "aptai_layernorm": (c_int, [c_void_p, c_int, c_i64, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
                                 c_int, c_void_p]),
     "aptai_cast_pad_bf16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "aptai_cast_pad_h16": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "aptai_posconv_fold": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "aptai_posconv_fold_fmt": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                       c_void_p]),
+    "aptai_attention_fwd_fmt": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "aptai_attention_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "aptai_attention_fwd_v2": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "aptai_attention_fwd_v3": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
@@ -59,6 +63,7 @@ PROTOTYPES = {
     "aptai_tail": (c_int, [c_void_p, c_i64, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int, c_int, c_void_p,
                            c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "aptai_posconv_slab": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "aptai_posconv_slab_fmt": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "aptai_frame_lengths": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "aptai_cross_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_void_p, c_float, c_int, c_int, c_void_p, c_void_p,
@@ -130,6 +135,7 @@ PROTOTYPES = {
                                         c_void_p, c_void_p, c_void_p]),
     "aptai_dropout": (c_int, [c_void_p, c_int, c_void_p, c_i64, c_float, C.c_uint64, c_void_p, c_void_p, c_void_p]),
     "aptai_prepare_weights": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "aptai_prepare_weights_fmt": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
     "aptai_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                 c_float, c_float, c_float, c_float, c_float, c_int, c_float, c_void_p]),
     # ---- callers' data formats

@@ -181,7 +181,9 @@ def posconv(x_pad: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], 
             act: int = 1, row_shift: int = 0, seg_valid_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Grouped positional conv + bias + GELU + residual.  x_pad bf16 [B, T+2*halo, H] (halo = taps//2, zeroed),
     w bf16 [H, taps*64] (per output channel: tap-major, 64-padded group input channels)."""
-    _req(x_pad, BF16, "x_pad"); _req(w, BF16, "w")
+    fmt = _h16(x_pad, "x_pad")
+    if _h16(w, "w") != fmt:
+        raise TypeError("posconv: x_pad and w must have the same 16-bit dtype")
     B, Tp, H2 = x_pad.shape
     assert H2 == H and Tp == T + taps
     gw = H // groups
@@ -190,8 +192,8 @@ def posconv(x_pad: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], 
         # in-place h += gelu(conv + bias), 64-channel groups: the slab kernel loads every input row once
         _req(out_f32, F32, "out_f32")
         done = _gemm_hook(None) if _gemm_hook is not None else None       # part of the GEMM family (bench roofline leg)
-        check(_lib.load().aptai_posconv_slab(x_pad.data_ptr(), w.data_ptr(), _ptr(bias), out_f32.data_ptr(), B, T, H,
-                                             _stream()), "posconv_slab")
+        check(_lib.load().aptai_posconv_slab_fmt(x_pad.data_ptr(), w.data_ptr(), _ptr(bias), out_f32.data_ptr(), B, T, H,
+                                                 fmt, _stream()), "posconv_slab")
         if done is not None:
             done()
         return out_f32
@@ -204,11 +206,11 @@ def posconv(x_pad: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], 
     g.w = w.data_ptr(); g.N = H; g.block_n = gw; g.segs = B; g.rows_per_seg = T
     g.bias = _ptr(bias); g.gamma = None; g.beta = None; g.residual = _ptr(residual)
     g.out_f32 = out_f32.data_ptr(); g.out_bf16 = None; g.ldo = H; g.out_seg_stride = T
-    g.seg_valid_rows = None; g.mask_seg_rows = 0; g.act = act; g.ln = 0; g.ln_eps = 0.0; g.cta_pair = 0; g.half_fmt = 0
+    g.seg_valid_rows = None; g.mask_seg_rows = 0; g.act = act; g.ln = 0; g.ln_eps = 0.0; g.cta_pair = 0; g.half_fmt = fmt
     if seg_valid_rows is not None:
         g.seg_valid_rows = _req(seg_valid_rows, I32, "seg_valid_rows").data_ptr(); g.mask_seg_rows = T
     if out_pre is not None:
-        g.out_pre = _req(out_pre, BF16, "out_pre").data_ptr()
+        g.out_pre = _req(out_pre, x_pad.dtype, "out_pre").data_ptr()
     gemm_raw(g)
     return out_f32
 
@@ -268,22 +270,24 @@ def frame_lengths(samples: torch.Tensor, kernels, strides, want_i64: bool = True
     return o64, o32
 
 
-def cast_pad(x: torch.Tensor, halo: int) -> torch.Tensor:
+def cast_pad(x: torch.Tensor, halo: int, dtype=None) -> torch.Tensor:
     _req(x, F32, "x")
     B, T, H = x.shape
-    out = torch.empty((B, T + 2 * halo, H), dtype=BF16, device=x.device)
-    check(_lib.load().aptai_cast_pad_bf16(x.data_ptr(), B, T, H, halo, out.data_ptr(), _stream()), "cast_pad_bf16")
+    out = torch.empty((B, T + 2 * halo, H), dtype=dtype or BF16, device=x.device)
+    check(_lib.load().aptai_cast_pad_h16(x.data_ptr(), B, T, H, halo, out.data_ptr(), _h16(out, "out"), _stream()),
+          "cast_pad_h16")
     return out
 
 
-def posconv_fold(g: torch.Tensor, v: torch.Tensor, cpad: int = 64, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """weight_norm(dim=2) fold: g [1,1,taps], v [H, cin, taps] -> bf16 [H, taps*cpad]."""
+def posconv_fold(g: torch.Tensor, v: torch.Tensor, cpad: int = 64, out: Optional[torch.Tensor] = None,
+                 dtype=None) -> torch.Tensor:
+    """weight_norm(dim=2) fold: g [1,1,taps], v [H, cin, taps] -> bf16 (or `dtype` = fp16) [H, taps*cpad]."""
     _req(g, F32, "g"); _req(v, F32, "v")
     H, cin, taps = v.shape
-    w = out if out is not None else torch.empty((H, taps * cpad), dtype=BF16, device=v.device)
+    w = out if out is not None else torch.empty((H, taps * cpad), dtype=dtype or BF16, device=v.device)
     ws = torch.empty((taps,), dtype=F32, device=v.device)
-    check(_lib.load().aptai_posconv_fold(g.data_ptr(), v.data_ptr(), H, cin, taps, cpad, w.data_ptr(), ws.data_ptr(),
-                                         _stream()), "posconv_fold")
+    check(_lib.load().aptai_posconv_fold_fmt(g.data_ptr(), v.data_ptr(), H, cin, taps, cpad, w.data_ptr(), ws.data_ptr(),
+                                             _h16(w, "w"), _stream()), "posconv_fold")
     return w
 
 
@@ -320,11 +324,13 @@ ATTENTION_POLY8 = int(os.environ.get("APTAI_ATTN_POLY8", "3"))
 def attention(qkv: torch.Tensor, key_len: Optional[torch.Tensor], B: int, T: int, heads: int,
               out: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None,
               impl: Optional[int] = None, drop_p: float = 0.0, drop_seed: int = 0) -> torch.Tensor:
-    _req(qkv, BF16, "qkv")
+    fmt = _h16(qkv, "qkv")
     H = heads * 64
     assert qkv.numel() == B * T * 3 * H
     if out is None:
-        out = torch.empty((B * T, H), dtype=BF16, device=qkv.device)
+        out = torch.empty((B * T, H), dtype=qkv.dtype, device=qkv.device)
+    elif out.dtype != qkv.dtype:
+        raise TypeError("attention: out must have qkv's dtype")
     if key_len is None:
         key_len = torch.full((B,), T, dtype=I32, device=qkv.device)
     _req(key_len, I32, "key_len")
@@ -332,6 +338,7 @@ def attention(qkv: torch.Tensor, key_len: Optional[torch.Tensor], B: int, T: int
         _req(lse, F32, "lse")
         assert lse.numel() == B * heads * T
     if drop_p > 0:        # training: dropout on the attention probabilities lives in the query-tile-pair kernel
+        _req(qkv, BF16, "qkv")
         check(_lib.load().aptai_attention_fwd_dropout(qkv.data_ptr(), out.data_ptr(), _ptr(lse), key_len.data_ptr(), B,
                                                       T, heads, float(drop_p), int(drop_seed) & 0xFFFFFFFFFFFFFFFF,
                                                       _stream()), "attention_fwd_dropout")
@@ -339,7 +346,11 @@ def attention(qkv: torch.Tensor, key_len: Optional[torch.Tensor], B: int, T: int
     which = impl or ATTENTION_IMPL or (3 if T > 128 else 1)
     if which == 3:
         check(_lib.load().aptai_attention_fwd_v3(qkv.data_ptr(), out.data_ptr(), _ptr(lse), key_len.data_ptr(), B, T,
-                                                 heads, ATTENTION_POLY8, _stream()), "attention_fwd_v3")
+                                                 heads, ATTENTION_POLY8 | (fmt << 24), _stream()), "attention_fwd_v3")
+        return out
+    if fmt:               # fp16 operands: the two-threads-per-row kernel for short utterances
+        check(_lib.load().aptai_attention_fwd_fmt(qkv.data_ptr(), out.data_ptr(), _ptr(lse), key_len.data_ptr(), B, T,
+                                                  heads, fmt, _stream()), "attention_fwd_fmt")
         return out
     if which == 2:
         check(_lib.load().aptai_attention_fwd_v2(qkv.data_ptr(), out.data_ptr(), _ptr(lse), key_len.data_ptr(), B, T,
@@ -757,9 +768,11 @@ def bilstm_256_bwd(sv, d_hidden: torch.Tensor, grads: dict) -> torch.Tensor:
     return dx.view(B, T, 256)
 
 
-def prepare_weights(table: torch.Tensor, n_entries: int, total_tiles: int) -> None:
-    """Launch the multi-tensor weight preparation over a device table of `aptai_prep_entry` rows."""
-    check(_lib.load().aptai_prepare_weights(table.data_ptr(), n_entries, total_tiles, _stream()), "prepare_weights")
+def prepare_weights(table: torch.Tensor, n_entries: int, total_tiles: int, half_fmt: int = 0) -> None:
+    """Launch the multi-tensor weight preparation over a device table of `aptai_prep_entry` rows; `half_fmt` 1: the
+    16-bit destinations are IEEE fp16 instead of bf16."""
+    check(_lib.load().aptai_prepare_weights_fmt(table.data_ptr(), n_entries, total_tiles, half_fmt, _stream()),
+          "prepare_weights")
 
 
 def dropout(x: torch.Tensor, p: float, seed: int, *, residual: Optional[torch.Tensor] = None, want_f32: bool = False,

@@ -15,7 +15,8 @@ Every rank runs the full workload on its own GPU (utterance-sharded path, no col
 Beside the contract's keys the line carries the rest of the scorecard:
   roofline          GEMM family, valid-frame algorithmic FLOPs / CUDA-event time of its launches
   cpu_baseline      reference classes on the host cores, bounded stratified sample (rank 0, N = 1)
-  accuracy_mode     precision="f32x3" on a sample of the same batches: audio-s/s and agreement with the bf16 mode
+  accuracy_mode     precision="f32x3" on a sample of the same batches: audio-s/s and agreement with the bf16 mode;
+                    its `fp16_mode` entry: the default kernels on fp16 operands on the same batches
   library_baseline  the reference's classes in torch eager + bf16 autocast on the SAME GPU, same batches (N = 1)
   strong            ONE 4096-utterance set split over the N ranks by sweep.shard_lpt (N > 1)
   train             BASELINE config 4: APTAI training step, batch 32 / GPU, NCCL gradient all-reduce at N ranks
@@ -514,8 +515,6 @@ def accuracy_mode_leg(model, cfg, lengths, batches, devb, dev):
     default mode on the valid frames."""
     pick = sorted({len(batches) // 6, len(batches) // 2, (5 * len(batches)) // 6})
     audio = sum(lengths[i] for k in pick for i in batches[k].indices) / 16000.0
-    agree_n = agree_d = 0
-    tv_d = lg_d = 0.0
 
     def run(mode):
         model.set_precision(mode)
@@ -527,38 +526,48 @@ def accuracy_mode_leg(model, cfg, lengths, batches, devb, dev):
 
     ref = run("bf16")
     run("f32x3")                                     # warm-up (plan build)
+    run("fp16")
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    acc = run("f32x3")
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    e0.record()
-    run("bf16")
-    e1.record()
-    torch.cuda.synchronize()
-    ms16 = e0.elapsed_time(e1)
-    path_same = path_all = 0
-    for k, a, r in zip(pick, acc, ref):
-        flen = torch.tensor([cfg.conv_out_length(lengths[i]) for i in batches[k].indices], device=dev)
-        T = a["phn_fc_pred"].shape[1]
-        valid = torch.arange(T, device=dev)[None, :] < flen[:, None]
-        agree_n += int(((a["phn_fc_pred"] == r["phn_fc_pred"]) & valid).sum())
-        agree_d += int(valid.sum())
-        tv_d = max(tv_d, float((a["tvs_pred"] - r["tvs_pred"]).abs()[valid].max()))
-        lg_d = max(lg_d, float((a["phn_fc_logits"] - r["phn_fc_logits"]).abs()[valid].max()))
-        path_same += int(((a["align_paths"] == r["align_paths"]) & valid).sum())
-        path_all += int(valid.sum())
+
+    def timed_run(mode):
+        e0.record()
+        o = run(mode)
+        e1.record()
+        torch.cuda.synchronize()
+        return o, e0.elapsed_time(e1)
+
+    acc, ms = timed_run("f32x3")
+    _, ms16 = timed_run("bf16")
+    half, ms_h = timed_run("fp16")
+
+    def compare(outs):
+        """valid-frame agreement of one mode's outputs with the accuracy mode's"""
+        n = d = same = 0
+        tv_d = lg_d = 0.0
+        for k, a, r in zip(pick, acc, outs):
+            flen = torch.tensor([cfg.conv_out_length(lengths[i]) for i in batches[k].indices], device=dev)
+            T = a["phn_fc_pred"].shape[1]
+            valid = torch.arange(T, device=dev)[None, :] < flen[:, None]
+            n += int(((a["phn_fc_pred"] == r["phn_fc_pred"]) & valid).sum())
+            d += int(valid.sum())
+            tv_d = max(tv_d, float((a["tvs_pred"] - r["tvs_pred"]).abs()[valid].max()))
+            lg_d = max(lg_d, float((a["phn_fc_logits"] - r["phn_fc_logits"]).abs()[valid].max()))
+            same += int(((a["align_paths"] == r["align_paths"]) & valid).sum())
+        return {"phoneme_argmax_agreement_valid_frames": n / d, "frames": d, "tv_max_abs": tv_d, "logit_max_abs": lg_d,
+                "viterbi_path_agreement_valid_frames": same / max(1, d)}
+
     model.set_precision("bf16")
     return {"precision": "f32x3 (every contraction as three bf16 products on hi/lo operand pairs, fp32 elsewhere)",
             "value": audio / (ms * 1e-3), "unit": "audio-s/s", "bf16_value_same_batches": audio / (ms16 * 1e-3),
             "sample": f"batches {pick} of {len(batches)} ({audio:.0f} audio-s)",
-            "bf16_vs_f32x3": {"phoneme_argmax_agreement_valid_frames": agree_n / agree_d, "frames": agree_d,
-                              "tv_max_abs": tv_d, "logit_max_abs": lg_d,
-                              "viterbi_path_agreement_valid_frames": path_same / max(1, path_all)},
-            "parity": "north-star tolerances are asserted literally against the reference's goldens in this mode "
-                      "(tests/test_parity_gpu.py); the bf16 mode meets the TV / CTC-loss tolerances"}
+            "bf16_vs_f32x3": compare(ref),
+            "fp16_mode": {"precision": "fp16 (the default kernels on IEEE fp16 operands: weights, activations, attention "
+                                       "probabilities; fp32 accumulation, residual stream and statistics)",
+                          "value": audio / (ms_h * 1e-3), "unit": "audio-s/s", "fp16_vs_f32x3": compare(half)},
+            "parity": "north-star tolerances are asserted literally against the reference's goldens in the f32x3 mode "
+                      "(tests/test_parity_gpu.py); the bf16 mode meets the TV / CTC-loss tolerances, the fp16 mode "
+                      "also every CTC-type loss tolerance at 7x smaller logit / trajectory error"}
 
 
 def library_baseline_leg(cfg, lengths, batches, dev, ours):

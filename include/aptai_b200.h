@@ -116,11 +116,16 @@ int aptai_layernorm(const void* x, int x_fmt /* 0 f32, 1 bf16, 2 fp16 */, int64_
 
 /* fp32 [segs][rows][cols] -> bf16 [segs][halo+rows+halo][cols] with zeroed halo rows (HF:371-379 'same' pad). */
 int aptai_cast_pad_bf16(const float* x, int segs, int rows, int cols, int halo, void* out_bf16, void* stream);
+/* same with the 16-bit format chosen by the caller: half_fmt 0 = bf16, 1 = IEEE fp16 (precision="fp16" inference) */
+int aptai_cast_pad_h16(const float* x, int segs, int rows, int cols, int halo, void* out_h16, int half_fmt,
+                       void* stream);
 
 /* weight-norm fold of the positional conv (torch parametrizations.weight_norm, dim=2; HF:336-358):
  * w[o][c][j] = g[j] * v[o][c][j] / ||v[:, :, j]||, written bf16 as [H][taps][cpad] (cpad >= cin, zero padded). */
 int aptai_posconv_fold(const float* g, const float* v, int H, int cin, int taps, int cpad, void* w_bf16,
                        float* norm_ws, void* stream);
+int aptai_posconv_fold_fmt(const float* g, const float* v, int H, int cin, int taps, int cpad, void* w_h16,
+                           float* norm_ws, int half_fmt /* 0 bf16, 1 fp16 */, void* stream);
 
 /* Grouped positional conv for 64-channel groups (H % 64 == 0, 128 taps), in place on the fp32 hidden stream:
  * h[b][t][:] += gelu(conv(x_pad)[b][t][:] + bias)  (HF:329-379; x_pad bf16 [B][T+128][H] from aptai_cast_pad_bf16,
@@ -128,19 +133,27 @@ int aptai_posconv_fold(const float* g, const float* v, int H, int cin, int taps,
  * shift is a descriptor offset into a shared-memory slab (csrc/posconv_tc.cu). */
 int aptai_posconv_slab(const void* x_pad, const void* w_fold, const float* bias, float* h, int B, int T, int H,
                        void* stream);
+/* same on operands in the caller's 16-bit format (x_pad and w_fold both bf16, half_fmt 0, or both fp16, half_fmt 1) */
+int aptai_posconv_slab_fmt(const void* x_pad, const void* w_fold, const float* bias, float* h, int B, int T, int H,
+                           int half_fmt, void* stream);
 
 /* ------------------------------------------------------------------ attention (HF:500-549, SDPA) ------------
  * qkv: bf16 [B*T][3*H] (q | k | v, q pre-scaled by head_dim^-0.5), ctx: bf16 [B*T][H], head_dim 64.
  * Keys t >= key_len[b] are masked; every query row is computed (padded queries attend to valid keys, HF:438-463).
  */
 int aptai_attention_fwd(const void* qkv, void* ctx, const int32_t* key_len, int B, int T, int heads, void* stream);
+/* same kernel with the 16-bit format of qkv / ctx chosen by the caller (half_fmt 0 = bf16, 1 = IEEE fp16: q, k, v, the
+ * probabilities and the context carry three more mantissa bits at the same tensor-core rate); lse may be NULL */
+int aptai_attention_fwd_fmt(const void* qkv, void* ctx, float* lse, const int32_t* key_len, int B, int T, int heads,
+                            int half_fmt, void* stream);
 /* second-generation tcgen05 kernel, same contract (+ optional lse, may be NULL): two 128-query tiles per CTA share one
  * K/V stream and run independent softmax chains (csrc/attention_tc2.cu) */
 int aptai_attention_fwd_v2(const void* qkv, void* ctx, float* lse, const int32_t* key_len, int B, int T, int heads,
                            void* stream);
 /* third-generation kernel, same contract (csrc/attention_v3.cu): P stays in TMEM as the A operand of P V, three S
  * buffers per query tile, part of the exponentials on the FMA pipe, TMA store of the context tile.
- * poly8: exponential pairs per 8 evaluated by the polynomial (0, 2, 3, 4; any other value selects the default 3). */
+ * poly8 bits 0..7: exponential pairs per 8 evaluated by the polynomial (0, 2, 3, 4; any other value selects the default
+ * 3); bits 8..23: issuer back-off in ns (profiling); bit 24: qkv / ctx are IEEE fp16 instead of bf16. */
 int aptai_attention_fwd_v3(const void* qkv, void* ctx, float* lse, const int32_t* key_len, int B, int T, int heads,
                            int poly8, void* stream);
 
@@ -398,6 +411,8 @@ typedef struct aptai_prep_entry {
   int32_t tile0, tiles_x;
 } aptai_prep_entry;
 int aptai_prepare_weights(const void* entries_dev, int n_entries, int total_tiles, void* stream);
+/* same with every 16-bit destination of the launch written as IEEE fp16 (half_fmt 1) instead of bf16 (0) */
+int aptai_prepare_weights_fmt(const void* entries_dev, int n_entries, int total_tiles, int half_fmt, void* stream);
 
 /* Inverted dropout, counter-based (HF:434,546,570,603-607,647-653,694,766; models/aptai.py:44,52; w2v2_pr.py:56):
  * out[i] = residual[i] + keep(seed, i) * x[i] / (1 - p), keep = hash(seed, i) >= p.  x fp32 or bf16 (x_bf16), residual

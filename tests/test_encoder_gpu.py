@@ -93,3 +93,37 @@ def test_maximum_length_20s(cuda):
     alone = m(wav[1:2, :32000].contiguous().to(cuda), attention_mask=torch.tensor([[32000]], device=cuda))
     d = (out.last_hidden_state[1, :99] - alone.last_hidden_state[0, :99]).abs().max().item()
     assert d < 3e-2, d
+
+
+@pytest.mark.parametrize("variant,H,heads,F,lens", [("layer", 1024, 16, 4096, [64000, 20000]),
+                                                    ("group", 768, 12, 3072, [32000, 20000]),
+                                                    ("layer", 256, 4, 512, [8000, 400, 3217])])
+def test_fp16_operand_mode(cuda, variant, H, heads, F, lens):
+    """precision="fp16": the same kernels on IEEE fp16 operands (both LayerNorm wirings, both pos-conv paths, both
+    attention kernels: T = 199 / 99 / 24) — the hidden states land eight times closer to the fp32 oracle than in bf16,
+    switching back gives the bf16 result bit for bit, and training stays on the bf16 plan."""
+    cfg = _cfg(variant, hidden_size=H, num_attention_heads=heads, intermediate_size=F,
+               num_conv_pos_embedding_groups=16 if H > 256 else 4)
+    sd = backbone_state_dict(cfg, seed=0)
+    wav = waveforms(len(lens), max(lens), lens, seed=1234)
+    ref = ow.forward(sd, cfg, wav, lens)
+    m = Wav2Vec2Backbone(cfg)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(cuda).eval()
+    am = torch.tensor(lens, device=cuda)[:, None]
+    o_bf = m(wav.to(cuda), attention_mask=am).last_hidden_state.clone()
+    m.set_precision("fp16")
+    out = m(wav.to(cuda), attention_mask=am, output_hidden_states=True)
+    assert m._plan_h is not None and m._plan_h.layers[0].qkv_w.dtype == torch.float16
+    assert m._plan.layers[0].qkv_w.dtype == torch.bfloat16
+    for i, (r, o) in enumerate(zip(ref, out.hidden_states)):
+        err = (o.cpu() - r).abs().max().item()
+        assert err < 8e-3, f"{variant}: hidden[{i}] max abs err {err}"
+    err = (out.last_hidden_state.cpu() - ref[-1]).abs()
+    e_bf = (o_bf.cpu() - ref[-1]).abs()
+    assert err.mean().item() < 1.5e-3 and err.mean().item() < 0.35 * e_bf.mean().item(), (err.mean().item(),
+                                                                                            e_bf.mean().item())
+    m.set_precision("bf16")
+    assert torch.equal(m(wav.to(cuda), attention_mask=am).last_hidden_state, o_bf)
+    with pytest.raises(ValueError):
+        m.set_precision("fp8")

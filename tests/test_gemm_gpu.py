@@ -147,3 +147,48 @@ def test_posconv_slab_matches_generic(cuda, T, B):
     finally:
         ops.POSCONV_SLAB = old
     torch.testing.assert_close(h1, h2, atol=2e-6, rtol=2e-6)
+
+
+@pytest.mark.parametrize("H,groups,T,B", [(1024, 16, 399, 2), (768, 16, 130, 2)])
+def test_posconv_fp16_operands(cuda, H, groups, T, B):
+    """precision="fp16": fold, cast + pad and both pos-conv kernels (slab for 64-channel groups, generic otherwise) on
+    IEEE fp16 operands against the fp32 conv on fp16-rounded operands."""
+    taps = 128
+    gw = H // groups
+    x = _rand((B, T, H), cuda, 1.0, 50)
+    v = _rand((H, gw, taps), cuda, 2 * (1.0 / (taps * H)) ** 0.5, 51)
+    g = torch.linalg.vector_norm(v, dim=(0, 1), keepdim=True) * (1 + _rand((1, 1, taps), cuda, 0.05, 52))
+    bias = _rand((H,), cuda, 0.1, 53)
+    wf = ops.posconv_fold(g.contiguous(), v.contiguous(), 64, dtype=torch.float16)
+    assert wf.dtype == torch.float16
+    w_ref = g * v / torch.linalg.vector_norm(v, dim=(0, 1), keepdim=True)
+    wf_ref = torch.zeros((H, taps, 64), device=cuda)
+    wf_ref[:, :, :gw] = w_ref.permute(0, 2, 1)
+    torch.testing.assert_close(wf.float().view(H, taps, 64), wf_ref.half().float(), atol=1e-6, rtol=2e-3)
+    xp = ops.cast_pad(x, taps // 2, dtype=torch.float16)
+    assert xp.dtype == torch.float16 and torch.equal(xp[:, taps // 2: taps // 2 + T], x.half())
+    assert float(xp[:, : taps // 2].abs().max()) == 0 and float(xp[:, taps // 2 + T:].abs().max()) == 0
+    h = x.clone().view(B * T, H)
+    ops.posconv(xp, wf, bias, h, T, H, groups, taps, h)
+    pos = F.conv1d(x.half().float().transpose(1, 2), w_ref.half().float(), bias, padding=taps // 2,
+                   groups=groups)[:, :, :-1]
+    ref = x + F.gelu(pos).transpose(1, 2)
+    torch.testing.assert_close(h.view(B, T, H), ref, atol=1e-4, rtol=1e-4)
+    with pytest.raises(TypeError):
+        ops.posconv(xp, wf.bfloat16(), bias, h, T, H, groups, taps, h)
+
+
+def test_linear_fp16_operands(cuda):
+    """The transformer GEMM shapes on fp16 operands (QKV, FFN1 + GELU, FFN2 + in-place residual)."""
+    M, H, Fi = 700, 1024, 4096
+    x = _rand((M, H), cuda, 1.0, 60)
+    w1, b1 = _rand((Fi, H), cuda, 0.03, 61), _rand((Fi,), cuda, 0.1, 62)
+    w2, b2 = _rand((H, Fi), cuda, 0.02, 63), _rand((H,), cuda, 0.1, 64)
+    _, u = ops.linear(x.half(), w1.half(), b1, act=1)
+    assert u.dtype == torch.float16
+    ref_u = F.gelu(x.half().float() @ w1.half().float().t() + b1)
+    torch.testing.assert_close(u.float(), ref_u, atol=2e-3, rtol=2e-3)
+    h = _rand((M, H), cuda, 1.0, 65)
+    h0 = h.clone()
+    ops.linear(u, w2.half(), b2, residual=h, out_f32=h, want_bf16=False)
+    torch.testing.assert_close(h, h0 + u.float() @ w2.half().float().t() + b2, atol=2e-4, rtol=2e-4)

@@ -160,6 +160,35 @@ def test_heads_lowpass_losses(cuda):
     torch.testing.assert_close(out.cpu(), torch.stack([loss, mse, ce]), atol=1e-5, rtol=1e-5)
 
 
+@pytest.mark.parametrize("B,T,heads,lens,scale", [(2, 199, 16, [199, 150], 1.0), (3, 64, 12, [64, 1, 33], 1.0),
+                                                  (1, 999, 4, [999], 1.0), (2, 513, 2, [513, 400], 3.0),
+                                                  (2, 128, 2, [128, 127], 1.0), (40, 399, 16, None, 0.5)])
+def test_attention_fp16_operands(cuda, B, T, heads, lens, scale):
+    """precision="fp16": both attention kernels (two threads per row for T <= 128, query-tile pairs with P in TMEM
+    above) on IEEE fp16 q / k / v / P / context — eight times tighter than the bf16 tolerance of test_attention."""
+    H = heads * 64
+    qkv = _rand((B * T, 3 * H), cuda, scale, 9).half()
+    if lens is None:
+        lens = [max(1, T - (7 * b) % 200) for b in range(B)]
+    if scale > 1.0:
+        qkv[T // 2:, H: 2 * H] *= 4.0          # later keys score much higher: exercises the lazy O rescale
+    kl = torch.tensor(lens, dtype=torch.int32, device=cuda)
+    q, k, v = qkv.float().view(B, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    s = q @ k.transpose(-1, -2)
+    mask = torch.arange(T, device=cuda)[None, :] < kl[:, None]
+    s = s.masked_fill(~mask[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * T, H)
+    for impl in (None, 3):                       # by shape, and the query-tile-pair kernel forced
+        lse = torch.empty((B, heads, T), dtype=torch.float32, device=cuda)
+        ctx = ops.attention(qkv, kl, B, T, heads, impl=impl, lse=lse,
+                            out=torch.full((B * T, H), float("nan"), dtype=torch.float16, device=cuda))
+        assert ctx.dtype == torch.float16
+        torch.testing.assert_close(ctx.float(), ref, atol=2.5e-3, rtol=2.5e-3)
+        torch.testing.assert_close(lse, torch.logsumexp(s, -1) * 1.4426950408889634, atol=2e-2, rtol=1e-3)
+    with pytest.raises(TypeError):
+        ops.attention(qkv, kl, B, T, heads, out=torch.empty((B * T, H), dtype=torch.bfloat16, device=cuda))
+
+
 def _ctc_case(B, T, V, Smax, seed, repeats=False):
     rng = np.random.default_rng(seed)
     logits = rng.standard_normal((B, T, V)).astype(np.float32) * 2

@@ -8,6 +8,9 @@ Tolerances are the literal ones of BASELINE.json's north_star:
     CTC / CTC-type losses      <= 1e-3 relative                                       (both modes for the CTC loss;
                                                                                        f32x3 for Force's align_loss)
     phoneme argmax agreement   >= 99.9 %                                              (precision="f32x3")
+precision="fp16" (the default kernels on IEEE fp16 operands, same speed) is asserted on what three more mantissa bits
+buy: the literal CTC-type loss tolerance everywhere (Force_APTAI's align_loss included), trajectories within 2.5e-3,
+logits within 4e-3 and a raw argmax agreement >= 99.5 % (profiles/scripts/operand_format_study.py: 99.8 % expected).
 In the default bf16 mode the argmax criterion is not reachable on an untrained head (median top-2 margin 0.07 vs a
 bf16 logit error of ~1e-2): there the tests assert full agreement on every frame whose fp32
 top-2 margin exceeds 4x the measured logit error and record the raw figure in gpurun_out/parity_report.json.
@@ -27,7 +30,7 @@ from aptai_b200.backbone import register_in_memory_checkpoint
 from oracle import weights as W
 
 REPORT = os.path.join(ROOT, "gpurun_out", "parity_report.json")
-MODES = ["f32x3", "bf16"]
+MODES = ["f32x3", "fp16", "bf16"]
 
 
 def _report(key, val):
@@ -55,6 +58,8 @@ def _check_argmax(mode, key, raw, safe, err, frames):
                                 "logit_max_abs_err": err, "frames": int(frames)})
     if mode == "f32x3":
         assert raw >= 0.999, (key, raw, err)               # north star, literal
+    elif mode == "fp16":
+        assert safe == 1.0 and raw >= 0.995 and err <= 4e-3, (key, raw, safe, err)
     else:
         assert safe == 1.0 and raw >= 0.97, (key, raw, safe, err)
 
@@ -88,7 +93,7 @@ def test_aptai_single_utterance_8s_20s(aptai_large, mode, tag, L, seed):
     d = float(np.abs(tvs - g[f"{tag}_tvs"]).max())
     pc = float(pearson(tvs, g[f"{tag}_tvs"]).min())
     _report(f"aptai_{tag}_tv[{mode}]", {"tv_max_abs": d, "pearson_min": pc})
-    assert d <= 1e-2 and pc >= 0.999, (d, pc)
+    assert d <= (2.5e-3 if mode == "fp16" else 1e-2) and pc >= 0.999, (d, pc)
     raw, safe, err = _argmax(r["phn_fc_logits"], g[f"{tag}_logits"])
     _check_argmax(mode, f"aptai_{tag}", raw, safe, err, T)
     assert np.array_equal(r["phn_fc_pred"], r["phn_fc_logits"].argmax(-1))
@@ -119,12 +124,12 @@ def test_aptai_forward_ragged_batch(aptai_large, cuda, mode):
     raw, safe, err = _argmax(lg[valid], g["r4_logits"][valid])
     _report(f"aptai_forward_b4_ragged[{mode}]", {"tv_max_abs_valid": d, "pearson_min": pc, "losses": losses.tolist(),
                                                  "ref_losses": g["r4_losses"].tolist(), "loss_rel": rel.tolist()})
-    assert d <= 1e-2 and pc >= 0.999, (d, pc)
-    assert rel.max() <= (1e-3 if mode == "f32x3" else 5e-3), rel
+    assert d <= (2.5e-3 if mode == "fp16" else 1e-2) and pc >= 0.999, (d, pc)
+    assert rel.max() <= (5e-3 if mode == "bf16" else 1e-3), rel
     _check_argmax(mode, "aptai_forward_b4_ragged", raw, safe, err, valid.sum())
     pred = out["phn_fc_pred"].cpu().numpy()
     agree = float((pred[valid] == g["r4_pred"].astype(np.int64)[valid]).mean())
-    assert agree >= (0.999 if mode == "f32x3" else 0.97), agree
+    assert agree >= {"f32x3": 0.999, "fp16": 0.995, "bf16": 0.97}[mode], agree
     # padded-batch semantics: the same utterance alone gives the same valid frames ('layer' variant)
     if mode == "bf16":
         one = aptai_large.predict(wav[3:4, :71000].contiguous(), torch.tensor([71000], device=cuda))
@@ -161,7 +166,7 @@ def test_pr_forward_config2_16x8s(cuda, mode):
     _report(f"pr_config2_16x8s[{mode}]", {"ctc_loss": loss, "ref": ref, "rel": rel, "grad_logits_max_abs_err": gerr})
     assert rel <= 1e-3, (loss, ref)                          # north star, literal, both modes
     _check_argmax(mode, "pr_config2_16x8s", raw, safe, err, valid.sum())
-    assert gerr <= (2e-5 if mode == "f32x3" else 2e-3), gerr
+    assert gerr <= {"f32x3": 2e-5, "fp16": 4e-4, "bf16": 2e-3}[mode], gerr
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -194,9 +199,12 @@ def test_force_aptai_8s(cuda, mode):
     _report(f"force_aptai_8s[{mode}]", {"alignment_prob_max_abs": dp, "frame_argmax_agreement": agree,
                                         "frame_phn_agreement": fp_agree, "tv_max_abs": d, "losses": losses.tolist(),
                                         "ref_losses": g["f8_losses"].tolist(), "loss_rel": rel.tolist()})
-    assert d <= 1e-2, d
+    assert d <= (2.5e-3 if mode == "fp16" else 1e-2), d
     if mode == "f32x3":
         assert rel.max() <= 1e-3, rel                        # align_loss is CTC-based: the CTC tolerance, literal
         assert agree >= 0.999 and fp_agree >= 0.999 and dp < 2e-3, (agree, fp_agree, dp)
+    elif mode == "fp16":
+        assert rel.max() <= 1e-3, rel                        # the literal tolerance at the default kernels' speed
+        assert agree >= 0.99 and dp < 1e-2, (agree, dp)
     else:
         assert rel.max() <= 1e-2 and agree >= 0.95 and dp < 5e-2, (rel, agree, dp)
