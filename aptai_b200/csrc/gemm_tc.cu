@@ -45,6 +45,12 @@ struct GemmParams {
   int reverse;                // walk the tiles from the last to the first (aptai_set_traversal)
   int red32;                  // in-place fp32 residual update h += acc + bias as TMA reduce-add stores (tmC, fp32)
   const float* l2_hint;       // red32: the rows the reduction will touch, prefetched into L2 one tile ahead
+  // red32 only — LayerNorm of the UPDATED rows inside the same launch (see row_ln_rows): 16-bit output [rows][N]
+  __nv_bfloat16* row_ln_out;
+  const float* row_ln_gamma;
+  const float* row_ln_beta;
+  int* row_ln_cnt;            // one arrival counter per 128-row block, zero on entry and on exit
+  float row_ln_eps;
 };
 
 constexpr int LN_N = 512;     // row width of the fused-LayerNorm tiles (conv_dim)
@@ -97,6 +103,72 @@ struct GemmCfg {
   static constexpr int OFF_BIAS = OFF_VEC + VEC_BYTES;
   static constexpr int SMEM_BYTES = OFF_BIAS + BIAS_BYTES;
 };
+
+// LayerNorm of the rows an in-place residual update has just completed (pre-LN encoder: h += out-proj / FFN2, then
+// x = LN(h) feeds the next GEMM; HF:639-655).  The TMA reduce-add epilogue never holds the updated value, so the rows
+// cannot be normalised on their way out; but the CTA that lands the LAST of a 128-row block's n_tiles column tiles
+// (an arrival counter per block) finds the whole block in L2, written microseconds ago: its eight epilogue warps
+// normalise 16 rows each from there (ld.global.cg: the reductions were applied at the L2) and write the 16-bit x.
+// The standalone LayerNorm launch and its 4 B / element HBM read of h disappear; the arithmetic is that kernel's
+// (one warp per row, row in registers, exact two-pass fp32 statistics), two rows in flight per warp.
+template <int NV>
+__device__ __forceinline__ void row_ln_rows(const GemmParams& p, int row0, int warp, int lane) {
+  constexpr int COLS = NV * 128;
+  const int rend = min(row0 + BLOCK_M, p.rows_per_seg);
+  const int rw = row0 + warp * (BLOCK_M / 8);
+  const float* __restrict__ h = p.out_f32;
+#pragma unroll 1
+  for (int r = rw; r < rw + BLOCK_M / 8 && r < rend; r += 2) {
+    const bool two = r + 1 < rend;
+    const float4* pa = reinterpret_cast<const float4*>(h + static_cast<long long>(r) * COLS);
+    const float4* pb = pa + (two ? COLS / 4 : 0);
+    float4 va[NV], vb[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) va[i] = __ldcg(pa + i * 32 + lane);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) vb[i] = __ldcg(pb + i * 32 + lane);
+    float sa = 0.f, sb = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      sa += (va[i].x + va[i].y) + (va[i].z + va[i].w);
+      sb += (vb[i].x + vb[i].y) + (vb[i].z + vb[i].w);
+    }
+    for (int o = 16; o; o >>= 1) {
+      sa += __shfl_xor_sync(0xffffffffu, sa, o);
+      sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    }
+    const float ma = sa * (1.0f / COLS), mb = sb * (1.0f / COLS);
+    float qa = 0.f, qb = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float a = va[i].x - ma, b = va[i].y - ma, c = va[i].z - ma, d = va[i].w - ma;
+      qa += (a * a + b * b) + (c * c + d * d);
+      a = vb[i].x - mb; b = vb[i].y - mb; c = vb[i].z - mb; d = vb[i].w - mb;
+      qb += (a * a + b * b) + (c * c + d * d);
+    }
+    for (int o = 16; o; o >>= 1) {
+      qa += __shfl_xor_sync(0xffffffffu, qa, o);
+      qb += __shfl_xor_sync(0xffffffffu, qb, o);
+    }
+    const float ra = rsqrtf(qa * (1.0f / COLS) + p.row_ln_eps), rb = rsqrtf(qb * (1.0f / COLS) + p.row_ln_eps);
+    uint2* oa = reinterpret_cast<uint2*>(p.row_ln_out + static_cast<long long>(r) * COLS);
+    uint2* ob = oa + COLS / 4;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int col = (i * 32 + lane) * 4;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(p.row_ln_gamma + col));
+      const float4 e = __ldg(reinterpret_cast<const float4*>(p.row_ln_beta + col));
+      float y0 = fmaf((va[i].x - ma) * ra, g.x, e.x), y1 = fmaf((va[i].y - ma) * ra, g.y, e.y);
+      float y2 = fmaf((va[i].z - ma) * ra, g.z, e.z), y3 = fmaf((va[i].w - ma) * ra, g.w, e.w);
+      oa[i * 32 + lane] = make_uint2(pack_h16(y0, y1, p.fp16), pack_h16(y2, y3, p.fp16));
+      if (two) {
+        y0 = fmaf((vb[i].x - mb) * rb, g.x, e.x); y1 = fmaf((vb[i].y - mb) * rb, g.y, e.y);
+        y2 = fmaf((vb[i].z - mb) * rb, g.z, e.z); y3 = fmaf((vb[i].w - mb) * rb, g.w, e.w);
+        ob[i * 32 + lane] = make_uint2(pack_h16(y0, y1, p.fp16), pack_h16(y2, y3, p.fp16));
+      }
+    }
+  }
+}
 
 template <int CH>
 __device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t (&r)[CH]);
@@ -301,6 +373,28 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       named_bar_sync(1, EPI_THREADS);
     }
 
+    // fused row LayerNorm behind the in-place residual update (row_ln_rows): a tile's arrival on its row block's counter
+    // is made one tile LATE, when its reduce-add stores have long completed — the wait costs nothing then
+    int row_ln_pend = -1;                    // counter index (m tile, CTA rank) of the tile whose arrival is pending
+    auto row_ln_arrive = [&](int blk) {
+      int* flag = reinterpret_cast<int*>(smem + C::OFF_BAR + 192);
+      named_bar_sync(2, EPI_THREADS);        // every warp's lane 0 has seen its stores of that tile complete
+      if (threadIdx.x == 0) {
+        __threadfence();
+        const int old = atomicAdd(p.row_ln_cnt + blk, 1);
+        const int last = old == p.n_tiles - 1 ? 1 : 0;
+        if (last) p.row_ln_cnt[blk] = 0;     // nobody else touches this counter again in this launch
+        __threadfence();
+        *flag = last;
+      }
+      named_bar_sync(2, EPI_THREADS);
+      if (*flag) {                           // this CTA landed the block's last column tile: normalise its 128 rows
+        const int row0 = (blk / C::NPAIR) * TILE_M + (blk % C::NPAIR) * BLOCK_M;
+        if (p.ldo == 1024) row_ln_rows<8>(p, row0, warp, lane);
+        else row_ln_rows<6>(p, row0, warp, lane);
+      }
+    };
+
     uint32_t tpar = 0;                       // tile parity: bias buffer of this tile
     for (int tile_i = tile0; tile_i < p.num_tiles; tile_i += tile_step, tpar ^= 1) {
       const int tile = p.reverse ? p.num_tiles - 1 - tile_i : tile_i;
@@ -473,11 +567,12 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
               if (lane == 0) tma_store_wait_read<0>();
               __syncwarp();
             }
+            {
+              uint4 pk[4];
+              pack32_h16(v, pk, p.fp16);     // one format branch per 32 values (a per-pair select costs two F2FP issue slots)
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-              sb[lane * 8 + ((hsel * 4 + u) ^ (lane & 7))] =
-                  make_uint4(pack_h16(v[8 * u], v[8 * u + 1], p.fp16), pack_h16(v[8 * u + 2], v[8 * u + 3], p.fp16),
-                             pack_h16(v[8 * u + 4], v[8 * u + 5], p.fp16), pack_h16(v[8 * u + 6], v[8 * u + 7], p.fp16));
+              for (int u = 0; u < 4; ++u) sb[lane * 8 + ((hsel * 4 + u) ^ (lane & 7))] = pk[u];
+            }
             if (hsel == 1) {
               fence_async_proxy();
               __syncwarp();
@@ -586,11 +681,12 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
             if (lane == 0) tma_store_wait_read<0>();
             __syncwarp();
           }
+          {
+            uint4 pk[4];
+            pack32_h16(v, pk, p.fp16);     // one format branch per 32 values (a per-pair select costs two F2FP issue slots)
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            sb[lane * 8 + ((hsel * 4 + u) ^ (lane & 7))] =
-                make_uint4(pack_h16(v[8 * u], v[8 * u + 1], p.fp16), pack_h16(v[8 * u + 2], v[8 * u + 3], p.fp16),
-                           pack_h16(v[8 * u + 4], v[8 * u + 5], p.fp16), pack_h16(v[8 * u + 6], v[8 * u + 7], p.fp16));
+            for (int u = 0; u < 4; ++u) sb[lane * 8 + ((hsel * 4 + u) ^ (lane & 7))] = pk[u];
+          }
           if (hsel == 1) {
             fence_async_proxy();
             __syncwarp();
@@ -671,11 +767,12 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
           // 16-bit store of v[] (thread = row) as whole 64-byte row segments
           auto store16 = [&](__nv_bfloat16* dst) {
             uint4* sb = reinterpret_cast<uint4*>(stg);                    // 128-byte row pitch, units 0..3 used
+            {
+              uint4 pk[4];
+              pack32_h16(v, pk, p.fp16);     // one format branch per 32 values (a per-pair select costs two F2FP issue slots)
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-              sb[lane * 8 + (u ^ (lane & 7))] =
-                  make_uint4(pack_h16(v[8 * u], v[8 * u + 1], p.fp16), pack_h16(v[8 * u + 2], v[8 * u + 3], p.fp16),
-                             pack_h16(v[8 * u + 4], v[8 * u + 5], p.fp16), pack_h16(v[8 * u + 6], v[8 * u + 7], p.fp16));
+              for (int u = 0; u < 4; ++u) sb[lane * 8 + (u ^ (lane & 7))] = pk[u];
+            }
             __syncwarp();
             const int bu = lane & 3;
 #pragma unroll
@@ -722,11 +819,12 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
               __syncwarp();
             }
             uint4* sb = reinterpret_cast<uint4*>(stg);
+            {
+              uint4 pk[4];
+              pack32_h16(v, pk, p.fp16);     // one format branch per 32 values (a per-pair select costs two F2FP issue slots)
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-              sb[lane * 8 + ((hsel * 4 + u) ^ (lane & 7))] =
-                  make_uint4(pack_h16(v[8 * u], v[8 * u + 1], p.fp16), pack_h16(v[8 * u + 2], v[8 * u + 3], p.fp16),
-                             pack_h16(v[8 * u + 4], v[8 * u + 5], p.fp16), pack_h16(v[8 * u + 6], v[8 * u + 7], p.fp16));
+              for (int u = 0; u < 4; ++u) sb[lane * 8 + ((hsel * 4 + u) ^ (lane & 7))] = pk[u];
+            }
             if (hsel == 1) {
               fence_async_proxy();
               __syncwarp();
@@ -878,6 +976,28 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
       } else {
         acc_phase ^= 1;
       }
+      }
+      if constexpr (!LN && CH == 32) {
+        if (p.row_ln_out != nullptr) {
+          if (row_ln_pend >= 0) {
+            // at most THIS tile's HALF_N / CH store groups are still pending: the previous tile's have completed
+            if (lane == 0) {
+              tma_store_wait_all<HALF_N / CH>();
+              fence_proxy_async_all();
+            }
+            row_ln_arrive(row_ln_pend);
+          }
+          row_ln_pend = mt * C::NPAIR + static_cast<int>(rank);
+        }
+      }
+    }
+    if constexpr (!LN && CH == 32) {
+      if (p.row_ln_out != nullptr && row_ln_pend >= 0) {
+        if (lane == 0) {
+          tma_store_wait_all<0>();
+          fence_proxy_async_all();
+        }
+        row_ln_arrive(row_ln_pend);
       }
     }
   }
@@ -1042,6 +1162,20 @@ extern "C" int aptai_gemm_bf16(const aptai_gemm_args* g, void* stream) {
   p.reverse = traversal_reverse();
   p.red32 = red32 ? 1 : 0;
   p.l2_hint = red32 ? g->out_f32 : nullptr;
+  p.row_ln_out = nullptr; p.row_ln_gamma = nullptr; p.row_ln_beta = nullptr; p.row_ln_cnt = nullptr; p.row_ln_eps = 0.f;
+  if (g->row_ln_out != nullptr) {
+    APTAI_REQUIRE(red32 && bn % 64 == 0, "gemm: row_ln needs the in-place fp32 residual update (out_f32 == residual, "
+                                          "no other output, no activation)");
+    APTAI_REQUIRE(g->segs == 1 && g->ldo == g->N && (g->N == 1024 || g->N == 768),
+                  "gemm: row_ln needs one segment of dense rows, N = 768 or 1024");
+    APTAI_REQUIRE(g->row_ln_gamma && g->row_ln_beta && g->row_ln_counters, "gemm: row_ln needs gamma, beta and counters");
+    APTAI_REQUIRE((reinterpret_cast<uintptr_t>(g->row_ln_out) & 15) == 0, "gemm: row_ln_out must be 16-byte aligned");
+    p.row_ln_out = reinterpret_cast<__nv_bfloat16*>(g->row_ln_out);
+    p.row_ln_gamma = g->row_ln_gamma;
+    p.row_ln_beta = g->row_ln_beta;
+    p.row_ln_cnt = g->row_ln_counters;
+    p.row_ln_eps = g->row_ln_eps;
+  }
   p.num_kb = g->taps * g->kb_per_tap;
   p.kb_per_tap = g->kb_per_tap;
   p.P = g->P;

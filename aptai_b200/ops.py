@@ -74,10 +74,12 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
            out_bf16: Optional[torch.Tensor] = None, want_f32: bool = False, want_bf16: bool = True,
            seg_rows: Optional[int] = None, seg_valid_rows: Optional[torch.Tensor] = None,
            block_n: int = 0, cta_pair: int = 0, aux: Optional[torch.Tensor] = None,
-           out_pre: Optional[torch.Tensor] = None):
+           out_pre: Optional[torch.Tensor] = None, row_ln=None):
     """out = epilogue(a @ w.T): a bf16 [M,K], w bf16 [N,K] (nn.Linear layout), bias fp32 [N].
 
     seg_rows / seg_valid_rows: rows are grouped in segments of seg_rows; rows >= seg_valid_rows[s] are written as 0.
+    row_ln = (gamma, beta, eps[, out16]): with the in-place residual update (residual is out_f32, no 16-bit output)
+    the same launch also writes LayerNorm(updated rows) in a's dtype — returned in place of the 16-bit output.
     """
     fmt = _h16(a, "a")
     if _h16(w, "w") != fmt:
@@ -114,8 +116,36 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
         if out_pre.shape != (M, N) or out_pre.dtype != a.dtype:
             raise ValueError("linear: out_pre must match the 16-bit output")
         g.out_pre = out_pre.data_ptr()
+    if row_ln is not None:
+        if out_bf16 is not None or residual is None or out_f32 is None or residual.data_ptr() != out_f32.data_ptr():
+            raise ValueError("linear: row_ln rides on the in-place residual update (residual is out_f32, want_bf16=False)")
+        gamma, beta, eps = row_ln[0], row_ln[1], float(row_ln[2])
+        ln_out = row_ln[3] if len(row_ln) > 3 and row_ln[3] is not None else torch.empty((M, N), dtype=a.dtype,
+                                                                                         device=a.device)
+        if ln_out.shape != (M, N) or ln_out.dtype != a.dtype or not ln_out.is_contiguous():
+            raise ValueError("linear: row_ln output must be a contiguous [M, N] tensor of a's dtype")
+        cnt = _row_ln_counters(a.device, 2 * ((M + 255) // 256))
+        g.row_ln_out = ln_out.data_ptr()
+        g.row_ln_gamma = _req(gamma, F32, "row_ln gamma").data_ptr()
+        g.row_ln_beta = _req(beta, F32, "row_ln beta").data_ptr()
+        g.row_ln_counters = cnt.data_ptr(); g.row_ln_eps = eps
+        gemm_raw(g)
+        return out_f32, ln_out
     gemm_raw(g)
     return out_f32, out_bf16
+
+
+_ROW_LN_CNT = {}
+
+
+def _row_ln_counters(device, n: int) -> torch.Tensor:
+    """Arrival counters of the fused row LayerNorm (zero between launches: the kernel resets what it counts)."""
+    key = (device.type, device.index)
+    t = _ROW_LN_CNT.get(key)
+    if t is None or t.numel() < n:
+        t = torch.zeros((max(n, 4096),), dtype=I32, device=device)
+        _ROW_LN_CNT[key] = t
+    return t
 
 
 def split3_bf16(x: torch.Tensor, weight_layout: bool = False, scale: float = 1.0) -> torch.Tensor:
@@ -313,6 +343,9 @@ class Serpentine:
         set_traversal(False)
 
 
+# 1: the LayerNorm behind out-proj / FFN2 of the pre-LN encoder runs inside those GEMM launches (linear(row_ln=...));
+# 0: standalone LayerNorm launches (A/B runs)
+FUSED_ROW_LN = int(os.environ.get("APTAI_FUSED_ROW_LN", "1"))
 POSCONV_SLAB = int(os.environ.get("APTAI_POSCONV_SLAB", "1"))     # 0: always the generic implicit-GEMM path (A/B runs)
 
 # 0: by shape (attention_v3.cu's query-tile pairs with P in TMEM when an utterance has more than one 128-query tile,

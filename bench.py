@@ -530,16 +530,23 @@ def accuracy_mode_leg(model, cfg, lengths, batches, devb, dev):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    def timed_run(mode):
+    def timed_run(mode, reps):
+        """`reps` back-to-back passes over the sample (the power cap needs a second to act: a single 0.2 s pass of a
+        16-bit mode runs at boost clocks the sustained step never sees)"""
+        run(mode)
+        torch.cuda.synchronize()
         e0.record()
-        o = run(mode)
+        for _ in range(reps):
+            o = run(mode)
         e1.record()
         torch.cuda.synchronize()
-        return o, e0.elapsed_time(e1)
+        return o, e0.elapsed_time(e1) / reps
 
-    acc, ms = timed_run("f32x3")
-    _, ms16 = timed_run("bf16")
-    half, ms_h = timed_run("fp16")
+    acc, ms = timed_run("f32x3", 2)
+    _, ms16 = timed_run("bf16", 8)
+    half, ms_h = timed_run("fp16", 8)
+    _, ms16b = timed_run("bf16", 8)                  # bf16 again behind fp16: the pair brackets box drift
+    ms16 = 0.5 * (ms16 + ms16b)
 
     def compare(outs):
         """valid-frame agreement of one mode's outputs with the accuracy mode's"""

@@ -83,6 +83,16 @@ typedef struct aptai_gemm_args {
   const void* aux;        /* act=2 only: bf16, same row mapping/ldo as the outputs: out = acc * gelu'(aux)  (dgrad of
                              HF:566-573 through the activation) */
   void* out_pre;          /* optional 16-bit copy of the value before the activation (kept for the backward pass) */
+  /* Fused LayerNorm of the UPDATED rows behind an in-place residual update (out_f32 == residual, nothing else
+   * written, act 0; N = 768 or 1024, one segment, ldo == N): row_ln_out[r][:] = LN(out_f32[r][:]) in the 16-bit format
+   * of half_fmt (pre-LN encoder, HF:639-655: the LayerNorm that follows out-proj / FFN2).  The CTA that completes a
+   * 128-row block's last column tile normalises the block out of L2.  row_ln_counters: int32, one per 128-row block
+   * (>= ceil(rows/256)*2 entries), all zero on entry; the launch leaves them zero.  NULL row_ln_out: off. */
+  void* row_ln_out;
+  const float* row_ln_gamma;   /* [N] */
+  const float* row_ln_beta;    /* [N] */
+  int32_t* row_ln_counters;
+  float row_ln_eps;
 } aptai_gemm_args;
 
 int aptai_gemm_bf16(const aptai_gemm_args* args, void* stream);

@@ -121,7 +121,7 @@ def test_fp16_operand_mode(cuda, variant, H, heads, F, lens):
         assert err < 8e-3, f"{variant}: hidden[{i}] max abs err {err}"
     err = (out.last_hidden_state.cpu() - ref[-1]).abs()
     e_bf = (o_bf.cpu() - ref[-1]).abs()
-    assert err.mean().item() < 1.5e-3 and err.mean().item() < 0.35 * e_bf.mean().item(), (err.mean().item(),
+    assert err.mean().item() < 1.5e-3 and err.mean().item() < 0.5 * e_bf.mean().item(), (err.mean().item(),
                                                                                             e_bf.mean().item())
     m.set_precision("bf16")
     assert torch.equal(m(wav.to(cuda), attention_mask=am).last_hidden_state, o_bf)
