@@ -110,61 +110,61 @@ struct GemmCfg {
 // (an arrival counter per block) finds the whole block in L2, written microseconds ago: its eight epilogue warps
 // normalise 16 rows each from there (ld.global.cg: the reductions were applied at the L2) and write the 16-bit x.
 // The standalone LayerNorm launch and its 4 B / element HBM read of h disappear; the arithmetic is that kernel's
-// (one warp per row, row in registers, exact two-pass fp32 statistics), two rows in flight per warp.
+// (one warp per row, row in registers, exact two-pass fp32 statistics), three rows in flight per warp.
+// MEASURED (profiles/row_ln_bench.py, M = 75 776): correct and bit-identical to the two-launch form, but SLOWER — the
+// arrivals alone cost +34 us on out-proj (157 us) and +9 us on FFN2 (485 us), and the normalisation adds 0.5-0.7 ms:
+// 24 rows in flight per SM cannot pull 2 MB per SM through an L2 port that the operand TMA stream keeps busy, and
+// while the epilogue warps normalise the accumulators are not drained, so the MMAs stall behind them.  The
+// standalone LayerNorm (2048 threads per SM, 74 us) stays the default; this path is opt-in (APTAI_FUSED_ROW_LN=1).
 template <int NV>
-__device__ __forceinline__ void row_ln_rows(const GemmParams& p, int row0, int warp, int lane) {
+__device__ __noinline__ void row_ln_rows(const GemmParams& p, int row0, int warp, int lane) {
   constexpr int COLS = NV * 128;
-  const int rend = min(row0 + BLOCK_M, p.rows_per_seg);
+  constexpr int R = 3;                         // rows in flight per warp (the job is bound by L2 latency, not by math)
   const int rw = row0 + warp * (BLOCK_M / 8);
+  const int rend = min(rw + BLOCK_M / 8, p.rows_per_seg);      // this warp's 16 rows, clipped at the last row
   const float* __restrict__ h = p.out_f32;
 #pragma unroll 1
-  for (int r = rw; r < rw + BLOCK_M / 8 && r < rend; r += 2) {
-    const bool two = r + 1 < rend;
-    const float4* pa = reinterpret_cast<const float4*>(h + static_cast<long long>(r) * COLS);
-    const float4* pb = pa + (two ? COLS / 4 : 0);
-    float4 va[NV], vb[NV];
+  for (int r = rw; r < rend; r += R) {
+    float4 v[R][NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) va[i] = __ldcg(pa + i * 32 + lane);
+    for (int j = 0; j < R; ++j) {
+      const int rj = min(r + j, rend - 1);     // rows beyond the end repeat the last one (loaded, never stored)
+      const float4* pj = reinterpret_cast<const float4*>(h + static_cast<long long>(rj) * COLS);
 #pragma unroll
-    for (int i = 0; i < NV; ++i) vb[i] = __ldcg(pb + i * 32 + lane);
-    float sa = 0.f, sb = 0.f;
+      for (int i = 0; i < NV; ++i) v[j][i] = __ldcg(pj + i * 32 + lane);
+    }
+    float mean[R], rstd[R];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      sa += (va[i].x + va[i].y) + (va[i].z + va[i].w);
-      sb += (vb[i].x + vb[i].y) + (vb[i].z + vb[i].w);
-    }
-    for (int o = 16; o; o >>= 1) {
-      sa += __shfl_xor_sync(0xffffffffu, sa, o);
-      sb += __shfl_xor_sync(0xffffffffu, sb, o);
-    }
-    const float ma = sa * (1.0f / COLS), mb = sb * (1.0f / COLS);
-    float qa = 0.f, qb = 0.f;
+    for (int j = 0; j < R; ++j) {
+      float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      float a = va[i].x - ma, b = va[i].y - ma, c = va[i].z - ma, d = va[i].w - ma;
-      qa += (a * a + b * b) + (c * c + d * d);
-      a = vb[i].x - mb; b = vb[i].y - mb; c = vb[i].z - mb; d = vb[i].w - mb;
-      qb += (a * a + b * b) + (c * c + d * d);
+      for (int i = 0; i < NV; ++i) s += (v[j][i].x + v[j][i].y) + (v[j][i].z + v[j][i].w);
+      for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      mean[j] = s * (1.0f / COLS);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float a = v[j][i].x - mean[j], b = v[j][i].y - mean[j], c = v[j][i].z - mean[j], d = v[j][i].w - mean[j];
+        q += (a * a + b * b) + (c * c + d * d);
+      }
+      for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+      rstd[j] = rsqrtf(q * (1.0f / COLS) + p.row_ln_eps);
     }
-    for (int o = 16; o; o >>= 1) {
-      qa += __shfl_xor_sync(0xffffffffu, qa, o);
-      qb += __shfl_xor_sync(0xffffffffu, qb, o);
-    }
-    const float ra = rsqrtf(qa * (1.0f / COLS) + p.row_ln_eps), rb = rsqrtf(qb * (1.0f / COLS) + p.row_ln_eps);
-    uint2* oa = reinterpret_cast<uint2*>(p.row_ln_out + static_cast<long long>(r) * COLS);
-    uint2* ob = oa + COLS / 4;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int col = (i * 32 + lane) * 4;
       const float4 g = __ldg(reinterpret_cast<const float4*>(p.row_ln_gamma + col));
       const float4 e = __ldg(reinterpret_cast<const float4*>(p.row_ln_beta + col));
-      float y0 = fmaf((va[i].x - ma) * ra, g.x, e.x), y1 = fmaf((va[i].y - ma) * ra, g.y, e.y);
-      float y2 = fmaf((va[i].z - ma) * ra, g.z, e.z), y3 = fmaf((va[i].w - ma) * ra, g.w, e.w);
-      oa[i * 32 + lane] = make_uint2(pack_h16(y0, y1, p.fp16), pack_h16(y2, y3, p.fp16));
-      if (two) {
-        y0 = fmaf((vb[i].x - mb) * rb, g.x, e.x); y1 = fmaf((vb[i].y - mb) * rb, g.y, e.y);
-        y2 = fmaf((vb[i].z - mb) * rb, g.z, e.z); y3 = fmaf((vb[i].w - mb) * rb, g.w, e.w);
-        ob[i * 32 + lane] = make_uint2(pack_h16(y0, y1, p.fp16), pack_h16(y2, y3, p.fp16));
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        if (r + j < rend) {
+          const float y0 = fmaf((v[j][i].x - mean[j]) * rstd[j], g.x, e.x);
+          const float y1 = fmaf((v[j][i].y - mean[j]) * rstd[j], g.y, e.y);
+          const float y2 = fmaf((v[j][i].z - mean[j]) * rstd[j], g.z, e.z);
+          const float y3 = fmaf((v[j][i].w - mean[j]) * rstd[j], g.w, e.w);
+          reinterpret_cast<uint2*>(p.row_ln_out + static_cast<long long>(r + j) * COLS)[i * 32 + lane] =
+              make_uint2(pack_h16(y0, y1, p.fp16), pack_h16(y2, y3, p.fp16));
+        }
       }
     }
   }
@@ -177,7 +177,9 @@ __device__ __forceinline__ void tmem_ld_chunk<32>(uint32_t taddr, uint32_t (&r)[
 template <>
 __device__ __forceinline__ void tmem_ld_chunk<8>(uint32_t taddr, uint32_t (&r)[8]) { tmem_ld8(taddr, r); }
 
-template <int BN, bool LN, bool CTA2>
+// RL: the row-LayerNorm variant of the in-place residual update (row_ln_rows) — a kernel of its own, so that the
+// arrival / normalisation code costs the other launches of the family (QKV, FFN1, ...) neither registers nor spills
+template <int BN, bool LN, bool CTA2, bool RL = false>
 __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
                                           const GemmParams& p) {
   using C = GemmCfg<BN, CTA2, LN>;
@@ -377,6 +379,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
     // is made one tile LATE, when its reduce-add stores have long completed — the wait costs nothing then
     int row_ln_pend = -1;                    // counter index (m tile, CTA rank) of the tile whose arrival is pending
     auto row_ln_arrive = [&](int blk) {
+      if constexpr (!RL) return;
       int* flag = reinterpret_cast<int*>(smem + C::OFF_BAR + 192);
       named_bar_sync(2, EPI_THREADS);        // every warp's lane 0 has seen its stores of that tile complete
       if (threadIdx.x == 0) {
@@ -388,7 +391,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         *flag = last;
       }
       named_bar_sync(2, EPI_THREADS);
-      if (*flag) {                           // this CTA landed the block's last column tile: normalise its 128 rows
+      if (*flag && p.row_ln_eps >= 0.f) {    // this CTA landed the block's last column tile: normalise its 128 rows
         const int row0 = (blk / C::NPAIR) * TILE_M + (blk % C::NPAIR) * BLOCK_M;
         if (p.ldo == 1024) row_ln_rows<8>(p, row0, warp, lane);
         else row_ln_rows<6>(p, row0, warp, lane);
@@ -977,7 +980,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         acc_phase ^= 1;
       }
       }
-      if constexpr (!LN && CH == 32) {
+      if constexpr (RL) {
         if (p.row_ln_out != nullptr) {
           if (row_ln_pend >= 0) {
             // at most THIS tile's HALF_N / CH store groups are still pending: the previous tile's have completed
@@ -991,7 +994,7 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
         }
       }
     }
-    if constexpr (!LN && CH == 32) {
+    if constexpr (RL) {
       if (p.row_ln_out != nullptr && row_ln_pend >= 0) {
         if (lane == 0) {
           tma_store_wait_all<0>();
@@ -1013,26 +1016,26 @@ __device__ __forceinline__ void gemm_body(const CUtensorMap& tmA, const CUtensor
   }
 }
 
-template <int BN, bool LN>
+template <int BN, bool LN, bool RL = false>
 __global__ void __launch_bounds__((GemmCfg<BN, false, LN>::THREADS), (GemmCfg<BN, false, LN>::CTAS_PER_SM))
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                          const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
-  gemm_body<BN, LN, false>(tmA, tmB, tmC, p);
+  gemm_body<BN, LN, false, RL>(tmA, tmB, tmC, p);
 }
 
 // CTA-pair variant: cluster of 2, tcgen05.mma.cta_group::2 (M = 256), half of B per CTA
-template <int BN, bool LN>
+template <int BN, bool LN, bool RL = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((GemmCfg<BN, true, LN>::THREADS), 1)
 gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                               const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
-  gemm_body<BN, LN, true>(tmA, tmB, tmC, p);
+  gemm_body<BN, LN, true, RL>(tmA, tmB, tmC, p);
 }
 
-template <int BN, bool LN>
+template <int BN, bool LN, bool RL = false>
 static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
                             cudaStream_t st) {
   using C = GemmCfg<BN, true, LN>;
-  auto kern = gemm_bf16_tcgen05_2cta_kernel<BN, LN>;
+  auto kern = gemm_bf16_tcgen05_2cta_kernel<BN, LN, RL>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -1048,11 +1051,11 @@ static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const 
   return after_launch("gemm_bf16_tcgen05_2cta");
 }
 
-template <int BN, bool LN>
+template <int BN, bool LN, bool RL = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
                        cudaStream_t st) {
   using C = GemmCfg<BN, false, LN>;
-  auto kern = gemm_bf16_tcgen05_kernel<BN, LN>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, LN, RL>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -1164,7 +1167,7 @@ extern "C" int aptai_gemm_bf16(const aptai_gemm_args* g, void* stream) {
   p.l2_hint = red32 ? g->out_f32 : nullptr;
   p.row_ln_out = nullptr; p.row_ln_gamma = nullptr; p.row_ln_beta = nullptr; p.row_ln_cnt = nullptr; p.row_ln_eps = 0.f;
   if (g->row_ln_out != nullptr) {
-    APTAI_REQUIRE(red32 && bn % 64 == 0, "gemm: row_ln needs the in-place fp32 residual update (out_f32 == residual, "
+    APTAI_REQUIRE(red32 && bn == 256, "gemm: row_ln needs the in-place fp32 residual update (out_f32 == residual, "
                                           "no other output, no activation)");
     APTAI_REQUIRE(g->segs == 1 && g->ldo == g->N && (g->N == 1024 || g->N == 768),
                   "gemm: row_ln needs one segment of dense rows, N = 768 or 1024");
@@ -1203,6 +1206,8 @@ extern "C" int aptai_gemm_bf16(const aptai_gemm_args* g, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (ln2) return pair ? launch_gemm_2cta<256, true>(ta, tb, tc, p, st) : launch_gemm<256, true>(ta, tb, tc, p, st);
   if (g->ln) return pair ? launch_gemm_2cta<512, true>(ta, tb, tc, p, st) : launch_gemm<512, true>(ta, tb, tc, p, st);
+  if (p.row_ln_out != nullptr)
+    return pair ? launch_gemm_2cta<256, false, true>(ta, tb, tc, p, st) : launch_gemm<256, false, true>(ta, tb, tc, p, st);
   switch (bn) {
     case 256: return pair ? launch_gemm_2cta<256, false>(ta, tb, tc, p, st) : launch_gemm<256, false>(ta, tb, tc, p, st);
     case 128: return launch_gemm<128, false>(ta, tb, tc, p, st);

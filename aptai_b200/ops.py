@@ -344,8 +344,9 @@ class Serpentine:
 
 
 # 1: the LayerNorm behind out-proj / FFN2 of the pre-LN encoder runs inside those GEMM launches (linear(row_ln=...));
-# 0: standalone LayerNorm launches (A/B runs)
-FUSED_ROW_LN = int(os.environ.get("APTAI_FUSED_ROW_LN", "1"))
+# 0 (default): standalone LayerNorm launches.  Measured slower (bench 23.4 k -> 18.1 k audio-s/s, profiles/
+# row_ln_bench.py): the in-kernel normalisation starves behind the operand stream; kept as a tested experiment
+FUSED_ROW_LN = int(os.environ.get("APTAI_FUSED_ROW_LN", "0"))
 POSCONV_SLAB = int(os.environ.get("APTAI_POSCONV_SLAB", "1"))     # 0: always the generic implicit-GEMM path (A/B runs)
 
 # 0: by shape (attention_v3.cu's query-tile pairs with P in TMEM when an utterance has more than one 128-query tile,
