@@ -418,25 +418,46 @@ namespace aptai {
 // Tail of the APTAI / Wav2Vec2_PR forward in ONE kernel: (final LayerNorm of the pre-LN encoder: HF:792) -> both heads
 // (models/aptai.py:43-55: tv = W_tv tanh(h) + b, logits = W_phn leaky_relu(h) + b; w2v2_pr.py:58) -> argmax (first
 // maximum, aptai.py:105-106) -> log_softmax of the phoneme logits (the alignment stage's input).
-// CTA = 64 rows x 64 output slots (16 for head A, 48 for head B), 256 threads, thread tile 2 rows x 8 slots: per k one
-// 8-byte and two 16-byte shared loads feed 16 FMAs (the round-1 heads kernel fed 8 FMAs from 6 scalar loads and was
-// LDS-bound at 13 TFLOP/s).  Pass 0: warp per row, exact two-pass LayerNorm statistics in registers; the main loop
-// re-reads the rows (L2 hits: 256 KB per CTA) and normalises + activates them while staging the k-chunk.  fp32 FMA
-// throughout: N = 9 + 46 is too small for a tensor-core tile to pay, and the argmax parity needs fp32 logits.
-constexpr int TL_ROWS = 64, TL_KC = 32, TL_SLOTS = 64, TL_A = 16;
+// CTA = 128 rows x 64 output slots (16 for head A, 48 for head B), 256 threads, thread tile 4 rows x 8 slots: per k
+// three 16-byte shared loads (broadcast within the warp: one wavefront each) feed 32 FMAs, so the loop is bound by FMA
+// issue (the first version's 2 x 8 tile fed 16 FMAs from three loads and spent a third of its instructions in tanhf).
+// The next k-chunk's rows and weights are fetched into registers BEFORE the current chunk is multiplied, so their
+// latency hides behind 1024 FMAs per thread; tanh = 1 - 2 / (exp(2|x|) + 1) on the MUFU (ex2 + rcp: ~1e-7 absolute,
+// far inside the 2e-5 the heads are held to).  Pass 0: warp per row, exact two-pass LayerNorm statistics in registers;
+// the main loop re-reads the rows (L2 hits: 512 KB per CTA) and normalises + activates them while staging the k-chunk.
+// fp32 FMA throughout: N = 9 + 46 is too small for a tensor-core tile to pay, and the argmax parity needs fp32 logits.
+constexpr int TL_ROWS = 128, TL_KC = 32, TL_SLOTS = 64, TL_A = 16;
+constexpr int TL_RP = TL_ROWS + 4;     // row pitch of the staged activations (floats): 16-byte aligned k rows
+constexpr int TL_WP = TL_SLOTS + 4;
 
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ float tail_tanh(float x) {
+  const float ax = fminf(fabsf(x), 15.f);                 // tanh(15) == 1 in fp32; keeps exp finite
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(ax * 2.885390081777927f));      // exp(2|x|)
+  const float t = 1.f - __fdividef(2.f, e + 1.f);
+  return copysignf(t, x);
+}
+__device__ __forceinline__ float tail_act(float x, int act) {
+  if (act == 1) return tail_tanh(x);
+  if (act == 2) return x > 0.f ? x : 0.01f * x;
+  return x;
+}
+
+__global__ void __launch_bounds__(256, 3)
 tail_kernel(const float* __restrict__ h, long long rows, int H, const float* __restrict__ gamma,
             const float* __restrict__ beta, float eps, const float* __restrict__ wa, const float* __restrict__ ba,
             int na, int act_a, float* __restrict__ out_a, const float* __restrict__ wb, const float* __restrict__ bb,
             int nb, int act_b, float* __restrict__ out_b, long long* __restrict__ argmax_b, float* __restrict__ logp_b,
             float* __restrict__ h_norm) {
-  // pitches 66 / 68 words: the staging stores (8 lanes per row, k apart by 4) spread over banks instead of hitting one
-  __shared__ __align__(16) float hA[TL_KC][TL_ROWS + 2];  // [k][row]: a thread's two rows are one 8-byte load
-  __shared__ __align__(16) float hB[TL_KC][TL_ROWS + 2];
-  __shared__ __align__(16) float ws[TL_KC][TL_SLOTS + 4]; // [k][slot]: a thread's eight slots are two 16-byte loads
+  // [k][row] activations of both heads (a thread's four rows are one 16-byte load), [k][slot] weights (a thread's
+  // eight slots are two 16-byte loads); the result tile re-uses the activation buffers after the main loop
+  __shared__ __align__(16) float hbuf[2 * TL_KC * TL_RP];
+  __shared__ __align__(16) float ws[TL_KC][TL_WP];
   __shared__ float2 stat[TL_ROWS];                         // {mean, rstd}
-  __shared__ float res[TL_ROWS][TL_SLOTS + 1];
+  float (*hA)[TL_RP] = reinterpret_cast<float (*)[TL_RP]>(hbuf);
+  float (*hB)[TL_RP] = reinterpret_cast<float (*)[TL_RP]>(hbuf + TL_KC * TL_RP);
+  float (*res)[TL_SLOTS + 1] = reinterpret_cast<float (*)[TL_SLOTS + 1]>(hbuf);
+  static_assert(TL_ROWS * (TL_SLOTS + 1) <= 2 * TL_KC * TL_RP, "result tile must fit the activation buffers");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long row0 = static_cast<long long>(blockIdx.x) * TL_ROWS;
   const bool ln = gamma != nullptr;
@@ -478,60 +499,81 @@ tail_kernel(const float* __restrict__ h, long long rows, int H, const float* __r
   }
   __syncthreads();
   const int tx = tid & 7;            // slots tx*8 .. tx*8+7 (tx < 2: head A)
-  const int ty = tid >> 3;           // rows ty*2, ty*2+1
+  const int ty = tid >> 3;           // rows ty*4 .. ty*4+3
   const bool is_a = tx < TL_A / 8;
-  float acc[2][8];
+  // staging role: a warp covers 32 consecutive rows at one k4 (conflict-free transposed stores); four h quads and two
+  // weight quads per thread and chunk
+  const int sr = tid & (TL_ROWS - 1), sk = (tid >> 7) * 4;             // h: rows sr, k4 = sk + 8 * m
+  const int wsl = tid & (TL_SLOTS - 1), wk = (tid >> 6) * 4;           // w: slot wsl, k4 = wk + 16 * m
+  const long long srow = row0 + sr;
+  const float* wrow = nullptr;
+  if (wsl < TL_A) {
+    if (wsl < na) wrow = wa + static_cast<long long>(wsl) * H;
+  } else if (wsl - TL_A < nb) {
+    wrow = wb + static_cast<long long>(wsl - TL_A) * H;
+  }
+  float4 ph[4], pw[2];
+  auto fetch = [&](int k0) {
 #pragma unroll
-  for (int i = 0; i < 2; ++i)
+    for (int m = 0; m < 4; ++m) {
+      ph[m] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (srow < rows) ph[m] = __ldg(reinterpret_cast<const float4*>(h + srow * H + k0 + sk + 8 * m));
+    }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < H; k0 += TL_KC) {
-    // stage the k-chunk: 64 rows x 32 k of h (normalised, both activations) and 64 slots x 32 k of the weights
-    for (int i = tid; i < TL_ROWS * TL_KC / 4; i += 256) {
-      const int r = i / (TL_KC / 4), k4 = (i % (TL_KC / 4)) * 4;
-      const long long row = row0 + r;
-      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row < rows) x = __ldg(reinterpret_cast<const float4*>(h + row * H + k0 + k4));
-      float xv[4] = {x.x, x.y, x.z, x.w};
+    for (int m = 0; m < 2; ++m) {
+      pw[m] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (wrow != nullptr) pw[m] = __ldg(reinterpret_cast<const float4*>(wrow + k0 + wk + 16 * m));
+    }
+  };
+  auto stage = [&](int k0) {
+    const float2 st = stat[sr];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int k4 = sk + 8 * m;
+      float xv[4] = {ph[m].x, ph[m].y, ph[m].z, ph[m].w};
       if (ln) {
-        const float2 st = stat[r];
         const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + k0 + k4));
         const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + k0 + k4));
         const float gv[4] = {g4.x, g4.y, g4.z, g4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) xv[j] = fmaf((xv[j] - st.x) * st.y, gv[j], bv[j]);
-        if (h_norm != nullptr && row < rows)
-          *reinterpret_cast<float4*>(h_norm + row * H + k0 + k4) = make_float4(xv[0], xv[1], xv[2], xv[3]);
+        if (h_norm != nullptr && srow < rows)
+          *reinterpret_cast<float4*>(h_norm + srow * H + k0 + k4) = make_float4(xv[0], xv[1], xv[2], xv[3]);
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        hA[k4 + j][r] = head_act(xv[j], act_a);
-        hB[k4 + j][r] = head_act(xv[j], act_b);
+        hA[k4 + j][sr] = tail_act(xv[j], act_a);
+        hB[k4 + j][sr] = tail_act(xv[j], act_b);
       }
     }
-    for (int i = tid; i < TL_SLOTS * TL_KC / 4; i += 256) {
-      const int sl = i / (TL_KC / 4), k4 = (i % (TL_KC / 4)) * 4;
-      float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (sl < TL_A) {
-        if (sl < na) w4 = __ldg(reinterpret_cast<const float4*>(wa + static_cast<long long>(sl) * H + k0 + k4));
-      } else if (sl - TL_A < nb) {
-        w4 = __ldg(reinterpret_cast<const float4*>(wb + static_cast<long long>(sl - TL_A) * H + k0 + k4));
-      }
-      ws[k4][sl] = w4.x; ws[k4 + 1][sl] = w4.y; ws[k4 + 2][sl] = w4.z; ws[k4 + 3][sl] = w4.w;
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      const int k4 = wk + 16 * m;
+      ws[k4][wsl] = pw[m].x; ws[k4 + 1][wsl] = pw[m].y; ws[k4 + 2][wsl] = pw[m].z; ws[k4 + 3][wsl] = pw[m].w;
     }
+  };
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  fetch(0);
+  for (int k0 = 0; k0 < H; k0 += TL_KC) {
+    stage(k0);
     __syncthreads();
-    const float (*hs)[TL_ROWS + 2] = is_a ? hA : hB;
+    if (k0 + TL_KC < H) fetch(k0 + TL_KC);         // in flight under the 1024 FMAs below
+    const float (*hs)[TL_RP] = is_a ? hA : hB;
 #pragma unroll 8
     for (int k = 0; k < TL_KC; ++k) {
-      const float2 x = *reinterpret_cast<const float2*>(&hs[k][ty * 2]);
+      const float4 x = *reinterpret_cast<const float4*>(&hs[k][ty * 4]);
       const float4 w0 = *reinterpret_cast<const float4*>(&ws[k][tx * 8]);
       const float4 w1 = *reinterpret_cast<const float4*>(&ws[k][tx * 8 + 4]);
+      const float xr[4] = {x.x, x.y, x.z, x.w};
       const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc[0][j] = fmaf(x.x, wv[j], acc[0][j]);
-        acc[1][j] = fmaf(x.y, wv[j], acc[1][j]);
-      }
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(xr[i], wv[j], acc[i][j]);
     }
     __syncthreads();
   }
@@ -544,8 +586,8 @@ tail_kernel(const float* __restrict__ h, long long rows, int H, const float* __r
     } else if (sl - TL_A < nb) {
       bv = bb[sl - TL_A];
     }
-    res[ty * 2][sl] = acc[0][j] + bv;
-    res[ty * 2 + 1][sl] = acc[1][j] + bv;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) res[ty * 4 + i][sl] = acc[i][j] + bv;
   }
   __syncthreads();
   for (int i = tid; i < TL_ROWS * TL_SLOTS; i += 256) {

@@ -480,7 +480,8 @@ def test_frame_lengths_kernel(cuda):
     assert [cfg.conv_out_length(int(v)) for v in n[:5]] == o64[:5].tolist()
 
 
-@pytest.mark.parametrize("rows,H,with_ln", [(150, 1024, True), (64, 768, True), (1000, 1024, False), (1, 1024, True)])
+@pytest.mark.parametrize("rows,H,with_ln", [(150, 1024, True), (64, 768, True), (1000, 1024, False), (1, 1024, True),
+                                            (5000, 1024, True), (129, 768, False)])
 def test_fused_tail(cuda, rows, H, with_ln):
     """One-launch tail (final LayerNorm + both heads + argmax + log-softmax) against the separate kernels it
     replaces and against torch: fp32 throughout, so logits agree to accumulation-order noise and the argmax /
