@@ -419,8 +419,8 @@ namespace aptai {
 // (models/aptai.py:43-55: tv = W_tv tanh(h) + b, logits = W_phn leaky_relu(h) + b; w2v2_pr.py:58) -> argmax (first
 // maximum, aptai.py:105-106) -> log_softmax of the phoneme logits (the alignment stage's input).
 // CTA = 128 rows x 64 output slots (16 for head A, 48 for head B), 256 threads, thread tile 4 rows x 8 slots: per k
-// three 16-byte shared loads (broadcast within the warp: one wavefront each) feed 32 FMAs, so the loop is bound by FMA
-// issue (the first version's 2 x 8 tile fed 16 FMAs from three loads and spent a third of its instructions in tanhf).
+// three 16-byte shared loads feed 32 FMAs (the first version's 2 x 8 tile fed 16 FMAs from three loads and spent a third
+// of its instructions in tanhf); the loop is bound by shared-memory wavefronts, see the lane mapping below.
 // The next k-chunk's rows and weights are fetched into registers BEFORE the current chunk is multiplied, so their
 // latency hides behind 1024 FMAs per thread; tanh = 1 - 2 / (exp(2|x|) + 1) on the MUFU (ex2 + rcp: ~1e-7 absolute,
 // far inside the 2e-5 the heads are held to).  Pass 0: warp per row, exact two-pass LayerNorm statistics in registers;
@@ -443,7 +443,7 @@ __device__ __forceinline__ float tail_act(float x, int act) {
   return x;
 }
 
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256)
 tail_kernel(const float* __restrict__ h, long long rows, int H, const float* __restrict__ gamma,
             const float* __restrict__ beta, float eps, const float* __restrict__ wa, const float* __restrict__ ba,
             int na, int act_a, float* __restrict__ out_a, const float* __restrict__ wb, const float* __restrict__ bb,
@@ -498,8 +498,12 @@ tail_kernel(const float* __restrict__ h, long long rows, int H, const float* __r
     stat[tid] = make_float2(0.f, 1.f);
   }
   __syncthreads();
-  const int tx = tid & 7;            // slots tx*8 .. tx*8+7 (tx < 2: head A)
-  const int ty = tid >> 3;           // rows ty*4 .. ty*4+3
+  // A 16-byte shared load is served one quarter-warp (8 lanes) at a time: the 8 lanes of a quarter own 8 DIFFERENT
+  // row groups (their x loads cover 128 contiguous bytes: one wavefront) and the SAME slot group (their weight loads
+  // are one broadcast wavefront each) — 12 wavefronts per 32 FMAs; with tid = ty * 8 + tx the weight loads of a
+  // quarter hit every bank twice and a k-step cost 20 (measured: 6.5 wavefronts per load, LSU pipe 73 % busy)
+  const int tx = (lane >> 3) + 4 * (warp & 1);        // slots tx*8 .. tx*8+7 (tx < 2: head A)
+  const int ty = (warp >> 1) * 8 + (lane & 7);        // rows ty*4 .. ty*4+3
   const bool is_a = tx < TL_A / 8;
   // staging role: a warp covers 32 consecutive rows at one k4 (conflict-free transposed stores); four h quads and two
   // weight quads per thread and chunk
