@@ -81,12 +81,47 @@ def _close(cfg, idx, lengths) -> Batch:
     return Batch(list(idx), L, cfg.conv_out_length(L), sum(flops_utt(cfg, lengths[i]) for i in idx))
 
 
-def shard_lpt(batches: Sequence[Batch], world: int) -> List[List[Batch]]:
-    """Longest-processing-time-first assignment of batches to ranks."""
+def shard_lpt(batches: Sequence[Batch], world: int, cfg: W2V2Config = None, lengths: Sequence[int] = None,
+              tol: float = 0.003) -> List[List[Batch]]:
+    """Longest-processing-time-first assignment of batches to ranks.
+
+    With `cfg` and `lengths` the assignment is refined: whole batches leave an imbalance of a few percent once there
+    are only 4-5 of them per rank (36 batches over 8 ranks: 1.024 max / mean), so the most loaded rank hands the tail
+    of one of its batches — utterances of the same length bucket: no extra padding — to the least loaded rank as a
+    batch of its own, until max / mean <= 1 + tol.  Every utterance stays in exactly one batch of exactly one rank."""
     loads = [0.0] * world
     out: List[List[Batch]] = [[] for _ in range(world)]
     for b in sorted(batches, key=lambda b: -b.flops):
         r = min(range(world), key=lambda r: loads[r])
         out[r].append(b)
         loads[r] += b.flops
+    if cfg is None or lengths is None or world < 2:
+        return out
+    for _ in range(4 * world):
+        mean = sum(loads) / world
+        hi = max(range(world), key=lambda r: loads[r])
+        lo = min(range(world), key=lambda r: loads[r])
+        if mean <= 0 or loads[hi] <= (1.0 + tol) * mean:
+            break
+        want = 0.5 * (loads[hi] - loads[lo])
+        # the batch of the loaded rank whose utterances are cheapest: the finest granularity for the hand-over
+        src = min((b for b in out[hi] if len(b.indices) > 1), key=lambda b: b.flops / len(b.indices), default=None)
+        if src is None:
+            break
+        moved, got = [], 0.0
+        while len(src.indices) - len(moved) > 1:
+            f = flops_utt(cfg, lengths[src.indices[-1 - len(moved)]])
+            if got + f > want and moved:
+                break
+            moved.append(src.indices[-1 - len(moved)])
+            got += f
+            if got >= want:
+                break
+        if not moved:
+            break
+        keep = src.indices[: len(src.indices) - len(moved)]
+        out[hi][out[hi].index(src)] = _close(cfg, keep, lengths)
+        out[lo].append(_close(cfg, list(reversed(moved)), lengths))
+        loads[hi] -= got
+        loads[lo] += got
     return out

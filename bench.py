@@ -422,7 +422,7 @@ def run_ours(args):
     strong = None
     if world > 1:
         l0, b0 = build_workload(cfg, args.utterances, seed=0, max_rows=args.max_rows)
-        shards = sweep.shard_lpt(b0, world)
+        shards = sweep.shard_lpt(b0, world, cfg, l0)
         mine = shards[rank]
         hs = [synth_batch_host(l0, b, 1000 * 0 + 100000 + i, pin=False) for i, b in enumerate(mine)]
         ds = [tuple(t.to(dev) for t in h) for h in hs]
@@ -434,7 +434,8 @@ def run_ours(args):
         strong = {"value": sum(l0) / 16000.0 * args.steps / (ms_s_max * 1e-3), "unit": "audio-s/s",
                   "ms_per_step": ms_s_max / args.steps, "scaling": "strong",
                   "workload": f"one set of {args.utterances} utterances (seed 0) split over {world} ranks by "
-                              "sweep.shard_lpt on the forward-FLOP estimate, no collective",
+                              "sweep.shard_lpt on the forward-FLOP estimate (whole batches, then the tail of one batch handed "
+                              "from the most to the least loaded rank until max/mean <= 1.003), no collective",
                   "flops_imbalance_max_over_mean": max(loads) / (sum(loads) / world),
                   "time_imbalance_max_over_this_rank0": ms_s_max / ms_s if rank == 0 else None}
         del ds

@@ -81,6 +81,18 @@ def test_bucketing_and_lpt_sharding():
     loads = [sum(b.flops for b in s) for s in shards]
     assert max(loads) / min(loads) < 1.10   # 50 coarse batches over 8 ranks
     assert sorted(i for s in shards for b in s for i in b.indices) == list(range(4096))
+    # refined assignment (tails of batches handed from the most to the least loaded rank): still a partition, every
+    # batch still inside its length bucket and row budget, max / mean within 0.5 %
+    for world in (2, 4, 8):
+        fine = sweep.shard_lpt(batches, world, cfg, lengths)
+        assert sorted(i for s in fine for b in s for i in b.indices) == list(range(4096))
+        fl = [sum(b.flops for b in s) for s in fine]
+        assert max(fl) / (sum(fl) / world) <= 1.005, (world, fl)
+        for s in fine:
+            for b in s:
+                Ts = [cfg.conv_out_length(lengths[i]) for i in b.indices]
+                assert max(Ts) - min(Ts) <= 32 and len(b.indices) * b.frames <= 49152 and b.frames == max(Ts)
+                assert abs(b.flops - sum(sweep.flops_utt(cfg, lengths[i]) for i in b.indices)) <= 1e-6 * b.flops
     # closed-form FLOPs: large, 8 s -> 303.06 GFLOP
     assert abs(sweep.flops_utt(cfg, 128000) / 1e9 - 303.06) < 0.5
 
