@@ -13,7 +13,9 @@ Design (B200-first):
 """
 from __future__ import annotations
 
+import bisect
 import ctypes as C
+import weakref
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
 import torch
@@ -30,8 +32,15 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+_BUFFERS: Dict[int, "weakref.ReferenceType"] = {}      # flat storage pointer -> GradBuffer (FusedAdam finds pending waits)
+
+
 class GradBuffer:
-    """Flat fp32 gradient storage; `p.grad` of every registered parameter is a view into it."""
+    """Flat fp32 gradient storage; `p.grad` of every registered parameter is a view into it.
+
+    `pending`: all-reduces of regions of the buffer that have been LAUNCHED but not yet waited for
+    (`GradReducer(defer_wait=True)`): a list of (wait, lo, hi) in launch order.  `FusedAdam.step()` consumes it region
+    by region; anything else that reads `.grad` first calls `wait_pending()`."""
 
     def __init__(self, named_params: Sequence[Tuple[str, torch.nn.Parameter]],
                  fused_groups: Sequence[Sequence[str]] = ()):
@@ -64,6 +73,8 @@ class GradBuffer:
             off += p.numel()
         self.numel = (off + _ALIGN - 1) // _ALIGN * _ALIGN
         self.flat = torch.zeros((self.numel,), dtype=F32, device=dev)
+        self.pending: List[Tuple] = []
+        _BUFFERS[self.flat.untyped_storage().data_ptr()] = weakref.ref(self)
         self.params = [(n, by_name[n]) for n in order]
         for n, p in self.params:
             if p.dtype != F32:
@@ -81,7 +92,14 @@ class GradBuffer:
         off, tot = self._fused[tuple(names)]
         return self.flat[off: off + tot].view(shape)
 
+    def wait_pending(self) -> None:
+        """Make the current stream wait for every launched-but-unawaited all-reduce of this buffer."""
+        pend, self.pending = self.pending, []
+        for wait, _, _ in pend:
+            wait()
+
     def zero(self) -> None:
+        self.wait_pending()
         self.flat.zero_()
 
     def owns(self, p: torch.nn.Parameter) -> bool:
@@ -114,8 +132,15 @@ class GradReducer:
     kernels keep the SMs busy); `finish()` reduces what is left (heads, positional conv, projection, norms) and
     makes the compute stream wait for all of it.  Averaging uses NCCL's AVG reduction (SUM + divide elsewhere)."""
 
-    def __init__(self, gb: GradBuffer, layer_prefix: str, n_layers: int, layers_per_bucket: int = 4, group=None):
+    def __init__(self, gb: GradBuffer, layer_prefix: str, n_layers: int, layers_per_bucket: int = 4, group=None,
+                 defer_wait: bool = False):
+        """`defer_wait`: `finish()` launches the last reductions but leaves the waiting to the consumer of the
+        gradients (`gb.pending`): `FusedAdam.step()` then updates each region as soon as ITS all-reduce has landed, so
+        the optimizer runs under the reductions that are still in flight instead of behind the last one.  Anything
+        else that reads `.grad` between backward and step must call `gb.wait_pending()` (the reference's training
+        loops read nothing there: train/train_aptai.py:431-443)."""
         self.gb, self.group, self.k = gb, group, max(1, layers_per_bucket)
+        self.defer_wait = defer_wait
         self.n_layers = n_layers
         spans = []
         for i in range(n_layers):
@@ -135,10 +160,15 @@ class GradReducer:
         chunk = self.gb.flat[lo:hi]
         world = dist.get_world_size(self.group)
         if dist.get_backend(self.group) == "nccl":
-            self.works.append(dist.all_reduce(chunk, op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+            w = dist.all_reduce(chunk, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
+            self.works.append((w.wait, lo, hi))
         else:
             w = dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-            self.works.append((w, chunk, world))
+
+            def wait(w=w, chunk=chunk, world=world):
+                w.wait()
+                chunk.div_(world)
+            self.works.append((wait, lo, hi))
 
     def layer_done(self, i: int) -> None:
         """Called by the backward after layer i's gradients are complete (layers arrive in decreasing order)."""
@@ -150,14 +180,11 @@ class GradReducer:
     def finish(self) -> None:
         self._launch(0, self.spans[0][0])
         self._launch(self.spans[-1][1], self.gb.numel)
-        for w in self.works:
-            if isinstance(w, tuple):
-                w[0].wait()
-                w[1].div_(w[2])
-            else:
-                w.wait()
+        self.gb.pending.extend(self.works)
         self.works = []
         self._done = [False] * self.n_layers
+        if not self.defer_wait:
+            self.gb.wait_pending()
 
 
 def broadcast_parameters(module: torch.nn.Module, src: int = 0, group=None) -> None:
@@ -232,15 +259,30 @@ class FusedAdam(torch.optim.Optimizer):
                 raise RuntimeError("FusedAdam: gradients must be contiguous fp32 views of ONE flat buffer "
                                    "(model.grad_buffer() / GradBuffer)")
         self._gbase = st
-        self._goffs = torch.tensor([(g.data_ptr() - st) // 4 for g in grads], dtype=torch.int64,
-                                   device=self._params[0].device)
+        goffs = [(g.data_ptr() - st) // 4 for g in grads]
+        dev = self._params[0].device
+        self._goffs = torch.tensor(goffs, dtype=torch.int64, device=dev)
+        # chunk table in the order of the flat gradient buffer: a region [lo, hi) of it (one all-reduce bucket) is
+        # then a contiguous range of chunks, found by bisection on the chunks' gradient offsets
+        chunks = sorted(((i, s) for i, p in enumerate(self._params) for s in range(0, p.numel(), self.CHUNK)),
+                        key=lambda c: goffs[c[0]] + c[1])
+        self._chunk_goff = [goffs[i] + s for i, s in chunks]
+        self._chunks = torch.tensor(chunks, dtype=torch.int64).reshape(-1, 2).to(dev)
+        self._n_chunks = len(chunks)
         self._bound = key
         return True
+
+    def _grad_buffer(self) -> Optional[GradBuffer]:
+        ref = _BUFFERS.get(self._gbase)
+        return ref() if ref is not None else None
 
     def zero_grad(self, set_to_none: bool = False) -> None:     # keep the views, clear the storage
         for p in self._params:
             if p.grad is not None:
                 if self._bind():
+                    gb = self._grad_buffer()
+                    if gb is not None:
+                        gb.wait_pending()
                     g0 = self._params[0].grad
                     # one memset over the whole flat buffer instead of one per tensor
                     torch.empty(0, dtype=F32, device=g0.device).set_(g0.untyped_storage()).zero_()
@@ -253,12 +295,38 @@ class FusedAdam(torch.optim.Optimizer):
             return loss
         g = self.param_groups[0]
         self._step += 1
-        check(_lib.load().aptai_adam_step(self._ptrs.data_ptr(), self._goffs.data_ptr(), self._soffs.data_ptr(),
-                                          self._nums.data_ptr(), self._chunks.data_ptr(), self._n_chunks, self.CHUNK,
-                                          self._gbase, self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
-                                          float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
-                                          float(g["weight_decay"]), self._step, float(self.grad_scale), _stream()),
-              "adam_step")
+
+        def launch(c0: int, c1: int) -> None:
+            if c1 <= c0:
+                return
+            check(_lib.load().aptai_adam_step(self._ptrs.data_ptr(), self._goffs.data_ptr(), self._soffs.data_ptr(),
+                                              self._nums.data_ptr(), self._chunks.data_ptr() + 16 * c0, c1 - c0, self.CHUNK,
+                                              self._gbase, self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                                              float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]),
+                                              float(g["eps"]), float(g["weight_decay"]), self._step,
+                                              float(self.grad_scale), _stream()), "adam_step")
+
+        gb = self._grad_buffer()
+        pend = []
+        if gb is not None and gb.pending:
+            pend, gb.pending = gb.pending, []
+        if not pend:
+            launch(0, self._n_chunks)
+        else:
+            # data parallel with deferred waits: update every all-reduce region as soon as its reduction has landed
+            # (the regions were launched last-layers-first), under the reductions still in flight
+            done = []
+            for wait, lo, hi in pend:
+                wait()
+                c0, c1 = bisect.bisect_left(self._chunk_goff, lo), bisect.bisect_left(self._chunk_goff, hi)
+                launch(c0, c1)
+                done.append((c0, c1))
+            done.sort()
+            at = 0
+            for c0, c1 in done:                  # anything no region covered (none with GradReducer's buckets)
+                launch(at, c0)
+                at = max(at, c1)
+            launch(at, self._n_chunks)
         # the kernel wrote through raw pointers: tell autograd / the kernel-weight cache that the values changed
         torch.autograd.graph.increment_version(self._params)
         return loss

@@ -125,14 +125,17 @@ class Wav2Vec2_PR(nn.Module):
                                  f(self.pr_head.bias), ops.ACT_NONE, want_argmax=False)
         return logits.view(B, T, -1)
 
-    def enable_data_parallel(self, group=None, layers_per_bucket: int = 4, broadcast: bool = True):
+    def enable_data_parallel(self, group=None, layers_per_bucket: int = 4, broadcast: bool = True,
+                             overlap_optimizer: bool = False):
         """Data-parallel training over `torch.distributed` (one process per GPU): weights are broadcast from rank 0
         and every backward all-reduces (averages) the flat gradient buffer, bucketed by encoder layers and
-        overlapped with the remaining backward kernels (BASELINE config 4; the reference trains single-GPU)."""
+        overlapped with the remaining backward kernels (BASELINE config 4; the reference trains single-GPU).
+        `overlap_optimizer`: see `APTAI.enable_data_parallel`."""
         if broadcast:
             broadcast_parameters(self, 0, group)
         gb = self.grad_buffer()
-        red = GradReducer(gb, "wav2vec2.encoder.layers.", len(self.wav2vec2.encoder.layers), layers_per_bucket, group)
+        red = GradReducer(gb, "wav2vec2.encoder.layers.", len(self.wav2vec2.encoder.layers), layers_per_bucket, group,
+                          defer_wait=overlap_optimizer)
         object.__setattr__(self, "_reducer", red)
         return red
 

@@ -691,6 +691,7 @@ def train_leg(cfg, dev, rank, world, args):
         object.__setattr__(model, "_reducer", red)
         opt.zero_grad()
         model(*mine)["loss"].backward()
+        gb.wait_pending()                                   # the reducer leaves the last waits to the optimizer
         torch.cuda.synchronize()
         err = torch.tensor([float((gb.flat - ref).norm() / ref.norm())], dtype=torch.float64, device=dev)
         dist.all_reduce(err, op=dist.ReduceOp.MAX)

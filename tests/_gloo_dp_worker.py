@@ -64,6 +64,25 @@ red.finish()
 expect = sum(range(1, world + 1)) / world
 for n, p in gb.params:
     assert torch.allclose(p.grad, torch.full_like(p.grad, expect)), n
+# deferred waits (the optimizer-overlap mode): finish() returns with the reductions registered as pending regions that
+# cover every parameter exactly once, in launch order (last layers first); wait_pending() completes them
+red2 = GradReducer(gb, "layers.", 6, layers_per_bucket=4, defer_wait=True)
+for n, p in gb.params:
+    p.grad.fill_(float(rank + 1))
+for i in range(5, -1, -1):
+    red2.layer_done(i)
+red2.finish()
+assert len(gb.pending) == 4, len(gb.pending)          # layers 4-5, layers 0-3, the head of the buffer, its tail
+covered = sorted((lo, hi) for _, lo, hi in gb.pending)
+assert covered[0][0] == 0 and covered[-1][1] == gb.numel and all(a[1] <= b[0] for a, b in zip(covered, covered[1:]))
+for n, p in gb.params:
+    lo = gb.offsets[n]
+    assert any(a <= lo and lo + p.numel() <= b for a, b in covered), n      # whole tensors per region
+assert gb.pending[0][1] == red2.spans[4][0]           # the last layers' bucket was launched first
+gb.wait_pending()
+assert gb.pending == []
+for n, p in gb.params:
+    assert torch.allclose(p.grad, torch.full_like(p.grad, expect)), n
 # the plain (non-overlapped) reduction gives the same result
 for n, p in gb.params:
     p.grad.fill_(float(rank + 1))

@@ -68,6 +68,37 @@ opt.step()
 dist.all_gather(gathered, probe.detach())
 assert all(torch.equal(g, gathered[0]) for g in gathered), "weights diverged after the data-parallel step"
 
+# ---- optimizer overlap: the reducer leaves the last waits to FusedAdam, which updates each all-reduce region as soon as
+# its reduction has landed.  Same batches, same starting weights and moments -> bit-identical weights after the step.
+import copy  # noqa: E402
+
+state0 = copy.deepcopy(m.state_dict())
+adam0 = copy.deepcopy(opt.state_dict())
+
+
+def one_step(overlap):
+    m.load_state_dict(state0)
+    opt.load_state_dict(copy.deepcopy(adam0))
+    m.enable_data_parallel(layers_per_bucket=4, broadcast=False, overlap_optimizer=overlap)
+    opt.zero_grad()
+    m(*batch(rank))["loss"].backward()
+    if overlap:
+        assert len(m.grad_buffer().pending) >= 3, "deferred mode must leave the reductions pending"
+    opt.step()
+    assert m.grad_buffer().pending == []
+    torch.cuda.synchronize()
+    return [p.detach().clone() for p in m.parameters()]
+
+
+w_plain = one_step(False)
+w_over = one_step(True)
+# the backward's fp32 atomics make two runs differ at the 1e-7 level; a region updated BEFORE its all-reduce landed
+# (or twice, or not at all) would differ by the whole Adam step (lr 1e-4)
+worst = max(float((a - b).abs().max()) for a, b in zip(w_plain, w_over))
+assert worst < 2e-6, f"rank {rank}: optimizer-overlap step differs from the plain data-parallel step ({worst:.2e})"
+dist.all_gather(gathered, probe.detach())
+assert all(torch.equal(g, gathered[0]) for g in gathered), "weights diverged after the overlapped step"
+
 # ---- Force_APTAI: the tail's flat gradient buffer is averaged by one all-reduce at the end of the backward
 from aptai_b200 import Force_APTAI, Wav2Vec2_PR  # noqa: E402
 
@@ -112,5 +143,6 @@ dist.all_gather(fg, fprobe.detach())
 assert all(torch.equal(g, fg[0]) for g in fg), "Force_APTAI weights diverged after the data-parallel step"
 dist.barrier()
 if rank == 0:
-    print(f"NCCL_DP_OK world={world} grad_rel_err={err:.2e} force_grad_rel_err={ferr:.2e}")
+    print(f"NCCL_DP_OK world={world} grad_rel_err={err:.2e} overlap_step_max_abs_diff={worst:.2e} "
+          f"force_grad_rel_err={ferr:.2e}")
 dist.destroy_process_group()
