@@ -207,3 +207,37 @@ def test_fused_adam_matches_torch(cuda):
         ropt.step()
     for p, r in zip(ps, ref):
         torch.testing.assert_close(p.detach(), r.detach(), atol=1e-6, rtol=1e-5)
+
+
+def test_fused_adam_consumes_pending_regions(cuda):
+    """Optimizer overlap on ONE GPU: all-reduce regions registered as pending on the gradient buffer (here with
+    recording no-op waits, in last-region-first order and with one tensor left uncovered) are updated region by region
+    — every parameter exactly once, each region only after ITS wait — and the result equals torch.optim.Adam."""
+    from aptai_b200.train import FusedAdam, GradBuffer
+    shapes = [(1024, 1024), (1024,), (46, 1024), (3,), (200000,), (64, 64)]
+    ps = [torch.nn.Parameter(_rand(s, cuda, 1.0, i)) for i, s in enumerate(shapes)]
+    ref = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    gb = GradBuffer([(f"p{i}", p) for i, p in enumerate(ps)])
+    opt = FusedAdam(ps, lr=1e-3, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.0)
+    ropt = torch.optim.Adam(ref, lr=1e-3, betas=(0.9, 0.98), eps=1e-8)
+    o = gb.offsets
+    regions = [(o["p4"], o["p5"]), (o["p2"], o["p4"]), (0, o["p2"])]        # p5 is covered by no region
+    for step in range(3):
+        for i, (p, r) in enumerate(zip(ps, ref)):
+            gr = _rand(p.shape, cuda, 0.1, 100 * step + i)
+            p.grad.copy_(gr)
+            r.grad = gr.clone()
+        calls = []
+        before = [p.detach().clone() for p in ps]
+        gb.pending = [((lambda k=k: calls.append(k)), lo, hi) for k, (lo, hi) in enumerate(regions)]
+        opt.step()
+        ropt.step()
+        assert calls == [0, 1, 2] and gb.pending == []
+        assert all(not torch.equal(b, p.detach()) for b, p in zip(before, ps))     # every tensor moved (p5 too)
+    for p, r in zip(ps, ref):
+        torch.testing.assert_close(p.detach(), r.detach(), atol=1e-6, rtol=1e-5)
+    # wait_pending() / zero_grad() complete what is left without an optimizer step
+    calls = []
+    gb.pending = [((lambda: calls.append("w")), 0, gb.numel)]
+    opt.zero_grad()
+    assert calls == ["w"] and gb.pending == [] and float(gb.flat.abs().sum()) == 0.0
