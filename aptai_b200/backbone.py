@@ -579,9 +579,15 @@ class Wav2Vec2Backbone(nn.Module):
         if len(sv.layers) in d_hidden:
             d_last = d_last + d_hidden.pop(len(sv.layers))
 
-        def lin_grads(dy_b, x_b, name):
+        def lin_grads(dy_b, x_b, name, bias_done=False):
             ops.wgrad(dy_b, x_b, G(name + ".weight"))
-            ops.colsum(dy_b, G(name + ".bias"))
+            if not bias_done:
+                ops.colsum(dy_b, G(name + ".bias"))
+
+        # Without hidden dropout the gradient of out-proj's / FFN2's OUTPUT is the residual-stream gradient a LayerNorm
+        # backward has just produced: that kernel accumulates its column sums (the bias gradient) on the way out
+        # (`dcolsum`), which saves the colsum launch that would re-read the tensor.
+        fuse_bias = p_h == 0 and bool(ops.FUSED_BIAS_COLSUM)
 
         def masked16(d32, d16, li, site):
             """bf16 gradient w.r.t. the input of a hidden-dropout site (same mask as the forward)."""
@@ -589,20 +595,20 @@ class Wav2Vec2Backbone(nn.Module):
                 return ops.dropout(d32, p_h, seed(li, site), want_bf16=True)[1]
             return d16
 
-        def ffn_block(i, s, lt, dy_b, x_in_b):
+        def ffn_block(i, s, lt, dy_b, x_in_b, bias_done=False):
             """FFN2 wgrad/dgrad (through activation dropout and the GELU) and FFN1 wgrad; returns du (bf16)."""
             base = f"encoder.layers.{i}.feed_forward."
-            lin_grads(dy_b, s.g, base + "output_dense")
+            lin_grads(dy_b, s.g, base + "output_dense", bias_done)
             _, du = ops.linear(dy_b, lt.ff2_wt, None, act=2, aux=s.u)
             if p_a > 0:
                 ops.dropout(du, p_a, seed(i, self.SITE_ACT), out_bf16=du)
             lin_grads(du, x_in_b, base + "intermediate_dense")
             return du
 
-        def attn_block(i, s, lt, dctx_src_b, x_in_b):
+        def attn_block(i, s, lt, dctx_src_b, x_in_b, bias_done=False):
             """out-proj dgrad -> attention backward -> fused QKV wgrad; returns dqkv."""
             base = f"encoder.layers.{i}.attention."
-            lin_grads(dctx_src_b, s.ctx, base + "out_proj")
+            lin_grads(dctx_src_b, s.ctx, base + "out_proj", bias_done)
             _, dctx = ops.linear(dctx_src_b, lt.o_wt, None)
             dqkv = ops.attention_bwd(s.qkv, s.ctx, dctx, s.lse, flen, B, T, heads, q_scale, drop_p=sv.p_at,
                                      drop_seed=seed(i, self.SITE_ATTN_P))
@@ -614,23 +620,34 @@ class Wav2Vec2Backbone(nn.Module):
 
         nl = len(sv.layers)
         if cfg.do_stable_layer_norm:
+            ff2_b = lambda j: G(f"encoder.layers.{j}.feed_forward.output_dense.bias")
+            # the LayerNorm backward that produces layer j's incoming residual gradient also sums its columns when
+            # layer j is the next one to run and nothing is added to the gradient in between
+            feeds = lambda j: fuse_bias and j >= 0 and sv.layers[j] is not None and (j + 1) not in d_hidden
+            ff2_done = feeds(nl - 1)
             dh32, dhb = ops.layernorm_bwd(d_last, sv.h_final_in, P.enc_ln_w, eps, dgamma=G("encoder.layer_norm.weight"),
-                                          dbeta=G("encoder.layer_norm.bias"), want_bf16=True)
+                                          dbeta=G("encoder.layer_norm.bias"), want_bf16=True,
+                                          dcolsum=ff2_b(nl - 1) if ff2_done else None)
             for i in range(nl - 1, -1, -1):
                 s, lw, lt = sv.layers[i], P.layers[i], TP.layers[i]
                 if s is not None:            # None: the layer was dropped by LayerDrop (identity)
                     base = f"encoder.layers.{i}."
-                    du = ffn_block(i, s, lt, masked16(dh32, dhb, i, self.SITE_FFN), s.x2)
+                    du = ffn_block(i, s, lt, masked16(dh32, dhb, i, self.SITE_FFN), s.x2, bias_done=ff2_done)
                     dx2, _ = ops.linear(du, lt.ff1_wt, None, want_f32=True, want_bf16=False)
                     dhm32, dhmb = ops.layernorm_bwd(dx2, s.h_mid, lw.ln2_w, eps, dres=dh32,
                                                     dgamma=G(base + "final_layer_norm.weight"),
-                                                    dbeta=G(base + "final_layer_norm.bias"), want_bf16=True)
-                    dqkv = attn_block(i, s, lt, masked16(dhm32, dhmb, i, self.SITE_ATTN), s.x1)
+                                                    dbeta=G(base + "final_layer_norm.bias"), want_bf16=True,
+                                                    dcolsum=G(base + "attention.out_proj.bias") if fuse_bias else None)
+                    dqkv = attn_block(i, s, lt, masked16(dhm32, dhmb, i, self.SITE_ATTN), s.x1, bias_done=fuse_bias)
                     dx1, _ = ops.linear(dqkv, lt.qkv_wt, None, want_f32=True, want_bf16=False)
+                    ff2_done = feeds(i - 1) and i not in d_hidden
                     dh32, dhb = ops.layernorm_bwd(dx1, s.h_in, lw.ln1_w, eps, dres=dhm32,
                                                   dgamma=G(base + "layer_norm.weight"),
-                                                  dbeta=G(base + "layer_norm.bias"), want_bf16=True)
+                                                  dbeta=G(base + "layer_norm.bias"), want_bf16=True,
+                                                  dcolsum=ff2_b(i - 1) if ff2_done else None)
                     sv.layers[i] = None
+                else:
+                    ff2_done = False         # a dropped layer passes the gradient on: the next FFN2 sums it itself
                 if i in d_hidden:             # hidden_states[i] = the residual stream entering layer i
                     dh32 = dh32 + d_hidden[i]
                     dhb = ops.scale_cast_bf16(dh32)
@@ -647,12 +664,14 @@ class Wav2Vec2Backbone(nn.Module):
                 if s is not None:
                     base = f"encoder.layers.{i}."
                     dt2, dt2b = ops.layernorm_bwd(dh32, s.t2, lw.ln2_w, eps, dgamma=G(base + "final_layer_norm.weight"),
-                                                  dbeta=G(base + "final_layer_norm.bias"), want_bf16=True)
-                    du = ffn_block(i, s, lt, masked16(dt2, dt2b, i, self.SITE_FFN), s.x1)
+                                                  dbeta=G(base + "final_layer_norm.bias"), want_bf16=True,
+                                                  dcolsum=G(base + "feed_forward.output_dense.bias") if fuse_bias else None)
+                    du = ffn_block(i, s, lt, masked16(dt2, dt2b, i, self.SITE_FFN), s.x1, bias_done=fuse_bias)
                     dh1, _ = ops.linear(du, lt.ff1_wt, None, residual=dt2, want_f32=True, want_bf16=False)
                     dt, dtb = ops.layernorm_bwd(dh1, s.t, lw.ln1_w, eps, dgamma=G(base + "layer_norm.weight"),
-                                                dbeta=G(base + "layer_norm.bias"), want_bf16=True)
-                    dqkv = attn_block(i, s, lt, masked16(dt, dtb, i, self.SITE_ATTN), s.x_in)
+                                                dbeta=G(base + "layer_norm.bias"), want_bf16=True,
+                                                dcolsum=G(base + "attention.out_proj.bias") if fuse_bias else None)
+                    dqkv = attn_block(i, s, lt, masked16(dt, dtb, i, self.SITE_ATTN), s.x_in, bias_done=fuse_bias)
                     dh32, _ = ops.linear(dqkv, lt.qkv_wt, None, residual=dt, want_f32=True, want_bf16=False)
                     sv.layers[i] = None
                 if on_layer_done is not None:

@@ -79,17 +79,22 @@ colsum_kernel(const void* __restrict__ xin, long long M, int N, long long ld, in
 // the saved input exactly as the forward kernel computes them); dgamma/dbeta accumulate in registers over the rows
 // a warp visits, are combined across the block's warps in shared memory and leave as atomics.
 // `dres` (optional) is the gradient arriving over the residual connection: dx_out = dres + dx.
-template <int NV>
+// CS: also accumulate dcol[c] += sum over rows of dx_out[row][c] — the bias gradient of the Linear whose output the
+// normalised tensor's INPUT is (out-proj / FFN2 write the residual stream this LayerNorm reads), which would
+// otherwise be a colsum launch re-reading dx_out.
+template <int NV, bool CS>
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, long long rows,
                      const float* __restrict__ gamma, float eps, const float* __restrict__ dres,
                      float* __restrict__ dx_f32, __nv_bfloat16* __restrict__ dx_bf16, float* __restrict__ dgamma,
-                     float* __restrict__ dbeta) {
+                     float* __restrict__ dbeta, float* __restrict__ dcol) {
   constexpr int COLS = NV * 128;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float4 ag[NV], ab[NV];
+  float4 ag[NV], ab[NV], ac[CS ? NV : 1];
 #pragma unroll
   for (int i = 0; i < NV; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < (CS ? NV : 1); ++i) ac[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   float4 gm[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) gm[i] = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
@@ -147,7 +152,31 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
       if (dx_bf16)
         reinterpret_cast<uint2*>(dx_bf16 + row * COLS)[i * 32 + lane] =
             make_uint2(pack_bf16(o4.x, o4.y), pack_bf16(o4.z, o4.w));
+      if constexpr (CS) {
+        ac[i].x += o4.x; ac[i].y += o4.y; ac[i].z += o4.z; ac[i].w += o4.w;
+      }
     }
+  }
+  if constexpr (CS) {
+    // combine the 8 warps' column sums in shared memory, then one atomic per column and CTA
+    __shared__ float scs[COLS];
+    for (int w = 0; w < 8; ++w) {
+      if (warp == w) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          float4* pc = reinterpret_cast<float4*>(scs) + i * 32 + lane;
+          if (w == 0) {
+            *pc = ac[i];
+          } else {
+            float4 a = *pc;
+            a.x += ac[i].x; a.y += ac[i].y; a.z += ac[i].z; a.w += ac[i].w;
+            *pc = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    for (int c = threadIdx.x; c < COLS; c += 256) atomicAdd(dcol + c, scs[c]);
   }
   if (dgamma == nullptr) return;
   // combine the 8 warps' partial dgamma/dbeta: warp w adds its registers into shared memory in turn
@@ -545,27 +574,41 @@ extern "C" int aptai_colsum(const void* x, int x_bf16, int64_t M, int N, int64_t
 
 template <int NV>
 static void launch_ln_bwd(const float* dy, const float* x, long long rows, const float* gamma, float eps,
-                          const float* dres, float* dx, void* dxb, float* dg, float* db, cudaStream_t st) {
+                          const float* dres, float* dx, void* dxb, float* dg, float* db, float* dcol, cudaStream_t st) {
   long long blocks = (rows + 7) / 8;
   const long long cap = 4LL * num_sms();
   if (blocks > cap) blocks = cap;
-  layernorm_bwd_kernel<NV><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
-      dy, x, rows, gamma, eps, dres, dx, reinterpret_cast<__nv_bfloat16*>(dxb), dg, db);
+  if (dcol != nullptr)
+    layernorm_bwd_kernel<NV, true><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+        dy, x, rows, gamma, eps, dres, dx, reinterpret_cast<__nv_bfloat16*>(dxb), dg, db, dcol);
+  else
+    layernorm_bwd_kernel<NV, false><<<static_cast<unsigned>(blocks), 256, 0, st>>>(
+        dy, x, rows, gamma, eps, dres, dx, reinterpret_cast<__nv_bfloat16*>(dxb), dg, db, nullptr);
 }
+
+extern "C" int aptai_layernorm_bwd_colsum(const float* dy, const float* x, int64_t rows, int cols, const float* gamma,
+                                          float eps, const float* dres, float* dx_f32, void* dx_bf16, float* dgamma,
+                                          float* dbeta, float* dcolsum, void* stream);
 
 extern "C" int aptai_layernorm_bwd(const float* dy, const float* x, int64_t rows, int cols, const float* gamma,
                                    float eps, const float* dres, float* dx_f32, void* dx_bf16, float* dgamma,
                                    float* dbeta, void* stream) {
+  return aptai_layernorm_bwd_colsum(dy, x, rows, cols, gamma, eps, dres, dx_f32, dx_bf16, dgamma, dbeta, nullptr, stream);
+}
+
+extern "C" int aptai_layernorm_bwd_colsum(const float* dy, const float* x, int64_t rows, int cols, const float* gamma,
+                                          float eps, const float* dres, float* dx_f32, void* dx_bf16, float* dgamma,
+                                          float* dbeta, float* dcolsum, void* stream) {
   if (int rc = check_arch()) return rc;
   APTAI_REQUIRE(dy && x && gamma && (dx_f32 || dx_bf16), "layernorm_bwd: null pointer");
   APTAI_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma and dbeta come together");
   APTAI_REQUIRE(rows >= 1, "layernorm_bwd: rows");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (cols) {
-    case 256: launch_ln_bwd<2>(dy, x, rows, gamma, eps, dres, dx_f32, dx_bf16, dgamma, dbeta, st); break;
-    case 512: launch_ln_bwd<4>(dy, x, rows, gamma, eps, dres, dx_f32, dx_bf16, dgamma, dbeta, st); break;
-    case 768: launch_ln_bwd<6>(dy, x, rows, gamma, eps, dres, dx_f32, dx_bf16, dgamma, dbeta, st); break;
-    case 1024: launch_ln_bwd<8>(dy, x, rows, gamma, eps, dres, dx_f32, dx_bf16, dgamma, dbeta, st); break;
+    case 256: launch_ln_bwd<2>(dy, x, rows, gamma, eps, dres, dx_f32, dx_bf16, dgamma, dbeta, dcolsum, st); break;
+    case 512: launch_ln_bwd<4>(dy, x, rows, gamma, eps, dres, dx_f32, dx_bf16, dgamma, dbeta, dcolsum, st); break;
+    case 768: launch_ln_bwd<6>(dy, x, rows, gamma, eps, dres, dx_f32, dx_bf16, dgamma, dbeta, dcolsum, st); break;
+    case 1024: launch_ln_bwd<8>(dy, x, rows, gamma, eps, dres, dx_f32, dx_bf16, dgamma, dbeta, dcolsum, st); break;
     default:
       set_error("layernorm_bwd: unsupported width %d (256, 512, 768, 1024)", cols);
       return APTAI_ERR_ARG;

@@ -131,6 +131,8 @@ PROTOTYPES = {
     "aptai_colsum": (c_int, [c_void_p, c_int, c_i64, c_int, c_i64, c_float, c_void_p, c_void_p]),
     "aptai_layernorm_bwd": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_float, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p, c_void_p]),
+    "aptai_layernorm_bwd_colsum": (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_float, c_void_p, c_void_p,
+                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "aptai_heads_bwd": (c_int, [c_void_p, c_i64, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p,
                                 c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "aptai_masked_mse_ce_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_int, c_void_p, c_void_p,

@@ -347,6 +347,9 @@ class Serpentine:
 # 0 (default): standalone LayerNorm launches.  Measured slower (bench 23.4 k -> 18.1 k audio-s/s, profiles/
 # row_ln_bench.py): the in-kernel normalisation starves behind the operand stream; kept as a tested experiment
 FUSED_ROW_LN = int(os.environ.get("APTAI_FUSED_ROW_LN", "0"))
+# 1: out-proj / FFN2 bias gradients come out of the LayerNorm backward that produces their dy (layernorm_bwd dcolsum);
+# 0: separate colsum launches (A/B runs)
+FUSED_BIAS_COLSUM = int(os.environ.get("APTAI_FUSED_BIAS_COLSUM", "1"))
 POSCONV_SLAB = int(os.environ.get("APTAI_POSCONV_SLAB", "1"))     # 0: always the generic implicit-GEMM path (A/B runs)
 
 # 0: by shape (attention_v3.cu's query-tile pairs with P in TMEM when an utterance has more than one 128-query tile,
@@ -685,17 +688,21 @@ def colsum(x: torch.Tensor, out: torch.Tensor, scale: float = 1.0) -> None:
 
 
 def layernorm_bwd(dy: torch.Tensor, x: torch.Tensor, gamma: torch.Tensor, eps: float, *, dres=None, dgamma=None,
-                  dbeta=None, want_f32=True, want_bf16=False, out_f32=None):
-    """Returns (dx fp32 | None, dx bf16 | None); dx = dres + LN'(dy).  dgamma/dbeta accumulate."""
+                  dbeta=None, want_f32=True, want_bf16=False, out_f32=None, dcolsum=None):
+    """Returns (dx fp32 | None, dx bf16 | None); dx = dres + LN'(dy).  dgamma/dbeta accumulate; `dcolsum` (fp32
+    [cols]) accumulates the column sums of dx: the bias gradient of the Linear that wrote this LayerNorm's input."""
     _req(dy, F32, "dy"); _req(x, F32, "x"); _req(gamma, F32, "gamma")
     cols = x.shape[-1]
     rows = x.numel() // cols
     if want_f32 and out_f32 is None:
         out_f32 = torch.empty(x.shape, dtype=F32, device=x.device)
     ob = torch.empty(x.shape, dtype=BF16, device=x.device) if want_bf16 else None
-    check(_lib.load().aptai_layernorm_bwd(dy.data_ptr(), x.data_ptr(), rows, cols, gamma.data_ptr(), eps, _ptr(dres),
-                                          _ptr(out_f32), _ptr(ob), _ptr(dgamma), _ptr(dbeta), _stream()),
-          "layernorm_bwd")
+    if dcolsum is not None:
+        _req(dcolsum, F32, "dcolsum")
+        assert dcolsum.numel() == cols
+    check(_lib.load().aptai_layernorm_bwd_colsum(dy.data_ptr(), x.data_ptr(), rows, cols, gamma.data_ptr(), eps,
+                                                 _ptr(dres), _ptr(out_f32), _ptr(ob), _ptr(dgamma), _ptr(dbeta),
+                                                 _ptr(dcolsum), _stream()), "layernorm_bwd")
     return out_f32, ob
 
 

@@ -395,6 +395,12 @@ int aptai_colsum(const void* x, int x_bf16, int64_t M, int N, int64_t ld, float 
  * written fp32 and/or bf16; dgamma/dbeta (optional, both or none) are accumulated (+=). */
 int aptai_layernorm_bwd(const float* dy, const float* x, int64_t rows, int cols, const float* gamma, float eps,
                         const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta, void* stream);
+/* same, and dcolsum[c] += sum over rows of the output gradient dx[row][c] (fp32, before the 16-bit rounding): the bias
+ * gradient of the Linear that wrote the residual stream this LayerNorm reads (out-proj / FFN2), without the colsum
+ * launch that would re-read dx */
+int aptai_layernorm_bwd_colsum(const float* dy, const float* x, int64_t rows, int cols, const float* gamma, float eps,
+                               const float* dres, float* dx_f32, void* dx_bf16, float* dgamma, float* dbeta,
+                               float* dcolsum, void* stream);
 
 /* backward of aptai_heads: dh = act_a'(h) (dA Wa) + act_b'(h) (dB Wb) (optional), dW += dOut^T act(h), db += colsum */
 int aptai_heads_bwd(const float* h, int64_t rows, int H, const float* da, int na, const float* wa, int act_a,

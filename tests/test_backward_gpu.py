@@ -135,6 +135,17 @@ def test_layernorm_bwd(cuda, rows, cols):
     assert _rel(dxb, xr.grad + dres) < 4e-3
     torch.testing.assert_close(dg, gr.grad, atol=2e-3, rtol=1e-4)
     torch.testing.assert_close(db, br.grad, atol=2e-3, rtol=1e-4)
+    # fused column sums of the output gradient (the bias gradient of the Linear that wrote x): accumulate into dcolsum,
+    # same dx / dgamma / dbeta as without it
+    dc = torch.full((cols,), 0.25, device=cuda)
+    dg2, db2 = torch.zeros_like(gamma), torch.zeros_like(beta)
+    dx2, dxb2 = ops.layernorm_bwd(dy, x, gamma, 1e-5, dres=dres, dgamma=dg2, dbeta=db2, want_bf16=True, dcolsum=dc)
+    assert torch.equal(dx2, dx) and torch.equal(dxb2, dxb)
+    torch.testing.assert_close(dg2, dg, atol=2e-3, rtol=1e-4)
+    torch.testing.assert_close(dc, 0.25 + (xr.grad + dres).sum(0), atol=3e-3, rtol=1e-4)
+    dc2 = torch.zeros((cols,), device=cuda)
+    ops.layernorm_bwd(dy, x, gamma, 1e-5, want_bf16=False, dcolsum=dc2)          # no residual, no dgamma / dbeta
+    torch.testing.assert_close(dc2, xr.grad.sum(0), atol=3e-3, rtol=1e-4)
 
 
 def test_colsum(cuda):
