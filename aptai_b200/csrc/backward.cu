@@ -394,7 +394,7 @@ __global__ void posconv_wn_apply_kernel(const float* __restrict__ dwf, const flo
 // (8 channels) of both tensors per step, 8 lanes cover one head and combine with three shuffles.
 __global__ void __launch_bounds__(256)
 attn_bwd_dot_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* __restrict__ O, int B, int T,
-                    int heads, float* __restrict__ D) {
+                    int heads, float* __restrict__ D, float* __restrict__ zero_f32) {
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= static_cast<long long>(B) * T) return;
@@ -406,6 +406,11 @@ attn_bwd_dot_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* _
     const int c = c0 + lane * 8;
     float s = 0.f;
     if (c < H) {
+      if (zero_f32 != nullptr) {           // the dQ accumulator of the backward kernel that follows: cleared here
+        float4* z = reinterpret_cast<float4*>(zero_f32 + row * H + c);
+        z[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        z[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       const uint4 a = __ldg(pa + c / 8), b = __ldg(pb + c / 8);
       const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
@@ -671,14 +676,21 @@ extern "C" int aptai_posconv_weightnorm_bwd(const float* dw_folded, const float*
   return after_launch("posconv_wn_apply");
 }
 
-extern "C" int aptai_attention_bwd_dot(const void* d_ctx, const void* ctx, int B, int T, int heads, float* D,
-                                       void* stream) {
+extern "C" int aptai_attention_bwd_dot_zero(const void* d_ctx, const void* ctx, int B, int T, int heads, float* D,
+                                            float* zero_f32, void* stream) {
   if (int rc = check_arch()) return rc;
   APTAI_REQUIRE(d_ctx && ctx && D && B >= 1 && T >= 1 && heads >= 1, "attention_bwd_dot: bad arguments");
+  APTAI_REQUIRE((reinterpret_cast<uintptr_t>(zero_f32) & 15) == 0, "attention_bwd_dot: zero_f32 must be 16-byte aligned");
   const long long total = static_cast<long long>(B) * T;
   attn_bwd_dot_kernel<<<static_cast<unsigned>((total + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(d_ctx), reinterpret_cast<const __nv_bfloat16*>(ctx), B, T, heads, D);
+      reinterpret_cast<const __nv_bfloat16*>(d_ctx), reinterpret_cast<const __nv_bfloat16*>(ctx), B, T, heads, D,
+      zero_f32);
   return after_launch("attention_bwd_dot");
+}
+
+extern "C" int aptai_attention_bwd_dot(const void* d_ctx, const void* ctx, int B, int T, int heads, float* D,
+                                       void* stream) {
+  return aptai_attention_bwd_dot_zero(d_ctx, ctx, B, T, heads, D, nullptr, stream);
 }
 
 extern "C" int aptai_scale_cast_bf16(const float* x, int64_t rows, int cols, float scale, void* out_bf16,

@@ -633,9 +633,9 @@ def attention_bwd(qkv: torch.Tensor, ctx: torch.Tensor, d_ctx: torch.Tensor, lse
     dev = qkv.device
     L = _lib.load()
     dvec = torch.empty((B, heads, T), dtype=F32, device=dev)
-    check(L.aptai_attention_bwd_dot(d_ctx.data_ptr(), ctx.data_ptr(), B, T, heads, dvec.data_ptr(), _stream()),
-          "attention_bwd_dot")
-    dq32 = torch.zeros((M, H), dtype=F32, device=dev)
+    dq32 = torch.empty((M, H), dtype=F32, device=dev)      # cleared by the row-dot kernel (no memset launch)
+    check(L.aptai_attention_bwd_dot_zero(d_ctx.data_ptr(), ctx.data_ptr(), B, T, heads, dvec.data_ptr(), dq32.data_ptr(),
+                                         _stream()), "attention_bwd_dot")
     dqkv = torch.empty((M, 3 * H), dtype=BF16, device=dev)
     check(L.aptai_attention_bwd_dropout(qkv.data_ptr(), d_ctx.data_ptr(), lse.data_ptr(), dvec.data_ptr(),
                                         key_len.data_ptr(), B, T, heads, dq32.data_ptr(), dqkv.data_ptr(), float(drop_p),

@@ -327,6 +327,10 @@ int aptai_attention_fwd_lse(const void* qkv, void* ctx, float* lse, const int32_
                             void* stream);
 /* D[b][h][t] = sum_d d_ctx * ctx  (bf16 [B*T][heads*64] inputs), the softmax-backward row term */
 int aptai_attention_bwd_dot(const void* d_ctx, const void* ctx, int B, int T, int heads, float* D, void* stream);
+/* same, and zero_f32 (fp32 [B*T][heads*64], may be NULL) is cleared in the same pass: the dQ accumulator of the
+ * aptai_attention_bwd launch that follows, without a memset launch of its own */
+int aptai_attention_bwd_dot_zero(const void* d_ctx, const void* ctx, int B, int T, int heads, float* D, float* zero_f32,
+                                 void* stream);
 /* attention backward (autograd of HF:500-549).  qkv bf16 [B*T][3H] (q pre-scaled), d_ctx bf16 [B*T][H];
  * writes dk, dv into the k / v blocks of dqkv (bf16 [B*T][3H]) and ACCUMULATES dq (w.r.t. the pre-scaled q) into
  * dq32 fp32 [B*T][H], which the caller zeroes before and converts with aptai_scale_cast_bf16 afterwards. */
