@@ -131,9 +131,9 @@ class _WeightTable:
         e.dst_f32 = dst_f32.data_ptr() + 4 * f32_off if dst_f32 is not None else None
         e.rows, e.cols, e.dst_ld, e.dst_t_ld = rows, cols, dst_ld or cols, dst_t_ld or rows
         e.scale, e.scale_t = scale, scale_t
-        e.tiles_x = (cols + 31) // 32
+        e.tiles_x = (cols + 63) // 64                     # 64 x 64 tiles (aptai_prepare_weights)
         e.tile0 = self.tiles
-        self.tiles += e.tiles_x * ((rows + 31) // 32)
+        self.tiles += e.tiles_x * ((rows + 63) // 64)
         self.rows.append(e)
         self.keep.append((src, dst, dst_t, dst_f32))
 

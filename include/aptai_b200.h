@@ -419,8 +419,8 @@ int aptai_masked_mse_ce_bwd(const float* tv_pred, const float* tv_tgt, const flo
 
 /* Kernel-operand copies of the fp32 master weights in one launch (after load_state_dict / every optimizer step):
  * per table entry dst[r][c] = bf16(scale*src[r][c]) (row pitch dst_ld), dst_t[c][r] = bf16(scale_t*src[r][c]) (row
- * pitch dst_t_ld), dst_f32 = scale*src; any destination may be NULL.  tile0 = index of the entry's first 32x32
- * tile, tiles_x = ceil(cols/32); total_tiles = sum over entries.  The table lives in device memory. */
+ * pitch dst_t_ld), dst_f32 = scale*src; any destination may be NULL.  tile0 = index of the entry's first 64x64
+ * tile, tiles_x = ceil(cols/64); total_tiles = sum over entries of tiles_x * ceil(rows/64).  The table lives in device memory. */
 typedef struct aptai_prep_entry {
   const float* src;
   void* dst;

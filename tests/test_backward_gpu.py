@@ -252,3 +252,37 @@ def test_fused_adam_consumes_pending_regions(cuda):
     gb.pending = [((lambda: calls.append("w")), 0, gb.numel)]
     opt.zero_grad()
     assert calls == ["w"] and gb.pending == [] and float(gb.flat.abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("half", [0, 1])
+def test_prepare_weights_table(cuda, half):
+    """One-launch operand preparation (aptai_prepare_weights_fmt): 16-bit [N][K] copies with a scale and a row offset
+    inside a fused buffer, transposed copies with their own pitch / offset / scale, fused fp32 biases — vector path
+    (shapes and pitches multiples of 4) and scalar path (odd shapes), bf16 and fp16, bit-exact against torch."""
+    from aptai_b200.backbone import _WeightTable
+    dt = torch.float16 if half else torch.bfloat16
+    H = 192
+    wq, wk = _rand((H, H), cuda, 1.0, 1), _rand((H, H), cuda, 1.0, 2)
+    bq, bk = _rand((H,), cuda, 1.0, 3), _rand((H,), cuda, 1.0, 4)
+    w1 = _rand((320, 100), cuda, 1.0, 5)              # 100 columns: a partial 64-wide tile on the vector path
+    wodd = _rand((37, 53), cuda, 1.0, 6)              # scalar path
+    qk = torch.full((2 * H, H), 7.0, dtype=dt, device=cuda)
+    qkt = torch.full((H, 2 * H), 7.0, dtype=dt, device=cuda)
+    qkb = torch.full((2 * H,), 7.0, device=cuda)
+    w1c, w1t = torch.empty((320, 100), dtype=dt, device=cuda), torch.empty((100, 320), dtype=dt, device=cuda)
+    oddc, oddt = torch.empty((37, 53), dtype=dt, device=cuda), torch.empty((53, 37), dtype=dt, device=cuda)
+    tb = _WeightTable(cuda)
+    tb.add(wq, dst=qk, dst_off=0, dst_ld=H, scale=0.125, dst_t=qkt, dst_t_off=0, dst_t_ld=2 * H, scale_t=1.0)
+    tb.add(bq, dst_f32=qkb, f32_off=0, scale=0.125)
+    tb.add(wk, dst=qk, dst_off=H * H, dst_ld=H, dst_t=qkt, dst_t_off=H, dst_t_ld=2 * H)
+    tb.add(bk, dst_f32=qkb, f32_off=H)
+    tb.add(w1, dst=w1c, dst_t=w1t)
+    tb.add(wodd, dst=oddc, dst_t=oddt, scale=0.5, scale_t=2.0)
+    ops.prepare_weights  # noqa: B018  (the table launches it)
+    tb.run(half)
+    torch.cuda.synchronize()
+    assert torch.equal(qk, torch.cat([(wq * 0.125).to(dt), wk.to(dt)]))
+    assert torch.equal(qkt, torch.cat([wq.t().to(dt), wk.t().to(dt)], dim=1))
+    assert torch.equal(qkb, torch.cat([bq * 0.125, bk]))
+    assert torch.equal(w1c, w1.to(dt)) and torch.equal(w1t, w1.t().to(dt))
+    assert torch.equal(oddc, (wodd * 0.5).to(dt)) and torch.equal(oddt, (wodd.t() * 2.0).to(dt))
