@@ -278,7 +278,6 @@ def test_prepare_weights_table(cuda, half):
     tb.add(bk, dst_f32=qkb, f32_off=H)
     tb.add(w1, dst=w1c, dst_t=w1t)
     tb.add(wodd, dst=oddc, dst_t=oddt, scale=0.5, scale_t=2.0)
-    ops.prepare_weights  # noqa: B018  (the table launches it)
     tb.run(half)
     torch.cuda.synchronize()
     assert torch.equal(qk, torch.cat([(wq * 0.125).to(dt), wk.to(dt)]))
