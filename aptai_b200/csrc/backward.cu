@@ -46,6 +46,13 @@ colsum_kernel(const void* __restrict__ xin, long long M, int N, long long ld, in
     const char* base = reinterpret_cast<const char*>(xin) + static_cast<long long>(col) * (BF16IN ? 2 : 4);
     const long long pitch = ld * (BF16IN ? 2 : 4);
     long long r = r0 + warp;
+    for (; r + 56 < r1; r += 64) {               // eight rows of this warp in flight together (4 KB per warp)
+      uint4 u[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) u[j] = __ldg(reinterpret_cast<const uint4*>(base + (r + 8 * j) * pitch));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) add(u[j]);
+    }
     for (; r + 24 < r1; r += 32) {               // rows r, r+8, r+16, r+24 of this warp in flight together
       const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(base + r * pitch));
       const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(base + (r + 8) * pitch));
