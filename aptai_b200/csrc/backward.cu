@@ -102,12 +102,10 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
   for (int i = 0; i < NV; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int i = 0; i < (CS ? NV : 1); ++i) ac[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  float4 gm[NV];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) gm[i] = __ldg(reinterpret_cast<const float4*>(gamma) + i * 32 + lane);
+  const float4* gmp = reinterpret_cast<const float4*>(gamma);
   for (long long row = static_cast<long long>(blockIdx.x) * 8 + warp; row < rows;
        row += static_cast<long long>(gridDim.x) * 8) {
-    float4 v[NV], d[NV];
+    float4 v[NV], d[NV], rs[NV];
     const float4* xp = reinterpret_cast<const float4*>(x + row * COLS);
     const float4* dp = reinterpret_cast<const float4*>(dy + row * COLS);
 #pragma unroll
@@ -115,6 +113,10 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
       v[i] = __ldg(xp + i * 32 + lane);
       d[i] = __ldg(dp + i * 32 + lane);
     }
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      rs[i] = dres ? __ldg(reinterpret_cast<const float4*>(dres + row * COLS) + i * 32 + lane)
+                   : make_float4(0.f, 0.f, 0.f, 0.f);
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
@@ -135,7 +137,8 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
       ag[i].x = fmaf(d[i].x, v[i].x, ag[i].x); ag[i].y = fmaf(d[i].y, v[i].y, ag[i].y);
       ag[i].z = fmaf(d[i].z, v[i].z, ag[i].z); ag[i].w = fmaf(d[i].w, v[i].w, ag[i].w);
       ab[i].x += d[i].x; ab[i].y += d[i].y; ab[i].z += d[i].z; ab[i].w += d[i].w;
-      d[i].x *= gm[i].x; d[i].y *= gm[i].y; d[i].z *= gm[i].z; d[i].w *= gm[i].w;   // g = dy * gamma
+      const float4 gmi = __ldg(gmp + i * 32 + lane);
+      d[i].x *= gmi.x; d[i].y *= gmi.y; d[i].z *= gmi.z; d[i].w *= gmi.w;   // g = dy * gamma
       sg += (d[i].x + d[i].y) + (d[i].z + d[i].w);
       sgx += (d[i].x * v[i].x + d[i].y * v[i].y) + (d[i].z * v[i].z + d[i].w * v[i].w);
     }
@@ -151,10 +154,7 @@ layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, 
       o4.y = rstd * (d[i].y - mg - v[i].y * mgx);
       o4.z = rstd * (d[i].z - mg - v[i].z * mgx);
       o4.w = rstd * (d[i].w - mg - v[i].w * mgx);
-      if (dres) {
-        const float4 r4 = __ldg(reinterpret_cast<const float4*>(dres + row * COLS) + i * 32 + lane);
-        o4.x += r4.x; o4.y += r4.y; o4.z += r4.z; o4.w += r4.w;
-      }
+      o4.x += rs[i].x; o4.y += rs[i].y; o4.z += rs[i].z; o4.w += rs[i].w;
       if (dx_f32) reinterpret_cast<float4*>(dx_f32 + row * COLS)[i * 32 + lane] = o4;
       if (dx_bf16)
         reinterpret_cast<uint2*>(dx_bf16 + row * COLS)[i * 32 + lane] =

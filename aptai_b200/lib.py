@@ -9,7 +9,11 @@ import ctypes as C
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libaptai_b200.so"
+import os as _os
+
+# APTAI_LIB_ALT: another build of the same library (same-box A/B of a kernel change against the previous build;
+# profiling only — the product library is the one next to this file)
+LIB_PATH = Path(_os.environ["APTAI_LIB_ALT"]).resolve() if _os.environ.get("APTAI_LIB_ALT") else _PKG / "libaptai_b200.so"
 
 c_void_p, c_int, c_i64, c_float, c_size_t = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
 

@@ -3,10 +3,7 @@ Usage: python profiles/tail_bench.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-if os.environ.get("APTAI_LIB_ALT"):          # A/B against another build of the library (profiling only)
-    import pathlib
-    from aptai_b200 import lib as _l
-    _l.LIB_PATH = pathlib.Path(os.environ["APTAI_LIB_ALT"])
+# A/B against another build of the library: APTAI_LIB_ALT=path/to/other/libaptai_b200.so (aptai_b200/lib.py)
 from aptai_b200 import ops
 
 dev = torch.device("cuda:0")
