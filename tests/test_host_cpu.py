@@ -29,6 +29,40 @@ def test_cabi_library_loads_and_exports_every_declared_symbol():
     assert isinstance(lib.last_error(), str)
 
 
+def test_cabi_struct_layouts_match_the_ctypes_mirrors(tmp_path):
+    """The two structs that cross the C ABI by pointer (aptai_gemm_args, aptai_prep_entry): size and every field offset
+    as a C compiler sees include/aptai_b200.h == the ctypes mirrors in aptai_b200/lib.py (a drifted field would
+    silently shift every argument behind it)."""
+    import ctypes as C
+    import shutil
+    from aptai_b200 import lib
+    gcc = shutil.which("gcc") or shutil.which("cc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    mirrors = {"aptai_gemm_args": lib.GemmArgs, "aptai_prep_entry": lib.PrepEntry}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "aptai_b200.h"', 'int main(void) {']
+    for cname, cls in mirrors.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    seen = {}
+    for ln in out:
+        if ln.strip():
+            cname, fname, val = ln.split()
+            seen[(cname, fname)] = int(val)
+    for cname, cls in mirrors.items():
+        assert seen[(cname, "size")] == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert seen[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
+    assert C.sizeof(lib.PrepEntry) == 64
+
+
 def test_compute_entry_points_fail_loudly_without_gpu():
     if torch.cuda.is_available():
         pytest.skip("GPU present")
