@@ -218,3 +218,20 @@ def test_aptai_and_pr_parameter_counts_match_reference():
     pr = Wav2Vec2_PR(cfg, None, name, VOCAB)
     assert sum(p.numel() for p in pr.parameters()) == n_backbone + 1024 * 46 + 46
     assert n_backbone + 1024 * 46 + 46 + 51 == 315485921          # what Force_APTAI freezes (row a8)
+
+
+def test_precision_modes_are_validated_on_the_host():
+    """set_precision accepts the three documented modes on every drop-in module's backbone and refuses anything else
+    (no kernels run: host logic only)."""
+    from aptai_b200.backbone import Wav2Vec2Backbone
+    cfg = W2V2Config.large(num_hidden_layers=1, hidden_size=256, num_attention_heads=4, intermediate_size=512,
+                           num_conv_pos_embedding_groups=4)
+    m = Wav2Vec2Backbone(cfg)
+    assert m.precision == "bf16" and m.defers_final_ln()
+    for mode in ("fp16", "f32x3", "bf16"):
+        assert m.set_precision(mode) is m and m.precision == mode
+        assert m.defers_final_ln() == (mode in ("bf16", "fp16"))
+    for bad in ("fp8", "float16", ""):
+        with pytest.raises(ValueError):
+            m.set_precision(bad)
+    assert m.precision == "bf16"
